@@ -1,0 +1,203 @@
+"""TEST INFRASTRUCTURE — mint tests/golden/*.npz by running the UNMODIFIED reference (imported from
+/root/reference, see oracle/ref_import.py) on seeded synthetic weights/inputs (oracle/synth.py).
+
+Run in the build container only:   python -m oracle.make_golden
+The fixtures pin (a) the CPU restatements in oracle/ and (b) the product's host-side geometry.
+"""
+import sys
+import zlib
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+from oracle import ref_import, synth  # noqa: E402
+
+OUT = ROOT / "tests" / "golden"
+
+GPT_KW = dict(embd_pdrop=0., resid_pdrop=0., attn_pdrop=0., n_unmasked=0, num_cams=6, vocab_size=1024,
+              cond_vocab_size=1024, hidden_size=1024, num_embed=1024, num_heads=16, num_layers=2,
+              backend="deepspeed", sparse_block_size=16, window_len=32, cam_res=(256, 256),
+              cam_latent_res=(16, 16), plot=False, causal_order=True, camera_bias=True, image_embed=True,
+              bev_embed=True, bev_latent_res=(16, 16), density=1.0, cam_names="NUSCENES_CAMERAS", dataset="NUSCENES")
+
+GPT_SMALL = {**GPT_KW, "hidden_size": 256, "num_embed": 256, "num_heads": 4, "vocab_size": 128, "cond_vocab_size": 128}
+GPT_PADDED = {**GPT_SMALL, "cam_latent_res": (7, 9), "cam_res": (112, 144)}      # L=640 with 6 pad tokens
+
+CONFIG_CASES = {
+    "nusc6_16x16": GPT_KW,
+    "nusc6_16x16_noncausal": {**GPT_KW, "causal_order": False},
+    "nusc6_14x25": {**GPT_KW, "cam_latent_res": (14, 25), "cam_res": (224, 400)},
+    "nusc6_7x9": GPT_PADDED,
+    "nusc3_16x16": {**GPT_KW, "num_cams": 3, "cam_names": "NUSCENES_ABLATION_CAMERAS"},
+    "argo3_16x16": {**GPT_KW, "num_cams": 3, "cam_names": "ARGOVERSE_FRONT_CAMERAS", "dataset": "ARGOVERSE"},
+}
+
+
+def crc(t):
+    return np.int64(zlib.crc32(np.ascontiguousarray(t.detach().cpu().numpy()).tobytes()))
+
+
+def golden_gptconfig():
+    m = ref_import.stage2()
+    for name, kw in CONFIG_CASES.items():
+        torch.manual_seed(0)
+        cfg = m.GPTConfig(**kw)
+        layouts, allowed = cfg.get_mask()
+        L = cfg.gpt_block_size
+        rows = np.unique(np.concatenate([np.arange(0, L, 97), [0, 255, 256, 257, L - 1]])).astype(np.int64)
+        rows = rows[rows < L]
+        np.savez_compressed(
+            OUT / f"gptconfig_{name}.npz",
+            forward_shuffle_idx=cfg.forward_shuffle_idx.numpy().astype(np.int32),
+            attention_mask_bits=np.packbits(cfg.attention_mask.numpy().astype(bool)),
+            layout_bits=np.packbits(layouts.numpy().astype(bool)),
+            layout_shape=np.array(layouts.shape),
+            prob_rows=rows, prob_values=cfg.prob_matrix[rows].numpy(),
+            prob_sum=np.float64(cfg.prob_matrix.sum().item()),
+            prob_diag=torch.diagonal(cfg.prob_matrix).numpy(),
+            sizes=np.array([cfg.gpt_block_size, cfg.num_cond_tokens, cfg.num_img_tokens, cfg.num_pad_tokens]))
+        print("gptconfig", name, L)
+
+
+def golden_vq():
+    _, q = ref_import.stage1()
+    for cb in ("normal", "default"):
+        sd = synth.vqgan_state_dict(synth.vqgan_ddconfig(), seed=3, codebook=cb)
+        vq = q.VectorQuantizer2(1024, 256, beta=0.25, legacy=True).eval()
+        vq.embedding.weight.data.copy_(sd["quantize.embedding.weight"])
+        z = synth.tensor_for("vq.z", (4, 256, 8, 8), seed=5, kind="embedding")
+        if cb == "default":
+            z = z * 1e-3
+        with torch.no_grad():
+            zq, loss, (_, _, idx) = vq(z)
+            zq2 = vq.get_codebook_entry(idx, (4, 8, 8, 256))
+        assert torch.equal(zq2, sd["quantize.embedding.weight"][idx].view(4, 8, 8, 256).permute(0, 3, 1, 2))
+        np.savez_compressed(OUT / f"vq_{cb}.npz", idx=idx.numpy().astype(np.int32), zq_crc=crc(zq2), z_crc=crc(z),
+                            zq_sample=zq2[0, :, 0, 0].numpy())
+        print("vq", cb, idx[:8].tolist())
+
+
+def _ref_vqgan(dd, sd):
+    m, q = ref_import.stage1()
+    enc, dec = m.Encoder(**dd).eval(), m.Decoder(**dd).eval()
+    vq = q.VectorQuantizer2(1024, 256, beta=0.25, legacy=True).eval()
+    qc = torch.nn.Conv2d(dd["z_channels"], 256, 1)
+    pqc = torch.nn.Conv2d(256, dd["z_channels"], 1)
+    enc.load_state_dict({k[len("encoder."):]: v for k, v in sd.items() if k.startswith("encoder.")})
+    dec.load_state_dict({k[len("decoder."):]: v for k, v in sd.items() if k.startswith("decoder.")})
+    vq.embedding.weight.data.copy_(sd["quantize.embedding.weight"])
+    qc.load_state_dict({"weight": sd["quant_conv.weight"], "bias": sd["quant_conv.bias"]})
+    pqc.load_state_dict({"weight": sd["post_quant_conv.weight"], "bias": sd["post_quant_conv.bias"]})
+    return enc, dec, vq, qc, pqc
+
+
+def golden_vqgan():
+    cases = {
+        # name: (ddconfig kwargs, batch, H, W)
+        "small_rgb": (dict(in_channels=3, ch=64), 2, 64, 64),
+        "small_bev": (dict(in_channels=7, ch=64), 1, 64, 64),
+        "config1_rgb": (dict(in_channels=3, ch=128), 2, 128, 128),      # BASELINE.json configs[0]
+    }
+    for name, (kw, n, H, W) in cases.items():
+        dd = synth.vqgan_ddconfig(**kw)
+        sd = synth.vqgan_state_dict(dd, seed=1)
+        enc, dec, vq, qc, pqc = _ref_vqgan(dd, sd)
+        x = synth.image_batch(n, dd["in_channels"], H, W, seed=7)
+        with torch.no_grad():                 # VQModel.encode / decode (vqgan.py:84-121), geometric_embedding=False
+            h = qc(enc(x))
+            quant, _, (_, _, idx) = vq(h)
+            rec = dec(pqc(vq.get_codebook_entry(idx, (n, H // 16, W // 16, 256))))
+        d = torch.cdist(h.permute(0, 2, 3, 1).reshape(-1, 256), sd["quantize.embedding.weight"])
+        top2 = d.topk(2, largest=False).values
+        np.savez_compressed(OUT / f"vqgan_{name}.npz", h=h.numpy(), idx=idx.numpy().astype(np.int32), rec=rec.numpy(),
+                            x_crc=crc(x), min_gap=np.float64((top2[:, 1] - top2[:, 0]).min().item()))
+        print("vqgan", name, tuple(rec.shape), "min top-2 gap", (top2[:, 1] - top2[:, 0]).min().item())
+
+
+def _sizes(cfg):
+    return dict(num_embed=cfg.num_embed, gpt_block_size=cfg.gpt_block_size, num_img_tokens=cfg.num_img_tokens,
+                num_cond_tokens=cfg.num_cond_tokens, num_cams=cfg.num_cams, vocab_size=cfg.vocab_size,
+                cond_vocab_size=cfg.cond_vocab_size, num_layers=cfg.num_layers)
+
+
+def golden_gpt():
+    m = ref_import.stage2()
+    cases = {"small": (GPT_SMALL, 2), "padded": (GPT_PADDED, 2), "wide2": (GPT_KW, 1)}
+    for name, (kw, B) in cases.items():
+        torch.manual_seed(0)
+        cfg = m.GPTConfig(**kw)
+        model = m.GPT(cfg).eval()
+        sd = synth.gpt_state_dict(_sizes(cfg), seed=2)
+        missing, unexpected = model.load_state_dict(sd, strict=False)
+        assert not unexpected and all("master_layout" in k or k == "bev_grid" for k in missing), (missing, unexpected)
+        cam, bev, batch = synth.stage2_inputs(B, cfg.num_cams, cfg.num_cam_tokens, cfg.num_cond_tokens,
+                                              cfg.vocab_size, cfg.cond_vocab_size, seed=4)
+        hid = []
+        hooks = [blk.register_forward_hook(lambda mod, i, o: hid.append(o[0].detach())) for blk in model.blocks]
+        with torch.no_grad():
+            logits_tf = model(cam.clone(), bev, batch, sampling=False)       # teacher-forced (pads last token)
+            hid_tf = [h.clone() for h in hid]
+            hid.clear()
+            logits_s = model(cam.clone(), bev, batch, sampling=True)
+        for h in hooks:
+            h.remove()
+        n = logits_tf.shape[1]
+        rows = np.unique(np.concatenate([np.arange(0, n, 61), [0, 1, n - 2, n - 1]])).astype(np.int64)
+        np.savez_compressed(OUT / f"gpt_{name}.npz", rows=rows, logits_tf=logits_tf[:, rows].numpy(),
+                            logits_s=logits_s[:, rows].numpy(), logits_tf_mean=np.float64(logits_tf.double().mean().item()),
+                            logits_tf_absmax=np.float64(logits_tf.abs().max().item()),
+                            hidden0_rows=hid_tf[0][:, ::97].numpy(), hidden_last_rows=hid_tf[-1][:, ::97].numpy(),
+                            cam_crc=crc(cam), B=np.int64(B))
+        print("gpt", name, tuple(logits_tf.shape), float(logits_tf.abs().max()))
+        if name == "small":
+            # reference sampling loop (cond_transformer_multi_view.py:172-219), greedy, 4 steps, PAD-initialised x
+            x = torch.full((B, cfg.num_cams, cfg.num_cam_tokens), cfg.vocab_size, dtype=torch.int64)
+            rows_l, toks = [], []
+            with torch.no_grad():
+                for t in range(4):
+                    j = int(cfg.forward_shuffle_idx[t])
+                    i, k = j // cfg.num_cam_tokens, j % cfg.num_cam_tokens
+                    lg = model(x, bev, batch, sampling=True).view(B, cfg.num_cams, cfg.num_cam_tokens, -1)[:, i, k]
+                    probs = torch.softmax(lg, -1)
+                    ix = probs.topk(1, dim=-1)[1].squeeze(-1)
+                    x[:, i, k] = ix
+                    rows_l.append(lg)
+                    toks.append(ix)
+            np.savez_compressed(OUT / "gpt_small_sample4.npz", logits=torch.stack(rows_l, 1).numpy(),
+                                tokens=torch.stack(toks, 1).numpy().astype(np.int32))
+            print("gpt sample4", torch.stack(toks, 1).tolist())
+
+
+def golden_topk():
+    """Net2NetTransformer.top_k_logits (cond_transformer_multi_view.py:138-142) + softmax on fixed logits, incl. ties."""
+    g = torch.Generator().manual_seed(11)
+    logits = torch.randn(4, 1024, generator=g)
+    logits[1, :200] = logits[1, 0]                      # 200-way tie above the k-th value boundary
+    logits[2] = torch.round(logits[2] * 4) / 4          # heavy ties everywhere
+    k = 100
+    v, _ = torch.topk(logits, k)
+    out = logits.clone()
+    out[out < v[..., [-1]]] = -float("inf")
+    probs = torch.softmax(out / 1.0, -1)
+    np.savez_compressed(OUT / "topk.npz", logits=logits.numpy(), probs=probs.numpy(), k=np.int64(k),
+                        kept=(out > -float("inf")).sum(-1).numpy())
+    print("topk kept", (out > -float("inf")).sum(-1).tolist())
+
+
+if __name__ == "__main__":
+    assert ref_import.available(), "run in the build container (needs /root/reference)"
+    OUT.mkdir(parents=True, exist_ok=True)
+    which = sys.argv[1:] or ["vq", "vqgan", "topk", "gptconfig", "gpt"]
+    if "vq" in which:
+        golden_vq()
+    if "vqgan" in which:
+        golden_vqgan()
+    if "topk" in which:
+        golden_topk()
+    if "gptconfig" in which:
+        golden_gptconfig()
+    if "gpt" in which:
+        golden_gpt()

@@ -1,0 +1,53 @@
+"""Host-side geometry (decode order, mask, camera-bias prior, block layout) vs goldens minted from the
+reference's GPTConfig.__post_init__ (mingpt_sparse.py:74-102).  Integer/bool artefacts: bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from bevgen_b200.gpt_config import GPTConfig
+from tests.cases import CONFIG_CASES
+
+
+@pytest.mark.parametrize("name", list(CONFIG_CASES))
+def test_gptconfig_matches_reference(name, golden_dir):
+    g = np.load(golden_dir / f"gptconfig_{name}.npz")
+    cfg = GPTConfig(**CONFIG_CASES[name])
+    L, nc, ni, npad = g["sizes"]
+    assert (cfg.gpt_block_size, cfg.num_cond_tokens, cfg.num_img_tokens, cfg.num_pad_tokens) == (L, nc, ni, npad)
+    assert np.array_equal(cfg.forward_shuffle_idx.numpy(), g["forward_shuffle_idx"])
+    assert torch.equal(cfg.backward_shuffle_idx, torch.argsort(cfg.forward_shuffle_idx))
+    mask = np.unpackbits(g["attention_mask_bits"])[: L * L].reshape(L, L).astype(bool)
+    assert np.array_equal(cfg.attention_mask.numpy().astype(bool), mask)
+    layouts, allowed = cfg.get_mask()
+    shp = tuple(g["layout_shape"])
+    ref_layout = np.unpackbits(g["layout_bits"])[: int(np.prod(shp))].reshape(shp).astype(bool)
+    assert np.array_equal(layouts.numpy().astype(bool), ref_layout)
+    assert allowed.shape == (cfg.num_heads, L, L)
+    assert cfg.prob_matrix.dtype == torch.float64
+    np.testing.assert_allclose(cfg.prob_matrix[g["prob_rows"]].numpy(), g["prob_values"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(torch.diagonal(cfg.prob_matrix).numpy(), g["prob_diag"], rtol=0, atol=1e-12)
+    assert abs(cfg.prob_matrix.sum().item() - float(g["prob_sum"])) < 1e-6
+    assert cfg.layout_covers_mask(layouts)        # density=1.0: the block layout never removes an allowed position
+
+
+def test_mask_closed_form():
+    """allowed(i,j) = (j < n_cond) or (i >= n_cond and j <= i) — the property the KV cache rests on."""
+    cfg = GPTConfig(**CONFIG_CASES["nusc6_16x16"])
+    L, nc = cfg.gpt_block_size, cfg.num_cond_tokens
+    i, j = np.meshgrid(np.arange(L), np.arange(L), indexing="ij")
+    expect = (j < nc) | ((i >= nc) & (j <= i))
+    assert np.array_equal(cfg.attention_mask.numpy().astype(bool), expect)
+    assert abs(cfg.attention_mask.mean().item() - 0.5104) < 1e-3
+
+
+def test_first_decode_entries():
+    cfg = GPTConfig(**CONFIG_CASES["nusc6_16x16"])
+    assert cfg.forward_shuffle_idx[:8].tolist() == [7, 263, 8, 264, 6, 262, 9, 265]     # SURVEY §8 a10 probe
+
+
+def test_errors():
+    kw = dict(CONFIG_CASES["nusc6_16x16"])
+    with pytest.raises(AssertionError):
+        GPTConfig(**{**kw, "num_cams": 5})
+    with pytest.raises(NotImplementedError):
+        GPTConfig(**{**kw, "legacy_prob_matrix": False})

@@ -1,0 +1,107 @@
+"""Pins the CPU restatements in oracle/ against goldens minted from the unmodified reference."""
+import zlib
+
+import numpy as np
+import pytest
+import torch
+
+from bevgen_b200.gpt_config import GPTConfig
+from oracle import gpt_oracle, synth, vqgan_oracle
+from tests.cases import GPT_CASES, GPT_SMALL, VQGAN_CASES, gpt_sizes
+
+
+def crc(t):
+    return zlib.crc32(np.ascontiguousarray(t.detach().cpu().numpy()).tobytes())
+
+
+@pytest.mark.parametrize("cb", ["normal", "default"])
+def test_vq_oracle(cb, golden_dir):
+    g = np.load(golden_dir / f"vq_{cb}.npz")
+    sd = synth.vqgan_state_dict(synth.vqgan_ddconfig(), seed=3, codebook=cb)
+    z = synth.tensor_for("vq.z", (4, 256, 8, 8), seed=5, kind="embedding")
+    if cb == "default":
+        z = z * 1e-3
+    assert crc(z) == int(g["z_crc"]), "synthetic input drifted (torch RNG change?)"
+    zq, idx, _ = vqgan_oracle.vq_nearest(z, sd["quantize.embedding.weight"])
+    assert np.array_equal(idx.numpy(), g["idx"])
+    assert crc(zq) == int(g["zq_crc"])
+    assert crc(vqgan_oracle.get_codebook_entry(idx, (4, 8, 8, 256), sd)) == int(g["zq_crc"])
+
+
+@pytest.mark.parametrize("name", list(VQGAN_CASES))
+def test_vqgan_oracle(name, golden_dir):
+    kw, n, H, W = VQGAN_CASES[name]
+    g = np.load(golden_dir / f"vqgan_{name}.npz")
+    dd = synth.vqgan_ddconfig(**kw)
+    sd = synth.vqgan_state_dict(dd, seed=1)
+    x = synth.image_batch(n, dd["in_channels"], H, W, seed=7)
+    assert crc(x) == int(g["x_crc"])
+    with torch.no_grad():
+        quant, idx, h = vqgan_oracle.encode(x, sd)
+        rec = vqgan_oracle.decode(vqgan_oracle.get_codebook_entry(idx, (n, H // 16, W // 16, 256), sd), sd)
+    assert idx.shape == (n * (H // 16) * (W // 16),) and idx.dtype == torch.int64
+    assert rec.shape == (n, dd["out_ch"], H, W)
+    np.testing.assert_allclose(h.numpy(), g["h"], rtol=0, atol=2e-5)
+    assert np.array_equal(idx.numpy(), g["idx"])
+    np.testing.assert_allclose(rec.numpy(), g["rec"], rtol=0, atol=2e-5)
+
+
+def _gpt_case(name):
+    kw, B = GPT_CASES[name]
+    cfg = GPTConfig(**kw)
+    sd = synth.gpt_state_dict(gpt_sizes(cfg), seed=2)
+    cam, bev, batch = synth.stage2_inputs(B, cfg.num_cams, cfg.num_cam_tokens, cfg.num_cond_tokens,
+                                          cfg.vocab_size, cfg.cond_vocab_size, seed=4)
+    return cfg, sd, cam, bev, batch
+
+
+@pytest.mark.parametrize("name", ["small", "padded", "wide2"])
+def test_gpt_oracle(name, golden_dir):
+    g = np.load(golden_dir / f"gpt_{name}.npz")
+    cfg, sd, cam, bev, batch = _gpt_case(name)
+    assert crc(cam) == int(g["cam_crc"])
+    geo = gpt_oracle.geo_from_config(cfg)
+    with torch.no_grad():
+        tf, hid = gpt_oracle.forward(sd, geo, cam, bev, batch, sampling=False, return_hidden=True)
+        s = gpt_oracle.forward(sd, geo, cam, bev, batch, sampling=True)
+    rows = g["rows"]
+    np.testing.assert_allclose(tf[:, rows].numpy(), g["logits_tf"], rtol=0, atol=2e-5)
+    np.testing.assert_allclose(s[:, rows].numpy(), g["logits_s"], rtol=0, atol=2e-5)
+    np.testing.assert_allclose(hid[0][:, ::97].numpy(), g["hidden0_rows"], rtol=0, atol=2e-5)
+    np.testing.assert_allclose(hid[-1][:, ::97].numpy(), g["hidden_last_rows"], rtol=0, atol=2e-5)
+    assert abs(tf.double().mean().item() - float(g["logits_tf_mean"])) < 1e-6
+
+
+def test_sampling_loop_and_kv_cache_oracle(golden_dir):
+    """The reference's own loop (4 greedy steps) is reproduced by both the O(L^2) restatement and the KV-cache one."""
+    g = np.load(golden_dir / "gpt_small_sample4.npz")
+    cfg, sd, cam, bev, batch = _gpt_case("small")
+    geo = gpt_oracle.geo_from_config(cfg)
+    with torch.no_grad():
+        x1, rows1 = gpt_oracle.sample_reference_loop(sd, geo, bev, batch, steps=4)
+        x2, rows2 = gpt_oracle.KVCacheDecoder(sd, geo).run(bev, batch, steps=4)
+    np.testing.assert_allclose(rows1.numpy(), g["logits"], rtol=0, atol=2e-5)
+    np.testing.assert_allclose(rows2.numpy(), g["logits"], rtol=0, atol=2e-5)
+    fwd = cfg.forward_shuffle_idx[:4]
+    for x in (x1, x2):
+        assert np.array_equal(x.reshape(2, -1)[:, fwd].numpy(), g["tokens"])
+
+
+def test_kv_cache_equals_full_forward_teacher_forced():
+    """Teacher-forced replay: feeding tokens z through the KV-cache decoder gives the rows of the full forward."""
+    cfg, sd, cam, bev, batch = _gpt_case("small")
+    geo = gpt_oracle.geo_from_config(cfg)
+    steps = 40
+    forced = cam.reshape(cam.shape[0], -1)[:, cfg.forward_shuffle_idx[:steps]]
+    with torch.no_grad():
+        full = gpt_oracle.forward(sd, geo, cam, bev, batch, sampling=True)
+        _, rows = gpt_oracle.KVCacheDecoder(sd, geo).run(bev, batch, steps=steps, forced_tokens=forced)
+    want = full[:, cfg.forward_shuffle_idx[:steps]]
+    np.testing.assert_allclose(rows.numpy(), want.numpy(), rtol=0, atol=3e-5)
+
+
+def test_topk_oracle(golden_dir):
+    g = np.load(golden_dir / "topk.npz")
+    p = gpt_oracle.sample_probs(torch.from_numpy(g["logits"]), 1.0, int(g["k"]))
+    np.testing.assert_allclose(p.numpy(), g["probs"], rtol=0, atol=1e-7)
+    assert np.array_equal((p > 0).sum(-1).numpy(), g["kept"])
