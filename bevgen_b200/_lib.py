@@ -1,0 +1,100 @@
+"""ctypes binding of libbevgen_b200.so (the C ABI in include/bevgen_b200.h).
+
+There is deliberately no fallback: if the shared library is missing, or a call returns a negative status, a
+RuntimeError is raised.  `load()` works without a GPU (symbol checks); the first compute call needs a B200.
+"""
+import ctypes as C
+from pathlib import Path
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = _HERE / "libbevgen_b200.so"
+MAX_TAPS = 9
+
+GF_GELU, GF_OUT_NCHW, GF_B_MN, GF_CAUSAL_SKIP = 1, 2, 4, 8
+PREP_IDENT, PREP_UP2, PREP_S2D = 0, 1, 2
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [
+        ("a_hi", C.c_void_p), ("a_lo", C.c_void_p),
+        ("a_n", C.c_int), ("a_h", C.c_int), ("a_w", C.c_int), ("a_c", C.c_int),
+        ("b_hi", C.c_void_p), ("b_lo", C.c_void_p),
+        ("b_rows", C.c_int), ("b_cols", C.c_int),
+        ("ntaps", C.c_int),
+        ("tap_dx", C.c_int * MAX_TAPS), ("tap_dy", C.c_int * MAX_TAPS), ("tap_dn", C.c_int * MAX_TAPS),
+        ("a_n_mul", C.c_int), ("a_n_zstride", C.c_int),
+        ("k", C.c_int),
+        ("a_c_off", C.c_int), ("a_c_zstride", C.c_int),
+        ("b_k_off", C.c_int), ("b_k_zstride", C.c_int),
+        ("b_row_zstride", C.c_int), ("b_row_tapstride", C.c_int),
+        ("z_inner", C.c_int), ("z_outer", C.c_int),
+        ("tile_w", C.c_int), ("tile_h", C.c_int),
+        ("out_w", C.c_int), ("out_h", C.c_int), ("n_cols", C.c_int),
+        ("out_zo_stride", C.c_longlong), ("out_zi_stride", C.c_longlong),
+        ("ldc", C.c_int),
+        ("bias", C.c_void_p), ("residual", C.c_void_p),
+        ("out_f32", C.c_void_p), ("out_hi", C.c_void_p), ("out_lo", C.c_void_p),
+        ("flags", C.c_int),
+        ("causal_ncond", C.c_int),
+        ("bn", C.c_int),
+        ("npass", C.c_int),
+    ]
+
+
+_vp, _i, _f, _ll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
+
+# name -> (restype, argtypes); must list every symbol declared in include/bevgen_b200.h
+SIGNATURES = {
+    "bevgen_init": (_i, [_i]),
+    "bevgen_last_error": (C.c_char_p, []),
+    "bevgen_version": (_i, []),
+    "bevgen_sm_count": (_i, []),
+    "bevgen_gemm_tc": (_i, [C.POINTER(GemmArgs), _vp]),
+    "bevgen_groupnorm_stats": (_i, [_vp, _i, _i, _i, _f, _vp, _vp, _vp]),
+    "bevgen_prep_operand": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
+    "bevgen_im2col3x3": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "bevgen_transpose_f32": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "bevgen_softmax_rows": (_i, [_vp, _ll, _i, _f, _vp, _vp, _vp]),
+    "bevgen_row_sqnorm": (_i, [_vp, _i, _i, _vp, _vp]),
+    "bevgen_vq_nearest": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "bevgen_codebook_gather": (_i, [_vp, _vp, _ll, _i, _i, _vp, _vp]),
+    "bevgen_denormalize": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library and bind every declared symbol; raises if anything is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise RuntimeError(
+            f"{LIB_PATH} is missing — build it with `python -m bevgen_b200.build` (or __graft_entry__.build()). "
+            "bevgen_b200 has no CPU / eager fallback.")
+    lib = C.CDLL(str(LIB_PATH))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(status: int, what: str = ""):
+    if status != 0:
+        msg = load().bevgen_last_error().decode(errors="replace")
+        raise RuntimeError(f"bevgen_b200: {what} failed with status {status}: {msg}")
+
+
+_initialised = False
+
+
+def init():
+    """One-time device check (sm_100 only) + driver entry points. Needs a GPU."""
+    global _initialised
+    if not _initialised:
+        check(load().bevgen_init(-1), "bevgen_init")
+        _initialised = True
+    return load()

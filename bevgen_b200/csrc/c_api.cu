@@ -1,0 +1,216 @@
+// extern "C" boundary: argument validation, TMA descriptor construction, launches.  See include/bevgen_b200.h.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "../../include/bevgen_b200.h"
+#include "common.cuh"
+#include "gemm_tc.cuh"
+
+namespace bevgen {
+int gemm_tc_dispatch(const GemmParams& p, int bn, int npass, int sm_count, cudaStream_t stream);
+struct PrepParams {
+  const float* x; const float* mean_rstd; const float* gamma; const float* beta; uint16_t* hi; uint16_t* lo;
+  int N, H, W, C; int mode; int swish;
+};
+int launch_gn_stats(const float* x, double* sums, float* mean_rstd, int N, int pixels, int C, float eps, cudaStream_t st);
+int launch_prep(const PrepParams& p, int sm_count, cudaStream_t st);
+int launch_im2col3x3(const float* x, uint16_t* hi, uint16_t* lo, int N, int Cin, int H, int W, int sm_count, cudaStream_t st);
+int launch_transpose(const float* src, float* dst, int N, int R, int Cc, cudaStream_t st);
+int launch_softmax_rows(const float* s, uint16_t* hi, uint16_t* lo, long long rows, int cols, float scale, cudaStream_t st);
+int launch_gather_rows(const float* table, const long long* idx, float* out, long long rows, int D, int n_table, int sm_count, cudaStream_t st);
+int launch_denorm(const float* x, float* out, int N, int C, int P, const float* mean, const float* std_, int sm_count, cudaStream_t st);
+int launch_row_sqnorm(const float* x, float* out, int rows, int D, cudaStream_t st);
+int launch_vq_nearest(const float* z, const float* cb, const float* zz, const float* ee, long long* idx, float* zq, int rows, int n_codes,
+                      int D, cudaStream_t st);
+}  // namespace bevgen
+
+using namespace bevgen;
+
+namespace {
+thread_local char g_err[512] = "";
+int g_sm_count = 0;
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+std::mutex g_mu;
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int ensure_init() {
+  if (g_encode != nullptr && g_sm_count > 0) return BEVGEN_OK;
+  return bevgen_init(-1);
+}
+
+// bf16 tensor map with SWIZZLE_128B; dims/strides innermost first
+int make_tmap(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
+  cuuint64_t gd[5], gs[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
+  if (((uintptr_t)base & 15) != 0) return fail(BEVGEN_ERR_ARG, "tensor map base not 16B aligned");
+  for (int i = 0; i + 1 < rank; ++i)
+    if (gs[i] % 16 != 0) return fail(BEVGEN_ERR_ARG, "tensor map stride %d (%llu B) not a multiple of 16", i, (unsigned long long)gs[i]);
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(BEVGEN_ERR_DRIVER, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d)", (int)r, rank);
+  return BEVGEN_OK;
+}
+}  // namespace
+
+extern "C" {
+
+BEVGEN_API const char* bevgen_last_error(void) { return g_err; }
+BEVGEN_API int bevgen_version(void) { return 100; }
+BEVGEN_API int bevgen_sm_count(void) { return g_sm_count; }
+
+BEVGEN_API int bevgen_init(int device) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  int dev = device;
+  if (dev < 0 && cudaGetDevice(&dev) != cudaSuccess) return fail(BEVGEN_ERR_CUDA, "no CUDA device: %s", cudaGetErrorString(cudaGetLastError()));
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return fail(BEVGEN_ERR_CUDA, "cudaGetDeviceProperties failed");
+  if (prop.major != 10) return fail(BEVGEN_ERR_ARCH, "device %d is sm_%d%d; this library is built for sm_100a only", dev, prop.major, prop.minor);
+  g_sm_count = prop.multiProcessorCount;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || fn == nullptr ||
+      qres != cudaDriverEntryPointSuccess)
+    return fail(BEVGEN_ERR_DRIVER, "cuTensorMapEncodeTiled entry point unavailable");
+  g_encode = (EncodeTiledFn)fn;
+  return BEVGEN_OK;
+}
+
+BEVGEN_API int bevgen_gemm_tc(const bevgen_gemm_args* a, void* stream) {
+  if (a == nullptr) return fail(BEVGEN_ERR_ARG, "null args");
+  int rc = ensure_init();
+  if (rc) return rc;
+  const int bn = a->bn, npass = a->npass;
+  if (!(bn == 16 || bn == 64 || bn == 128)) return fail(BEVGEN_ERR_ARG, "bn must be 16, 64 or 128 (got %d)", bn);
+  if (!(npass == 1 || npass == 3)) return fail(BEVGEN_ERR_ARG, "npass must be 1 or 3 (got %d)", npass);
+  if (npass == 3 && (a->a_lo == nullptr || a->b_lo == nullptr)) return fail(BEVGEN_ERR_ARG, "npass=3 needs lo planes");
+  if (a->ntaps < 1 || a->ntaps > BEVGEN_MAX_TAPS) return fail(BEVGEN_ERR_ARG, "ntaps %d out of range", a->ntaps);
+  if (a->k <= 0 || a->k % 64 != 0) return fail(BEVGEN_ERR_ARG, "k (%d) must be a positive multiple of 64", a->k);
+  if (a->tile_w * a->tile_h != 128 || a->tile_w > 256 || a->tile_h > 256) return fail(BEVGEN_ERR_ARG, "tile %dx%d != 128 pixels", a->tile_w, a->tile_h);
+  if (a->a_c % 8 != 0 || a->b_cols % 8 != 0) return fail(BEVGEN_ERR_ARG, "channel counts must be multiples of 8");
+  if (a->z_inner < 1 || a->z_outer < 1 || a->out_w < 1 || a->out_h < 1 || a->n_cols < 1) return fail(BEVGEN_ERR_ARG, "empty problem");
+  if ((a->flags & BEVGEN_GF_B_MN) && bn < 64) return fail(BEVGEN_ERR_ARG, "MN-major B needs bn >= 64");
+  if (a->out_f32 == nullptr && a->out_hi == nullptr) return fail(BEVGEN_ERR_ARG, "no output buffer");
+  if ((a->flags & BEVGEN_GF_OUT_NCHW) && a->out_hi != nullptr) return fail(BEVGEN_ERR_ARG, "NCHW output is fp32 only");
+
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  const void* aplanes[2] = {a->a_hi, a->a_lo};
+  const void* bplanes[2] = {a->b_hi, a->b_lo};
+  for (int o = 0; o < (npass == 3 ? 2 : 1); ++o) {
+    uint64_t ad[4] = {(uint64_t)a->a_c, (uint64_t)a->a_w, (uint64_t)a->a_h, (uint64_t)a->a_n};
+    uint64_t as[3] = {(uint64_t)a->a_c * 2, (uint64_t)a->a_c * a->a_w * 2, (uint64_t)a->a_c * a->a_w * a->a_h * 2};
+    uint32_t ab[4] = {64, (uint32_t)a->tile_w, (uint32_t)a->tile_h, 1};
+    rc = make_tmap(&p.tmA[o], aplanes[o], 4, ad, as, ab);
+    if (rc) return rc;
+    uint64_t bd[2] = {(uint64_t)a->b_cols, (uint64_t)a->b_rows};
+    uint64_t bs[1] = {(uint64_t)a->b_cols * 2};
+    uint32_t bb[2] = {64, (uint32_t)((a->flags & BEVGEN_GF_B_MN) ? 64 : bn)};
+    rc = make_tmap(&p.tmB[o], bplanes[o], 2, bd, bs, bb);
+    if (rc) return rc;
+  }
+  p.ntaps = a->ntaps;
+  for (int t = 0; t < a->ntaps; ++t) { p.tap_dx[t] = a->tap_dx[t]; p.tap_dy[t] = a->tap_dy[t]; p.tap_dn[t] = a->tap_dn[t]; }
+  p.a_n_mul = a->a_n_mul; p.a_n_zstride = a->a_n_zstride;
+  p.kchunks = a->k / 64;
+  p.a_c_off = a->a_c_off; p.a_c_zstride = a->a_c_zstride;
+  p.b_k_off = a->b_k_off; p.b_k_zstride = a->b_k_zstride;
+  p.b_row_zstride = a->b_row_zstride; p.b_row_tapstride = a->b_row_tapstride;
+  p.z_inner = a->z_inner; p.z_outer = a->z_outer;
+  p.tile_w = a->tile_w; p.tile_h = a->tile_h;
+  p.tiles_w = (a->out_w + a->tile_w - 1) / a->tile_w;
+  p.tiles_h = (a->out_h + a->tile_h - 1) / a->tile_h;
+  p.out_w = a->out_w; p.out_h = a->out_h; p.n_cols = a->n_cols;
+  p.out_zo_stride = a->out_zo_stride; p.out_zi_stride = a->out_zi_stride; p.ldc = a->ldc;
+  p.bias = a->bias; p.residual = a->residual; p.out_f32 = a->out_f32;
+  p.out_hi = (uint16_t*)a->out_hi; p.out_lo = (uint16_t*)a->out_lo;
+  p.flags = a->flags; p.causal_ncond = a->causal_ncond;
+  rc = gemm_tc_dispatch(p, bn, npass, g_sm_count, (cudaStream_t)stream);
+  if (rc) return fail(rc, "gemm_tc launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+  return BEVGEN_OK;
+}
+
+#define CHECK_LAUNCH(expr, name)                                                                         \
+  do {                                                                                                   \
+    int rc_ = (expr);                                                                                    \
+    if (rc_) return fail(rc_, "%s failed (%d): %s", name, rc_, cudaGetErrorString(cudaGetLastError())); \
+    return BEVGEN_OK;                                                                                    \
+  } while (0)
+
+BEVGEN_API int bevgen_groupnorm_stats(const float* x, int n, int pixels, int c, float eps, double* ws_sums, float* mean_rstd, void* stream) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  if (!x || !ws_sums || !mean_rstd || n < 1 || pixels < 1) return fail(BEVGEN_ERR_ARG, "groupnorm_stats: bad args");
+  CHECK_LAUNCH(launch_gn_stats(x, ws_sums, mean_rstd, n, pixels, c, eps, (cudaStream_t)stream), "groupnorm_stats");
+}
+
+BEVGEN_API int bevgen_prep_operand(const float* x, int n, int h, int w, int c, const float* mean_rstd, const float* gamma, const float* beta,
+                        int swish, int mode, void* out_hi, void* out_lo, void* stream) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  if (!x || !out_hi || n < 1 || h < 1 || w < 1) return fail(BEVGEN_ERR_ARG, "prep_operand: bad args");
+  if (mean_rstd && (!gamma || !beta)) return fail(BEVGEN_ERR_ARG, "prep_operand: affine params missing");
+  if (mode < 0 || mode > 2) return fail(BEVGEN_ERR_ARG, "prep_operand: bad mode");
+  PrepParams p{x, mean_rstd, gamma, beta, (uint16_t*)out_hi, (uint16_t*)out_lo, n, h, w, c, mode, swish};
+  CHECK_LAUNCH(launch_prep(p, g_sm_count, (cudaStream_t)stream), "prep_operand");
+}
+
+BEVGEN_API int bevgen_im2col3x3(const float* x_nchw, int n, int cin, int h, int w, void* out_hi, void* out_lo, void* stream) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  if (!x_nchw || !out_hi) return fail(BEVGEN_ERR_ARG, "im2col3x3: bad args");
+  CHECK_LAUNCH(launch_im2col3x3(x_nchw, (uint16_t*)out_hi, (uint16_t*)out_lo, n, cin, h, w, g_sm_count, (cudaStream_t)stream), "im2col3x3");
+}
+
+BEVGEN_API int bevgen_transpose_f32(const float* src, float* dst, int n, int r, int c, void* stream) {
+  if (!src || !dst || n < 1 || r < 1 || c < 1) return fail(BEVGEN_ERR_ARG, "transpose: bad args");
+  CHECK_LAUNCH(launch_transpose(src, dst, n, r, c, (cudaStream_t)stream), "transpose_f32");
+}
+
+BEVGEN_API int bevgen_softmax_rows(const float* s, long long rows, int cols, float scale, void* out_hi, void* out_lo, void* stream) {
+  if (!s || !out_hi || rows < 1) return fail(BEVGEN_ERR_ARG, "softmax_rows: bad args");
+  CHECK_LAUNCH(launch_softmax_rows(s, (uint16_t*)out_hi, (uint16_t*)out_lo, rows, cols, scale, (cudaStream_t)stream), "softmax_rows");
+}
+
+BEVGEN_API int bevgen_row_sqnorm(const float* x, int rows, int dim, float* out, void* stream) {
+  if (!x || !out || rows < 1 || dim < 1) return fail(BEVGEN_ERR_ARG, "row_sqnorm: bad args");
+  CHECK_LAUNCH(launch_row_sqnorm(x, out, rows, dim, (cudaStream_t)stream), "row_sqnorm");
+}
+
+BEVGEN_API int bevgen_vq_nearest(const float* z, const float* codebook, const float* code_sqnorm, int rows, int n_codes, int dim, float* ws_zz,
+                      long long* idx, float* zq, void* stream) {
+  if (!z || !codebook || !code_sqnorm || !ws_zz || !idx || rows < 1 || n_codes < 1) return fail(BEVGEN_ERR_ARG, "vq_nearest: bad args");
+  int rc = launch_row_sqnorm(z, ws_zz, rows, dim, (cudaStream_t)stream);
+  if (rc) return fail(rc, "vq_nearest: row_sqnorm failed");
+  CHECK_LAUNCH(launch_vq_nearest(z, codebook, ws_zz, code_sqnorm, idx, zq, rows, n_codes, dim, (cudaStream_t)stream), "vq_nearest");
+}
+
+BEVGEN_API int bevgen_codebook_gather(const float* codebook, const long long* idx, long long rows, int dim, int n_codes, float* out, void* stream) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  if (!codebook || !idx || !out || rows < 1) return fail(BEVGEN_ERR_ARG, "codebook_gather: bad args");
+  CHECK_LAUNCH(launch_gather_rows(codebook, idx, out, rows, dim, n_codes, g_sm_count, (cudaStream_t)stream), "codebook_gather");
+}
+
+BEVGEN_API int bevgen_denormalize(const float* x, float* out, int n, int c, int pixels, const float* mean3, const float* std3, void* stream) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  if (!x || !out || !mean3 || !std3) return fail(BEVGEN_ERR_ARG, "denormalize: bad args");
+  CHECK_LAUNCH(launch_denorm(x, out, n, c, pixels, mean3, std3, g_sm_count, (cudaStream_t)stream), "denormalize");
+}
+
+}  // extern "C"

@@ -1,0 +1,323 @@
+// tcgen05 implicit-GEMM kernel: one persistent, warp-specialised kernel that serves
+//   * 3x3 / 1x1 convolutions over NHWC activations (taps = shifted TMA boxes, OOB zero fill = padding),
+//   * stride-2 convs (space-to-depth phase planes selected per tap) and nearest-upsampled convs,
+//   * nn.Linear layers ([M,K] x [N,K]^T) and batched, channel-sliced products (Q.K^T, P.V).
+// D[128 x BN] accumulates in TMEM (fp32, double buffered); operands are staged by TMA into SWIZZLE_128B
+// shared-memory tiles.  NPASS=3 runs the bf16x3 split product (A_hi.B_hi + A_lo.B_hi + A_hi.B_lo) that
+// reproduces fp32 results to ~1e-5; NPASS=1 is plain bf16.
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane), warp 2 = TMEM allocator,
+// warps 4-7 = epilogue (TMEM -> registers -> bias/activation/residual -> global).
+#include "common.cuh"
+#include "gemm_tc.cuh"
+
+namespace bevgen {
+
+constexpr int BM = 128;
+constexpr int BK = 64;                     // bf16 elements per k-chunk = one 128-byte swizzle row
+constexpr int A_TILE_BYTES = BM * BK * 2;  // 16 KB
+constexpr int GEMM_THREADS = 256;
+
+template <int BN, int NPASS>
+struct GemmCfg {
+  static constexpr int B_TILE_BYTES = (BN < 8 ? 8 : BN) * BK * 2;
+  static constexpr int NOPS = (NPASS == 3) ? 2 : 1;  // hi (+ lo) planes per operand
+  static constexpr int STAGE_BYTES = NOPS * (A_TILE_BYTES + B_TILE_BYTES);
+  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+};
+
+template <int BN, int NPASS>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
+  using Cfg = GemmCfg<BN, NPASS>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = (uint64_t*)(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int n_tiles_n = (p.n_cols + BN - 1) / BN;
+  const int m_tiles_per_z = p.tiles_w * p.tiles_h;
+  const int n_z = p.z_outer * p.z_inner;
+  const int total_tiles = n_z * m_tiles_per_z * n_tiles_n;
+  const int k_iters = p.ntaps * p.kchunks;
+  const bool b_mn = (p.flags & GF_B_MN) != 0;
+  const bool causal = (p.flags & GF_CAUSAL_SKIP) != 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA[0]);
+    tma_prefetch_desc(&p.tmB[0]);
+    if (NPASS == 3) {
+      tma_prefetch_desc(&p.tmA[1]);
+      tma_prefetch_desc(&p.tmB[1]);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // tile -> coordinates.  n-tile fastest so that CTAs running side by side share the same A tile in L2.
+  auto decode_tile = [&](int t, int& z, int& tw, int& th, int& nt) {
+    nt = t % n_tiles_n;
+    int r = t / n_tiles_n;
+    int mt = r % m_tiles_per_z;
+    z = r / m_tiles_per_z;
+    tw = mt % p.tiles_w;
+    th = mt / p.tiles_w;
+  };
+  // causal support of an output tile (attention scores / P.V): rows m0..m0+127 (w axis), cols n0..n0+BN-1
+  auto tile_skipped = [&](int tw, int nt) -> bool {
+    if (!causal) return false;
+    int m_last = tw * p.tile_w + BM - 1, n0 = nt * BN;
+    return (n0 >= p.causal_ncond) && (n0 > m_last);
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int z, tw, th, nt;
+        decode_tile(t, z, tw, th, nt);
+        if (tile_skipped(tw, nt)) continue;
+        const int zo = z / p.z_inner, zi = z % p.z_inner;
+        const int w0 = tw * p.tile_w, h0 = th * p.tile_h, n0 = nt * BN;
+        for (int it = 0; it < k_iters; ++it) {
+          const int tap = it / p.kchunks, kc = it % p.kchunks;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* st = smem + stage * Cfg::STAGE_BYTES;
+          mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          const int ac = p.a_c_off + zi * p.a_c_zstride + kc * BK;
+          const int an = zo * p.a_n_mul + zi * p.a_n_zstride + p.tap_dn[tap];
+#pragma unroll
+          for (int o = 0; o < Cfg::NOPS; ++o) {
+            tma_load_4d(st + o * A_TILE_BYTES, &p.tmA[o], &full_bar[stage], ac, w0 + p.tap_dx[tap], h0 + p.tap_dy[tap], an);
+            uint8_t* bdst = st + Cfg::NOPS * A_TILE_BYTES + o * Cfg::B_TILE_BYTES;
+            if (!b_mn) {
+              const int bk = p.b_k_off + zi * p.b_k_zstride + kc * BK;
+              const int brow = zo * p.b_row_zstride + tap * p.b_row_tapstride + n0;
+              tma_load_2d(bdst, &p.tmB[o], &full_bar[stage], bk, brow);
+            } else {
+              // MN-major B: global [k rows][n cols]; one (64 cols x 64 k-rows) box per 64 output columns
+              const int krow = zo * p.b_row_zstride + kc * BK;
+              const int col0 = p.b_k_off + zi * p.b_k_zstride + n0;
+#pragma unroll
+              for (int j = 0; j < (BN + 63) / 64; ++j)
+                tma_load_2d(bdst + j * (64 * BK * 2), &p.tmB[o], &full_bar[stage], col0 + j * 64, krow);
+            }
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(BM, BN < 8 ? 8 : BN, 0, b_mn ? 1 : 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int z, tw, th, nt;
+        decode_tile(t, z, tw, th, nt);
+        if (tile_skipped(tw, nt)) continue;
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int it = 0; it < k_iters; ++it) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t b_base = a_base + Cfg::NOPS * A_TILE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // K-major SW128: 8-row groups 1024 B apart (SBO), k-advance = 32 B inside the swizzle row.
+            // MN-major SW128 (B only): 8 k-rows per 1024 B (SBO), 64-column atoms 8192 B apart (LBO), k-advance = 16 rows.
+            const uint64_t a_hi = make_sdesc_sw128(a_base + k * 32, 16, 1024);
+            const uint64_t b_hi = b_mn ? make_sdesc_sw128(b_base + k * 2048, 8192, 1024)
+                                       : make_sdesc_sw128(b_base + k * 32, 16, 1024);
+            const uint32_t first = (it == 0 && k == 0) ? 0u : 1u;
+            if (NPASS == 3) {
+              const uint64_t a_lo = make_sdesc_sw128(a_base + A_TILE_BYTES + k * 32, 16, 1024);
+              const uint64_t b_lo = b_mn ? make_sdesc_sw128(b_base + Cfg::B_TILE_BYTES + k * 2048, 8192, 1024)
+                                         : make_sdesc_sw128(b_base + Cfg::B_TILE_BYTES + k * 32, 16, 1024);
+              umma_bf16(d_tmem, a_lo, b_hi, idesc, first);   // small terms first
+              umma_bf16(d_tmem, a_hi, b_lo, idesc, 1u);
+              umma_bf16(d_tmem, a_hi, b_hi, idesc, 1u);
+            } else {
+              umma_bf16(d_tmem, a_hi, b_hi, idesc, first);
+            }
+          }
+          umma_commit(&empty_bar[stage]);   // frees the smem stage once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[acc]);       // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int q = warp - 4;                 // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;          // row of the 128-row tile handled by this thread
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      int z, tw, th, nt;
+      decode_tile(t, z, tw, th, nt);
+      if (tile_skipped(tw, nt)) continue;
+      const int zo = z / p.z_inner, zi = z % p.z_inner;
+      const int n0 = nt * BN;
+      const int ow = tw * p.tile_w + (row % p.tile_w);
+      const int oh = th * p.tile_h + (row / p.tile_w);
+      const bool row_ok = (ow < p.out_w) && (oh < p.out_h);
+      const long long zoff = (long long)zo * p.out_zo_stride + (long long)zi * p.out_zi_stride;
+      const long long roff = zoff + ((long long)oh * p.out_w + ow) * p.ldc + n0;
+
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+      constexpr int CH = (BN >= 32) ? 32 : 16;
+#pragma unroll 1
+      for (int c = 0; c < BN; c += CH) {
+        float v[CH];
+        if (CH == 32) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + c, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        } else {
+          uint32_t r[16];
+          tmem_ld_32x16(taddr + c, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+        }
+        if (c + CH >= BN) {
+          // all TMEM reads of this accumulator are done: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        }
+        if (!row_ok) continue;
+        const int col0 = n0 + c;
+        const bool full = (col0 + CH <= p.n_cols) && ((p.ldc & 3) == 0) && !(p.flags & GF_OUT_NCHW);
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < CH; ++j)
+            if (col0 + j < p.n_cols) v[j] += __ldg(p.bias + col0 + j);
+        }
+        if (p.flags & GF_GELU) {
+#pragma unroll
+          for (int j = 0; j < CH; ++j) v[j] = gelu_erf(v[j]);
+        }
+        if (full) {
+          if (p.residual != nullptr) {
+            const float4* rp = reinterpret_cast<const float4*>(p.residual + roff + c);
+#pragma unroll
+            for (int j = 0; j < CH / 4; ++j) {
+              float4 rv = rp[j];
+              v[4 * j] += rv.x; v[4 * j + 1] += rv.y; v[4 * j + 2] += rv.z; v[4 * j + 3] += rv.w;
+            }
+          }
+          if (p.out_f32 != nullptr) {
+            float4* op = reinterpret_cast<float4*>(p.out_f32 + roff + c);
+#pragma unroll
+            for (int j = 0; j < CH / 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+          if (p.out_hi != nullptr) {
+            uint4* hp = reinterpret_cast<uint4*>(p.out_hi + roff + c);
+            uint4* lp = (p.out_lo != nullptr) ? reinterpret_cast<uint4*>(p.out_lo + roff + c) : nullptr;
+#pragma unroll
+            for (int j = 0; j < CH / 8; ++j) {
+              uint32_t h[4], l[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                __nv_bfloat16 h0, l0, h1, l1;
+                split_bf16(v[8 * j + 2 * e], h0, l0);
+                split_bf16(v[8 * j + 2 * e + 1], h1, l1);
+                h[e] = pack_bf16(h0, h1);
+                l[e] = pack_bf16(l0, l1);
+              }
+              hp[j] = make_uint4(h[0], h[1], h[2], h[3]);
+              if (lp != nullptr) lp[j] = make_uint4(l[0], l[1], l[2], l[3]);
+            }
+          }
+        } else {
+          // ragged / tiny-N path (e.g. conv_out with 3 or 7 channels): scalar, optionally NCHW
+#pragma unroll
+          for (int j = 0; j < CH; ++j) {
+            const int col = col0 + j;
+            if (col >= p.n_cols) continue;
+            long long o = (p.flags & GF_OUT_NCHW)
+                              ? zoff + ((long long)col * p.out_h + oh) * p.out_w + ow
+                              : roff + c + j;
+            float x = v[j];
+            if (p.residual != nullptr) x += p.residual[o];
+            if (p.out_f32 != nullptr) p.out_f32[o] = x;
+            if (p.out_hi != nullptr) {
+              __nv_bfloat16 h0, l0;
+              split_bf16(x, h0, l0);
+              p.out_hi[o] = __bfloat16_as_ushort(h0);
+              if (p.out_lo != nullptr) p.out_lo[o] = __bfloat16_as_ushort(l0);
+            }
+          }
+        }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+template <int BN, int NPASS>
+static int launch_gemm(const GemmParams& p, int total_tiles, int sm_count, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN, NPASS>;
+  auto kern = gemm_tc_kernel<BN, NPASS>;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess)
+      return BEVGEN_ERR_CUDA;
+    configured = true;
+  }
+  int grid = total_tiles < sm_count ? total_tiles : sm_count;
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(p);
+  return cudaGetLastError() == cudaSuccess ? BEVGEN_OK : BEVGEN_ERR_CUDA;
+}
+
+int gemm_tc_dispatch(const GemmParams& p, int bn, int npass, int sm_count, cudaStream_t stream) {
+  const int n_tiles_n = (p.n_cols + bn - 1) / bn;
+  const int total = p.z_outer * p.z_inner * p.tiles_w * p.tiles_h * n_tiles_n;
+  if (total <= 0) return BEVGEN_ERR_ARG;
+#define CASE(BN_, NP_) \
+  if (bn == BN_ && npass == NP_) return launch_gemm<BN_, NP_>(p, total, sm_count, stream);
+  CASE(128, 3) CASE(128, 1) CASE(64, 3) CASE(64, 1) CASE(16, 3) CASE(16, 1)
+#undef CASE
+  return BEVGEN_ERR_ARG;
+}
+
+}  // namespace bevgen

@@ -1,0 +1,42 @@
+// Descriptor of one implicit-GEMM launch (shared between host launcher and kernel).
+#pragma once
+#include <cuda.h>
+#include <stdint.h>
+
+namespace bevgen {
+
+constexpr int GEMM_MAX_TAPS = 9;
+
+enum GemmFlags : int {
+  GF_GELU = 1,        // exact-erf GELU after bias
+  GF_OUT_NCHW = 2,    // fp32 output written as [z][col][h][w] (tiny Cout: conv_out)
+  GF_B_MN = 4,        // B operand is MN-major in global memory: [k rows][n cols] (e.g. V in P.V)
+  GF_CAUSAL_SKIP = 8, // skip output tiles / k-chunks entirely outside the [cond | causal] support (attention)
+};
+
+struct GemmParams {
+  CUtensorMap tmA[2];   // hi, lo : 4D (c, w, h, n) bf16, box (64, tile_w, tile_h, 1), SWIZZLE_128B
+  CUtensorMap tmB[2];   // hi, lo : 2D, K-major: (k, row) box (64, BN); MN-major: (col, krow) box (64, 64)
+  int ntaps;
+  int tap_dx[GEMM_MAX_TAPS], tap_dy[GEMM_MAX_TAPS], tap_dn[GEMM_MAX_TAPS];
+  int a_n_mul, a_n_zstride;   // A image coordinate = z_outer*a_n_mul + z_inner*a_n_zstride + tap_dn[tap]
+  int kchunks;          // K / 64 per tap
+  int a_c_off, a_c_zstride;         // A channel coordinate = a_c_off + z_inner*a_c_zstride + kc*64
+  int b_k_off, b_k_zstride;         // B k coordinate       = b_k_off + z_inner*b_k_zstride + kc*64   (K-major)
+  int b_row_zstride, b_row_tapstride;  // B row coordinate  = z_outer*b_row_zstride + tap*b_row_tapstride + n0
+  int z_inner, z_outer;
+  int tile_w, tile_h, tiles_w, tiles_h;   // M tile = tile_h x tile_w output pixels
+  int out_w, out_h;     // valid output extent per z (rows beyond are not stored)
+  int n_cols;           // valid output columns (Cout)
+  long long out_zo_stride, out_zi_stride;   // element strides of the output per z_outer / z_inner
+  int ldc;              // elements between consecutive output rows (pixels)
+  const float* bias;    // [n_cols] or null
+  const float* residual;  // same indexing as out_f32, or null
+  float* out_f32;       // or null
+  uint16_t* out_hi;     // bf16 split outputs (same indexing), or null
+  uint16_t* out_lo;
+  int flags;
+  int causal_ncond;     // GF_CAUSAL_SKIP: columns < ncond always allowed; else col <= row
+};
+
+}  // namespace bevgen

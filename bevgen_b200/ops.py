@@ -1,0 +1,130 @@
+"""Thin torch-tensor -> C-ABI adapters.  torch is used for device memory and the current CUDA stream only;
+all arithmetic happens inside libbevgen_b200.so."""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import GF_B_MN, GF_CAUSAL_SKIP, GF_GELU, GF_OUT_NCHW, PREP_IDENT, PREP_S2D, PREP_UP2, GemmArgs  # noqa: F401
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _chk_cuda(*ts):
+    for t in ts:
+        if t is not None:
+            if not t.is_cuda:
+                raise RuntimeError("bevgen_b200 ops need CUDA tensors (there is no CPU path)")
+            if not t.is_contiguous():
+                raise RuntimeError("bevgen_b200 ops need contiguous tensors")
+
+
+def split_planes(x: torch.Tensor, npass: int = 3):
+    """fp32 tensor -> (hi, lo) bf16 planes with x ~= hi + lo (packing-time helper for weights)."""
+    hi = x.to(torch.bfloat16)
+    lo = (x - hi.float()).to(torch.bfloat16) if npass == 3 else None
+    return hi.contiguous(), (None if lo is None else lo.contiguous())
+
+
+TAPS_3X3 = [(kw - 1, kh - 1) for kh in range(3) for kw in range(3)]
+
+
+def gemm_tc(*, a_hi, a_lo, a_dims, b_hi, b_lo, k, n_cols, taps=((0, 0, 0),), a_n_mul=1, a_n_zstride=0, a_c_off=0, a_c_zstride=0,
+            b_k_off=0, b_k_zstride=0, b_row_zstride=0, b_row_tapstride=0, z_inner=1, z_outer=1, tile=(128, 1),
+            out_w, out_h=1, out_zo_stride=0, out_zi_stride=0, ldc, bias=None, residual=None, out_f32=None, out_hi=None,
+            out_lo=None, flags=0, causal_ncond=0, bn=128, npass=3):
+    lib = _lib.init()
+    _chk_cuda(a_hi, a_lo, b_hi, b_lo, bias, residual, out_f32, out_hi, out_lo)
+    g = GemmArgs()
+    g.a_hi, g.a_lo = _ptr(a_hi), _ptr(a_lo)
+    g.a_n, g.a_h, g.a_w, g.a_c = a_dims
+    g.b_hi, g.b_lo = _ptr(b_hi), _ptr(b_lo)
+    g.b_rows, g.b_cols = b_hi.shape[0], b_hi.shape[1]
+    g.ntaps = len(taps)
+    for i, t in enumerate(taps):
+        g.tap_dx[i], g.tap_dy[i] = t[0], t[1]
+        g.tap_dn[i] = t[2] if len(t) > 2 else 0
+    g.a_n_mul, g.a_n_zstride, g.k = a_n_mul, a_n_zstride, k
+    g.a_c_off, g.a_c_zstride, g.b_k_off, g.b_k_zstride = a_c_off, a_c_zstride, b_k_off, b_k_zstride
+    g.b_row_zstride, g.b_row_tapstride = b_row_zstride, b_row_tapstride
+    g.z_inner, g.z_outer = z_inner, z_outer
+    g.tile_w, g.tile_h = tile
+    g.out_w, g.out_h, g.n_cols = out_w, out_h, n_cols
+    g.out_zo_stride, g.out_zi_stride, g.ldc = out_zo_stride, out_zi_stride, ldc
+    g.bias, g.residual = _ptr(bias), _ptr(residual)
+    g.out_f32, g.out_hi, g.out_lo = _ptr(out_f32), _ptr(out_hi), _ptr(out_lo)
+    g.flags, g.causal_ncond, g.bn, g.npass = flags, causal_ncond, bn, npass
+    _lib.check(lib.bevgen_gemm_tc(C.byref(g), _stream()), "bevgen_gemm_tc")
+
+
+def groupnorm_stats(x_nhwc, ws_sums, mean_rstd, eps=1e-6):
+    lib = _lib.init()
+    _chk_cuda(x_nhwc, ws_sums, mean_rstd)
+    n, c = x_nhwc.shape[0], x_nhwc.shape[-1]
+    pixels = x_nhwc.numel() // (n * c)
+    _lib.check(lib.bevgen_groupnorm_stats(_ptr(x_nhwc), n, pixels, c, eps, _ptr(ws_sums), _ptr(mean_rstd), _stream()), "groupnorm_stats")
+
+
+def prep_operand(x_nhwc, out_hi, out_lo, mean_rstd=None, gamma=None, beta=None, swish=False, mode=PREP_IDENT):
+    lib = _lib.init()
+    _chk_cuda(x_nhwc, out_hi, out_lo, mean_rstd, gamma, beta)
+    n, h, w, c = x_nhwc.shape
+    _lib.check(lib.bevgen_prep_operand(_ptr(x_nhwc), n, h, w, c, _ptr(mean_rstd), _ptr(gamma), _ptr(beta), int(swish), mode,
+                                       _ptr(out_hi), _ptr(out_lo), _stream()), "prep_operand")
+
+
+def im2col3x3(x_nchw, out_hi, out_lo):
+    lib = _lib.init()
+    _chk_cuda(x_nchw, out_hi, out_lo)
+    n, cin, h, w = x_nchw.shape
+    _lib.check(lib.bevgen_im2col3x3(_ptr(x_nchw), n, cin, h, w, _ptr(out_hi), _ptr(out_lo), _stream()), "im2col3x3")
+
+
+def transpose_f32(src, dst, n, r, c):
+    lib = _lib.init()
+    _chk_cuda(src, dst)
+    _lib.check(lib.bevgen_transpose_f32(_ptr(src), _ptr(dst), n, r, c, _stream()), "transpose_f32")
+
+
+def softmax_rows(s, out_hi, out_lo, scale):
+    lib = _lib.init()
+    _chk_cuda(s, out_hi, out_lo)
+    cols = s.shape[-1]
+    _lib.check(lib.bevgen_softmax_rows(_ptr(s), s.numel() // cols, cols, float(scale), _ptr(out_hi), _ptr(out_lo), _stream()), "softmax_rows")
+
+
+def row_sqnorm(x, out):
+    lib = _lib.init()
+    _chk_cuda(x, out)
+    _lib.check(lib.bevgen_row_sqnorm(_ptr(x), x.shape[0], x.shape[1], _ptr(out), _stream()), "row_sqnorm")
+
+
+def vq_nearest(z, codebook, code_sqnorm, ws_zz, idx, zq=None):
+    lib = _lib.init()
+    _chk_cuda(z, codebook, code_sqnorm, ws_zz, idx, zq)
+    assert idx.dtype == torch.int64
+    _lib.check(lib.bevgen_vq_nearest(_ptr(z), _ptr(codebook), _ptr(code_sqnorm), z.shape[0], codebook.shape[0], codebook.shape[1],
+                                     _ptr(ws_zz), _ptr(idx), _ptr(zq), _stream()), "vq_nearest")
+
+
+def codebook_gather(codebook, idx, out):
+    lib = _lib.init()
+    _chk_cuda(codebook, idx, out)
+    assert idx.dtype == torch.int64
+    _lib.check(lib.bevgen_codebook_gather(_ptr(codebook), _ptr(idx), idx.numel(), codebook.shape[1], codebook.shape[0], _ptr(out),
+                                          _stream()), "codebook_gather")
+
+
+def denormalize(x_nchw, out, mean, std):
+    lib = _lib.init()
+    _chk_cuda(x_nchw, out)
+    n, c, h, w = x_nchw.shape
+    m = (C.c_float * 3)(*mean)
+    s = (C.c_float * 3)(*std)
+    _lib.check(lib.bevgen_denormalize(_ptr(x_nchw), _ptr(out), n, c, h * w, m, s, _stream()), "denormalize")

@@ -1,0 +1,112 @@
+/* bevgen_b200 — C ABI of the B200 (sm_100a) kernels behind BEVGen's two hot paths.
+ *
+ * The reference (alexanderswerdlow/BEVGen) is pure Python: its "operator API" for these paths is a set of
+ * torch.nn.Module calls (cuDNN/cuBLAS/DeepSpeed-Triton underneath).  Each entry point below names the reference
+ * call sites it replaces (paths relative to /root/reference/multi_view_generation).  Conventions:
+ *   - plain device pointers + sizes, a CUDA stream passed as void* (cudaStream_t); no allocation, no host sync;
+ *   - activations are NHWC; "bf16 planes" are the (hi, lo) split of an fp32 tensor (x ~= hi + lo), lo may be NULL
+ *     for single-pass bf16 arithmetic (npass = 1); npass = 3 is the fp32-equivalent bf16x3 product;
+ *   - every function returns 0 on success or a negative BEVGEN_ERR_* code; bevgen_last_error() has the text.
+ * INTEGRATION.md shows the ctypes binding used on the Python side.
+ */
+#ifndef BEVGEN_B200_H
+#define BEVGEN_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define BEVGEN_API __attribute__((visibility("default")))
+#else
+#define BEVGEN_API
+#endif
+
+#define BEVGEN_OK 0
+#define BEVGEN_ERR_ARG (-1)    /* bad shape / alignment / unsupported size */
+#define BEVGEN_ERR_CUDA (-2)   /* CUDA runtime error (launch failure, ...) */
+#define BEVGEN_ERR_ARCH (-3)   /* device is not sm_100 */
+#define BEVGEN_ERR_DRIVER (-4) /* driver entry point (cuTensorMapEncodeTiled) unavailable */
+
+#define BEVGEN_MAX_TAPS 9
+
+/* flags of bevgen_gemm_args.flags */
+#define BEVGEN_GF_GELU 1        /* exact-erf GELU after bias (mingpt_sparse.py:235) */
+#define BEVGEN_GF_OUT_NCHW 2    /* fp32 output stored [z][col][h][w] (tiny Cout, e.g. conv_out -> NCHW images) */
+#define BEVGEN_GF_B_MN 4        /* B operand is [k rows][n cols] in memory (V in P.V) */
+#define BEVGEN_GF_CAUSAL_SKIP 8 /* skip output tiles outside the [cond | causal] support */
+
+/* prep modes */
+#define BEVGEN_PREP_IDENT 0
+#define BEVGEN_PREP_UP2 1 /* nearest 2x upsample (model.py:49-53) folded into the operand write */
+#define BEVGEN_PREP_S2D 2 /* space-to-depth phase planes for the stride-2 asymmetric-pad conv (model.py:68-75) */
+
+/* One implicit-GEMM launch: D[z][pixel][col] = sum_tap sum_k A[z, pixel + tap offset][k] * B[tap][col][k] (+bias, act, residual).
+ * Serves torch.nn.Conv2d 3x3/1x1 (stage1/model.py:43-47,62-66,88-115,146-165,355-359,399-403,458-462,500-504; vqgan.py:72-73),
+ * nn.Linear (mingpt_sparse.py:173-175,233-238,286) and the batched attention products (model.py:178-187;
+ * sparse_self_attention.py:153,176). */
+typedef struct {
+  const void* a_hi; const void* a_lo;   /* bf16 planes, logical [a_n][a_h][a_w][a_c] */
+  int a_n, a_h, a_w, a_c;
+  const void* b_hi; const void* b_lo;   /* bf16 planes, row-major [b_rows][b_cols] */
+  int b_rows, b_cols;
+  int ntaps;
+  int tap_dx[BEVGEN_MAX_TAPS], tap_dy[BEVGEN_MAX_TAPS], tap_dn[BEVGEN_MAX_TAPS];
+  int a_n_mul, a_n_zstride;             /* A image index = z_outer*a_n_mul + z_inner*a_n_zstride + tap_dn[tap] */
+  int k;                                /* reduction length per tap, multiple of 64 */
+  int a_c_off, a_c_zstride;             /* A channel offset = a_c_off + z_inner*a_c_zstride */
+  int b_k_off, b_k_zstride;             /* B k offset (K-major) or column offset (MN-major) */
+  int b_row_zstride, b_row_tapstride;   /* B row = z_outer*b_row_zstride + tap*b_row_tapstride + col */
+  int z_inner, z_outer;
+  int tile_w, tile_h;                   /* output tile, tile_w*tile_h == 128 */
+  int out_w, out_h, n_cols;
+  long long out_zo_stride, out_zi_stride;
+  int ldc;
+  const float* bias; const float* residual;
+  float* out_f32; void* out_hi; void* out_lo;
+  int flags;
+  int causal_ncond;
+  int bn;                               /* N tile: 16, 64 or 128 */
+  int npass;                            /* 1 (bf16) or 3 (bf16x3 ~ fp32) */
+} bevgen_gemm_args;
+
+BEVGEN_API int bevgen_init(int device);                 /* selects nothing, queries: SM count, arch check, driver entry points */
+BEVGEN_API const char* bevgen_last_error(void);
+BEVGEN_API int bevgen_version(void);
+BEVGEN_API int bevgen_sm_count(void);
+
+BEVGEN_API int bevgen_gemm_tc(const bevgen_gemm_args* args, void* stream);
+
+/* torch.nn.GroupNorm(32, C, eps) statistics (stage1/model.py:34-35): fp32 NHWC x[n][pixels][c] -> mean_rstd[n][32][2].
+ * ws_sums: n*64 doubles of scratch. */
+BEVGEN_API int bevgen_groupnorm_stats(const float* x, int n, int pixels, int c, float eps, double* ws_sums, float* mean_rstd, void* stream);
+
+/* GroupNorm-apply (+ swish, model.py:29-31) + bf16 split + optional spatial remap; mean_rstd NULL = no normalisation. */
+BEVGEN_API int bevgen_prep_operand(const float* x, int n, int h, int w, int c, const float* mean_rstd, const float* gamma, const float* beta,
+                        int swish, int mode, void* out_hi, void* out_lo, void* stream);
+
+/* conv_in operand: fp32 NCHW image (cin*9 <= 64) -> [n][h][w][64] bf16 planes, k = (kh*3+kw)*cin + c (model.py:355-359). */
+BEVGEN_API int bevgen_im2col3x3(const float* x_nchw, int n, int cin, int h, int w, void* out_hi, void* out_lo, void* stream);
+
+/* fp32 [n][r][c] -> [n][c][r] */
+BEVGEN_API int bevgen_transpose_f32(const float* src, float* dst, int n, int r, int c, void* stream);
+
+/* softmax(scale * s) per row of fp32 [rows][cols] -> bf16 planes (model.py:179-180) */
+BEVGEN_API int bevgen_softmax_rows(const float* s, long long rows, int cols, float scale, void* out_hi, void* out_lo, void* stream);
+
+/* VectorQuantizer2.forward (stage1/quantize.py:276-285): idx[r] = argmin_j |z_r|^2 + |e_j|^2 - 2 z_r.e_j ; zq = e[idx] (optional).
+ * code_sqnorm[n_codes] from bevgen_row_sqnorm(codebook); ws_zz: rows floats of scratch. */
+BEVGEN_API int bevgen_row_sqnorm(const float* x, int rows, int dim, float* out, void* stream);
+BEVGEN_API int bevgen_vq_nearest(const float* z, const float* codebook, const float* code_sqnorm, int rows, int n_codes, int dim, float* ws_zz,
+                      long long* idx, float* zq, void* stream);
+
+/* VectorQuantizer2.get_codebook_entry (quantize.py:314-329), NHWC result: out[r][:] = codebook[idx[r]][:] */
+BEVGEN_API int bevgen_codebook_gather(const float* codebook, const long long* idx, long long rows, int dim, int n_codes, float* out, void* stream);
+
+/* bev_utils/util.py:97-118 denormalize_tensor(keep_tensor=True) on fp32 NCHW, 3 channels */
+BEVGEN_API int bevgen_denormalize(const float* x, float* out, int n, int c, int pixels, const float* mean3, const float* std3, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

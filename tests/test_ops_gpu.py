@@ -1,0 +1,267 @@
+"""GPU parity of the individual kernels (through the C ABI) against plain fp32/fp64 torch references."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from bevgen_b200 import ops  # noqa: E402
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def _split(x):
+    hi = x.to(torch.bfloat16)
+    lo = (x - hi.float()).to(torch.bfloat16)
+    return hi.contiguous(), lo.contiguous()
+
+
+def _ref_planes(hi, lo, npass):
+    return (hi.double() + lo.double()) if npass == 3 else hi.double()
+
+
+@pytest.mark.parametrize("npass", [3, 1])
+@pytest.mark.parametrize("bn", [128, 64, 16])
+@pytest.mark.parametrize("M,N,K", [(256, 128, 64), (1000, 200, 320), (128, 3, 128)])
+def test_linear(M, N, K, bn, npass):
+    g = torch.Generator().manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g).to(dev())
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(dev())
+    bias = torch.randn(N, generator=g).to(dev())
+    res = torch.randn(M, N, generator=g).to(dev())
+    a_hi, a_lo = _split(a)
+    rows_pad = max(bn, ((N + 15) // 16) * 16)
+    wp = torch.zeros(rows_pad, K, device=dev())
+    wp[:N] = w
+    w_hi, w_lo = _split(wp)
+    out = torch.full((M, N), float("nan"), device=dev())
+    ops.gemm_tc(a_hi=a_hi, a_lo=a_lo, a_dims=(1, 1, M, K), b_hi=w_hi, b_lo=w_lo, k=K, n_cols=N, out_w=M, ldc=N,
+                bias=bias, residual=res, out_f32=out, bn=bn, npass=npass)
+    torch.cuda.synchronize()
+    if npass == 3:
+        ref = a.double() @ w.double().t() + bias.double() + res.double()
+        tol = 2e-5 * K ** 0.5
+    else:
+        ref = a_hi.double() @ w_hi[:N].double().t() + bias.double() + res.double()
+        tol = 1e-5 * K ** 0.5
+    err = (out.double() - ref).abs().max().item()
+    assert torch.isfinite(out).all()
+    assert err < tol, f"max err {err}"
+
+
+@pytest.mark.parametrize("npass", [3, 1])
+def test_linear_split_out_gelu(npass):
+    M, N, K = 384, 256, 128
+    g = torch.Generator().manual_seed(5)
+    a = torch.randn(M, K, generator=g).to(dev())
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(dev())
+    bias = torch.randn(N, generator=g).to(dev())
+    a_hi, a_lo = _split(a)
+    w_hi, w_lo = _split(w)
+    o_hi = torch.zeros(M, N, dtype=torch.bfloat16, device=dev())
+    o_lo = torch.zeros(M, N, dtype=torch.bfloat16, device=dev())
+    ops.gemm_tc(a_hi=a_hi, a_lo=a_lo, a_dims=(1, 1, M, K), b_hi=w_hi, b_lo=w_lo, k=K, n_cols=N, out_w=M, ldc=N, bias=bias,
+                out_hi=o_hi, out_lo=o_lo, flags=ops.GF_GELU, bn=128, npass=npass)
+    torch.cuda.synchronize()
+    ref = F.gelu(_ref_planes(a_hi, a_lo, npass) @ _ref_planes(w_hi, w_lo, npass).t() + bias.double())
+    got = o_hi.double() + o_lo.double()
+    assert (got - ref).abs().max().item() < 5e-5
+
+
+@pytest.mark.parametrize("npass", [3, 1])
+@pytest.mark.parametrize("N_,H,W,Cin,Cout,bn", [(2, 16, 16, 64, 128, 128), (1, 32, 32, 128, 64, 64), (3, 8, 8, 128, 3, 16),
+                                                 (2, 4, 4, 64, 64, 64), (1, 24, 40, 64, 192, 128)])
+def test_conv3x3(N_, H, W, Cin, Cout, bn, npass):
+    g = torch.Generator().manual_seed(H * W + Cin)
+    x = torch.randn(N_, Cin, H, W, generator=g).to(dev())
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / (9 * Cin) ** 0.5).to(dev())
+    b = torch.randn(Cout, generator=g).to(dev())
+    x_nhwc = x.permute(0, 2, 3, 1).contiguous()
+    a_hi, a_lo = _split(x_nhwc)
+    rows = 9 * Cout
+    rows_pad = max(rows, 8 * Cout + bn)
+    wp = torch.zeros(rows_pad, Cin, device=dev())
+    wp[:rows] = w.permute(2, 3, 0, 1).reshape(rows, Cin)      # [tap=(kh,kw)][cout][cin]
+    w_hi, w_lo = _split(wp)
+    nchw = Cout < 8
+    out = torch.full((N_, Cout, H, W) if nchw else (N_, H, W, Cout), float("nan"), device=dev())
+    tw = 16 if W >= 16 else 8
+    ops.gemm_tc(a_hi=a_hi, a_lo=a_lo, a_dims=(N_, H, W, Cin), b_hi=w_hi, b_lo=w_lo, k=Cin, n_cols=Cout,
+                taps=[(dx, dy, 0) for dx, dy in ops.TAPS_3X3], b_row_tapstride=Cout, z_outer=N_, tile=(tw, 128 // tw),
+                out_w=W, out_h=H, out_zo_stride=H * W * Cout, ldc=Cout, bias=b, out_f32=out,
+                flags=ops.GF_OUT_NCHW if nchw else 0, bn=bn, npass=npass)
+    torch.cuda.synchronize()
+    xin = _ref_planes(a_hi, a_lo, npass).permute(0, 3, 1, 2)
+    win = _ref_planes(w_hi, w_lo, npass)[:rows].reshape(3, 3, Cout, Cin).permute(2, 3, 0, 1)
+    ref = F.conv2d(xin, win, b.double(), padding=1)
+    got = out.double() if nchw else out.double().permute(0, 3, 1, 2)
+    assert torch.isfinite(out).all()
+    err = (got - ref).abs().max().item()
+    assert err < (3e-5 if npass == 3 else 1e-5) * 10, f"max err {err}"
+
+
+def test_conv_stride2_space_to_depth():
+    """Downsample (model.py:68-75): pad (0,1,0,1) + 3x3 stride 2 == 9 taps over 4 phase planes."""
+    N_, H, W, Cc = 2, 16, 16, 64
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(N_, Cc, H, W, generator=g).to(dev())
+    w = (torch.randn(Cc, Cc, 3, 3, generator=g) / (9 * Cc) ** 0.5).to(dev())
+    b = torch.randn(Cc, generator=g).to(dev())
+    x_nhwc = x.permute(0, 2, 3, 1).contiguous()
+    hi = torch.empty(N_ * 4, H // 2, W // 2, Cc, dtype=torch.bfloat16, device=dev())
+    lo = torch.empty_like(hi)
+    ops.prep_operand(x_nhwc, hi, lo, mode=ops.PREP_S2D)
+    wp = torch.zeros(9 * Cc + 64, Cc, device=dev())
+    wp[:9 * Cc] = w.permute(2, 3, 0, 1).reshape(9 * Cc, Cc)
+    w_hi, w_lo = _split(wp)
+    out = torch.full((N_, H // 2, W // 2, Cc), float("nan"), device=dev())
+    taps = [(kw // 2, kh // 2, (kh & 1) * 2 + (kw & 1)) for kh in range(3) for kw in range(3)]
+    ops.gemm_tc(a_hi=hi, a_lo=lo, a_dims=(N_ * 4, H // 2, W // 2, Cc), b_hi=w_hi, b_lo=w_lo, k=Cc, n_cols=Cc, taps=taps, a_n_mul=4,
+                b_row_tapstride=Cc, z_outer=N_, tile=(8, 16), out_w=W // 2, out_h=H // 2, out_zo_stride=(H // 2) * (W // 2) * Cc,
+                ldc=Cc, bias=b, out_f32=out, bn=64, npass=3)
+    torch.cuda.synchronize()
+    ref = F.conv2d(F.pad(x.double(), (0, 1, 0, 1)), w.double(), b.double(), stride=2)
+    err = (out.double().permute(0, 3, 1, 2) - ref).abs().max().item()
+    assert err < 1e-4, f"max err {err}"
+
+
+def test_batched_qk_and_pv_mn_major():
+    """S = Q K^T per (batch, head) from a fused qkv buffer, then O = P V with V read MN-major (no transpose)."""
+    B, Hh, L, dh = 2, 4, 256, 64
+    d = Hh * dh
+    g = torch.Generator().manual_seed(3)
+    qkv = torch.randn(B, L, 3 * d, generator=g).to(dev())
+    q_hi, q_lo = _split(qkv)
+    S = torch.full((B, Hh, L, L), float("nan"), device=dev())
+    q2h, q2l = q_hi.view(B * L, 3 * d), q_lo.view(B * L, 3 * d)
+    ops.gemm_tc(a_hi=q_hi, a_lo=q_lo, a_dims=(B, 1, L, 3 * d), b_hi=q2h, b_lo=q2l, k=dh, n_cols=L, a_c_off=0, a_c_zstride=dh,
+                b_k_off=d, b_k_zstride=dh, b_row_zstride=L, z_inner=Hh, z_outer=B, out_w=L, out_zo_stride=Hh * L * L,
+                out_zi_stride=L * L, ldc=L, out_f32=S, bn=128, npass=3)
+    torch.cuda.synchronize()
+    qd = qkv.double().view(B, L, 3, Hh, dh)
+    ref_S = torch.einsum("blhd,bmhd->bhlm", qd[:, :, 0], qd[:, :, 1])
+    err = (S.double() - ref_S).abs().max().item()
+    assert err < 2e-4, f"QK^T max err {err}"
+    P = torch.softmax(ref_S / 8, -1).float()
+    p_hi, p_lo = _split(P)
+    O = torch.full((B, L, d), float("nan"), device=dev())
+    ops.gemm_tc(a_hi=p_hi, a_lo=p_lo, a_dims=(B * Hh, 1, L, L), b_hi=q2h, b_lo=q2l, k=L, n_cols=dh, a_n_mul=Hh, a_n_zstride=1,
+                b_k_off=2 * d, b_k_zstride=dh, b_row_zstride=L, z_inner=Hh, z_outer=B, out_w=L, out_zo_stride=L * d,
+                out_zi_stride=dh, ldc=d, out_f32=O, flags=ops.GF_B_MN, bn=64, npass=3)
+    torch.cuda.synchronize()
+    ref_O = torch.einsum("bhlm,bmhd->blhd", P.double(), qd[:, :, 2]).reshape(B, L, d)
+    err = (O.double() - ref_O).abs().max().item()
+    assert err < 2e-5, f"PV max err {err}"
+
+
+@pytest.mark.parametrize("C_", [64, 128, 256, 512])
+def test_groupnorm_prep(C_):
+    N_, H, W = 3, 16, 8
+    g = torch.Generator().manual_seed(C_)
+    x = (torch.randn(N_, C_, H, W, generator=g) * 2 + 0.5).to(dev())
+    gamma = torch.randn(C_, generator=g).to(dev())
+    beta = torch.randn(C_, generator=g).to(dev())
+    x_nhwc = x.permute(0, 2, 3, 1).contiguous()
+    ws = torch.empty(N_ * 64, dtype=torch.float64, device=dev())
+    mr = torch.empty(N_ * 64, dtype=torch.float32, device=dev())
+    ops.groupnorm_stats(x_nhwc, ws, mr, 1e-6)
+    for swish, mode in [(True, ops.PREP_IDENT), (False, ops.PREP_IDENT), (True, ops.PREP_UP2)]:
+        oh, ow = (2 * H, 2 * W) if mode == ops.PREP_UP2 else (H, W)
+        hi = torch.empty(N_, oh, ow, C_, dtype=torch.bfloat16, device=dev())
+        lo = torch.empty_like(hi)
+        ops.prep_operand(x_nhwc, hi, lo, mr, gamma, beta, swish=swish, mode=mode)
+        torch.cuda.synchronize()
+        ref = F.group_norm(x.double(), 32, gamma.double(), beta.double(), eps=1e-6)
+        if swish:
+            ref = ref * torch.sigmoid(ref)
+        if mode == ops.PREP_UP2:
+            ref = F.interpolate(ref, scale_factor=2.0, mode="nearest")
+        got = (hi.double() + lo.double()).permute(0, 3, 1, 2)
+        err = ((got - ref).abs() / (1 + ref.abs())).max().item()
+        assert err < 2e-5, f"C={C_} swish={swish} mode={mode}: {err}"
+
+
+@pytest.mark.parametrize("cin", [3, 7])
+def test_im2col(cin):
+    N_, H, W = 2, 12, 20
+    g = torch.Generator().manual_seed(cin)
+    x = torch.randn(N_, cin, H, W, generator=g).to(dev())
+    hi = torch.empty(N_, H, W, 64, dtype=torch.bfloat16, device=dev())
+    lo = torch.empty_like(hi)
+    ops.im2col3x3(x, hi, lo)
+    torch.cuda.synchronize()
+    cols = F.unfold(x, 3, padding=1).view(N_, cin, 9, H, W).permute(0, 3, 4, 2, 1).reshape(N_, H, W, 9 * cin)
+    got = hi.float() + lo.float()
+    assert (got[..., :9 * cin] - cols).abs().max().item() < 1e-4
+    assert (got[..., 9 * cin:] == 0).all()
+
+
+@pytest.mark.parametrize("cb", ["normal", "default"])
+def test_vq_nearest_golden(cb, golden_dir):
+    """Bit-exact indices vs the reference's VectorQuantizer2 on the committed golden (separated + default codebooks)."""
+    from oracle import synth
+    gold = np.load(golden_dir / f"vq_{cb}.npz")
+    sd = synth.vqgan_state_dict(synth.vqgan_ddconfig(), seed=3, codebook=cb)
+    z = synth.tensor_for("vq.z", (4, 256, 8, 8), seed=5, kind="embedding")
+    if cb == "default":
+        z = z * 1e-3
+    book = sd["quantize.embedding.weight"].to(dev())
+    zf = z.permute(0, 2, 3, 1).reshape(-1, 256).contiguous().to(dev())
+    ee = torch.empty(1024, device=dev())
+    ops.row_sqnorm(book, ee)
+    idx = torch.empty(zf.shape[0], dtype=torch.int64, device=dev())
+    zq = torch.empty_like(zf)
+    ws = torch.empty(zf.shape[0], device=dev())
+    ops.vq_nearest(zf, book, ee, ws, idx, zq)
+    torch.cuda.synchronize()
+    if cb == "normal":
+        assert np.array_equal(idx.cpu().numpy(), gold["idx"])
+    else:
+        # degenerate near-tie codebook: the chosen code must be within a few ulps of the true minimum
+        d = torch.cdist(zf.double(), book.double()) ** 2
+        chosen = d.gather(1, idx[:, None])[:, 0]
+        assert ((chosen - d.min(1).values) <= 1e-9 + 4e-7 * (zf.double() ** 2).sum(1)).all()
+        assert (idx.cpu().numpy() == gold["idx"]).mean() > 0.95
+    assert torch.equal(zq, book[idx])
+
+
+def test_vq_large_and_ragged():
+    g = torch.Generator().manual_seed(0)
+    for rows in (1, 63, 24576):
+        z = torch.randn(rows, 256, generator=g).to(dev())
+        book = torch.randn(1024, 256, generator=g).to(dev())
+        ee = torch.empty(1024, device=dev())
+        ops.row_sqnorm(book, ee)
+        idx = torch.empty(rows, dtype=torch.int64, device=dev())
+        ws = torch.empty(rows, device=dev())
+        ops.vq_nearest(z, book, ee, ws, idx, None)
+        ref = torch.cdist(z.double(), book.double()).argmin(1)
+        assert torch.equal(idx, ref)
+
+
+def test_softmax_transpose_gather_denorm():
+    g = torch.Generator().manual_seed(1)
+    s = torch.randn(700, 256, generator=g).to(dev()) * 5
+    hi = torch.empty(700, 256, dtype=torch.bfloat16, device=dev())
+    lo = torch.empty_like(hi)
+    ops.softmax_rows(s, hi, lo, 0.125)
+    ref = torch.softmax(s.double() * 0.125, -1)
+    assert ((hi.double() + lo.double()) - ref).abs().max().item() < 1e-6
+    src = torch.randn(3, 50, 70, generator=g).to(dev())
+    dst = torch.empty(3, 70, 50, device=dev())
+    ops.transpose_f32(src, dst, 3, 50, 70)
+    assert torch.equal(dst, src.transpose(1, 2).contiguous())
+    book = torch.randn(1024, 256, generator=g).to(dev())
+    idx = torch.randint(0, 1024, (513,), generator=g).to(dev())
+    out = torch.empty(513, 256, device=dev())
+    ops.codebook_gather(book, idx, out)
+    assert torch.equal(out, book[idx])
+    x = torch.randn(2, 3, 8, 8, generator=g).to(dev()) * 3
+    o = torch.empty_like(x)
+    mean, std = [0.4265, 0.4489, 0.4769], [0.2053, 0.2206, 0.2578]
+    ops.denormalize(x, o, mean, std)
+    ref = torch.clamp(x * torch.tensor(std, device=dev()).view(1, 3, 1, 1) + torch.tensor(mean, device=dev()).view(1, 3, 1, 1), 0, 1)
+    assert (o - ref).abs().max().item() < 1e-6
