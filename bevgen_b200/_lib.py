@@ -54,7 +54,7 @@ SIGNATURES = {
     "bevgen_prep_operand": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "bevgen_im2col3x3": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "bevgen_transpose_f32": (_i, [_vp, _vp, _i, _i, _i, _vp]),
-    "bevgen_softmax_rows": (_i, [_vp, _ll, _i, _f, _vp, _vp, _vp]),
+    "bevgen_softmax_rows": (_i, [_vp, _ll, _i, _f, _vp, _vp, _i, _vp]),
     "bevgen_row_sqnorm": (_i, [_vp, _i, _i, _vp, _vp]),
     "bevgen_vq_nearest": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "bevgen_codebook_gather": (_i, [_vp, _vp, _ll, _i, _i, _vp, _vp]),

@@ -18,7 +18,7 @@ int launch_gn_stats(const float* x, double* sums, float* mean_rstd, int N, int p
 int launch_prep(const PrepParams& p, int sm_count, cudaStream_t st);
 int launch_im2col3x3(const float* x, uint16_t* hi, uint16_t* lo, int N, int Cin, int H, int W, int sm_count, cudaStream_t st);
 int launch_transpose(const float* src, float* dst, int N, int R, int Cc, cudaStream_t st);
-int launch_softmax_rows(const float* s, uint16_t* hi, uint16_t* lo, long long rows, int cols, float scale, cudaStream_t st);
+int launch_softmax_rows(const float* s, uint16_t* hi, uint16_t* lo, long long rows, int cols, int out_ld, float scale, cudaStream_t st);
 int launch_gather_rows(const float* table, const long long* idx, float* out, long long rows, int D, int n_table, int sm_count, cudaStream_t st);
 int launch_denorm(const float* x, float* out, int N, int C, int P, const float* mean, const float* std_, int sm_count, cudaStream_t st);
 int launch_row_sqnorm(const float* x, float* out, int rows, int D, cudaStream_t st);
@@ -181,9 +181,9 @@ BEVGEN_API int bevgen_transpose_f32(const float* src, float* dst, int n, int r, 
   CHECK_LAUNCH(launch_transpose(src, dst, n, r, c, (cudaStream_t)stream), "transpose_f32");
 }
 
-BEVGEN_API int bevgen_softmax_rows(const float* s, long long rows, int cols, float scale, void* out_hi, void* out_lo, void* stream) {
-  if (!s || !out_hi || rows < 1) return fail(BEVGEN_ERR_ARG, "softmax_rows: bad args");
-  CHECK_LAUNCH(launch_softmax_rows(s, (uint16_t*)out_hi, (uint16_t*)out_lo, rows, cols, scale, (cudaStream_t)stream), "softmax_rows");
+BEVGEN_API int bevgen_softmax_rows(const float* s, long long rows, int cols, float scale, void* out_hi, void* out_lo, int out_ld, void* stream) {
+  if (!s || !out_hi || rows < 1 || out_ld < cols) return fail(BEVGEN_ERR_ARG, "softmax_rows: bad args");
+  CHECK_LAUNCH(launch_softmax_rows(s, (uint16_t*)out_hi, (uint16_t*)out_lo, rows, cols, out_ld, scale, (cudaStream_t)stream), "softmax_rows");
 }
 
 BEVGEN_API int bevgen_row_sqnorm(const float* x, int rows, int dim, float* out, void* stream) {

@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict_
 // one warp per row
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ s, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo,
-                                                           long long rows, int cols, float scale) {
+                                                           long long rows, int cols, int out_ld, float scale) {
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -223,8 +223,8 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restri
       if (c < cols) {
         __nv_bfloat16 h0, l0;
         split_bf16(v[j] * inv, h0, l0);
-        hi[row * cols + c] = __bfloat16_as_ushort(h0);
-        if (lo != nullptr) lo[row * cols + c] = __bfloat16_as_ushort(l0);
+        hi[row * out_ld + c] = __bfloat16_as_ushort(h0);
+        if (lo != nullptr) lo[row * out_ld + c] = __bfloat16_as_ushort(l0);
       }
     }
   }
@@ -297,9 +297,9 @@ int launch_transpose(const float* src, float* dst, int N, int R, int Cc, cudaStr
   return cudaGetLastError() == cudaSuccess ? BEVGEN_OK : BEVGEN_ERR_CUDA;
 }
 
-int launch_softmax_rows(const float* s, uint16_t* hi, uint16_t* lo, long long rows, int cols, float scale, cudaStream_t st) {
+int launch_softmax_rows(const float* s, uint16_t* hi, uint16_t* lo, long long rows, int cols, int out_ld, float scale, cudaStream_t st) {
   if (cols > 1024 || cols < 1) return BEVGEN_ERR_ARG;
-  softmax_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(s, hi, lo, rows, cols, scale);
+  softmax_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(s, hi, lo, rows, cols, out_ld, scale);
   return cudaGetLastError() == cudaSuccess ? BEVGEN_OK : BEVGEN_ERR_CUDA;
 }
 

@@ -92,11 +92,12 @@ def transpose_f32(src, dst, n, r, c):
     _lib.check(lib.bevgen_transpose_f32(_ptr(src), _ptr(dst), n, r, c, _stream()), "transpose_f32")
 
 
-def softmax_rows(s, out_hi, out_lo, scale):
+def softmax_rows(s, out_hi, out_lo, scale, out_ld=None):
     lib = _lib.init()
     _chk_cuda(s, out_hi, out_lo)
     cols = s.shape[-1]
-    _lib.check(lib.bevgen_softmax_rows(_ptr(s), s.numel() // cols, cols, float(scale), _ptr(out_hi), _ptr(out_lo), _stream()), "softmax_rows")
+    _lib.check(lib.bevgen_softmax_rows(_ptr(s), s.numel() // cols, cols, float(scale), _ptr(out_hi), _ptr(out_lo),
+                                       cols if out_ld is None else out_ld, _stream()), "softmax_rows")
 
 
 def row_sqnorm(x, out):

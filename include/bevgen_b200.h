@@ -91,8 +91,8 @@ BEVGEN_API int bevgen_im2col3x3(const float* x_nchw, int n, int cin, int h, int 
 /* fp32 [n][r][c] -> [n][c][r] */
 BEVGEN_API int bevgen_transpose_f32(const float* src, float* dst, int n, int r, int c, void* stream);
 
-/* softmax(scale * s) per row of fp32 [rows][cols] -> bf16 planes (model.py:179-180) */
-BEVGEN_API int bevgen_softmax_rows(const float* s, long long rows, int cols, float scale, void* out_hi, void* out_lo, void* stream);
+/* softmax(scale * s) per row of fp32 [rows][cols] -> bf16 planes with row pitch out_ld >= cols (model.py:179-180) */
+BEVGEN_API int bevgen_softmax_rows(const float* s, long long rows, int cols, float scale, void* out_hi, void* out_lo, int out_ld, void* stream);
 
 /* VectorQuantizer2.forward (stage1/quantize.py:276-285): idx[r] = argmin_j |z_r|^2 + |e_j|^2 - 2 z_r.e_j ; zq = e[idx] (optional).
  * code_sqnorm[n_codes] from bevgen_row_sqnorm(codebook); ws_zz: rows floats of scratch. */

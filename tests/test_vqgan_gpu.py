@@ -1,0 +1,75 @@
+"""GPU parity of the stage-1 VQGAN engine vs goldens minted from the unmodified reference (tests/golden/vqgan_*.npz)
+and vs the CPU oracle.  Tolerance: north_star's 1e-3 on pixels / latents (fp32x3 mode); token indices bit-exact wherever
+the reference's own top-2 distance gap exceeds the fp noise floor."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from bevgen_b200.vqgan_engine import VQGANEngine  # noqa: E402
+from oracle import synth, vqgan_oracle  # noqa: E402
+from tests.cases import VQGAN_CASES  # noqa: E402
+
+PIXEL_TOL = 1e-3
+
+
+def _engine(name, precision="fp32x3"):
+    kw, n, H, W = VQGAN_CASES[name]
+    dd = synth.vqgan_ddconfig(**kw)
+    sd = synth.vqgan_state_dict(dd, seed=1)
+    x = synth.image_batch(n, dd["in_channels"], H, W, seed=7)
+    return VQGANEngine(sd, dd, device="cuda:0", precision=precision), sd, dd, x, (n, H, W)
+
+
+@pytest.mark.parametrize("name", list(VQGAN_CASES))
+def test_vqgan_fp32x3_vs_reference_golden(name, golden_dir):
+    g = np.load(golden_dir / f"vqgan_{name}.npz")
+    eng, sd, dd, x, (n, H, W) = _engine(name)
+    zq, idx, h = eng.encode(x.cuda())
+    torch.cuda.synchronize()
+    h_nchw = eng.nhwc_to_nchw(h).cpu().numpy()
+    err_h = np.abs(h_nchw - g["h"]).max()
+    assert err_h < PIXEL_TOL, f"pre-quant latent max err {err_h}"
+    idx_c = idx.cpu().numpy()
+    mism = np.nonzero(idx_c != g["idx"])[0]
+    # any mismatch must be a near-tie of the reference itself: distance gap of the two candidates below the fp noise
+    if len(mism):
+        hf = torch.from_numpy(g["h"]).permute(0, 2, 3, 1).reshape(-1, 256).double()
+        book = sd["quantize.embedding.weight"].double()
+        d = torch.cdist(hf, book)
+        for r in mism:
+            assert abs(d[r, idx_c[r]] - d[r, g["idx"][r]]) < 4 * err_h * 16, f"row {r}: not a near tie"
+    assert len(mism) <= max(1, len(idx_c) // 100), f"{len(mism)} token mismatches"
+    assert torch.equal(zq.view(-1, 256), eng.codebook[idx])
+    # decode from the REFERENCE's indices so the comparison isolates the decoder
+    rec = eng.decode_indices(torch.from_numpy(g["idx"]).long().cuda(), n, H // 16, W // 16)
+    torch.cuda.synchronize()
+    assert rec.shape == (n, dd["out_ch"], H, W)
+    err_r = np.abs(rec.cpu().numpy() - g["rec"]).max()
+    assert err_r < PIXEL_TOL, f"reconstruction max err {err_r}"
+    print(f"[{name}] fp32x3: latent err {err_h:.2e}, rec err {err_r:.2e}, token mismatches {len(mism)}/{len(idx_c)}")
+
+
+@pytest.mark.parametrize("name", ["small_rgb", "config1_rgb"])
+def test_vqgan_bf16_mode_error_budget(name, golden_dir):
+    """Single-pass bf16 is the fast mode; it cannot meet 1e-3 (bf16 decoder max err ~1e-1) — budget documented here."""
+    g = np.load(golden_dir / f"vqgan_{name}.npz")
+    eng, sd, dd, x, (n, H, W) = _engine(name, "bf16")
+    zq, idx, h = eng.encode(x.cuda())
+    rec = eng.decode_indices(torch.from_numpy(g["idx"]).long().cuda(), n, H // 16, W // 16)
+    torch.cuda.synchronize()
+    err_h = np.abs(eng.nhwc_to_nchw(h).cpu().numpy() - g["h"]).max()
+    err_r = np.abs(rec.cpu().numpy() - g["rec"]).max()
+    agree = (idx.cpu().numpy() == g["idx"]).mean()
+    print(f"[{name}] bf16: latent err {err_h:.2e}, rec err {err_r:.2e}, token agreement {agree:.3f}")
+    assert err_h < 0.1 and err_r < 0.3 and agree > 0.9
+
+
+def test_decode_nchw_roundtrip_helpers():
+    eng, sd, dd, x, (n, H, W) = _engine("small_rgb")
+    zq, idx, h = eng.encode(x.cuda())
+    q_nchw = eng.nhwc_to_nchw(zq)
+    assert torch.equal(eng.nchw_to_nhwc(q_nchw), zq)
+    want = vqgan_oracle.get_codebook_entry(idx.cpu(), (n, H // 16, W // 16, 256), sd)
+    assert torch.equal(q_nchw.cpu(), want)
