@@ -8,6 +8,19 @@ from . import _lib
 from ._lib import GF_B_MN, GF_CAUSAL_SKIP, GF_GELU, GF_OUT_NCHW, PREP_IDENT, PREP_S2D, PREP_UP2, GemmArgs  # noqa: F401
 
 
+class Stats:
+    """Launch accounting for bench.py: number of kernel launches and algorithmic FLOPs of the GEMM launches.
+    `timer`, when set, is called as timer(kind, launch_fn, flops) and must invoke launch_fn() itself (CUDA-event timing)."""
+    launches = 0
+    gemm_launches = 0
+    gemm_flops = 0.0
+    timer = None
+
+    @classmethod
+    def reset(cls):
+        cls.launches, cls.gemm_launches, cls.gemm_flops = 0, 0, 0.0
+
+
 def _ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
@@ -38,7 +51,7 @@ TAPS_3X3 = [(kw - 1, kh - 1) for kh in range(3) for kw in range(3)]
 def gemm_tc(*, a_hi, a_lo, a_dims, b_hi, b_lo, k, n_cols, taps=((0, 0, 0),), a_n_mul=1, a_n_zstride=0, a_c_off=0, a_c_zstride=0,
             b_k_off=0, b_k_zstride=0, b_row_zstride=0, b_row_tapstride=0, z_inner=1, z_outer=1, tile=(128, 1),
             out_w, out_h=1, out_zo_stride=0, out_zi_stride=0, ldc, bias=None, residual=None, out_f32=None, out_hi=None,
-            out_lo=None, flags=0, causal_ncond=0, bn=128, npass=3):
+            out_lo=None, flags=0, causal_ncond=0, bn=128, npass=3, algo_flops=None):
     lib = _lib.init()
     _chk_cuda(a_hi, a_lo, b_hi, b_lo, bias, residual, out_f32, out_hi, out_lo)
     g = GemmArgs()
@@ -60,11 +73,19 @@ def gemm_tc(*, a_hi, a_lo, a_dims, b_hi, b_lo, k, n_cols, taps=((0, 0, 0),), a_n
     g.bias, g.residual = _ptr(bias), _ptr(residual)
     g.out_f32, g.out_hi, g.out_lo = _ptr(out_f32), _ptr(out_hi), _ptr(out_lo)
     g.flags, g.causal_ncond, g.bn, g.npass = flags, causal_ncond, bn, npass
-    _lib.check(lib.bevgen_gemm_tc(C.byref(g), _stream()), "bevgen_gemm_tc")
+    flops = algo_flops if algo_flops is not None else 2.0 * z_inner * z_outer * out_w * out_h * n_cols * k * len(taps)
+    Stats.launches += 1
+    Stats.gemm_launches += 1
+    Stats.gemm_flops += flops
+    if Stats.timer is not None:
+        Stats.timer("gemm_tc", lambda: _lib.check(lib.bevgen_gemm_tc(C.byref(g), _stream()), "bevgen_gemm_tc"), flops)
+    else:
+        _lib.check(lib.bevgen_gemm_tc(C.byref(g), _stream()), "bevgen_gemm_tc")
 
 
 def groupnorm_stats(x_nhwc, ws_sums, mean_rstd, eps=1e-6):
     lib = _lib.init()
+    Stats.launches += 2
     _chk_cuda(x_nhwc, ws_sums, mean_rstd)
     n, c = x_nhwc.shape[0], x_nhwc.shape[-1]
     pixels = x_nhwc.numel() // (n * c)
@@ -73,6 +94,7 @@ def groupnorm_stats(x_nhwc, ws_sums, mean_rstd, eps=1e-6):
 
 def prep_operand(x_nhwc, out_hi, out_lo, mean_rstd=None, gamma=None, beta=None, swish=False, mode=PREP_IDENT):
     lib = _lib.init()
+    Stats.launches += 1
     _chk_cuda(x_nhwc, out_hi, out_lo, mean_rstd, gamma, beta)
     n, h, w, c = x_nhwc.shape
     _lib.check(lib.bevgen_prep_operand(_ptr(x_nhwc), n, h, w, c, _ptr(mean_rstd), _ptr(gamma), _ptr(beta), int(swish), mode,
@@ -81,6 +103,7 @@ def prep_operand(x_nhwc, out_hi, out_lo, mean_rstd=None, gamma=None, beta=None, 
 
 def im2col3x3(x_nchw, out_hi, out_lo):
     lib = _lib.init()
+    Stats.launches += 1
     _chk_cuda(x_nchw, out_hi, out_lo)
     n, cin, h, w = x_nchw.shape
     _lib.check(lib.bevgen_im2col3x3(_ptr(x_nchw), n, cin, h, w, _ptr(out_hi), _ptr(out_lo), _stream()), "im2col3x3")
@@ -88,12 +111,14 @@ def im2col3x3(x_nchw, out_hi, out_lo):
 
 def transpose_f32(src, dst, n, r, c):
     lib = _lib.init()
+    Stats.launches += 1
     _chk_cuda(src, dst)
     _lib.check(lib.bevgen_transpose_f32(_ptr(src), _ptr(dst), n, r, c, _stream()), "transpose_f32")
 
 
 def softmax_rows(s, out_hi, out_lo, scale, out_ld=None):
     lib = _lib.init()
+    Stats.launches += 1
     _chk_cuda(s, out_hi, out_lo)
     cols = s.shape[-1]
     _lib.check(lib.bevgen_softmax_rows(_ptr(s), s.numel() // cols, cols, float(scale), _ptr(out_hi), _ptr(out_lo),
@@ -102,12 +127,14 @@ def softmax_rows(s, out_hi, out_lo, scale, out_ld=None):
 
 def row_sqnorm(x, out):
     lib = _lib.init()
+    Stats.launches += 1
     _chk_cuda(x, out)
     _lib.check(lib.bevgen_row_sqnorm(_ptr(x), x.shape[0], x.shape[1], _ptr(out), _stream()), "row_sqnorm")
 
 
 def vq_nearest(z, codebook, code_sqnorm, ws_zz, idx, zq=None):
     lib = _lib.init()
+    Stats.launches += 2
     _chk_cuda(z, codebook, code_sqnorm, ws_zz, idx, zq)
     assert idx.dtype == torch.int64
     _lib.check(lib.bevgen_vq_nearest(_ptr(z), _ptr(codebook), _ptr(code_sqnorm), z.shape[0], codebook.shape[0], codebook.shape[1],
@@ -116,6 +143,7 @@ def vq_nearest(z, codebook, code_sqnorm, ws_zz, idx, zq=None):
 
 def codebook_gather(codebook, idx, out):
     lib = _lib.init()
+    Stats.launches += 1
     _chk_cuda(codebook, idx, out)
     assert idx.dtype == torch.int64
     _lib.check(lib.bevgen_codebook_gather(_ptr(codebook), _ptr(idx), idx.numel(), codebook.shape[1], codebook.shape[0], _ptr(out),
@@ -124,6 +152,7 @@ def codebook_gather(codebook, idx, out):
 
 def denormalize(x_nchw, out, mean, std):
     lib = _lib.init()
+    Stats.launches += 1
     _chk_cuda(x_nchw, out)
     n, c, h, w = x_nchw.shape
     m = (C.c_float * 3)(*mean)

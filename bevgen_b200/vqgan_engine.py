@@ -129,14 +129,14 @@ class VQGANEngine:
             ops.prep_operand(x, hi, lo, mode=mode)
         return hi, lo
 
-    def _gemm_conv(self, planes, pc: PackedConv, taps, geom, out_hw, residual=None, a_n_mul=1, out_planes=False, nchw=False):
+    def _gemm_conv(self, planes, pc: PackedConv, taps, geom, out_hw, residual=None, a_n_mul=1, out_planes=False, nchw=False, algo_flops=None):
         """planes: (hi, lo) of logical shape geom=(a_n,a_h,a_w,a_c); output pixels out_hw=(N,H,W)."""
         hi, lo = planes
         N, H, W = out_hw
         tw = 16 if W >= 16 else 8
         kw = dict(a_hi=hi, a_lo=lo, a_dims=geom, b_hi=pc.hi, b_lo=pc.lo, k=pc.k, n_cols=pc.cout, taps=taps, a_n_mul=a_n_mul,
                   b_row_tapstride=pc.cout, z_outer=N, tile=(tw, 128 // tw), out_w=W, out_h=H, out_zo_stride=H * W * pc.cout,
-                  ldc=pc.cout, bias=pc.bias, residual=residual, bn=pc.bn, npass=self.npass)
+                  ldc=pc.cout, bias=pc.bias, residual=residual, bn=pc.bn, npass=self.npass, algo_flops=algo_flops)
         if out_planes:
             oh, ol = self._planes((N, H, W, pc.cout))
             ops.gemm_tc(out_hi=oh, out_lo=ol, **kw)
@@ -213,7 +213,8 @@ class VQGANEngine:
         n, cin, H, W = x_nchw.shape
         hi, lo = self._planes((n, H, W, 64))
         ops.im2col3x3(x_nchw, hi, lo)
-        h = self._gemm_conv((hi, lo), self._conv("encoder.conv_in", True), self._TAPS1, (n, H, W, 64), (n, H, W))
+        pc_in = self._conv("encoder.conv_in", True)
+        h = self._gemm_conv((hi, lo), pc_in, self._TAPS1, (n, H, W, 64), (n, H, W), algo_flops=2.0 * n * H * W * pc_in.cout * 9 * cin)
         for l in range(self.nlev):
             for b in range(self.nres):
                 h = self.resnet_block(h, f"encoder.down.{l}.block.{b}")
@@ -241,7 +242,9 @@ class VQGANEngine:
             if l != 0:
                 h = self.upsample(h, f"decoder.up.{l}.upsample")
         pc = self._conv("decoder.conv_out")
-        return self.conv3x3(h, "decoder.conv_out", norm="decoder.norm_out", swish=True, nchw=pc.cout < 16)
+        if pc.cout < 16:      # image-like outputs (3 / 7 channels): the epilogue writes NCHW directly
+            return self.conv3x3(h, "decoder.conv_out", norm="decoder.norm_out", swish=True, nchw=True)
+        return self.nhwc_to_nchw(self.conv3x3(h, "decoder.conv_out", norm="decoder.norm_out", swish=True))
 
     # ------------------------------------------------------------------ VQModel-level entry points
     @torch.no_grad()
