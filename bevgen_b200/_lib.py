@@ -10,7 +10,7 @@ _HERE = Path(__file__).resolve().parent
 LIB_PATH = _HERE / "libbevgen_b200.so"
 MAX_TAPS = 9
 
-GF_GELU, GF_OUT_NCHW, GF_B_MN, GF_CAUSAL_SKIP = 1, 2, 4, 8
+GF_GELU, GF_OUT_NCHW, GF_B_MN, GF_CAUSAL_SKIP, GF_CAUSAL_KLIMIT = 1, 2, 4, 8, 16
 PREP_IDENT, PREP_UP2, PREP_S2D = 0, 1, 2
 
 
@@ -41,6 +41,12 @@ class GemmArgs(C.Structure):
     ]
 
 
+class EmbedArgs(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("cam_idx", "bev_idx", "intrinsics_inv", "extrinsics_inv", "x_tok_emb", "cond_tok_emb",
+                                          "x_pos_emb", "cond_static", "img_embed_w", "cam_embed_w", "forward_shuffle_idx", "pixel", "out")] + \
+               [(n, C.c_int) for n in ("B", "ncam", "hw", "nc", "n_img", "L", "d", "vocab", "pad_last", "bev_embed", "row0", "nrows")]
+
+
 _vp, _i, _f, _ll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
 
 # name -> (restype, argtypes); must list every symbol declared in include/bevgen_b200.h
@@ -59,6 +65,9 @@ SIGNATURES = {
     "bevgen_vq_nearest": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "bevgen_codebook_gather": (_i, [_vp, _vp, _ll, _i, _i, _vp, _vp]),
     "bevgen_denormalize": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "bevgen_layernorm": (_i, [_vp, _ll, _i, _ll, _vp, _vp, _f, _vp, _vp, _vp, _vp]),
+    "bevgen_embed_assemble": (_i, [C.POINTER(EmbedArgs), _vp]),
+    "bevgen_attn_softmax": (_i, [_vp, _vp, _vp, _ll, _i, _i, _f, _vp, _vp, _vp]),
 }
 
 _lib = None

@@ -24,6 +24,17 @@ int launch_denorm(const float* x, float* out, int N, int C, int P, const float* 
 int launch_row_sqnorm(const float* x, float* out, int rows, int D, cudaStream_t st);
 int launch_vq_nearest(const float* z, const float* cb, const float* zz, const float* ee, long long* idx, float* zq, int rows, int n_codes,
                       int D, cudaStream_t st);
+struct EmbedParams {
+  const long long* cam_idx; const long long* bev_idx; const float* I_inv; const float* E_inv; const float* x_tok_emb;
+  const float* cond_tok_emb; const float* x_pos_emb; const float* cond_static; const float* img_embed_w; const float* cam_embed_w;
+  const int* fwd; const float* pixel; float* out;
+  int B, ncam, hw, nc, n_img, L, d, vocab; int pad_last; int bev_embed; int row0, nrows;
+};
+int launch_layernorm(const float* x, const float* gamma, const float* beta, float* y, uint16_t* hi, uint16_t* lo, long long rows, int d,
+                     long long x_row_stride, float eps, cudaStream_t st);
+int launch_embed(const EmbedParams& p, cudaStream_t st);
+int launch_attn_softmax(const float* S, const float* bias, const uint8_t* mask, uint16_t* hi, uint16_t* lo, long long zrows, int L, int Lk,
+                        float scale, cudaStream_t st);
 }  // namespace bevgen
 
 using namespace bevgen;
@@ -211,6 +222,30 @@ BEVGEN_API int bevgen_denormalize(const float* x, float* out, int n, int c, int 
   if (rc) return rc;
   if (!x || !out || !mean3 || !std3) return fail(BEVGEN_ERR_ARG, "denormalize: bad args");
   CHECK_LAUNCH(launch_denorm(x, out, n, c, pixels, mean3, std3, g_sm_count, (cudaStream_t)stream), "denormalize");
+}
+
+BEVGEN_API int bevgen_layernorm(const float* x, long long rows, int d, long long x_row_stride, const float* gamma, const float* beta, float eps,
+                                float* y, void* out_hi, void* out_lo, void* stream) {
+  if (!x || !gamma || !beta || (!y && !out_hi)) return fail(BEVGEN_ERR_ARG, "layernorm: bad args");
+  if (x_row_stride % 4 != 0) return fail(BEVGEN_ERR_ARG, "layernorm: row stride must be a multiple of 4");
+  CHECK_LAUNCH(launch_layernorm(x, gamma, beta, y, (uint16_t*)out_hi, (uint16_t*)out_lo, rows, d, x_row_stride, eps, (cudaStream_t)stream), "layernorm");
+}
+
+BEVGEN_API int bevgen_embed_assemble(const bevgen_embed_args* a, void* stream) {
+  if (!a || !a->cam_idx || !a->bev_idx || !a->x_tok_emb || !a->cond_tok_emb || !a->x_pos_emb || !a->cond_static || !a->forward_shuffle_idx || !a->out)
+    return fail(BEVGEN_ERR_ARG, "embed_assemble: null argument");
+  if (a->img_embed_w && (!a->cam_embed_w || !a->intrinsics_inv || !a->extrinsics_inv || !a->pixel)) return fail(BEVGEN_ERR_ARG, "embed_assemble: ray embedding inputs missing");
+  if (a->row0 < 0 || a->row0 + a->nrows > a->L) return fail(BEVGEN_ERR_ARG, "embed_assemble: row range outside the sequence");
+  EmbedParams p{a->cam_idx, a->bev_idx, a->intrinsics_inv, a->extrinsics_inv, a->x_tok_emb, a->cond_tok_emb, a->x_pos_emb, a->cond_static,
+                a->img_embed_w, a->cam_embed_w, a->forward_shuffle_idx, a->pixel, a->out, a->B, a->ncam, a->hw, a->nc, a->n_img, a->L, a->d,
+                a->vocab, a->pad_last, a->bev_embed, a->row0, a->nrows};
+  CHECK_LAUNCH(launch_embed(p, (cudaStream_t)stream), "embed_assemble");
+}
+
+BEVGEN_API int bevgen_attn_softmax(const float* s, const float* bias, const unsigned char* mask, long long zrows, int L, int Lk, float scale,
+                                   void* out_hi, void* out_lo, void* stream) {
+  if (!s || !mask || !out_hi) return fail(BEVGEN_ERR_ARG, "attn_softmax: bad args");
+  CHECK_LAUNCH(launch_attn_softmax(s, bias, mask, (uint16_t*)out_hi, (uint16_t*)out_lo, zrows, L, Lk, scale, (cudaStream_t)stream), "attn_softmax");
 }
 
 }  // extern "C"

@@ -85,6 +85,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     th = mt / p.tiles_w;
   };
   // causal support of an output tile (attention scores / P.V): rows m0..m0+127 (w axis), cols n0..n0+BN-1
+  auto k_iters_for = [&](int tw) -> int {
+    if (!(p.flags & GF_CAUSAL_KLIMIT)) return k_iters;
+    const int need = max(p.causal_ncond, tw * p.tile_w + BM);
+    return min(k_iters, (need + BK - 1) / BK);
+  };
   auto tile_skipped = [&](int tw, int nt) -> bool {
     if (!causal) return false;
     int m_last = tw * p.tile_w + BM - 1, n0 = nt * BN;
@@ -102,7 +107,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         if (tile_skipped(tw, nt)) continue;
         const int zo = z / p.z_inner, zi = z % p.z_inner;
         const int w0 = tw * p.tile_w, h0 = th * p.tile_h, n0 = nt * BN;
-        for (int it = 0; it < k_iters; ++it) {
+        const int kit = k_iters_for(tw);
+        for (int it = 0; it < kit; ++it) {
           const int tap = it / p.kchunks, kc = it % p.kchunks;
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = smem + stage * Cfg::STAGE_BYTES;
@@ -145,7 +151,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int it = 0; it < k_iters; ++it) {
+        const int kit = k_iters_for(tw);
+        for (int it = 0; it < kit; ++it) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t a_base = smem_u32(smem + stage * Cfg::STAGE_BYTES);

@@ -11,7 +11,8 @@ enum GemmFlags : int {
   GF_GELU = 1,        // exact-erf GELU after bias
   GF_OUT_NCHW = 2,    // fp32 output written as [z][col][h][w] (tiny Cout: conv_out)
   GF_B_MN = 4,        // B operand is MN-major in global memory: [k rows][n cols] (e.g. V in P.V)
-  GF_CAUSAL_SKIP = 8, // skip output tiles / k-chunks entirely outside the [cond | causal] support (attention)
+  GF_CAUSAL_SKIP = 8, // skip output tiles entirely outside the [cond | causal] support (attention scores)
+  GF_CAUSAL_KLIMIT = 16, // reduction index = key index: stop at max(ncond, last row of the tile + 1) (P.V)
 };
 
 struct GemmParams {

@@ -5,7 +5,8 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import GF_B_MN, GF_CAUSAL_SKIP, GF_GELU, GF_OUT_NCHW, PREP_IDENT, PREP_S2D, PREP_UP2, GemmArgs  # noqa: F401
+from ._lib import (GF_B_MN, GF_CAUSAL_KLIMIT, GF_CAUSAL_SKIP, GF_GELU, GF_OUT_NCHW, PREP_IDENT, PREP_S2D, PREP_UP2,  # noqa: F401
+                   EmbedArgs, GemmArgs)
 
 
 class Stats:
@@ -158,3 +159,29 @@ def denormalize(x_nchw, out, mean, std):
     m = (C.c_float * 3)(*mean)
     s = (C.c_float * 3)(*std)
     _lib.check(lib.bevgen_denormalize(_ptr(x_nchw), _ptr(out), n, c, h * w, m, s, _stream()), "denormalize")
+
+
+def layernorm(x, gamma, beta, y=None, out_hi=None, out_lo=None, eps=1e-5, rows=None, row_stride=None):
+    lib = _lib.init()
+    Stats.launches += 1
+    _chk_cuda(gamma, beta, y, out_hi, out_lo)
+    d = gamma.numel()
+    rows = x.numel() // d if rows is None else rows
+    row_stride = d if row_stride is None else row_stride
+    _lib.check(lib.bevgen_layernorm(_ptr(x), rows, d, row_stride, _ptr(gamma), _ptr(beta), eps, _ptr(y), _ptr(out_hi), _ptr(out_lo), _stream()),
+               "layernorm")
+
+
+def embed_assemble(args: "EmbedArgs"):
+    lib = _lib.init()
+    Stats.launches += 1
+    _lib.check(lib.bevgen_embed_assemble(C.byref(args), _stream()), "embed_assemble")
+
+
+def attn_softmax(S, bias, mask_u8, out_hi, out_lo, L, scale):
+    lib = _lib.init()
+    Stats.launches += 1
+    _chk_cuda(S, bias, mask_u8, out_hi, out_lo)
+    Lk = S.shape[-1]
+    _lib.check(lib.bevgen_attn_softmax(_ptr(S), _ptr(bias), _ptr(mask_u8), S.numel() // Lk, L, Lk, float(scale), _ptr(out_hi), _ptr(out_lo),
+                                       _stream()), "attn_softmax")

@@ -34,7 +34,8 @@ extern "C" {
 #define BEVGEN_GF_GELU 1        /* exact-erf GELU after bias (mingpt_sparse.py:235) */
 #define BEVGEN_GF_OUT_NCHW 2    /* fp32 output stored [z][col][h][w] (tiny Cout, e.g. conv_out -> NCHW images) */
 #define BEVGEN_GF_B_MN 4        /* B operand is [k rows][n cols] in memory (V in P.V) */
-#define BEVGEN_GF_CAUSAL_SKIP 8 /* skip output tiles outside the [cond | causal] support */
+#define BEVGEN_GF_CAUSAL_SKIP 8 /* skip output tiles outside the [cond | causal] support (Q.K^T) */
+#define BEVGEN_GF_CAUSAL_KLIMIT 16 /* reduction over keys stops at max(ncond, last tile row + 1) (P.V) */
 
 /* prep modes */
 #define BEVGEN_PREP_IDENT 0
@@ -105,6 +106,40 @@ BEVGEN_API int bevgen_codebook_gather(const float* codebook, const long long* id
 
 /* bev_utils/util.py:97-118 denormalize_tensor(keep_tensor=True) on fp32 NCHW, 3 channels */
 BEVGEN_API int bevgen_denormalize(const float* x, float* out, int n, int c, int pixels, const float* mean3, const float* std3, void* stream);
+
+/* ---------------------------------------------------------------- stage-2 transformer */
+
+/* nn.LayerNorm(d) (mingpt_sparse.py:220-221,285): x fp32 rows (pitch x_row_stride elements) -> y fp32 [rows][d] (optional)
+ * and bf16 planes [rows][d] (optional). d % 128 == 0, d <= 1024. */
+BEVGEN_API int bevgen_layernorm(const float* x, long long rows, int d, long long x_row_stride, const float* gamma, const float* beta, float eps,
+                                float* y, void* out_hi, void* out_lo, void* stream);
+
+/* Input-embedding assembly of GPT.forward (mingpt_sparse.py:319-373) for sequence rows [row0, row0+nrows):
+ * token + ray embedding (L2-normalised) + position embeddings, decode-order permutation, [cond | img | pad] concat. */
+typedef struct {
+  const long long* cam_idx;  /* [B][ncam][hw] int64 tokens */
+  const long long* bev_idx;  /* [B][nc] */
+  const float* intrinsics_inv; /* [B][ncam][3][3] */
+  const float* extrinsics_inv; /* [B][ncam][4][4] */
+  const float* x_tok_emb;    /* [vocab+1][d] */
+  const float* cond_tok_emb; /* [cond_vocab][d] */
+  const float* x_pos_emb;    /* [n_img][d] */
+  const float* cond_static;  /* [nc][d]: cond_pos_emb (+ bev_embed(grid) - sum_cam bev_cam_pos_emb) */
+  const float* img_embed_w;  /* [d][4] or NULL */
+  const float* cam_embed_w;  /* [d][4] or NULL */
+  const int* forward_shuffle_idx; /* [n_img] */
+  const float* pixel;        /* [hw][3] image-plane grid */
+  float* out;                /* [B][nrows][d] */
+  int B, ncam, hw, nc, n_img, L, d, vocab;
+  int pad_last, bev_embed;
+  int row0, nrows;
+} bevgen_embed_args;
+BEVGEN_API int bevgen_embed_assemble(const bevgen_embed_args* args, void* stream);
+
+/* P = softmax_j(scale * (S + bias)) over mask != 0, zeros elsewhere (sparse_self_attention.py:153-173, dense form).
+ * S fp32 [zrows][Lk] with zrows = batch*heads*L rows, bias fp32 [L][Lk] or NULL, mask uint8 [L][Lk]. */
+BEVGEN_API int bevgen_attn_softmax(const float* s, const float* bias, const unsigned char* mask, long long zrows, int L, int Lk, float scale,
+                                   void* out_hi, void* out_lo, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,62 @@
+"""GPU parity of the stage-2 transformer engine vs goldens minted from the unmodified reference GPT (dense fp32 stand-in for
+the absent DeepSpeed ops) and vs the CPU oracle.  Tolerance: north_star's 1e-3 on logits (fp32x3 mode)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from bevgen_b200.gpt_config import GPTConfig  # noqa: E402
+from bevgen_b200.gpt_engine import GPTEngine  # noqa: E402
+from oracle import gpt_oracle, synth  # noqa: E402
+from tests.cases import GPT_CASES, gpt_sizes  # noqa: E402
+
+LOGIT_TOL = 1e-3
+
+
+def _case(name, precision="fp32x3"):
+    kw, B = GPT_CASES[name]
+    cfg = GPTConfig(**kw)
+    sd = synth.gpt_state_dict(gpt_sizes(cfg), seed=2)
+    cam, bev, batch = synth.stage2_inputs(B, cfg.num_cams, cfg.num_cam_tokens, cfg.num_cond_tokens, cfg.vocab_size, cfg.cond_vocab_size, seed=4)
+    eng = GPTEngine(sd, cfg, device="cuda:0", precision=precision)
+    return cfg, sd, cam, bev, batch, eng
+
+
+def test_embed_vs_oracle():
+    cfg, sd, cam, bev, batch, eng = _case("small")
+    geo = gpt_oracle.geo_from_config(cfg)
+    for sampling in (True, False):
+        want = gpt_oracle.embed(sd, geo, cam, bev, batch, sampling)
+        got = eng.embed(cam.cuda(), bev.cuda(), batch, sampling).cpu()
+        assert (got - want).abs().max().item() < 2e-6
+    cfg, sd, cam, bev, batch, eng = _case("padded")
+    want = gpt_oracle.embed(sd, gpt_oracle.geo_from_config(cfg), cam, bev, batch, True)
+    assert (eng.embed(cam.cuda(), bev.cuda(), batch, True).cpu() - want).abs().max().item() < 2e-6
+
+
+@pytest.mark.parametrize("name", ["small", "padded", "wide2"])
+def test_forward_fp32x3_vs_reference_golden(name, golden_dir):
+    g = np.load(golden_dir / f"gpt_{name}.npz")
+    cfg, sd, cam, bev, batch, eng = _case(name)
+    rows = g["rows"]
+    tf, hid = eng.forward(cam.clone().cuda(), bev.cuda(), batch, sampling=False, return_hidden=True)
+    s = eng.forward(cam.cuda(), bev.cuda(), batch, sampling=True)
+    torch.cuda.synchronize()
+    e_h0 = np.abs(hid[0][:, ::97].cpu().numpy() - g["hidden0_rows"]).max()
+    e_hl = np.abs(hid[-1][:, ::97].cpu().numpy() - g["hidden_last_rows"]).max()
+    e_tf = np.abs(tf[:, rows].cpu().numpy() - g["logits_tf"]).max()
+    e_s = np.abs(s[:, rows].cpu().numpy() - g["logits_s"]).max()
+    print(f"[{name}] fp32x3: hidden0 {e_h0:.2e} hidden_last {e_hl:.2e} logits tf {e_tf:.2e} sampling {e_s:.2e} (|logit| max {float(g['logits_tf_absmax']):.2f})")
+    assert e_h0 < LOGIT_TOL and e_hl < LOGIT_TOL and e_tf < LOGIT_TOL and e_s < LOGIT_TOL
+    assert abs(tf.double().mean().item() - float(g["logits_tf_mean"])) < 1e-5
+
+
+def test_forward_bf16_error_budget(golden_dir):
+    """Single-pass bf16 (BASELINE config 3 names bf16): cannot meet 1e-3 (naive bf16 3.4e-2); budget documented."""
+    g = np.load(golden_dir / "gpt_wide2.npz")
+    cfg, sd, cam, bev, batch, eng = _case("wide2", "bf16")
+    tf = eng.forward(cam.clone().cuda(), bev.cuda(), batch, sampling=False)
+    err = np.abs(tf[:, g["rows"]].cpu().numpy() - g["logits_tf"])
+    print(f"[wide2] bf16: logits max err {err.max():.2e} mean {err.mean():.2e}")
+    assert err.max() < 6e-2 and err.mean() < 1e-2
