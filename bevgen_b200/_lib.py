@@ -10,7 +10,7 @@ _HERE = Path(__file__).resolve().parent
 LIB_PATH = _HERE / "libbevgen_b200.so"
 MAX_TAPS = 9
 
-GF_GELU, GF_OUT_NCHW, GF_B_MN, GF_CAUSAL_SKIP, GF_CAUSAL_KLIMIT = 1, 2, 4, 8, 16
+GF_GELU, GF_OUT_NCHW, GF_B_MN, GF_CAUSAL_SKIP, GF_CAUSAL_KLIMIT, GF_OUT_T = 1, 2, 4, 8, 16, 32
 PREP_IDENT, PREP_UP2, PREP_S2D = 0, 1, 2
 
 
@@ -43,7 +43,8 @@ class GemmArgs(C.Structure):
 
 class EmbedArgs(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("cam_idx", "bev_idx", "intrinsics_inv", "extrinsics_inv", "x_tok_emb", "cond_tok_emb",
-                                          "x_pos_emb", "cond_static", "img_embed_w", "cam_embed_w", "forward_shuffle_idx", "pixel", "out")] + \
+                                          "x_pos_emb", "cond_static", "img_embed_w", "cam_embed_w", "forward_shuffle_idx", "pixel", "out",
+                                          "step_ptr")] + \
                [(n, C.c_int) for n in ("B", "ncam", "hw", "nc", "n_img", "L", "d", "vocab", "pad_last", "bev_embed", "row0", "nrows")]
 
 
@@ -68,6 +69,12 @@ SIGNATURES = {
     "bevgen_layernorm": (_i, [_vp, _ll, _i, _ll, _vp, _vp, _f, _vp, _vp, _vp, _vp]),
     "bevgen_embed_assemble": (_i, [C.POINTER(EmbedArgs), _vp]),
     "bevgen_attn_softmax": (_i, [_vp, _vp, _vp, _ll, _i, _i, _f, _vp, _vp, _vp]),
+    "bevgen_dec_reduce_ln": (_i, [_vp, _i, _ll, _vp, _vp, _ll, _vp, _vp, _f, _vp, _vp, _vp, _vp, _i, _i, _vp]),
+    "bevgen_dec_reduce_act": (_i, [_vp, _i, _ll, _vp, _i, _vp, _vp, _i, _i, _vp]),
+    "bevgen_kv_store": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "bevgen_dec_attention": (_i, [_vp, _i, _ll, _vp, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp]),
+    "bevgen_sample_topk": (_i, [_vp, _i, _ll, _i, _i, _f, _i, _i, C.c_ulonglong, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "bevgen_dec_advance": (_i, [_vp, _vp]),
 }
 
 _lib = None

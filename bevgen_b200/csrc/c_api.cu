@@ -7,35 +7,7 @@
 #include "../../include/bevgen_b200.h"
 #include "common.cuh"
 #include "gemm_tc.cuh"
-
-namespace bevgen {
-int gemm_tc_dispatch(const GemmParams& p, int bn, int npass, int sm_count, cudaStream_t stream);
-struct PrepParams {
-  const float* x; const float* mean_rstd; const float* gamma; const float* beta; uint16_t* hi; uint16_t* lo;
-  int N, H, W, C; int mode; int swish;
-};
-int launch_gn_stats(const float* x, double* sums, float* mean_rstd, int N, int pixels, int C, float eps, cudaStream_t st);
-int launch_prep(const PrepParams& p, int sm_count, cudaStream_t st);
-int launch_im2col3x3(const float* x, uint16_t* hi, uint16_t* lo, int N, int Cin, int H, int W, int sm_count, cudaStream_t st);
-int launch_transpose(const float* src, float* dst, int N, int R, int Cc, cudaStream_t st);
-int launch_softmax_rows(const float* s, uint16_t* hi, uint16_t* lo, long long rows, int cols, int out_ld, float scale, cudaStream_t st);
-int launch_gather_rows(const float* table, const long long* idx, float* out, long long rows, int D, int n_table, int sm_count, cudaStream_t st);
-int launch_denorm(const float* x, float* out, int N, int C, int P, const float* mean, const float* std_, int sm_count, cudaStream_t st);
-int launch_row_sqnorm(const float* x, float* out, int rows, int D, cudaStream_t st);
-int launch_vq_nearest(const float* z, const float* cb, const float* zz, const float* ee, long long* idx, float* zq, int rows, int n_codes,
-                      int D, cudaStream_t st);
-struct EmbedParams {
-  const long long* cam_idx; const long long* bev_idx; const float* I_inv; const float* E_inv; const float* x_tok_emb;
-  const float* cond_tok_emb; const float* x_pos_emb; const float* cond_static; const float* img_embed_w; const float* cam_embed_w;
-  const int* fwd; const float* pixel; float* out;
-  int B, ncam, hw, nc, n_img, L, d, vocab; int pad_last; int bev_embed; int row0, nrows;
-};
-int launch_layernorm(const float* x, const float* gamma, const float* beta, float* y, uint16_t* hi, uint16_t* lo, long long rows, int d,
-                     long long x_row_stride, float eps, cudaStream_t st);
-int launch_embed(const EmbedParams& p, cudaStream_t st);
-int launch_attn_softmax(const float* S, const float* bias, const uint8_t* mask, uint16_t* hi, uint16_t* lo, long long zrows, int L, int Lk,
-                        float scale, cudaStream_t st);
-}  // namespace bevgen
+#include "kernels.cuh"
 
 using namespace bevgen;
 
@@ -117,6 +89,8 @@ BEVGEN_API int bevgen_gemm_tc(const bevgen_gemm_args* a, void* stream) {
   if ((a->flags & BEVGEN_GF_B_MN) && bn < 64) return fail(BEVGEN_ERR_ARG, "MN-major B needs bn >= 64");
   if (a->out_f32 == nullptr && a->out_hi == nullptr) return fail(BEVGEN_ERR_ARG, "no output buffer");
   if ((a->flags & BEVGEN_GF_OUT_NCHW) && a->out_hi != nullptr) return fail(BEVGEN_ERR_ARG, "NCHW output is fp32 only");
+  if ((a->flags & BEVGEN_GF_OUT_T) && (a->out_f32 == nullptr || a->out_hi != nullptr || a->bias || a->residual || (a->flags & BEVGEN_GF_GELU)))
+    return fail(BEVGEN_ERR_ARG, "transposed output is a raw fp32 partial (no bias/activation/residual/split planes)");
 
   GemmParams p;
   memset(&p, 0, sizeof(p));
@@ -235,9 +209,9 @@ BEVGEN_API int bevgen_embed_assemble(const bevgen_embed_args* a, void* stream) {
   if (!a || !a->cam_idx || !a->bev_idx || !a->x_tok_emb || !a->cond_tok_emb || !a->x_pos_emb || !a->cond_static || !a->forward_shuffle_idx || !a->out)
     return fail(BEVGEN_ERR_ARG, "embed_assemble: null argument");
   if (a->img_embed_w && (!a->cam_embed_w || !a->intrinsics_inv || !a->extrinsics_inv || !a->pixel)) return fail(BEVGEN_ERR_ARG, "embed_assemble: ray embedding inputs missing");
-  if (a->row0 < 0 || a->row0 + a->nrows > a->L) return fail(BEVGEN_ERR_ARG, "embed_assemble: row range outside the sequence");
+  if (!a->step_ptr && (a->row0 < 0 || a->row0 + a->nrows > a->L)) return fail(BEVGEN_ERR_ARG, "embed_assemble: row range outside the sequence");
   EmbedParams p{a->cam_idx, a->bev_idx, a->intrinsics_inv, a->extrinsics_inv, a->x_tok_emb, a->cond_tok_emb, a->x_pos_emb, a->cond_static,
-                a->img_embed_w, a->cam_embed_w, a->forward_shuffle_idx, a->pixel, a->out, a->B, a->ncam, a->hw, a->nc, a->n_img, a->L, a->d,
+                a->img_embed_w, a->cam_embed_w, a->forward_shuffle_idx, a->pixel, a->out, a->step_ptr, a->B, a->ncam, a->hw, a->nc, a->n_img, a->L, a->d,
                 a->vocab, a->pad_last, a->bev_embed, a->row0, a->nrows};
   CHECK_LAUNCH(launch_embed(p, (cudaStream_t)stream), "embed_assemble");
 }
@@ -246,6 +220,51 @@ BEVGEN_API int bevgen_attn_softmax(const float* s, const float* bias, const unsi
                                    void* out_hi, void* out_lo, void* stream) {
   if (!s || !mask || !out_hi) return fail(BEVGEN_ERR_ARG, "attn_softmax: bad args");
   CHECK_LAUNCH(launch_attn_softmax(s, bias, mask, (uint16_t*)out_hi, (uint16_t*)out_lo, zrows, L, Lk, scale, (cudaStream_t)stream), "attn_softmax");
+}
+
+/* ---------------------------------------------------------------- KV-cache decode */
+BEVGEN_API int bevgen_dec_reduce_ln(const float* partials, int ks, long long zstride, const float* bias, const float* residual,
+                                    long long residual_row_stride, const float* gamma, const float* beta, float eps, float* x_out, float* y,
+                                    void* out_hi, void* out_lo, int rows, int d, void* stream) {
+  if (!gamma || !beta || (ks > 0 && !partials) || (ks == 0 && !residual)) return fail(BEVGEN_ERR_ARG, "dec_reduce_ln: bad args");
+  CHECK_LAUNCH(launch_dec_reduce_ln(partials, ks, zstride, bias, residual, residual_row_stride, gamma, beta, eps, x_out, y, (uint16_t*)out_hi,
+                                    (uint16_t*)out_lo, rows, d, (cudaStream_t)stream), "dec_reduce_ln");
+}
+
+BEVGEN_API int bevgen_dec_reduce_act(const float* partials, int ks, long long zstride, const float* bias, int gelu, void* out_hi, void* out_lo,
+                                     int rows, int n, void* stream) {
+  if (!partials || !bias || !out_hi || ks < 1) return fail(BEVGEN_ERR_ARG, "dec_reduce_act: bad args");
+  CHECK_LAUNCH(launch_dec_reduce_act(partials, ks, zstride, bias, (uint16_t*)out_hi, (uint16_t*)out_lo, rows, n, gelu, (cudaStream_t)stream),
+               "dec_reduce_act");
+}
+
+BEVGEN_API int bevgen_kv_store(const void* qkv_hi, const void* qkv_lo, void* k_cache, void* v_cache, int kv_bf16, int batch, int lp, int nrows,
+                               int heads, int d, int lmax, void* stream) {
+  if (!qkv_hi || !k_cache || !v_cache || nrows > lp || nrows > lmax) return fail(BEVGEN_ERR_ARG, "kv_store: bad args");
+  CHECK_LAUNCH(launch_kv_store((const uint16_t*)qkv_hi, (const uint16_t*)qkv_lo, k_cache, v_cache, kv_bf16, batch, lp, nrows, heads, d, lmax,
+                               (cudaStream_t)stream), "kv_store");
+}
+
+BEVGEN_API int bevgen_dec_attention(const float* qkv_partials, int ks, long long zstride, const float* qkv_bias, const float* y,
+                                    const float* camera_bias, int bias_ld, void* k_cache, void* v_cache, int kv_bf16, float* x1,
+                                    const int* step_ptr, int batch, int n_cond, int heads, int d, int lmax, float scale, void* stream) {
+  if (!qkv_partials || !qkv_bias || !y || !k_cache || !v_cache || !x1 || !step_ptr || ks < 1) return fail(BEVGEN_ERR_ARG, "dec_attention: bad args");
+  CHECK_LAUNCH(launch_dec_attn(qkv_partials, ks, zstride, qkv_bias, y, camera_bias, bias_ld, k_cache, v_cache, kv_bf16, x1, step_ptr, batch, n_cond,
+                               heads, d, lmax, scale, (cudaStream_t)stream), "dec_attention");
+}
+
+BEVGEN_API int bevgen_sample_topk(const float* logit_partials, int ks, long long zstride, int vpad, int vocab, float temperature, int top_k,
+                                  int greedy, unsigned long long seed, const long long* forced_tokens, const int* forward_shuffle_idx,
+                                  long long* cam_idx, long long* tokens_out, float* logits_trace, float* probs_out, const int* step_ptr, int batch,
+                                  int n_img, int hw, int ncam, void* stream) {
+  if (!logit_partials || !forward_shuffle_idx || !cam_idx || !step_ptr || ks < 1) return fail(BEVGEN_ERR_ARG, "sample_topk: bad args");
+  CHECK_LAUNCH(launch_dec_sample(logit_partials, ks, zstride, vpad, vocab, temperature, top_k, greedy, seed, forced_tokens, forward_shuffle_idx,
+                                 cam_idx, tokens_out, logits_trace, probs_out, step_ptr, batch, n_img, hw, ncam, (cudaStream_t)stream), "sample_topk");
+}
+
+BEVGEN_API int bevgen_dec_advance(int* step_ptr, void* stream) {
+  if (!step_ptr) return fail(BEVGEN_ERR_ARG, "dec_advance: null step");
+  CHECK_LAUNCH(launch_dec_advance(step_ptr, (cudaStream_t)stream), "dec_advance");
 }
 
 }  // extern "C"

@@ -3,6 +3,7 @@
 // nearest 2x upsampling or the stride-2 space-to-depth split), conv_in im2col, LayerNorm, layout transposes,
 // row softmax and row gathers.  All are coalesced / 128-bit vectorised grid-stride kernels.
 #include "common.cuh"
+#include "kernels.cuh"
 
 namespace bevgen {
 
@@ -65,20 +66,6 @@ __global__ void gn_finalize_kernel(const double* __restrict__ sums, float* __res
 // ------------------------------------------------------------------------------------------------
 // prep: fp32 NHWC -> bf16 hi/lo planes, optional GroupNorm-apply (+swish), optional spatial remap.
 // ------------------------------------------------------------------------------------------------
-enum PrepMode : int { PREP_IDENT = 0, PREP_UP2 = 1, PREP_S2D = 2 };
-
-struct PrepParams {
-  const float* x;         // [N][H][W][C]
-  const float* mean_rstd; // [N][32][2] (mean, rstd) or null (no normalisation)
-  const float* gamma;     // [C]
-  const float* beta;      // [C]
-  uint16_t* hi;           // bf16 planes
-  uint16_t* lo;           // may be null (single-pass bf16 mode)
-  int N, H, W, C;         // source geometry
-  int mode;               // PrepMode
-  int swish;              // apply x*sigmoid(x) after the affine
-};
-
 __global__ void __launch_bounds__(256) prep_kernel(const PrepParams p) {
   const int oct = p.C >> 3;  // 8 channels per thread
   int OH = p.H, OW = p.W, ON = p.N;

@@ -8,6 +8,7 @@
 // Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane), warp 2 = TMEM allocator,
 // warps 4-7 = epilogue (TMEM -> registers -> bias/activation/residual -> global).
 #include "common.cuh"
+#include "kernels.cuh"
 #include "gemm_tc.cuh"
 
 namespace bevgen {
@@ -229,6 +230,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         }
         if (!row_ok) continue;
         const int col0 = n0 + c;
+        if (p.flags & GF_OUT_T) {
+          // D^T: lanes hold consecutive rows -> each store instruction writes 32 consecutive floats of one output row
+          const long long pix = (long long)oh * p.out_w + ow;
+#pragma unroll
+          for (int j = 0; j < CH; ++j)
+            if (col0 + j < p.n_cols) p.out_f32[zoff + (long long)(col0 + j) * p.ldc + pix] = v[j];
+          continue;
+        }
         const bool full = (col0 + CH <= p.n_cols) && ((p.ldc & 3) == 0) && !(p.flags & GF_OUT_NCHW);
         if (p.bias != nullptr) {
 #pragma unroll

@@ -12,6 +12,7 @@ enum GemmFlags : int {
   GF_OUT_NCHW = 2,    // fp32 output written as [z][col][h][w] (tiny Cout: conv_out)
   GF_B_MN = 4,        // B operand is MN-major in global memory: [k rows][n cols] (e.g. V in P.V)
   GF_CAUSAL_SKIP = 8, // skip output tiles entirely outside the [cond | causal] support (attention scores)
+  GF_OUT_T = 32,      // swap-AB decode GEMMs: store D^T, out[z][col][row] fp32, no bias/act/residual (split-K partials)
   GF_CAUSAL_KLIMIT = 16, // reduction index = key index: stop at max(ncond, last row of the tile + 1) (P.V)
 };
 

@@ -1,0 +1,79 @@
+// Internal launcher interface shared by the kernel translation units and c_api.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "gemm_tc.cuh"
+
+namespace bevgen {
+
+enum PrepMode : int { PREP_IDENT = 0, PREP_UP2 = 1, PREP_S2D = 2 };
+
+struct PrepParams {
+  const float* x;          // [N][H][W][C]
+  const float* mean_rstd;  // [N][32][2] (mean, rstd) or null (no normalisation)
+  const float* gamma;      // [C]
+  const float* beta;       // [C]
+  uint16_t* hi;            // bf16 planes
+  uint16_t* lo;            // may be null (single-pass bf16 mode)
+  int N, H, W, C;          // source geometry
+  int mode;                // PrepMode
+  int swish;               // apply x*sigmoid(x) after the affine
+};
+
+struct EmbedParams {
+  const long long* cam_idx;    // [B][ncam][hw]
+  const long long* bev_idx;    // [B][nc]
+  const float* I_inv;          // [B][ncam][3][3]
+  const float* E_inv;          // [B][ncam][4][4]
+  const float* x_tok_emb;      // [vocab+1][d]
+  const float* cond_tok_emb;   // [cond_vocab][d]
+  const float* x_pos_emb;      // [n_img][d]
+  const float* cond_static;    // [nc][d]
+  const float* img_embed_w;    // [d][4] or null
+  const float* cam_embed_w;    // [d][4] or null
+  const int* fwd;              // [n_img]
+  const float* pixel;          // [hw][3]
+  float* out;                  // [B][nrows][d]
+  const int* step_ptr;         // decode: first row = nc + *step_ptr - 1 (overrides row0), or null
+  int B, ncam, hw, nc, n_img, L, d, vocab;
+  int pad_last;                // teacher forcing: the last (cam,h,w) token is replaced by PAD (:328-329)
+  int bev_embed;               // subtract sum_cam c_embed on cond rows
+  int row0, nrows;             // sequence rows [row0, row0+nrows) are produced; out row index = s - row0
+};
+
+int gemm_tc_dispatch(const GemmParams& p, int bn, int npass, int sm_count, cudaStream_t stream);
+
+int launch_gn_stats(const float* x, double* sums, float* mean_rstd, int N, int pixels, int C, float eps, cudaStream_t st);
+int launch_prep(const PrepParams& p, int sm_count, cudaStream_t st);
+int launch_im2col3x3(const float* x, uint16_t* hi, uint16_t* lo, int N, int Cin, int H, int W, int sm_count, cudaStream_t st);
+int launch_transpose(const float* src, float* dst, int N, int R, int Cc, cudaStream_t st);
+int launch_softmax_rows(const float* s, uint16_t* hi, uint16_t* lo, long long rows, int cols, int out_ld, float scale, cudaStream_t st);
+int launch_gather_rows(const float* table, const long long* idx, float* out, long long rows, int D, int n_table, int sm_count, cudaStream_t st);
+int launch_denorm(const float* x, float* out, int N, int C, int P, const float* mean, const float* std_, int sm_count, cudaStream_t st);
+int launch_row_sqnorm(const float* x, float* out, int rows, int D, cudaStream_t st);
+int launch_vq_nearest(const float* z, const float* cb, const float* zz, const float* ee, long long* idx, float* zq, int rows, int n_codes,
+                      int D, cudaStream_t st);
+
+int launch_layernorm(const float* x, const float* gamma, const float* beta, float* y, uint16_t* hi, uint16_t* lo, long long rows, int d,
+                     long long x_row_stride, float eps, cudaStream_t st);
+int launch_embed(const EmbedParams& p, cudaStream_t st);
+int launch_attn_softmax(const float* S, const float* bias, const uint8_t* mask, uint16_t* hi, uint16_t* lo, long long zrows, int L, int Lk,
+                        float scale, cudaStream_t st);
+
+int launch_dec_reduce_ln(const float* partials, int ks, long long zstride, const float* bias, const float* residual, long long res_stride,
+                         const float* gamma, const float* beta, float eps, float* x_out, float* y, uint16_t* hi, uint16_t* lo, int rows, int d,
+                         cudaStream_t st);
+int launch_dec_reduce_act(const float* partials, int ks, long long zstride, const float* bias, uint16_t* hi, uint16_t* lo, int rows, int n,
+                          int gelu, cudaStream_t st);
+int launch_kv_store(const uint16_t* hi, const uint16_t* lo, void* kc, void* vc, int kv_bf16, int B, int Lp, int nrows, int H, int d, int Lmax,
+                    cudaStream_t st);
+int launch_dec_attn(const float* qkv_part, int ks, long long zstride, const float* bqkv, const float* y, const float* bias, int bias_ld,
+                    void* kc, void* vc, int kv_bf16, float* x1, const int* step_ptr, int B, int nc, int H, int d, int Lmax, float scale,
+                    cudaStream_t st);
+int launch_dec_sample(const float* part, int ks, long long zstride, int vpad, int V, float temperature, int top_k, int greedy,
+                      unsigned long long seed, const long long* forced, const int* fwd, long long* cam_idx, long long* tokens_out, float* trace,
+                      float* probs_out, const int* step_ptr, int B, int n_img, int hw, int ncam, cudaStream_t st);
+int launch_dec_advance(int* step, cudaStream_t st);
+
+}  // namespace bevgen

@@ -1,6 +1,7 @@
 // Stage-2 transformer helper kernels (HBM-bound, coalesced): input-embedding assembly, LayerNorm (+ bf16 split),
 // masked/biased attention softmax.  The GEMMs and attention products run in gemm_tc.cu / attn kernels.
 #include "common.cuh"
+#include "kernels.cuh"
 
 namespace bevgen {
 
@@ -70,30 +71,10 @@ int launch_layernorm(const float* x, const float* gamma, const float* beta, floa
 //                with j = forward_shuffle_idx[s - n_cond]  (position embedding is added BEFORE the permutation)
 //   pad row   :  x_tok_emb[vocab]
 // ------------------------------------------------------------------------------------------------
-struct EmbedParams {
-  const long long* cam_idx;    // [B][ncam][hw]
-  const long long* bev_idx;    // [B][nc]
-  const float* I_inv;          // [B][ncam][3][3]
-  const float* E_inv;          // [B][ncam][4][4]
-  const float* x_tok_emb;      // [vocab+1][d]
-  const float* cond_tok_emb;   // [cond_vocab][d]
-  const float* x_pos_emb;      // [n_img][d]
-  const float* cond_static;    // [nc][d]
-  const float* img_embed_w;    // [d][4] or null
-  const float* cam_embed_w;    // [d][4] or null
-  const int* fwd;              // [n_img]
-  const float* pixel;          // [hw][3]
-  float* out;                  // [B][out_rows][d]
-  int B, ncam, hw, nc, n_img, L, d, vocab;
-  int pad_last;                // teacher forcing: the last (cam,h,w) token is replaced by PAD (:328-329)
-  int bev_embed;               // subtract sum_cam c_embed on cond rows
-  int row0, nrows;             // sequence rows [row0, row0+nrows) are produced; out row index = s - row0
-};
-
 __global__ void __launch_bounds__(128) embed_kernel(const EmbedParams p) {
   __shared__ float red[4];
   const int b = blockIdx.y;
-  const int s = p.row0 + blockIdx.x;
+  const int s = (p.step_ptr != nullptr ? p.nc + *p.step_ptr - 1 : p.row0) + blockIdx.x;
   float* out = p.out + ((size_t)b * p.nrows + blockIdx.x) * p.d;
   const int tid = threadIdx.x;
   if (s >= p.nc + p.n_img) {  // pad rows

@@ -5,6 +5,7 @@
 // tensor-core operands here): CTA = 64 rows x 128 codes per sweep, 256 threads as 16x16, 4 rows x 8 codes per
 // thread, running (min, argmin) kept per row and merged across the 16 lanes sharing a row with warp shuffles.
 #include "common.cuh"
+#include "kernels.cuh"
 
 namespace bevgen {
 

@@ -1,0 +1,196 @@
+"""KV-cache autoregressive sampler for the stage-2 transformer (the B200-native replacement of the reference's
+O(L^2)-per-token loop, Net2NetTransformer.sample, modules/stage2/cond_transformer_multi_view.py:154-227).
+
+Equivalence (checked by tests/test_decode_gpu.py against the reference's own outputs): with the closed-form
+mask allowed(i,j) = (j < n_cond) or (i >= n_cond and j <= i), the 256 conditioning rows only see each other, so they are
+prefilled once; every generated token then needs one new row attending to the cached keys with one camera-bias row.
+
+Per step (captured once as a CUDA graph and replayed 1535 times, the step counter lives in device memory):
+  embed(row) -> [reduce+LayerNorm] -> 24 x { swap-AB tcgen05 GEMM (Wqkv) -> decode attention (append K/V, softmax, P.V, +residual)
+  -> LayerNorm -> GEMM (W1) -> reduce+GELU -> GEMM (W2) -> reduce+bias+residual+LayerNorm } -> GEMM (head) -> top-k sample.
+The weight GEMMs stream each weight matrix exactly once per step (HBM-bound: weights are the 128-row MMA operand, the 16
+batch rows are the N=16 operand); split-K spreads every matrix over ~100 CTAs.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib, ops
+from .ops import EmbedArgs, _ptr, _stream
+
+
+def _kslice(K):
+    for k in (256, 128, 64):
+        if K % k == 0:
+            return k
+    raise ValueError(f"reduction length {K} is not a multiple of 64")
+
+
+class GPTSampler:
+    def __init__(self, engine, batch_size, kv_dtype=None):
+        self.eng = e = engine
+        if not e.causal:
+            raise NotImplementedError("KV-cache decoding needs the [cond | causal] mask (causal_order=True, no pad tokens)")
+        self.B = B = batch_size
+        self.Bp = ((B + 15) // 16) * 16
+        dev, d, H = e.dev, e.d, e.H
+        self.kv_bf16 = int((kv_dtype or (torch.float32 if e.npass == 3 else torch.bfloat16)) == torch.bfloat16)
+        kvt = torch.bfloat16 if self.kv_bf16 else torch.float32
+        nl = len(e.layers)
+        self.Lmax = e.L
+        self.kc = [torch.zeros((B, H, 64, self.Lmax), dtype=kvt, device=dev) for _ in range(nl)]
+        self.vc = [torch.zeros((B, H, self.Lmax, 64), dtype=kvt, device=dev) for _ in range(nl)]
+        self.step = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.cam_idx = torch.full((B, e.cfg.num_cams, e.cfg.num_cam_tokens), e.cfg.vocab_size, dtype=torch.int64, device=dev)
+        self.tokens = torch.zeros((B, e.n_img), dtype=torch.int64, device=dev)
+        f32 = lambda *s: torch.zeros(s, dtype=torch.float32, device=dev)
+        self.xrow, self.y, self.x1 = f32(B, 1, d), f32(self.Bp, d), f32(self.Bp, d)
+        pl = lambda n: (torch.zeros((self.Bp, n), dtype=torch.bfloat16, device=dev),
+                        torch.zeros((self.Bp, n), dtype=torch.bfloat16, device=dev) if e.npass == 3 else None)
+        self.yp, self.zp, self.hp, self.fp = pl(d), pl(d), pl(4 * d), pl(d)
+        self.vpad = e.whead[0].shape[0]
+        ks = lambda K: K // _kslice(K)
+        self.ks_d, self.ks_4d = ks(d), ks(4 * d)
+        self.part_qkv = f32(self.ks_d, self.Bp, 3 * d)
+        self.part_h = f32(self.ks_d, self.Bp, 4 * d)
+        self.part_o = f32(self.ks_4d, self.Bp, d)
+        self.part_v = f32(self.ks_d, self.Bp, self.vpad)
+        self.bias_cc = None if e.bias is None else e.bias[: e.nc, : e.nc].contiguous()
+        self.mask_cc = e.mask_u8[: e.nc, : e.nc].contiguous()
+        self.graph = None
+        self._graph_key = None
+        self.trace = None
+
+    # ------------------------------------------------------------------ launches
+    def _gemm_t(self, w, xp, n_out, K, part):
+        """partials[z][b][n] = sum_{k in slice z} W[n][k] x[b][k]  — weights are the 128-row (M) operand, batch the N=16 operand."""
+        kk = _kslice(K)
+        ops.gemm_tc(a_hi=w[0], a_lo=w[1], a_dims=(1, 1, w[0].shape[0], K), b_hi=xp[0], b_lo=xp[1], k=kk, n_cols=self.B, a_c_zstride=kk,
+                    b_k_zstride=kk, z_inner=K // kk, out_w=n_out, out_zi_stride=self.Bp * n_out, ldc=n_out, out_f32=part,
+                    flags=ops.GF_OUT_T, bn=16, npass=self.eng.npass, algo_flops=2.0 * self.B * n_out * K)
+
+    def _reduce_ln(self, part, ks, bias, residual, res_stride, ln, y, planes, rows=None, x_out=None):
+        lib = _lib.init()
+        ops.Stats.launches += 1
+        d = self.eng.d
+        zs = 0 if part is None else part.shape[1] * part.shape[2]
+        _lib.check(lib.bevgen_dec_reduce_ln(_ptr(part), ks, zs, _ptr(bias), _ptr(residual), res_stride, _ptr(ln[0]), _ptr(ln[1]), 1e-5, _ptr(x_out),
+                                            _ptr(y), _ptr(planes[0]) if planes else None, _ptr(planes[1]) if planes else None,
+                                            self.B if rows is None else rows, d, _stream()), "dec_reduce_ln")
+
+    def _sample(self, temperature, top_k, greedy, seed, forced):
+        lib, e = _lib.init(), self.eng
+        ops.Stats.launches += 2
+        _lib.check(lib.bevgen_sample_topk(_ptr(self.part_v), self.ks_d, self.Bp * self.vpad, self.vpad, e.vocab, float(temperature),
+                                          int(top_k or 0), int(greedy), C.c_ulonglong(seed), _ptr(forced), _ptr(e.fwd), _ptr(self.cam_idx),
+                                          _ptr(self.tokens), _ptr(self.trace), None, _ptr(self.step), self.B, e.n_img, e.cfg.num_cam_tokens,
+                                          e.cfg.num_cams, _stream()), "sample_topk")
+        _lib.check(lib.bevgen_dec_advance(_ptr(self.step), _stream()), "dec_advance")
+
+    def _embed_args(self, bev_idx, batch):
+        e = self.eng
+        a = EmbedArgs()
+        self._keep = [bev_idx, batch["intrinsics_inv"], batch["extrinsics_inv"]]
+        a.cam_idx, a.bev_idx = self.cam_idx.data_ptr(), bev_idx.data_ptr()
+        a.intrinsics_inv, a.extrinsics_inv = batch["intrinsics_inv"].data_ptr(), batch["extrinsics_inv"].data_ptr()
+        a.x_tok_emb, a.cond_tok_emb = e.x_tok_emb.data_ptr(), e.cond_tok_emb.data_ptr()
+        a.x_pos_emb, a.cond_static = e.x_pos_emb.data_ptr(), e.cond_static.data_ptr()
+        a.img_embed_w = e.img_w.data_ptr() if e.image_embed else None
+        a.cam_embed_w = e.cam_w.data_ptr() if e.image_embed else None
+        a.forward_shuffle_idx, a.pixel, a.out = e.fwd.data_ptr(), e.pixel.data_ptr(), self.xrow.data_ptr()
+        a.step_ptr = self.step.data_ptr()
+        a.B, a.ncam, a.hw, a.nc, a.n_img, a.L, a.d, a.vocab = self.B, e.cfg.num_cams, e.cfg.num_cam_tokens, e.nc, e.n_img, e.L, e.d, e.cfg.vocab_size
+        a.pad_last, a.bev_embed, a.row0, a.nrows = 0, int(e.bev_embed), 0, 1
+        return a
+
+    def _step(self, embed_args, temperature, top_k, greedy, seed, forced):
+        """One decode step (graph-capturable: no allocation, no host sync, step counter read on the device)."""
+        e, lib = self.eng, _lib.init()
+        d, H = e.d, e.H
+        ops.embed_assemble(embed_args)
+        self._reduce_ln(None, 0, None, self.xrow, d, e.layers[0]["ln1"], self.y, self.yp)
+        for li, lw in enumerate(e.layers):
+            self._gemm_t(lw["wqkv"], self.yp, 3 * d, d, self.part_qkv)
+            ops.Stats.launches += 1
+            _lib.check(lib.bevgen_dec_attention(_ptr(self.part_qkv), self.ks_d, self.Bp * 3 * d, _ptr(lw["bqkv"]), _ptr(self.y), _ptr(e.bias), e.L,
+                                                _ptr(self.kc[li]), _ptr(self.vc[li]), self.kv_bf16, _ptr(self.x1), _ptr(self.step), self.B, e.nc, H,
+                                                d, self.Lmax, float(e.dh) ** -0.5, _stream()), "dec_attention")
+            self._reduce_ln(None, 0, None, self.x1, d, lw["ln2"], None, self.zp)
+            self._gemm_t(lw["w1"], self.zp, 4 * d, d, self.part_h)
+            ops.Stats.launches += 1
+            _lib.check(lib.bevgen_dec_reduce_act(_ptr(self.part_h), self.ks_d, self.Bp * 4 * d, _ptr(lw["b1"]), 1, _ptr(self.hp[0]), _ptr(self.hp[1]),
+                                                 self.B, 4 * d, _stream()), "dec_reduce_act")
+            self._gemm_t(lw["w2"], self.hp, d, 4 * d, self.part_o)
+            last = li == len(e.layers) - 1
+            nxt = e.ln_f if last else e.layers[li + 1]["ln1"]
+            self._reduce_ln(self.part_o, self.ks_4d, lw["b2"], self.x1, d, nxt, None if last else self.y, self.fp if last else self.yp)
+        self._gemm_t(e.whead, self.fp, self.vpad, d, self.part_v)
+        self._sample(temperature, top_k, greedy, seed, forced)
+
+    # ------------------------------------------------------------------ prefill
+    def _prefill(self, bev_idx, batch):
+        e = self.eng
+        B, nc, d = self.B, e.nc, e.d
+        x = e.embed(self.cam_idx, bev_idx, batch, sampling=True, row0=0, nrows=nc)
+        lib = _lib.init()
+        for li, lw in enumerate(e.layers):
+            def store(qkv, li=li):
+                ops.Stats.launches += 1
+                _lib.check(lib.bevgen_kv_store(_ptr(qkv[0]), _ptr(qkv[1]), _ptr(self.kc[li]), _ptr(self.vc[li]), self.kv_bf16, B, nc, nc, e.H, d,
+                                               self.Lmax, _stream()), "kv_store")
+            x = e.block(x, lw, B, nc, attn_kw=dict(bias=self.bias_cc, mask=self.mask_cc, causal=False, allowed=float(nc * nc)), on_qkv=store)
+        # logits of decode-order token 0 come from the last conditioning row (mingpt_sparse.py:390)
+        self._last = x
+        self._reduce_ln(None, 0, None, x.view(-1)[(nc - 1) * d:], nc * d, e.ln_f, None, self.fp)
+        self._gemm_t(e.whead, self.fp, self.vpad, d, self.part_v)
+
+    # ------------------------------------------------------------------ public
+    @torch.no_grad()
+    def sample(self, bev_idx, batch, temperature=1.0, top_k=None, greedy=False, seed=0, forced_tokens=None, steps=None,
+               trace_logits=False, use_graph=True):
+        """-> tokens int64 (B, num_cams, cam_tokens) [, logits trace (steps, B, vocab)].  forced_tokens (B, n_img) in decode
+        order turns this into a teacher-forced replay (the sampled token is replaced, logits are still traced)."""
+        e = self.eng
+        dev = e.dev
+        steps = e.n_img if steps is None else steps
+        bev_idx = bev_idx.to(dev, torch.int64).contiguous()
+        batch = {k: batch[k].to(dev, torch.float32).contiguous() for k in ("intrinsics_inv", "extrinsics_inv")}
+        forced = None if forced_tokens is None else forced_tokens.to(dev, torch.int64).contiguous()
+        self.trace = torch.zeros((e.n_img, self.B, e.vocab), dtype=torch.float32, device=dev) if trace_logits else None
+        self.cam_idx.fill_(e.cfg.vocab_size)
+        self.step.zero_()
+        self._prefill(bev_idx, batch)
+        self._sample(temperature, top_k, greedy, seed, forced)           # token 0; step -> 1
+        args = self._embed_args(bev_idx, batch)
+        key = (bev_idx.data_ptr(), batch["intrinsics_inv"].data_ptr(), batch["extrinsics_inv"].data_ptr(), float(temperature), top_k, greedy,
+               seed, None if forced is None else forced.data_ptr(), None if self.trace is None else self.trace.data_ptr())
+        done = 1
+        if steps > 1:
+            self._step(args, temperature, top_k, greedy, seed, forced)    # eager step 1 (also warms every kernel variant up)
+            done = 2
+        if use_graph and steps > done:
+            if self.graph is None or self._graph_key != key:
+                self._hold = (bev_idx, batch, forced, self.trace)         # keep the captured buffers alive
+                g = torch.cuda.CUDAGraph()
+                snap = (self.step.clone(), self.cam_idx.clone(), self.tokens.clone())
+                with torch.cuda.graph(g):
+                    self._step(args, temperature, top_k, greedy, seed, forced)
+                # capture does not execute, but be safe if a driver replays it: restore the state
+                self.step.copy_(snap[0]); self.cam_idx.copy_(snap[1]); self.tokens.copy_(snap[2])
+                self.graph, self._graph_key = g, key
+            for _ in range(done, steps):
+                self.graph.replay()
+        else:
+            for _ in range(done, steps):
+                self._step(args, temperature, top_k, greedy, seed, forced)
+        out = self.cam_idx.clone()
+        return (out, self.trace[:steps]) if trace_logits else out
+
+    def bytes_per_batch(self, steps=None):
+        """Algorithmic HBM bytes of one full sample(): weights streamed once per step + KV cache reads."""
+        e = self.eng
+        steps = e.n_img if steps is None else steps
+        wbytes = (2 if e.npass == 1 else 4) * (len(e.layers) * 12 * e.d * e.d + e.vocab * e.d)
+        kvb = 2 if self.kv_bf16 else 4
+        kv = sum(len(e.layers) * 2 * (e.nc + t) * e.d * kvb for t in range(1, steps)) * self.B
+        return wbytes * steps + kv

@@ -126,28 +126,33 @@ class GPTEngine:
         ops.embed_assemble(a)
         return out
 
-    def attention(self, qkv, y, B, L):
-        """qkv planes [B, L, 3d]; returns x1 = y + concat_heads(softmax(scale*(QK^T + bias))V) as fp32 [B, L, d]."""
+    def attention(self, qkv, y, B, L, bias="full", mask=None, causal=None, allowed=None):
+        """qkv planes [B, L, 3d]; returns x1 = y + concat_heads(softmax(scale*(QK^T + bias))V) as fp32 [B, L, d].
+        bias/mask default to the full-sequence camera bias and attention mask; the KV-cache prefill passes the cond x cond blocks."""
         d, H, dh = self.d, self.H, self.dh
+        bias = self.bias if isinstance(bias, str) else bias
+        mask = self.mask_u8 if mask is None else mask
+        causal = self.causal if causal is None else causal
+        allowed = self._allowed if allowed is None else allowed
         q_hi, q_lo = qkv
         flat = lambda t: None if t is None else t.view(B * L, 3 * d)
         S = torch.empty((B, H, L, L), dtype=torch.float32, device=self.dev)
-        cz = ops.GF_CAUSAL_SKIP if self.causal else 0
+        cz = ops.GF_CAUSAL_SKIP if causal else 0
         ops.gemm_tc(a_hi=q_hi, a_lo=q_lo, a_dims=(B, 1, L, 3 * d), b_hi=flat(q_hi), b_lo=flat(q_lo), k=dh, n_cols=L, a_c_zstride=dh,
                     b_k_off=d, b_k_zstride=dh, b_row_zstride=L, z_inner=H, z_outer=B, out_w=L, out_zo_stride=H * L * L,
                     out_zi_stride=L * L, ldc=L, out_f32=S, flags=cz, causal_ncond=self.nc, bn=128, npass=self.npass,
-                    algo_flops=2.0 * B * H * dh * self._allowed)
+                    algo_flops=2.0 * B * H * dh * allowed)
         p_hi, p_lo = self._planes((B, H, L, L))
-        ops.attn_softmax(S, self.bias, self.mask_u8, p_hi, p_lo, L, float(dh) ** -0.5)
+        ops.attn_softmax(S, bias, mask, p_hi, p_lo, L, float(dh) ** -0.5)
         x1 = torch.empty((B, L, d), dtype=torch.float32, device=self.dev)
-        kz = ops.GF_CAUSAL_KLIMIT if self.causal else 0
+        kz = ops.GF_CAUSAL_KLIMIT if causal else 0
         ops.gemm_tc(a_hi=p_hi, a_lo=p_lo, a_dims=(B * H, 1, L, L), b_hi=flat(q_hi), b_lo=flat(q_lo), k=L, n_cols=dh, a_n_mul=H, a_n_zstride=1,
                     b_k_off=2 * d, b_k_zstride=dh, b_row_zstride=L, z_inner=H, z_outer=B, out_w=L, out_zo_stride=L * d, out_zi_stride=dh,
                     ldc=d, residual=y, out_f32=x1, flags=ops.GF_B_MN | kz, causal_ncond=self.nc, bn=64, npass=self.npass,
-                    algo_flops=2.0 * B * H * dh * self._allowed)
+                    algo_flops=2.0 * B * H * dh * allowed)
         return x1
 
-    def block(self, x, lw, B, L):
+    def block(self, x, lw, B, L, attn_kw=None, on_qkv=None):
         d = self.d
         rows = B * L
         y = torch.empty_like(x)
@@ -155,7 +160,9 @@ class GPTEngine:
         ops.layernorm(x, *lw["ln1"], y=y, out_hi=yp[0], out_lo=yp[1])
         qkv = self._planes((B, L, 3 * d))
         self._linear(yp, lw["wqkv"], 3 * d, rows, d, bias=lw["bqkv"], out_planes=qkv)
-        x1 = self.attention(qkv, y, B, L)
+        if on_qkv is not None:
+            on_qkv(qkv)
+        x1 = self.attention(qkv, y, B, L, **(attn_kw or {}))
         zp = self._planes((rows, d))
         ops.layernorm(x1, *lw["ln2"], out_hi=zp[0], out_lo=zp[1])
         hp = self._planes((rows, 4 * d))

@@ -5,7 +5,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import (GF_B_MN, GF_CAUSAL_KLIMIT, GF_CAUSAL_SKIP, GF_GELU, GF_OUT_NCHW, PREP_IDENT, PREP_S2D, PREP_UP2,  # noqa: F401
+from ._lib import (GF_B_MN, GF_CAUSAL_KLIMIT, GF_CAUSAL_SKIP, GF_GELU, GF_OUT_NCHW, GF_OUT_T, PREP_IDENT, PREP_S2D, PREP_UP2,  # noqa: F401
                    EmbedArgs, GemmArgs)
 
 

@@ -35,6 +35,7 @@ extern "C" {
 #define BEVGEN_GF_OUT_NCHW 2    /* fp32 output stored [z][col][h][w] (tiny Cout, e.g. conv_out -> NCHW images) */
 #define BEVGEN_GF_B_MN 4        /* B operand is [k rows][n cols] in memory (V in P.V) */
 #define BEVGEN_GF_CAUSAL_SKIP 8 /* skip output tiles outside the [cond | causal] support (Q.K^T) */
+#define BEVGEN_GF_OUT_T 32 /* store D^T: out_f32[z][col][row] (swap-AB decode GEMMs, split-K partials; no bias/act/residual) */
 #define BEVGEN_GF_CAUSAL_KLIMIT 16 /* reduction over keys stops at max(ncond, last tile row + 1) (P.V) */
 
 /* prep modes */
@@ -130,6 +131,7 @@ typedef struct {
   const int* forward_shuffle_idx; /* [n_img] */
   const float* pixel;        /* [hw][3] image-plane grid */
   float* out;                /* [B][nrows][d] */
+  const int* step_ptr;       /* decode: device step counter s, first row = nc + s - 1 (overrides row0); NULL otherwise */
   int B, ncam, hw, nc, n_img, L, d, vocab;
   int pad_last, bev_embed;
   int row0, nrows;
@@ -140,6 +142,33 @@ BEVGEN_API int bevgen_embed_assemble(const bevgen_embed_args* args, void* stream
  * S fp32 [zrows][Lk] with zrows = batch*heads*L rows, bias fp32 [L][Lk] or NULL, mask uint8 [L][Lk]. */
 BEVGEN_API int bevgen_attn_softmax(const float* s, const float* bias, const unsigned char* mask, long long zrows, int L, int Lk, float scale,
                                    void* out_hi, void* out_lo, void* stream);
+
+/* ---------------------------------------------------------------- KV-cache autoregressive decode
+ * Replaces the per-token full forward of Net2NetTransformer.sample (modules/stage2/cond_transformer_multi_view.py:154-227)
+ * with the cached formulation of SURVEY.md §3.4.  All kernels read the step counter s from device memory (one CUDA graph
+ * is replayed per token): they process sequence row r = n_cond + s - 1 against keys 0..r and sample decode-order token s.
+ * The per-step weight GEMMs are bevgen_gemm_tc launches with BEVGEN_GF_OUT_T (swap-AB, split-K partials [ks][batch][n]). */
+
+/* x = residual + bias + sum_z partials[z]; x_out = x (optional); LayerNorm(x) -> y fp32 (optional) + bf16 planes (optional) */
+BEVGEN_API int bevgen_dec_reduce_ln(const float* partials, int ks, long long zstride, const float* bias, const float* residual,
+                                    long long residual_row_stride, const float* gamma, const float* beta, float eps, float* x_out, float* y,
+                                    void* out_hi, void* out_lo, int rows, int d, void* stream);
+/* planes[b][n] = act(bias[n] + sum_z partials[z][b][n]); gelu != 0 -> exact-erf GELU */
+BEVGEN_API int bevgen_dec_reduce_act(const float* partials, int ks, long long zstride, const float* bias, int gelu, void* out_hi, void* out_lo,
+                                     int rows, int n, void* stream);
+/* prefill: rows [0,nrows) of the fused qkv planes [batch][lp][3d] -> K cache [batch][heads][64][lmax], V cache [batch][heads][lmax][64] */
+BEVGEN_API int bevgen_kv_store(const void* qkv_hi, const void* qkv_lo, void* k_cache, void* v_cache, int kv_bf16, int batch, int lp, int nrows,
+                               int heads, int d, int lmax, void* stream);
+/* one decode row: finish q/k/v (+bias), append k/v, softmax(scale*(q.K + camera_bias[r][:])) V, x1 = y + heads concat */
+BEVGEN_API int bevgen_dec_attention(const float* qkv_partials, int ks, long long zstride, const float* qkv_bias, const float* y,
+                                    const float* camera_bias, int bias_ld, void* k_cache, void* v_cache, int kv_bf16, float* x1,
+                                    const int* step_ptr, int batch, int n_cond, int heads, int d, int lmax, float scale, void* stream);
+/* sampling tail (cond_transformer_multi_view.py:138-142,200-219): logits/T, top-k (ties kept), softmax, multinomial|greedy|forced */
+BEVGEN_API int bevgen_sample_topk(const float* logit_partials, int ks, long long zstride, int vpad, int vocab, float temperature, int top_k,
+                                  int greedy, unsigned long long seed, const long long* forced_tokens, const int* forward_shuffle_idx,
+                                  long long* cam_idx, long long* tokens_out, float* logits_trace, float* probs_out, const int* step_ptr, int batch,
+                                  int n_img, int hw, int ncam, void* stream);
+BEVGEN_API int bevgen_dec_advance(int* step_ptr, void* stream);
 
 #ifdef __cplusplus
 }
