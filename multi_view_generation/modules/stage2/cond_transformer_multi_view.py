@@ -1,0 +1,180 @@
+"""Net2NetTransformer under the reference's import path (reference modules/stage2/cond_transformer_multi_view.py:30-561).
+
+Inference surface only: forward / sample / encode_to_z / encode_to_c / decode_to_img / get_input / get_xc / shared_step /
+inference_step / log_images / test_step with the reference's signatures.  `sample` runs the KV-cache CUDA-graph sampler
+(bevgen_b200.gpt_decode) instead of 1536 full forwards; training hooks, wandb visualisations and bbox-weighted loss are out
+of scope.
+"""
+import logging
+import time
+from typing import Optional
+
+import torch
+import torch.nn.functional as F
+
+from multi_view_generation import utils
+from multi_view_generation.bev_utils import util
+from multi_view_generation.modules.transformer.permuter import Identity
+
+try:
+    import pytorch_lightning as pl
+    _Base = pl.LightningModule
+except Exception:  # pragma: no cover
+    _Base = torch.nn.Module
+
+log = logging.getLogger(__name__)
+
+
+def disabled_train(self, mode=True):
+    return self
+
+
+class Net2NetTransformer(_Base):
+    def __init__(self, transformer, first_stage, cond_stage, permuter=None, ckpt_path=None, ignore_keys=[], unfrozen_keys=[],
+                 first_stage_key="image", cond_stage_key="segmentation", downsample_cond_size=-1, pkeep=1.0, sos_token=0,
+                 unconditional=False, skip_sampling: bool = False, bbox_ce_weight: float = 0.0, reset_random_mask: int = 0,
+                 debug_viz: bool = False, partial_decoding: Optional[int] = None, bbox_weight_epoch: int = -1,
+                 top_k: Optional[int] = None, warmup_steps: int = 500, lr_decay: bool = False, **kwargs):
+        super().__init__()
+        for k, v in kwargs.items():           # the reference setattr()s every unknown kwarg (:58-61)
+            if k != "self":
+                setattr(self, k, v)
+        self.be_unconditional, self.sos_token = unconditional, sos_token
+        self.first_stage_key, self.cond_stage_key = first_stage_key, cond_stage_key
+        self.skip_sampling, self.bbox_ce_weight, self.reset_random_mask = skip_sampling, bbox_ce_weight, reset_random_mask
+        self.debug_viz, self.partial_decoding, self.bbox_weight_epoch = debug_viz, partial_decoding, bbox_weight_epoch
+        self.top_k, self.lr_decay, self.warmup_steps = top_k, lr_decay, warmup_steps
+        self.first_stage_model = self._freeze(first_stage)
+        self.cond_stage_model = self._freeze(cond_stage)
+        self.transformer = transformer
+        self.cfg = self.transformer.cfg
+        self.permuter = Identity() if permuter is None else permuter
+        if ckpt_path is not None:
+            utils.init_from_ckpt(self, ckpt_path, ignore_keys=ignore_keys, unfrozen_keys=unfrozen_keys)
+        self.downsample_cond_size, self.pkeep = downsample_cond_size, pkeep
+        self.sample_seed = None               # set to an int for reproducible sampling; default draws from torch's RNG
+
+    @staticmethod
+    def _freeze(model):
+        model = model.eval()
+        model.train = disabled_train.__get__(model)
+        return model
+
+    def expand_all_images(self, arr):
+        return arr.reshape(-1, self.cfg.num_cams, *arr.shape[1:])
+
+    def combine_all_images(self, arr):
+        return arr.reshape(-1, *arr.shape[2:])
+
+    # ---------------------------------------------------------------- forward / sample
+    @torch.no_grad()
+    def forward(self, x, c, batch):
+        _, z_indices = self.encode_to_z(x, batch)
+        _, c_indices = self.encode_to_c(c, batch)
+        z_indices = self.expand_all_images(z_indices)
+        target = z_indices.reshape(z_indices.shape[0], -1).clone()
+        logits = self.transformer(z_indices, c_indices, batch, sampling=False)
+        return logits.contiguous(), target.contiguous()
+
+    def top_k_logits(self, logits, k):
+        v, _ = torch.topk(logits, k)
+        out = logits.clone()
+        out[out < v[..., [-1]]] = -float("Inf")
+        return out
+
+    @torch.no_grad()
+    def inference_step(self, batch):
+        if not hasattr(self, "z_indices"):
+            x, c = self.get_xc(batch)
+            _, self.c_indices = self.encode_to_c(c.to(self._dev()), batch)
+            self.z_indices = torch.full((c.shape[0], self.cfg.num_cams, self.cfg.num_cam_tokens), self.cfg.vocab_size, dtype=torch.int64,
+                                        device=self._dev())
+        return self.transformer(self.z_indices, self.c_indices, batch, sampling=False)
+
+    @torch.no_grad()
+    def sample(self, x, c, batch, temperature=1.0, sample=False, top_k=None, callback=lambda k: None, partial_decoding_idx=None):
+        """-> LongTensor (B, num_cams, cam_tokens).  Only x.shape[0] of `x` is used (as in the reference, :157)."""
+        B = x.shape[0]
+        if self.skip_sampling:
+            return torch.zeros((B, self.cfg.num_cams, self.cfg.num_cam_tokens), dtype=torch.int64, device=c.device)
+        if partial_decoding_idx is not None:
+            raise NotImplementedError("partial decoding (conditioning on ground-truth cameras) is not implemented yet")
+        assert not self.transformer.training
+        seed = self.sample_seed if self.sample_seed is not None else int(torch.randint(0, 2 ** 62, (1,)).item())
+        out = self.transformer.sampler(B).sample(c, batch, temperature=temperature, top_k=top_k, greedy=not sample, seed=seed)
+        assert out.max() < self.cfg.vocab_size
+        return out
+
+    # ---------------------------------------------------------------- stage-1 plumbing
+    def _dev(self):
+        return self.transformer.head.weight.device
+
+    @torch.no_grad()
+    def encode_to_z(self, x, batch):
+        quant_z, _, info = self.first_stage_model.encode(x, batch)
+        indices = self.permuter(info[2].view(quant_z.shape[0], -1))
+        return quant_z, indices
+
+    @torch.no_grad()
+    def encode_to_c(self, c, batch):
+        if self.downsample_cond_size > -1:
+            c = F.interpolate(c, size=(self.downsample_cond_size, self.downsample_cond_size))
+        quant_c, _, [_, _, indices] = self.cond_stage_model.encode(c, batch)
+        return quant_c, indices.view(c.shape[0], -1)
+
+    @torch.no_grad()
+    def decode_to_img(self, index, zshape):
+        index = self.permuter(index, reverse=True)
+        bhwc = (zshape[0], zshape[2], zshape[3], zshape[1])
+        return self.first_stage_model.decode_indices(index.reshape(-1), bhwc)      # get_codebook_entry + decode, NHWC throughout
+
+    def get_input(self, key, batch):
+        x = batch[key]
+        if x.dtype == torch.double or x.dtype == torch.uint8:
+            x = x.float()
+        x = x.movedim(-1, -3)                                   # ... h w c -> ... c h w
+        if key == "image":
+            if len(x.shape) == 4:
+                x = x[None, ...]
+            x = self.combine_all_images(x)
+        return x.contiguous()
+
+    def get_xc(self, batch, N=None):
+        x, c = self.get_input(self.first_stage_key, batch), self.get_input(self.cond_stage_key, batch)
+        if N is not None:
+            x, c = x[:N], c[:N]
+        return x, c
+
+    @torch.no_grad()
+    def shared_step(self, batch, batch_idx=0, inference=False):
+        if self.bbox_ce_weight > 0:
+            raise NotImplementedError("bbox-weighted cross entropy is a training-only path")
+        x, c = self.get_xc(batch)
+        logits, target = self(x.to(self._dev()), c.to(self._dev()), batch)
+        return sum(F.cross_entropy(l.view(-1, l.shape[-1]), t.view(-1)) for l, t in zip(logits, target)) / len(logits)
+
+    def test_step(self, batch, batch_idx=0):
+        loss = self.shared_step(batch, batch_idx)
+        if hasattr(self, "log") and _Base is not torch.nn.Module:
+            self.log("test/loss", loss, prog_bar=True, on_step=False, on_epoch=True)
+        self.last_test_loss = loss
+        return self.log_images(batch, generate_only=True, top_k=self.top_k)
+
+    @torch.no_grad()
+    def log_images(self, batch, temperature=None, top_k=None, callback=None, generate_only=False, **kwargs):
+        """-> {'gen','rec','gt'} each (B, num_cams, 3, H, W) fp32 in [0,1] (reference :479-544, generate_only branch)."""
+        start = time.time()
+        dev = self._dev()
+        x, c = self.get_xc(batch)
+        x, c = x.to(dev), c.to(dev)
+        quant_z, z_indices = self.encode_to_z(x, batch)
+        _, c_indices = self.encode_to_c(c, batch)
+        zshape = quant_z.shape
+        rec = util.denormalize_tensor(self.decode_to_img(z_indices, zshape), keep_tensor=True)
+        index_sample = self.sample(self.expand_all_images(z_indices)[:, :0], c_indices, batch,
+                                   temperature=temperature if temperature is not None else 1.0, sample=True,
+                                   top_k=top_k if top_k is not None else 100)
+        gen = util.denormalize_tensor(self.decode_to_img(self.combine_all_images(index_sample), zshape), keep_tensor=True)
+        gt = util.denormalize_tensor(x, keep_tensor=True)
+        log.info("Generating images took %.3f s", time.time() - start)
+        return {"gen": self.expand_all_images(gen), "rec": self.expand_all_images(rec), "gt": self.expand_all_images(gt)}
