@@ -72,7 +72,8 @@ SIGNATURES = {
     "bevgen_dec_reduce_ln": (_i, [_vp, _i, _ll, _vp, _vp, _ll, _vp, _vp, _f, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     "bevgen_dec_reduce_act": (_i, [_vp, _i, _ll, _vp, _i, _vp, _vp, _i, _i, _vp]),
     "bevgen_kv_store": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
-    "bevgen_dec_attention": (_i, [_vp, _i, _ll, _vp, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp]),
+    "bevgen_dec_attention": (_i, [_vp, _i, _ll, _vp, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp]),
+    "bevgen_dec_attention_workspace_floats": (_i, [_i, _i]),
     "bevgen_sample_topk": (_i, [_vp, _i, _ll, _i, _i, _f, _i, _i, C.c_ulonglong, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "bevgen_dec_advance": (_i, [_vp, _vp]),
 }

@@ -247,11 +247,15 @@ BEVGEN_API int bevgen_kv_store(const void* qkv_hi, const void* qkv_lo, void* k_c
 
 BEVGEN_API int bevgen_dec_attention(const float* qkv_partials, int ks, long long zstride, const float* qkv_bias, const float* y,
                                     const float* camera_bias, int bias_ld, void* k_cache, void* v_cache, int kv_bf16, float* x1,
-                                    const int* step_ptr, int batch, int n_cond, int heads, int d, int lmax, float scale, void* stream) {
-  if (!qkv_partials || !qkv_bias || !y || !k_cache || !v_cache || !x1 || !step_ptr || ks < 1) return fail(BEVGEN_ERR_ARG, "dec_attention: bad args");
-  CHECK_LAUNCH(launch_dec_attn(qkv_partials, ks, zstride, qkv_bias, y, camera_bias, bias_ld, k_cache, v_cache, kv_bf16, x1, step_ptr, batch, n_cond,
-                               heads, d, lmax, scale, (cudaStream_t)stream), "dec_attention");
+                                    const int* step_ptr, float* workspace, unsigned int* counters, int batch, int n_cond, int heads, int d,
+                                    int lmax, float scale, void* stream) {
+  if (!qkv_partials || !qkv_bias || !y || !k_cache || !v_cache || !x1 || !step_ptr || !workspace || !counters || ks < 1)
+    return fail(BEVGEN_ERR_ARG, "dec_attention: bad args");
+  CHECK_LAUNCH(launch_dec_attn(qkv_partials, ks, zstride, qkv_bias, y, camera_bias, bias_ld, k_cache, v_cache, kv_bf16, x1, step_ptr, workspace,
+                               counters, batch, n_cond, heads, d, lmax, scale, (cudaStream_t)stream), "dec_attention");
 }
+
+BEVGEN_API int bevgen_dec_attention_workspace_floats(int batch, int heads) { return dec_attn_workspace_floats(batch, heads); }
 
 BEVGEN_API int bevgen_sample_topk(const float* logit_partials, int ks, long long zstride, int vpad, int vocab, float temperature, int top_k,
                                   int greedy, unsigned long long seed, const long long* forced_tokens, const int* forward_shuffle_idx,

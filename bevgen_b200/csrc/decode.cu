@@ -50,7 +50,16 @@ __global__ void __launch_bounds__(256) dec_reduce_ln_kernel(const float* __restr
       const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + c4);
       v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
     }
-    for (int z = 0; z < ks; ++z) {
+    int z = 0;
+    for (; z + 4 <= ks; z += 4) {       // 4 independent loads in flight
+      const float4 t0 = reinterpret_cast<const float4*>(partials + (z + 0) * zstride + (size_t)row * d)[c4];
+      const float4 t1 = reinterpret_cast<const float4*>(partials + (z + 1) * zstride + (size_t)row * d)[c4];
+      const float4 t2 = reinterpret_cast<const float4*>(partials + (z + 2) * zstride + (size_t)row * d)[c4];
+      const float4 t3 = reinterpret_cast<const float4*>(partials + (z + 3) * zstride + (size_t)row * d)[c4];
+      v.x += (t0.x + t1.x) + (t2.x + t3.x); v.y += (t0.y + t1.y) + (t2.y + t3.y);
+      v.z += (t0.z + t1.z) + (t2.z + t3.z); v.w += (t0.w + t1.w) + (t2.w + t3.w);
+    }
+    for (; z < ks; ++z) {
       const float4 t = reinterpret_cast<const float4*>(partials + z * zstride + (size_t)row * d)[c4];
       v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
     }
@@ -131,66 +140,146 @@ __global__ void __launch_bounds__(256) kv_store_kernel(const uint16_t* __restric
 }
 
 constexpr int DEC_MAXL = 2560;
+constexpr int DEC_SPLIT = 4;          // key-range splits per (batch, head): 4 x 256 CTAs keep every SM streaming the cache
+constexpr int DEC_WS = 68;            // floats per partial: m, l, pad, pad, o[64]
 
-// one CTA per (head, batch): finish q/k/v of the new row, append k/v, single-query attention over the cache with the
-// camera-bias row added BEFORE the 1/sqrt(d_head) scale, residual add:  x1 = y + concat_heads(softmax(...) V)
+template <typename T> struct KV2;
+template <> struct KV2<float> {
+  static __device__ __forceinline__ float2 load(const float* p) { return *reinterpret_cast<const float2*>(p); }
+};
+template <> struct KV2<__nv_bfloat16> {
+  static __device__ __forceinline__ float2 load(const __nv_bfloat16* p) {
+    const uint32_t u = *reinterpret_cast<const uint32_t*>(p);
+    return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+  }
+};
+
+// grid (heads, batch, DEC_SPLIT), 8 warps per CTA.  Every CTA finishes q for its (batch, head) from the split-K partials; the CTA
+// owning the newest key also finishes k/v and appends them to the cache.  The n keys are cut into DEC_SPLIT*8 contiguous
+// segments, one per warp; each warp runs an independent online-softmax pass over its segment, 32 keys at a time:
+// scores with thread = key (64 coalesced loads of the transposed K cache in flight per lane; camera-bias row added BEFORE
+// the 1/sqrt(d_head) scale), then P.V with lane = channel pair (32 row loads in flight per lane).  Warp partials are merged
+// in shared memory, CTA partials through a workspace by the last CTA to arrive per (batch, head) (flash-decoding with a
+// fused combine), which writes x1 = y + concat_heads(softmax(...) V).
 template <typename KVT>
-__global__ void __launch_bounds__(256) dec_attn_kernel(const float* __restrict__ qkv_part, int ks, long long zstride,
+__global__ void __launch_bounds__(256, 2) dec_attn_kernel(const float* __restrict__ qkv_part, int ks, long long zstride,
                                                        const float* __restrict__ bqkv, const float* __restrict__ y,
                                                        const float* __restrict__ bias, int bias_ld, KVT* __restrict__ kc,
                                                        KVT* __restrict__ vc, float* __restrict__ x1, const int* __restrict__ step_ptr,
-                                                       int nc, int H, int d, int Lmax, float scale) {
-  __shared__ float q[64], knew[64], vnew[64], red[8], opart[4][64];
-  __shared__ float sc[DEC_MAXL];
-  const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+                                                       float* __restrict__ ws, unsigned int* __restrict__ counters, int nc, int H, int d,
+                                                       int Lmax, float scale) {
+  __shared__ float q[64], knew[64], vnew[64];
+  __shared__ float wm[8], wl[8];
+  __shared__ float wo[8][64];
+  __shared__ unsigned int ticket;
+  const int h = blockIdx.x, b = blockIdx.y, sp = blockIdx.z, tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
   const int r = nc + *step_ptr - 1;
   const int n = r + 1;
+  const int seg = (n + DEC_SPLIT * 8 - 1) / (DEC_SPLIT * 8);
+  const int g0 = min(n, (sp * 8 + warp) * seg), g1 = min(n, g0 + seg);
+  const bool owns_new = (sp == DEC_SPLIT - 1);          // the last segment always contains key r
   const size_t bh = (size_t)b * H + h;
   if (tid < 192) {
     const int which = tid >> 6, c = tid & 63;
-    const int col = which * d + h * 64 + c;
-    float v = __ldg(bqkv + col);
-    for (int z = 0; z < ks; ++z) v += qkv_part[z * zstride + (size_t)b * 3 * d + col];
-    if (which == 0) q[c] = v;
-    else if (which == 1) { knew[c] = v; kv_store(kc + (bh * 64 + c) * Lmax + r, v); }
-    else { vnew[c] = v; kv_store(vc + (bh * Lmax + r) * 64 + c, v); }
+    if (which == 0 || owns_new) {
+      const int col = which * d + h * 64 + c;
+      float v = __ldg(bqkv + col);
+      for (int z = 0; z < ks; ++z) v += qkv_part[z * zstride + (size_t)b * 3 * d + col];
+      if (which == 0) q[c] = v;
+      else if (which == 1) { knew[c] = v; kv_store(kc + (bh * 64 + c) * Lmax + r, v); }
+      else { vnew[c] = v; kv_store(vc + (bh * Lmax + r) * 64 + c, v); }
+    }
   }
   __syncthreads();
   const KVT* kb = kc + bh * 64 * Lmax;
-  const float* brow = bias ? bias + (size_t)r * bias_ld : nullptr;
-  float m = -INFINITY;
-  for (int j = tid; j < n; j += 256) {
-    float dot = 0.f;
-    if (j < r) {
-#pragma unroll 16
-      for (int c = 0; c < 64; ++c) dot = fmaf(q[c], kv_load(kb + (size_t)c * Lmax + j), dot);
-    } else {
-#pragma unroll 16
-      for (int c = 0; c < 64; ++c) dot = fmaf(q[c], knew[c], dot);
-    }
-    const float s = (dot + (brow ? brow[j] : 0.f)) * scale;
-    sc[j] = s;
-    m = fmaxf(m, s);
-  }
-  m = block_max_256(m, red);
-  float sum = 0.f;
-  for (int j = tid; j < n; j += 256) {
-    const float e = expf(sc[j] - m);
-    sc[j] = e;
-    sum += e;
-  }
-  sum = block_sum_256(sum, red);     // includes the __syncthreads that publishes sc[]
-  const int g = tid >> 6, c = tid & 63;
   const KVT* vb = vc + bh * (size_t)Lmax * 64;
-  float acc = 0.f;
-  for (int j = g; j < r; j += 4) acc = fmaf(sc[j], kv_load(vb + (size_t)j * 64 + c), acc);
-  if (g == (r & 3)) acc = fmaf(sc[r], vnew[c], acc);
-  opart[g][c] = acc;
+  const float* brow = bias ? bias + (size_t)r * bias_ld : nullptr;
+  float m = -INFINITY, l = 0.f;
+  float2 acc = make_float2(0.f, 0.f);
+  for (int base = g0; base < g1; base += 32) {
+    const int j = base + lane;
+    float sv = -INFINITY;
+    if (j < g1) {
+      float dot = 0.f;
+      if (j < r) {
+        float kv[64];
+#pragma unroll
+        for (int c = 0; c < 64; ++c) kv[c] = kv_load(kb + (size_t)c * Lmax + j);
+#pragma unroll
+        for (int c = 0; c < 64; ++c) dot = fmaf(q[c], kv[c], dot);
+      } else {
+#pragma unroll 16
+        for (int c = 0; c < 64; ++c) dot = fmaf(q[c], knew[c], dot);
+      }
+      sv = (dot + (brow ? brow[j] : 0.f)) * scale;
+    }
+    float tmax = sv;
+    for (int o = 16; o; o >>= 1) tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+    const float m_new = fmaxf(m, tmax);
+    const float corr = (m == -INFINITY) ? 0.f : expf(m - m_new);
+    const float p = (j < g1) ? expf(sv - m_new) : 0.f;
+    float psum = p;
+    for (int o = 16; o; o >>= 1) psum += __shfl_xor_sync(0xffffffffu, psum, o);
+    l = l * corr + psum;
+    acc.x *= corr; acc.y *= corr;
+    m = m_new;
+    const int cnt = min(32, g1 - base);
+    float2 vr[32];
+#pragma unroll
+    for (int t = 0; t < 32; ++t) {
+      const int jj = base + t;
+      vr[t] = make_float2(0.f, 0.f);
+      if (t < cnt) vr[t] = (jj < r) ? KV2<KVT>::load(vb + (size_t)jj * 64 + 2 * lane) : make_float2(vnew[2 * lane], vnew[2 * lane + 1]);
+    }
+#pragma unroll
+    for (int t = 0; t < 32; ++t) {
+      const float pj = __shfl_sync(0xffffffffu, p, t);
+      acc.x = fmaf(pj, vr[t].x, acc.x);
+      acc.y = fmaf(pj, vr[t].y, acc.y);
+    }
+  }
+  if (lane == 0) { wm[warp] = m; wl[warp] = l; }
+  wo[warp][2 * lane] = acc.x;
+  wo[warp][2 * lane + 1] = acc.y;
   __syncthreads();
+  float* wp = ws + (bh * DEC_SPLIT + sp) * DEC_WS;
   if (tid < 64) {
-    const float o = (opart[0][tid] + opart[1][tid]) + (opart[2][tid] + opart[3][tid]);
+    float M = wm[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) M = fmaxf(M, wm[w]);
+    float Ls = 0.f, o = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      const float sc_ = (wm[w] == -INFINITY) ? 0.f : expf(wm[w] - M);
+      Ls += wl[w] * sc_;
+      o += wo[w][tid] * sc_;
+    }
+    wp[4 + tid] = o;
+    if (tid == 0) { wp[0] = M; wp[1] = Ls; }
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) ticket = atomicAdd(&counters[bh], 1u);
+  __syncthreads();
+  if (ticket != DEC_SPLIT - 1) return;
+  __threadfence();
+  if (tid < 64) {
+    const volatile float* wv = ws + bh * DEC_SPLIT * DEC_WS;
+    float M = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < DEC_SPLIT; ++i) M = fmaxf(M, wv[i * DEC_WS]);
+    float Lsum = 0.f, o = 0.f;
+#pragma unroll
+    for (int i = 0; i < DEC_SPLIT; ++i) {
+      const float mi = wv[i * DEC_WS];
+      const float w = (mi == -INFINITY) ? 0.f : expf(mi - M);
+      Lsum += wv[i * DEC_WS + 1] * w;
+      o += wv[i * DEC_WS + 4 + tid] * w;
+    }
     const size_t idx = (size_t)b * d + h * 64 + tid;
-    x1[idx] = y[idx] + o / sum;
+    x1[idx] = y[idx] + o / Lsum;
+    if (tid == 0) counters[bh] = 0u;      // self-reset for the next launch
   }
 }
 
@@ -359,17 +448,19 @@ int launch_kv_store(const uint16_t* hi, const uint16_t* lo, void* kc, void* vc, 
   else kv_store_kernel<float><<<grid, 256, 0, st>>>(hi, lo, (float*)kc, (float*)vc, Lp, nrows, H, d, Lmax);
   return cudaGetLastError() == cudaSuccess ? BEVGEN_OK : BEVGEN_ERR_CUDA;
 }
+int dec_attn_workspace_floats(int B, int H) { return B * H * DEC_SPLIT * DEC_WS; }
+
 int launch_dec_attn(const float* qkv_part, int ks, long long zstride, const float* bqkv, const float* y, const float* bias, int bias_ld,
-                    void* kc, void* vc, int kv_bf16, float* x1, const int* step_ptr, int B, int nc, int H, int d, int Lmax, float scale,
-                    cudaStream_t st) {
-  if (Lmax > DEC_MAXL || B < 1 || B > 65535 || d != H * 64) return BEVGEN_ERR_ARG;
-  dim3 grid(H, B);
+                    void* kc, void* vc, int kv_bf16, float* x1, const int* step_ptr, float* ws, unsigned int* counters, int B, int nc, int H,
+                    int d, int Lmax, float scale, cudaStream_t st) {
+  if (Lmax > DEC_MAXL || B < 1 || B > 65535 || d != H * 64 || (Lmax & 3)) return BEVGEN_ERR_ARG;
+  dim3 grid(H, B, DEC_SPLIT);
   if (kv_bf16)
     dec_attn_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(qkv_part, ks, zstride, bqkv, y, bias, bias_ld, (__nv_bfloat16*)kc, (__nv_bfloat16*)vc, x1,
-                                                         step_ptr, nc, H, d, Lmax, scale);
+                                                         step_ptr, ws, counters, nc, H, d, Lmax, scale);
   else
-    dec_attn_kernel<float><<<grid, 256, 0, st>>>(qkv_part, ks, zstride, bqkv, y, bias, bias_ld, (float*)kc, (float*)vc, x1, step_ptr, nc, H, d,
-                                                 Lmax, scale);
+    dec_attn_kernel<float><<<grid, 256, 0, st>>>(qkv_part, ks, zstride, bqkv, y, bias, bias_ld, (float*)kc, (float*)vc, x1, step_ptr, ws,
+                                                 counters, nc, H, d, Lmax, scale);
   return cudaGetLastError() == cudaSuccess ? BEVGEN_OK : BEVGEN_ERR_CUDA;
 }
 int launch_dec_sample(const float* part, int ks, long long zstride, int vpad, int V, float temperature, int top_k, int greedy,

@@ -57,6 +57,8 @@ class GPTSampler:
         self.part_v = f32(self.ks_d, self.Bp, self.vpad)
         self.bias_cc = None if e.bias is None else e.bias[: e.nc, : e.nc].contiguous()
         self.mask_cc = e.mask_u8[: e.nc, : e.nc].contiguous()
+        self.attn_ws = f32(_lib.load().bevgen_dec_attention_workspace_floats(B, H))
+        self.attn_cnt = torch.zeros(B * H, dtype=torch.int32, device=dev)
         self.graph = None
         self._graph_key = None
         self.trace = None
@@ -113,8 +115,8 @@ class GPTSampler:
             self._gemm_t(lw["wqkv"], self.yp, 3 * d, d, self.part_qkv)
             ops.Stats.launches += 1
             _lib.check(lib.bevgen_dec_attention(_ptr(self.part_qkv), self.ks_d, self.Bp * 3 * d, _ptr(lw["bqkv"]), _ptr(self.y), _ptr(e.bias), e.L,
-                                                _ptr(self.kc[li]), _ptr(self.vc[li]), self.kv_bf16, _ptr(self.x1), _ptr(self.step), self.B, e.nc, H,
-                                                d, self.Lmax, float(e.dh) ** -0.5, _stream()), "dec_attention")
+                                                _ptr(self.kc[li]), _ptr(self.vc[li]), self.kv_bf16, _ptr(self.x1), _ptr(self.step), _ptr(self.attn_ws),
+                                                _ptr(self.attn_cnt), self.B, e.nc, H, d, self.Lmax, float(e.dh) ** -0.5, _stream()), "dec_attention")
             self._reduce_ln(None, 0, None, self.x1, d, lw["ln2"], None, self.zp)
             self._gemm_t(lw["w1"], self.zp, 4 * d, d, self.part_h)
             ops.Stats.launches += 1

@@ -159,10 +159,13 @@ BEVGEN_API int bevgen_dec_reduce_act(const float* partials, int ks, long long zs
 /* prefill: rows [0,nrows) of the fused qkv planes [batch][lp][3d] -> K cache [batch][heads][64][lmax], V cache [batch][heads][lmax][64] */
 BEVGEN_API int bevgen_kv_store(const void* qkv_hi, const void* qkv_lo, void* k_cache, void* v_cache, int kv_bf16, int batch, int lp, int nrows,
                                int heads, int d, int lmax, void* stream);
-/* one decode row: finish q/k/v (+bias), append k/v, softmax(scale*(q.K + camera_bias[r][:])) V, x1 = y + heads concat */
+/* one decode row: finish q/k/v (+bias), append k/v, softmax(scale*(q.K + camera_bias[r][:])) V, x1 = y + heads concat.
+ * workspace: bevgen_dec_attention_workspace_floats(batch, heads) floats; counters: batch*heads uint32 zero-initialised once. */
 BEVGEN_API int bevgen_dec_attention(const float* qkv_partials, int ks, long long zstride, const float* qkv_bias, const float* y,
                                     const float* camera_bias, int bias_ld, void* k_cache, void* v_cache, int kv_bf16, float* x1,
-                                    const int* step_ptr, int batch, int n_cond, int heads, int d, int lmax, float scale, void* stream);
+                                    const int* step_ptr, float* workspace, unsigned int* counters, int batch, int n_cond, int heads, int d,
+                                    int lmax, float scale, void* stream);
+BEVGEN_API int bevgen_dec_attention_workspace_floats(int batch, int heads);
 /* sampling tail (cond_transformer_multi_view.py:138-142,200-219): logits/T, top-k (ties kept), softmax, multinomial|greedy|forced */
 BEVGEN_API int bevgen_sample_topk(const float* logit_partials, int ks, long long zstride, int vpad, int vocab, float temperature, int top_k,
                                   int greedy, unsigned long long seed, const long long* forced_tokens, const int* forward_shuffle_idx,
