@@ -125,6 +125,7 @@ def main():
     ap.add_argument("--precision", default="fp32x3", choices=["fp32x3", "bf16"])
     ap.add_argument("--scenes", type=int, default=SCENES)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-stage2", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
@@ -153,17 +154,12 @@ def main():
     model = model.to(dev).eval()
     bcast_ms = 0.0
     if world > 1:
-        flat = torch.cat([p.data.reshape(-1) for p in model.parameters()])
+        from bevgen_b200.sharding import broadcast_module_weights
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        dist.broadcast(flat, src=0)
+        broadcast_module_weights(model, src=0)
         torch.cuda.synchronize()
         bcast_ms = (time.perf_counter() - t0) * 1e3
-        o = 0
-        for p in model.parameters():
-            p.data.copy_(flat[o:o + p.numel()].view_as(p))
-            o += p.numel()
-        del flat
 
     n_img = args.scenes * CAMS
     x_host = synth.image_batch(n_img, 3, RES, RES, seed=100 + rank).pin_memory()
@@ -269,6 +265,27 @@ def main():
                      "executed_mma_multiplier": 3 if args.precision == "fp32x3" else 1,
                      "kernel_share_of_step": gemm_ms / (ms / args.steps)},
     }
+    if world == 1 and not args.no_stage2:
+        try:   # BASELINE configs[2]/[3]: stage-2 teacher-forced forward and KV-cache sampling (reported beside the headline)
+            del model, x_dev
+            torch.cuda.empty_cache()
+            from tools.stage2_perf import run as stage2_run
+            r2 = stage2_run(args.precision, B=args.scenes)
+            hbm_peak = hbm
+            line["stage2"] = {
+                "forward_configs2": {"samples_per_s": r2["forward"]["samples_per_s"], "ms_per_batch": r2["forward"]["ms"], "batch": args.scenes,
+                                     "algorithmic_tflops": r2["forward"]["algorithmic_tflops"],
+                                     "attention_layer_ms": r2["attention_layer"]["ms"],
+                                     "attention_tflops_allowed_only": r2["attention_layer"]["allowed_tflops"],
+                                     "attention_tflops_dense_equiv": r2["attention_layer"]["dense_equiv_tflops"]},
+                "sample_configs3": {"images_per_s": r2["sample"]["images_per_s"], "ms_per_batch": r2["sample"]["ms"],
+                                    "ms_per_token_step": r2["sample"]["ms_per_token_step"],
+                                    "roofline": {"bound": "hbm", "achieved": r2["sample"]["achieved_GBps"], "peak": hbm_peak, "unit": "GB/s",
+                                                 "frac": r2["sample"]["achieved_GBps"] / hbm_peak,
+                                                 "algorithmic_GB_per_batch": r2["sample"]["algorithmic_GB"]}},
+                "note": "full-size GPT (24 layers, d=1024, 16 heads, L=1792); KV-cache sampling of 16 scenes x 1536 tokens, top_k=100"}
+        except Exception as ex:  # the headline line must still be printed
+            line["stage2"] = {"error": repr(ex)}
     if world == 1 and not args.no_cpu_baseline:
         rate, cores, sec = cpu_reference_rate(8)
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
