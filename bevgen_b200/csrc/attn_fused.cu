@@ -1,0 +1,327 @@
+// Fused stage-2 attention forward for sm_100a (replaces DeepSpeed's sdd -> bias add -> block-sparse softmax -> dsd chain,
+// modules/transformer/sparse_self_attention.py:153-176, and the scores tensor it materialises):
+//   O[b,i,h,:] = sum_j softmax_j( d_head^-1/2 * (Q_i.K_j + bias[i][j]) ) V_j  over allowed(i,j) = j < n_cond || (i >= n_cond && j <= i)
+//   x1 = y + concat_heads(O)                                  (Block.forward residual, mingpt_sparse.py:250)
+// One CTA per (batch, head, 128-query tile); flash-style loop over 128-key tiles, fully-masked tiles skipped.
+//   warp 0      TMA producer: Q once, K/V tiles through a 2-stage ring, all boxes (64 cols x 128 rows) of the fused qkv planes
+//   warp 1      tcgen05 issuer: S = Q.K^T into a double-buffered TMEM tile, PV = P.V (V read MN-major, no transpose) into a second
+//   warp 2      TMEM allocator
+//   warps 4-11  softmax: thread = (query row, 64-key half): tcgen05.ld S, + fp16 bias row, base-2 online softmax, P -> swizzled smem
+//               as the A operand of the PV MMA, running O kept in registers (rescaled on the fly), final normalise + residual store.
+// NPASS = 3 keeps fp32-equivalent accuracy (bf16x3 split products for both MMAs, P split into hi/lo); NPASS = 1 is plain bf16.
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace bevgen {
+
+constexpr int AT_BM = 128, AT_BN = 128, AT_DH = 64;
+constexpr int AT_TILE = AT_BM * AT_DH * 2;       // 16 KB: one (128 x 64) bf16 tile
+constexpr int AT_PTILE = AT_BM * AT_BN * 2;      // 32 KB: P (128 x 128) bf16
+constexpr int AT_THREADS = 384;
+
+template <int NPASS>
+struct AttnCfg {
+  static constexpr int NOPS = (NPASS == 3) ? 2 : 1;
+  static constexpr int Q_BYTES = NOPS * AT_TILE;
+  static constexpr int KV_STAGE = 2 * NOPS * AT_TILE;           // K + V
+  static constexpr int P_BYTES = NOPS * AT_PTILE;
+  static constexpr int SMEM = Q_BYTES + 2 * KV_STAGE + P_BYTES + 1024 + 256 + 128 * 2 * 4;
+};
+
+struct AttnParams {
+  CUtensorMap tm[2];        // hi, lo planes of qkv viewed as [B*L rows][3d cols], box (64, 128)
+  const __half* bias;       // [L][L] fp16 or null
+  const float* y;           // [B][L][d]
+  float* x1;                // [B][L][d]
+  int B, H, L, nc, d;
+  float scale_log2e;        // d_head^-1/2 * log2(e)
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+template <int NPASS>
+__global__ void __launch_bounds__(AT_THREADS, 1) attn_fused_kernel(const __grid_constant__ AttnParams p) {
+  using Cfg = AttnCfg<NPASS>;
+  constexpr int NOPS = Cfg::NOPS;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sQ = smem;
+  uint8_t* sKV = sQ + Cfg::Q_BYTES;
+  uint8_t* sP = sKV + 2 * Cfg::KV_STAGE;
+  uint64_t* bars = (uint64_t*)(sP + Cfg::P_BYTES);
+  uint64_t* q_full = bars;            // 1
+  uint64_t* k_full = bars + 1;        // 2
+  uint64_t* v_full = bars + 3;        // 2
+  uint64_t* kv_empty = bars + 5;      // 2
+  uint64_t* s_full = bars + 7;        // 2
+  uint64_t* s_empty = bars + 9;       // 2
+  uint64_t* p_full = bars + 11;       // 1
+  uint64_t* pv_done = bars + 12;      // 2
+  uint64_t* pv_empty = bars + 14;     // 2
+  uint32_t* tmem_slot = (uint32_t*)(bars + 16);
+  float* xmax = (float*)(bars + 32);  // [128 rows][2 halves]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nq = p.L / AT_BM;
+  // heavy (late) query tiles first
+  const int qt = nq - 1 - (int)(blockIdx.x / (p.B * p.H));
+  const int bh = blockIdx.x % (p.B * p.H);
+  const int b = bh / p.H, h = bh % p.H;
+  const int m0 = qt * AT_BM;
+  const int T = (m0 < p.nc) ? (p.nc / AT_BN) : (m0 / AT_BN + 1);
+  const int row0 = b * p.L;           // first row of this batch element in the [B*L, 3d] view
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tm[0]);
+    if (NPASS == 3) tma_prefetch_desc(&p.tm[1]);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&k_full[i], 1); mbar_init(&v_full[i], 1); mbar_init(&kv_empty[i], 1);
+      mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 8);
+      mbar_init(&pv_done[i], 1); mbar_init(&pv_empty[i], 8);
+    }
+    mbar_init(p_full, 8);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tS[2] = {tmem, tmem + 128}, tPV[2] = {tmem + 256, tmem + 320};
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(q_full, Cfg::Q_BYTES);
+#pragma unroll
+      for (int o = 0; o < NOPS; ++o) tma_load_2d(sQ + o * AT_TILE, &p.tm[o], q_full, h * AT_DH, row0 + m0);
+      for (int t = 0; t < T; ++t) {
+        const int s = t & 1;
+        mbar_wait(&kv_empty[s], ((t >> 1) & 1) ^ 1);
+        uint8_t* st = sKV + s * Cfg::KV_STAGE;
+        mbar_expect_tx(&k_full[s], NOPS * AT_TILE);
+#pragma unroll
+        for (int o = 0; o < NOPS; ++o) tma_load_2d(st + o * AT_TILE, &p.tm[o], &k_full[s], p.d + h * AT_DH, row0 + t * AT_BN);
+        mbar_expect_tx(&v_full[s], NOPS * AT_TILE);
+#pragma unroll
+        for (int o = 0; o < NOPS; ++o) tma_load_2d(st + (NOPS + o) * AT_TILE, &p.tm[o], &v_full[s], 2 * p.d + h * AT_DH, row0 + t * AT_BN);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc_bf16(AT_BM, AT_BN, 0, 0);
+      const uint32_t idesc_pv = make_idesc_bf16(AT_BM, AT_DH, 0, 1);
+      const uint32_t q_base = smem_u32(sQ), p_base = smem_u32(sP);
+      auto issue_s = [&](int t) {
+        const int s = t & 1;
+        mbar_wait(&k_full[s], (t >> 1) & 1);
+        mbar_wait(&s_empty[s], ((t >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t k_base = smem_u32(sKV + s * Cfg::KV_STAGE);
+#pragma unroll
+        for (int k = 0; k < AT_DH / 16; ++k) {
+          const uint64_t qh = make_sdesc_sw128(q_base + k * 32, 16, 1024), kh = make_sdesc_sw128(k_base + k * 32, 16, 1024);
+          if (NPASS == 3) {
+            const uint64_t ql = make_sdesc_sw128(q_base + AT_TILE + k * 32, 16, 1024), kl = make_sdesc_sw128(k_base + AT_TILE + k * 32, 16, 1024);
+            umma_bf16(tS[s], ql, kh, idesc_s, k == 0 ? 0u : 1u);
+            umma_bf16(tS[s], qh, kl, idesc_s, 1u);
+            umma_bf16(tS[s], qh, kh, idesc_s, 1u);
+          } else {
+            umma_bf16(tS[s], qh, kh, idesc_s, k == 0 ? 0u : 1u);
+          }
+        }
+        umma_commit(&s_full[s]);
+      };
+      mbar_wait(q_full, 0);
+      issue_s(0);
+      for (int t = 0; t < T; ++t) {
+        if (t + 1 < T) issue_s(t + 1);
+        const int s = t & 1;
+        mbar_wait(p_full, t & 1);
+        mbar_wait(&v_full[s], (t >> 1) & 1);
+        mbar_wait(&pv_empty[s], ((t >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t v_base = smem_u32(sKV + s * Cfg::KV_STAGE + NOPS * AT_TILE);
+#pragma unroll
+        for (int k = 0; k < AT_BN / 16; ++k) {
+          const uint32_t pa = p_base + (k >> 2) * AT_TILE + (k & 3) * 32;      // two 64-key chunks of 128 rows x 128 B
+          const uint64_t ph = make_sdesc_sw128(pa, 16, 1024), vh = make_sdesc_sw128(v_base + k * 2048, 8192, 1024);
+          if (NPASS == 3) {
+            const uint64_t pl = make_sdesc_sw128(pa + AT_PTILE, 16, 1024), vl = make_sdesc_sw128(v_base + AT_TILE + k * 2048, 8192, 1024);
+            umma_bf16(tPV[s], pl, vh, idesc_pv, k == 0 ? 0u : 1u);
+            umma_bf16(tPV[s], ph, vl, idesc_pv, 1u);
+            umma_bf16(tPV[s], ph, vh, idesc_pv, 1u);
+          } else {
+            umma_bf16(tPV[s], ph, vh, idesc_pv, k == 0 ? 0u : 1u);
+          }
+        }
+        umma_commit(&pv_done[s]);
+        umma_commit(&kv_empty[s]);
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== softmax / output warps =====================
+    const int sw = warp - 4;
+    const int quarter = warp & 3;                  // TMEM lane quarter accessible by this warp (warp index % 4)
+    const int half = sw >> 2;                      // which 64 keys of the 128-key tile / which 32 of the 64 output channels
+    const int row = quarter * 32 + lane;           // query row within the tile
+    const int gi = m0 + row;                       // sequence position
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    float o_acc[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) o_acc[c] = 0.f;
+    float m_run = -INFINITY, l_run = 0.f, corr_saved = 0.f;
+    const __half* brow = p.bias ? p.bias + (size_t)gi * p.L : nullptr;
+
+    for (int t = 0; t < T; ++t) {
+      const int s = t & 1;
+      const int n0 = t * AT_BN + half * 64;
+      // bias row chunk: 64 fp16 = 128 B, issued before waiting on the MMA
+      uint4 bq[8];
+      if (brow != nullptr) {
+        const uint4* bp = reinterpret_cast<const uint4*>(brow + n0);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) bq[u] = __ldg(bp + u);
+      }
+      mbar_wait(&s_full[s], (t >> 1) & 1);
+      tc_fence_after();
+      float tv[64];
+      {
+        uint32_t r0[32], r1[32];
+        tmem_ld_32x32(tS[s] + lane_off + half * 64, r0);
+        tmem_ld_32x32(tS[s] + lane_off + half * 64 + 32, r1);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { tv[j] = __uint_as_float(r0[j]); tv[32 + j] = __uint_as_float(r1[j]); }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[s]);
+      const bool diag = (m0 >= p.nc) && (t == T - 1);       // the only partially masked tile: n0 == m0, allowed iff key <= query
+      float mx = -INFINITY;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const __half2* hb = reinterpret_cast<const __half2*>(&bq[u]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int j = u * 8 + e * 2;
+          float2 bf = brow ? __half22float2(hb[e]) : make_float2(0.f, 0.f);
+          float a0 = (tv[j] + bf.x) * p.scale_log2e, a1 = (tv[j + 1] + bf.y) * p.scale_log2e;
+          if (diag) {
+            if (half * 64 + j > row) a0 = -INFINITY;
+            if (half * 64 + j + 1 > row) a1 = -INFINITY;
+          }
+          tv[j] = a0; tv[j + 1] = a1;
+          mx = fmaxf(mx, fmaxf(a0, a1));
+        }
+      }
+      // exchange the row maximum with the partner thread handling the other 64 keys
+      xmax[row * 2 + half] = mx;
+      named_bar_sync(1 + quarter, 64);
+      mx = fmaxf(mx, xmax[row * 2 + (half ^ 1)]);
+      named_bar_sync(1 + quarter, 64);                      // both partners have read before either slot is rewritten
+      const float m_new = fmaxf(m_run, mx);                 // finite: every row has key 0 (cond) allowed
+      const float corr = exp2f(m_run - m_new);              // 0 on the first tile
+      float psum = 0.f;
+#pragma unroll
+      for (int j = 0; j < 64; ++j) { tv[j] = exp2f(tv[j] - m_new); psum += tv[j]; }
+      l_run = l_run * corr + psum;
+      m_run = m_new;
+      // fold in the previous tile's P.V (also guarantees the PV MMA finished reading P from smem)
+      if (t > 0) {
+        const int sp = (t - 1) & 1;
+        mbar_wait(&pv_done[sp], ((t - 1) >> 1) & 1);
+        tc_fence_after();
+        uint32_t r[32];
+        tmem_ld_32x32(tPV[sp] + lane_off + half * 32, r);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&pv_empty[sp]);
+#pragma unroll
+        for (int c = 0; c < 32; ++c) o_acc[c] = o_acc[c] * corr_saved + __uint_as_float(r[c]);
+      }
+      corr_saved = corr;
+      // P -> smem, K-major SWIZZLE_128B: row r at r*128 B inside each 64-key chunk, 16-byte unit u stored at u ^ (r & 7)
+      {
+        uint8_t* prow = sP + half * AT_TILE + row * 128;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          uint32_t hh[4], ll[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            __nv_bfloat16 h0, l0, h1, l1;
+            split_bf16(tv[u * 8 + 2 * e], h0, l0);
+            split_bf16(tv[u * 8 + 2 * e + 1], h1, l1);
+            hh[e] = pack_bf16(h0, h1);
+            ll[e] = pack_bf16(l0, l1);
+          }
+          const int us = (u ^ (row & 7)) * 16;
+          *reinterpret_cast<uint4*>(prow + us) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+          if (NPASS == 3) *reinterpret_cast<uint4*>(prow + AT_PTILE + us) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+        }
+      }
+      fence_proxy_async();          // make the generic-proxy smem writes visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+    }
+    // last tile's P.V
+    {
+      const int sp = (T - 1) & 1;
+      mbar_wait(&pv_done[sp], ((T - 1) >> 1) & 1);
+      tc_fence_after();
+      uint32_t r[32];
+      tmem_ld_32x32(tPV[sp] + lane_off + half * 32, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < 32; ++c) o_acc[c] = o_acc[c] * corr_saved + __uint_as_float(r[c]);
+    }
+    // total row sum = own half + partner half
+    xmax[row * 2 + half] = l_run;
+    named_bar_sync(1 + quarter, 64);
+    const float inv = 1.0f / (l_run + xmax[row * 2 + (half ^ 1)]);
+    const size_t off = ((size_t)(b * p.L + gi)) * p.d + h * AT_DH + half * 32;
+    const float4* yp = reinterpret_cast<const float4*>(p.y + off);
+    float4* op = reinterpret_cast<float4*>(p.x1 + off);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const float4 yv = __ldg(yp + c);
+      op[c] = make_float4(yv.x + o_acc[4 * c] * inv, yv.y + o_acc[4 * c + 1] * inv, yv.z + o_acc[4 * c + 2] * inv, yv.w + o_acc[4 * c + 3] * inv);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem, 512);
+}
+
+template <int NPASS>
+static int launch_attn(const AttnParams& p, cudaStream_t st) {
+  using Cfg = AttnCfg<NPASS>;
+  auto kern = attn_fused_kernel<NPASS>;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess) return BEVGEN_ERR_CUDA;
+    configured = true;
+  }
+  kern<<<p.B * p.H * (p.L / AT_BM), AT_THREADS, Cfg::SMEM, st>>>(p);
+  return cudaGetLastError() == cudaSuccess ? BEVGEN_OK : BEVGEN_ERR_CUDA;
+}
+
+int launch_attn_fused(const CUtensorMap* tm_hi, const CUtensorMap* tm_lo, const void* bias_f16, const float* y, float* x1, int B, int H, int L,
+                      int nc, int d, float scale, int npass, cudaStream_t st) {
+  if (L % AT_BM != 0 || nc % AT_BN != 0 || nc < AT_BN || nc > L || d != H * AT_DH) return BEVGEN_ERR_ARG;
+  AttnParams p;
+  p.tm[0] = *tm_hi;
+  p.tm[1] = tm_lo ? *tm_lo : *tm_hi;
+  p.bias = (const __half*)bias_f16;
+  p.y = y; p.x1 = x1;
+  p.B = B; p.H = H; p.L = L; p.nc = nc; p.d = d;
+  p.scale_log2e = scale * 1.4426950408889634f;
+  return npass == 3 ? launch_attn<3>(p, st) : launch_attn<1>(p, st);
+}
+
+}  // namespace bevgen

@@ -222,6 +222,26 @@ BEVGEN_API int bevgen_attn_softmax(const float* s, const float* bias, const unsi
   CHECK_LAUNCH(launch_attn_softmax(s, bias, mask, (uint16_t*)out_hi, (uint16_t*)out_lo, zrows, L, Lk, scale, (cudaStream_t)stream), "attn_softmax");
 }
 
+BEVGEN_API int bevgen_attn_fused_fwd(const void* qkv_hi, const void* qkv_lo, int batch, int seq_len, int heads, int d, int n_cond,
+                                     const void* bias_f16, const float* y, float* x1, float scale, int npass, void* stream) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  if (!qkv_hi || !y || !x1 || (npass == 3 && !qkv_lo) || !(npass == 1 || npass == 3)) return fail(BEVGEN_ERR_ARG, "attn_fused_fwd: bad args");
+  if (seq_len % 128 != 0 || n_cond % 128 != 0 || n_cond < 128 || n_cond > seq_len || d != heads * 64)
+    return fail(BEVGEN_ERR_ARG, "attn_fused_fwd: needs seq_len, n_cond multiples of 128 and d_head = 64 (got L=%d nc=%d d=%d H=%d)", seq_len, n_cond, d, heads);
+  CUtensorMap tm[2];
+  const void* planes[2] = {qkv_hi, qkv_lo};
+  for (int o = 0; o < (npass == 3 ? 2 : 1); ++o) {
+    uint64_t dims[2] = {(uint64_t)3 * d, (uint64_t)batch * seq_len};
+    uint64_t strides[1] = {(uint64_t)3 * d * 2};
+    uint32_t box[2] = {64, 128};
+    rc = make_tmap(&tm[o], planes[o], 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  CHECK_LAUNCH(launch_attn_fused(&tm[0], npass == 3 ? &tm[1] : nullptr, bias_f16, y, x1, batch, heads, seq_len, n_cond, d, scale, npass,
+                                 (cudaStream_t)stream), "attn_fused_fwd");
+}
+
 /* ---------------------------------------------------------------- KV-cache decode */
 BEVGEN_API int bevgen_dec_reduce_ln(const float* partials, int ks, long long zstride, const float* bias, const float* residual,
                                     long long residual_row_stride, const float* gamma, const float* beta, float eps, float* x_out, float* y,

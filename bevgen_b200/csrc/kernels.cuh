@@ -61,6 +61,9 @@ int launch_embed(const EmbedParams& p, cudaStream_t st);
 int launch_attn_softmax(const float* S, const float* bias, const uint8_t* mask, uint16_t* hi, uint16_t* lo, long long zrows, int L, int Lk,
                         float scale, cudaStream_t st);
 
+int launch_attn_fused(const CUtensorMap* tm_hi, const CUtensorMap* tm_lo, const void* bias_f16, const float* y, float* x1, int B, int H, int L,
+                      int nc, int d, float scale, int npass, cudaStream_t st);
+
 int launch_dec_reduce_ln(const float* partials, int ks, long long zstride, const float* bias, const float* residual, long long res_stride,
                          const float* gamma, const float* beta, float eps, float* x_out, float* y, uint16_t* hi, uint16_t* lo, int rows, int d,
                          cudaStream_t st);

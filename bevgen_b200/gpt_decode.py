@@ -57,6 +57,9 @@ class GPTSampler:
         self.part_v = f32(self.ks_d, self.Bp, self.vpad)
         self.bias_cc = None if e.bias is None else e.bias[: e.nc, : e.nc].contiguous()
         self.mask_cc = e.mask_u8[: e.nc, : e.nc].contiguous()
+        full_cc = bool(self.mask_cc.all())      # cond rows see every cond column: the fused kernel's "all cond" case
+        self.bias_cc_f16 = (torch.zeros((e.nc, e.nc), dtype=torch.float16, device=dev) if self.bias_cc is None
+                            else self.bias_cc.to(torch.float16).contiguous()) if full_cc else None
         self.attn_ws = f32(_lib.load().bevgen_dec_attention_workspace_floats(B, H))
         self.attn_cnt = torch.zeros(B * H, dtype=torch.int32, device=dev)
         self.graph = None
@@ -140,7 +143,8 @@ class GPTSampler:
                 ops.Stats.launches += 1
                 _lib.check(lib.bevgen_kv_store(_ptr(qkv[0]), _ptr(qkv[1]), _ptr(self.kc[li]), _ptr(self.vc[li]), self.kv_bf16, B, nc, nc, e.H, d,
                                                self.Lmax, _stream()), "kv_store")
-            x = e.block(x, lw, B, nc, attn_kw=dict(bias=self.bias_cc, mask=self.mask_cc, causal=False, allowed=float(nc * nc)), on_qkv=store)
+            x = e.block(x, lw, B, nc, attn_kw=dict(bias=self.bias_cc, mask=self.mask_cc, causal=False, allowed=float(nc * nc),
+                                                    fused_cond=self.bias_cc_f16), on_qkv=store)
         # logits of decode-order token 0 come from the last conditioning row (mingpt_sparse.py:390)
         self._last = x
         self._reduce_ln(None, 0, None, x.view(-1)[(nc - 1) * d:], nc * d, e.ln_f, None, self.fp)

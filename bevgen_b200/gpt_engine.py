@@ -91,6 +91,8 @@ class GPTEngine:
         i, j = torch.meshgrid(torch.arange(self.L), torch.arange(self.L), indexing="ij")
         closed = (j < self.nc) | ((i >= self.nc) & (j <= i))
         self.causal = bool(torch.equal(closed, cfg.attention_mask.bool() | closed) and self.npad == 0)   # mask ⊆ [cond | causal]
+        self.bias_f16 = None if self.bias is None else self.bias.to(torch.float16).contiguous()
+        self.fused_attention = True          # tcgen05 flash-style kernel when the geometry allows; composed path otherwise
         self._perm_cache = {}
         self._allowed = float(self.mask_u8.sum().item())      # attended (row, col) pairs: algorithmic attention work
 
@@ -126,10 +128,20 @@ class GPTEngine:
         ops.embed_assemble(a)
         return out
 
-    def attention(self, qkv, y, B, L, bias="full", mask=None, causal=None, allowed=None):
+    def attention(self, qkv, y, B, L, bias="full", mask=None, causal=None, allowed=None, fused_cond=None):
         """qkv planes [B, L, 3d]; returns x1 = y + concat_heads(softmax(scale*(QK^T + bias))V) as fp32 [B, L, d].
         bias/mask default to the full-sequence camera bias and attention mask; the KV-cache prefill passes the cond x cond blocks."""
         d, H, dh = self.d, self.H, self.dh
+        if self.fused_attention and isinstance(bias, str) and mask is None and self.causal and L % 128 == 0 and self.nc % 128 == 0:
+            x1 = torch.empty((B, L, d), dtype=torch.float32, device=self.dev)
+            ops.attn_fused_fwd(qkv[0], qkv[1], B, L, H, d, self.nc, self.bias_f16, y, x1, float(dh) ** -0.5, self.npass,
+                               algo_flops=4.0 * B * H * dh * self._allowed)
+            return x1
+        if self.fused_attention and fused_cond is not None and L % 128 == 0:
+            x1 = torch.empty((B, L, d), dtype=torch.float32, device=self.dev)
+            ops.attn_fused_fwd(qkv[0], qkv[1], B, L, H, d, L, fused_cond, y, x1, float(dh) ** -0.5, self.npass,
+                               algo_flops=4.0 * B * H * dh * float(L * L))
+            return x1
         bias = self.bias if isinstance(bias, str) else bias
         mask = self.mask_u8 if mask is None else mask
         causal = self.causal if causal is None else causal

@@ -185,3 +185,15 @@ def attn_softmax(S, bias, mask_u8, out_hi, out_lo, L, scale):
     Lk = S.shape[-1]
     _lib.check(lib.bevgen_attn_softmax(_ptr(S), _ptr(bias), _ptr(mask_u8), S.numel() // Lk, L, Lk, float(scale), _ptr(out_hi), _ptr(out_lo),
                                        _stream()), "attn_softmax")
+
+
+def attn_fused_fwd(qkv_hi, qkv_lo, B, L, H, d, n_cond, bias_f16, y, x1, scale, npass, algo_flops=0.0):
+    lib = _lib.init()
+    _chk_cuda(qkv_hi, qkv_lo, bias_f16, y, x1)
+    Stats.launches += 1
+    call = lambda: _lib.check(lib.bevgen_attn_fused_fwd(_ptr(qkv_hi), _ptr(qkv_lo), B, L, H, d, n_cond, _ptr(bias_f16), _ptr(y), _ptr(x1),
+                                                        float(scale), npass, _stream()), "attn_fused_fwd")
+    if Stats.timer is not None:
+        Stats.timer("attn_fused", call, algo_flops)
+    else:
+        call()

@@ -143,6 +143,13 @@ BEVGEN_API int bevgen_embed_assemble(const bevgen_embed_args* args, void* stream
 BEVGEN_API int bevgen_attn_softmax(const float* s, const float* bias, const unsigned char* mask, long long zrows, int L, int Lk, float scale,
                                    void* out_hi, void* out_lo, void* stream);
 
+/* Fused attention forward (one kernel for sparse_self_attention.py:153-176 + the residual add of mingpt_sparse.py:250):
+ *   x1[b,i,h*64:(h+1)*64] = y[...] + sum_j softmax_j(scale * (q_i.k_j + bias[i][j])) v_j,  allowed(i,j) = j < n_cond || (i >= n_cond && j <= i)
+ * q/k/v are the column blocks [0,d), [d,2d), [2d,3d) of the fused qkv bf16 planes [batch][seq_len][3d]; bias is fp16 [seq_len][seq_len]
+ * (pre-scale, shared by batch and heads) or NULL.  seq_len and n_cond must be multiples of 128, d = heads*64. */
+BEVGEN_API int bevgen_attn_fused_fwd(const void* qkv_hi, const void* qkv_lo, int batch, int seq_len, int heads, int d, int n_cond,
+                                     const void* bias_f16, const float* y, float* x1, float scale, int npass, void* stream);
+
 /* ---------------------------------------------------------------- KV-cache autoregressive decode
  * Replaces the per-token full forward of Net2NetTransformer.sample (modules/stage2/cond_transformer_multi_view.py:154-227)
  * with the cached formulation of SURVEY.md §3.4.  All kernels read the step counter s from device memory (one CUDA graph

@@ -60,3 +60,32 @@ def test_forward_bf16_error_budget(golden_dir):
     err = np.abs(tf[:, g["rows"]].cpu().numpy() - g["logits_tf"])
     print(f"[wide2] bf16: logits max err {err.max():.2e} mean {err.mean():.2e}")
     assert err.max() < 6e-2 and err.mean() < 1e-2
+
+
+@pytest.mark.parametrize("npass", [3, 1])
+def test_fused_attention_matches_composed(npass):
+    """Fused tcgen05 attention vs the composed (QK^T GEMM -> softmax -> PV GEMM) path on the full-size geometry."""
+    from bevgen_b200 import ops
+    from tests.cases import GPT_KW
+    cfg = GPTConfig(**GPT_KW)
+    sd = synth.gpt_state_dict(gpt_sizes(cfg), seed=2)
+    eng = GPTEngine(sd, cfg, device="cuda:0", precision="fp32x3" if npass == 3 else "bf16")
+    B, L, d = 2, cfg.gpt_block_size, cfg.num_embed
+    g = torch.Generator().manual_seed(0)
+    qkv = torch.randn(B, L, 3 * d, generator=g).cuda()
+    hi, lo = ops.split_planes(qkv, npass)
+    y = torch.randn(B, L, d, generator=g).cuda()
+    eng.fused_attention = True
+    fused = eng.attention((hi, lo), y, B, L)
+    eng.fused_attention = False
+    comp = eng.attention((hi, lo), y, B, L)
+    torch.cuda.synchronize()
+    # dense fp64 reference
+    q, k, v = [(hi.double() + (lo.double() if lo is not None else 0)).view(B, L, 3, 16, 64)[:, :, i].permute(0, 2, 1, 3) for i in range(3)]
+    s = (q @ k.transpose(-1, -2) + eng.bias.double()[None, None]) * 0.125
+    s = s.masked_fill(eng.mask_u8[None, None] == 0, float("-inf"))
+    ref = y.double() + (torch.softmax(s, -1) @ v).permute(0, 2, 1, 3).reshape(B, L, d)
+    e_f, e_c = (fused.double() - ref).abs().max().item(), (comp.double() - ref).abs().max().item()
+    print(f"[npass={npass}] fused err {e_f:.2e} composed err {e_c:.2e}")
+    assert torch.isfinite(fused).all()
+    assert e_f < (3e-4 if npass == 3 else 3e-2)
