@@ -38,6 +38,12 @@ class GemmArgs(C.Structure):
         ("causal_ncond", C.c_int),
         ("bn", C.c_int),
         ("npass", C.c_int),
+        ("fin_mode", C.c_int), ("fin_gelu", C.c_int), ("fin_rows", C.c_int),
+        ("fin_bias", C.c_void_p), ("fin_resid", C.c_void_p),
+        ("fin_x", C.c_void_p), ("fin_y", C.c_void_p), ("fin_hi", C.c_void_p), ("fin_lo", C.c_void_p),
+        ("fin_gamma", C.c_void_p), ("fin_beta", C.c_void_p),
+        ("fin_eps", C.c_float),
+        ("fin_counters", C.c_void_p),
     ]
 
 
@@ -73,7 +79,8 @@ SIGNATURES = {
     "bevgen_dec_reduce_ln": (_i, [_vp, _i, _ll, _vp, _vp, _ll, _vp, _vp, _f, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     "bevgen_dec_reduce_act": (_i, [_vp, _i, _ll, _vp, _i, _vp, _vp, _i, _i, _vp]),
     "bevgen_kv_store": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
-    "bevgen_dec_attention": (_i, [_vp, _i, _ll, _vp, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp]),
+    "bevgen_dec_attention": (_i, [_vp, _i, _ll, _vp, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f,
+                                  _vp, _vp, _vp, _f, _vp, _vp, _vp]),
     "bevgen_dec_attention_workspace_floats": (_i, [_i, _i]),
     "bevgen_sample_topk": (_i, [_vp, _i, _ll, _i, _i, _f, _i, _i, C.c_ulonglong, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "bevgen_dec_advance": (_i, [_vp, _vp]),

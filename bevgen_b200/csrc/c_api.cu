@@ -124,6 +124,16 @@ BEVGEN_API int bevgen_gemm_tc(const bevgen_gemm_args* a, void* stream) {
   p.bias = a->bias; p.residual = a->residual; p.out_f32 = a->out_f32;
   p.out_hi = (uint16_t*)a->out_hi; p.out_lo = (uint16_t*)a->out_lo;
   p.flags = a->flags; p.causal_ncond = a->causal_ncond;
+  p.fin_mode = a->fin_mode;
+  if (a->fin_mode != 0) {
+    if (!(a->flags & BEVGEN_GF_OUT_T) || a->z_outer != 1 || !a->fin_counters || !a->fin_hi || a->fin_rows < 1 || a->fin_rows > a->n_cols)
+      return fail(BEVGEN_ERR_ARG, "fused finalize needs a transposed split-K launch, counters and output planes");
+    if (a->fin_mode == 2 && (!a->fin_resid || !a->fin_x || !a->fin_gamma || !a->fin_beta || (a->out_w * a->out_h) % 128 != 0 || a->out_w * a->out_h > 1024))
+      return fail(BEVGEN_ERR_ARG, "residual+LayerNorm finalize: missing buffers or feature count not a multiple of 128 <= 1024");
+    p.fin_gelu = a->fin_gelu; p.fin_rows = a->fin_rows; p.fin_bias = a->fin_bias; p.fin_resid = a->fin_resid; p.fin_x = a->fin_x;
+    p.fin_y = a->fin_y; p.fin_hi = (uint16_t*)a->fin_hi; p.fin_lo = (uint16_t*)a->fin_lo; p.fin_gamma = a->fin_gamma; p.fin_beta = a->fin_beta;
+    p.fin_eps = a->fin_eps; p.fin_counters = a->fin_counters;
+  }
   rc = gemm_tc_dispatch(p, bn, npass, g_sm_count, (cudaStream_t)stream);
   if (rc) return fail(rc, "gemm_tc launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   return BEVGEN_OK;
@@ -268,11 +278,13 @@ BEVGEN_API int bevgen_kv_store(const void* qkv_hi, const void* qkv_lo, void* k_c
 BEVGEN_API int bevgen_dec_attention(const float* qkv_partials, int ks, long long zstride, const float* qkv_bias, const float* y,
                                     const float* camera_bias, int bias_ld, void* k_cache, void* v_cache, int kv_bf16, float* x1,
                                     const int* step_ptr, float* workspace, unsigned int* counters, int batch, int n_cond, int heads, int d,
-                                    int lmax, float scale, void* stream) {
+                                    int lmax, float scale, unsigned int* row_counters, const float* ln_gamma, const float* ln_beta, float ln_eps,
+                                    void* ln_hi, void* ln_lo, void* stream) {
   if (!qkv_partials || !qkv_bias || !y || !k_cache || !v_cache || !x1 || !step_ptr || !workspace || !counters || ks < 1)
     return fail(BEVGEN_ERR_ARG, "dec_attention: bad args");
   CHECK_LAUNCH(launch_dec_attn(qkv_partials, ks, zstride, qkv_bias, y, camera_bias, bias_ld, k_cache, v_cache, kv_bf16, x1, step_ptr, workspace,
-                               counters, batch, n_cond, heads, d, lmax, scale, (cudaStream_t)stream), "dec_attention");
+                               counters, batch, n_cond, heads, d, lmax, scale, row_counters, ln_gamma, ln_beta, ln_eps, (uint16_t*)ln_hi,
+                               (uint16_t*)ln_lo, (cudaStream_t)stream), "dec_attention");
 }
 
 BEVGEN_API int bevgen_dec_attention_workspace_floats(int batch, int heads) { return dec_attn_workspace_floats(batch, heads); }

@@ -167,8 +167,10 @@ __global__ void __launch_bounds__(256, 2) dec_attn_kernel(const float* __restric
                                                        const float* __restrict__ bias, int bias_ld, KVT* __restrict__ kc,
                                                        KVT* __restrict__ vc, float* __restrict__ x1, const int* __restrict__ step_ptr,
                                                        float* __restrict__ ws, unsigned int* __restrict__ counters, int nc, int H, int d,
-                                                       int Lmax, float scale) {
-  __shared__ float q[64], knew[64], vnew[64];
+                                                       int Lmax, float scale, unsigned int* __restrict__ row_counters,
+                                                       const float* __restrict__ ln_gamma, const float* __restrict__ ln_beta, float ln_eps,
+                                                       uint16_t* __restrict__ ln_hi, uint16_t* __restrict__ ln_lo) {
+  __shared__ float q[64], knew[64], vnew[64], red[8];
   __shared__ float wm[8], wl[8];
   __shared__ float wo[8][64];
   __shared__ unsigned int ticket;
@@ -281,6 +283,29 @@ __global__ void __launch_bounds__(256, 2) dec_attn_kernel(const float* __restric
     x1[idx] = y[idx] + o / Lsum;
     if (tid == 0) counters[bh] = 0u;      // self-reset for the next launch
   }
+  if (ln_gamma == nullptr) return;
+  // ---- fused LayerNorm (ln2) of the finished row: the last head of batch row b normalises x1[b,:] into the MLP operand planes
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) ticket = atomicAdd(&row_counters[b], 1u);
+  __syncthreads();
+  if (ticket != (unsigned)(H - 1)) return;
+  __threadfence();
+  const bool act = tid < (d >> 2);
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (act) v = __ldcg(reinterpret_cast<const float4*>(x1 + (size_t)b * d) + tid);
+  const float mean = block_sum_256(act ? (v.x + v.y) + (v.z + v.w) : 0.f, red) / d;
+  v.x -= mean; v.y -= mean; v.z -= mean; v.w -= mean;
+  const float var = block_sum_256(act ? (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w) : 0.f, red) / d;
+  const float rstd = rsqrtf(var + ln_eps);
+  if (tid == 0) row_counters[b] = 0u;
+  if (!act) return;
+  const float4 g = __ldg(reinterpret_cast<const float4*>(ln_gamma) + tid), be = __ldg(reinterpret_cast<const float4*>(ln_beta) + tid);
+  const float4 o4 = make_float4(v.x * rstd * g.x + be.x, v.y * rstd * g.y + be.y, v.z * rstd * g.z + be.z, v.w * rstd * g.w + be.w);
+  __nv_bfloat16 h0, l0, h1, l1, h2, l2, h3, l3;
+  split_bf16(o4.x, h0, l0); split_bf16(o4.y, h1, l1); split_bf16(o4.z, h2, l2); split_bf16(o4.w, h3, l3);
+  reinterpret_cast<uint2*>(ln_hi + (size_t)b * d)[tid] = make_uint2(pack_bf16(h0, h1), pack_bf16(h2, h3));
+  if (ln_lo != nullptr) reinterpret_cast<uint2*>(ln_lo + (size_t)b * d)[tid] = make_uint2(pack_bf16(l0, l1), pack_bf16(l2, l3));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -452,15 +477,18 @@ int dec_attn_workspace_floats(int B, int H) { return B * H * DEC_SPLIT * DEC_WS;
 
 int launch_dec_attn(const float* qkv_part, int ks, long long zstride, const float* bqkv, const float* y, const float* bias, int bias_ld,
                     void* kc, void* vc, int kv_bf16, float* x1, const int* step_ptr, float* ws, unsigned int* counters, int B, int nc, int H,
-                    int d, int Lmax, float scale, cudaStream_t st) {
+                    int d, int Lmax, float scale, unsigned int* row_counters, const float* ln_gamma, const float* ln_beta, float ln_eps,
+                    uint16_t* ln_hi, uint16_t* ln_lo, cudaStream_t st) {
   if (Lmax > DEC_MAXL || B < 1 || B > 65535 || d != H * 64 || (Lmax & 3)) return BEVGEN_ERR_ARG;
+  if (ln_gamma != nullptr && (!row_counters || !ln_beta || !ln_hi || d > 1024)) return BEVGEN_ERR_ARG;
   dim3 grid(H, B, DEC_SPLIT);
   if (kv_bf16)
     dec_attn_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(qkv_part, ks, zstride, bqkv, y, bias, bias_ld, (__nv_bfloat16*)kc, (__nv_bfloat16*)vc, x1,
-                                                         step_ptr, ws, counters, nc, H, d, Lmax, scale);
+                                                         step_ptr, ws, counters, nc, H, d, Lmax, scale, row_counters, ln_gamma, ln_beta, ln_eps,
+                                                         ln_hi, ln_lo);
   else
     dec_attn_kernel<float><<<grid, 256, 0, st>>>(qkv_part, ks, zstride, bqkv, y, bias, bias_ld, (float*)kc, (float*)vc, x1, step_ptr, ws,
-                                                 counters, nc, H, d, Lmax, scale);
+                                                 counters, nc, H, d, Lmax, scale, row_counters, ln_gamma, ln_beta, ln_eps, ln_hi, ln_lo);
   return cudaGetLastError() == cudaSuccess ? BEVGEN_OK : BEVGEN_ERR_CUDA;
 }
 int launch_dec_sample(const float* part, int ks, long long zstride, int vpad, int V, float temperature, int top_k, int greedy,

@@ -39,6 +39,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
+  uint32_t* fin_ticket = tmem_slot + 1;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -298,6 +299,87 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
               p.out_hi[o] = __bfloat16_as_ushort(h0);
               if (p.out_lo != nullptr) p.out_lo[o] = __bfloat16_as_ushort(l0);
             }
+          }
+        }
+      }
+      if (p.fin_mode != 0) {
+        // ---- split-K finalize: the last CTA to arrive for this row tile sums the partials (decode GEMMs)
+        const int et = threadIdx.x - 128;                 // 0..127 within the epilogue warps
+        const int mt = th * p.tiles_w + tw;
+        const int expected = p.z_inner * n_tiles_n;
+        __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (et == 0) *fin_ticket = atomicAdd(&p.fin_counters[mt], 1u);
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if ((int)*fin_ticket == expected - 1) {
+          __threadfence();
+          const int n_out = p.out_w * p.out_h;            // features (rows of D^T)
+          const int n = mt * BM + et;
+          if (n < n_out) {
+            const float bias_n = p.fin_bias ? __ldg(p.fin_bias + n) : 0.f;
+            for (int bb = 0; bb < p.fin_rows; ++bb) {
+              float v = bias_n;
+              for (int z = 0; z < p.z_inner; ++z) v += __ldcg(p.out_f32 + (long long)z * p.out_zi_stride + (long long)bb * p.ldc + n);
+              if (p.fin_mode == GEMM_FIN_ACT) {
+                if (p.fin_gelu) v = gelu_erf(v);
+                __nv_bfloat16 h0, l0;
+                split_bf16(v, h0, l0);
+                p.fin_hi[(size_t)bb * n_out + n] = __bfloat16_as_ushort(h0);
+                if (p.fin_lo != nullptr) p.fin_lo[(size_t)bb * n_out + n] = __bfloat16_as_ushort(l0);
+              } else {
+                v += __ldcg(p.fin_resid + (size_t)bb * n_out + n);
+                p.fin_x[(size_t)bb * n_out + n] = v;
+              }
+            }
+          }
+          if (p.fin_mode == GEMM_FIN_RESID_LN) {
+            const int m_tiles = p.tiles_w * p.tiles_h;
+            __threadfence();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (et == 0) { p.fin_counters[mt] = 0u; *fin_ticket = atomicAdd(&p.fin_counters[m_tiles], 1u); }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if ((int)*fin_ticket == m_tiles - 1) {
+              // last row tile: LayerNorm of every batch row over all features (warp per row, features across lanes)
+              __threadfence();
+              const int ew = et >> 5;
+              const int nv = n_out >> 7;                    // float4 per lane (n_out % 128 == 0, <= 8)
+              for (int bb = ew; bb < p.fin_rows; bb += 4) {
+                const float4* xr = reinterpret_cast<const float4*>(p.fin_x + (size_t)bb * n_out);
+                float4 xv[8];
+                float sum = 0.f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  if (j < nv) { xv[j] = __ldcg(xr + j * 32 + lane); sum += (xv[j].x + xv[j].y) + (xv[j].z + xv[j].w); }
+                for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                const float mean = sum / n_out;
+                float sq = 0.f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  if (j < nv) {
+                    xv[j].x -= mean; xv[j].y -= mean; xv[j].z -= mean; xv[j].w -= mean;
+                    sq += (xv[j].x * xv[j].x + xv[j].y * xv[j].y) + (xv[j].z * xv[j].z + xv[j].w * xv[j].w);
+                  }
+                for (int o = 16; o; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+                const float rstd = rsqrtf(sq / n_out + p.fin_eps);
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  if (j < nv) {
+                    const int c4 = j * 32 + lane;
+                    const float4 g = __ldg(reinterpret_cast<const float4*>(p.fin_gamma) + c4), be = __ldg(reinterpret_cast<const float4*>(p.fin_beta) + c4);
+                    float4 o4;
+                    o4.x = xv[j].x * rstd * g.x + be.x; o4.y = xv[j].y * rstd * g.y + be.y;
+                    o4.z = xv[j].z * rstd * g.z + be.z; o4.w = xv[j].w * rstd * g.w + be.w;
+                    if (p.fin_y != nullptr) reinterpret_cast<float4*>(p.fin_y + (size_t)bb * n_out)[c4] = o4;
+                    __nv_bfloat16 h0, l0, h1, l1, h2, l2, h3, l3;
+                    split_bf16(o4.x, h0, l0); split_bf16(o4.y, h1, l1); split_bf16(o4.z, h2, l2); split_bf16(o4.w, h3, l3);
+                    reinterpret_cast<uint2*>(p.fin_hi + (size_t)bb * n_out)[c4] = make_uint2(pack_bf16(h0, h1), pack_bf16(h2, h3));
+                    if (p.fin_lo != nullptr) reinterpret_cast<uint2*>(p.fin_lo + (size_t)bb * n_out)[c4] = make_uint2(pack_bf16(l0, l1), pack_bf16(l2, l3));
+                  }
+              }
+              if (et == 0) p.fin_counters[m_tiles] = 0u;
+            }
+          } else if (et == 0) {
+            p.fin_counters[mt] = 0u;
           }
         }
       }

@@ -7,6 +7,8 @@ namespace bevgen {
 
 constexpr int GEMM_MAX_TAPS = 9;
 
+constexpr int GEMM_FIN_ACT = 1, GEMM_FIN_RESID_LN = 2;
+
 enum GemmFlags : int {
   GF_GELU = 1,        // exact-erf GELU after bias
   GF_OUT_NCHW = 2,    // fp32 output written as [z][col][h][w] (tiny Cout: conv_out)
@@ -39,6 +41,20 @@ struct GemmParams {
   uint16_t* out_lo;
   int flags;
   int causal_ncond;     // GF_CAUSAL_SKIP: columns < ncond always allowed; else col <= row
+  // ---- split-K finalize fused into GF_OUT_T launches (decode): the last CTA to finish a row tile reduces the partials
+  int fin_mode;               // 0 none | 1 planes = act(sum + bias) | 2 x = sum + bias + residual, then LayerNorm by the last tile
+  int fin_gelu;
+  int fin_rows;               // batch rows (columns of D^T)
+  const float* fin_bias;      // [n_out]
+  const float* fin_resid;     // [rows][n_out]           (mode 2)
+  float* fin_x;               // [rows][n_out] fp32      (mode 2)
+  float* fin_y;               // LayerNorm output fp32 or null (mode 2)
+  uint16_t* fin_hi;           // bf16 planes [rows][n_out] (mode 1: activation; mode 2: LayerNorm output)
+  uint16_t* fin_lo;
+  const float* fin_gamma;     // (mode 2)
+  const float* fin_beta;
+  float fin_eps;
+  unsigned int* fin_counters; // [m_tiles + 1], zero before the first launch; self-resetting
 };
 
 }  // namespace bevgen

@@ -62,17 +62,22 @@ class GPTSampler:
                             else self.bias_cc.to(torch.float16).contiguous()) if full_cc else None
         self.attn_ws = f32(_lib.load().bevgen_dec_attention_workspace_floats(B, H))
         self.attn_cnt = torch.zeros(B * H, dtype=torch.int32, device=dev)
+        self.row_cnt = torch.zeros(B, dtype=torch.int32, device=dev)
+        self.cnt_h = torch.zeros(4 * d // 128 + 1, dtype=torch.int32, device=dev)      # MLP1 finalize tickets
+        self.cnt_o = torch.zeros(d // 128 + 1, dtype=torch.int32, device=dev)          # MLP2 finalize tickets
+        self.x2 = f32(self.Bp, d)
+        self.fuse_finalize = True
         self.graph = None
         self._graph_key = None
         self.trace = None
 
     # ------------------------------------------------------------------ launches
-    def _gemm_t(self, w, xp, n_out, K, part):
+    def _gemm_t(self, w, xp, n_out, K, part, fin=None):
         """partials[z][b][n] = sum_{k in slice z} W[n][k] x[b][k]  — weights are the 128-row (M) operand, batch the N=16 operand."""
         kk = _kslice(K)
         ops.gemm_tc(a_hi=w[0], a_lo=w[1], a_dims=(1, 1, w[0].shape[0], K), b_hi=xp[0], b_lo=xp[1], k=kk, n_cols=self.B, a_c_zstride=kk,
                     b_k_zstride=kk, z_inner=K // kk, out_w=n_out, out_zi_stride=self.Bp * n_out, ldc=n_out, out_f32=part,
-                    flags=ops.GF_OUT_T, bn=16, npass=self.eng.npass, algo_flops=2.0 * self.B * n_out * K)
+                    flags=ops.GF_OUT_T, bn=16, npass=self.eng.npass, algo_flops=2.0 * self.B * n_out * K, fin=fin)
 
     def _reduce_ln(self, part, ks, bias, residual, res_stride, ln, y, planes, rows=None, x_out=None):
         lib = _lib.init()
@@ -117,17 +122,30 @@ class GPTSampler:
         for li, lw in enumerate(e.layers):
             self._gemm_t(lw["wqkv"], self.yp, 3 * d, d, self.part_qkv)
             ops.Stats.launches += 1
+            fz = self.fuse_finalize
             _lib.check(lib.bevgen_dec_attention(_ptr(self.part_qkv), self.ks_d, self.Bp * 3 * d, _ptr(lw["bqkv"]), _ptr(self.y), _ptr(e.bias), e.L,
                                                 _ptr(self.kc[li]), _ptr(self.vc[li]), self.kv_bf16, _ptr(self.x1), _ptr(self.step), _ptr(self.attn_ws),
-                                                _ptr(self.attn_cnt), self.B, e.nc, H, d, self.Lmax, float(e.dh) ** -0.5, _stream()), "dec_attention")
+                                                _ptr(self.attn_cnt), self.B, e.nc, H, d, self.Lmax, float(e.dh) ** -0.5,
+                                                _ptr(self.row_cnt) if fz else None, _ptr(lw["ln2"][0]) if fz else None,
+                                                _ptr(lw["ln2"][1]) if fz else None, 1e-5, _ptr(self.zp[0]) if fz else None,
+                                                _ptr(self.zp[1]) if fz else None, _stream()), "dec_attention")
+            last = li == len(e.layers) - 1
+            nxt = e.ln_f if last else e.layers[li + 1]["ln1"]
+            if fz:
+                # split-K reductions fused into the producing GEMMs (last CTA per feature tile): 4 launches per layer
+                self._gemm_t(lw["w1"], self.zp, 4 * d, d, self.part_h,
+                             fin=dict(mode=1, gelu=1, rows=self.B, counters=self.cnt_h, hi=self.hp[0], lo=self.hp[1], bias=lw["b1"]))
+                outp = self.fp if last else self.yp
+                self._gemm_t(lw["w2"], self.hp, d, 4 * d, self.part_o,
+                             fin=dict(mode=2, rows=self.B, counters=self.cnt_o, hi=outp[0], lo=outp[1], bias=lw["b2"], resid=self.x1, x=self.x2,
+                                      y=None if last else self.y, gamma=nxt[0], beta=nxt[1], eps=1e-5))
+                continue
             self._reduce_ln(None, 0, None, self.x1, d, lw["ln2"], None, self.zp)
             self._gemm_t(lw["w1"], self.zp, 4 * d, d, self.part_h)
             ops.Stats.launches += 1
             _lib.check(lib.bevgen_dec_reduce_act(_ptr(self.part_h), self.ks_d, self.Bp * 4 * d, _ptr(lw["b1"]), 1, _ptr(self.hp[0]), _ptr(self.hp[1]),
                                                  self.B, 4 * d, _stream()), "dec_reduce_act")
             self._gemm_t(lw["w2"], self.hp, d, 4 * d, self.part_o)
-            last = li == len(e.layers) - 1
-            nxt = e.ln_f if last else e.layers[li + 1]["ln1"]
             self._reduce_ln(self.part_o, self.ks_4d, lw["b2"], self.x1, d, nxt, None if last else self.y, self.fp if last else self.yp)
         self._gemm_t(e.whead, self.fp, self.vpad, d, self.part_v)
         self._sample(temperature, top_k, greedy, seed, forced)

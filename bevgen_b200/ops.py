@@ -52,7 +52,7 @@ TAPS_3X3 = [(kw - 1, kh - 1) for kh in range(3) for kw in range(3)]
 def gemm_tc(*, a_hi, a_lo, a_dims, b_hi, b_lo, k, n_cols, taps=((0, 0, 0),), a_n_mul=1, a_n_zstride=0, a_c_off=0, a_c_zstride=0,
             b_k_off=0, b_k_zstride=0, b_row_zstride=0, b_row_tapstride=0, z_inner=1, z_outer=1, tile=(128, 1),
             out_w, out_h=1, out_zo_stride=0, out_zi_stride=0, ldc, bias=None, residual=None, out_f32=None, out_hi=None,
-            out_lo=None, flags=0, causal_ncond=0, bn=128, npass=3, algo_flops=None):
+            out_lo=None, flags=0, causal_ncond=0, bn=128, npass=3, algo_flops=None, fin=None):
     lib = _lib.init()
     _chk_cuda(a_hi, a_lo, b_hi, b_lo, bias, residual, out_f32, out_hi, out_lo)
     g = GemmArgs()
@@ -74,6 +74,12 @@ def gemm_tc(*, a_hi, a_lo, a_dims, b_hi, b_lo, k, n_cols, taps=((0, 0, 0),), a_n
     g.bias, g.residual = _ptr(bias), _ptr(residual)
     g.out_f32, g.out_hi, g.out_lo = _ptr(out_f32), _ptr(out_hi), _ptr(out_lo)
     g.flags, g.causal_ncond, g.bn, g.npass = flags, causal_ncond, bn, npass
+    if fin is not None:        # fused split-K finalize (decode): dict(mode, rows, counters, hi, lo, bias, gelu, resid, x, y, gamma, beta, eps)
+        g.fin_mode, g.fin_gelu, g.fin_rows = fin["mode"], int(fin.get("gelu", 0)), fin["rows"]
+        g.fin_bias, g.fin_resid = _ptr(fin.get("bias")), _ptr(fin.get("resid"))
+        g.fin_x, g.fin_y, g.fin_hi, g.fin_lo = _ptr(fin.get("x")), _ptr(fin.get("y")), _ptr(fin["hi"]), _ptr(fin.get("lo"))
+        g.fin_gamma, g.fin_beta, g.fin_eps = _ptr(fin.get("gamma")), _ptr(fin.get("beta")), float(fin.get("eps", 1e-5))
+        g.fin_counters = _ptr(fin["counters"])
     flops = algo_flops if algo_flops is not None else 2.0 * z_inner * z_outer * out_w * out_h * n_cols * k * len(taps)
     Stats.launches += 1
     Stats.gemm_launches += 1

@@ -70,6 +70,14 @@ typedef struct {
   int causal_ncond;
   int bn;                               /* N tile: 16, 64 or 128 */
   int npass;                            /* 1 (bf16) or 3 (bf16x3 ~ fp32) */
+  /* split-K finalize fused into BEVGEN_GF_OUT_T launches: the last CTA per 128-feature tile reduces the z_inner partials */
+  int fin_mode;                         /* 0 none; 1: planes = act(sum + bias); 2: x = sum + bias + residual, then LayerNorm(x) */
+  int fin_gelu, fin_rows;
+  const float* fin_bias; const float* fin_resid;
+  float* fin_x; float* fin_y; void* fin_hi; void* fin_lo;
+  const float* fin_gamma; const float* fin_beta;
+  float fin_eps;
+  unsigned int* fin_counters;           /* [ceil(out_w/128) + 1] uint32, zeroed once by the caller (self-resetting) */
 } bevgen_gemm_args;
 
 BEVGEN_API int bevgen_init(int device);                 /* selects nothing, queries: SM count, arch check, driver entry points */
@@ -167,11 +175,13 @@ BEVGEN_API int bevgen_dec_reduce_act(const float* partials, int ks, long long zs
 BEVGEN_API int bevgen_kv_store(const void* qkv_hi, const void* qkv_lo, void* k_cache, void* v_cache, int kv_bf16, int batch, int lp, int nrows,
                                int heads, int d, int lmax, void* stream);
 /* one decode row: finish q/k/v (+bias), append k/v, softmax(scale*(q.K + camera_bias[r][:])) V, x1 = y + heads concat.
- * workspace: bevgen_dec_attention_workspace_floats(batch, heads) floats; counters: batch*heads uint32 zero-initialised once. */
+ * workspace: bevgen_dec_attention_workspace_floats(batch, heads) floats; counters: batch*heads uint32 zero-initialised once.
+ * Optional fused LayerNorm of the finished row (ln_gamma != NULL): planes ln_hi/ln_lo[batch][d] = LN(x1); row_counters: batch uint32 zeros. */
 BEVGEN_API int bevgen_dec_attention(const float* qkv_partials, int ks, long long zstride, const float* qkv_bias, const float* y,
                                     const float* camera_bias, int bias_ld, void* k_cache, void* v_cache, int kv_bf16, float* x1,
                                     const int* step_ptr, float* workspace, unsigned int* counters, int batch, int n_cond, int heads, int d,
-                                    int lmax, float scale, void* stream);
+                                    int lmax, float scale, unsigned int* row_counters, const float* ln_gamma, const float* ln_beta, float ln_eps,
+                                    void* ln_hi, void* ln_lo, void* stream);
 BEVGEN_API int bevgen_dec_attention_workspace_floats(int batch, int heads);
 /* sampling tail (cond_transformer_multi_view.py:138-142,200-219): logits/T, top-k (ties kept), softmax, multinomial|greedy|forced */
 BEVGEN_API int bevgen_sample_topk(const float* logit_partials, int ks, long long zstride, int vpad, int vocab, float temperature, int top_k,

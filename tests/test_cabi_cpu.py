@@ -44,7 +44,7 @@ def test_struct_layout_matches_header(lib):
         stmt = stmt.replace("typedef struct {", "").strip()
         if not stmt:
             continue
-        stmt = re.sub(r"^(const\s+)?(void|float|int|long long)\s*\*?", "", stmt).strip()
+        stmt = re.sub(r"^(const\s+)?(void|float|unsigned int|int|long long)\s*\*?", "", stmt).strip()
         for part in stmt.split(","):
             names.append(re.sub(r"\[.*\]", "", part).replace("*", "").strip())
     assert names == [f[0] for f in _lib.GemmArgs._fields_]

@@ -22,12 +22,13 @@ def _case(name, precision="fp32x3"):
     return cfg, sd, cam, bev, batch, eng, B
 
 
-@pytest.mark.parametrize("use_graph", [False, True])
-def test_greedy_matches_reference_sampling_loop(golden_dir, use_graph):
+@pytest.mark.parametrize("use_graph,fuse", [(False, True), (True, True), (True, False)])
+def test_greedy_matches_reference_sampling_loop(golden_dir, use_graph, fuse):
     """First 4 greedy steps of the reference's Net2NetTransformer.sample loop: same logits rows, same tokens."""
     g = np.load(golden_dir / "gpt_small_sample4.npz")
     cfg, sd, cam, bev, batch, eng, B = _case("small")
     sampler = GPTSampler(eng, B)
+    sampler.fuse_finalize = fuse
     toks, trace = sampler.sample(bev, batch, greedy=True, steps=4, trace_logits=True, use_graph=use_graph)
     torch.cuda.synchronize()
     got = trace.permute(1, 0, 2).cpu().numpy()
