@@ -140,29 +140,25 @@ __global__ void __launch_bounds__(256) kv_store_kernel(const uint16_t* __restric
 }
 
 constexpr int DEC_MAXL = 2560;
-constexpr int DEC_SPLIT = 4;          // key-range splits per (batch, head): 4 x 256 CTAs keep every SM streaming the cache
+constexpr int DEC_MAX_SPLIT = 32;     // key-range splits per (batch, head)
+constexpr int DEC_CHUNK = 128;        // keys per CTA: K^T slab (64 x 128) + V slab (128 x 64) staged in shared memory
 constexpr int DEC_WS = 68;            // floats per partial: m, l, pad, pad, o[64]
 
-template <typename T> struct KV2;
-template <> struct KV2<float> {
-  static __device__ __forceinline__ float2 load(const float* p) { return *reinterpret_cast<const float2*>(p); }
-};
-template <> struct KV2<__nv_bfloat16> {
-  static __device__ __forceinline__ float2 load(const __nv_bfloat16* p) {
-    const uint32_t u = *reinterpret_cast<const uint32_t*>(p);
-    return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
-  }
-};
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+               "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
 
-// grid (heads, batch, DEC_SPLIT), 8 warps per CTA.  Every CTA finishes q for its (batch, head) from the split-K partials; the CTA
-// owning the newest key also finishes k/v and appends them to the cache.  The n keys are cut into DEC_SPLIT*8 contiguous
-// segments, one per warp; each warp runs an independent online-softmax pass over its segment, 32 keys at a time:
-// scores with thread = key (64 coalesced loads of the transposed K cache in flight per lane; camera-bias row added BEFORE
-// the 1/sqrt(d_head) scale), then P.V with lane = channel pair (32 row loads in flight per lane).  Warp partials are merged
-// in shared memory, CTA partials through a workspace by the last CTA to arrive per (batch, head) (flash-decoding with a
-// fused combine), which writes x1 = y + concat_heads(softmax(...) V).
+// grid (heads, batch, splits), 256 threads.  Each CTA owns a contiguous range of <= DEC_CHUNK keys.  One thread issues bulk
+// async copies (cp.async.bulk -> mbarrier) for the K^T slab (64 row segments) and the V slab (one contiguous block) of that range
+// at kernel entry, so the whole KV traffic of the CTA is in flight while the other threads finish q (and k/v of the newest key,
+// appended to the cache by the CTA that owns it) from the split-K partials of the QKV GEMM.  Scores (thread = key, camera-bias row
+// added BEFORE the 1/sqrt(d_head) scale), block softmax and P.V (thread = channel) then run out of shared memory; the CTA leaves an
+// (m, l, o[64]) partial and the last CTA to arrive per (batch, head) merges them: x1 = y + concat_heads(softmax(...) V)
+// (flash-decoding with a fused combine).  Optionally the last head of a batch row applies LayerNorm (ln2) to the finished row.
 template <typename KVT>
-__global__ void __launch_bounds__(256, 2) dec_attn_kernel(const float* __restrict__ qkv_part, int ks, long long zstride,
+__global__ void __launch_bounds__(256) dec_attn_kernel(const float* __restrict__ qkv_part, int ks, long long zstride,
                                                        const float* __restrict__ bqkv, const float* __restrict__ y,
                                                        const float* __restrict__ bias, int bias_ld, KVT* __restrict__ kc,
                                                        KVT* __restrict__ vc, float* __restrict__ x1, const int* __restrict__ step_ptr,
@@ -170,110 +166,100 @@ __global__ void __launch_bounds__(256, 2) dec_attn_kernel(const float* __restric
                                                        int Lmax, float scale, unsigned int* __restrict__ row_counters,
                                                        const float* __restrict__ ln_gamma, const float* __restrict__ ln_beta, float ln_eps,
                                                        uint16_t* __restrict__ ln_hi, uint16_t* __restrict__ ln_lo) {
-  __shared__ float q[64], knew[64], vnew[64], red[8];
-  __shared__ float wm[8], wl[8];
-  __shared__ float wo[8][64];
+  extern __shared__ __align__(128) uint8_t dsm[];
+  KVT* Ks = reinterpret_cast<KVT*>(dsm);                                  // [64][pitch]
+  KVT* Vs = reinterpret_cast<KVT*>(dsm + 64 * DEC_CHUNK * sizeof(KVT));   // [keys][64]
+  __shared__ float q[64], knew[64], vnew[64], red[8], sc[DEC_CHUNK];
+  __shared__ float opart[4][64];
+  __shared__ __align__(8) uint64_t bar;
   __shared__ unsigned int ticket;
-  const int h = blockIdx.x, b = blockIdx.y, sp = blockIdx.z, tid = threadIdx.x;
-  const int warp = tid >> 5, lane = tid & 31;
+  const int h = blockIdx.x, b = blockIdx.y, sp = blockIdx.z, S = gridDim.z, tid = threadIdx.x;
   const int r = nc + *step_ptr - 1;
   const int n = r + 1;
-  const int seg = (n + DEC_SPLIT * 8 - 1) / (DEC_SPLIT * 8);
-  const int g0 = min(n, (sp * 8 + warp) * seg), g1 = min(n, g0 + seg);
-  const bool owns_new = (sp == DEC_SPLIT - 1);          // the last segment always contains key r
+  const int j0 = sp * DEC_CHUNK;
+  const int cnt = max(0, min(n - j0, DEC_CHUNK));          // valid keys of this CTA (key r included if in range)
+  const int pitch = (cnt + 7) & ~7;                        // copied keys: 16-byte granules; stale tail entries are never used
+  const bool owns_new = (r >= j0 && r < j0 + DEC_CHUNK);
   const size_t bh = (size_t)b * H + h;
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    fence_barrier_init();
+    if (cnt > 0) {
+      const uint32_t row_bytes = pitch * sizeof(KVT);
+      mbar_expect_tx(&bar, 65u * 0u + 64u * row_bytes + (uint32_t)pitch * 64u * (uint32_t)sizeof(KVT));
+      const KVT* kb = kc + bh * 64 * Lmax + j0;
+      for (int c = 0; c < 64; ++c) bulk_g2s(Ks + c * pitch, kb + (size_t)c * Lmax, row_bytes, &bar);
+      bulk_g2s(Vs, vc + (bh * Lmax + j0) * 64, (uint32_t)pitch * 64u * (uint32_t)sizeof(KVT), &bar);
+    }
+  }
   if (tid < 192) {
     const int which = tid >> 6, c = tid & 63;
-    if (which == 0 || owns_new) {
+    if (cnt > 0 && (which == 0 || owns_new)) {
       const int col = which * d + h * 64 + c;
+      const float* pp = qkv_part + (size_t)b * 3 * d + col;
       float v = __ldg(bqkv + col);
-      for (int z = 0; z < ks; ++z) v += qkv_part[z * zstride + (size_t)b * 3 * d + col];
+      int z = 0;
+      for (; z + 4 <= ks; z += 4) v += (pp[z * zstride] + pp[(z + 1) * zstride]) + (pp[(z + 2) * zstride] + pp[(z + 3) * zstride]);
+      for (; z < ks; ++z) v += pp[z * zstride];
       if (which == 0) q[c] = v;
       else if (which == 1) { knew[c] = v; kv_store(kc + (bh * 64 + c) * Lmax + r, v); }
       else { vnew[c] = v; kv_store(vc + (bh * Lmax + r) * 64 + c, v); }
     }
   }
   __syncthreads();
-  const KVT* kb = kc + bh * 64 * Lmax;
-  const KVT* vb = vc + bh * (size_t)Lmax * 64;
-  const float* brow = bias ? bias + (size_t)r * bias_ld : nullptr;
-  float m = -INFINITY, l = 0.f;
-  float2 acc = make_float2(0.f, 0.f);
-  for (int base = g0; base < g1; base += 32) {
-    const int j = base + lane;
-    float sv = -INFINITY;
-    if (j < g1) {
-      float dot = 0.f;
-      if (j < r) {
-        float kv[64];
+  float m = -INFINITY, sum = 0.f;
+  if (cnt > 0) {
+    mbar_wait(&bar, 0);
+    if (owns_new && tid < 64) {        // the slab may hold a stale copy of the newest key: take it from registers instead
+      kv_store(Ks + tid * pitch + (r - j0), knew[tid]);
+      kv_store(Vs + (size_t)(r - j0) * 64 + tid, vnew[tid]);
+    }
+    __syncthreads();
+    const float* brow = bias ? bias + (size_t)r * bias_ld + j0 : nullptr;
+    if (tid < cnt) {
+      float d0 = 0.f, d1 = 0.f;
 #pragma unroll
-        for (int c = 0; c < 64; ++c) kv[c] = kv_load(kb + (size_t)c * Lmax + j);
-#pragma unroll
-        for (int c = 0; c < 64; ++c) dot = fmaf(q[c], kv[c], dot);
-      } else {
-#pragma unroll 16
-        for (int c = 0; c < 64; ++c) dot = fmaf(q[c], knew[c], dot);
+      for (int c = 0; c < 64; c += 2) {
+        d0 = fmaf(q[c], kv_load(Ks + c * pitch + tid), d0);
+        d1 = fmaf(q[c + 1], kv_load(Ks + (c + 1) * pitch + tid), d1);
       }
-      sv = (dot + (brow ? brow[j] : 0.f)) * scale;
+      m = ((d0 + d1) + (brow ? brow[tid] : 0.f)) * scale;
     }
-    float tmax = sv;
-    for (int o = 16; o; o >>= 1) tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
-    const float m_new = fmaxf(m, tmax);
-    const float corr = (m == -INFINITY) ? 0.f : expf(m - m_new);
-    const float p = (j < g1) ? expf(sv - m_new) : 0.f;
-    float psum = p;
-    for (int o = 16; o; o >>= 1) psum += __shfl_xor_sync(0xffffffffu, psum, o);
-    l = l * corr + psum;
-    acc.x *= corr; acc.y *= corr;
-    m = m_new;
-    const int cnt = min(32, g1 - base);
-    float2 vr[32];
-#pragma unroll
-    for (int t = 0; t < 32; ++t) {
-      const int jj = base + t;
-      vr[t] = make_float2(0.f, 0.f);
-      if (t < cnt) vr[t] = (jj < r) ? KV2<KVT>::load(vb + (size_t)jj * 64 + 2 * lane) : make_float2(vnew[2 * lane], vnew[2 * lane + 1]);
+    const float mloc = block_max_256(m, red);
+    float e = 0.f;
+    if (tid < cnt) { e = expf(m - mloc); sc[tid] = e; }
+    sum = block_sum_256(e, red);       // its barriers publish sc[]
+    m = mloc;
+    const int g = tid >> 6, c = tid & 63;
+    float a0 = 0.f, a1 = 0.f;
+    int jj = g;
+    for (; jj + 4 < cnt; jj += 8) {
+      a0 = fmaf(sc[jj], kv_load(Vs + (size_t)jj * 64 + c), a0);
+      a1 = fmaf(sc[jj + 4], kv_load(Vs + (size_t)(jj + 4) * 64 + c), a1);
     }
-#pragma unroll
-    for (int t = 0; t < 32; ++t) {
-      const float pj = __shfl_sync(0xffffffffu, p, t);
-      acc.x = fmaf(pj, vr[t].x, acc.x);
-      acc.y = fmaf(pj, vr[t].y, acc.y);
-    }
+    if (jj < cnt) a0 = fmaf(sc[jj], kv_load(Vs + (size_t)jj * 64 + c), a0);
+    opart[g][c] = a0 + a1;
+  } else if (tid < 256) {
+    opart[tid >> 6][tid & 63] = 0.f;
   }
-  if (lane == 0) { wm[warp] = m; wl[warp] = l; }
-  wo[warp][2 * lane] = acc.x;
-  wo[warp][2 * lane + 1] = acc.y;
   __syncthreads();
-  float* wp = ws + (bh * DEC_SPLIT + sp) * DEC_WS;
+  float* wp = ws + (bh * S + sp) * DEC_WS;
   if (tid < 64) {
-    float M = wm[0];
-#pragma unroll
-    for (int w = 1; w < 8; ++w) M = fmaxf(M, wm[w]);
-    float Ls = 0.f, o = 0.f;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) {
-      const float sc_ = (wm[w] == -INFINITY) ? 0.f : expf(wm[w] - M);
-      Ls += wl[w] * sc_;
-      o += wo[w][tid] * sc_;
-    }
-    wp[4 + tid] = o;
-    if (tid == 0) { wp[0] = M; wp[1] = Ls; }
+    wp[4 + tid] = (opart[0][tid] + opart[1][tid]) + (opart[2][tid] + opart[3][tid]);
+    if (tid == 0) { wp[0] = m; wp[1] = sum; }
   }
   __threadfence();
   __syncthreads();
   if (tid == 0) ticket = atomicAdd(&counters[bh], 1u);
   __syncthreads();
-  if (ticket != DEC_SPLIT - 1) return;
+  if (ticket != (unsigned)(S - 1)) return;
   __threadfence();
   if (tid < 64) {
-    const volatile float* wv = ws + bh * DEC_SPLIT * DEC_WS;
+    const volatile float* wv = ws + bh * S * DEC_WS;
     float M = -INFINITY;
-#pragma unroll
-    for (int i = 0; i < DEC_SPLIT; ++i) M = fmaxf(M, wv[i * DEC_WS]);
+    for (int i = 0; i < S; ++i) M = fmaxf(M, wv[i * DEC_WS]);
     float Lsum = 0.f, o = 0.f;
-#pragma unroll
-    for (int i = 0; i < DEC_SPLIT; ++i) {
+    for (int i = 0; i < S; ++i) {
       const float mi = wv[i * DEC_WS];
       const float w = (mi == -INFINITY) ? 0.f : expf(mi - M);
       Lsum += wv[i * DEC_WS + 1] * w;
@@ -473,22 +459,31 @@ int launch_kv_store(const uint16_t* hi, const uint16_t* lo, void* kc, void* vc, 
   else kv_store_kernel<float><<<grid, 256, 0, st>>>(hi, lo, (float*)kc, (float*)vc, Lp, nrows, H, d, Lmax);
   return cudaGetLastError() == cudaSuccess ? BEVGEN_OK : BEVGEN_ERR_CUDA;
 }
-int dec_attn_workspace_floats(int B, int H) { return B * H * DEC_SPLIT * DEC_WS; }
+static inline int dec_splits(int Lmax) { return (Lmax + DEC_CHUNK - 1) / DEC_CHUNK; }
+int dec_attn_workspace_floats(int B, int H) { return B * H * DEC_MAX_SPLIT * DEC_WS; }
 
 int launch_dec_attn(const float* qkv_part, int ks, long long zstride, const float* bqkv, const float* y, const float* bias, int bias_ld,
                     void* kc, void* vc, int kv_bf16, float* x1, const int* step_ptr, float* ws, unsigned int* counters, int B, int nc, int H,
                     int d, int Lmax, float scale, unsigned int* row_counters, const float* ln_gamma, const float* ln_beta, float ln_eps,
                     uint16_t* ln_hi, uint16_t* ln_lo, cudaStream_t st) {
-  if (Lmax > DEC_MAXL || B < 1 || B > 65535 || d != H * 64 || (Lmax & 3)) return BEVGEN_ERR_ARG;
+  if (Lmax > DEC_MAXL || B < 1 || B > 65535 || d != H * 64 || (Lmax & 7) || dec_splits(Lmax) > DEC_MAX_SPLIT) return BEVGEN_ERR_ARG;
   if (ln_gamma != nullptr && (!row_counters || !ln_beta || !ln_hi || d > 1024)) return BEVGEN_ERR_ARG;
-  dim3 grid(H, B, DEC_SPLIT);
-  if (kv_bf16)
-    dec_attn_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(qkv_part, ks, zstride, bqkv, y, bias, bias_ld, (__nv_bfloat16*)kc, (__nv_bfloat16*)vc, x1,
-                                                         step_ptr, ws, counters, nc, H, d, Lmax, scale, row_counters, ln_gamma, ln_beta, ln_eps,
-                                                         ln_hi, ln_lo);
-  else
-    dec_attn_kernel<float><<<grid, 256, 0, st>>>(qkv_part, ks, zstride, bqkv, y, bias, bias_ld, (float*)kc, (float*)vc, x1, step_ptr, ws,
-                                                 counters, nc, H, d, Lmax, scale, row_counters, ln_gamma, ln_beta, ln_eps, ln_hi, ln_lo);
+  dim3 grid(H, B, dec_splits(Lmax));
+  if (kv_bf16) {
+    const int smem = 2 * 64 * DEC_CHUNK * 2;
+    dec_attn_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>(qkv_part, ks, zstride, bqkv, y, bias, bias_ld, (__nv_bfloat16*)kc, (__nv_bfloat16*)vc,
+                                                            x1, step_ptr, ws, counters, nc, H, d, Lmax, scale, row_counters, ln_gamma, ln_beta,
+                                                            ln_eps, ln_hi, ln_lo);
+  } else {
+    const int smem = 2 * 64 * DEC_CHUNK * 4;
+    static bool configured = false;
+    if (!configured) {
+      if (cudaFuncSetAttribute(dec_attn_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return BEVGEN_ERR_CUDA;
+      configured = true;
+    }
+    dec_attn_kernel<float><<<grid, 256, smem, st>>>(qkv_part, ks, zstride, bqkv, y, bias, bias_ld, (float*)kc, (float*)vc, x1, step_ptr, ws,
+                                                    counters, nc, H, d, Lmax, scale, row_counters, ln_gamma, ln_beta, ln_eps, ln_hi, ln_lo);
+  }
   return cudaGetLastError() == cudaSuccess ? BEVGEN_OK : BEVGEN_ERR_CUDA;
 }
 int launch_dec_sample(const float* part, int ks, long long zstride, int vpad, int V, float temperature, int top_k, int greedy,

@@ -317,18 +317,38 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
           const int n = mt * BM + et;
           if (n < n_out) {
             const float bias_n = p.fin_bias ? __ldg(p.fin_bias + n) : 0.f;
-            for (int bb = 0; bb < p.fin_rows; ++bb) {
-              float v = bias_n;
-              for (int z = 0; z < p.z_inner; ++z) v += __ldcg(p.out_f32 + (long long)z * p.out_zi_stride + (long long)bb * p.ldc + n);
-              if (p.fin_mode == GEMM_FIN_ACT) {
-                if (p.fin_gelu) v = gelu_erf(v);
-                __nv_bfloat16 h0, l0;
-                split_bf16(v, h0, l0);
-                p.fin_hi[(size_t)bb * n_out + n] = __bfloat16_as_ushort(h0);
-                if (p.fin_lo != nullptr) p.fin_lo[(size_t)bb * n_out + n] = __bfloat16_as_ushort(l0);
+            // 4 batch rows x up to 8 split partials = 32 independent L2 loads in flight per thread
+            for (int b0 = 0; b0 < p.fin_rows; b0 += 4) {
+              float v[4] = {bias_n, bias_n, bias_n, bias_n};
+              for (int z0 = 0; z0 < p.z_inner; z0 += 8) {
+                float t[4][8];
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                  for (int z = 0; z < 8; ++z)
+                    t[r][z] = (b0 + r < p.fin_rows && z0 + z < p.z_inner)
+                                  ? __ldcg(p.out_f32 + (long long)(z0 + z) * p.out_zi_stride + (long long)(b0 + r) * p.ldc + n) : 0.f;
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+                  v[r] += ((t[r][0] + t[r][1]) + (t[r][2] + t[r][3])) + ((t[r][4] + t[r][5]) + (t[r][6] + t[r][7]));
+              }
+              if (p.fin_mode == GEMM_FIN_RESID_LN) {
+                float rs[4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) rs[r] = (b0 + r < p.fin_rows) ? __ldcg(p.fin_resid + (size_t)(b0 + r) * n_out + n) : 0.f;
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+                  if (b0 + r < p.fin_rows) p.fin_x[(size_t)(b0 + r) * n_out + n] = v[r] + rs[r];
               } else {
-                v += __ldcg(p.fin_resid + (size_t)bb * n_out + n);
-                p.fin_x[(size_t)bb * n_out + n] = v;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                  if (b0 + r >= p.fin_rows) continue;
+                  const float a = p.fin_gelu ? gelu_erf(v[r]) : v[r];
+                  __nv_bfloat16 h0, l0;
+                  split_bf16(a, h0, l0);
+                  p.fin_hi[(size_t)(b0 + r) * n_out + n] = __bfloat16_as_ushort(h0);
+                  if (p.fin_lo != nullptr) p.fin_lo[(size_t)(b0 + r) * n_out + n] = __bfloat16_as_ushort(l0);
+                }
               }
             }
           }

@@ -66,7 +66,8 @@ class GPTSampler:
         self.cnt_h = torch.zeros(4 * d // 128 + 1, dtype=torch.int32, device=dev)      # MLP1 finalize tickets
         self.cnt_o = torch.zeros(d // 128 + 1, dtype=torch.int32, device=dev)          # MLP2 finalize tickets
         self.x2 = f32(self.Bp, d)
-        self.fuse_finalize = True
+        self.fuse_finalize = False       # split-K finalize inside the GEMMs (one tail CTA) measured slower than separate reduce kernels
+        self.fuse_ln2 = True             # ln2 applied by the last head CTA of the decode-attention kernel
         self.graph = None
         self._graph_key = None
         self.trace = None
@@ -123,12 +124,13 @@ class GPTSampler:
             self._gemm_t(lw["wqkv"], self.yp, 3 * d, d, self.part_qkv)
             ops.Stats.launches += 1
             fz = self.fuse_finalize
+            f2 = self.fuse_ln2 or fz
             _lib.check(lib.bevgen_dec_attention(_ptr(self.part_qkv), self.ks_d, self.Bp * 3 * d, _ptr(lw["bqkv"]), _ptr(self.y), _ptr(e.bias), e.L,
                                                 _ptr(self.kc[li]), _ptr(self.vc[li]), self.kv_bf16, _ptr(self.x1), _ptr(self.step), _ptr(self.attn_ws),
                                                 _ptr(self.attn_cnt), self.B, e.nc, H, d, self.Lmax, float(e.dh) ** -0.5,
-                                                _ptr(self.row_cnt) if fz else None, _ptr(lw["ln2"][0]) if fz else None,
-                                                _ptr(lw["ln2"][1]) if fz else None, 1e-5, _ptr(self.zp[0]) if fz else None,
-                                                _ptr(self.zp[1]) if fz else None, _stream()), "dec_attention")
+                                                _ptr(self.row_cnt) if f2 else None, _ptr(lw["ln2"][0]) if f2 else None,
+                                                _ptr(lw["ln2"][1]) if f2 else None, 1e-5, _ptr(self.zp[0]) if f2 else None,
+                                                _ptr(self.zp[1]) if f2 else None, _stream()), "dec_attention")
             last = li == len(e.layers) - 1
             nxt = e.ln_f if last else e.layers[li + 1]["ln1"]
             if fz:
@@ -140,7 +142,8 @@ class GPTSampler:
                              fin=dict(mode=2, rows=self.B, counters=self.cnt_o, hi=outp[0], lo=outp[1], bias=lw["b2"], resid=self.x1, x=self.x2,
                                       y=None if last else self.y, gamma=nxt[0], beta=nxt[1], eps=1e-5))
                 continue
-            self._reduce_ln(None, 0, None, self.x1, d, lw["ln2"], None, self.zp)
+            if not f2:
+                self._reduce_ln(None, 0, None, self.x1, d, lw["ln2"], None, self.zp)
             self._gemm_t(lw["w1"], self.zp, 4 * d, d, self.part_h)
             ops.Stats.launches += 1
             _lib.check(lib.bevgen_dec_reduce_act(_ptr(self.part_h), self.ks_d, self.Bp * 4 * d, _ptr(lw["b1"]), 1, _ptr(self.hp[0]), _ptr(self.hp[1]),
