@@ -106,6 +106,12 @@ __global__ void __launch_bounds__(256) dec_reduce_act_kernel(const float* __rest
 // KV cache.  K is stored transposed per (batch, head): [64][Lmax] so that the score pass (thread = key) is coalesced;
 // V is stored [Lmax][64] so that the P.V pass (thread = channel) is coalesced.  KVT = float (exact) or bf16 (fast mode).
 // ------------------------------------------------------------------------------------------------
+// K cache index: blocked by 128 keys so that the (64 x 128) slab a decode CTA needs is one contiguous 32 KB (fp32) block:
+//   K[b][h][j / 128][c][j % 128]          (Lmax must be a multiple of 128)
+__device__ __forceinline__ size_t k_index(size_t bh, int c, int j, int Lmax) {
+  return ((bh * (size_t)(Lmax >> 7) + (size_t)(j >> 7)) * 64 + (size_t)c) * 128 + (size_t)(j & 127);
+}
+
 template <typename T> __device__ __forceinline__ float kv_load(const T* p);
 template <> __device__ __forceinline__ float kv_load<float>(const float* p) { return *p; }
 template <> __device__ __forceinline__ float kv_load<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
@@ -135,7 +141,7 @@ __global__ void __launch_bounds__(256) kv_store_kernel(const uint16_t* __restric
   __syncthreads();
   for (int i = threadIdx.x; i < 64 * 64; i += 256) {
     const int c = i >> 6, rr = i & 63;
-    if (r0 + rr < nrows) kv_store(kc + (bh * 64 + c) * Lmax + r0 + rr, tile[rr][c]);
+    if (r0 + rr < nrows) kv_store(kc + k_index(bh, c, r0 + rr, Lmax), tile[rr][c]);
   }
 }
 
@@ -185,11 +191,10 @@ __global__ void __launch_bounds__(256) dec_attn_kernel(const float* __restrict__
     mbar_init(&bar, 1);
     fence_barrier_init();
     if (cnt > 0) {
-      const uint32_t row_bytes = pitch * sizeof(KVT);
-      mbar_expect_tx(&bar, 65u * 0u + 64u * row_bytes + (uint32_t)pitch * 64u * (uint32_t)sizeof(KVT));
-      const KVT* kb = kc + bh * 64 * Lmax + j0;
-      for (int c = 0; c < 64; ++c) bulk_g2s(Ks + c * pitch, kb + (size_t)c * Lmax, row_bytes, &bar);
-      bulk_g2s(Vs, vc + (bh * Lmax + j0) * 64, (uint32_t)pitch * 64u * (uint32_t)sizeof(KVT), &bar);
+      const uint32_t kbytes = 64u * DEC_CHUNK * (uint32_t)sizeof(KVT), vbytes = (uint32_t)pitch * 64u * (uint32_t)sizeof(KVT);
+      mbar_expect_tx(&bar, kbytes + vbytes);
+      bulk_g2s(Ks, kc + k_index(bh, 0, j0, Lmax), kbytes, &bar);           // whole 128-key K^T block: one contiguous copy
+      bulk_g2s(Vs, vc + (bh * Lmax + j0) * 64, vbytes, &bar);
     }
   }
   if (tid < 192) {
@@ -202,7 +207,7 @@ __global__ void __launch_bounds__(256) dec_attn_kernel(const float* __restrict__
       for (; z + 4 <= ks; z += 4) v += (pp[z * zstride] + pp[(z + 1) * zstride]) + (pp[(z + 2) * zstride] + pp[(z + 3) * zstride]);
       for (; z < ks; ++z) v += pp[z * zstride];
       if (which == 0) q[c] = v;
-      else if (which == 1) { knew[c] = v; kv_store(kc + (bh * 64 + c) * Lmax + r, v); }
+      else if (which == 1) { knew[c] = v; kv_store(kc + k_index(bh, c, r, Lmax), v); }
       else { vnew[c] = v; kv_store(vc + (bh * Lmax + r) * 64 + c, v); }
     }
   }
@@ -211,7 +216,7 @@ __global__ void __launch_bounds__(256) dec_attn_kernel(const float* __restrict__
   if (cnt > 0) {
     mbar_wait(&bar, 0);
     if (owns_new && tid < 64) {        // the slab may hold a stale copy of the newest key: take it from registers instead
-      kv_store(Ks + tid * pitch + (r - j0), knew[tid]);
+      kv_store(Ks + tid * DEC_CHUNK + (r - j0), knew[tid]);
       kv_store(Vs + (size_t)(r - j0) * 64 + tid, vnew[tid]);
     }
     __syncthreads();
@@ -220,8 +225,8 @@ __global__ void __launch_bounds__(256) dec_attn_kernel(const float* __restrict__
       float d0 = 0.f, d1 = 0.f;
 #pragma unroll
       for (int c = 0; c < 64; c += 2) {
-        d0 = fmaf(q[c], kv_load(Ks + c * pitch + tid), d0);
-        d1 = fmaf(q[c + 1], kv_load(Ks + (c + 1) * pitch + tid), d1);
+        d0 = fmaf(q[c], kv_load(Ks + c * DEC_CHUNK + tid), d0);
+        d1 = fmaf(q[c + 1], kv_load(Ks + (c + 1) * DEC_CHUNK + tid), d1);
       }
       m = ((d0 + d1) + (brow ? brow[tid] : 0.f)) * scale;
     }
@@ -453,7 +458,7 @@ int launch_dec_reduce_act(const float* partials, int ks, long long zstride, cons
 }
 int launch_kv_store(const uint16_t* hi, const uint16_t* lo, void* kc, void* vc, int kv_bf16, int B, int Lp, int nrows, int H, int d, int Lmax,
                     cudaStream_t st) {
-  if (B < 1 || B > 65535 || nrows < 1) return BEVGEN_ERR_ARG;
+  if (B < 1 || B > 65535 || nrows < 1 || (Lmax & 127)) return BEVGEN_ERR_ARG;
   dim3 grid(H, B, (nrows + 63) / 64);
   if (kv_bf16) kv_store_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(hi, lo, (__nv_bfloat16*)kc, (__nv_bfloat16*)vc, Lp, nrows, H, d, Lmax);
   else kv_store_kernel<float><<<grid, 256, 0, st>>>(hi, lo, (float*)kc, (float*)vc, Lp, nrows, H, d, Lmax);
@@ -466,7 +471,7 @@ int launch_dec_attn(const float* qkv_part, int ks, long long zstride, const floa
                     void* kc, void* vc, int kv_bf16, float* x1, const int* step_ptr, float* ws, unsigned int* counters, int B, int nc, int H,
                     int d, int Lmax, float scale, unsigned int* row_counters, const float* ln_gamma, const float* ln_beta, float ln_eps,
                     uint16_t* ln_hi, uint16_t* ln_lo, cudaStream_t st) {
-  if (Lmax > DEC_MAXL || B < 1 || B > 65535 || d != H * 64 || (Lmax & 7) || dec_splits(Lmax) > DEC_MAX_SPLIT) return BEVGEN_ERR_ARG;
+  if (Lmax > DEC_MAXL || B < 1 || B > 65535 || d != H * 64 || (Lmax & 127) || dec_splits(Lmax) > DEC_MAX_SPLIT) return BEVGEN_ERR_ARG;
   if (ln_gamma != nullptr && (!row_counters || !ln_beta || !ln_hi || d > 1024)) return BEVGEN_ERR_ARG;
   dim3 grid(H, B, dec_splits(Lmax));
   if (kv_bf16) {

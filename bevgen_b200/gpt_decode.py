@@ -37,8 +37,8 @@ class GPTSampler:
         self.kv_bf16 = int((kv_dtype or (torch.float32 if e.npass == 3 else torch.bfloat16)) == torch.bfloat16)
         kvt = torch.bfloat16 if self.kv_bf16 else torch.float32
         nl = len(e.layers)
-        self.Lmax = e.L
-        self.kc = [torch.zeros((B, H, 64, self.Lmax), dtype=kvt, device=dev) for _ in range(nl)]
+        self.Lmax = ((e.L + 127) // 128) * 128          # K cache is blocked by 128 keys
+        self.kc = [torch.zeros((B, H, self.Lmax // 128, 64, 128), dtype=kvt, device=dev) for _ in range(nl)]
         self.vc = [torch.zeros((B, H, self.Lmax, 64), dtype=kvt, device=dev) for _ in range(nl)]
         self.step = torch.zeros(1, dtype=torch.int32, device=dev)
         self.cam_idx = torch.full((B, e.cfg.num_cams, e.cfg.num_cam_tokens), e.cfg.vocab_size, dtype=torch.int64, device=dev)

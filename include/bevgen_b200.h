@@ -171,7 +171,8 @@ BEVGEN_API int bevgen_dec_reduce_ln(const float* partials, int ks, long long zst
 /* planes[b][n] = act(bias[n] + sum_z partials[z][b][n]); gelu != 0 -> exact-erf GELU */
 BEVGEN_API int bevgen_dec_reduce_act(const float* partials, int ks, long long zstride, const float* bias, int gelu, void* out_hi, void* out_lo,
                                      int rows, int n, void* stream);
-/* prefill: rows [0,nrows) of the fused qkv planes [batch][lp][3d] -> K cache [batch][heads][64][lmax], V cache [batch][heads][lmax][64] */
+/* prefill: rows [0,nrows) of the fused qkv planes [batch][lp][3d] -> K cache [batch][heads][lmax/128][64][128] (blocked, transposed),
+ * V cache [batch][heads][lmax][64]; lmax % 128 == 0 */
 BEVGEN_API int bevgen_kv_store(const void* qkv_hi, const void* qkv_lo, void* k_cache, void* v_cache, int kv_bf16, int batch, int lp, int nrows,
                                int heads, int d, int lmax, void* stream);
 /* one decode row: finish q/k/v (+bias), append k/v, softmax(scale*(q.K + camera_bias[r][:])) V, x1 = y + heads concat.
