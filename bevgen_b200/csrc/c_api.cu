@@ -280,11 +280,13 @@ BEVGEN_API int bevgen_dec_attention(const float* qkv_partials, int ks, long long
                                     const int* step_ptr, float* workspace, unsigned int* counters, int batch, int n_cond, int heads, int d,
                                     int lmax, float scale, unsigned int* row_counters, const float* ln_gamma, const float* ln_beta, float ln_eps,
                                     void* ln_hi, void* ln_lo, void* stream) {
+  int rc0 = ensure_init();
+  if (rc0) return rc0;
   if (!qkv_partials || !qkv_bias || !y || !k_cache || !v_cache || !x1 || !step_ptr || !workspace || !counters || ks < 1)
     return fail(BEVGEN_ERR_ARG, "dec_attention: bad args");
   CHECK_LAUNCH(launch_dec_attn(qkv_partials, ks, zstride, qkv_bias, y, camera_bias, bias_ld, k_cache, v_cache, kv_bf16, x1, step_ptr, workspace,
                                counters, batch, n_cond, heads, d, lmax, scale, row_counters, ln_gamma, ln_beta, ln_eps, (uint16_t*)ln_hi,
-                               (uint16_t*)ln_lo, (cudaStream_t)stream), "dec_attention");
+                               (uint16_t*)ln_lo, g_sm_count, (cudaStream_t)stream), "dec_attention");
 }
 
 BEVGEN_API int bevgen_dec_attention_workspace_floats(int batch, int heads) { return dec_attn_workspace_floats(batch, heads); }

@@ -156,71 +156,94 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                : "memory");
 }
 
-// grid (heads, batch, splits), 256 threads.  Each CTA owns a contiguous range of <= DEC_CHUNK keys.  One thread issues bulk
-// async copies (cp.async.bulk -> mbarrier) for the K^T slab (64 row segments) and the V slab (one contiguous block) of that range
-// at kernel entry, so the whole KV traffic of the CTA is in flight while the other threads finish q (and k/v of the newest key,
-// appended to the cache by the CTA that owns it) from the split-K partials of the QKV GEMM.  Scores (thread = key, camera-bias row
-// added BEFORE the 1/sqrt(d_head) scale), block softmax and P.V (thread = channel) then run out of shared memory; the CTA leaves an
-// (m, l, o[64]) partial and the last CTA to arrive per (batch, head) merges them: x1 = y + concat_heads(softmax(...) V)
-// (flash-decoding with a fused combine).  Optionally the last head of a batch row applies LayerNorm (ln2) to the finished row.
+constexpr int DEC_STAGES = 3;
+
+// Persistent decode attention: grid = #SMs, 256 threads.  Work items are (batch*head, 128-key block) pairs for the blocks that hold
+// keys (ceil(n/128) per pair); every CTA walks items c, c+G, c+2G, ... with a 3-deep shared-memory ring: one thread issues the bulk
+// async copies (cp.async.bulk -> mbarrier) of the K^T block (64 x 128, one contiguous 32 KB piece of the blocked cache) and of the
+// V rows two items ahead, so ~128 KB of KV traffic per SM is always in flight while the current item is processed:
+//   finish q for (batch, head) from the split-K partials of the QKV GEMM (+bias); the item holding the newest key also finishes
+//   k/v, appends them to the cache and patches its shared-memory copy;  scores with thread = key (camera-bias row added BEFORE
+//   the 1/sqrt(d_head) scale), block softmax, P.V with thread = channel;  (m, l, o[64]) partial to a workspace;  the last item to
+//   arrive per (batch, head) merges the partials: x1 = y + concat_heads(softmax(...) V)   (flash-decoding, fused combine);
+//   optionally the last head of a batch row applies LayerNorm (ln2) to the finished row and writes the MLP operand planes.
 template <typename KVT>
-__global__ void __launch_bounds__(256) dec_attn_kernel(const float* __restrict__ qkv_part, int ks, long long zstride,
-                                                       const float* __restrict__ bqkv, const float* __restrict__ y,
-                                                       const float* __restrict__ bias, int bias_ld, KVT* __restrict__ kc,
-                                                       KVT* __restrict__ vc, float* __restrict__ x1, const int* __restrict__ step_ptr,
-                                                       float* __restrict__ ws, unsigned int* __restrict__ counters, int nc, int H, int d,
-                                                       int Lmax, float scale, unsigned int* __restrict__ row_counters,
-                                                       const float* __restrict__ ln_gamma, const float* __restrict__ ln_beta, float ln_eps,
-                                                       uint16_t* __restrict__ ln_hi, uint16_t* __restrict__ ln_lo) {
+__global__ void __launch_bounds__(256, 1) dec_attn_kernel(const float* __restrict__ qkv_part, int ks, long long zstride,
+                                                          const float* __restrict__ bqkv, const float* __restrict__ y,
+                                                          const float* __restrict__ bias, int bias_ld, KVT* __restrict__ kc,
+                                                          KVT* __restrict__ vc, float* __restrict__ x1, const int* __restrict__ step_ptr,
+                                                          float* __restrict__ ws, unsigned int* __restrict__ counters, int nc, int B, int H,
+                                                          int d, int Lmax, float scale, unsigned int* __restrict__ row_counters,
+                                                          const float* __restrict__ ln_gamma, const float* __restrict__ ln_beta, float ln_eps,
+                                                          uint16_t* __restrict__ ln_hi, uint16_t* __restrict__ ln_lo) {
   extern __shared__ __align__(128) uint8_t dsm[];
-  KVT* Ks = reinterpret_cast<KVT*>(dsm);                                  // [64][pitch]
-  KVT* Vs = reinterpret_cast<KVT*>(dsm + 64 * DEC_CHUNK * sizeof(KVT));   // [keys][64]
+  constexpr uint32_t KBYTES = 64u * DEC_CHUNK * (uint32_t)sizeof(KVT);
   __shared__ float q[64], knew[64], vnew[64], red[8], sc[DEC_CHUNK];
   __shared__ float opart[4][64];
-  __shared__ __align__(8) uint64_t bar;
+  __shared__ __align__(8) uint64_t full[DEC_STAGES];
   __shared__ unsigned int ticket;
-  const int h = blockIdx.x, b = blockIdx.y, sp = blockIdx.z, S = gridDim.z, tid = threadIdx.x;
+  const int tid = threadIdx.x;
   const int r = nc + *step_ptr - 1;
   const int n = r + 1;
-  const int j0 = sp * DEC_CHUNK;
-  const int cnt = max(0, min(n - j0, DEC_CHUNK));          // valid keys of this CTA (key r included if in range)
-  const int pitch = (cnt + 7) & ~7;                        // copied keys: 16-byte granules; stale tail entries are never used
-  const bool owns_new = (r >= j0 && r < j0 + DEC_CHUNK);
-  const size_t bh = (size_t)b * H + h;
+  const int nsp = (n + DEC_CHUNK - 1) / DEC_CHUNK;           // key blocks in use
+  const int items = B * H * nsp;
+  const int G = gridDim.x;
+
+  auto issue = [&](int it) {                                 // thread 0 only
+    const int item = blockIdx.x + it * G;
+    if (item >= items) return;
+    const int st = it % DEC_STAGES;
+    const size_t bh = item / nsp;
+    const int j0 = (item % nsp) * DEC_CHUNK;
+    const int cnt = min(n - j0, DEC_CHUNK);
+    const uint32_t vbytes = (uint32_t)((cnt + 7) & ~7) * 64u * (uint32_t)sizeof(KVT);
+    uint8_t* base = dsm + (size_t)st * 2 * KBYTES;
+    mbar_expect_tx(&full[st], KBYTES + vbytes);
+    bulk_g2s(base, kc + k_index(bh, 0, j0, Lmax), KBYTES, &full[st]);
+    bulk_g2s(base + KBYTES, vc + (bh * Lmax + j0) * 64, vbytes, &full[st]);
+  };
+
   if (tid == 0) {
-    mbar_init(&bar, 1);
+    for (int s = 0; s < DEC_STAGES; ++s) mbar_init(&full[s], 1);
     fence_barrier_init();
-    if (cnt > 0) {
-      const uint32_t kbytes = 64u * DEC_CHUNK * (uint32_t)sizeof(KVT), vbytes = (uint32_t)pitch * 64u * (uint32_t)sizeof(KVT);
-      mbar_expect_tx(&bar, kbytes + vbytes);
-      bulk_g2s(Ks, kc + k_index(bh, 0, j0, Lmax), kbytes, &bar);           // whole 128-key K^T block: one contiguous copy
-      bulk_g2s(Vs, vc + (bh * Lmax + j0) * 64, vbytes, &bar);
-    }
+    for (int s = 0; s < DEC_STAGES - 1; ++s) issue(s);
   }
-  if (tid < 192) {
-    const int which = tid >> 6, c = tid & 63;
-    if (cnt > 0 && (which == 0 || owns_new)) {
-      const int col = which * d + h * 64 + c;
-      const float* pp = qkv_part + (size_t)b * 3 * d + col;
-      float v = __ldg(bqkv + col);
-      int z = 0;
-      for (; z + 4 <= ks; z += 4) v += (pp[z * zstride] + pp[(z + 1) * zstride]) + (pp[(z + 2) * zstride] + pp[(z + 3) * zstride]);
-      for (; z < ks; ++z) v += pp[z * zstride];
-      if (which == 0) q[c] = v;
-      else if (which == 1) { knew[c] = v; kv_store(kc + k_index(bh, c, r, Lmax), v); }
-      else { vnew[c] = v; kv_store(vc + (bh * Lmax + r) * 64 + c, v); }
+  for (int it = 0;; ++it) {
+    const int item = blockIdx.x + it * G;
+    if (item >= items) break;
+    const int st = it % DEC_STAGES;
+    const int bh = item / nsp, sp = item % nsp;
+    const int b = bh / H, h = bh % H;
+    const int j0 = sp * DEC_CHUNK;
+    const int cnt = min(n - j0, DEC_CHUNK);
+    const bool owns_new = (sp == nsp - 1);
+    KVT* Ks = reinterpret_cast<KVT*>(dsm + (size_t)st * 2 * KBYTES);
+    KVT* Vs = reinterpret_cast<KVT*>(dsm + (size_t)st * 2 * KBYTES + KBYTES);
+    __syncthreads();                                         // everyone is done with the previous item's smem
+    if (tid == 0) issue(it + DEC_STAGES - 1);                // refill the stage that was just released
+    if (tid < 192) {
+      const int which = tid >> 6, c = tid & 63;
+      if (which == 0 || owns_new) {
+        const int col = which * d + h * 64 + c;
+        const float* pp = qkv_part + (size_t)b * 3 * d + col;
+        float v = __ldg(bqkv + col);
+        int z = 0;
+        for (; z + 4 <= ks; z += 4) v += (pp[z * zstride] + pp[(z + 1) * zstride]) + (pp[(z + 2) * zstride] + pp[(z + 3) * zstride]);
+        for (; z < ks; ++z) v += pp[z * zstride];
+        if (which == 0) q[c] = v;
+        else if (which == 1) { knew[c] = v; kv_store(kc + k_index(bh, c, r, Lmax), v); }
+        else { vnew[c] = v; kv_store(vc + ((size_t)bh * Lmax + r) * 64 + c, v); }
+      }
     }
-  }
-  __syncthreads();
-  float m = -INFINITY, sum = 0.f;
-  if (cnt > 0) {
-    mbar_wait(&bar, 0);
-    if (owns_new && tid < 64) {        // the slab may hold a stale copy of the newest key: take it from registers instead
+    __syncthreads();
+    mbar_wait(&full[st], (it / DEC_STAGES) & 1);
+    if (owns_new && tid < 64) {        // the staged block may hold a stale copy of the newest key: patch it
       kv_store(Ks + tid * DEC_CHUNK + (r - j0), knew[tid]);
       kv_store(Vs + (size_t)(r - j0) * 64 + tid, vnew[tid]);
     }
     __syncthreads();
     const float* brow = bias ? bias + (size_t)r * bias_ld + j0 : nullptr;
+    float m = -INFINITY;
     if (tid < cnt) {
       float d0 = 0.f, d1 = 0.f;
 #pragma unroll
@@ -233,70 +256,69 @@ __global__ void __launch_bounds__(256) dec_attn_kernel(const float* __restrict__
     const float mloc = block_max_256(m, red);
     float e = 0.f;
     if (tid < cnt) { e = expf(m - mloc); sc[tid] = e; }
-    sum = block_sum_256(e, red);       // its barriers publish sc[]
-    m = mloc;
-    const int g = tid >> 6, c = tid & 63;
-    float a0 = 0.f, a1 = 0.f;
-    int jj = g;
-    for (; jj + 4 < cnt; jj += 8) {
-      a0 = fmaf(sc[jj], kv_load(Vs + (size_t)jj * 64 + c), a0);
-      a1 = fmaf(sc[jj + 4], kv_load(Vs + (size_t)(jj + 4) * 64 + c), a1);
+    const float sum = block_sum_256(e, red);       // its barriers publish sc[]
+    {
+      const int g = tid >> 6, c = tid & 63;
+      float a0 = 0.f, a1 = 0.f;
+      int jj = g;
+      for (; jj + 4 < cnt; jj += 8) {
+        a0 = fmaf(sc[jj], kv_load(Vs + (size_t)jj * 64 + c), a0);
+        a1 = fmaf(sc[jj + 4], kv_load(Vs + (size_t)(jj + 4) * 64 + c), a1);
+      }
+      if (jj < cnt) a0 = fmaf(sc[jj], kv_load(Vs + (size_t)jj * 64 + c), a0);
+      opart[g][c] = a0 + a1;
     }
-    if (jj < cnt) a0 = fmaf(sc[jj], kv_load(Vs + (size_t)jj * 64 + c), a0);
-    opart[g][c] = a0 + a1;
-  } else if (tid < 256) {
-    opart[tid >> 6][tid & 63] = 0.f;
-  }
-  __syncthreads();
-  float* wp = ws + (bh * S + sp) * DEC_WS;
-  if (tid < 64) {
-    wp[4 + tid] = (opart[0][tid] + opart[1][tid]) + (opart[2][tid] + opart[3][tid]);
-    if (tid == 0) { wp[0] = m; wp[1] = sum; }
-  }
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) ticket = atomicAdd(&counters[bh], 1u);
-  __syncthreads();
-  if (ticket != (unsigned)(S - 1)) return;
-  __threadfence();
-  if (tid < 64) {
-    const volatile float* wv = ws + bh * S * DEC_WS;
-    float M = -INFINITY;
-    for (int i = 0; i < S; ++i) M = fmaxf(M, wv[i * DEC_WS]);
-    float Lsum = 0.f, o = 0.f;
-    for (int i = 0; i < S; ++i) {
-      const float mi = wv[i * DEC_WS];
-      const float w = (mi == -INFINITY) ? 0.f : expf(mi - M);
-      Lsum += wv[i * DEC_WS + 1] * w;
-      o += wv[i * DEC_WS + 4 + tid] * w;
+    __syncthreads();
+    float* wp = ws + ((size_t)bh * DEC_MAX_SPLIT + sp) * DEC_WS;
+    if (tid < 64) {
+      wp[4 + tid] = (opart[0][tid] + opart[1][tid]) + (opart[2][tid] + opart[3][tid]);
+      if (tid == 0) { wp[0] = mloc; wp[1] = sum; }
     }
-    const size_t idx = (size_t)b * d + h * 64 + tid;
-    x1[idx] = y[idx] + o / Lsum;
-    if (tid == 0) counters[bh] = 0u;      // self-reset for the next launch
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) ticket = atomicAdd(&counters[bh], 1u);
+    __syncthreads();
+    if (ticket != (unsigned)(nsp - 1)) continue;
+    __threadfence();
+    if (tid < 64) {
+      const volatile float* wv = ws + (size_t)bh * DEC_MAX_SPLIT * DEC_WS;
+      float M = -INFINITY;
+      for (int i = 0; i < nsp; ++i) M = fmaxf(M, wv[i * DEC_WS]);
+      float Lsum = 0.f, o = 0.f;
+      for (int i = 0; i < nsp; ++i) {
+        const float w = expf(wv[i * DEC_WS] - M);
+        Lsum += wv[i * DEC_WS + 1] * w;
+        o += wv[i * DEC_WS + 4 + tid] * w;
+      }
+      const size_t idx = (size_t)b * d + h * 64 + tid;
+      x1[idx] = y[idx] + o / Lsum;
+      if (tid == 0) counters[bh] = 0u;      // self-reset for the next launch
+    }
+    if (ln_gamma == nullptr) continue;
+    // ---- fused LayerNorm (ln2): the last head of batch row b normalises x1[b,:] into the MLP operand planes
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) ticket = atomicAdd(&row_counters[b], 1u);
+    __syncthreads();
+    if (ticket != (unsigned)(H - 1)) continue;
+    __threadfence();
+    const bool act = tid < (d >> 2);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (act) v = __ldcg(reinterpret_cast<const float4*>(x1 + (size_t)b * d) + tid);
+    const float mean = block_sum_256(act ? (v.x + v.y) + (v.z + v.w) : 0.f, red) / d;
+    v.x -= mean; v.y -= mean; v.z -= mean; v.w -= mean;
+    const float var = block_sum_256(act ? (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w) : 0.f, red) / d;
+    const float rstd = rsqrtf(var + ln_eps);
+    if (tid == 0) row_counters[b] = 0u;
+    if (act) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(ln_gamma) + tid), be = __ldg(reinterpret_cast<const float4*>(ln_beta) + tid);
+      const float4 o4 = make_float4(v.x * rstd * g.x + be.x, v.y * rstd * g.y + be.y, v.z * rstd * g.z + be.z, v.w * rstd * g.w + be.w);
+      __nv_bfloat16 h0, l0, h1, l1, h2, l2, h3, l3;
+      split_bf16(o4.x, h0, l0); split_bf16(o4.y, h1, l1); split_bf16(o4.z, h2, l2); split_bf16(o4.w, h3, l3);
+      reinterpret_cast<uint2*>(ln_hi + (size_t)b * d)[tid] = make_uint2(pack_bf16(h0, h1), pack_bf16(h2, h3));
+      if (ln_lo != nullptr) reinterpret_cast<uint2*>(ln_lo + (size_t)b * d)[tid] = make_uint2(pack_bf16(l0, l1), pack_bf16(l2, l3));
+    }
   }
-  if (ln_gamma == nullptr) return;
-  // ---- fused LayerNorm (ln2) of the finished row: the last head of batch row b normalises x1[b,:] into the MLP operand planes
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) ticket = atomicAdd(&row_counters[b], 1u);
-  __syncthreads();
-  if (ticket != (unsigned)(H - 1)) return;
-  __threadfence();
-  const bool act = tid < (d >> 2);
-  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (act) v = __ldcg(reinterpret_cast<const float4*>(x1 + (size_t)b * d) + tid);
-  const float mean = block_sum_256(act ? (v.x + v.y) + (v.z + v.w) : 0.f, red) / d;
-  v.x -= mean; v.y -= mean; v.z -= mean; v.w -= mean;
-  const float var = block_sum_256(act ? (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w) : 0.f, red) / d;
-  const float rstd = rsqrtf(var + ln_eps);
-  if (tid == 0) row_counters[b] = 0u;
-  if (!act) return;
-  const float4 g = __ldg(reinterpret_cast<const float4*>(ln_gamma) + tid), be = __ldg(reinterpret_cast<const float4*>(ln_beta) + tid);
-  const float4 o4 = make_float4(v.x * rstd * g.x + be.x, v.y * rstd * g.y + be.y, v.z * rstd * g.z + be.z, v.w * rstd * g.w + be.w);
-  __nv_bfloat16 h0, l0, h1, l1, h2, l2, h3, l3;
-  split_bf16(o4.x, h0, l0); split_bf16(o4.y, h1, l1); split_bf16(o4.z, h2, l2); split_bf16(o4.w, h3, l3);
-  reinterpret_cast<uint2*>(ln_hi + (size_t)b * d)[tid] = make_uint2(pack_bf16(h0, h1), pack_bf16(h2, h3));
-  if (ln_lo != nullptr) reinterpret_cast<uint2*>(ln_lo + (size_t)b * d)[tid] = make_uint2(pack_bf16(l0, l1), pack_bf16(l2, l3));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -467,29 +489,34 @@ int launch_kv_store(const uint16_t* hi, const uint16_t* lo, void* kc, void* vc, 
 static inline int dec_splits(int Lmax) { return (Lmax + DEC_CHUNK - 1) / DEC_CHUNK; }
 int dec_attn_workspace_floats(int B, int H) { return B * H * DEC_MAX_SPLIT * DEC_WS; }
 
+template <typename KVT>
+static int launch_dec_attn_t(const float* qkv_part, int ks, long long zstride, const float* bqkv, const float* y, const float* bias, int bias_ld,
+                             KVT* kc, KVT* vc, float* x1, const int* step_ptr, float* ws, unsigned int* counters, int B, int nc, int H, int d,
+                             int Lmax, float scale, unsigned int* row_counters, const float* ln_gamma, const float* ln_beta, float ln_eps,
+                             uint16_t* ln_hi, uint16_t* ln_lo, int sm_count, cudaStream_t st) {
+  const int smem = DEC_STAGES * 2 * 64 * DEC_CHUNK * (int)sizeof(KVT);
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(dec_attn_kernel<KVT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return BEVGEN_ERR_CUDA;
+    configured = true;
+  }
+  const int per_sm = (sizeof(KVT) == 2) ? 2 : 1;      // bf16 ring is 96 KB: two CTAs per SM
+  dec_attn_kernel<KVT><<<sm_count * per_sm, 256, smem, st>>>(qkv_part, ks, zstride, bqkv, y, bias, bias_ld, kc, vc, x1, step_ptr, ws, counters, nc, B,
+                                                             H, d, Lmax, scale, row_counters, ln_gamma, ln_beta, ln_eps, ln_hi, ln_lo);
+  return cudaGetLastError() == cudaSuccess ? BEVGEN_OK : BEVGEN_ERR_CUDA;
+}
+
 int launch_dec_attn(const float* qkv_part, int ks, long long zstride, const float* bqkv, const float* y, const float* bias, int bias_ld,
                     void* kc, void* vc, int kv_bf16, float* x1, const int* step_ptr, float* ws, unsigned int* counters, int B, int nc, int H,
                     int d, int Lmax, float scale, unsigned int* row_counters, const float* ln_gamma, const float* ln_beta, float ln_eps,
-                    uint16_t* ln_hi, uint16_t* ln_lo, cudaStream_t st) {
+                    uint16_t* ln_hi, uint16_t* ln_lo, int sm_count, cudaStream_t st) {
   if (Lmax > DEC_MAXL || B < 1 || B > 65535 || d != H * 64 || (Lmax & 127) || dec_splits(Lmax) > DEC_MAX_SPLIT) return BEVGEN_ERR_ARG;
   if (ln_gamma != nullptr && (!row_counters || !ln_beta || !ln_hi || d > 1024)) return BEVGEN_ERR_ARG;
-  dim3 grid(H, B, dec_splits(Lmax));
-  if (kv_bf16) {
-    const int smem = 2 * 64 * DEC_CHUNK * 2;
-    dec_attn_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>(qkv_part, ks, zstride, bqkv, y, bias, bias_ld, (__nv_bfloat16*)kc, (__nv_bfloat16*)vc,
-                                                            x1, step_ptr, ws, counters, nc, H, d, Lmax, scale, row_counters, ln_gamma, ln_beta,
-                                                            ln_eps, ln_hi, ln_lo);
-  } else {
-    const int smem = 2 * 64 * DEC_CHUNK * 4;
-    static bool configured = false;
-    if (!configured) {
-      if (cudaFuncSetAttribute(dec_attn_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return BEVGEN_ERR_CUDA;
-      configured = true;
-    }
-    dec_attn_kernel<float><<<grid, 256, smem, st>>>(qkv_part, ks, zstride, bqkv, y, bias, bias_ld, (float*)kc, (float*)vc, x1, step_ptr, ws,
-                                                    counters, nc, H, d, Lmax, scale, row_counters, ln_gamma, ln_beta, ln_eps, ln_hi, ln_lo);
-  }
-  return cudaGetLastError() == cudaSuccess ? BEVGEN_OK : BEVGEN_ERR_CUDA;
+  if (kv_bf16)
+    return launch_dec_attn_t<__nv_bfloat16>(qkv_part, ks, zstride, bqkv, y, bias, bias_ld, (__nv_bfloat16*)kc, (__nv_bfloat16*)vc, x1, step_ptr, ws,
+                                            counters, B, nc, H, d, Lmax, scale, row_counters, ln_gamma, ln_beta, ln_eps, ln_hi, ln_lo, sm_count, st);
+  return launch_dec_attn_t<float>(qkv_part, ks, zstride, bqkv, y, bias, bias_ld, (float*)kc, (float*)vc, x1, step_ptr, ws, counters, B, nc, H, d,
+                                  Lmax, scale, row_counters, ln_gamma, ln_beta, ln_eps, ln_hi, ln_lo, sm_count, st);
 }
 int launch_dec_sample(const float* part, int ks, long long zstride, int vpad, int V, float temperature, int top_k, int greedy,
                       unsigned long long seed, const long long* forced, const int* fwd, long long* cam_idx, long long* tokens_out, float* trace,

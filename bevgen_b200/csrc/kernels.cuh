@@ -74,7 +74,7 @@ int launch_kv_store(const uint16_t* hi, const uint16_t* lo, void* kc, void* vc, 
 int launch_dec_attn(const float* qkv_part, int ks, long long zstride, const float* bqkv, const float* y, const float* bias, int bias_ld,
                     void* kc, void* vc, int kv_bf16, float* x1, const int* step_ptr, float* ws, unsigned int* counters, int B, int nc, int H,
                     int d, int Lmax, float scale, unsigned int* row_counters, const float* ln_gamma, const float* ln_beta, float ln_eps,
-                    uint16_t* ln_hi, uint16_t* ln_lo, cudaStream_t st);
+                    uint16_t* ln_hi, uint16_t* ln_lo, int sm_count, cudaStream_t st);
 int dec_attn_workspace_floats(int B, int H);
 int launch_dec_sample(const float* part, int ks, long long zstride, int vpad, int V, float temperature, int top_k, int greedy,
                       unsigned long long seed, const long long* forced, const int* fwd, long long* cam_idx, long long* tokens_out, float* trace,
