@@ -156,237 +156,147 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                : "memory");
 }
 
-template <typename T> struct KV2;
-template <> struct KV2<float> {
-  static __device__ __forceinline__ float2 load(const float* p) { return *reinterpret_cast<const float2*>(p); }
-};
-template <> struct KV2<__nv_bfloat16> {
-  static __device__ __forceinline__ float2 load(const __nv_bfloat16* p) {
-    const uint32_t u = *reinterpret_cast<const uint32_t*>(p);
-    return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
-  }
-};
-
-constexpr int DEC_STAGES = 3;
-constexpr int DEC_KSPLIT = 2;         // key-range halves per (batch, head): 2 * B * H work items per launch
-
-// Persistent decode attention: grid = #SMs, 9 warps.  A work item is one half of the key range of a (batch, head) pair; every CTA walks
-// items c, c+G, ... .  Warp 8 is the producer: it streams the 128-key blocks of the CTA's items through a 3-deep shared-memory ring with
-// bulk async copies (cp.async.bulk -> mbarrier; K^T block = one contiguous 32 KB piece of the blocked cache, V rows contiguous), running
-// ahead across item boundaries, so ~128 KB of KV traffic per SM stays in flight.  Warps 0-7 are consumers with NO block-wide barrier in the
-// block loop: warp w owns keys [16w, 16w+16) of every block and keeps its own online-softmax state (m, l, 2 channels per lane):
-//   scores: lane = (key, half of the 64 channels) out of shared memory, camera-bias row added BEFORE the 1/sqrt(d_head) scale;
-//   P.V: lane = channel pair, probabilities broadcast by shuffle.
-// Per item: q (and k/v of the newest key, appended to the cache by the item that owns it) are finished from the split-K partials of the
-// QKV GEMM; the 8 warp states are merged in shared memory, the item's (m, l, o[64]) goes to a workspace and the last item per
-// (batch, head) merges the halves:  x1 = y + concat_heads(softmax(...) V).  Optionally the last head of a batch row applies LayerNorm (ln2).
+// grid (heads, batch, splits), 256 threads.  Each CTA owns a contiguous range of <= DEC_CHUNK keys.  One thread issues bulk
+// async copies (cp.async.bulk -> mbarrier) for the K^T slab (64 row segments) and the V slab (one contiguous block) of that range
+// at kernel entry, so the whole KV traffic of the CTA is in flight while the other threads finish q (and k/v of the newest key,
+// appended to the cache by the CTA that owns it) from the split-K partials of the QKV GEMM.  Scores (thread = key, camera-bias row
+// added BEFORE the 1/sqrt(d_head) scale), block softmax and P.V (thread = channel) then run out of shared memory; the CTA leaves an
+// (m, l, o[64]) partial and the last CTA to arrive per (batch, head) merges them: x1 = y + concat_heads(softmax(...) V)
+// (flash-decoding with a fused combine).  Optionally the last head of a batch row applies LayerNorm (ln2) to the finished row.
 template <typename KVT>
-__global__ void __launch_bounds__(288, 1) dec_attn_kernel(const float* __restrict__ qkv_part, int ks, long long zstride,
-                                                          const float* __restrict__ bqkv, const float* __restrict__ y,
-                                                          const float* __restrict__ bias, int bias_ld, KVT* __restrict__ kc,
-                                                          KVT* __restrict__ vc, float* __restrict__ x1, const int* __restrict__ step_ptr,
-                                                          float* __restrict__ ws, unsigned int* __restrict__ counters, int nc, int B, int H,
-                                                          int d, int Lmax, float scale, unsigned int* __restrict__ row_counters,
-                                                          const float* __restrict__ ln_gamma, const float* __restrict__ ln_beta, float ln_eps,
-                                                          uint16_t* __restrict__ ln_hi, uint16_t* __restrict__ ln_lo) {
+__global__ void __launch_bounds__(256) dec_attn_kernel(const float* __restrict__ qkv_part, int ks, long long zstride,
+                                                       const float* __restrict__ bqkv, const float* __restrict__ y,
+                                                       const float* __restrict__ bias, int bias_ld, KVT* __restrict__ kc,
+                                                       KVT* __restrict__ vc, float* __restrict__ x1, const int* __restrict__ step_ptr,
+                                                       float* __restrict__ ws, unsigned int* __restrict__ counters, int nc, int H, int d,
+                                                       int Lmax, float scale, unsigned int* __restrict__ row_counters,
+                                                       const float* __restrict__ ln_gamma, const float* __restrict__ ln_beta, float ln_eps,
+                                                       uint16_t* __restrict__ ln_hi, uint16_t* __restrict__ ln_lo) {
   extern __shared__ __align__(128) uint8_t dsm[];
-  constexpr uint32_t KBYTES = 64u * DEC_CHUNK * (uint32_t)sizeof(KVT);
-  __shared__ float q[64], knew[64], vnew[64], red[8];
-  __shared__ float wm[8], wl[8], wo[8][64];
-  __shared__ __align__(8) uint64_t full[DEC_STAGES], empty[DEC_STAGES];
+  KVT* Ks = reinterpret_cast<KVT*>(dsm);                                  // [64][pitch]
+  KVT* Vs = reinterpret_cast<KVT*>(dsm + 64 * DEC_CHUNK * sizeof(KVT));   // [keys][64]
+  __shared__ float q[64], knew[64], vnew[64], red[8], sc[DEC_CHUNK];
+  __shared__ float opart[4][64];
+  __shared__ __align__(8) uint64_t bar;
   __shared__ unsigned int ticket;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int h = blockIdx.x, b = blockIdx.y, sp = blockIdx.z, S = gridDim.z, tid = threadIdx.x;
   const int r = nc + *step_ptr - 1;
   const int n = r + 1;
-  const int nblk = (n + DEC_CHUNK - 1) / DEC_CHUNK;          // key blocks in use
-  const int bps = (nblk + DEC_KSPLIT - 1) / DEC_KSPLIT;      // blocks per item (the last item of a pair may get fewer, possibly 0)
-  const int items = B * H * DEC_KSPLIT;
-  const int G = gridDim.x;
+  const int j0 = sp * DEC_CHUNK;
+  const int cnt = max(0, min(n - j0, DEC_CHUNK));          // valid keys of this CTA (key r included if in range)
+  const int pitch = (cnt + 7) & ~7;                        // copied keys: 16-byte granules; stale tail entries are never used
+  const bool owns_new = (r >= j0 && r < j0 + DEC_CHUNK);
+  const size_t bh = (size_t)b * H + h;
   if (tid == 0) {
-    for (int s = 0; s < DEC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 8); }
+    mbar_init(&bar, 1);
     fence_barrier_init();
+    if (cnt > 0) {
+      const uint32_t kbytes = 64u * DEC_CHUNK * (uint32_t)sizeof(KVT), vbytes = (uint32_t)pitch * 64u * (uint32_t)sizeof(KVT);
+      mbar_expect_tx(&bar, kbytes + vbytes);
+      bulk_g2s(Ks, kc + k_index(bh, 0, j0, Lmax), kbytes, &bar);           // whole 128-key K^T block: one contiguous copy
+      bulk_g2s(Vs, vc + (bh * Lmax + j0) * 64, vbytes, &bar);
+    }
+  }
+  if (tid < 192) {
+    const int which = tid >> 6, c = tid & 63;
+    if (cnt > 0 && (which == 0 || owns_new)) {
+      const int col = which * d + h * 64 + c;
+      const float* pp = qkv_part + (size_t)b * 3 * d + col;
+      float v = __ldg(bqkv + col);
+      int z = 0;
+      for (; z + 4 <= ks; z += 4) v += (pp[z * zstride] + pp[(z + 1) * zstride]) + (pp[(z + 2) * zstride] + pp[(z + 3) * zstride]);
+      for (; z < ks; ++z) v += pp[z * zstride];
+      if (which == 0) q[c] = v;
+      else if (which == 1) { knew[c] = v; kv_store(kc + k_index(bh, c, r, Lmax), v); }
+      else { vnew[c] = v; kv_store(vc + (bh * Lmax + r) * 64 + c, v); }
+    }
   }
   __syncthreads();
-
-  if (warp == 8) {
-    // ===================== producer =====================
-    if (lane == 0) {
-      int slot = 0;
-      for (int item = blockIdx.x; item < items; item += G) {
-        const size_t bh = item / DEC_KSPLIT;
-        const int b0 = (item % DEC_KSPLIT) * bps, b1 = min(nblk, b0 + bps);
-        for (int blk = b0; blk < b1; ++blk, ++slot) {
-          const int st = slot % DEC_STAGES;
-          mbar_wait(&empty[st], ((slot / DEC_STAGES) & 1) ^ 1);
-          const int j0 = blk * DEC_CHUNK;
-          const int cnt = min(n - j0, DEC_CHUNK);
-          const uint32_t vbytes = (uint32_t)((cnt + 7) & ~7) * 64u * (uint32_t)sizeof(KVT);
-          uint8_t* base = dsm + (size_t)st * 2 * KBYTES;
-          mbar_expect_tx(&full[st], KBYTES + vbytes);
-          bulk_g2s(base, kc + k_index(bh, 0, j0, Lmax), KBYTES, &full[st]);
-          bulk_g2s(base + KBYTES, vc + (bh * Lmax + j0) * 64, vbytes, &full[st]);
-        }
-      }
+  float m = -INFINITY, sum = 0.f;
+  if (cnt > 0) {
+    mbar_wait(&bar, 0);
+    if (owns_new && tid < 64) {        // the slab may hold a stale copy of the newest key: take it from registers instead
+      kv_store(Ks + tid * DEC_CHUNK + (r - j0), knew[tid]);
+      kv_store(Vs + (size_t)(r - j0) * 64 + tid, vnew[tid]);
     }
-    return;
+    __syncthreads();
+    const float* brow = bias ? bias + (size_t)r * bias_ld + j0 : nullptr;
+    if (tid < cnt) {
+      float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < 64; c += 2) {
+        d0 = fmaf(q[c], kv_load(Ks + c * DEC_CHUNK + tid), d0);
+        d1 = fmaf(q[c + 1], kv_load(Ks + (c + 1) * DEC_CHUNK + tid), d1);
+      }
+      m = ((d0 + d1) + (brow ? brow[tid] : 0.f)) * scale;
+    }
+    const float mloc = block_max_256(m, red);
+    float e = 0.f;
+    if (tid < cnt) { e = expf(m - mloc); sc[tid] = e; }
+    sum = block_sum_256(e, red);       // its barriers publish sc[]
+    m = mloc;
+    const int g = tid >> 6, c = tid & 63;
+    float a0 = 0.f, a1 = 0.f;
+    int jj = g;
+    for (; jj + 4 < cnt; jj += 8) {
+      a0 = fmaf(sc[jj], kv_load(Vs + (size_t)jj * 64 + c), a0);
+      a1 = fmaf(sc[jj + 4], kv_load(Vs + (size_t)(jj + 4) * 64 + c), a1);
+    }
+    if (jj < cnt) a0 = fmaf(sc[jj], kv_load(Vs + (size_t)jj * 64 + c), a0);
+    opart[g][c] = a0 + a1;
+  } else if (tid < 256) {
+    opart[tid >> 6][tid & 63] = 0.f;
   }
-  // ===================== consumers (warps 0-7, named barrier 1 with 256 threads) =====================
-  const int kk = lane & 15, hh = lane >> 4;                  // scores: key within the warp's 16, channel half
-  int slot = 0;
-  for (int item = blockIdx.x; item < items; item += G) {
-    const int bh = item / DEC_KSPLIT, sp = item % DEC_KSPLIT;
-    const int b = bh / H, h = bh % H;
-    const int b0 = sp * bps, b1 = min(nblk, b0 + bps);
-    const bool owns_new = (b0 < b1) && (b1 == nblk);
-    asm volatile("bar.sync 1, 256;" ::: "memory");           // previous item's q / wm / wo are no longer read
-    if (b0 < b1 && tid < 192) {
-      const int which = tid >> 6, c = tid & 63;
-      if (which == 0 || owns_new) {
-        const int col = which * d + h * 64 + c;
-        const float* pp = qkv_part + (size_t)b * 3 * d + col;
-        float v = __ldg(bqkv + col);
-        int z = 0;
-        for (; z + 4 <= ks; z += 4) v += (pp[z * zstride] + pp[(z + 1) * zstride]) + (pp[(z + 2) * zstride] + pp[(z + 3) * zstride]);
-        for (; z < ks; ++z) v += pp[z * zstride];
-        if (which == 0) q[c] = v;
-        else if (which == 1) { knew[c] = v; kv_store(kc + k_index(bh, c, r, Lmax), v); }
-        else { vnew[c] = v; kv_store(vc + ((size_t)bh * Lmax + r) * 64 + c, v); }
-      }
-    }
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    float qh[32];
-#pragma unroll
-    for (int c = 0; c < 32; ++c) qh[c] = q[hh * 32 + c];
-    float m = -INFINITY, l = 0.f;
-    float2 acc = make_float2(0.f, 0.f);
-    const float* brow = bias ? bias + (size_t)r * bias_ld : nullptr;
-    for (int blk = b0; blk < b1; ++blk, ++slot) {
-      const int st = slot % DEC_STAGES;
-      const KVT* Ks = reinterpret_cast<const KVT*>(dsm + (size_t)st * 2 * KBYTES);
-      const KVT* Vs = reinterpret_cast<const KVT*>(dsm + (size_t)st * 2 * KBYTES + KBYTES);
-      const int j0 = blk * DEC_CHUNK;
-      const int jk = warp * 16 + kk;                          // key within the block
-      const int j = j0 + jk;
-      mbar_wait(&full[st], (slot / DEC_STAGES) & 1);
-      float sv = -INFINITY;
-      if (j < n) {
-        float dot = 0.f;
-        if (j < r) {
-#pragma unroll
-          for (int c = 0; c < 32; ++c) dot = fmaf(qh[c], kv_load(Ks + (hh * 32 + c) * DEC_CHUNK + jk), dot);
-        } else {
-#pragma unroll
-          for (int c = 0; c < 32; ++c) dot = fmaf(qh[c], knew[hh * 32 + c], dot);
-        }
-        sv = dot;
-      }
-      sv += __shfl_xor_sync(0xffffffffu, sv, 16);             // both channel halves; -inf stays -inf
-      if (j < n) sv = (sv + (brow ? brow[j] : 0.f)) * scale;
-      float tmax = sv;
-#pragma unroll
-      for (int o = 8; o; o >>= 1) tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
-      const float m_new = fmaxf(m, tmax);
-      if (m_new != -INFINITY) {                               // warp-uniform: this warp has at least one valid key so far
-        const float corr = (m == -INFINITY) ? 0.f : expf(m - m_new);
-        const float p = (j < n) ? expf(sv - m_new) : 0.f;     // lanes 16-31 mirror lanes 0-15
-        float psum = (hh == 0) ? p : 0.f;
-#pragma unroll
-        for (int o = 16; o; o >>= 1) psum += __shfl_xor_sync(0xffffffffu, psum, o);
-        l = l * corr + psum;
-        acc.x *= corr; acc.y *= corr;
-        m = m_new;
-        const int nv = min(16, n - (j0 + warp * 16));         // valid keys of this warp in the block (>= 1 here)
-#pragma unroll
-        for (int t = 0; t < 16; ++t) {
-          const float pj = __shfl_sync(0xffffffffu, p, t);
-          if (t < nv) {
-            const int jj = j0 + warp * 16 + t;
-            float2 vv;
-            if (jj < r) vv = KV2<KVT>::load(Vs + (size_t)(warp * 16 + t) * 64 + 2 * lane);
-            else vv = make_float2(vnew[2 * lane], vnew[2 * lane + 1]);
-            acc.x = fmaf(pj, vv.x, acc.x);
-            acc.y = fmaf(pj, vv.y, acc.y);
-          }
-        }
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[st]);
-    }
-    if (lane == 0) { wm[warp] = m; wl[warp] = l; }
-    wo[warp][2 * lane] = acc.x;
-    wo[warp][2 * lane + 1] = acc.y;
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    float* wp = ws + ((size_t)bh * DEC_MAX_SPLIT + sp) * DEC_WS;
-    if (tid < 64) {
-      float M = wm[0];
-#pragma unroll
-      for (int w = 1; w < 8; ++w) M = fmaxf(M, wm[w]);
-      float Ls = 0.f, o = 0.f;
-#pragma unroll
-      for (int w = 0; w < 8; ++w) {
-        const float f = (wm[w] == -INFINITY) ? 0.f : expf(wm[w] - M);
-        Ls += wl[w] * f;
-        o += wo[w][tid] * f;
-      }
-      wp[4 + tid] = o;
-      if (tid == 0) { wp[0] = M; wp[1] = Ls; }
-    }
-    __threadfence();
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    if (tid == 0) ticket = atomicAdd(&counters[bh], 1u);
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    if (ticket != (unsigned)(DEC_KSPLIT - 1)) continue;
-    __threadfence();
-    if (tid < 64) {
-      const volatile float* wv = ws + (size_t)bh * DEC_MAX_SPLIT * DEC_WS;
-      float M = -INFINITY;
-#pragma unroll
-      for (int i = 0; i < DEC_KSPLIT; ++i) M = fmaxf(M, wv[i * DEC_WS]);
-      float Lsum = 0.f, o = 0.f;
-#pragma unroll
-      for (int i = 0; i < DEC_KSPLIT; ++i) {
-        const float mi = wv[i * DEC_WS];
-        const float w = (mi == -INFINITY) ? 0.f : expf(mi - M);
-        Lsum += wv[i * DEC_WS + 1] * w;
-        o += wv[i * DEC_WS + 4 + tid] * w;
-      }
-      const size_t idx = (size_t)b * d + h * 64 + tid;
-      x1[idx] = y[idx] + o / Lsum;
-      if (tid == 0) counters[bh] = 0u;      // self-reset for the next launch
-    }
-    if (ln_gamma == nullptr) continue;
-    // ---- fused LayerNorm (ln2): the last head of batch row b normalises x1[b,:] into the MLP operand planes
-    __threadfence();
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    if (tid == 0) ticket = atomicAdd(&row_counters[b], 1u);
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    if (ticket != (unsigned)(H - 1)) continue;
-    __threadfence();
-    const bool act = tid < (d >> 2);
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (act) v = __ldcg(reinterpret_cast<const float4*>(x1 + (size_t)b * d) + tid);
-    float s1 = act ? (v.x + v.y) + (v.z + v.w) : 0.f;
-    for (int o = 16; o; o >>= 1) s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-    if (lane == 0) red[warp] = s1;
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    const float mean = (((red[0] + red[1]) + (red[2] + red[3])) + ((red[4] + red[5]) + (red[6] + red[7]))) / d;
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    v.x -= mean; v.y -= mean; v.z -= mean; v.w -= mean;
-    float s2 = act ? (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w) : 0.f;
-    for (int o = 16; o; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-    if (lane == 0) red[warp] = s2;
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    const float rstd = rsqrtf((((red[0] + red[1]) + (red[2] + red[3])) + ((red[4] + red[5]) + (red[6] + red[7]))) / d + ln_eps);
-    if (tid == 0) row_counters[b] = 0u;
-    if (act) {
-      const float4 g = __ldg(reinterpret_cast<const float4*>(ln_gamma) + tid), be = __ldg(reinterpret_cast<const float4*>(ln_beta) + tid);
-      const float4 o4 = make_float4(v.x * rstd * g.x + be.x, v.y * rstd * g.y + be.y, v.z * rstd * g.z + be.z, v.w * rstd * g.w + be.w);
-      __nv_bfloat16 h0, l0, h1, l1, h2, l2, h3, l3;
-      split_bf16(o4.x, h0, l0); split_bf16(o4.y, h1, l1); split_bf16(o4.z, h2, l2); split_bf16(o4.w, h3, l3);
-      reinterpret_cast<uint2*>(ln_hi + (size_t)b * d)[tid] = make_uint2(pack_bf16(h0, h1), pack_bf16(h2, h3));
-      if (ln_lo != nullptr) reinterpret_cast<uint2*>(ln_lo + (size_t)b * d)[tid] = make_uint2(pack_bf16(l0, l1), pack_bf16(l2, l3));
-    }
+  __syncthreads();
+  float* wp = ws + (bh * S + sp) * DEC_WS;
+  if (tid < 64) {
+    wp[4 + tid] = (opart[0][tid] + opart[1][tid]) + (opart[2][tid] + opart[3][tid]);
+    if (tid == 0) { wp[0] = m; wp[1] = sum; }
   }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) ticket = atomicAdd(&counters[bh], 1u);
+  __syncthreads();
+  if (ticket != (unsigned)(S - 1)) return;
+  __threadfence();
+  if (tid < 64) {
+    const volatile float* wv = ws + bh * S * DEC_WS;
+    float M = -INFINITY;
+    for (int i = 0; i < S; ++i) M = fmaxf(M, wv[i * DEC_WS]);
+    float Lsum = 0.f, o = 0.f;
+    for (int i = 0; i < S; ++i) {
+      const float mi = wv[i * DEC_WS];
+      const float w = (mi == -INFINITY) ? 0.f : expf(mi - M);
+      Lsum += wv[i * DEC_WS + 1] * w;
+      o += wv[i * DEC_WS + 4 + tid] * w;
+    }
+    const size_t idx = (size_t)b * d + h * 64 + tid;
+    x1[idx] = y[idx] + o / Lsum;
+    if (tid == 0) counters[bh] = 0u;      // self-reset for the next launch
+  }
+  if (ln_gamma == nullptr) return;
+  // ---- fused LayerNorm (ln2) of the finished row: the last head of batch row b normalises x1[b,:] into the MLP operand planes
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) ticket = atomicAdd(&row_counters[b], 1u);
+  __syncthreads();
+  if (ticket != (unsigned)(H - 1)) return;
+  __threadfence();
+  const bool act = tid < (d >> 2);
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (act) v = __ldcg(reinterpret_cast<const float4*>(x1 + (size_t)b * d) + tid);
+  const float mean = block_sum_256(act ? (v.x + v.y) + (v.z + v.w) : 0.f, red) / d;
+  v.x -= mean; v.y -= mean; v.z -= mean; v.w -= mean;
+  const float var = block_sum_256(act ? (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w) : 0.f, red) / d;
+  const float rstd = rsqrtf(var + ln_eps);
+  if (tid == 0) row_counters[b] = 0u;
+  if (!act) return;
+  const float4 g = __ldg(reinterpret_cast<const float4*>(ln_gamma) + tid), be = __ldg(reinterpret_cast<const float4*>(ln_beta) + tid);
+  const float4 o4 = make_float4(v.x * rstd * g.x + be.x, v.y * rstd * g.y + be.y, v.z * rstd * g.z + be.z, v.w * rstd * g.w + be.w);
+  __nv_bfloat16 h0, l0, h1, l1, h2, l2, h3, l3;
+  split_bf16(o4.x, h0, l0); split_bf16(o4.y, h1, l1); split_bf16(o4.z, h2, l2); split_bf16(o4.w, h3, l3);
+  reinterpret_cast<uint2*>(ln_hi + (size_t)b * d)[tid] = make_uint2(pack_bf16(h0, h1), pack_bf16(h2, h3));
+  if (ln_lo != nullptr) reinterpret_cast<uint2*>(ln_lo + (size_t)b * d)[tid] = make_uint2(pack_bf16(l0, l1), pack_bf16(l2, l3));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -557,34 +467,29 @@ int launch_kv_store(const uint16_t* hi, const uint16_t* lo, void* kc, void* vc, 
 static inline int dec_splits(int Lmax) { return (Lmax + DEC_CHUNK - 1) / DEC_CHUNK; }
 int dec_attn_workspace_floats(int B, int H) { return B * H * DEC_MAX_SPLIT * DEC_WS; }
 
-template <typename KVT>
-static int launch_dec_attn_t(const float* qkv_part, int ks, long long zstride, const float* bqkv, const float* y, const float* bias, int bias_ld,
-                             KVT* kc, KVT* vc, float* x1, const int* step_ptr, float* ws, unsigned int* counters, int B, int nc, int H, int d,
-                             int Lmax, float scale, unsigned int* row_counters, const float* ln_gamma, const float* ln_beta, float ln_eps,
-                             uint16_t* ln_hi, uint16_t* ln_lo, int sm_count, cudaStream_t st) {
-  const int smem = DEC_STAGES * 2 * 64 * DEC_CHUNK * (int)sizeof(KVT);
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(dec_attn_kernel<KVT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return BEVGEN_ERR_CUDA;
-    configured = true;
-  }
-  const int per_sm = (sizeof(KVT) == 2) ? 2 : 1;      // bf16 ring is 96 KB: two CTAs per SM
-  dec_attn_kernel<KVT><<<sm_count * per_sm, 288, smem, st>>>(qkv_part, ks, zstride, bqkv, y, bias, bias_ld, kc, vc, x1, step_ptr, ws, counters, nc, B,
-                                                             H, d, Lmax, scale, row_counters, ln_gamma, ln_beta, ln_eps, ln_hi, ln_lo);
-  return cudaGetLastError() == cudaSuccess ? BEVGEN_OK : BEVGEN_ERR_CUDA;
-}
-
 int launch_dec_attn(const float* qkv_part, int ks, long long zstride, const float* bqkv, const float* y, const float* bias, int bias_ld,
                     void* kc, void* vc, int kv_bf16, float* x1, const int* step_ptr, float* ws, unsigned int* counters, int B, int nc, int H,
                     int d, int Lmax, float scale, unsigned int* row_counters, const float* ln_gamma, const float* ln_beta, float ln_eps,
-                    uint16_t* ln_hi, uint16_t* ln_lo, int sm_count, cudaStream_t st) {
+                    uint16_t* ln_hi, uint16_t* ln_lo, int /*sm_count*/, cudaStream_t st) {
   if (Lmax > DEC_MAXL || B < 1 || B > 65535 || d != H * 64 || (Lmax & 127) || dec_splits(Lmax) > DEC_MAX_SPLIT) return BEVGEN_ERR_ARG;
   if (ln_gamma != nullptr && (!row_counters || !ln_beta || !ln_hi || d > 1024)) return BEVGEN_ERR_ARG;
-  if (kv_bf16)
-    return launch_dec_attn_t<__nv_bfloat16>(qkv_part, ks, zstride, bqkv, y, bias, bias_ld, (__nv_bfloat16*)kc, (__nv_bfloat16*)vc, x1, step_ptr, ws,
-                                            counters, B, nc, H, d, Lmax, scale, row_counters, ln_gamma, ln_beta, ln_eps, ln_hi, ln_lo, sm_count, st);
-  return launch_dec_attn_t<float>(qkv_part, ks, zstride, bqkv, y, bias, bias_ld, (float*)kc, (float*)vc, x1, step_ptr, ws, counters, B, nc, H, d,
-                                  Lmax, scale, row_counters, ln_gamma, ln_beta, ln_eps, ln_hi, ln_lo, sm_count, st);
+  dim3 grid(H, B, dec_splits(Lmax));
+  if (kv_bf16) {
+    const int smem = 2 * 64 * DEC_CHUNK * 2;
+    dec_attn_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>(qkv_part, ks, zstride, bqkv, y, bias, bias_ld, (__nv_bfloat16*)kc, (__nv_bfloat16*)vc,
+                                                            x1, step_ptr, ws, counters, nc, H, d, Lmax, scale, row_counters, ln_gamma, ln_beta,
+                                                            ln_eps, ln_hi, ln_lo);
+  } else {
+    const int smem = 2 * 64 * DEC_CHUNK * 4;
+    static bool configured = false;
+    if (!configured) {
+      if (cudaFuncSetAttribute(dec_attn_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return BEVGEN_ERR_CUDA;
+      configured = true;
+    }
+    dec_attn_kernel<float><<<grid, 256, smem, st>>>(qkv_part, ks, zstride, bqkv, y, bias, bias_ld, (float*)kc, (float*)vc, x1, step_ptr, ws,
+                                                    counters, nc, H, d, Lmax, scale, row_counters, ln_gamma, ln_beta, ln_eps, ln_hi, ln_lo);
+  }
+  return cudaGetLastError() == cudaSuccess ? BEVGEN_OK : BEVGEN_ERR_CUDA;
 }
 int launch_dec_sample(const float* part, int ks, long long zstride, int vpad, int V, float temperature, int top_k, int greedy,
                       unsigned long long seed, const long long* forced, const int* fwd, long long* cam_idx, long long* tokens_out, float* trace,
