@@ -33,8 +33,9 @@ int ensure_init() {
   return bevgen_init(-1);
 }
 
-// bf16 tensor map with SWIZZLE_128B; dims/strides innermost first
-int make_tmap(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
+// bf16 tensor map (SWIZZLE_128B unless swizzle == false); dims/strides innermost first
+int make_tmap(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
+              bool swizzle = true) {
   cuuint64_t gd[5], gs[4];
   cuuint32_t bx[5], es[5];
   for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
@@ -43,7 +44,8 @@ int make_tmap(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, 
   for (int i = 0; i + 1 < rank; ++i)
     if (gs[i] % 16 != 0) return fail(BEVGEN_ERR_ARG, "tensor map stride %d (%llu B) not a multiple of 16", i, (unsigned long long)gs[i]);
   CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(BEVGEN_ERR_DRIVER, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d)", (int)r, rank);
   return BEVGEN_OK;
@@ -139,12 +141,48 @@ BEVGEN_API int bevgen_gemm_tc(const bevgen_gemm_args* a, void* stream) {
   return BEVGEN_OK;
 }
 
+#define CHECK_LAUNCH_DEFINED 1
 #define CHECK_LAUNCH(expr, name)                                                                         \
   do {                                                                                                   \
     int rc_ = (expr);                                                                                    \
     if (rc_) return fail(rc_, "%s failed (%d): %s", name, rc_, cudaGetErrorString(cudaGetLastError())); \
     return BEVGEN_OK;                                                                                    \
   } while (0)
+
+BEVGEN_API int bevgen_conv3x3_halo(const void* a_hi, const void* a_lo, int n, int h, int w, int cin, const void* w_hi, const void* w_lo, int w_rows,
+                                   int cout, const float* bias, const float* residual, float* out, double* gn_sums, int npass, void* stream) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  if (!a_hi || !w_hi || !bias || !out || (npass == 3 && (!a_lo || !w_lo)) || !(npass == 1 || npass == 3)) return fail(BEVGEN_ERR_ARG, "conv3x3_halo: bad args");
+  if (cin % 64 != 0 || cout % 32 != 0 || n < 1 || h < 1 || w < 1) return fail(BEVGEN_ERR_ARG, "conv3x3_halo: cin %% 64 / cout %% 32 required (cin=%d cout=%d)", cin, cout);
+  if (w_rows < 8 * cout + ((cout + 127) / 128) * 128) return fail(BEVGEN_ERR_ARG, "conv3x3_halo: weight rows must be padded to 8*cout + ceil128(cout)");
+  ConvHaloParams p;
+  memset(&p, 0, sizeof(p));
+  const void* ap[2] = {a_hi, a_lo};
+  const void* wp[2] = {w_hi, w_lo};
+  for (int o = 0; o < (npass == 3 ? 2 : 1); ++o) {
+    uint64_t ad[5] = {8, (uint64_t)w, (uint64_t)h, (uint64_t)cin / 8, (uint64_t)n};
+    uint64_t as[4] = {(uint64_t)cin * 2, (uint64_t)cin * w * 2, 16, (uint64_t)cin * w * h * 2};
+    uint32_t ab[5] = {8, 10, 18, 8, 1};
+    rc = make_tmap(&p.tmA[o], ap[o], 5, ad, as, ab, false);
+    if (rc) return rc;
+    uint64_t wd[2] = {(uint64_t)cin, (uint64_t)w_rows};
+    uint64_t wst[1] = {(uint64_t)cin * 2};
+    uint32_t wb[2] = {64, 128};
+    rc = make_tmap(&p.tmW[o], wp[o], 2, wd, wst, wb, true);
+    if (rc) return rc;
+  }
+  p.N = n; p.H = h; p.W = w; p.Cin = cin; p.Cout = cout;
+  p.bias = bias; p.residual = residual; p.out = out; p.gn_sums = gn_sums;
+  if (gn_sums != nullptr && cudaMemsetAsync(gn_sums, 0, (size_t)n * 64 * sizeof(double), (cudaStream_t)stream) != cudaSuccess)
+    return fail(BEVGEN_ERR_CUDA, "conv3x3_halo: memset failed");
+  CHECK_LAUNCH(launch_conv_halo(p, npass, g_sm_count, (cudaStream_t)stream), "conv3x3_halo");
+}
+
+BEVGEN_API int bevgen_groupnorm_finalize(const double* sums, int n, int pixels, int c, float eps, float* mean_rstd, void* stream) {
+  if (!sums || !mean_rstd || n < 1 || c % 32 != 0) return fail(BEVGEN_ERR_ARG, "groupnorm_finalize: bad args");
+  CHECK_LAUNCH(launch_gn_finalize(sums, mean_rstd, n, pixels, c, eps, (cudaStream_t)stream), "groupnorm_finalize");
+}
 
 BEVGEN_API int bevgen_groupnorm_stats(const float* x, int n, int pixels, int c, float eps, double* ws_sums, float* mean_rstd, void* stream) {
   int rc = ensure_init();

@@ -263,6 +263,11 @@ int launch_gn_stats(const float* x, double* sums, float* mean_rstd, int N, int p
   return cudaGetLastError() == cudaSuccess ? BEVGEN_OK : BEVGEN_ERR_CUDA;
 }
 
+int launch_gn_finalize(const double* sums, float* mean_rstd, int N, int pixels, int C, float eps, cudaStream_t st) {
+  gn_finalize_kernel<<<(N * 32 + 127) / 128, 128, 0, st>>>(sums, mean_rstd, N * 32, 1.0 / ((double)pixels * (C / 32)), (double)eps);
+  return cudaGetLastError() == cudaSuccess ? BEVGEN_OK : BEVGEN_ERR_CUDA;
+}
+
 int launch_prep(const PrepParams& p, int sm_count, cudaStream_t st) {
   if (p.C % 8 != 0) return BEVGEN_ERR_ARG;
   if (p.mean_rstd != nullptr && p.C % 32 != 0) return BEVGEN_ERR_ARG;

@@ -46,6 +46,7 @@ int gemm_tc_dispatch(const GemmParams& p, int bn, int npass, int sm_count, cudaS
 
 int launch_gn_stats(const float* x, double* sums, float* mean_rstd, int N, int pixels, int C, float eps, cudaStream_t st);
 int launch_prep(const PrepParams& p, int sm_count, cudaStream_t st);
+int launch_gn_finalize(const double* sums, float* mean_rstd, int N, int pixels, int C, float eps, cudaStream_t st);
 int launch_im2col3x3(const float* x, uint16_t* hi, uint16_t* lo, int N, int Cin, int H, int W, int sm_count, cudaStream_t st);
 int launch_transpose(const float* src, float* dst, int N, int R, int Cc, cudaStream_t st);
 int launch_softmax_rows(const float* s, uint16_t* hi, uint16_t* lo, long long rows, int cols, int out_ld, float scale, cudaStream_t st);
@@ -60,6 +61,18 @@ int launch_layernorm(const float* x, const float* gamma, const float* beta, floa
 int launch_embed(const EmbedParams& p, cudaStream_t st);
 int launch_attn_softmax(const float* S, const float* bias, const uint8_t* mask, uint16_t* hi, uint16_t* lo, long long zrows, int L, int Lk,
                         float scale, cudaStream_t st);
+
+struct ConvHaloParams {
+  CUtensorMap tmA[2];      // 5D (c8, w, h, chunk, n), box (8, 10, 18, 8, 1), no swizzle
+  CUtensorMap tmW[2];      // 2D (cin, tap*cout + co), box (64, 128), SWIZZLE_128B
+  int N, H, W, Cin, Cout;
+  const float* bias;
+  const float* residual;   // [N][H][W][Cout] or null
+  float* out;              // [N][H][W][Cout]
+  double* gn_sums;         // [N][32][2] or null: GroupNorm statistics of `out`
+};
+
+int launch_conv_halo(const ConvHaloParams& p, int npass, int sm_count, cudaStream_t st);
 
 int launch_attn_fused(const CUtensorMap* tm_hi, const CUtensorMap* tm_lo, const void* bias_f16, const float* y, float* x1, int B, int H, int L,
                       int nc, int d, float scale, int npass, cudaStream_t st);

@@ -203,3 +203,27 @@ def attn_fused_fwd(qkv_hi, qkv_lo, B, L, H, d, n_cond, bias_f16, y, x1, scale, n
         Stats.timer("attn_fused", call, algo_flops)
     else:
         call()
+
+
+def conv3x3_halo(a_hi, a_lo, dims, w_hi, w_lo, cout, bias, out, residual=None, gn_sums=None, npass=3):
+    """3x3 s1 'same' conv on NHWC planes via the halo-tile kernel; optional fused GroupNorm statistics of the output."""
+    lib = _lib.init()
+    _chk_cuda(a_hi, a_lo, w_hi, w_lo, bias, out, residual, gn_sums)
+    n, h, w, cin = dims
+    flops = 2.0 * n * h * w * cout * cin * 9
+    Stats.launches += 1
+    Stats.gemm_launches += 1
+    Stats.gemm_flops += flops
+    call = lambda: _lib.check(lib.bevgen_conv3x3_halo(_ptr(a_hi), _ptr(a_lo), n, h, w, cin, _ptr(w_hi), _ptr(w_lo), w_hi.shape[0], cout, _ptr(bias),
+                                                      _ptr(residual), _ptr(out), _ptr(gn_sums), npass, _stream()), "conv3x3_halo")
+    if Stats.timer is not None:
+        Stats.timer("conv_halo", call, flops)
+    else:
+        call()
+
+
+def groupnorm_finalize(sums, mean_rstd, n, pixels, c, eps=1e-6):
+    lib = _lib.init()
+    Stats.launches += 1
+    _chk_cuda(sums, mean_rstd)
+    _lib.check(lib.bevgen_groupnorm_finalize(_ptr(sums), n, pixels, c, eps, _ptr(mean_rstd), _stream()), "groupnorm_finalize")

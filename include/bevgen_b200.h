@@ -87,6 +87,14 @@ BEVGEN_API int bevgen_sm_count(void);
 
 BEVGEN_API int bevgen_gemm_tc(const bevgen_gemm_args* args, void* stream);
 
+/* 3x3 stride-1 "same" Conv2d (stage1/model.py:43-47,88-102,355-359,399-403,458-462,500-504) over NHWC bf16 operand planes with a
+ * shared-memory halo tile (activations loaded once per 64-channel chunk instead of once per tap), fused bias + residual and, when
+ * gn_sums != NULL, the GroupNorm(32) statistics of the OUTPUT: gn_sums[n][32][2] (sum, sum of squares; zeroed by this call), to be
+ * turned into (mean, rstd) by bevgen_groupnorm_finalize.  Weights: [tap][cout][cin] planes, rows padded to 8*cout + ceil128(cout). */
+BEVGEN_API int bevgen_conv3x3_halo(const void* a_hi, const void* a_lo, int n, int h, int w, int cin, const void* w_hi, const void* w_lo, int w_rows,
+                                   int cout, const float* bias, const float* residual, float* out, double* gn_sums, int npass, void* stream);
+BEVGEN_API int bevgen_groupnorm_finalize(const double* sums, int n, int pixels, int c, float eps, float* mean_rstd, void* stream);
+
 /* torch.nn.GroupNorm(32, C, eps) statistics (stage1/model.py:34-35): fp32 NHWC x[n][pixels][c] -> mean_rstd[n][32][2].
  * ws_sums: n*64 doubles of scratch. */
 BEVGEN_API int bevgen_groupnorm_stats(const float* x, int n, int pixels, int c, float eps, double* ws_sums, float* mean_rstd, void* stream);

@@ -265,3 +265,39 @@ def test_softmax_transpose_gather_denorm():
     ops.denormalize(x, o, mean, std)
     ref = torch.clamp(x * torch.tensor(std, device=dev()).view(1, 3, 1, 1) + torch.tensor(mean, device=dev()).view(1, 3, 1, 1), 0, 1)
     assert (o - ref).abs().max().item() < 1e-6
+
+
+@pytest.mark.parametrize("npass", [3, 1])
+@pytest.mark.parametrize("N_,H,W,Cin,Cout", [(2, 16, 16, 64, 128), (1, 20, 28, 128, 128), (3, 8, 8, 128, 256), (2, 4, 4, 64, 64), (1, 64, 64, 128, 128)])
+def test_conv3x3_halo(N_, H, W, Cin, Cout, npass):
+    """Halo-tile conv kernel (no-swizzle shifted A descriptors) + fused GroupNorm statistics of the output."""
+    g = torch.Generator().manual_seed(H * W + Cin + Cout)
+    x = torch.randn(N_, Cin, H, W, generator=g).to(dev())
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / (9 * Cin) ** 0.5).to(dev())
+    b = torch.randn(Cout, generator=g).to(dev())
+    res = torch.randn(N_, H, W, Cout, generator=g).to(dev())
+    a_hi, a_lo = _split(x.permute(0, 2, 3, 1).contiguous())
+    rows = 9 * Cout
+    wp = torch.zeros(8 * Cout + ((Cout + 127) // 128) * 128, Cin, device=dev())
+    wp[:rows] = w.permute(2, 3, 0, 1).reshape(rows, Cin)
+    w_hi, w_lo = _split(wp)
+    out = torch.full((N_, H, W, Cout), float("nan"), device=dev())
+    sums = torch.full((N_ * 64,), float("nan"), dtype=torch.float64, device=dev())
+    ops.conv3x3_halo(a_hi, a_lo if npass == 3 else None, (N_, H, W, Cin), w_hi, w_lo if npass == 3 else None, Cout, b, out, residual=res,
+                     gn_sums=sums, npass=npass)
+    torch.cuda.synchronize()
+    xin = _ref_planes(a_hi, a_lo, npass).permute(0, 3, 1, 2)
+    win = _ref_planes(w_hi, w_lo, npass)[:rows].reshape(3, 3, Cout, Cin).permute(2, 3, 0, 1)
+    ref = F.conv2d(xin, win, b.double(), padding=1) + res.double().permute(0, 3, 1, 2)
+    assert torch.isfinite(out).all()
+    err = (out.double().permute(0, 3, 1, 2) - ref).abs().max().item()
+    assert err < 3e-4, f"max err {err}"
+    # GroupNorm statistics of the output: sum and sum of squares per (image, group)
+    o = out.double().permute(0, 3, 1, 2).reshape(N_, 32, -1)
+    want = torch.stack([o.sum(-1), (o * o).sum(-1)], -1).reshape(-1)
+    rel = ((sums - want).abs() / (1 + want.abs())).max().item()
+    assert rel < 1e-5, f"gn sums rel err {rel}"
+    mr = torch.empty(N_ * 64, dtype=torch.float32, device=dev())
+    ops.groupnorm_finalize(sums, mr, N_, H * W, Cout, 1e-6)
+    mean = o.mean(-1).reshape(-1)
+    assert (mr.view(-1, 2)[:, 0].double() - mean).abs().max().item() < 1e-5
