@@ -46,7 +46,7 @@ class PackedConv:
             w2 = w.permute(2, 3, 0, 1).reshape(kh * kw * cout, cin)
             self.k = cin
         n_tiles = (cout + self.bn - 1) // self.bn
-        w2 = _pad_rows(w2, (self.ntaps - 1) * cout + n_tiles * self.bn)
+        w2 = _pad_rows(w2, (self.ntaps - 1) * cout + max(n_tiles * self.bn, ((cout + 127) // 128) * 128))
         self.hi, self.lo = ops.split_planes(w2, npass)
         self.bias = None if bias is None else bias.to(device=device, dtype=torch.float32).contiguous()
 
@@ -60,6 +60,7 @@ class VQGANEngine:
         self.dd = dict(ddconfig)
         self.n_embed, self.embed_dim = n_embed, embed_dim
         self.sd = state_dict
+        self.use_halo = True          # halo-tile conv kernel for 3x3 stride-1 convs (Cin % 64 == 0)
         self.w = {}
         self._pack()
 
@@ -121,9 +122,13 @@ class VQGANEngine:
         hi, lo = self._planes(shape)
         if norm is not None:
             gamma, beta = self._norm(norm)
-            ws = torch.empty(n * 64, dtype=torch.float64, device=self.dev)
             mr = torch.empty(n * 64, dtype=torch.float32, device=self.dev)
-            ops.groupnorm_stats(x, ws, mr, 1e-6)
+            sums = getattr(x, "_gn_sums", None)
+            if sums is not None:          # statistics were accumulated by the producing conv's epilogue
+                ops.groupnorm_finalize(sums, mr, n, h * w, c, 1e-6)
+            else:
+                ws = torch.empty(n * 64, dtype=torch.float64, device=self.dev)
+                ops.groupnorm_stats(x, ws, mr, 1e-6)
             ops.prep_operand(x, hi, lo, mr, gamma, beta, swish=swish, mode=mode)
         else:
             ops.prep_operand(x, hi, lo, mode=mode)
@@ -153,10 +158,20 @@ class VQGANEngine:
     _TAPS1 = [(0, 0, 0)]
     _TAPS_S2 = [(kw // 2, kh // 2, (kh & 1) * 2 + (kw & 1)) for kh in range(3) for kw in range(3)]
 
+    def _conv3x3_planes(self, planes, pc, dims, residual=None, nchw=False):
+        """3x3 s1 'same' conv on operand planes: halo-tile kernel (+ fused GroupNorm statistics of the output) when eligible."""
+        n, h, w, c = dims
+        if self.use_halo and not nchw and c % 64 == 0 and pc.cout % 32 == 0 and pc.ntaps == 9:
+            out = torch.empty((n, h, w, pc.cout), dtype=torch.float32, device=self.dev)
+            sums = torch.empty(n * 64, dtype=torch.float64, device=self.dev)
+            ops.conv3x3_halo(planes[0], planes[1], dims, pc.hi, pc.lo, pc.cout, pc.bias, out, residual=residual, gn_sums=sums, npass=self.npass)
+            out._gn_sums = sums
+            return out
+        return self._gemm_conv(planes, pc, self._TAPS3, dims, (n, h, w), residual, nchw=nchw)
+
     def conv3x3(self, x, name, norm=None, swish=False, residual=None, nchw=False):
-        n, h, w, c = x.shape
         planes = self._prep(x, norm, swish)
-        return self._gemm_conv(planes, self._conv(name), self._TAPS3, (n, h, w, c), (n, h, w), residual, nchw=nchw)
+        return self._conv3x3_planes(planes, self._conv(name), tuple(x.shape), residual, nchw)
 
     def conv1x1(self, x, name, residual=None):
         n, h, w, c = x.shape
@@ -203,7 +218,7 @@ class VQGANEngine:
     def upsample(self, x, name):
         n, h, w, c = x.shape
         planes = self._prep(x, mode=ops.PREP_UP2)
-        return self._gemm_conv(planes, self._conv(f"{name}.conv"), self._TAPS3, (n, 2 * h, 2 * w, c), (n, 2 * h, 2 * w))
+        return self._conv3x3_planes(planes, self._conv(f"{name}.conv"), (n, 2 * h, 2 * w, c))
 
     # ------------------------------------------------------------------ networks
     @torch.no_grad()
