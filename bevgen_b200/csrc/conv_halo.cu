@@ -29,8 +29,9 @@ struct ConvHaloCfg {
   static constexpr int A_SLOT = NOPS * CH_A_PLANE;                       // 46080 / 23040
   static constexpr int A_SLOT_PAD = (A_SLOT + 1023) & ~1023;
   static constexpr int W_STAGE = NOPS * CH_W_TILE;                       // 32 KB / 16 KB
-  static constexpr int W_STAGES = (NPASS == 3) ? 4 : 8;
-  static constexpr int SMEM = 2 * A_SLOT_PAD + W_STAGES * W_STAGE + 1024 + 512 + 64 * 8;
+  static constexpr int W_STAGES = (NPASS == 3) ? 3 : 6;
+  static constexpr int STATS_BYTES = 4 * 64 * 8 + 4 * 16 * 33 * 4;       // per-warp fp64 accumulators + transpose scratch
+  static constexpr int SMEM = 2 * A_SLOT_PAD + W_STAGES * W_STAGE + 1024 + 512 + STATS_BYTES;
 };
 
 __device__ __forceinline__ uint64_t make_sdesc_noswz(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -44,23 +45,29 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* m, uin
       : "memory");
 }
 
-// GroupNorm partial statistics of one pixel row chunk (32 channels, CPG channels per group): warp-reduce over the 32 pixels of the warp,
-// lane 0 adds into the CTA accumulator (fp64 shared-memory atomics).
+// GroupNorm partial statistics of one 32-channel chunk (CPG channels per group, CPG >= 4): every lane (= pixel) forms its 2*(32/CPG)
+// per-group (sum, sum of squares), the warp transposes them through a private shared-memory scratch and lanes 0..NV-1 each reduce one
+// value over the 32 pixels and add it (fp64, no atomics: each slot has a single owner lane) into the warp's accumulator row.
 template <int CPG>
-__device__ __forceinline__ void gn_accumulate(const float (&v)[32], bool row_ok, int lane, int col0, double* gsm) {
+__device__ __forceinline__ void gn_accumulate(const float (&v)[32], bool row_ok, int lane, int col0, float* scratch /*[16][33]*/,
+                                              double* wacc /*[64] of this warp*/) {
+  constexpr int NG = 32 / CPG, NV = 2 * NG;
 #pragma unroll
-  for (int g = 0; g < 32 / CPG; ++g) {
+  for (int g = 0; g < NG; ++g) {
     float s = 0.f, ss = 0.f;
 #pragma unroll
     for (int j = 0; j < CPG; ++j) { const float x = row_ok ? v[g * CPG + j] : 0.f; s += x; ss += x * x; }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); ss += __shfl_xor_sync(0xffffffffu, ss, o); }
-    if (lane == 0) {
-      const int gi = col0 / CPG + g;
-      atomicAdd(&gsm[gi * 2], (double)s);
-      atomicAdd(&gsm[gi * 2 + 1], (double)ss);
-    }
+    scratch[(2 * g) * 33 + lane] = s;
+    scratch[(2 * g + 1) * 33 + lane] = ss;
   }
+  __syncwarp();
+  if (lane < NV) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) t += scratch[lane * 33 + i];
+    wacc[(col0 / CPG) * 2 + lane] += (double)t;        // group (col0/CPG + lane/2), component lane&1
+  }
+  __syncwarp();
 }
 
 template <int NPASS>
@@ -79,7 +86,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_halo_kernel(const __grid_c
   uint64_t* tfull = bars + 4 + 2 * WS;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
-  double* gsm = (double*)(bars + 64);                           // [64] group sums / sums of squares of the current image
+  double* gsm = (double*)(bars + 64);                           // [4 warps][64] group sums / sums of squares of the current image
+  float* gscr = (float*)(gsm + 4 * 64);                         // [4 warps][16][33] transpose scratch
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_w = (p.W + CH_TW - 1) / CH_TW, tiles_h = (p.H + CH_TH - 1) / CH_TH;
@@ -99,7 +107,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_halo_kernel(const __grid_c
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 256);
-  if (threadIdx.x >= 128 && threadIdx.x < 192) gsm[threadIdx.x - 128] = 0.0;
+  if (threadIdx.x >= 128) { gsm[threadIdx.x - 128] = 0.0; gsm[threadIdx.x] = 0.0; }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -189,9 +197,9 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_halo_kernel(const __grid_c
     auto flush = [&](int n_img) {                         // all 128 epilogue threads
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (n_img >= 0 && et < 64) {
-        const double v = gsm[et];
+        const double v = (gsm[et] + gsm[64 + et]) + (gsm[128 + et] + gsm[192 + et]);
         if (v != 0.0) atomicAdd(p.gn_sums + (size_t)n_img * 64 + et, v);
-        gsm[et] = 0.0;
+        gsm[et] = 0.0; gsm[64 + et] = 0.0; gsm[128 + et] = 0.0; gsm[192 + et] = 0.0;
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
     };
@@ -236,12 +244,10 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_halo_kernel(const __grid_c
         }
         if (p.gn_sums != nullptr) {
           switch (cpg) {
-            case 1: gn_accumulate<1>(v, row_ok, lane, col0, gsm); break;
-            case 2: gn_accumulate<2>(v, row_ok, lane, col0, gsm); break;
-            case 4: gn_accumulate<4>(v, row_ok, lane, col0, gsm); break;
-            case 8: gn_accumulate<8>(v, row_ok, lane, col0, gsm); break;
-            case 16: gn_accumulate<16>(v, row_ok, lane, col0, gsm); break;
-            default: gn_accumulate<32>(v, row_ok, lane, col0, gsm); break;
+            case 4: gn_accumulate<4>(v, row_ok, lane, col0, gscr + q * 16 * 33, gsm + q * 64); break;
+            case 8: gn_accumulate<8>(v, row_ok, lane, col0, gscr + q * 16 * 33, gsm + q * 64); break;
+            case 16: gn_accumulate<16>(v, row_ok, lane, col0, gscr + q * 16 * 33, gsm + q * 64); break;
+            default: gn_accumulate<32>(v, row_ok, lane, col0, gscr + q * 16 * 33, gsm + q * 64); break;
           }
         }
       }
@@ -271,7 +277,7 @@ static int launch_conv_halo_t(const ConvHaloParams& p, int sm_count, cudaStream_
 
 int launch_conv_halo(const ConvHaloParams& p, int npass, int sm_count, cudaStream_t st) {
   if (p.Cin % 64 != 0 || p.Cout % 32 != 0 || p.Cout % 4 != 0) return BEVGEN_ERR_ARG;
-  if (p.gn_sums != nullptr && (p.Cout / 32 > 32 || 32 % (p.Cout / 32) != 0 || p.Cout > 1024)) return BEVGEN_ERR_ARG;
+  if (p.gn_sums != nullptr && (p.Cout / 32 < 4 || p.Cout / 32 > 32 || 32 % (p.Cout / 32) != 0 || p.Cout > 1024)) return BEVGEN_ERR_ARG;
   return npass == 3 ? launch_conv_halo_t<3>(p, sm_count, st) : launch_conv_halo_t<1>(p, sm_count, st);
 }
 

@@ -163,9 +163,10 @@ class VQGANEngine:
         n, h, w, c = dims
         if self.use_halo and not nchw and c % 64 == 0 and pc.cout % 32 == 0 and pc.ntaps == 9:
             out = torch.empty((n, h, w, pc.cout), dtype=torch.float32, device=self.dev)
-            sums = torch.empty(n * 64, dtype=torch.float64, device=self.dev)
+            sums = torch.empty(n * 64, dtype=torch.float64, device=self.dev) if pc.cout >= 128 else None   # fused stats need >= 4 ch / group
             ops.conv3x3_halo(planes[0], planes[1], dims, pc.hi, pc.lo, pc.cout, pc.bias, out, residual=residual, gn_sums=sums, npass=self.npass)
-            out._gn_sums = sums
+            if sums is not None:
+                out._gn_sums = sums
             return out
         return self._gemm_conv(planes, pc, self._TAPS3, dims, (n, h, w), residual, nchw=nchw)
 

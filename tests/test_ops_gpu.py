@@ -282,7 +282,7 @@ def test_conv3x3_halo(N_, H, W, Cin, Cout, npass):
     wp[:rows] = w.permute(2, 3, 0, 1).reshape(rows, Cin)
     w_hi, w_lo = _split(wp)
     out = torch.full((N_, H, W, Cout), float("nan"), device=dev())
-    sums = torch.full((N_ * 64,), float("nan"), dtype=torch.float64, device=dev())
+    sums = torch.full((N_ * 64,), float("nan"), dtype=torch.float64, device=dev()) if Cout >= 128 else None
     ops.conv3x3_halo(a_hi, a_lo if npass == 3 else None, (N_, H, W, Cin), w_hi, w_lo if npass == 3 else None, Cout, b, out, residual=res,
                      gn_sums=sums, npass=npass)
     torch.cuda.synchronize()
@@ -292,6 +292,8 @@ def test_conv3x3_halo(N_, H, W, Cin, Cout, npass):
     assert torch.isfinite(out).all()
     err = (out.double().permute(0, 3, 1, 2) - ref).abs().max().item()
     assert err < 3e-4, f"max err {err}"
+    if sums is None:
+        return
     # GroupNorm statistics of the output: sum and sum of squares per (image, group)
     o = out.double().permute(0, 3, 1, 2).reshape(N_, 32, -1)
     want = torch.stack([o.sum(-1), (o * o).sum(-1)], -1).reshape(-1)
