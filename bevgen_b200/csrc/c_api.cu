@@ -179,6 +179,39 @@ BEVGEN_API int bevgen_conv3x3_halo(const void* a_hi, const void* a_lo, int n, in
   CHECK_LAUNCH(launch_conv_halo(p, npass, g_sm_count, (cudaStream_t)stream), "conv3x3_halo");
 }
 
+BEVGEN_API int bevgen_conv3x3_fused(const float* x, int n, int h, int w, int cin, const float* affine, int swish, int up2, const void* w_hi,
+                                    const void* w_lo, int w_rows, int cout, const float* bias, const float* residual, float* out, double* gn_sums,
+                                    int npass, void* stream) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  if (!x || !w_hi || !bias || !out || (npass == 3 && !w_lo) || !(npass == 1 || npass == 3)) return fail(BEVGEN_ERR_ARG, "conv3x3_fused: bad args");
+  if (cin % 64 != 0 || cout % 32 != 0 || n < 1 || h < 1 || w < 1) return fail(BEVGEN_ERR_ARG, "conv3x3_fused: cin %% 64 / cout %% 32 required (cin=%d cout=%d)", cin, cout);
+  if (w_rows < 8 * cout + ((cout + 127) / 128) * 128) return fail(BEVGEN_ERR_ARG, "conv3x3_fused: weight rows must be padded to 8*cout + ceil128(cout)");
+  if (((uintptr_t)x & 15) != 0 || (affine && ((uintptr_t)affine & 15) != 0)) return fail(BEVGEN_ERR_ARG, "conv3x3_fused: x / affine must be 16-byte aligned");
+  ConvFusedParams p;
+  memset(&p, 0, sizeof(p));
+  const void* wp[2] = {w_hi, w_lo};
+  for (int o = 0; o < (npass == 3 ? 2 : 1); ++o) {
+    uint64_t wd[2] = {(uint64_t)cin, (uint64_t)w_rows};
+    uint64_t wst[1] = {(uint64_t)cin * 2};
+    uint32_t wb[2] = {64, 128};
+    rc = make_tmap(&p.tmW[o], wp[o], 2, wd, wst, wb, true);
+    if (rc) return rc;
+  }
+  p.x = x; p.affine = affine; p.swish = swish; p.up2 = up2;
+  p.N = n; p.H = h; p.W = w; p.Cin = cin; p.Cout = cout;
+  p.bias = bias; p.residual = residual; p.out = out; p.gn_sums = gn_sums;
+  if (gn_sums != nullptr && cudaMemsetAsync(gn_sums, 0, (size_t)n * 64 * sizeof(double), (cudaStream_t)stream) != cudaSuccess)
+    return fail(BEVGEN_ERR_CUDA, "conv3x3_fused: memset failed");
+  CHECK_LAUNCH(launch_conv_fused(p, npass, g_sm_count, (cudaStream_t)stream), "conv3x3_fused");
+}
+
+BEVGEN_API int bevgen_groupnorm_affine(const double* sums, const float* gamma, const float* beta, int n, int pixels, int c, float eps, float* affine,
+                                       void* stream) {
+  if (!sums || !gamma || !beta || !affine || n < 1 || c % 32 != 0) return fail(BEVGEN_ERR_ARG, "groupnorm_affine: bad args");
+  CHECK_LAUNCH(launch_gn_affine(sums, gamma, beta, affine, n, pixels, c, eps, (cudaStream_t)stream), "groupnorm_affine");
+}
+
 BEVGEN_API int bevgen_groupnorm_finalize(const double* sums, int n, int pixels, int c, float eps, float* mean_rstd, void* stream) {
   if (!sums || !mean_rstd || n < 1 || c % 32 != 0) return fail(BEVGEN_ERR_ARG, "groupnorm_finalize: bad args");
   CHECK_LAUNCH(launch_gn_finalize(sums, mean_rstd, n, pixels, c, eps, (cudaStream_t)stream), "groupnorm_finalize");

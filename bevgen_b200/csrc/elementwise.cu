@@ -263,6 +263,27 @@ int launch_gn_stats(const float* x, double* sums, float* mean_rstd, int N, int p
   return cudaGetLastError() == cudaSuccess ? BEVGEN_OK : BEVGEN_ERR_CUDA;
 }
 
+// sums -> per-(image, channel) affine of the fused GroupNorm: y = x * scale + shift, scale = rstd*gamma, shift = beta - mean*rstd*gamma
+__global__ void gn_affine_kernel(const double* __restrict__ sums, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                 float* __restrict__ affine, int N, int C, double inv_cnt, double eps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * C) return;
+  const int n = i / C, c = i % C, g = c / (C / 32);
+  const double mean = sums[((size_t)n * 32 + g) * 2] * inv_cnt;
+  double var = sums[((size_t)n * 32 + g) * 2 + 1] * inv_cnt - mean * mean;
+  var = var < 0 ? 0 : var;
+  const double rstd = 1.0 / sqrt(var + eps);
+  const double sc = rstd * (double)gamma[c];
+  affine[2 * i] = (float)sc;
+  affine[2 * i + 1] = (float)((double)beta[c] - mean * sc);
+}
+
+int launch_gn_affine(const double* sums, const float* gamma, const float* beta, float* affine, int N, int pixels, int C, float eps, cudaStream_t st) {
+  if (C % 32 != 0) return BEVGEN_ERR_ARG;
+  gn_affine_kernel<<<(N * C + 255) / 256, 256, 0, st>>>(sums, gamma, beta, affine, N, C, 1.0 / ((double)pixels * (C / 32)), (double)eps);
+  return cudaGetLastError() == cudaSuccess ? BEVGEN_OK : BEVGEN_ERR_CUDA;
+}
+
 int launch_gn_finalize(const double* sums, float* mean_rstd, int N, int pixels, int C, float eps, cudaStream_t st) {
   gn_finalize_kernel<<<(N * 32 + 127) / 128, 128, 0, st>>>(sums, mean_rstd, N * 32, 1.0 / ((double)pixels * (C / 32)), (double)eps);
   return cudaGetLastError() == cudaSuccess ? BEVGEN_OK : BEVGEN_ERR_CUDA;

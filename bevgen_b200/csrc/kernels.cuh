@@ -74,6 +74,20 @@ struct ConvHaloParams {
 
 int launch_conv_halo(const ConvHaloParams& p, int npass, int sm_count, cudaStream_t st);
 
+struct ConvFusedParams {
+  CUtensorMap tmW[2];      // 2D (cin, tap*cout + co), box (64, 128), SWIZZLE_128B
+  const float* x;          // fp32 NHWC source [N][Hs][Ws][Cin] (Hs = H/2, Ws = W/2 when up2)
+  const float* affine;     // [N][Cin][2] (scale, shift) of the fused GroupNorm, or null
+  int swish, up2;
+  int N, H, W, Cin, Cout;  // H, W: conv (= output) geometry
+  const float* bias;
+  const float* residual;   // [N][H][W][Cout] or null
+  float* out;              // [N][H][W][Cout]
+  double* gn_sums;         // [N][32][2] or null: GroupNorm statistics of `out`
+};
+int launch_conv_fused(const ConvFusedParams& p, int npass, int sm_count, cudaStream_t st);
+int launch_gn_affine(const double* sums, const float* gamma, const float* beta, float* affine, int N, int pixels, int C, float eps, cudaStream_t st);
+
 int launch_attn_fused(const CUtensorMap* tm_hi, const CUtensorMap* tm_lo, const void* bias_f16, const float* y, float* x1, int B, int H, int L,
                       int nc, int d, float scale, int npass, cudaStream_t st);
 

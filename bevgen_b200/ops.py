@@ -227,3 +227,28 @@ def groupnorm_finalize(sums, mean_rstd, n, pixels, c, eps=1e-6):
     Stats.launches += 1
     _chk_cuda(sums, mean_rstd)
     _lib.check(lib.bevgen_groupnorm_finalize(_ptr(sums), n, pixels, c, eps, _ptr(mean_rstd), _stream()), "groupnorm_finalize")
+
+
+def conv3x3_fused(x, w_hi, w_lo, cout, bias, out, affine=None, swish=False, up2=False, residual=None, gn_sums=None, npass=3):
+    """3x3 s1 'same' conv straight from the fp32 NHWC activation `x` (GroupNorm-apply/swish/split/upsample fused into the operand path)."""
+    lib = _lib.init()
+    _chk_cuda(x, w_hi, w_lo, bias, out, affine, residual, gn_sums)
+    n, h, w, cout_ = out.shape
+    cin = x.shape[-1]
+    flops = 2.0 * n * h * w * cout * cin * 9
+    Stats.launches += 1
+    Stats.gemm_launches += 1
+    Stats.gemm_flops += flops
+    call = lambda: _lib.check(lib.bevgen_conv3x3_fused(_ptr(x), n, h, w, cin, _ptr(affine), int(swish), int(up2), _ptr(w_hi), _ptr(w_lo), w_hi.shape[0],
+                                                       cout, _ptr(bias), _ptr(residual), _ptr(out), _ptr(gn_sums), npass, _stream()), "conv3x3_fused")
+    if Stats.timer is not None:
+        Stats.timer("conv_fused", call, flops)
+    else:
+        call()
+
+
+def groupnorm_affine(sums, gamma, beta, affine, n, pixels, c, eps=1e-6):
+    lib = _lib.init()
+    Stats.launches += 1
+    _chk_cuda(sums, gamma, beta, affine)
+    _lib.check(lib.bevgen_groupnorm_affine(_ptr(sums), _ptr(gamma), _ptr(beta), n, pixels, c, eps, _ptr(affine), _stream()), "groupnorm_affine")

@@ -60,6 +60,7 @@ class VQGANEngine:
         self.dd = dict(ddconfig)
         self.n_embed, self.embed_dim = n_embed, embed_dim
         self.sd = state_dict
+        self.use_fused = True         # conv reads fp32 activations directly; GroupNorm/swish/split/upsample fused into its operand path
         self.use_halo = True          # halo-tile conv kernel for 3x3 stride-1 convs (Cin % 64 == 0)
         self.w = {}
         self._pack()
@@ -170,7 +171,33 @@ class VQGANEngine:
             return out
         return self._gemm_conv(planes, pc, self._TAPS3, dims, (n, h, w), residual, nchw=nchw)
 
+    def _conv3x3_fused(self, x, pc, norm, swish, residual, up2=False):
+        """conv straight from the fp32 activation: GroupNorm-apply + swish + split (+ 2x upsample) happen in the conv's operand path."""
+        n, h, w, c = x.shape
+        if up2:
+            h, w = 2 * h, 2 * w
+        affine = None
+        if norm is not None:
+            gamma, beta = self._norm(norm)
+            sums = getattr(x, "_gn_sums", None)
+            if sums is None:
+                sums = torch.empty(n * 64, dtype=torch.float64, device=self.dev)
+                mr = torch.empty(n * 64, dtype=torch.float32, device=self.dev)
+                ops.groupnorm_stats(x, sums, mr, 1e-6)
+            affine = torch.empty((n, c, 2), dtype=torch.float32, device=self.dev)
+            ops.groupnorm_affine(sums, gamma, beta, affine, n, x.shape[1] * x.shape[2], c, 1e-6)
+        out = torch.empty((n, h, w, pc.cout), dtype=torch.float32, device=self.dev)
+        osums = torch.empty(n * 64, dtype=torch.float64, device=self.dev) if pc.cout >= 128 else None
+        ops.conv3x3_fused(x, pc.hi, pc.lo, pc.cout, pc.bias, out, affine=affine, swish=swish, up2=up2, residual=residual, gn_sums=osums,
+                          npass=self.npass)
+        if osums is not None:
+            out._gn_sums = osums
+        return out
+
     def conv3x3(self, x, name, norm=None, swish=False, residual=None, nchw=False):
+        pc = self._conv(name)
+        if self.use_fused and not nchw and x.shape[-1] % 64 == 0 and pc.cout % 32 == 0 and pc.ntaps == 9:
+            return self._conv3x3_fused(x, pc, norm, swish, residual)
         planes = self._prep(x, norm, swish)
         return self._conv3x3_planes(planes, self._conv(name), tuple(x.shape), residual, nchw)
 
@@ -218,6 +245,9 @@ class VQGANEngine:
 
     def upsample(self, x, name):
         n, h, w, c = x.shape
+        pc = self._conv(f"{name}.conv")
+        if self.use_fused and c % 64 == 0 and pc.cout % 32 == 0:
+            return self._conv3x3_fused(x, pc, None, False, None, up2=True)
         planes = self._prep(x, mode=ops.PREP_UP2)
         return self._conv3x3_planes(planes, self._conv(f"{name}.conv"), (n, 2 * h, 2 * w, c))
 

@@ -93,6 +93,15 @@ BEVGEN_API int bevgen_gemm_tc(const bevgen_gemm_args* args, void* stream);
  * turned into (mean, rstd) by bevgen_groupnorm_finalize.  Weights: [tap][cout][cin] planes, rows padded to 8*cout + ceil128(cout). */
 BEVGEN_API int bevgen_conv3x3_halo(const void* a_hi, const void* a_lo, int n, int h, int w, int cin, const void* w_hi, const void* w_lo, int w_rows,
                                    int cout, const float* bias, const float* residual, float* out, double* gn_sums, int npass, void* stream);
+/* Same convolution reading the fp32 NHWC activation directly: GroupNorm-apply (per-(image,channel) affine from bevgen_groupnorm_affine,
+ * or NULL) + swish (model.py:29-31) + bf16 split + optional nearest 2x upsampling (up2: x is [n][h/2][w/2][cin], model.py:49-53) are
+ * fused into the operand path of the conv (no `prep` pass, no operand planes in HBM). */
+BEVGEN_API int bevgen_conv3x3_fused(const float* x, int n, int h, int w, int cin, const float* affine, int swish, int up2, const void* w_hi,
+                                    const void* w_lo, int w_rows, int cout, const float* bias, const float* residual, float* out, double* gn_sums,
+                                    int npass, void* stream);
+/* (sum, sumsq) per (image, group) + GroupNorm weight/bias -> affine[n][c][2] = (rstd*gamma, beta - mean*rstd*gamma) */
+BEVGEN_API int bevgen_groupnorm_affine(const double* sums, const float* gamma, const float* beta, int n, int pixels, int c, float eps, float* affine,
+                                       void* stream);
 BEVGEN_API int bevgen_groupnorm_finalize(const double* sums, int n, int pixels, int c, float eps, float* mean_rstd, void* stream);
 
 /* torch.nn.GroupNorm(32, C, eps) statistics (stage1/model.py:34-35): fp32 NHWC x[n][pixels][c] -> mean_rstd[n][32][2].

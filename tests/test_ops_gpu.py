@@ -303,3 +303,46 @@ def test_conv3x3_halo(N_, H, W, Cin, Cout, npass):
     ops.groupnorm_finalize(sums, mr, N_, H * W, Cout, 1e-6)
     mean = o.mean(-1).reshape(-1)
     assert (mr.view(-1, 2)[:, 0].double() - mean).abs().max().item() < 1e-5
+
+
+@pytest.mark.parametrize("npass", [3, 1])
+@pytest.mark.parametrize("N_,H,W,Cin,Cout,mode", [(2, 16, 16, 64, 128, "gn_swish"), (1, 20, 28, 128, 128, "gn_swish"), (3, 8, 8, 128, 256, "plain"),
+                                                   (2, 16, 16, 128, 128, "up2"), (1, 64, 64, 128, 128, "gn_swish")])
+def test_conv3x3_fused_prologue(N_, H, W, Cin, Cout, mode, npass):
+    """Conv reading fp32 activations directly with GroupNorm-apply + swish (+ nearest 2x upsample) fused into the operand path."""
+    g = torch.Generator().manual_seed(H * W + Cin + Cout + len(mode))
+    hs, ws_ = (H // 2, W // 2) if mode == "up2" else (H, W)
+    x = (torch.randn(N_, Cin, hs, ws_, generator=g) * 1.5 + 0.3).to(dev())
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / (9 * Cin) ** 0.5).to(dev())
+    b = torch.randn(Cout, generator=g).to(dev())
+    gamma, beta = torch.randn(Cin, generator=g).to(dev()), torch.randn(Cin, generator=g).to(dev())
+    res = torch.randn(N_, H, W, Cout, generator=g).to(dev())
+    x_nhwc = x.permute(0, 2, 3, 1).contiguous()
+    rows = 9 * Cout
+    wp = torch.zeros(8 * Cout + ((Cout + 127) // 128) * 128, Cin, device=dev())
+    wp[:rows] = w.permute(2, 3, 0, 1).reshape(rows, Cin)
+    w_hi, w_lo = _split(wp)
+    affine = None
+    ref_in = x.double()
+    if mode == "gn_swish":
+        sums = torch.empty(N_ * 64, dtype=torch.float64, device=dev())
+        mr = torch.empty(N_ * 64, dtype=torch.float32, device=dev())
+        ops.groupnorm_stats(x_nhwc, sums, mr, 1e-6)
+        affine = torch.empty(N_, Cin, 2, device=dev())
+        ops.groupnorm_affine(sums, gamma, beta, affine, N_, hs * ws_, Cin, 1e-6)
+        ref_in = F.group_norm(ref_in, 32, gamma.double(), beta.double(), eps=1e-6)
+        ref_in = ref_in * torch.sigmoid(ref_in)
+    if mode == "up2":
+        ref_in = F.interpolate(ref_in, scale_factor=2.0, mode="nearest")
+    out = torch.full((N_, H, W, Cout), float("nan"), device=dev())
+    osums = torch.full((N_ * 64,), float("nan"), dtype=torch.float64, device=dev())
+    ops.conv3x3_fused(x_nhwc, w_hi, w_lo if npass == 3 else None, Cout, b, out, affine=affine, swish=(mode == "gn_swish"), up2=(mode == "up2"),
+                      residual=res, gn_sums=osums, npass=npass)
+    torch.cuda.synchronize()
+    ref = F.conv2d(ref_in, w.double(), b.double(), padding=1) + res.double().permute(0, 3, 1, 2)
+    assert torch.isfinite(out).all()
+    err = (out.double().permute(0, 3, 1, 2) - ref).abs().max().item()
+    assert err < (3e-4 if npass == 3 else 8e-2), f"max err {err}"
+    o = out.double().permute(0, 3, 1, 2).reshape(N_, 32, -1)
+    want = torch.stack([o.sum(-1), (o * o).sum(-1)], -1).reshape(-1)
+    assert ((osums - want).abs() / (1 + want.abs())).max().item() < 1e-5
