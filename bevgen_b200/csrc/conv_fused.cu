@@ -35,8 +35,9 @@ struct ConvFusedCfg {
   static constexpr int A_SLOT_PAD = (A_SLOT + 1023) & ~1023;
   static constexpr int W_STAGE = NOPS * CH_W_TILE;                       // 32 KB / 16 KB
   static constexpr int W_STAGES = (NPASS == 3) ? 3 : 6;
-  static constexpr int STATS_BYTES = 4 * 64 * 8 + 4 * 16 * 33 * 4;       // per-warp fp64 accumulators + transpose scratch
-  static constexpr int SMEM = 2 * A_SLOT_PAD + W_STAGES * W_STAGE + 1024 + 512 + STATS_BYTES;
+  static constexpr int STATS_BYTES = 4 * 64 * 8 + 4 * 16 * 33 * 4 + 16;       // per-warp fp64 accumulators + transpose scratch
+  static constexpr int STAGE_BYTES = 3 * 2 * 256 * 16;                   // producer cp.async ring: 3 slots x 2 halves x 256 threads x 16 B
+  static constexpr int SMEM = 2 * A_SLOT_PAD + W_STAGES * W_STAGE + 1024 + 512 + STATS_BYTES + STAGE_BYTES;
 };
 
 __device__ __forceinline__ uint64_t make_sdesc_noswz(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -93,6 +94,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_fused_kernel(const __grid_
   uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
   double* gsm = (double*)(bars + 64);                           // [4 warps][64] group sums / sums of squares of the current image
   float* gscr = (float*)(gsm + 4 * 64);                         // [4 warps][16][33] transpose scratch
+  uint8_t* sStage = (uint8_t*)(((uintptr_t)(gscr + 4 * 16 * 33) + 15) & ~(uintptr_t)15);   // producer staging ring
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_w = (p.W + CH_TW - 1) / CH_TW, tiles_h = (p.H + CH_TH - 1) / CH_TH;
@@ -256,75 +258,100 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_fused_kernel(const __grid_
   }
   else if (warp >= 8) {
     // ===================== operand producers: global fp32 -> affine (+swish) -> bf16 hi/lo -> halo in shared memory =====================
+    // Every thread owns items (8-channel chunk, halo pixel) j*256 + pt of each (tile, channel chunk): 1440 items = 6 per thread, pixel
+    // fastest (conflict-free 16-byte shared stores).  The raw 32 bytes of an item are fetched with cp.async into a PRIVATE 3-deep ring
+    // of staging slots, 3 items ahead of the one being transformed (across tile / chunk boundaries), so global latency is hidden without
+    // holding the data in registers.
     const int pt = threadIdx.x - 256;                    // 0..255
     const int Hs = p.up2 ? p.H / 2 : p.H, Ws = p.up2 ? p.W / 2 : p.W;      // source geometry
+    constexpr int DEPTH = 3, IPT = 6;                     // ring depth, items per thread per (tile, kc)
+    uint8_t* stg = sStage + pt * 16;                      // slot s, half h at stg + (s*2 + h) * 256*16
+    const long long n_units = (t_end - t_begin) * KC;    // (tile, kc) units of this CTA
+    const long long n_items = n_units * IPT;
+
+    // item g -> (unit u = g / IPT, j = g % IPT) -> geometry; returns the shared-memory offset inside the halo plane (or -1) and whether
+    // it is inside the image; issues the two 16-byte cp.async when in bounds.
+    auto fetch = [&](long long g) {
+      if (g < n_items) {
+        const long long u = g / IPT;
+        const int jj = (int)(g % IPT);
+        const long long t = t_begin + u / KC;
+        const int kc = (int)(u % KC);
+        int n, th, tw, nt;
+        decode(t, n, th, tw, nt);
+        const int i = pt + 256 * jj;
+        if (i < 8 * CH_HPIX) {
+          const int chunk = i / CH_HPIX, px = i % CH_HPIX;
+          const int gh = th * CH_TH - 1 + px / CH_HW, gw = tw * CH_TW - 1 + px % CH_HW;
+          if (gh >= 0 && gh < p.H && gw >= 0 && gw < p.W) {
+            const int sh = p.up2 ? gh >> 1 : gh, sw_ = p.up2 ? gw >> 1 : gw;
+            const float* src = p.x + (((size_t)n * Hs + sh) * Ws + sw_) * p.Cin + kc * 64 + chunk * 8;
+            const uint32_t d0 = smem_u32(stg + ((int)(g % DEPTH) * 2) * 256 * 16);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0), "l"(src) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + 256 * 16), "l"(src + 4) : "memory");
+          }
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");      // one group per item (possibly empty) keeps the wait arithmetic uniform
+    };
+
+    for (int g = 0; g < DEPTH; ++g) fetch(g);
+    long long g = 0;
     uint32_t ai = 0;
     for (long long t = t_begin; t < t_end; ++t) {
       int n, th, tw, nt;
       decode(t, n, th, tw, nt);
-      const float* xn = p.x + (size_t)n * Hs * Ws * p.Cin;
       for (int kc = 0; kc < KC; ++kc, ++ai) {
         const int as = ai & 1;
-        // 1440 items = 8 channel chunks x 180 halo pixels, pixel fastest (conflict-free 16-byte shared stores)
-        float4 v0[6], v1[6];
-        int soff[6];
-#pragma unroll
-        for (int j = 0; j < 6; ++j) {
-          const int i = pt + 256 * j;
-          soff[j] = -1;
-          v0[j] = make_float4(0.f, 0.f, 0.f, 0.f); v1[j] = v0[j];
+        mbar_wait(&a_empty[as], ((ai >> 1) & 1) ^ 1);
+        uint8_t* dst = sA + as * Cfg::A_SLOT_PAD;
+#pragma unroll 1
+        for (int jj = 0; jj < IPT; ++jj, ++g) {
+          asm volatile("cp.async.wait_group %0;" ::"n"(DEPTH - 1) : "memory");     // item g has landed
+          const int i = pt + 256 * jj;
           if (i < 8 * CH_HPIX) {
             const int chunk = i / CH_HPIX, px = i % CH_HPIX;
             const int gh = th * CH_TH - 1 + px / CH_HW, gw = tw * CH_TW - 1 + px % CH_HW;
-            soff[j] = chunk * CH_CHUNK_STRIDE + px * 16;
-            if (gh >= 0 && gh < p.H && gw >= 0 && gw < p.W) {
-              const int sh = p.up2 ? gh >> 1 : gh, sw_ = p.up2 ? gw >> 1 : gw;
-              const float4* src = reinterpret_cast<const float4*>(xn + ((size_t)sh * Ws + sw_) * p.Cin + kc * 64 + chunk * 8);
-              v0[j] = __ldg(src); v1[j] = __ldg(src + 1);
-              soff[j] |= 0x40000000;                      // in-bounds marker (zero padding applies AFTER the transform)
-            }
-          }
-        }
-        mbar_wait(&a_empty[as], ((ai >> 1) & 1) ^ 1);
-        uint8_t* dst = sA + as * Cfg::A_SLOT_PAD;
+            const int off = chunk * CH_CHUNK_STRIDE + px * 16;
+            float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (gh >= 0 && gh < p.H && gw >= 0 && gw < p.W) {        // zero padding applies AFTER the transform
+              const uint8_t* sp = stg + ((int)(g % DEPTH) * 2) * 256 * 16;
+              const float4 a = *reinterpret_cast<const float4*>(sp), b = *reinterpret_cast<const float4*>(sp + 256 * 16);
+              f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+              if (p.affine != nullptr) {
+                const float4* ap = reinterpret_cast<const float4*>(p.affine + ((size_t)n * p.Cin + kc * 64 + chunk * 8) * 2);
 #pragma unroll
-        for (int j = 0; j < 6; ++j) {
-          if (soff[j] == -1) continue;
-          const int off = soff[j] & 0x3FFFFFFF;
-          float f[8] = {v0[j].x, v0[j].y, v0[j].z, v0[j].w, v1[j].x, v1[j].y, v1[j].z, v1[j].w};
-          if (soff[j] & 0x40000000) {
-            if (p.affine != nullptr) {
-              const int c0 = kc * 64 + (off / CH_CHUNK_STRIDE) * 8;
-              const float4* ap = reinterpret_cast<const float4*>(p.affine + ((size_t)n * p.Cin + c0) * 2);
+                for (int e = 0; e < 4; ++e) {
+                  const float4 sc = __ldg(ap + e);             // (scale, shift) x 2 channels
+                  f[2 * e] = fmaf(f[2 * e], sc.x, sc.y);
+                  f[2 * e + 1] = fmaf(f[2 * e + 1], sc.z, sc.w);
+                }
+              }
+              if (p.swish) {
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float4 sc = __ldg(ap + e);             // (scale, shift) x 2 channels
-                f[2 * e] = fmaf(f[2 * e], sc.x, sc.y);
-                f[2 * e + 1] = fmaf(f[2 * e + 1], sc.z, sc.w);
+                for (int e = 0; e < 8; ++e) f[e] = __fdividef(f[e], 1.0f + __expf(-f[e]));     // swish, fast intrinsics (~1e-6 rel.)
               }
             }
-            if (p.swish) {
+            uint32_t hh[4], ll[4];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) f[e] = f[e] / (1.0f + expf(-f[e]));
+            for (int e = 0; e < 4; ++e) {
+              __nv_bfloat16 h0, l0, h1, l1;
+              split_bf16(f[2 * e], h0, l0);
+              split_bf16(f[2 * e + 1], h1, l1);
+              hh[e] = pack_bf16(h0, h1);
+              ll[e] = pack_bf16(l0, l1);
             }
+            *reinterpret_cast<uint4*>(dst + off) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+            if (NPASS == 3) *reinterpret_cast<uint4*>(dst + CH_A_PLANE + off) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
           }
-          uint32_t hh[4], ll[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            __nv_bfloat16 h0, l0, h1, l1;
-            split_bf16(f[2 * e], h0, l0);
-            split_bf16(f[2 * e + 1], h1, l1);
-            hh[e] = pack_bf16(h0, h1);
-            ll[e] = pack_bf16(l0, l1);
-          }
-          *reinterpret_cast<uint4*>(dst + off) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
-          if (NPASS == 3) *reinterpret_cast<uint4*>(dst + CH_A_PLANE + off) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+          fetch(g + DEPTH);                 // refill the slot just consumed
         }
         fence_proxy_async();            // generic-proxy stores -> visible to the tensor core (async proxy)
         __syncwarp();
         if (lane == 0) mbar_arrive(&a_full[as]);
       }
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();

@@ -308,6 +308,7 @@ def test_conv3x3_halo(N_, H, W, Cin, Cout, npass):
 @pytest.mark.parametrize("npass", [3, 1])
 @pytest.mark.parametrize("N_,H,W,Cin,Cout,mode", [(2, 16, 16, 64, 128, "gn_swish"), (1, 20, 28, 128, 128, "gn_swish"), (3, 8, 8, 128, 256, "plain"),
                                                    (2, 16, 16, 128, 128, "up2"), (1, 64, 64, 128, 128, "gn_swish")])
+@pytest.mark.timeout(400)
 def test_conv3x3_fused_prologue(N_, H, W, Cin, Cout, mode, npass):
     """Conv reading fp32 activations directly with GroupNorm-apply + swish (+ nearest 2x upsample) fused into the operand path."""
     g = torch.Generator().manual_seed(H * W + Cin + Cout + len(mode))
