@@ -266,37 +266,39 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_fused_kernel(const __grid_
     const int Hs = p.up2 ? p.H / 2 : p.H, Ws = p.up2 ? p.W / 2 : p.W;      // source geometry
     constexpr int DEPTH = 3, IPT = 6;                     // ring depth, items per thread per (tile, kc)
     uint8_t* stg = sStage + pt * 16;                      // slot s, half h at stg + (s*2 + h) * 256*16
-    const long long n_units = (t_end - t_begin) * KC;    // (tile, kc) units of this CTA
-    const long long n_items = n_units * IPT;
 
-    // item g -> (unit u = g / IPT, j = g % IPT) -> geometry; returns the shared-memory offset inside the halo plane (or -1) and whether
-    // it is inside the image; issues the two 16-byte cp.async when in bounds.
-    auto fetch = [&](long long g) {
-      if (g < n_items) {
-        const long long u = g / IPT;
-        const int jj = (int)(g % IPT);
-        const long long t = t_begin + u / KC;
-        const int kc = (int)(u % KC);
-        int n, th, tw, nt;
-        decode(t, n, th, tw, nt);
-        const int i = pt + 256 * jj;
+    // fetch cursor (runs DEPTH items ahead of the transform cursor); advanced incrementally, no divisions by runtime values
+    long long f_t = t_begin;
+    int f_kc = 0, f_j = 0, f_slot = 0, f_n = 0, f_th = 0, f_tw = 0, f_nt = 0;
+    if (t_begin < t_end) decode(f_t, f_n, f_th, f_tw, f_nt);
+    auto fetch = [&]() {
+      if (f_t < t_end) {
+        const int i = pt + 256 * f_j;
         if (i < 8 * CH_HPIX) {
           const int chunk = i / CH_HPIX, px = i % CH_HPIX;
-          const int gh = th * CH_TH - 1 + px / CH_HW, gw = tw * CH_TW - 1 + px % CH_HW;
+          const int gh = f_th * CH_TH - 1 + px / CH_HW, gw = f_tw * CH_TW - 1 + px % CH_HW;
           if (gh >= 0 && gh < p.H && gw >= 0 && gw < p.W) {
             const int sh = p.up2 ? gh >> 1 : gh, sw_ = p.up2 ? gw >> 1 : gw;
-            const float* src = p.x + (((size_t)n * Hs + sh) * Ws + sw_) * p.Cin + kc * 64 + chunk * 8;
-            const uint32_t d0 = smem_u32(stg + ((int)(g % DEPTH) * 2) * 256 * 16);
+            const float* src = p.x + (((size_t)f_n * Hs + sh) * Ws + sw_) * p.Cin + f_kc * 64 + chunk * 8;
+            const uint32_t d0 = smem_u32(stg + (f_slot * 2) * 256 * 16);
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0), "l"(src) : "memory");
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + 256 * 16), "l"(src + 4) : "memory");
           }
         }
+        if (++f_j == IPT) {
+          f_j = 0;
+          if (++f_kc == KC) {
+            f_kc = 0;
+            if (++f_t < t_end) decode(f_t, f_n, f_th, f_tw, f_nt);
+          }
+        }
       }
+      if (++f_slot == DEPTH) f_slot = 0;
       asm volatile("cp.async.commit_group;" ::: "memory");      // one group per item (possibly empty) keeps the wait arithmetic uniform
     };
 
-    for (int g = 0; g < DEPTH; ++g) fetch(g);
-    long long g = 0;
+    for (int g = 0; g < DEPTH; ++g) fetch();
+    int c_slot = 0;                                       // transform cursor's staging slot
     uint32_t ai = 0;
     for (long long t = t_begin; t < t_end; ++t) {
       int n, th, tw, nt;
@@ -306,7 +308,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_fused_kernel(const __grid_
         mbar_wait(&a_empty[as], ((ai >> 1) & 1) ^ 1);
         uint8_t* dst = sA + as * Cfg::A_SLOT_PAD;
 #pragma unroll 1
-        for (int jj = 0; jj < IPT; ++jj, ++g) {
+        for (int jj = 0; jj < IPT; ++jj) {
           asm volatile("cp.async.wait_group %0;" ::"n"(DEPTH - 1) : "memory");     // item g has landed
           const int i = pt + 256 * jj;
           if (i < 8 * CH_HPIX) {
@@ -315,7 +317,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_fused_kernel(const __grid_
             const int off = chunk * CH_CHUNK_STRIDE + px * 16;
             float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             if (gh >= 0 && gh < p.H && gw >= 0 && gw < p.W) {        // zero padding applies AFTER the transform
-              const uint8_t* sp = stg + ((int)(g % DEPTH) * 2) * 256 * 16;
+              const uint8_t* sp = stg + (c_slot * 2) * 256 * 16;
               const float4 a = *reinterpret_cast<const float4*>(sp), b = *reinterpret_cast<const float4*>(sp + 256 * 16);
               f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
               if (p.affine != nullptr) {
@@ -344,7 +346,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_fused_kernel(const __grid_
             *reinterpret_cast<uint4*>(dst + off) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
             if (NPASS == 3) *reinterpret_cast<uint4*>(dst + CH_A_PLANE + off) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
           }
-          fetch(g + DEPTH);                 // refill the slot just consumed
+          if (++c_slot == DEPTH) c_slot = 0;
+          fetch();                          // refill the slot just consumed
         }
         fence_proxy_async();            // generic-proxy stores -> visible to the tensor core (async proxy)
         __syncwarp();
