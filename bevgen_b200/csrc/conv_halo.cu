@@ -227,8 +227,15 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_halo_kernel(const __grid_c
         const int col0 = n0 + c;
         if (col0 >= p.Cout) continue;                   // warp-uniform
         float v[32];
+        {
+          const float4* bp = reinterpret_cast<const float4*>(p.bias + col0);      // col0 % 32 == 0: 16-byte aligned, warp-uniform
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + __ldg(p.bias + col0 + j);
+          for (int j = 0; j < 8; ++j) {
+            const float4 b4 = __ldg(bp + j);
+            v[4 * j] = __uint_as_float(r[4 * j]) + b4.x; v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b4.y;
+            v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b4.z; v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b4.w;
+          }
+        }
         if (row_ok) {
           if (p.residual != nullptr) {
             const float4* rp = reinterpret_cast<const float4*>(p.residual + roff + c);

@@ -241,9 +241,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         }
         const bool full = (col0 + CH <= p.n_cols) && ((p.ldc & 3) == 0) && !(p.flags & GF_OUT_NCHW);
         if (p.bias != nullptr) {
+          if (col0 + CH <= p.n_cols && ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0)) {
+            const float4* bp = reinterpret_cast<const float4*>(p.bias + col0);    // warp-uniform, 16-byte aligned (col0 % 16 == 0)
 #pragma unroll
-          for (int j = 0; j < CH; ++j)
-            if (col0 + j < p.n_cols) v[j] += __ldg(p.bias + col0 + j);
+            for (int j = 0; j < CH / 4; ++j) {
+              const float4 b4 = __ldg(bp + j);
+              v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < CH; ++j)
+              if (col0 + j < p.n_cols) v[j] += __ldg(p.bias + col0 + j);
+          }
         }
         if (p.flags & GF_GELU) {
 #pragma unroll
