@@ -9,7 +9,6 @@
 // per (image, group), accumulated per CTA in shared memory and flushed with fp64 atomics when the image changes).
 // Output tile = 16 rows x 8 columns of pixels x 128 output channels; CTAs own contiguous tile ranges (halo reuse in L2, few flushes).
 #include "common.cuh"
-#include "epilogue.cuh"
 #include "kernels.cuh"
 
 namespace bevgen {
@@ -31,7 +30,7 @@ struct ConvHaloCfg {
   static constexpr int A_SLOT_PAD = (A_SLOT + 1023) & ~1023;
   static constexpr int W_STAGE = NOPS * CH_W_TILE;                       // 32 KB / 16 KB
   static constexpr int W_STAGES = (NPASS == 3) ? 3 : 6;
-  static constexpr int STATS_BYTES = 4 * 64 * 8 + 4 * 4096 + 16;      // per-warp fp64 GroupNorm accumulators + 4 KB epilogue transpose buffer per warp
+  static constexpr int STATS_BYTES = 4 * 64 * 8 + 4 * 16 * 33 * 4;       // per-warp fp64 accumulators + transpose scratch
   static constexpr int SMEM = 2 * A_SLOT_PAD + W_STAGES * W_STAGE + 1024 + 512 + STATS_BYTES;
 };
 
@@ -44,6 +43,31 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* m, uin
       "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
       ::"r"(smem_u32(dst)), "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
+}
+
+// GroupNorm partial statistics of one 32-channel chunk (CPG channels per group, CPG >= 4): every lane (= pixel) forms its 2*(32/CPG)
+// per-group (sum, sum of squares), the warp transposes them through a private shared-memory scratch and lanes 0..NV-1 each reduce one
+// value over the 32 pixels and add it (fp64, no atomics: each slot has a single owner lane) into the warp's accumulator row.
+template <int CPG>
+__device__ __forceinline__ void gn_accumulate(const float (&v)[32], bool row_ok, int lane, int col0, float* scratch /*[16][33]*/,
+                                              double* wacc /*[64] of this warp*/) {
+  constexpr int NG = 32 / CPG, NV = 2 * NG;
+#pragma unroll
+  for (int g = 0; g < NG; ++g) {
+    float s = 0.f, ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < CPG; ++j) { const float x = row_ok ? v[g * CPG + j] : 0.f; s += x; ss += x * x; }
+    scratch[(2 * g) * 33 + lane] = s;
+    scratch[(2 * g + 1) * 33 + lane] = ss;
+  }
+  __syncwarp();
+  if (lane < NV) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) t += scratch[lane * 33 + i];
+    wacc[(col0 / CPG) * 2 + lane] += (double)t;        // group (col0/CPG + lane/2), component lane&1
+  }
+  __syncwarp();
 }
 
 template <int NPASS>
@@ -63,7 +87,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_halo_kernel(const __grid_c
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
   double* gsm = (double*)(bars + 64);                           // [4 warps][64] group sums / sums of squares of the current image
-  uint8_t* estage = (uint8_t*)(((uintptr_t)(gsm + 4 * 64) + 15) & ~(uintptr_t)15);   // [4 warps][4 KB] epilogue transpose buffers
+  float* gscr = (float*)(gsm + 4 * 64);                         // [4 warps][16][33] transpose scratch
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_w = (p.W + CH_TW - 1) / CH_TW, tiles_h = (p.H + CH_TH - 1) / CH_TH;
@@ -184,13 +208,9 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_halo_kernel(const __grid_c
       decode(t, n, th, tw, nt);
       if (p.gn_sums != nullptr && n != cur_n) { flush(cur_n); cur_n = n; }
       const int n0 = nt * CH_BN;
-      RowMap rm;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int rr = q * 32 + 4 * i + (lane >> 3);              // tile row handled by this lane in transposed step i
-        const int ow = tw * CH_TW + (rr % CH_TW), oh = th * CH_TH + (rr / CH_TW);
-        rm.off[i] = (ow < p.W && oh < p.H) ? (((long long)n * p.H + oh) * p.W + ow) * p.Cout + n0 : -1;
-      }
+      const int ow = tw * CH_TW + (row % CH_TW), oh = th * CH_TH + (row / CH_TW);
+      const bool row_ok = (ow < p.W) && (oh < p.H);
+      const long long roff = (((long long)n * p.H + oh) * p.W + ow) * p.Cout + n0;
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * CH_BN;
@@ -216,7 +236,27 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_halo_kernel(const __grid_c
             v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b4.z; v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b4.w;
           }
         }
-        epilogue_chunk32(v, estage + q * 4096, lane, rm, c, p.residual, p.out, cpg, col0, p.gn_sums ? gsm + q * 64 : nullptr);
+        if (row_ok) {
+          if (p.residual != nullptr) {
+            const float4* rp = reinterpret_cast<const float4*>(p.residual + roff + c);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 rv = rp[j];
+              v[4 * j] += rv.x; v[4 * j + 1] += rv.y; v[4 * j + 2] += rv.z; v[4 * j + 3] += rv.w;
+            }
+          }
+          float4* op = reinterpret_cast<float4*>(p.out + roff + c);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+        if (p.gn_sums != nullptr) {
+          switch (cpg) {
+            case 4: gn_accumulate<4>(v, row_ok, lane, col0, gscr + q * 16 * 33, gsm + q * 64); break;
+            case 8: gn_accumulate<8>(v, row_ok, lane, col0, gscr + q * 16 * 33, gsm + q * 64); break;
+            case 16: gn_accumulate<16>(v, row_ok, lane, col0, gscr + q * 16 * 33, gsm + q * 64); break;
+            default: gn_accumulate<32>(v, row_ok, lane, col0, gscr + q * 16 * 33, gsm + q * 64); break;
+          }
+        }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
@@ -244,7 +284,7 @@ static int launch_conv_halo_t(const ConvHaloParams& p, int sm_count, cudaStream_
 
 int launch_conv_halo(const ConvHaloParams& p, int npass, int sm_count, cudaStream_t st) {
   if (p.Cin % 64 != 0 || p.Cout % 32 != 0 || p.Cout % 4 != 0) return BEVGEN_ERR_ARG;
-  if (p.gn_sums != nullptr && (p.Cout / 32 < 2 || p.Cout / 32 > 32 || 32 % (p.Cout / 32) != 0 || p.Cout > 1024)) return BEVGEN_ERR_ARG;
+  if (p.gn_sums != nullptr && (p.Cout / 32 < 4 || p.Cout / 32 > 32 || 32 % (p.Cout / 32) != 0 || p.Cout > 1024)) return BEVGEN_ERR_ARG;
   return npass == 3 ? launch_conv_halo_t<3>(p, sm_count, st) : launch_conv_halo_t<1>(p, sm_count, st);
 }
 

@@ -164,7 +164,7 @@ class VQGANEngine:
         n, h, w, c = dims
         if self.use_halo and not nchw and c % 64 == 0 and pc.cout % 32 == 0 and pc.ntaps == 9:
             out = torch.empty((n, h, w, pc.cout), dtype=torch.float32, device=self.dev)
-            sums = torch.empty(n * 64, dtype=torch.float64, device=self.dev) if pc.cout >= 64 else None   # fused stats need >= 2 ch / group
+            sums = torch.empty(n * 64, dtype=torch.float64, device=self.dev) if pc.cout >= 128 else None   # fused stats need >= 4 ch / group
             ops.conv3x3_halo(planes[0], planes[1], dims, pc.hi, pc.lo, pc.cout, pc.bias, out, residual=residual, gn_sums=sums, npass=self.npass)
             if sums is not None:
                 out._gn_sums = sums
@@ -187,7 +187,7 @@ class VQGANEngine:
             affine = torch.empty((n, c, 2), dtype=torch.float32, device=self.dev)
             ops.groupnorm_affine(sums, gamma, beta, affine, n, x.shape[1] * x.shape[2], c, 1e-6)
         out = torch.empty((n, h, w, pc.cout), dtype=torch.float32, device=self.dev)
-        osums = torch.empty(n * 64, dtype=torch.float64, device=self.dev) if pc.cout >= 64 else None
+        osums = torch.empty(n * 64, dtype=torch.float64, device=self.dev) if pc.cout >= 128 else None
         ops.conv3x3_fused(x, pc.hi, pc.lo, pc.cout, pc.bias, out, affine=affine, swish=swish, up2=up2, residual=residual, gn_sums=osums,
                           npass=self.npass)
         if osums is not None:

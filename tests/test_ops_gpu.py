@@ -282,7 +282,7 @@ def test_conv3x3_halo(N_, H, W, Cin, Cout, npass):
     wp[:rows] = w.permute(2, 3, 0, 1).reshape(rows, Cin)
     w_hi, w_lo = _split(wp)
     out = torch.full((N_, H, W, Cout), float("nan"), device=dev())
-    sums = torch.full((N_ * 64,), float("nan"), dtype=torch.float64, device=dev()) if Cout >= 64 else None
+    sums = torch.full((N_ * 64,), float("nan"), dtype=torch.float64, device=dev()) if Cout >= 128 else None
     ops.conv3x3_halo(a_hi, a_lo if npass == 3 else None, (N_, H, W, Cin), w_hi, w_lo if npass == 3 else None, Cout, b, out, residual=res,
                      gn_sums=sums, npass=npass)
     torch.cuda.synchronize()
