@@ -258,7 +258,7 @@ def main():
                 "d2h_bytes_per_step": rec_host.numel() * 4 + idx_host.numel() * 8, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 implicit GEMM, all conv/1x1/attention products)",
+        "roofline": {"bound": "tensor", "kernel": "conv_fused_kernel + gemm_tc_kernel (tcgen05 implicit-GEMM family: every conv / 1x1 / attention product of the step)",
                      "achieved": achieved, "peak": sustained, "unit": "TFLOP/s", "frac": achieved / sustained,
                      "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({how})", "traffic": None,
                      "launches_per_step": len(pairs), "kernel_ms_per_step": gemm_ms, "algorithmic_gflop_per_image": step_flops / n_img / 1e9,

@@ -65,9 +65,9 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fused_kernel(const __grid_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nq = p.L / AT_BM;
-  // heavy (late) query tiles first
-  const int qt = nq - 1 - (int)(blockIdx.x / (p.B * p.H));
-  const int bh = blockIdx.x % (p.B * p.H);
+  // (batch, head)-major order so the K/V of a pair stay L2-resident while its query tiles run; heavy (late) query tiles first
+  const int bh = (int)(blockIdx.x / nq);
+  const int qt = nq - 1 - (int)(blockIdx.x % nq);
   const int b = bh / p.H, h = bh % p.H;
   const int m0 = qt * AT_BM;
   const int T = (m0 < p.nc) ? (p.nc / AT_BN) : (m0 / AT_BN + 1);
