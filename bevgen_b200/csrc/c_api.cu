@@ -184,6 +184,8 @@ BEVGEN_API int bevgen_conv3x3_fused(const float* x, int n, int h, int w, int cin
                                     int npass, void* stream) {
   int rc = ensure_init();
   if (rc) return rc;
+  const bool two_cta = (npass & 0x100) != 0;      // bit 8 of npass selects the cta_group::2 (cluster of two CTAs) kernel
+  npass &= 0xff;
   if (!x || !w_hi || !bias || !out || (npass == 3 && !w_lo) || !(npass == 1 || npass == 3)) return fail(BEVGEN_ERR_ARG, "conv3x3_fused: bad args");
   if (cin % 64 != 0 || cout % 32 != 0 || n < 1 || h < 1 || w < 1) return fail(BEVGEN_ERR_ARG, "conv3x3_fused: cin %% 64 / cout %% 32 required (cin=%d cout=%d)", cin, cout);
   if (w_rows < 8 * cout + ((cout + 127) / 128) * 128) return fail(BEVGEN_ERR_ARG, "conv3x3_fused: weight rows must be padded to 8*cout + ceil128(cout)");
@@ -194,7 +196,7 @@ BEVGEN_API int bevgen_conv3x3_fused(const float* x, int n, int h, int w, int cin
   for (int o = 0; o < (npass == 3 ? 2 : 1); ++o) {
     uint64_t wd[2] = {(uint64_t)cin, (uint64_t)w_rows};
     uint64_t wst[1] = {(uint64_t)cin * 2};
-    uint32_t wb[2] = {64, 128};
+    uint32_t wb[2] = {64, (uint32_t)(two_cta ? 64 : 128)};
     rc = make_tmap(&p.tmW[o], wp[o], 2, wd, wst, wb, true);
     if (rc) return rc;
   }
@@ -203,6 +205,7 @@ BEVGEN_API int bevgen_conv3x3_fused(const float* x, int n, int h, int w, int cin
   p.bias = bias; p.residual = residual; p.out = out; p.gn_sums = gn_sums;
   if (gn_sums != nullptr && cudaMemsetAsync(gn_sums, 0, (size_t)n * 64 * sizeof(double), (cudaStream_t)stream) != cudaSuccess)
     return fail(BEVGEN_ERR_CUDA, "conv3x3_fused: memset failed");
+  if (two_cta) CHECK_LAUNCH(launch_conv_fused2(p, npass, g_sm_count, (cudaStream_t)stream), "conv3x3_fused (2-CTA)");
   CHECK_LAUNCH(launch_conv_fused(p, npass, g_sm_count, (cudaStream_t)stream), "conv3x3_fused");
 }
 

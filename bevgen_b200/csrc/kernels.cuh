@@ -86,6 +86,7 @@ struct ConvFusedParams {
   double* gn_sums;         // [N][32][2] or null: GroupNorm statistics of `out`
 };
 int launch_conv_fused(const ConvFusedParams& p, int npass, int sm_count, cudaStream_t st);
+int launch_conv_fused2(const ConvFusedParams& p, int npass, int sm_count, cudaStream_t st);   // 2-CTA clusters; tmW box = (64, 64)
 int launch_gn_affine(const double* sums, const float* gamma, const float* beta, float* affine, int N, int pixels, int C, float eps, cudaStream_t st);
 
 int launch_attn_fused(const CUtensorMap* tm_hi, const CUtensorMap* tm_lo, const void* bias_f16, const float* y, float* x1, int B, int H, int L,

@@ -229,7 +229,7 @@ def groupnorm_finalize(sums, mean_rstd, n, pixels, c, eps=1e-6):
     _lib.check(lib.bevgen_groupnorm_finalize(_ptr(sums), n, pixels, c, eps, _ptr(mean_rstd), _stream()), "groupnorm_finalize")
 
 
-def conv3x3_fused(x, w_hi, w_lo, cout, bias, out, affine=None, swish=False, up2=False, residual=None, gn_sums=None, npass=3):
+def conv3x3_fused(x, w_hi, w_lo, cout, bias, out, affine=None, swish=False, up2=False, residual=None, gn_sums=None, npass=3, two_cta=False):
     """3x3 s1 'same' conv straight from the fp32 NHWC activation `x` (GroupNorm-apply/swish/split/upsample fused into the operand path)."""
     lib = _lib.init()
     _chk_cuda(x, w_hi, w_lo, bias, out, affine, residual, gn_sums)
@@ -240,7 +240,7 @@ def conv3x3_fused(x, w_hi, w_lo, cout, bias, out, affine=None, swish=False, up2=
     Stats.gemm_launches += 1
     Stats.gemm_flops += flops
     call = lambda: _lib.check(lib.bevgen_conv3x3_fused(_ptr(x), n, h, w, cin, _ptr(affine), int(swish), int(up2), _ptr(w_hi), _ptr(w_lo), w_hi.shape[0],
-                                                       cout, _ptr(bias), _ptr(residual), _ptr(out), _ptr(gn_sums), npass, _stream()), "conv3x3_fused")
+                                                       cout, _ptr(bias), _ptr(residual), _ptr(out), _ptr(gn_sums), npass | (0x100 if two_cta else 0), _stream()), "conv3x3_fused")
     if Stats.timer is not None:
         Stats.timer("conv_fused", call, flops)
     else:

@@ -95,7 +95,8 @@ BEVGEN_API int bevgen_conv3x3_halo(const void* a_hi, const void* a_lo, int n, in
                                    int cout, const float* bias, const float* residual, float* out, double* gn_sums, int npass, void* stream);
 /* Same convolution reading the fp32 NHWC activation directly: GroupNorm-apply (per-(image,channel) affine from bevgen_groupnorm_affine,
  * or NULL) + swish (model.py:29-31) + bf16 split + optional nearest 2x upsampling (up2: x is [n][h/2][w/2][cin], model.py:49-53) are
- * fused into the operand path of the conv (no `prep` pass, no operand planes in HBM). */
+ * fused into the operand path of the conv (no `prep` pass, no operand planes in HBM).  npass | 0x100 selects the cta_group::2 kernel
+ * (clusters of two CTAs sharing every weight tile: half the L2->SM weight traffic and shared-memory reads per MMA). */
 BEVGEN_API int bevgen_conv3x3_fused(const float* x, int n, int h, int w, int cin, const float* affine, int swish, int up2, const void* w_hi,
                                     const void* w_lo, int w_rows, int cout, const float* bias, const float* residual, float* out, double* gn_sums,
                                     int npass, void* stream);

@@ -308,8 +308,9 @@ def test_conv3x3_halo(N_, H, W, Cin, Cout, npass):
 @pytest.mark.parametrize("npass", [3, 1])
 @pytest.mark.parametrize("N_,H,W,Cin,Cout,mode", [(2, 16, 16, 64, 128, "gn_swish"), (1, 20, 28, 128, 128, "gn_swish"), (3, 8, 8, 128, 256, "plain"),
                                                    (2, 16, 16, 128, 128, "up2"), (1, 64, 64, 128, 128, "gn_swish")])
+@pytest.mark.parametrize("two_cta", [False, True])
 @pytest.mark.timeout(400)
-def test_conv3x3_fused_prologue(N_, H, W, Cin, Cout, mode, npass):
+def test_conv3x3_fused_prologue(N_, H, W, Cin, Cout, mode, npass, two_cta):
     """Conv reading fp32 activations directly with GroupNorm-apply + swish (+ nearest 2x upsample) fused into the operand path."""
     g = torch.Generator().manual_seed(H * W + Cin + Cout + len(mode))
     hs, ws_ = (H // 2, W // 2) if mode == "up2" else (H, W)
@@ -338,7 +339,7 @@ def test_conv3x3_fused_prologue(N_, H, W, Cin, Cout, mode, npass):
     out = torch.full((N_, H, W, Cout), float("nan"), device=dev())
     osums = torch.full((N_ * 64,), float("nan"), dtype=torch.float64, device=dev())
     ops.conv3x3_fused(x_nhwc, w_hi, w_lo if npass == 3 else None, Cout, b, out, affine=affine, swish=(mode == "gn_swish"), up2=(mode == "up2"),
-                      residual=res, gn_sums=osums, npass=npass)
+                      residual=res, gn_sums=osums, npass=npass, two_cta=two_cta)
     torch.cuda.synchronize()
     ref = F.conv2d(ref_in, w.double(), b.double(), padding=1) + res.double().permute(0, 3, 1, 2)
     assert torch.isfinite(out).all()
