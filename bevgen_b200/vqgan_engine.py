@@ -60,6 +60,7 @@ class VQGANEngine:
         self.dd = dict(ddconfig)
         self.n_embed, self.embed_dim = n_embed, embed_dim
         self.sd = state_dict
+        self.use_two_cta = True       # cta_group::2 conv kernel (clusters of two CTAs share each weight tile)
         self.use_fused = True         # conv reads fp32 activations directly; GroupNorm/swish/split/upsample fused into its operand path
         self.use_halo = True          # halo-tile conv kernel for 3x3 stride-1 convs (Cin % 64 == 0)
         self.w = {}
@@ -189,7 +190,7 @@ class VQGANEngine:
         out = torch.empty((n, h, w, pc.cout), dtype=torch.float32, device=self.dev)
         osums = torch.empty(n * 64, dtype=torch.float64, device=self.dev) if pc.cout >= 128 else None
         ops.conv3x3_fused(x, pc.hi, pc.lo, pc.cout, pc.bias, out, affine=affine, swish=swish, up2=up2, residual=residual, gn_sums=osums,
-                          npass=self.npass)
+                          npass=self.npass, two_cta=self.use_two_cta)
         if osums is not None:
             out._gn_sums = osums
         return out
