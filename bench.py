@@ -245,7 +245,17 @@ def main():
         return
 
     sustained, burst, hbm, how = peaks()
-    achieved = gemm_fl / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+    agg_achieved = gemm_fl / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+    # dominant kernel = the launch shape with the largest total time (here: conv_fused 128->128 3x3 at 256x256 over 96 images)
+    groups = {}
+    for a, b, f in pairs:
+        g = groups.setdefault(round(f), [0.0, 0])
+        g[0] += a.elapsed_time(b)
+        g[1] += 1
+    dom_flops, (dom_ms, dom_n) = max(groups.items(), key=lambda kv: kv[1][0]) if groups else (0, (0.0, 0))
+    achieved = dom_flops / (dom_ms / dom_n / 1e3) / 1e12 if dom_n else 0.0
+    # DRAM traffic of that launch from the committed ncu capture (profiles/r01_conv_fused_ncu_full_summary.json): 3.60 GB read + 3.18 GB written
+    dom_traffic = 6.78e9 if abs(dom_flops - 2.0 * n_img * 256 * 256 * 128 * 128 * 9) < 1e6 and n_img == 96 else None
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -259,11 +269,16 @@ def main():
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "conv_fused_kernel + gemm_tc_kernel (tcgen05 implicit-GEMM family: every conv / 1x1 / attention product of the step)",
+                     "dominant_launch": f"3x3 conv 128->128 at 256x256 over {n_img} images: {dom_flops / 1e12:.3f} TFLOP algorithmic per launch, "
+                                        f"{dom_n} launches/step, {dom_ms / max(dom_n, 1):.3f} ms each (CUDA events, launching stream)",
                      "achieved": achieved, "peak": sustained, "unit": "TFLOP/s", "frac": achieved / sustained,
-                     "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({how})", "traffic": None,
-                     "launches_per_step": len(pairs), "kernel_ms_per_step": gemm_ms, "algorithmic_gflop_per_image": step_flops / n_img / 1e9,
+                     "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({how})", "traffic": dom_traffic,
+                     "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r01_conv_fused_ncu_full_summary.json "
+                                       "(algorithmic bytes: 3.22 GB fp32 in + 3.22 GB fp32 out)",
                      "executed_mma_multiplier": 3 if args.precision == "fp32x3" else 1,
-                     "kernel_share_of_step": gemm_ms / (ms / args.steps)},
+                     "executed_tflops": achieved * (3 if args.precision == "fp32x3" else 1),
+                     "family_launches_per_step": len(pairs), "family_ms_per_step": gemm_ms, "family_achieved_tflops": agg_achieved,
+                     "family_share_of_step": gemm_ms / (ms / args.steps), "algorithmic_gflop_per_image": step_flops / n_img / 1e9},
     }
     if world == 1 and not args.no_stage2:
         try:   # BASELINE configs[2]/[3]: stage-2 teacher-forced forward and KV-cache sampling (reported beside the headline)
