@@ -54,13 +54,14 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fused_kernel(const __grid_
   uint64_t* q_full = bars;            // 1
   uint64_t* k_full = bars + 1;        // 2
   uint64_t* v_full = bars + 3;        // 2
-  uint64_t* kv_empty = bars + 5;      // 2
+  uint64_t* v_empty = bars + 5;       // 2: V stage free once P.V of its tile completed
+  uint64_t* k_empty = bars + 16;      // 2: K stage free as soon as Q.K^T of its tile completed (lets the next K load start a whole softmax period early)
   uint64_t* s_full = bars + 7;        // 2
   uint64_t* s_empty = bars + 9;       // 2
   uint64_t* p_full = bars + 11;       // 1
   uint64_t* pv_done = bars + 12;      // 2
   uint64_t* pv_empty = bars + 14;     // 2
-  uint32_t* tmem_slot = (uint32_t*)(bars + 16);
+  uint32_t* tmem_slot = (uint32_t*)(bars + 18);
   float* xmax = (float*)(bars + 32);  // [128 rows][2 halves]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -80,7 +81,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fused_kernel(const __grid_
   if (warp == 1 && lane == 0) {
     mbar_init(q_full, 1);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&k_full[i], 1); mbar_init(&v_full[i], 1); mbar_init(&kv_empty[i], 1);
+      mbar_init(&k_full[i], 1); mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); mbar_init(&k_empty[i], 1);
       mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 8);
       mbar_init(&pv_done[i], 1); mbar_init(&pv_empty[i], 8);
     }
@@ -101,11 +102,12 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fused_kernel(const __grid_
       for (int o = 0; o < NOPS; ++o) tma_load_2d(sQ + o * AT_TILE, &p.tm[o], q_full, h * AT_DH, row0 + m0);
       for (int t = 0; t < T; ++t) {
         const int s = t & 1;
-        mbar_wait(&kv_empty[s], ((t >> 1) & 1) ^ 1);
         uint8_t* st = sKV + s * Cfg::KV_STAGE;
+        mbar_wait(&k_empty[s], ((t >> 1) & 1) ^ 1);
         mbar_expect_tx(&k_full[s], NOPS * AT_TILE);
 #pragma unroll
         for (int o = 0; o < NOPS; ++o) tma_load_2d(st + o * AT_TILE, &p.tm[o], &k_full[s], p.d + h * AT_DH, row0 + t * AT_BN);
+        mbar_wait(&v_empty[s], ((t >> 1) & 1) ^ 1);
         mbar_expect_tx(&v_full[s], NOPS * AT_TILE);
 #pragma unroll
         for (int o = 0; o < NOPS; ++o) tma_load_2d(st + (NOPS + o) * AT_TILE, &p.tm[o], &v_full[s], 2 * p.d + h * AT_DH, row0 + t * AT_BN);
@@ -135,6 +137,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fused_kernel(const __grid_
           }
         }
         umma_commit(&s_full[s]);
+        umma_commit(&k_empty[s]);
       };
       mbar_wait(q_full, 0);
       issue_s(0);
@@ -160,7 +163,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fused_kernel(const __grid_
           }
         }
         umma_commit(&pv_done[s]);
-        umma_commit(&kv_empty[s]);
+        umma_commit(&v_empty[s]);
       }
     }
   } else if (warp >= 4) {
