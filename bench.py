@@ -122,7 +122,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="fp32x3", choices=["fp32x3", "bf16"])
+    ap.add_argument("--precision", default="fp32x3", choices=["fp32x3", "f16f8", "bf16"])
     ap.add_argument("--scenes", type=int, default=SCENES)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stage2", action="store_true")

@@ -1,6 +1,7 @@
 // extern "C" boundary: argument validation, TMA descriptor construction, launches.  See include/bevgen_b200.h.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -179,21 +180,22 @@ BEVGEN_API int bevgen_conv3x3_halo(const void* a_hi, const void* a_lo, int n, in
   CHECK_LAUNCH(launch_conv_halo(p, npass, g_sm_count, (cudaStream_t)stream), "conv3x3_halo");
 }
 
-BEVGEN_API int bevgen_conv3x3_fused(const float* x, int n, int h, int w, int cin, const float* affine, int swish, int up2, const void* w_hi,
-                                    const void* w_lo, int w_rows, int cout, const float* bias, const float* residual, float* out, double* gn_sums,
-                                    int npass, void* stream) {
+static int conv3x3_fused_impl(const float* x, int n, int h, int w, int cin, const float* affine, int swish, int up2, const void* w_hi,
+                              const void* w_lo, int w_rows, int cout, const float* bias, const float* residual, float* out, double* gn_sums,
+                              int npass, float lo_scale, void* stream) {
   int rc = ensure_init();
   if (rc) return rc;
   const bool two_cta = (npass & 0x100) != 0;      // bit 8 of npass selects the cta_group::2 (cluster of two CTAs) kernel
   npass &= 0xff;
-  if (!x || !w_hi || !bias || !out || (npass == 3 && !w_lo) || !(npass == 1 || npass == 3)) return fail(BEVGEN_ERR_ARG, "conv3x3_fused: bad args");
+  if (!x || !w_hi || !bias || !out || (npass >= 2 && !w_lo) || !(npass >= 1 && npass <= 3)) return fail(BEVGEN_ERR_ARG, "conv3x3_fused: bad args");
+  if (npass == 2 && (!two_cta || !(lo_scale > 0.f))) return fail(BEVGEN_ERR_ARG, "conv3x3_fused: the f16+f8 mode exists for the 2-CTA kernel only and needs lo_scale > 0");
   if (cin % 64 != 0 || cout % 32 != 0 || n < 1 || h < 1 || w < 1) return fail(BEVGEN_ERR_ARG, "conv3x3_fused: cin %% 64 / cout %% 32 required (cin=%d cout=%d)", cin, cout);
   if (w_rows < 8 * cout + ((cout + 127) / 128) * 128) return fail(BEVGEN_ERR_ARG, "conv3x3_fused: weight rows must be padded to 8*cout + ceil128(cout)");
   if (((uintptr_t)x & 15) != 0 || (affine && ((uintptr_t)affine & 15) != 0)) return fail(BEVGEN_ERR_ARG, "conv3x3_fused: x / affine must be 16-byte aligned");
   ConvFusedParams p;
   memset(&p, 0, sizeof(p));
   const void* wp[2] = {w_hi, w_lo};
-  for (int o = 0; o < (npass == 3 ? 2 : 1); ++o) {
+  for (int o = 0; o < (npass >= 2 ? 2 : 1); ++o) {      // npass == 2: plane 1 is the packed e4m3 pair, also 2*cin bytes per row
     uint64_t wd[2] = {(uint64_t)cin, (uint64_t)w_rows};
     uint64_t wst[1] = {(uint64_t)cin * 2};
     uint32_t wb[2] = {64, (uint32_t)(two_cta ? 64 : 128)};
@@ -202,11 +204,26 @@ BEVGEN_API int bevgen_conv3x3_fused(const float* x, int n, int h, int w, int cin
   }
   p.x = x; p.affine = affine; p.swish = swish; p.up2 = up2;
   p.N = n; p.H = h; p.W = w; p.Cin = cin; p.Cout = cout;
-  p.bias = bias; p.residual = residual; p.out = out; p.gn_sums = gn_sums;
+  p.bias = bias; p.residual = residual; p.out = out; p.gn_sums = gn_sums; p.lo_scale = lo_scale;
+  { const char* e = getenv("BEVGEN_CONV_DBG"); p.dbg = e ? atoi(e) : 0; }
   if (gn_sums != nullptr && cudaMemsetAsync(gn_sums, 0, (size_t)n * 64 * sizeof(double), (cudaStream_t)stream) != cudaSuccess)
     return fail(BEVGEN_ERR_CUDA, "conv3x3_fused: memset failed");
   if (two_cta) CHECK_LAUNCH(launch_conv_fused2(p, npass, g_sm_count, (cudaStream_t)stream), "conv3x3_fused (2-CTA)");
   CHECK_LAUNCH(launch_conv_fused(p, npass, g_sm_count, (cudaStream_t)stream), "conv3x3_fused");
+}
+
+BEVGEN_API int bevgen_conv3x3_fused(const float* x, int n, int h, int w, int cin, const float* affine, int swish, int up2, const void* w_hi,
+                                    const void* w_lo, int w_rows, int cout, const float* bias, const float* residual, float* out, double* gn_sums,
+                                    int npass, void* stream) {
+  if ((npass & 0xff) == 2) return fail(BEVGEN_ERR_ARG, "conv3x3_fused: npass 2 is bevgen_conv3x3_fused_f16f8");
+  return conv3x3_fused_impl(x, n, h, w, cin, affine, swish, up2, w_hi, w_lo, w_rows, cout, bias, residual, out, gn_sums, npass, 0.f, stream);
+}
+
+BEVGEN_API int bevgen_conv3x3_fused_f16f8(const float* x, int n, int h, int w, int cin, const float* affine, int swish, int up2, const void* w_f16,
+                                          const void* w_f8pair, int w_rows, int cout, float lo_scale, const float* bias, const float* residual,
+                                          float* out, double* gn_sums, void* stream) {
+  return conv3x3_fused_impl(x, n, h, w, cin, affine, swish, up2, w_f16, w_f8pair, w_rows, cout, bias, residual, out, gn_sums, 2 | 0x100, lo_scale,
+                            stream);
 }
 
 BEVGEN_API int bevgen_groupnorm_affine(const double* sums, const float* gamma, const float* beta, int n, int pixels, int c, float eps, float* affine,

@@ -19,6 +19,9 @@
 // ring exactly as in gemm_tc.cu.  The epilogue fuses bias, residual and the GroupNorm(32) statistics of the OUTPUT (sum / sum of squares
 // per (image, group), accumulated per CTA in shared memory and flushed with fp64 atomics when the image changes).
 // Output tile = 16 rows x 8 columns of pixels x 128 output channels; CTAs own contiguous tile ranges (halo reuse in L2, few flushes).
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
+
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -37,11 +40,12 @@ constexpr int CH_THREADS = 512;        // warps 0-3 control, 4-7 epilogue, 8-15 
 
 template <int NPASS>
 struct ConvFusedCfg {
-  static constexpr int NOPS = (NPASS == 3) ? 2 : 1;
+  static constexpr int NOPS = (NPASS >= 2) ? 2 : 1;                       // NPASS == 2: fp16 plane + packed fp8 correction planes
+  static constexpr int TMEM_COLS = (NPASS == 2) ? 512 : 256;             // NPASS == 2 keeps the fp8 correction sum in its own accumulator
   static constexpr int A_SLOT = NOPS * CH_A_PLANE;                       // 46080 / 23040
   static constexpr int A_SLOT_PAD = (A_SLOT + 1023) & ~1023;
   static constexpr int W_STAGE = NOPS * CH_W_TILE;                       // 32 KB / 16 KB
-  static constexpr int W_STAGES = (NPASS == 3) ? 6 : 8;
+  static constexpr int W_STAGES = (NPASS >= 2) ? 6 : 8;
   static constexpr int STATS_BYTES = 4 * 64 * 8 + 4 * 16 * 33 * 4 + 16;       // per-warp fp64 accumulators + transpose scratch
   static constexpr int STAGE_BYTES = 3 * 2 * 256 * 16;                   // producer cp.async ring: 3 slots x 2 halves x 256 threads x 16 B
   static constexpr int SMEM = 2 * A_SLOT_PAD + W_STAGES * W_STAGE + 1024 + 512 + STATS_BYTES + STAGE_BYTES;
@@ -117,6 +121,15 @@ __device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, u
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// same issue shape for 8-bit operands (e4m3 x e4m3 -> fp32, K = 32 per instruction)
+__device__ __forceinline__ void umma_f8_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // arrive on the same-offset mbarrier of BOTH CTAs once all previously issued MMAs have completed
 __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
@@ -160,7 +173,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1) conv_
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmW[0]);
-    if (NPASS == 3) tma_prefetch_desc(&p.tmW[1]);
+    if (NPASS >= 2) tma_prefetch_desc(&p.tmW[1]);
   }
   if (warp == 1 && lane == 0) {
     // leader-side barriers collect arrivals from BOTH CTAs (a_full: 16 producer warps, tempty: 8 epilogue warps)
@@ -168,7 +181,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1) conv_
     for (int i = 0; i < WS; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc_2sm(tmem_slot, 256);
+  if (warp == 2) tmem_alloc_2sm(tmem_slot, Cfg::TMEM_COLS);
   if (threadIdx.x >= 128 && threadIdx.x < 384) gsm[threadIdx.x - 128] = 0.0;
   tc_fence_before();
   __syncthreads();
@@ -207,12 +220,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1) conv_
     }
   } else if (warp == 1) {
     if (lane == 0 && leader) {
-      const uint32_t idesc = make_idesc_bf16(256, CH_BN, 0, 0);           // M = 256 across the CTA pair
+      // M = 256 across the CTA pair.  NPASS == 2: A/B format field 0 = F16 under kind::f16 and = E4M3 under kind::f8f6f4 (same bits)
+      const uint32_t idesc = (NPASS == 2) ? (make_idesc_bf16(256, CH_BN, 0, 0) & ~((1u << 7) | (1u << 10))) : make_idesc_bf16(256, CH_BN, 0, 0);
+      constexpr uint32_t ACC_COLS = (NPASS == 2) ? 2 * CH_BN : CH_BN;
       uint32_t ai = 0, wi = 0, acc = 0, acc_phase = 0;
       for (long long t = t_begin; t < t_end; ++t) {
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * CH_BN;
+        const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
         for (int kc = 0; kc < KC; ++kc, ++ai) {
           const int as = ai & 1;
           mbar_wait(&a_full[as], (ai >> 1) & 1);
@@ -224,6 +239,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1) conv_
             tc_fence_after();
             const uint32_t b_base = smem_u32(sW + ws * Cfg::W_STAGE);
             const uint32_t a_tap = a_base + ((tap / 3) * CH_HW + (tap % 3)) * 16;     // shifted window inside the halo
+            if (p.dbg & 8) {
+            } else if (NPASS == 2) {
+              // x*w ~= x16*w16 (fp16 MMA, accumulator 0) + [xlo8*w8 + x8*wlo8] / S (e4m3 MMAs at twice the rate, accumulator 1)
+              const uint32_t first = (kc == 0 && tap == 0) ? 0u : 1u;
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_bf16_2sm(d_tmem, make_sdesc_noswz(a_tap + k * 2 * CH_CHUNK_STRIDE, CH_CHUNK_STRIDE, CH_ROW_STRIDE),
+                              make_sdesc_sw128(b_base + k * 32, 16, 1024), idesc, (k == 0) ? first : 1u);
+#pragma unroll
+              for (int k = 0; k < 2; ++k) {
+                umma_f8_2sm(d_tmem + CH_BN, make_sdesc_noswz(a_tap + CH_A_PLANE + k * 2 * CH_CHUNK_STRIDE, CH_CHUNK_STRIDE, CH_ROW_STRIDE),
+                            make_sdesc_sw128(b_base + CH_W_TILE + k * 32, 16, 1024), idesc, (k == 0) ? first : 1u);
+                umma_f8_2sm(d_tmem + CH_BN, make_sdesc_noswz(a_tap + CH_A_PLANE + CH_A_PLANE / 2 + k * 2 * CH_CHUNK_STRIDE, CH_CHUNK_STRIDE, CH_ROW_STRIDE),
+                            make_sdesc_sw128(b_base + CH_W_TILE + 64 + k * 32, 16, 1024), idesc, 1u);
+              }
+            } else {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const uint64_t a_hi = make_sdesc_noswz(a_tap + k * 2 * CH_CHUNK_STRIDE, CH_CHUNK_STRIDE, CH_ROW_STRIDE);
@@ -238,6 +269,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1) conv_
               } else {
                 umma_bf16_2sm(d_tmem, a_hi, b_hi, idesc, first);
               }
+            }
             }
             umma_commit_2sm(&w_empty[ws]);
           }
@@ -273,11 +305,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1) conv_
       const long long roff = (((long long)n * p.H + oh) * p.W + ow) * p.Cout + n0;
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * CH_BN;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ((NPASS == 2) ? 2 * CH_BN : CH_BN);
 #pragma unroll 1
       for (int c = 0; c < CH_BN; c += 32) {
         uint32_t r[32];
         tmem_ld_32x32(taddr + c, r);
+        if (NPASS == 2) {                                    // add the scaled fp8 correction accumulator
+          uint32_t r2[32];
+          tmem_ld_32x32(taddr + CH_BN + c, r2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(fmaf(__uint_as_float(r2[j]), p.lo_scale, __uint_as_float(r[j])));
+        }
         tmem_ld_wait();
         if (c + 32 >= CH_BN) {
           tc_fence_before();
@@ -288,7 +327,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1) conv_
           }
         }
         const int col0 = n0 + c;
-        if (col0 >= p.Cout) continue;                   // warp-uniform
+        if (col0 >= p.Cout || (p.dbg & 4)) continue;    // warp-uniform
         float v[32];
         {
           const float4* bp = reinterpret_cast<const float4*>(p.bias + col0);      // col0 % 32 == 0: 16-byte aligned, warp-uniform
@@ -346,7 +385,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1) conv_
         if (i < 8 * CH_HPIX) {
           const int chunk = i / CH_HPIX, px = i % CH_HPIX;
           const int gh = f_th * CH_TH - 1 + px / CH_HW, gw = f_tw * CH_TW - 1 + px % CH_HW;
-          if (gh >= 0 && gh < p.H && gw >= 0 && gw < p.W) {
+          if (gh >= 0 && gh < p.H && gw >= 0 && gw < p.W && !(p.dbg & 1)) {
             const int sh = p.up2 ? gh >> 1 : gh, sw_ = p.up2 ? gw >> 1 : gw;
             const float* src = p.x + (((size_t)f_n * Hs + sh) * Ws + sw_) * p.Cin + f_kc * 64 + chunk * 8;
             const uint32_t d0 = smem_u32(stg + (f_slot * 2) * 256 * 16);
@@ -380,7 +419,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1) conv_
         for (int jj = 0; jj < IPT; ++jj) {
           asm volatile("cp.async.wait_group %0;" ::"n"(DEPTH - 1) : "memory");     // item g has landed
           const int i = pt + 256 * jj;
-          if (i < 8 * CH_HPIX) {
+          if (i < 8 * CH_HPIX && !(p.dbg & 2)) {
             const int chunk = i / CH_HPIX, px = i % CH_HPIX;
             const int gh = th * CH_TH - 1 + px / CH_HW, gw = tw * CH_TW - 1 + px % CH_HW;
             const int off = chunk * CH_CHUNK_STRIDE + px * 16;
@@ -403,6 +442,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1) conv_
                 for (int e = 0; e < 8; ++e) f[e] = __fdividef(f[e], 1.0f + __expf(-f[e]));     // swish, fast intrinsics (~1e-6 rel.)
               }
             }
+            if (NPASS == 2) {
+              // fp16 plane + two e4m3 planes: lo8 = (x - fp16(x)) * 2^13 and x8 = x * 4 (satfinite: out-of-range values degrade gracefully)
+              uint32_t h16[4];
+              uint32_t l8[2] = {0u, 0u}, x8[2] = {0u, 0u};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const __half2 h2 = __floats2half2_rn(f[2 * e], f[2 * e + 1]);
+                h16[e] = *reinterpret_cast<const uint32_t*>(&h2);
+                const float2 hf = __half22float2(h2);
+                const uint32_t lo2 = __nv_cvt_float2_to_fp8x2(make_float2((f[2 * e] - hf.x) * 8192.0f, (f[2 * e + 1] - hf.y) * 8192.0f), __NV_SATFINITE, __NV_E4M3);
+                const uint32_t xx2 = __nv_cvt_float2_to_fp8x2(make_float2(f[2 * e] * 4.0f, f[2 * e + 1] * 4.0f), __NV_SATFINITE, __NV_E4M3);
+                l8[e >> 1] |= lo2 << (16 * (e & 1));
+                x8[e >> 1] |= xx2 << (16 * (e & 1));
+              }
+              *reinterpret_cast<uint4*>(dst + off) = make_uint4(h16[0], h16[1], h16[2], h16[3]);
+              const int off8 = (chunk >> 1) * CH_CHUNK_STRIDE + px * 16 + (chunk & 1) * 8;      // 16-channel chunks of 1-byte elements
+              *reinterpret_cast<uint2*>(dst + CH_A_PLANE + off8) = make_uint2(l8[0], l8[1]);
+              *reinterpret_cast<uint2*>(dst + CH_A_PLANE + CH_A_PLANE / 2 + off8) = make_uint2(x8[0], x8[1]);
+            } else {
             uint32_t hh[4], ll[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -414,6 +472,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1) conv_
             }
             *reinterpret_cast<uint4*>(dst + off) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
             if (NPASS == 3) *reinterpret_cast<uint4*>(dst + CH_A_PLANE + off) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+            }
           }
           if (++c_slot == DEPTH) c_slot = 0;
           fetch();                          // refill the slot just consumed
@@ -431,7 +490,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1) conv_
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();                 // the peer may still multicast into / arrive on this CTA's shared memory until both are done
-  if (warp == 2) tmem_dealloc_2sm(tmem_base, 256);
+  if (warp == 2) tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
 }
 
 template <int NPASS>
@@ -455,6 +514,7 @@ int launch_conv_fused(const ConvFusedParams& p, int npass, int sm_count, cudaStr
   if (p.Cin % 64 != 0 || p.Cout % 32 != 0 || p.Cout % 4 != 0) return BEVGEN_ERR_ARG;
   if (p.up2 && ((p.H | p.W) & 1)) return BEVGEN_ERR_ARG;
   if (p.gn_sums != nullptr && (p.Cout / 32 < 4 || p.Cout / 32 > 32 || 32 % (p.Cout / 32) != 0 || p.Cout > 1024)) return BEVGEN_ERR_ARG;
+  if (npass == 2) return launch_conv_fused2_t<2>(p, sm_count, st);
   return npass == 3 ? launch_conv_fused2_t<3>(p, sm_count, st) : launch_conv_fused2_t<1>(p, sm_count, st);
 }
 

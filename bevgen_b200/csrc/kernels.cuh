@@ -84,6 +84,9 @@ struct ConvFusedParams {
   const float* residual;   // [N][H][W][Cout] or null
   float* out;              // [N][H][W][Cout]
   double* gn_sums;         // [N][32][2] or null: GroupNorm statistics of `out`
+  int dbg;                 // ablation switches (BEVGEN_CONV_DBG, tools/conv_ablation.py): 1 no global fetch, 2 no operand transform/stores,
+                           // 4 epilogue drains TMEM only, 8 no MMA issue.  0 in production.
+  float lo_scale;          // npass == 2 (fp16 + e4m3 corrections): 1 / (2^13 * weight scale), applied to the correction accumulator
 };
 int launch_conv_fused(const ConvFusedParams& p, int npass, int sm_count, cudaStream_t st);
 int launch_conv_fused2(const ConvFusedParams& p, int npass, int sm_count, cudaStream_t st);   // 2-CTA clusters; tmW box = (64, 64)

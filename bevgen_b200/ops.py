@@ -1,6 +1,7 @@
 """Thin torch-tensor -> C-ABI adapters.  torch is used for device memory and the current CUDA stream only;
 all arithmetic happens inside libbevgen_b200.so."""
 import ctypes as C
+import math
 
 import torch
 
@@ -44,6 +45,28 @@ def split_planes(x: torch.Tensor, npass: int = 3):
     hi = x.to(torch.bfloat16)
     lo = (x - hi.float()).to(torch.bfloat16) if npass == 3 else None
     return hi.contiguous(), (None if lo is None else lo.contiguous())
+
+
+F8_ACT_LO_SHIFT = 13        # conv_fused2.cu producer: lo8 = e4m3((x - fp16(x)) * 2^13), x8 = e4m3(x * 2^2)
+F8_ACT_SHIFT = 2
+
+
+def pack_f16f8(w2d: torch.Tensor):
+    """fp32 weight rows [rows][cin] (cin % 64 == 0) -> (w16 [rows][cin] fp16, pair [rows][2*cin] uint8, lo_scale) for
+    bevgen_conv3x3_fused_f16f8: per 64-channel chunk 64 bytes e4m3(w * S) then 64 bytes e4m3((w - fp16(w)) * S * 2^11), with
+    S the largest power of two keeping max|w| * S <= 256 (e4m3 saturates at 448)."""
+    rows, cin = w2d.shape
+    assert cin % 64 == 0
+    w = w2d.float()
+    w16 = w.to(torch.float16)
+    amax = float(w.abs().max().item())
+    e = 8 if amax == 0.0 else min(max(8 - math.ceil(math.log2(amax)), -16), 24)
+    s = 2.0 ** e
+    k = F8_ACT_LO_SHIFT - F8_ACT_SHIFT
+    w8 = (w * s).clamp(-448.0, 448.0).to(torch.float8_e4m3fn)
+    wlo8 = ((w - w16.float()) * (s * 2.0 ** k)).clamp(-448.0, 448.0).to(torch.float8_e4m3fn)
+    pair = torch.stack([w8.view(torch.uint8).view(rows, cin // 64, 64), wlo8.view(torch.uint8).view(rows, cin // 64, 64)], 2)
+    return w16.contiguous(), pair.reshape(rows, 2 * cin).contiguous(), 1.0 / (2.0 ** F8_ACT_LO_SHIFT * s)
 
 
 TAPS_3X3 = [(kw - 1, kh - 1) for kh in range(3) for kw in range(3)]
@@ -241,6 +264,25 @@ def conv3x3_fused(x, w_hi, w_lo, cout, bias, out, affine=None, swish=False, up2=
     Stats.gemm_flops += flops
     call = lambda: _lib.check(lib.bevgen_conv3x3_fused(_ptr(x), n, h, w, cin, _ptr(affine), int(swish), int(up2), _ptr(w_hi), _ptr(w_lo), w_hi.shape[0],
                                                        cout, _ptr(bias), _ptr(residual), _ptr(out), _ptr(gn_sums), npass | (0x100 if two_cta else 0), _stream()), "conv3x3_fused")
+    if Stats.timer is not None:
+        Stats.timer("conv_fused", call, flops)
+    else:
+        call()
+
+
+def conv3x3_fused_f16f8(x, w16, w8pair, lo_scale, cout, bias, out, affine=None, swish=False, up2=False, residual=None, gn_sums=None):
+    """conv3x3_fused with the fp32-equivalent product formed as one fp16 MMA + two e4m3 MMAs (weights from pack_f16f8)."""
+    lib = _lib.init()
+    _chk_cuda(x, w16, w8pair, bias, out, affine, residual, gn_sums)
+    n, h, w, _ = out.shape
+    cin = x.shape[-1]
+    flops = 2.0 * n * h * w * cout * cin * 9
+    Stats.launches += 1
+    Stats.gemm_launches += 1
+    Stats.gemm_flops += flops
+    call = lambda: _lib.check(lib.bevgen_conv3x3_fused_f16f8(_ptr(x), n, h, w, cin, _ptr(affine), int(swish), int(up2), _ptr(w16), _ptr(w8pair),
+                                                             w16.shape[0], cout, float(lo_scale), _ptr(bias), _ptr(residual), _ptr(out),
+                                                             _ptr(gn_sums), _stream()), "conv3x3_fused_f16f8")
     if Stats.timer is not None:
         Stats.timer("conv_fused", call, flops)
     else:

@@ -348,3 +348,52 @@ def test_conv3x3_fused_prologue(N_, H, W, Cin, Cout, mode, npass, two_cta):
     o = out.double().permute(0, 3, 1, 2).reshape(N_, 32, -1)
     want = torch.stack([o.sum(-1), (o * o).sum(-1)], -1).reshape(-1)
     assert ((osums - want).abs() / (1 + want.abs())).max().item() < 1e-5
+
+
+@pytest.mark.parametrize("N_,H,W,Cin,Cout,mode", [(2, 16, 16, 64, 128, "gn_swish"), (1, 20, 28, 128, 128, "gn_swish"), (3, 8, 8, 128, 256, "plain"),
+                                                   (2, 16, 16, 128, 128, "up2"), (1, 64, 64, 128, 128, "gn_swish"), (1, 24, 8, 256, 96, "big")])
+@pytest.mark.timeout(400)
+def test_conv3x3_fused_f16f8(N_, H, W, Cin, Cout, mode):
+    """fp16 + 2 x e4m3 split product (bevgen_conv3x3_fused_f16f8): same contract as the bf16x3 kernel, error bound ~2^-15 per product.
+    "big" feeds activations far outside the e4m3 window (|x| up to ~400): the kernel must degrade to fp16 accuracy, not overflow."""
+    g = torch.Generator().manual_seed(H * W + Cin + Cout + len(mode))
+    hs, ws_ = (H // 2, W // 2) if mode == "up2" else (H, W)
+    amp = 100.0 if mode == "big" else 1.5
+    x = (torch.randn(N_, Cin, hs, ws_, generator=g) * amp + 0.3).to(dev())
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / (9 * Cin) ** 0.5).to(dev())
+    b = torch.randn(Cout, generator=g).to(dev())
+    gamma, beta = torch.randn(Cin, generator=g).to(dev()), torch.randn(Cin, generator=g).to(dev())
+    res = torch.randn(N_, H, W, Cout, generator=g).to(dev())
+    x_nhwc = x.permute(0, 2, 3, 1).contiguous()
+    rows = 9 * Cout
+    wp = torch.zeros(8 * Cout + ((Cout + 127) // 128) * 128, Cin, device=dev())
+    wp[:rows] = w.permute(2, 3, 0, 1).reshape(rows, Cin)
+    w16, w8pair, lo_scale = ops.pack_f16f8(wp)
+    assert w16.dtype == torch.float16 and w8pair.dtype == torch.uint8 and w8pair.shape == (wp.shape[0], 2 * Cin)
+    affine = None
+    ref_in = x.double()
+    if mode == "gn_swish":
+        sums = torch.empty(N_ * 64, dtype=torch.float64, device=dev())
+        mr = torch.empty(N_ * 64, dtype=torch.float32, device=dev())
+        ops.groupnorm_stats(x_nhwc, sums, mr, 1e-6)
+        affine = torch.empty(N_, Cin, 2, device=dev())
+        ops.groupnorm_affine(sums, gamma, beta, affine, N_, hs * ws_, Cin, 1e-6)
+        ref_in = F.group_norm(ref_in, 32, gamma.double(), beta.double(), eps=1e-6)
+        ref_in = ref_in * torch.sigmoid(ref_in)
+    if mode == "up2":
+        ref_in = F.interpolate(ref_in, scale_factor=2.0, mode="nearest")
+    out = torch.full((N_, H, W, Cout), float("nan"), device=dev())
+    osums = torch.full((N_ * 64,), float("nan"), dtype=torch.float64, device=dev()) if Cout >= 128 else None
+    ops.conv3x3_fused_f16f8(x_nhwc, w16, w8pair, lo_scale, Cout, b, out, affine=affine, swish=(mode == "gn_swish"), up2=(mode == "up2"),
+                            residual=res, gn_sums=osums)
+    torch.cuda.synchronize()
+    ref = F.conv2d(ref_in, w.double(), b.double(), padding=1) + res.double().permute(0, 3, 1, 2)
+    assert torch.isfinite(out).all()
+    err = (out.double().permute(0, 3, 1, 2) - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    # fp16-only accuracy would be ~5e-4 * scale-ish; the split product is two orders better
+    assert err < (1e-3 * scale if mode == "big" else 3e-4), f"max err {err} (output scale {scale})"
+    if osums is not None:
+        o = out.double().permute(0, 3, 1, 2).reshape(N_, 32, -1)
+        want = torch.stack([o.sum(-1), (o * o).sum(-1)], -1).reshape(-1)
+        assert ((osums - want).abs() / (1 + want.abs())).max().item() < 1e-5

@@ -22,10 +22,12 @@ def _engine(name, precision="fp32x3"):
     return VQGANEngine(sd, dd, device="cuda:0", precision=precision), sd, dd, x, (n, H, W)
 
 
+@pytest.mark.parametrize("precision", ["fp32x3", "f16f8"])
 @pytest.mark.parametrize("name", list(VQGAN_CASES))
-def test_vqgan_fp32x3_vs_reference_golden(name, golden_dir):
+def test_vqgan_fp32x3_vs_reference_golden(name, precision, golden_dir):
+    """Both parity modes (bf16x3 everywhere / fp16 + 2 x e4m3 in the 3x3 convs) must meet the same 1e-3 + bit-exact-token bar."""
     g = np.load(golden_dir / f"vqgan_{name}.npz")
-    eng, sd, dd, x, (n, H, W) = _engine(name)
+    eng, sd, dd, x, (n, H, W) = _engine(name, precision)
     zq, idx, h = eng.encode(x.cuda())
     torch.cuda.synchronize()
     h_nchw = eng.nhwc_to_nchw(h).cpu().numpy()
@@ -48,7 +50,7 @@ def test_vqgan_fp32x3_vs_reference_golden(name, golden_dir):
     assert rec.shape == (n, dd["out_ch"], H, W)
     err_r = np.abs(rec.cpu().numpy() - g["rec"]).max()
     assert err_r < PIXEL_TOL, f"reconstruction max err {err_r}"
-    print(f"[{name}] fp32x3: latent err {err_h:.2e}, rec err {err_r:.2e}, token mismatches {len(mism)}/{len(idx_c)}")
+    print(f"[{name}] {precision}: latent err {err_h:.2e}, rec err {err_r:.2e}, token mismatches {len(mism)}/{len(idx_c)}")
 
 
 @pytest.mark.parametrize("name", ["small_rgb", "config1_rgb"])

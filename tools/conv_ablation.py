@@ -17,10 +17,17 @@ out = torch.empty(N, H, W, C, device=dev)
 sums = torch.empty(N * 64, dtype=torch.float64, device=dev)
 flops = 2.0 * N * H * W * C * C * 9
 
-def t(label, npass=3, two_cta=True, **kw):
+import os
+w16, w8pair, lo_scale = ops.pack_f16f8(w)
+
+def t(label, npass=3, two_cta=True, dbg=0, **kw):
     args = dict(affine=aff, swish=True, residual=res, gn_sums=sums)
     args.update(kw)
-    f = lambda: ops.conv3x3_fused(x, w_hi, w_lo if npass == 3 else None, C, b, out, npass=npass, two_cta=two_cta, **args)
+    os.environ["BEVGEN_CONV_DBG"] = str(dbg)
+    if npass == 2:
+        f = lambda: ops.conv3x3_fused_f16f8(x, w16, w8pair, lo_scale, C, b, out, **args)
+    else:
+        f = lambda: ops.conv3x3_fused(x, w_hi, w_lo if npass == 3 else None, C, b, out, npass=npass, two_cta=two_cta, **args)
     for _ in range(2): f()
     torch.cuda.synchronize()
     a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -38,3 +45,17 @@ t("no stats", gn_sums=None)
 t("bare (identity prologue, no residual, no stats)", affine=None, swish=False, residual=None, gn_sums=None)
 t("bf16 full", npass=1)
 t("bf16 bare", npass=1, affine=None, swish=False, residual=None, gn_sums=None)
+
+for npass in (2, 3, 1):
+    print(f"--- kernel-internal ablations (BEVGEN_CONV_DBG), npass={npass}; results are wrong by construction")
+    t("full", npass=npass)
+    t("1: producers skip the global fetch", npass=npass, dbg=1)
+    t("2: producers skip transform + smem stores", npass=npass, dbg=2)
+    t("3: producers do nothing", npass=npass, dbg=3)
+    t("4: epilogue drains TMEM only", npass=npass, dbg=4)
+    t("8: no MMA issue", npass=npass, dbg=8)
+    t("7: producers + epilogue idle (MMA + weights)", npass=npass, dbg=7)
+    t("12: no MMA, epilogue idle (producers + weights)", npass=npass, dbg=12)
+    t("11: no MMA, producers idle (epilogue + weights)", npass=npass, dbg=11)
+    t("15: weights ring only", npass=npass, dbg=15)
+os.environ["BEVGEN_CONV_DBG"] = "0"
