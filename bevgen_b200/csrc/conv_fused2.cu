@@ -45,8 +45,8 @@ struct ConvFusedCfg {
   static constexpr int A_SLOT = NOPS * CH_A_PLANE;                       // 46080 / 23040
   static constexpr int A_SLOT_PAD = (A_SLOT + 1023) & ~1023;
   static constexpr int W_STAGE = NOPS * CH_W_TILE;                       // 32 KB / 16 KB
-  static constexpr int W_STAGES = (NPASS >= 2) ? 6 : 8;
-  static constexpr int STATS_BYTES = 4 * 64 * 8 + 4 * 16 * 33 * 4 + 16;       // per-warp fp64 accumulators + transpose scratch
+  static constexpr int W_STAGES = (NPASS >= 2) ? 5 : 8;
+  static constexpr int STATS_BYTES = 4 * 64 * 8 + 16 + 4 * 4096;             // per-warp fp64 GroupNorm accumulators + 4 KB epilogue transpose buffer per warp
   static constexpr int STAGE_BYTES = 3 * 2 * 256 * 16;                   // producer cp.async ring: 3 slots x 2 halves x 256 threads x 16 B
   static constexpr int SMEM = 2 * A_SLOT_PAD + W_STAGES * W_STAGE + 1024 + 512 + STATS_BYTES + STAGE_BYTES;
 };
@@ -60,31 +60,6 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* m, uin
       "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
       ::"r"(smem_u32(dst)), "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
-}
-
-// GroupNorm partial statistics of one 32-channel chunk (CPG channels per group, CPG >= 4): every lane (= pixel) forms its 2*(32/CPG)
-// per-group (sum, sum of squares), the warp transposes them through a private shared-memory scratch and lanes 0..NV-1 each reduce one
-// value over the 32 pixels and add it (fp64, no atomics: each slot has a single owner lane) into the warp's accumulator row.
-template <int CPG>
-__device__ __forceinline__ void gn_accumulate(const float (&v)[32], bool row_ok, int lane, int col0, float* scratch /*[16][33]*/,
-                                              double* wacc /*[64] of this warp*/) {
-  constexpr int NG = 32 / CPG, NV = 2 * NG;
-#pragma unroll
-  for (int g = 0; g < NG; ++g) {
-    float s = 0.f, ss = 0.f;
-#pragma unroll
-    for (int j = 0; j < CPG; ++j) { const float x = row_ok ? v[g * CPG + j] : 0.f; s += x; ss += x * x; }
-    scratch[(2 * g) * 33 + lane] = s;
-    scratch[(2 * g + 1) * 33 + lane] = ss;
-  }
-  __syncwarp();
-  if (lane < NV) {
-    float t = 0.f;
-#pragma unroll
-    for (int i = 0; i < 32; ++i) t += scratch[lane * 33 + i];
-    wacc[(col0 / CPG) * 2 + lane] += (double)t;        // group (col0/CPG + lane/2), component lane&1
-  }
-  __syncwarp();
 }
 
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
@@ -130,6 +105,11 @@ __device__ __forceinline__ void umma_f8_2sm(uint32_t tmem_d, uint64_t adesc, uin
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 // arrive on the same-offset mbarrier of BOTH CTAs once all previously issued MMAs have completed
 __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
@@ -152,10 +132,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1) conv_
   uint64_t* w_empty = bars + 4 + WS;  // WS
   uint64_t* tfull = bars + 4 + 2 * WS;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+  uint64_t* a_fwd = tempty + 2;       // 2: peer CTA only, its 8 producer warps; warp 3 forwards each completion to the leader's a_full
+  uint32_t* tmem_slot = (uint32_t*)(a_fwd + 2);
   double* gsm = (double*)(bars + 64);                           // [4 warps][64] group sums / sums of squares of the current image
-  float* gscr = (float*)(gsm + 4 * 64);                         // [4 warps][16][33] transpose scratch
-  uint8_t* sStage = (uint8_t*)(((uintptr_t)(gscr + 4 * 16 * 33) + 15) & ~(uintptr_t)15);   // producer staging ring
+  uint8_t* sEpi = (uint8_t*)(((uintptr_t)(gsm + 4 * 64) + 15) & ~(uintptr_t)15);            // [4 warps][4 KB] epilogue transpose buffers
+  uint8_t* sStage = sEpi + 4 * 4096;                                                          // producer staging ring
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_w = (p.W + CH_TW - 1) / CH_TW, tiles_h = (p.H + CH_TH - 1) / CH_TH;
@@ -176,8 +157,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1) conv_
     if (NPASS >= 2) tma_prefetch_desc(&p.tmW[1]);
   }
   if (warp == 1 && lane == 0) {
-    // leader-side barriers collect arrivals from BOTH CTAs (a_full: 16 producer warps, tempty: 8 epilogue warps)
-    for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 16); mbar_init(&a_empty[i], 1); mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
+    // leader-side barriers collect arrivals from BOTH CTAs (a_full: 8 own producer warps + the peer's forwarder, tempty: 8 epilogue warps)
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&a_full[i], 9); mbar_init(&a_empty[i], 1); mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); mbar_init(&a_fwd[i], 8);
+    }
     for (int i = 0; i < WS; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
     fence_barrier_init();
   }
@@ -219,70 +202,93 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1) conv_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && leader) {
+    if (leader) {
+      // The WHOLE warp runs the (warp-uniform) control flow, so ptxas keeps barrier addresses / descriptors in uniform registers; one
+      // elected lane issues the MMAs and commits (a lane-0-only branch made every descriptor a chain of R2UR moves and the single issuing
+      // thread the limiter of the kernel: ~980 cycles per 8-MMA stage against 512 cycles of tensor time, profiles/r01 ablation).
+      const bool elected = elect_one();
       // M = 256 across the CTA pair.  NPASS == 2: A/B format field 0 = F16 under kind::f16 and = E4M3 under kind::f8f6f4 (same bits)
       const uint32_t idesc = (NPASS == 2) ? (make_idesc_bf16(256, CH_BN, 0, 0) & ~((1u << 7) | (1u << 10))) : make_idesc_bf16(256, CH_BN, 0, 0);
       constexpr uint32_t ACC_COLS = (NPASS == 2) ? 2 * CH_BN : CH_BN;
-      uint32_t ai = 0, wi = 0, acc = 0, acc_phase = 0;
+      // descriptors = constant high word + (address >> 4) in the low 14 bits: all per-tap / per-k variants are small constant increments
+      const uint64_t adesc0 = make_sdesc_noswz(smem_u32(sA), CH_CHUNK_STRIDE, CH_ROW_STRIDE);
+      const uint64_t bdesc0 = make_sdesc_sw128(smem_u32(sW), 16, 1024);
+      constexpr uint64_t AK = (2 * CH_CHUNK_STRIDE) >> 4, AP = CH_A_PLANE >> 4, WT = CH_W_TILE >> 4;
+      const bool issue = elected && !(p.dbg & 8);
+      uint32_t ai = 0, ws = 0, wphase = 0, acc = 0, acc_phase = 0;
       for (long long t = t_begin; t < t_end; ++t) {
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
         for (int kc = 0; kc < KC; ++kc, ++ai) {
-          const int as = ai & 1;
+          const uint32_t as = ai & 1;
           mbar_wait(&a_full[as], (ai >> 1) & 1);
           tc_fence_after();
-          const uint32_t a_base = smem_u32(sA + as * Cfg::A_SLOT_PAD);
-          for (int tap = 0; tap < 9; ++tap, ++wi) {
-            const int ws = wi % WS;
-            mbar_wait(&w_full[ws], (wi / WS) & 1);
+          const uint64_t a_slot = adesc0 + (uint64_t)(as * (Cfg::A_SLOT_PAD >> 4));
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(&w_full[ws], wphase);
             tc_fence_after();
-            const uint32_t b_base = smem_u32(sW + ws * Cfg::W_STAGE);
-            const uint32_t a_tap = a_base + ((tap / 3) * CH_HW + (tap % 3)) * 16;     // shifted window inside the halo
-            if (p.dbg & 8) {
-            } else if (NPASS == 2) {
-              // x*w ~= x16*w16 (fp16 MMA, accumulator 0) + [xlo8*w8 + x8*wlo8] / S (e4m3 MMAs at twice the rate, accumulator 1)
-              const uint32_t first = (kc == 0 && tap == 0) ? 0u : 1u;
+            const uint64_t at = a_slot + (uint64_t)((tap / 3) * CH_HW + (tap % 3));     // shifted window inside the halo (16-byte units)
+            const uint64_t bt = bdesc0 + (uint64_t)(ws * (Cfg::W_STAGE >> 4));
+            if (issue) {
+              if (NPASS == 2) {
+                // x*w ~= x16*w16 (fp16 MMA, accumulator 0) + [xlo8*w8 + x8*wlo8] / S (e4m3 MMAs at twice the rate, accumulator 1)
+                const uint32_t first = (kc == 0 && tap == 0) ? 0u : 1u;
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_bf16_2sm(d_tmem, make_sdesc_noswz(a_tap + k * 2 * CH_CHUNK_STRIDE, CH_CHUNK_STRIDE, CH_ROW_STRIDE),
-                              make_sdesc_sw128(b_base + k * 32, 16, 1024), idesc, (k == 0) ? first : 1u);
+                for (int k = 0; k < 4; ++k) umma_bf16_2sm(d_tmem, at + k * AK, bt + k * 2, idesc, (k == 0) ? first : 1u);
 #pragma unroll
-              for (int k = 0; k < 2; ++k) {
-                umma_f8_2sm(d_tmem + CH_BN, make_sdesc_noswz(a_tap + CH_A_PLANE + k * 2 * CH_CHUNK_STRIDE, CH_CHUNK_STRIDE, CH_ROW_STRIDE),
-                            make_sdesc_sw128(b_base + CH_W_TILE + k * 32, 16, 1024), idesc, (k == 0) ? first : 1u);
-                umma_f8_2sm(d_tmem + CH_BN, make_sdesc_noswz(a_tap + CH_A_PLANE + CH_A_PLANE / 2 + k * 2 * CH_CHUNK_STRIDE, CH_CHUNK_STRIDE, CH_ROW_STRIDE),
-                            make_sdesc_sw128(b_base + CH_W_TILE + 64 + k * 32, 16, 1024), idesc, 1u);
-              }
-            } else {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint64_t a_hi = make_sdesc_noswz(a_tap + k * 2 * CH_CHUNK_STRIDE, CH_CHUNK_STRIDE, CH_ROW_STRIDE);
-              const uint64_t b_hi = make_sdesc_sw128(b_base + k * 32, 16, 1024);
-              const uint32_t first = (kc == 0 && tap == 0 && k == 0) ? 0u : 1u;
-              if (NPASS == 3) {
-                const uint64_t a_lo = make_sdesc_noswz(a_tap + CH_A_PLANE + k * 2 * CH_CHUNK_STRIDE, CH_CHUNK_STRIDE, CH_ROW_STRIDE);
-                const uint64_t b_lo = make_sdesc_sw128(b_base + CH_W_TILE + k * 32, 16, 1024);
-                umma_bf16_2sm(d_tmem, a_lo, b_hi, idesc, first);
-                umma_bf16_2sm(d_tmem, a_hi, b_lo, idesc, 1u);
-                umma_bf16_2sm(d_tmem, a_hi, b_hi, idesc, 1u);
+                for (int k = 0; k < 2; ++k) {
+                  umma_f8_2sm(d_tmem + CH_BN, at + AP + k * AK, bt + WT + k * 2, idesc, (k == 0) ? first : 1u);
+                  umma_f8_2sm(d_tmem + CH_BN, at + AP + AP / 2 + k * AK, bt + WT + 4 + k * 2, idesc, 1u);
+                }
               } else {
-                umma_bf16_2sm(d_tmem, a_hi, b_hi, idesc, first);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const uint32_t first = (kc == 0 && tap == 0 && k == 0) ? 0u : 1u;
+                  if (NPASS == 3) {
+                    umma_bf16_2sm(d_tmem, at + AP + k * AK, bt + k * 2, idesc, first);
+                    umma_bf16_2sm(d_tmem, at + k * AK, bt + WT + k * 2, idesc, 1u);
+                    umma_bf16_2sm(d_tmem, at + k * AK, bt + k * 2, idesc, 1u);
+                  } else {
+                    umma_bf16_2sm(d_tmem, at + k * AK, bt + k * 2, idesc, first);
+                  }
+                }
               }
             }
-            }
-            umma_commit_2sm(&w_empty[ws]);
+            if (elected) umma_commit_2sm(&w_empty[ws]);
+            if (++ws == WS) { ws = 0; wphase ^= 1; }
           }
-          umma_commit_2sm(&a_empty[as]);
+          if (elected) umma_commit_2sm(&a_empty[as]);
         }
-        umma_commit_2sm(&tfull[acc]);
+        if (elected) umma_commit_2sm(&tfull[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp == 3) {
+    // peer CTA: one cluster-scope release per operand slot instead of one per producer warp (the release is a heavyweight MEMBAR.ALL.GPU)
+    if (lane == 0 && !leader) {
+      const long long n_slots = (t_end - t_begin) * KC;
+      for (long long i = 0; i < n_slots; ++i) {
+        const int as = (int)(i & 1);
+        mbar_wait(&a_fwd[as], (uint32_t)(i >> 1) & 1);
+        mbar_arrive_cluster(mapa_u32(smem_u32(&a_full[as]), 0));
       }
     }
   } else if (warp >= 4 && warp < 8) {
     const int q = warp - 4;
-    const int row = q * 32 + lane;
     const int et = threadIdx.x - 128;
+    const int unit = lane & 7, rsub = lane >> 3;
+    const uint32_t est = smem_u32(sEpi) + q * 4096;      // this warp's 4 KB transpose buffer
+    const int cpg_log2 = 31 - __clz(p.Cout / 32);
+    int roff[8];                                          // element offset of transposed step i from the tile's first pixel (tile-invariant)
+    uint32_t ld_off[8];                                   // swizzled shared-memory offset of that step's 16-byte unit
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      roff[i] = ((i >> 1) * p.W + 4 * (i & 1)) * p.Cout;
+      const int rrow = 4 * i + rsub;
+      ld_off[i] = rrow * 128 + ((unit ^ (rrow & 7)) * 16);
+    }
     const int cpg = p.Cout / 32;                        // channels per GroupNorm group (4, 8 or 16 here)
     uint32_t acc = 0, acc_phase = 0;
     int cur_n = -1;
@@ -300,9 +306,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1) conv_
       decode(t, n, th, tw, nt);
       if (p.gn_sums != nullptr && n != cur_n) { flush(cur_n); cur_n = n; }
       const int n0 = nt * CH_BN;
-      const int ow = tw * CH_TW + (row % CH_TW), oh = th * CH_TH + (row / CH_TW);
-      const bool row_ok = (ow < p.W) && (oh < p.H) && tile_valid(t);
-      const long long roff = (((long long)n * p.H + oh) * p.W + ow) * p.Cout + n0;
+      // Transposed domain: in step i (0..7) lane l handles tile row q*32 + 4*i + (l >> 3), columns 4*(l & 7) .. +3 of the 32-column chunk,
+      // i.e. output pixel (oh0 + i/2, ow0 + 4*(i & 1)): every global load / store of the warp moves four complete 128-byte lines.
+      const int ow0 = tw * CH_TW + rsub, oh0 = th * CH_TH + q * 4;
+      uint32_t okm = 0;                                      // bit i: step i lies inside the image (and the tile is not the odd-tail duplicate)
+      if (tile_valid(t)) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) okm |= ((oh0 + (i >> 1) < p.H) && (ow0 + 4 * (i & 1) < p.W)) ? (1u << i) : 0u;
+      }
+      const long long obase = (((long long)n * p.H + oh0) * p.W + ow0) * p.Cout + n0 + unit * 4;
+      if (p.residual != nullptr && t + 1 < t_end) {          // pull the NEXT tile's residual rows into L2 while this tile is processed
+        int n2, th2, tw2, nt2;
+        decode(t + 1, n2, th2, tw2, nt2);
+        const int pr = q * 32 + lane, pw_ = tw2 * CH_TW + (pr % CH_TW), ph_ = th2 * CH_TH + (pr / CH_TW);
+        if (pw_ < p.W && ph_ < p.H) {
+          const float* pp = p.residual + (((long long)n2 * p.H + ph_) * p.W + pw_) * p.Cout + nt2 * CH_BN;
+#pragma unroll
+          for (int j = 0; j < CH_BN / 32; ++j)
+            if (nt2 * CH_BN + j * 32 < p.Cout) asm volatile("prefetch.global.L2 [%0];" ::"l"(pp + j * 32));
+        }
+      }
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ((NPASS == 2) ? 2 * CH_BN : CH_BN);
@@ -328,35 +351,49 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1) conv_
         }
         const int col0 = n0 + c;
         if (col0 >= p.Cout || (p.dbg & 4)) continue;    // warp-uniform
-        float v[32];
-        {
-          const float4* bp = reinterpret_cast<const float4*>(p.bias + col0);      // col0 % 32 == 0: 16-byte aligned, warp-uniform
+        // residual rows of the transposed domain: issued before the transpose so their latency overlaps it
+        const float* rptr = p.residual + obase + c;
+        float* optr = p.out + obase + c;
+        float4 rres[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 b4 = __ldg(bp + j);
-            v[4 * j] = __uint_as_float(r[4 * j]) + b4.x; v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b4.y;
-            v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b4.z; v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b4.w;
+        for (int i = 0; i < 8; ++i) {
+          rres[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.residual != nullptr) rres[i] = *reinterpret_cast<const float4*>(((okm >> i) & 1) ? rptr + roff[i] : p.residual);
+        }
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + unit * 4));
+        // thread = row  ->  shared (16-byte units XOR-swizzled by row: conflict-free both ways)  ->  thread = (row quad, 4-column unit)
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(est + lane * 128 + ((u ^ (lane & 7)) * 16)), "r"(r[4 * u]),
+                       "r"(r[4 * u + 1]), "r"(r[4 * u + 2]), "r"(r[4 * u + 3]) : "memory");
+        __syncwarp();
+        float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;          // (sum, sumsq) of channels {0,1} and {2,3} of this lane's unit
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float4 x;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(est + ld_off[i]));
+          if ((okm >> i) & 1) {
+            x.x += b4.x + rres[i].x; x.y += b4.y + rres[i].y; x.z += b4.z + rres[i].z; x.w += b4.w + rres[i].w;
+            *reinterpret_cast<float4*>(optr + roff[i]) = x;
+            s0 += x.x + x.y; q0 = fmaf(x.x, x.x, fmaf(x.y, x.y, q0));
+            s1 += x.z + x.w; q1 = fmaf(x.z, x.z, fmaf(x.w, x.w, q1));
           }
         }
-        if (row_ok) {
-          if (p.residual != nullptr) {
-            const float4* rp = reinterpret_cast<const float4*>(p.residual + roff + c);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 rv = rp[j];
-              v[4 * j] += rv.x; v[4 * j + 1] += rv.y; v[4 * j + 2] += rv.z; v[4 * j + 3] += rv.w;
-            }
-          }
-          float4* op = reinterpret_cast<float4*>(p.out + roff + c);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        }
+        __syncwarp();
         if (p.gn_sums != nullptr) {
-          switch (cpg) {
-            case 4: gn_accumulate<4>(v, row_ok, lane, col0, gscr + q * 16 * 33, gsm + q * 64); break;
-            case 8: gn_accumulate<8>(v, row_ok, lane, col0, gscr + q * 16 * 33, gsm + q * 64); break;
-            case 16: gn_accumulate<16>(v, row_ok, lane, col0, gscr + q * 16 * 33, gsm + q * 64); break;
-            default: gn_accumulate<32>(v, row_ok, lane, col0, gscr + q * 16 * 33, gsm + q * 64); break;
+          // cpg >= 4: a 4-column unit lies inside one group.  Reduce over the 4 row-quads (lanes xor 8, 16), then over the units of a group.
+          s0 += s1; q0 += q1;
+          s0 += __shfl_xor_sync(0xffffffffu, s0, 8);  q0 += __shfl_xor_sync(0xffffffffu, q0, 8);
+          s0 += __shfl_xor_sync(0xffffffffu, s0, 16); q0 += __shfl_xor_sync(0xffffffffu, q0, 16);
+          const int upg = cpg >> 2;                            // units per group: 1, 2, 4 or 8
+          for (int w = 1; w < upg; w <<= 1) {
+            s0 += __shfl_xor_sync(0xffffffffu, s0, w);
+            q0 += __shfl_xor_sync(0xffffffffu, q0, w);
+          }
+          if (lane < 8 && (lane & (upg - 1)) == 0) {
+            double* wacc = gsm + q * 64 + ((col0 >> cpg_log2) + (lane >> (cpg_log2 - 2))) * 2;      // single owner lane per slot: no atomics
+            wacc[0] += (double)s0;
+            wacc[1] += (double)q0;
           }
         }
       }
@@ -365,85 +402,93 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1) conv_
     if (p.gn_sums != nullptr) flush(cur_n);
   }
   else if (warp >= 8) {
-    // ===================== operand producers: global fp32 -> affine (+swish) -> bf16 hi/lo -> halo in shared memory =====================
-    // Every thread owns items (8-channel chunk, halo pixel) j*256 + pt of each (tile, channel chunk): 1440 items = 6 per thread, pixel
-    // fastest (conflict-free 16-byte shared stores).  The raw 32 bytes of an item are fetched with cp.async into a PRIVATE 3-deep ring
-    // of staging slots, 3 items ahead of the one being transformed (across tile / chunk boundaries), so global latency is hidden without
-    // holding the data in registers.
+    // ===================== operand producers: global fp32 -> affine (+swish) -> split -> halo layout in shared memory =====================
+    // Producer warp pw owns the 8-channel chunk pw of every 64-channel slice; lane l owns halo pixels l + 32*jj (jj < 6, 180 pixels), so
+    // all item geometry (halo row / column, shared-memory offsets) is tile-invariant and lives in registers, and the GroupNorm affine of
+    // the warp's 8 channels is fetched once per (tile, slice).  The raw 32 bytes of an item are fetched with cp.async into a PRIVATE
+    // 3-deep ring of staging slots, 3 items ahead of the one being transformed (across slice / tile boundaries): slot = jj % 3.
+    const int pw = warp - 8;
     const int pt = threadIdx.x - 256;                    // 0..255
     const int Hs = p.up2 ? p.H / 2 : p.H, Ws = p.up2 ? p.W / 2 : p.W;      // source geometry
-    constexpr int DEPTH = 3, IPT = 6;                     // ring depth, items per thread per (tile, kc)
-    uint8_t* stg = sStage + pt * 16;                      // slot s, half h at stg + (s*2 + h) * 256*16
+    const int ush = p.up2 ? 1 : 0;
+    constexpr int IPT = 6;                                // items per thread per (tile, slice); ring depth 3 = IPT / 2
+    const uint32_t stg = smem_u32(sStage) + pt * 16;      // slot s, half h at stg + (s*2 + h) * 256*16
+    int hy[IPT], hx[IPT];                                 // halo row / column of item jj
+#pragma unroll
+    for (int jj = 0; jj < IPT; ++jj) { const int hp = lane + 32 * jj; hy[jj] = hp / CH_HW; hx[jj] = hp % CH_HW; }
+    const bool last_ok = lane < CH_HPIX - 32 * (IPT - 1);         // item 5 exists for lanes < 20
+    const uint32_t item_off = pw * CH_CHUNK_STRIDE + lane * 16;   // + jj*512: this thread's 16-byte cell in a 2-byte plane
+    const uint32_t item_off8 = (pw >> 1) * CH_CHUNK_STRIDE + lane * 16 + (pw & 1) * 8;   // 8-byte cell in a 1-byte plane
+    const float* xw = p.x + pw * 8;
 
-    // fetch cursor (runs DEPTH items ahead of the transform cursor); advanced incrementally, no divisions by runtime values
-    long long f_t = t_begin;
-    int f_kc = 0, f_j = 0, f_slot = 0, f_n = 0, f_th = 0, f_tw = 0, f_nt = 0;
-    if (t_begin < t_end) decode(f_t, f_n, f_th, f_tw, f_nt);
-    auto fetch = [&]() {
-      if (f_t < t_end) {
-        const int i = pt + 256 * f_j;
-        if (i < 8 * CH_HPIX) {
-          const int chunk = i / CH_HPIX, px = i % CH_HPIX;
-          const int gh = f_th * CH_TH - 1 + px / CH_HW, gw = f_tw * CH_TW - 1 + px % CH_HW;
-          if (gh >= 0 && gh < p.H && gw >= 0 && gw < p.W && !(p.dbg & 1)) {
-            const int sh = p.up2 ? gh >> 1 : gh, sw_ = p.up2 ? gw >> 1 : gw;
-            const float* src = p.x + (((size_t)f_n * Hs + sh) * Ws + sw_) * p.Cin + f_kc * 64 + chunk * 8;
-            const uint32_t d0 = smem_u32(stg + (f_slot * 2) * 256 * 16);
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0), "l"(src) : "memory");
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + 256 * 16), "l"(src + 4) : "memory");
-          }
-        }
-        if (++f_j == IPT) {
-          f_j = 0;
-          if (++f_kc == KC) {
-            f_kc = 0;
-            if (++f_t < t_end) decode(f_t, f_n, f_th, f_tw, f_nt);
-          }
+    // issue the fetch of item jj of slice (n_, th_, tw_, kc_) into staging slot jj % 3 (one commit group per item, possibly empty)
+    auto fetch = [&](int jj, bool live, int n_, int th_, int tw_, int kc_) {
+      if (live && (jj < IPT - 1 || last_ok) && !(p.dbg & 1)) {
+        const int gh = th_ * CH_TH - 1 + hy[jj], gw = tw_ * CH_TW - 1 + hx[jj];
+        if ((unsigned)gh < (unsigned)p.H && (unsigned)gw < (unsigned)p.W) {
+          const float* src = xw + ((size_t)n_ * Hs * Ws + (size_t)((gh >> ush) * Ws + (gw >> ush))) * p.Cin + kc_ * 64;
+          const uint32_t d0 = stg + ((jj % 3) * 2) * 256 * 16;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0), "l"(src) : "memory");
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + 256 * 16), "l"(src + 4) : "memory");
         }
       }
-      if (++f_slot == DEPTH) f_slot = 0;
-      asm volatile("cp.async.commit_group;" ::: "memory");      // one group per item (possibly empty) keeps the wait arithmetic uniform
+      asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
-    for (int g = 0; g < DEPTH; ++g) fetch();
-    int c_slot = 0;                                       // transform cursor's staging slot
+    int n = 0, th = 0, tw = 0, nt = 0;
+    if (t_begin < t_end) decode(t_begin, n, th, tw, nt);
+#pragma unroll
+    for (int jj = 0; jj < 3; ++jj) fetch(jj, t_begin < t_end, n, th, tw, 0);
     uint32_t ai = 0;
     for (long long t = t_begin; t < t_end; ++t) {
-      int n, th, tw, nt;
-      decode(t, n, th, tw, nt);
+      int n2 = n, th2 = th, tw2 = tw, nt2 = nt;            // next tile (prefetch target of the last slice)
+      const bool more = t + 1 < t_end;
+      if (more) decode(t + 1, n2, th2, tw2, nt2);
       for (int kc = 0; kc < KC; ++kc, ++ai) {
         const int as = ai & 1;
-        mbar_wait(&a_empty[as], ((ai >> 1) & 1) ^ 1);
-        uint8_t* dst = sA + as * Cfg::A_SLOT_PAD;
-#pragma unroll 1
-        for (int jj = 0; jj < IPT; ++jj) {
-          asm volatile("cp.async.wait_group %0;" ::"n"(DEPTH - 1) : "memory");     // item g has landed
-          const int i = pt + 256 * jj;
-          if (i < 8 * CH_HPIX && !(p.dbg & 2)) {
-            const int chunk = i / CH_HPIX, px = i % CH_HPIX;
-            const int gh = th * CH_TH - 1 + px / CH_HW, gw = tw * CH_TW - 1 + px % CH_HW;
-            const int off = chunk * CH_CHUNK_STRIDE + px * 16;
-            float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            if (gh >= 0 && gh < p.H && gw >= 0 && gw < p.W) {        // zero padding applies AFTER the transform
-              const uint8_t* sp = stg + (c_slot * 2) * 256 * 16;
-              const float4 a = *reinterpret_cast<const float4*>(sp), b = *reinterpret_cast<const float4*>(sp + 256 * 16);
-              f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
-              if (p.affine != nullptr) {
-                const float4* ap = reinterpret_cast<const float4*>(p.affine + ((size_t)n * p.Cin + kc * 64 + chunk * 8) * 2);
+        const bool last_kc = (kc + 1 == KC);
+        const bool nx_live = !last_kc || more;
+        const int nx_n = last_kc ? n2 : n, nx_th = last_kc ? th2 : th, nx_tw = last_kc ? tw2 : tw, nx_kc = last_kc ? 0 : kc + 1;
+        // GroupNorm affine (scale, shift) of this warp's 8 channels: one fetch per slice, consumed by 6 items
+        float sc[8], sf[8];
+        if (p.affine != nullptr) {
+          const float4* ap = reinterpret_cast<const float4*>(p.affine + ((size_t)n * p.Cin + kc * 64 + pw * 8) * 2);
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float4 sc = __ldg(ap + e);             // (scale, shift) x 2 channels
-                  f[2 * e] = fmaf(f[2 * e], sc.x, sc.y);
-                  f[2 * e + 1] = fmaf(f[2 * e + 1], sc.z, sc.w);
-                }
-              }
+          for (int e = 0; e < 4; ++e) {
+            const float4 q4 = __ldg(ap + e);
+            sc[2 * e] = q4.x; sf[2 * e] = q4.y; sc[2 * e + 1] = q4.z; sf[2 * e + 1] = q4.w;
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) { sc[e] = 1.f; sf[e] = 0.f; }
+        }
+        mbar_wait(&a_empty[as], ((ai >> 1) & 1) ^ 1);
+        const uint32_t dst = smem_u32(sA + as * Cfg::A_SLOT_PAD);
+#pragma unroll
+        for (int jj = 0; jj < IPT; ++jj) {
+          asm volatile("cp.async.wait_group 2;" ::: "memory");          // item jj has landed
+          if ((jj < IPT - 1 || last_ok) && !(p.dbg & 2)) {
+            const int gh = th * CH_TH - 1 + hy[jj], gw = tw * CH_TW - 1 + hx[jj];
+            float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if ((unsigned)gh < (unsigned)p.H && (unsigned)gw < (unsigned)p.W) {        // zero padding applies AFTER the transform
+              const uint32_t sp = stg + ((jj % 3) * 2) * 256 * 16;
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(f[0]), "=f"(f[1]), "=f"(f[2]), "=f"(f[3]) : "r"(sp));
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(f[4]), "=f"(f[5]), "=f"(f[6]), "=f"(f[7]) : "r"(sp + 256 * 16));
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = fmaf(f[e], sc[e], sf[e]);
               if (p.swish) {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) f[e] = __fdividef(f[e], 1.0f + __expf(-f[e]));     // swish, fast intrinsics (~1e-6 rel.)
+                for (int e = 0; e < 8; ++e) {                   // x * sigmoid(x) = x / (1 + 2^(-x log2 e)), approx ex2 / rcp (~1e-7 rel.)
+                  float ex, rc;
+                  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(f[e] * -1.4426950408889634f));
+                  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(1.0f + ex));
+                  f[e] *= rc;
+                }
               }
             }
+            const uint32_t o16 = dst + item_off + jj * 512;
             if (NPASS == 2) {
-              // fp16 plane + two e4m3 planes: lo8 = (x - fp16(x)) * 2^13 and x8 = x * 4 (satfinite: out-of-range values degrade gracefully)
+              // fp16 plane + two e4m3 planes: lo8 = (x - fp16(x)) * 2^13 and x8 = x (satfinite: out-of-range values degrade gracefully)
               uint32_t h16[4];
               uint32_t l8[2] = {0u, 0u}, x8[2] = {0u, 0u};
 #pragma unroll
@@ -452,38 +497,41 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1) conv_
                 h16[e] = *reinterpret_cast<const uint32_t*>(&h2);
                 const float2 hf = __half22float2(h2);
                 const uint32_t lo2 = __nv_cvt_float2_to_fp8x2(make_float2((f[2 * e] - hf.x) * 8192.0f, (f[2 * e + 1] - hf.y) * 8192.0f), __NV_SATFINITE, __NV_E4M3);
-                const uint32_t xx2 = __nv_cvt_float2_to_fp8x2(make_float2(f[2 * e] * 4.0f, f[2 * e + 1] * 4.0f), __NV_SATFINITE, __NV_E4M3);
+                const uint32_t xx2 = __nv_cvt_float2_to_fp8x2(make_float2(f[2 * e], f[2 * e + 1]), __NV_SATFINITE, __NV_E4M3);
                 l8[e >> 1] |= lo2 << (16 * (e & 1));
                 x8[e >> 1] |= xx2 << (16 * (e & 1));
               }
-              *reinterpret_cast<uint4*>(dst + off) = make_uint4(h16[0], h16[1], h16[2], h16[3]);
-              const int off8 = (chunk >> 1) * CH_CHUNK_STRIDE + px * 16 + (chunk & 1) * 8;      // 16-channel chunks of 1-byte elements
-              *reinterpret_cast<uint2*>(dst + CH_A_PLANE + off8) = make_uint2(l8[0], l8[1]);
-              *reinterpret_cast<uint2*>(dst + CH_A_PLANE + CH_A_PLANE / 2 + off8) = make_uint2(x8[0], x8[1]);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(o16), "r"(h16[0]), "r"(h16[1]), "r"(h16[2]), "r"(h16[3]) : "memory");
+              const uint32_t o8 = dst + CH_A_PLANE + item_off8 + jj * 512;      // 16-channel chunks of 1-byte elements
+              asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(o8), "r"(l8[0]), "r"(l8[1]) : "memory");
+              asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(o8 + CH_A_PLANE / 2), "r"(x8[0]), "r"(x8[1]) : "memory");
             } else {
-            uint32_t hh[4], ll[4];
+              uint32_t hh[4], ll[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              __nv_bfloat16 h0, l0, h1, l1;
-              split_bf16(f[2 * e], h0, l0);
-              split_bf16(f[2 * e + 1], h1, l1);
-              hh[e] = pack_bf16(h0, h1);
-              ll[e] = pack_bf16(l0, l1);
-            }
-            *reinterpret_cast<uint4*>(dst + off) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
-            if (NPASS == 3) *reinterpret_cast<uint4*>(dst + CH_A_PLANE + off) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+              for (int e = 0; e < 4; ++e) {
+                __nv_bfloat16 h0, l0, h1, l1;
+                split_bf16(f[2 * e], h0, l0);
+                split_bf16(f[2 * e + 1], h1, l1);
+                hh[e] = pack_bf16(h0, h1);
+                ll[e] = pack_bf16(l0, l1);
+              }
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(o16), "r"(hh[0]), "r"(hh[1]), "r"(hh[2]), "r"(hh[3]) : "memory");
+              if (NPASS == 3)
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(o16 + CH_A_PLANE), "r"(ll[0]), "r"(ll[1]), "r"(ll[2]), "r"(ll[3]) : "memory");
             }
           }
-          if (++c_slot == DEPTH) c_slot = 0;
-          fetch();                          // refill the slot just consumed
+          // refill the slot just consumed with the item 3 ahead: same slice for jj < 3, next slice (possibly of the next tile) otherwise
+          if (jj < 3) fetch(jj + 3, true, n, th, tw, kc);
+          else fetch(jj - 3, nx_live, nx_n, nx_th, nx_tw, nx_kc);
         }
         fence_proxy_async();            // generic-proxy stores -> visible to the tensor core (async proxy)
         __syncwarp();
-        if (lane == 0) {                                     // operand slot filled: tell the leader's MMA thread
-          if (leader) mbar_arrive(&a_full[as]);
-          else mbar_arrive_cluster(mapa_u32(smem_u32(&a_full[as]), 0));
+        if (lane == 0) {                                     // operand slot filled
+          if (leader) mbar_arrive(&a_full[as]);              // straight to the MMA thread's barrier
+          else mbar_arrive(&a_fwd[as]);                      // peer CTA: a local barrier, forwarded across the cluster by warp 3
         }
       }
+      n = n2; th = th2; tw = tw2; nt = nt2;
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
   }

@@ -101,11 +101,11 @@ BEVGEN_API int bevgen_conv3x3_fused(const float* x, int n, int h, int w, int cin
                                     const void* w_lo, int w_rows, int cout, const float* bias, const float* residual, float* out, double* gn_sums,
                                     int npass, void* stream);
 /* Same convolution (cta_group::2 kernel) with the fp32-equivalent product formed as ONE fp16 MMA plus TWO e4m3 MMAs (which run at twice
- * the fp16 rate) instead of three bf16 MMAs:   x*w ~= x16*w16 + [ e4m3((x - x16) * 2^13) * e4m3(w * S)  +  e4m3(x * 4) * e4m3((w - w16) * S * 2^11) ] * lo_scale,
+ * the fp16 rate) instead of three bf16 MMAs:   x*w ~= x16*w16 + [ e4m3((x - x16) * 2^13) * e4m3(w * S)  +  e4m3(x) * e4m3((w - w16) * S * 2^13) ] * lo_scale,
  * lo_scale = 1 / (2^13 * S).  The correction sum has its own TMEM accumulator and is folded in by the epilogue; out-of-range values saturate
  * (the affected element degrades to fp16 accuracy instead of overflowing).  Max error ~2^-15 relative per product (bf16x3: ~2^-17).
  *   w_f16    [tap][cout][cin] fp16, rows padded like bevgen_conv3x3_fused
- *   w_f8pair same rows, 2*cin bytes per row: per 64-channel chunk 64 bytes e4m3(w * S) followed by 64 bytes e4m3((w - w16) * S * 2^11)   */
+ *   w_f8pair same rows, 2*cin bytes per row: per 64-channel chunk 64 bytes e4m3(w * S) followed by 64 bytes e4m3((w - w16) * S * 2^13)   */
 BEVGEN_API int bevgen_conv3x3_fused_f16f8(const float* x, int n, int h, int w, int cin, const float* affine, int swish, int up2, const void* w_f16,
                                           const void* w_f8pair, int w_rows, int cout, float lo_scale, const float* bias, const float* residual,
                                           float* out, double* gn_sums, void* stream);

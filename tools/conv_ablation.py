@@ -32,9 +32,9 @@ def t(label, npass=3, two_cta=True, dbg=0, **kw):
     torch.cuda.synchronize()
     a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
-    for _ in range(5): f()
+    for _ in range(10): f()
     e.record(); torch.cuda.synchronize()
-    ms = a.elapsed_time(e) / 5
+    ms = a.elapsed_time(e) / 10
     print(f"{label:44s} {ms:7.3f} ms  {flops / ms / 1e9:7.1f} TFLOP/s algorithmic")
 
 t("full (affine+swish, residual, stats) 2cta")
