@@ -65,7 +65,7 @@ SIGNATURES = {
     "bevgen_gemm_tc": (_i, [C.POINTER(GemmArgs), _vp]),
     "bevgen_conv3x3_halo": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _i, _vp]),
     "bevgen_conv3x3_fused": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _i, _vp]),
-    "bevgen_conv3x3_fused_f16f8": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp, _i, _i, _f, _vp, _vp, _vp, _vp, _vp]),
+    "bevgen_conv3x3_fused_f16f8": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp, _i, _i, _f, _vp, _vp, _vp, _vp, _i, _vp]),
     "bevgen_groupnorm_affine": (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp]),
     "bevgen_groupnorm_finalize": (_i, [_vp, _i, _i, _i, _f, _vp, _vp]),
     "bevgen_groupnorm_stats": (_i, [_vp, _i, _i, _i, _f, _vp, _vp, _vp]),

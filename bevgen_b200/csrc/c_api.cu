@@ -36,7 +36,7 @@ int ensure_init() {
 
 // bf16 tensor map (SWIZZLE_128B unless swizzle == false); dims/strides innermost first
 int make_tmap(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
-              bool swizzle = true) {
+              bool swizzle = true, bool swizzle64 = false) {
   cuuint64_t gd[5], gs[4];
   cuuint32_t bx[5], es[5];
   for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
@@ -45,7 +45,8 @@ int make_tmap(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, 
   for (int i = 0; i + 1 < rank; ++i)
     if (gs[i] % 16 != 0) return fail(BEVGEN_ERR_ARG, "tensor map stride %d (%llu B) not a multiple of 16", i, (unsigned long long)gs[i]);
   CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        swizzle64 ? CU_TENSOR_MAP_SWIZZLE_64B : (swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE),
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(BEVGEN_ERR_DRIVER, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d)", (int)r, rank);
@@ -186,10 +187,13 @@ static int conv3x3_fused_impl(const float* x, int n, int h, int w, int cin, cons
   int rc = ensure_init();
   if (rc) return rc;
   const bool two_cta = (npass & 0x100) != 0;      // bit 8 of npass selects the cta_group::2 (cluster of two CTAs) kernel
+  const bool block16 = (npass & 0x200) != 0;      // bit 9: weight-stationary 16x16-block kernel (conv_fused3.cu), 32-channel weight boxes
   npass &= 0xff;
   if (!x || !w_hi || !bias || !out || (npass >= 2 && !w_lo) || !(npass >= 1 && npass <= 3)) return fail(BEVGEN_ERR_ARG, "conv3x3_fused: bad args");
-  if (npass == 2 && (!two_cta || !(lo_scale > 0.f))) return fail(BEVGEN_ERR_ARG, "conv3x3_fused: the f16+f8 mode exists for the 2-CTA kernel only and needs lo_scale > 0");
-  if (cin % 64 != 0 || cout % 32 != 0 || n < 1 || h < 1 || w < 1) return fail(BEVGEN_ERR_ARG, "conv3x3_fused: cin %% 64 / cout %% 32 required (cin=%d cout=%d)", cin, cout);
+  if (npass == 2 && ((!two_cta && !block16) || !(lo_scale > 0.f))) return fail(BEVGEN_ERR_ARG, "conv3x3_fused: the f16+f8 mode exists for the 2-CTA kernels only and needs lo_scale > 0");
+  if (block16 && cin % 32 != 0) return fail(BEVGEN_ERR_ARG, "conv3x3_fused: the block kernel needs cin %% 32 == 0");
+  if (!block16 && cin % 64 != 0) return fail(BEVGEN_ERR_ARG, "conv3x3_fused: cin %% 64 required (cin=%d)", cin);
+  if (cin % 32 != 0 || cout % 32 != 0 || n < 1 || h < 1 || w < 1) return fail(BEVGEN_ERR_ARG, "conv3x3_fused: cin %% 32 / cout %% 32 required (cin=%d cout=%d)", cin, cout);
   if (w_rows < 8 * cout + ((cout + 127) / 128) * 128) return fail(BEVGEN_ERR_ARG, "conv3x3_fused: weight rows must be padded to 8*cout + ceil128(cout)");
   if (((uintptr_t)x & 15) != 0 || (affine && ((uintptr_t)affine & 15) != 0)) return fail(BEVGEN_ERR_ARG, "conv3x3_fused: x / affine must be 16-byte aligned");
   ConvFusedParams p;
@@ -198,8 +202,8 @@ static int conv3x3_fused_impl(const float* x, int n, int h, int w, int cin, cons
   for (int o = 0; o < (npass >= 2 ? 2 : 1); ++o) {      // npass == 2: plane 1 is the packed e4m3 pair, also 2*cin bytes per row
     uint64_t wd[2] = {(uint64_t)cin, (uint64_t)w_rows};
     uint64_t wst[1] = {(uint64_t)cin * 2};
-    uint32_t wb[2] = {64, (uint32_t)(two_cta ? 64 : 128)};
-    rc = make_tmap(&p.tmW[o], wp[o], 2, wd, wst, wb, true);
+    uint32_t wb[2] = {(uint32_t)(block16 ? 32 : 64), (uint32_t)((two_cta || block16) ? 64 : 128)};
+    rc = make_tmap(&p.tmW[o], wp[o], 2, wd, wst, wb, true, block16);
     if (rc) return rc;
   }
   p.x = x; p.affine = affine; p.swish = swish; p.up2 = up2;
@@ -208,6 +212,10 @@ static int conv3x3_fused_impl(const float* x, int n, int h, int w, int cin, cons
   { const char* e = getenv("BEVGEN_CONV_DBG"); p.dbg = e ? atoi(e) : 0; }
   if (gn_sums != nullptr && cudaMemsetAsync(gn_sums, 0, (size_t)n * 64 * sizeof(double), (cudaStream_t)stream) != cudaSuccess)
     return fail(BEVGEN_ERR_CUDA, "conv3x3_fused: memset failed");
+  if (block16) {
+    if (npass != 2) p.lo_scale = 1.0f;            // the block kernel applies lo_scale to the whole accumulator
+    CHECK_LAUNCH(launch_conv_fused3(p, npass, g_sm_count, (cudaStream_t)stream), "conv3x3_fused (16x16 block)");
+  }
   if (two_cta) CHECK_LAUNCH(launch_conv_fused2(p, npass, g_sm_count, (cudaStream_t)stream), "conv3x3_fused (2-CTA)");
   CHECK_LAUNCH(launch_conv_fused(p, npass, g_sm_count, (cudaStream_t)stream), "conv3x3_fused");
 }
@@ -221,9 +229,9 @@ BEVGEN_API int bevgen_conv3x3_fused(const float* x, int n, int h, int w, int cin
 
 BEVGEN_API int bevgen_conv3x3_fused_f16f8(const float* x, int n, int h, int w, int cin, const float* affine, int swish, int up2, const void* w_f16,
                                           const void* w_f8pair, int w_rows, int cout, float lo_scale, const float* bias, const float* residual,
-                                          float* out, double* gn_sums, void* stream) {
-  return conv3x3_fused_impl(x, n, h, w, cin, affine, swish, up2, w_f16, w_f8pair, w_rows, cout, bias, residual, out, gn_sums, 2 | 0x100, lo_scale,
-                            stream);
+                                          float* out, double* gn_sums, int block16, void* stream) {
+  return conv3x3_fused_impl(x, n, h, w, cin, affine, swish, up2, w_f16, w_f8pair, w_rows, cout, bias, residual, out, gn_sums,
+                            2 | (block16 ? 0x200 : 0x100), lo_scale, stream);
 }
 
 BEVGEN_API int bevgen_groupnorm_affine(const double* sums, const float* gamma, const float* beta, int n, int pixels, int c, float eps, float* affine,

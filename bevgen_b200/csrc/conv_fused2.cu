@@ -183,7 +183,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1) conv_
   };
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (lane == 0 && !(p.dbg & 16)) {
       uint32_t wi = 0;
       for (long long t = t_begin; t < t_end; ++t) {
         int n, th, tw, nt;
@@ -227,7 +227,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1) conv_
           const uint64_t a_slot = adesc0 + (uint64_t)(as * (Cfg::A_SLOT_PAD >> 4));
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
-            mbar_wait(&w_full[ws], wphase);
+            if (!(p.dbg & 16)) mbar_wait(&w_full[ws], wphase);
             tc_fence_after();
             const uint64_t at = a_slot + (uint64_t)((tap / 3) * CH_HW + (tap % 3));     // shifted window inside the halo (16-byte units)
             const uint64_t bt = bdesc0 + (uint64_t)(ws * (Cfg::W_STAGE >> 4));
@@ -403,33 +403,58 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1) conv_
   }
   else if (warp >= 8) {
     // ===================== operand producers: global fp32 -> affine (+swish) -> split -> halo layout in shared memory =====================
-    // Producer warp pw owns the 8-channel chunk pw of every 64-channel slice; lane l owns halo pixels l + 32*jj (jj < 6, 180 pixels), so
-    // all item geometry (halo row / column, shared-memory offsets) is tile-invariant and lives in registers, and the GroupNorm affine of
-    // the warp's 8 channels is fetched once per (tile, slice).  The raw 32 bytes of an item are fetched with cp.async into a PRIVATE
-    // 3-deep ring of staging slots, 3 items ahead of the one being transformed (across slice / tile boundaries): slot = jj % 3.
+    // Producer warp pw owns channel group g = pw & 1 (32 channels = ONE 128-byte line per pixel) of every 64-channel slice and the halo
+    // pixel block pb = pw >> 1 (45 of the 180 halo pixels), processed in 6 rounds of 8 pixels.
+    //   fetch:   two cp.async per lane and round; instruction s covers pixels 4s .. 4s+3 of the round with lane -> (pixel l >> 3, 16-byte
+    //            piece l & 7): every instruction moves four COMPLETE 128-byte lines (the previous lane = pixel mapping asked L2 for 32
+    //            half-used sectors per instruction and capped the kernel's DRAM stream at ~3 TB/s, profiles/r01 ablation);
+    //   consume: lane -> (8-channel chunk l >> 3, pixel l & 7) reads its 32 bytes back from the warp's staging slot (pieces XOR-swizzled by
+    //            pixel: conflict-free), so consecutive lanes write consecutive pixels of one chunk plane (conflict-free 16-byte stores).
+    // Lanes exchange data through the slot, hence the __syncwarp()s around the staging reads.  All geometry is tile-invariant and lives
+    // in registers; the GroupNorm affine of a lane's 8 channels is fetched once per (tile, slice); the staging ring is 3 rounds deep and
+    // runs across slice / tile boundaries (slot = round % 3).
     const int pw = warp - 8;
-    const int pt = threadIdx.x - 256;                    // 0..255
+    const int g = pw & 1, pb = pw >> 1;
+    constexpr int PBLK = CH_HPIX / 4;                     // 45 halo pixels per block
     const int Hs = p.up2 ? p.H / 2 : p.H, Ws = p.up2 ? p.W / 2 : p.W;      // source geometry
     const int ush = p.up2 ? 1 : 0;
-    constexpr int IPT = 6;                                // items per thread per (tile, slice); ring depth 3 = IPT / 2
-    const uint32_t stg = smem_u32(sStage) + pt * 16;      // slot s, half h at stg + (s*2 + h) * 256*16
-    int hy[IPT], hx[IPT];                                 // halo row / column of item jj
+    constexpr int IPT = 6;                                // rounds per (tile, slice); ring depth 3 = IPT / 2
+    const uint32_t stg = smem_u32(sStage) + pw * 3072;    // this warp's 3 slots of 1 KB: [8 pixels][8 pieces ^ pixel][16 B]
+    // fetch geometry: (halo row | halo column << 8) of the pixel this lane fetches in round jj, instruction s; -1 = beyond the block
+    int fgeo[IPT][2], cgeo[IPT];
+    uint32_t coff[IPT];                                   // consume side: halo pixel index * 16
 #pragma unroll
-    for (int jj = 0; jj < IPT; ++jj) { const int hp = lane + 32 * jj; hy[jj] = hp / CH_HW; hx[jj] = hp % CH_HW; }
-    const bool last_ok = lane < CH_HPIX - 32 * (IPT - 1);         // item 5 exists for lanes < 20
-    const uint32_t item_off = pw * CH_CHUNK_STRIDE + lane * 16;   // + jj*512: this thread's 16-byte cell in a 2-byte plane
-    const uint32_t item_off8 = (pw >> 1) * CH_CHUNK_STRIDE + lane * 16 + (pw & 1) * 8;   // 8-byte cell in a 1-byte plane
-    const float* xw = p.x + pw * 8;
+    for (int jj = 0; jj < IPT; ++jj) {
+#pragma unroll
+      for (int s2 = 0; s2 < 2; ++s2) {
+        const int pi = jj * 8 + s2 * 4 + (lane >> 3), hp = pb * PBLK + pi;
+        fgeo[jj][s2] = pi < PBLK ? ((hp / CH_HW) | ((hp % CH_HW) << 8)) : -1;
+      }
+      const int pi = jj * 8 + (lane & 7), hp = pb * PBLK + pi;
+      cgeo[jj] = pi < PBLK ? ((hp / CH_HW) | ((hp % CH_HW) << 8)) : -1;
+      coff[jj] = hp * 16;
+    }
+    const int cch = g * 4 + (lane >> 3);                  // 8-channel chunk (0..7) of the slice this lane transforms
+    const uint32_t f_dst0 = stg + (lane >> 3) * 128 + (((lane & 7) ^ (lane >> 3)) * 16);            // instruction 0: pixel l >> 3
+    const uint32_t f_dst1 = stg + (4 + (lane >> 3)) * 128 + (((lane & 7) ^ (4 + (lane >> 3))) * 16);  // instruction 1: pixel 4 + (l >> 3)
+    const uint32_t c_src0 = stg + (lane & 7) * 128 + (((2 * (lane >> 3)) ^ (lane & 7)) * 16);       // pieces 2c, 2c+1 of pixel l & 7
+    const uint32_t c_src1 = stg + (lane & 7) * 128 + (((2 * (lane >> 3) + 1) ^ (lane & 7)) * 16);
+    const uint32_t item_off = cch * CH_CHUNK_STRIDE;      // + coff: this lane's 16-byte cell in a 2-byte plane
+    const uint32_t item_off8 = (cch >> 1) * CH_CHUNK_STRIDE + (cch & 1) * 8;   // 8-byte cell in a 1-byte plane
+    const float* xw = p.x + g * 32 + (lane & 7) * 4;
 
-    // issue the fetch of item jj of slice (n_, th_, tw_, kc_) into staging slot jj % 3 (one commit group per item, possibly empty)
+    // issue the fetches of round jj of slice (n_, th_, tw_, kc_) into staging slot jj % 3 (one commit group per round, possibly empty)
     auto fetch = [&](int jj, bool live, int n_, int th_, int tw_, int kc_) {
-      if (live && (jj < IPT - 1 || last_ok) && !(p.dbg & 1)) {
-        const int gh = th_ * CH_TH - 1 + hy[jj], gw = tw_ * CH_TW - 1 + hx[jj];
-        if ((unsigned)gh < (unsigned)p.H && (unsigned)gw < (unsigned)p.W) {
-          const float* src = xw + ((size_t)n_ * Hs * Ws + (size_t)((gh >> ush) * Ws + (gw >> ush))) * p.Cin + kc_ * 64;
-          const uint32_t d0 = stg + ((jj % 3) * 2) * 256 * 16;
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0), "l"(src) : "memory");
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + 256 * 16), "l"(src + 4) : "memory");
+      if (live && !(p.dbg & 1)) {
+        const float* base = xw + (size_t)n_ * Hs * Ws * p.Cin + kc_ * 64;
+#pragma unroll
+        for (int s2 = 0; s2 < 2; ++s2) {
+          const int ge = fgeo[jj][s2];
+          const int gh = th_ * CH_TH - 1 + (ge & 0xff), gw = tw_ * CH_TW - 1 + (ge >> 8);
+          if (ge >= 0 && (unsigned)gh < (unsigned)p.H && (unsigned)gw < (unsigned)p.W) {
+            const float* src = base + (size_t)((gh >> ush) * Ws + (gw >> ush)) * p.Cin;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((s2 ? f_dst1 : f_dst0) + (jj % 3) * 1024), "l"(src) : "memory");
+          }
         }
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
@@ -449,10 +474,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1) conv_
         const bool last_kc = (kc + 1 == KC);
         const bool nx_live = !last_kc || more;
         const int nx_n = last_kc ? n2 : n, nx_th = last_kc ? th2 : th, nx_tw = last_kc ? tw2 : tw, nx_kc = last_kc ? 0 : kc + 1;
-        // GroupNorm affine (scale, shift) of this warp's 8 channels: one fetch per slice, consumed by 6 items
+        // GroupNorm affine (scale, shift) of this lane's 8 channels: one fetch per slice, consumed by 6 items
         float sc[8], sf[8];
         if (p.affine != nullptr) {
-          const float4* ap = reinterpret_cast<const float4*>(p.affine + ((size_t)n * p.Cin + kc * 64 + pw * 8) * 2);
+          const float4* ap = reinterpret_cast<const float4*>(p.affine + ((size_t)n * p.Cin + kc * 64 + cch * 8) * 2);
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const float4 q4 = __ldg(ap + e);
@@ -466,14 +491,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1) conv_
         const uint32_t dst = smem_u32(sA + as * Cfg::A_SLOT_PAD);
 #pragma unroll
         for (int jj = 0; jj < IPT; ++jj) {
-          asm volatile("cp.async.wait_group 2;" ::: "memory");          // item jj has landed
-          if ((jj < IPT - 1 || last_ok) && !(p.dbg & 2)) {
-            const int gh = th * CH_TH - 1 + hy[jj], gw = tw * CH_TW - 1 + hx[jj];
-            float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            if ((unsigned)gh < (unsigned)p.H && (unsigned)gw < (unsigned)p.W) {        // zero padding applies AFTER the transform
-              const uint32_t sp = stg + ((jj % 3) * 2) * 256 * 16;
-              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(f[0]), "=f"(f[1]), "=f"(f[2]), "=f"(f[3]) : "r"(sp));
-              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(f[4]), "=f"(f[5]), "=f"(f[6]), "=f"(f[7]) : "r"(sp + 256 * 16));
+          asm volatile("cp.async.wait_group 2;" ::: "memory");          // this lane's pieces of round jj have landed ...
+          __syncwarp();                                                  // ... and so have the other lanes'
+          const int ge = cgeo[jj];
+          float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          const int gh = th * CH_TH - 1 + (ge & 0xff), gw = tw * CH_TW - 1 + (ge >> 8);
+          const bool inside = ge >= 0 && (unsigned)gh < (unsigned)p.H && (unsigned)gw < (unsigned)p.W;
+          if (inside && !(p.dbg & 2)) {                                  // zero padding applies AFTER the transform
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(f[0]), "=f"(f[1]), "=f"(f[2]), "=f"(f[3]) : "r"(c_src0 + (jj % 3) * 1024));
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(f[4]), "=f"(f[5]), "=f"(f[6]), "=f"(f[7]) : "r"(c_src1 + (jj % 3) * 1024));
+          }
+          __syncwarp();                                                  // every lane has read the slot: it may be refilled
+          // refill the slot just consumed with the round 3 ahead: same slice for jj < 3, next slice (possibly of the next tile) otherwise
+          if (jj < 3) fetch(jj + 3, true, n, th, tw, kc);
+          else fetch(jj - 3, nx_live, nx_n, nx_th, nx_tw, nx_kc);
+          if (ge >= 0 && !(p.dbg & 2)) {
+            if (inside) {
 #pragma unroll
               for (int e = 0; e < 8; ++e) f[e] = fmaf(f[e], sc[e], sf[e]);
               if (p.swish) {
@@ -486,7 +519,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1) conv_
                 }
               }
             }
-            const uint32_t o16 = dst + item_off + jj * 512;
+            const uint32_t o16 = dst + item_off + coff[jj];
             if (NPASS == 2) {
               // fp16 plane + two e4m3 planes: lo8 = (x - fp16(x)) * 2^13 and x8 = x (satfinite: out-of-range values degrade gracefully)
               uint32_t h16[4];
@@ -502,7 +535,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1) conv_
                 x8[e >> 1] |= xx2 << (16 * (e & 1));
               }
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(o16), "r"(h16[0]), "r"(h16[1]), "r"(h16[2]), "r"(h16[3]) : "memory");
-              const uint32_t o8 = dst + CH_A_PLANE + item_off8 + jj * 512;      // 16-channel chunks of 1-byte elements
+              const uint32_t o8 = dst + CH_A_PLANE + item_off8 + coff[jj];      // 16-channel chunks of 1-byte elements
               asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(o8), "r"(l8[0]), "r"(l8[1]) : "memory");
               asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(o8 + CH_A_PLANE / 2), "r"(x8[0]), "r"(x8[1]) : "memory");
             } else {
@@ -520,9 +553,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1) conv_
                 asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(o16 + CH_A_PLANE), "r"(ll[0]), "r"(ll[1]), "r"(ll[2]), "r"(ll[3]) : "memory");
             }
           }
-          // refill the slot just consumed with the item 3 ahead: same slice for jj < 3, next slice (possibly of the next tile) otherwise
-          if (jj < 3) fetch(jj + 3, true, n, th, tw, kc);
-          else fetch(jj - 3, nx_live, nx_n, nx_th, nx_tw, nx_kc);
         }
         fence_proxy_async();            // generic-proxy stores -> visible to the tensor core (async proxy)
         __syncwarp();

@@ -140,8 +140,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // The whole warp runs the warp-uniform control flow (barrier addresses and descriptors stay in uniform registers); one elected
+    // lane issues the MMAs and the commits.  Descriptors are a constant high word + (address >> 4): per-k variants are increments.
+    {
+      uint32_t el;
+      asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(el));
+      const bool elected = el != 0;
       const uint32_t idesc = make_idesc_bf16(BM, BN < 8 ? 8 : BN, 0, b_mn ? 1 : 0);
+      const uint64_t adesc0 = make_sdesc_sw128(smem_u32(smem), 16, 1024);
+      const uint64_t bdesc0 = b_mn ? make_sdesc_sw128(smem_u32(smem) + Cfg::NOPS * A_TILE_BYTES, 8192, 1024)
+                                   : make_sdesc_sw128(smem_u32(smem) + Cfg::NOPS * A_TILE_BYTES, 16, 1024);
+      const uint64_t bk = b_mn ? (2048 >> 4) : (32 >> 4);           // k-advance of B in 16-byte units
+      constexpr uint64_t ALO = A_TILE_BYTES >> 4, BLO = Cfg::B_TILE_BYTES >> 4;
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -157,31 +167,28 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         for (int it = 0; it < kit; ++it) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t a_base = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-          const uint32_t b_base = a_base + Cfg::NOPS * A_TILE_BYTES;
+          const uint64_t a_st = adesc0 + (uint64_t)(stage * (Cfg::STAGE_BYTES >> 4));
+          const uint64_t b_st = bdesc0 + (uint64_t)(stage * (Cfg::STAGE_BYTES >> 4));
+          if (elected) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            // K-major SW128: 8-row groups 1024 B apart (SBO), k-advance = 32 B inside the swizzle row.
-            // MN-major SW128 (B only): 8 k-rows per 1024 B (SBO), 64-column atoms 8192 B apart (LBO), k-advance = 16 rows.
-            const uint64_t a_hi = make_sdesc_sw128(a_base + k * 32, 16, 1024);
-            const uint64_t b_hi = b_mn ? make_sdesc_sw128(b_base + k * 2048, 8192, 1024)
-                                       : make_sdesc_sw128(b_base + k * 32, 16, 1024);
-            const uint32_t first = (it == 0 && k == 0) ? 0u : 1u;
-            if (NPASS == 3) {
-              const uint64_t a_lo = make_sdesc_sw128(a_base + A_TILE_BYTES + k * 32, 16, 1024);
-              const uint64_t b_lo = b_mn ? make_sdesc_sw128(b_base + Cfg::B_TILE_BYTES + k * 2048, 8192, 1024)
-                                         : make_sdesc_sw128(b_base + Cfg::B_TILE_BYTES + k * 32, 16, 1024);
-              umma_bf16(d_tmem, a_lo, b_hi, idesc, first);   // small terms first
-              umma_bf16(d_tmem, a_hi, b_lo, idesc, 1u);
-              umma_bf16(d_tmem, a_hi, b_hi, idesc, 1u);
-            } else {
-              umma_bf16(d_tmem, a_hi, b_hi, idesc, first);
+            for (int k = 0; k < BK / 16; ++k) {
+              // K-major SW128: 8-row groups 1024 B apart (SBO), k-advance = 32 B inside the swizzle row.
+              // MN-major SW128 (B only): 8 k-rows per 1024 B (SBO), 64-column atoms 8192 B apart (LBO), k-advance = 16 rows.
+              const uint64_t a_hi = a_st + k * 2, b_hi = b_st + k * bk;
+              const uint32_t first = (it == 0 && k == 0) ? 0u : 1u;
+              if (NPASS == 3) {
+                umma_bf16(d_tmem, a_hi + ALO, b_hi, idesc, first);   // small terms first
+                umma_bf16(d_tmem, a_hi, b_hi + BLO, idesc, 1u);
+                umma_bf16(d_tmem, a_hi, b_hi, idesc, 1u);
+              } else {
+                umma_bf16(d_tmem, a_hi, b_hi, idesc, first);
+              }
             }
+            umma_commit(&empty_bar[stage]);   // frees the smem stage once these MMAs retire
           }
-          umma_commit(&empty_bar[stage]);   // frees the smem stage once these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull_bar[acc]);       // accumulator complete -> epilogue
+        if (elected) umma_commit(&tfull_bar[acc]);       // accumulator complete -> epilogue
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }

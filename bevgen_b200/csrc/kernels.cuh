@@ -85,11 +85,12 @@ struct ConvFusedParams {
   float* out;              // [N][H][W][Cout]
   double* gn_sums;         // [N][32][2] or null: GroupNorm statistics of `out`
   int dbg;                 // ablation switches (BEVGEN_CONV_DBG, tools/conv_ablation.py): 1 no global fetch, 2 no operand transform/stores,
-                           // 4 epilogue drains TMEM only, 8 no MMA issue.  0 in production.
+                           // 4 epilogue drains TMEM only, 8 no MMA issue, 16 no weight traffic.  0 in production.
   float lo_scale;          // npass == 2 (fp16 + e4m3 corrections): 1 / (2^13 * weight scale), applied to the correction accumulator
 };
 int launch_conv_fused(const ConvFusedParams& p, int npass, int sm_count, cudaStream_t st);
 int launch_conv_fused2(const ConvFusedParams& p, int npass, int sm_count, cudaStream_t st);   // 2-CTA clusters; tmW box = (64, 64)
+int launch_conv_fused3(const ConvFusedParams& p, int npass, int sm_count, cudaStream_t st);   // 2-CTA clusters, 16x16 blocks; tmW box = (32, 64), SWIZZLE_64B
 int launch_gn_affine(const double* sums, const float* gamma, const float* beta, float* affine, int N, int pixels, int C, float eps, cudaStream_t st);
 
 int launch_attn_fused(const CUtensorMap* tm_hi, const CUtensorMap* tm_lo, const void* bias_f16, const float* y, float* x1, int B, int H, int L,

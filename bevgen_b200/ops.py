@@ -69,6 +69,23 @@ def pack_f16f8(w2d: torch.Tensor):
     return w16.contiguous(), pair.reshape(rows, 2 * cin).contiguous(), 1.0 / (2.0 ** F8_ACT_LO_SHIFT * s)
 
 
+def pack_f16f8_block(w2d: torch.Tensor):
+    """Weights for the 16x16-block f16f8 kernel (bevgen_conv3x3_fused_f16f8, block16=1): (w16s fp16(w * S * 2^7), pair [rows][2*cin] uint8 with,
+    per 32-channel slice, 32 bytes e4m3(w * S) then 32 bytes e4m3((w - w16) * S * 2^13), lo_scale = 1 / (2^13 * S))."""
+    rows, cin = w2d.shape
+    assert cin % 32 == 0
+    w = w2d.float()
+    amax = float(w.abs().max().item())
+    e = 6 if amax == 0.0 else min(max(6 - math.ceil(math.log2(amax)), -16), 24)
+    s = 2.0 ** e
+    w16s = (w * (s * 128.0)).to(torch.float16)
+    w16 = w16s.float() / (s * 128.0)
+    w8 = (w * s).clamp(-448.0, 448.0).to(torch.float8_e4m3fn)
+    wlo8 = ((w - w16) * (s * 2.0 ** F8_ACT_LO_SHIFT)).clamp(-448.0, 448.0).to(torch.float8_e4m3fn)
+    pair = torch.stack([w8.view(torch.uint8).view(rows, cin // 32, 32), wlo8.view(torch.uint8).view(rows, cin // 32, 32)], 2)
+    return w16s.contiguous(), pair.reshape(rows, 2 * cin).contiguous(), 1.0 / (2.0 ** F8_ACT_LO_SHIFT * s)
+
+
 TAPS_3X3 = [(kw - 1, kh - 1) for kh in range(3) for kw in range(3)]
 
 
@@ -252,7 +269,8 @@ def groupnorm_finalize(sums, mean_rstd, n, pixels, c, eps=1e-6):
     _lib.check(lib.bevgen_groupnorm_finalize(_ptr(sums), n, pixels, c, eps, _ptr(mean_rstd), _stream()), "groupnorm_finalize")
 
 
-def conv3x3_fused(x, w_hi, w_lo, cout, bias, out, affine=None, swish=False, up2=False, residual=None, gn_sums=None, npass=3, two_cta=False):
+def conv3x3_fused(x, w_hi, w_lo, cout, bias, out, affine=None, swish=False, up2=False, residual=None, gn_sums=None, npass=3, two_cta=False,
+                  block16=False):
     """3x3 s1 'same' conv straight from the fp32 NHWC activation `x` (GroupNorm-apply/swish/split/upsample fused into the operand path)."""
     lib = _lib.init()
     _chk_cuda(x, w_hi, w_lo, bias, out, affine, residual, gn_sums)
@@ -263,15 +281,17 @@ def conv3x3_fused(x, w_hi, w_lo, cout, bias, out, affine=None, swish=False, up2=
     Stats.gemm_launches += 1
     Stats.gemm_flops += flops
     call = lambda: _lib.check(lib.bevgen_conv3x3_fused(_ptr(x), n, h, w, cin, _ptr(affine), int(swish), int(up2), _ptr(w_hi), _ptr(w_lo), w_hi.shape[0],
-                                                       cout, _ptr(bias), _ptr(residual), _ptr(out), _ptr(gn_sums), npass | (0x100 if two_cta else 0), _stream()), "conv3x3_fused")
+                                                       cout, _ptr(bias), _ptr(residual), _ptr(out), _ptr(gn_sums),
+                                                       npass | (0x200 if block16 else (0x100 if two_cta else 0)), _stream()), "conv3x3_fused")
     if Stats.timer is not None:
         Stats.timer("conv_fused", call, flops)
     else:
         call()
 
 
-def conv3x3_fused_f16f8(x, w16, w8pair, lo_scale, cout, bias, out, affine=None, swish=False, up2=False, residual=None, gn_sums=None):
-    """conv3x3_fused with the fp32-equivalent product formed as one fp16 MMA + two e4m3 MMAs (weights from pack_f16f8)."""
+def conv3x3_fused_f16f8(x, w16, w8pair, lo_scale, cout, bias, out, affine=None, swish=False, up2=False, residual=None, gn_sums=None, block16=False):
+    """conv3x3_fused with the fp32-equivalent product formed as one fp16 MMA + two e4m3 MMAs (weights from pack_f16f8, or from
+    pack_f16f8_block when block16 selects the weight-stationary 16x16-block kernel: GroupNorm-ed inputs only, |x| < 1024)."""
     lib = _lib.init()
     _chk_cuda(x, w16, w8pair, bias, out, affine, residual, gn_sums)
     n, h, w, _ = out.shape
@@ -282,7 +302,7 @@ def conv3x3_fused_f16f8(x, w16, w8pair, lo_scale, cout, bias, out, affine=None, 
     Stats.gemm_flops += flops
     call = lambda: _lib.check(lib.bevgen_conv3x3_fused_f16f8(_ptr(x), n, h, w, cin, _ptr(affine), int(swish), int(up2), _ptr(w16), _ptr(w8pair),
                                                              w16.shape[0], cout, float(lo_scale), _ptr(bias), _ptr(residual), _ptr(out),
-                                                             _ptr(gn_sums), _stream()), "conv3x3_fused_f16f8")
+                                                             _ptr(gn_sums), int(block16), _stream()), "conv3x3_fused_f16f8")
     if Stats.timer is not None:
         Stats.timer("conv_fused", call, flops)
     else:

@@ -100,15 +100,21 @@ BEVGEN_API int bevgen_conv3x3_halo(const void* a_hi, const void* a_lo, int n, in
 BEVGEN_API int bevgen_conv3x3_fused(const float* x, int n, int h, int w, int cin, const float* affine, int swish, int up2, const void* w_hi,
                                     const void* w_lo, int w_rows, int cout, const float* bias, const float* residual, float* out, double* gn_sums,
                                     int npass, void* stream);
-/* Same convolution (cta_group::2 kernel) with the fp32-equivalent product formed as ONE fp16 MMA plus TWO e4m3 MMAs (which run at twice
- * the fp16 rate) instead of three bf16 MMAs:   x*w ~= x16*w16 + [ e4m3((x - x16) * 2^13) * e4m3(w * S)  +  e4m3(x) * e4m3((w - w16) * S * 2^13) ] * lo_scale,
- * lo_scale = 1 / (2^13 * S).  The correction sum has its own TMEM accumulator and is folded in by the epilogue; out-of-range values saturate
- * (the affected element degrades to fp16 accuracy instead of overflowing).  Max error ~2^-15 relative per product (bf16x3: ~2^-17).
- *   w_f16    [tap][cout][cin] fp16, rows padded like bevgen_conv3x3_fused
- *   w_f8pair same rows, 2*cin bytes per row: per 64-channel chunk 64 bytes e4m3(w * S) followed by 64 bytes e4m3((w - w16) * S * 2^13)   */
+/* Same convolution (cta_group::2 kernels) with the fp32-equivalent product formed as ONE fp16 MMA plus TWO e4m3 MMAs (which run at twice
+ * the fp16 rate) instead of three bf16 MMAs.  Max error ~2^-15 relative per product (bf16x3: ~2^-17).
+ * block16 == 0 (conv_fused2.cu, any input range):
+ *     x*w ~= x16*w16 + [ e4m3((x - x16) * 2^13) * e4m3(w * S)  +  e4m3(x) * e4m3((w - w16) * S * 2^13) ] * lo_scale,   lo_scale = 1 / (2^13 * S)
+ *   the correction sum has its own TMEM accumulator; out-of-range values saturate (the element degrades to fp16 accuracy, no overflow).
+ *     w_f16    [tap][cout][cin] fp16, rows padded like bevgen_conv3x3_fused
+ *     w_f8pair same rows, 2*cin bytes per row: per 64-channel chunk 64 bytes e4m3(w * S) followed by 64 bytes e4m3((w - w16) * S * 2^13)
+ * block16 == 1 (conv_fused3.cu, weight-stationary 16x16 pixel blocks for the large feature maps; |x| < 1024 required, i.e. GroupNorm-ed inputs):
+ *     x*w ~= [ fp16(x * 2^6) * w16s + e4m3((x - x16) * 2^13) * e4m3(w * S) + e4m3(x) * e4m3((w - w16) * S * 2^13) ] * lo_scale
+ *   one accumulator; w_f16 = fp16(w * S * 2^7) (so w16 = w_f16 / (S * 2^7)), and the pair rows hold, per 32-channel slice, 32 bytes
+ *   e4m3(w * S) followed by 32 bytes e4m3((w - w16) * S * 2^13).  cin % 32 == 0.
+ * bevgen_conv3x3_fused with npass | 0x200 selects the block kernel for the bf16 / bf16x3 products (same weight planes). */
 BEVGEN_API int bevgen_conv3x3_fused_f16f8(const float* x, int n, int h, int w, int cin, const float* affine, int swish, int up2, const void* w_f16,
                                           const void* w_f8pair, int w_rows, int cout, float lo_scale, const float* bias, const float* residual,
-                                          float* out, double* gn_sums, void* stream);
+                                          float* out, double* gn_sums, int block16, void* stream);
 /* (sum, sumsq) per (image, group) + GroupNorm weight/bias -> affine[n][c][2] = (rstd*gamma, beta - mean*rstd*gamma) */
 BEVGEN_API int bevgen_groupnorm_affine(const double* sums, const float* gamma, const float* beta, int n, int pixels, int c, float eps, float* affine,
                                        void* stream);

@@ -63,7 +63,7 @@ class _EngineBacked(nn.Module):
         self._dd = dict(ddconfig)
         self._engine = None
         self._engine_key = None
-        self.precision = "fp32x3"
+        self.precision = "f16f8"
 
     def _load_from_state_dict(self, *a, **k):
         self._engine = None

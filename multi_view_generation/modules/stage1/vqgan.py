@@ -21,7 +21,7 @@ except Exception:  # pragma: no cover
 class VQModel(_Base):
     def __init__(self, ddconfig, lossconfig, n_embed, embed_dim, cam_res, cam_latent_res, cam_emd_dim, geometric_embedding=False,
                  ckpt_path=None, ignore_keys=[], image_key="image", colorize_nlabels=None, monitor=None, remap=None,
-                 sane_index_shape=False, denormalize=True, legacy=True, precision="fp32x3", **kwargs):
+                 sane_index_shape=False, denormalize=True, legacy=True, precision="f16f8", **kwargs):
         super().__init__()
         if geometric_embedding:
             raise NotImplementedError("geometric_embedding=True (stage-1 ray embedding) is a 'next' row (SURVEY §8f-4)")

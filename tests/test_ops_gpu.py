@@ -308,7 +308,7 @@ def test_conv3x3_halo(N_, H, W, Cin, Cout, npass):
 @pytest.mark.parametrize("npass", [3, 1])
 @pytest.mark.parametrize("N_,H,W,Cin,Cout,mode", [(2, 16, 16, 64, 128, "gn_swish"), (1, 20, 28, 128, 128, "gn_swish"), (3, 8, 8, 128, 256, "plain"),
                                                    (2, 16, 16, 128, 128, "up2"), (1, 64, 64, 128, 128, "gn_swish")])
-@pytest.mark.parametrize("two_cta", [False, True])
+@pytest.mark.parametrize("two_cta", [False, True, "block16"])
 @pytest.mark.timeout(400)
 def test_conv3x3_fused_prologue(N_, H, W, Cin, Cout, mode, npass, two_cta):
     """Conv reading fp32 activations directly with GroupNorm-apply + swish (+ nearest 2x upsample) fused into the operand path."""
@@ -339,7 +339,7 @@ def test_conv3x3_fused_prologue(N_, H, W, Cin, Cout, mode, npass, two_cta):
     out = torch.full((N_, H, W, Cout), float("nan"), device=dev())
     osums = torch.full((N_ * 64,), float("nan"), dtype=torch.float64, device=dev())
     ops.conv3x3_fused(x_nhwc, w_hi, w_lo if npass == 3 else None, Cout, b, out, affine=affine, swish=(mode == "gn_swish"), up2=(mode == "up2"),
-                      residual=res, gn_sums=osums, npass=npass, two_cta=two_cta)
+                      residual=res, gn_sums=osums, npass=npass, two_cta=(two_cta is True), block16=(two_cta == "block16"))
     torch.cuda.synchronize()
     ref = F.conv2d(ref_in, w.double(), b.double(), padding=1) + res.double().permute(0, 3, 1, 2)
     assert torch.isfinite(out).all()
@@ -352,8 +352,9 @@ def test_conv3x3_fused_prologue(N_, H, W, Cin, Cout, mode, npass, two_cta):
 
 @pytest.mark.parametrize("N_,H,W,Cin,Cout,mode", [(2, 16, 16, 64, 128, "gn_swish"), (1, 20, 28, 128, 128, "gn_swish"), (3, 8, 8, 128, 256, "plain"),
                                                    (2, 16, 16, 128, 128, "up2"), (1, 64, 64, 128, 128, "gn_swish"), (1, 24, 8, 256, 96, "big")])
+@pytest.mark.parametrize("block16", [False, True])
 @pytest.mark.timeout(400)
-def test_conv3x3_fused_f16f8(N_, H, W, Cin, Cout, mode):
+def test_conv3x3_fused_f16f8(N_, H, W, Cin, Cout, mode, block16):
     """fp16 + 2 x e4m3 split product (bevgen_conv3x3_fused_f16f8): same contract as the bf16x3 kernel, error bound ~2^-15 per product.
     "big" feeds activations far outside the e4m3 window (|x| up to ~400): the kernel must degrade to fp16 accuracy, not overflow."""
     g = torch.Generator().manual_seed(H * W + Cin + Cout + len(mode))
@@ -368,7 +369,7 @@ def test_conv3x3_fused_f16f8(N_, H, W, Cin, Cout, mode):
     rows = 9 * Cout
     wp = torch.zeros(8 * Cout + ((Cout + 127) // 128) * 128, Cin, device=dev())
     wp[:rows] = w.permute(2, 3, 0, 1).reshape(rows, Cin)
-    w16, w8pair, lo_scale = ops.pack_f16f8(wp)
+    w16, w8pair, lo_scale = (ops.pack_f16f8_block if block16 else ops.pack_f16f8)(wp)
     assert w16.dtype == torch.float16 and w8pair.dtype == torch.uint8 and w8pair.shape == (wp.shape[0], 2 * Cin)
     affine = None
     ref_in = x.double()
@@ -385,7 +386,7 @@ def test_conv3x3_fused_f16f8(N_, H, W, Cin, Cout, mode):
     out = torch.full((N_, H, W, Cout), float("nan"), device=dev())
     osums = torch.full((N_ * 64,), float("nan"), dtype=torch.float64, device=dev()) if Cout >= 128 else None
     ops.conv3x3_fused_f16f8(x_nhwc, w16, w8pair, lo_scale, Cout, b, out, affine=affine, swish=(mode == "gn_swish"), up2=(mode == "up2"),
-                            residual=res, gn_sums=osums)
+                            residual=res, gn_sums=osums, block16=block16)
     torch.cuda.synchronize()
     ref = F.conv2d(ref_in, w.double(), b.double(), padding=1) + res.double().permute(0, 3, 1, 2)
     assert torch.isfinite(out).all()

@@ -19,15 +19,18 @@ flops = 2.0 * N * H * W * C * C * 9
 
 import os
 w16, w8pair, lo_scale = ops.pack_f16f8(w)
+w16b, w8pairb, lo_scaleb = ops.pack_f16f8_block(w)
 
-def t(label, npass=3, two_cta=True, dbg=0, **kw):
+def t(label, npass=3, two_cta=True, dbg=0, block16=False, **kw):
     args = dict(affine=aff, swish=True, residual=res, gn_sums=sums)
     args.update(kw)
     os.environ["BEVGEN_CONV_DBG"] = str(dbg)
-    if npass == 2:
+    if npass == 2 and block16:
+        f = lambda: ops.conv3x3_fused_f16f8(x, w16b, w8pairb, lo_scaleb, C, b, out, block16=True, **args)
+    elif npass == 2:
         f = lambda: ops.conv3x3_fused_f16f8(x, w16, w8pair, lo_scale, C, b, out, **args)
     else:
-        f = lambda: ops.conv3x3_fused(x, w_hi, w_lo if npass == 3 else None, C, b, out, npass=npass, two_cta=two_cta, **args)
+        f = lambda: ops.conv3x3_fused(x, w_hi, w_lo if npass == 3 else None, C, b, out, npass=npass, two_cta=two_cta, block16=block16, **args)
     for _ in range(2): f()
     torch.cuda.synchronize()
     a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -37,15 +40,36 @@ def t(label, npass=3, two_cta=True, dbg=0, **kw):
     ms = a.elapsed_time(e) / 10
     print(f"{label:44s} {ms:7.3f} ms  {flops / ms / 1e9:7.1f} TFLOP/s algorithmic")
 
-t("full (affine+swish, residual, stats) 2cta")
-t("full, 1cta", two_cta=False)
-t("no affine/swish (identity prologue)", affine=None, swish=False)
-t("no residual", residual=None)
-t("no stats", gn_sums=None)
-t("bare (identity prologue, no residual, no stats)", affine=None, swish=False, residual=None, gn_sums=None)
-t("bf16 full", npass=1)
-t("bf16 bare", npass=1, affine=None, swish=False, residual=None, gn_sums=None)
+if len(sys.argv) < 2: t("full (affine+swish, residual, stats) 2cta")
+if len(sys.argv) < 2: t("full, 1cta", two_cta=False)
+if len(sys.argv) < 2: t("no affine/swish (identity prologue)", affine=None, swish=False)
+if len(sys.argv) < 2: t("no residual", residual=None)
+if len(sys.argv) < 2: t("no stats", gn_sums=None)
+if len(sys.argv) < 2: t("bare (identity prologue, no residual, no stats)", affine=None, swish=False, residual=None, gn_sums=None)
+if len(sys.argv) < 2: t("bf16 full", npass=1)
+if len(sys.argv) < 2: t("bf16 bare", npass=1, affine=None, swish=False, residual=None, gn_sums=None)
 
+if len(sys.argv) > 1 and sys.argv[1] == "block":
+    for npass in (2, 3, 1):
+        t(f"npass={npass} conv_fused2 (128-pixel tiles)", npass=npass)
+        t(f"npass={npass} conv_fused3 (16x16 blocks)", npass=npass, block16=True)
+        for dbg, label in [(8, "no MMA"), (24, "no MMA, no weights"), (7, "MMA + weights only"), (3, "producers idle"), (4, "epilogue drains only")]:
+            t(f"   block16 {dbg}: {label}", npass=npass, block16=True, dbg=dbg)
+    os.environ["BEVGEN_CONV_DBG"] = "0"
+    sys.exit(0)
+if len(sys.argv) > 1 and sys.argv[1] == "pe":
+    print("--- producer / epilogue interplay, f16f8 kernel, MMA issue off (8); 16 = no weight traffic")
+    for dbg, label in [(0, "full"), (8, "no MMA"), (24, "no MMA, no weights"), (24 | 4, "no MMA/weights, epilogue idle (P only)"),
+                       (24 | 3, "no MMA/weights, producers idle (E only)"), (24 | 2, "no MMA/weights, P fetch only + E"),
+                       (24 | 1, "no MMA/weights, P transform only + E"), (24 | 7, "nothing (loop skeleton)"),
+                       (24 | 4 | 2, "P fetch only"), (24 | 4 | 1, "P transform only")]:
+        t(f"{dbg}: {label}", npass=2, dbg=dbg)
+    t("24|3, no residual: E without residual", npass=2, dbg=24 | 3, residual=None)
+    t("24|3, no stats: E without stats", npass=2, dbg=24 | 3, gn_sums=None)
+    t("24, no residual: P + E without residual", npass=2, dbg=24, residual=None)
+    t("24, no swish/affine", npass=2, dbg=24, affine=None, swish=False)
+    os.environ["BEVGEN_CONV_DBG"] = "0"
+    sys.exit(0)
 for npass in (2, 3, 1):
     print(f"--- kernel-internal ablations (BEVGEN_CONV_DBG), npass={npass}; results are wrong by construction")
     t("full", npass=npass)

@@ -18,7 +18,10 @@ aff = torch.randn(N, C, 2, device=dev)
 out = torch.empty(N, H, W, C, device=dev)
 sums = torch.empty(N * 64, dtype=torch.float64, device=dev)
 kw = dict(affine=aff, swish=True, residual=res, gn_sums=sums)
-if mode == "f16f8":
+if mode == "f16f8b":       # 16x16-block kernel (conv_fused3.cu)
+    w16, w8pair, lo_scale = ops.pack_f16f8_block(w)
+    f = lambda: ops.conv3x3_fused_f16f8(x, w16, w8pair, lo_scale, C, b, out, block16=True, **kw)
+elif mode == "f16f8":
     w16, w8pair, lo_scale = ops.pack_f16f8(w)
     f = lambda: ops.conv3x3_fused_f16f8(x, w16, w8pair, lo_scale, C, b, out, **kw)
 else:

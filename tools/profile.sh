@@ -1,15 +1,23 @@
 #!/bin/bash
-# Run under gpurun: ncu launch list of one steady-state VQGAN step, one `--set full` capture of the dominant kernel (conv_fused, the
-# 128->128 3x3 convs at 256x256), and the same for the stage-2 forward (fused attention).  Numbers printed under ncu are never bench values.
+# Run under gpurun: ncu launch list of one steady-state VQGAN step (only this library's kernels: -k regex over their names; the last
+# quarter of the 4 captured steps is the steady-state one), plus `--set full` captures of the dominant kernel.  Numbers printed under ncu
+# are never bench values.
 set -x
 mkdir -p gpurun_out
-L=${LAUNCHES_PER_STEP:-223}
-BENCH_LITE=1 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s $((3*L+1)) -c $L --csv \
-   --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 3 > gpurun_out/ncu_list.log 2>&1
-F=$(grep -c conv_fused gpurun_out/launches.csv)
-echo "conv_fused launches per step: $F"
-BENCH_LITE=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_fused -s $((3*F)) -c 3 \
-   -f -o gpurun_out/prof_conv_fused python bench.py --steps 1 --warmup 3 > gpurun_out/ncu_full.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:attn_fused -s 30 -c 2 \
-   -f -o gpurun_out/prof_attn_fused python tools/stage2_perf.py fp32x3 > gpurun_out/ncu_attn.log 2>&1
-ls -la gpurun_out
+P=${PRECISION:-f16f8}
+K='regex:^(attn_fused|attn_softmax|conv_fused2|conv_fused|conv_halo|denorm|gather_rows|gemm_tc|gn_affine|gn_finalize|gn_stats|im2col3x3|prep|row_sqnorm|softmax_rows|transpose|vq_nearest)_kernel'
+BENCH_LITE=1 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k "$K" -c 2000 --csv \
+   --log-file gpurun_out/launches_all.csv python bench.py --precision $P --steps 1 --warmup 3 > gpurun_out/ncu_list.log 2>&1
+python - <<'PY'
+lines = [l for l in open("gpurun_out/launches_all.csv") if not l.startswith("==")]
+hdr, rows = lines[0], lines[1:]
+n = len(rows) // 4
+open("gpurun_out/launches_step.csv", "w").writelines([hdr] + rows[-n:])
+print("kernels per step:", n)
+PY
+python tools/summarize_launches.py gpurun_out/launches_step.csv
+# `--set full` of three consecutive dominant launches (conv 128->128 3x3 at 256x256 x 96: conv1 without / conv2 with residual) inside a step
+F=$(grep -c conv_fused2 gpurun_out/launches_step.csv)
+BENCH_LITE=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_fused2 -s $((3*F+2)) -c 3 \
+   -f -o gpurun_out/prof_conv_fused python bench.py --precision $P --steps 1 --warmup 3 > gpurun_out/ncu_full.log 2>&1
+tail -2 gpurun_out/ncu_full.log
