@@ -62,6 +62,7 @@ SIGNATURES = {
     "bevgen_last_error": (C.c_char_p, []),
     "bevgen_version": (_i, []),
     "bevgen_sm_count": (_i, []),
+    "bevgen_set_pdl": (_i, [_i]),
     "bevgen_gemm_tc": (_i, [C.POINTER(GemmArgs), _vp]),
     "bevgen_conv3x3_halo": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _i, _vp]),
     "bevgen_conv3x3_fused": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _i, _vp]),

@@ -12,6 +12,8 @@
 
 using namespace bevgen;
 
+namespace bevgen { int g_pdl_enabled = 0; }
+
 namespace {
 thread_local char g_err[512] = "";
 int g_sm_count = 0;
@@ -59,6 +61,7 @@ extern "C" {
 BEVGEN_API const char* bevgen_last_error(void) { return g_err; }
 BEVGEN_API int bevgen_version(void) { return 100; }
 BEVGEN_API int bevgen_sm_count(void) { return g_sm_count; }
+BEVGEN_API int bevgen_set_pdl(int enabled) { const int old = bevgen::g_pdl_enabled; bevgen::g_pdl_enabled = enabled ? 1 : 0; return old; }
 
 BEVGEN_API int bevgen_init(int device) {
   std::lock_guard<std::mutex> lk(g_mu);

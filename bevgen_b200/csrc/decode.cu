@@ -5,6 +5,8 @@
 // r = n_cond + s - 1 (the row holding token s-1, or the last cond row for s = 0) against keys 0..r.
 // The weight GEMMs of a step are swap-AB tcgen05 launches (gemm_tc.cu, GF_OUT_T) that leave split-K partials
 // [ks][batch][features]; the kernels here fold "sum partials + bias (+ activation / residual / LayerNorm)" into one pass.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -41,6 +43,8 @@ __global__ void __launch_bounds__(256) dec_reduce_ln_kernel(const float* __restr
                                                             const float* __restrict__ beta, float eps, float* __restrict__ x_out,
                                                             float* __restrict__ y, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, int d) {
   __shared__ float red[8];
+  pdl_launch_dependents();
+  pdl_wait();
   const int row = blockIdx.x, c4 = threadIdx.x;
   const bool act = c4 < (d >> 2);
   float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -86,6 +90,8 @@ __global__ void __launch_bounds__(256) dec_reduce_ln_kernel(const float* __restr
 __global__ void __launch_bounds__(256) dec_reduce_act_kernel(const float* __restrict__ partials, int ks, long long zstride,
                                                              const float* __restrict__ bias, uint16_t* __restrict__ hi,
                                                              uint16_t* __restrict__ lo, int rows, int n, int gelu) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int q = n >> 2;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * q) return;
@@ -115,7 +121,9 @@ __device__ __forceinline__ size_t k_index(size_t bh, int c, int j, int Lmax) {
 template <typename T> __device__ __forceinline__ float kv_load(const T* p);
 template <> __device__ __forceinline__ float kv_load<float>(const float* p) { return *p; }
 template <> __device__ __forceinline__ float kv_load<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+template <> __device__ __forceinline__ float kv_load<__half>(const __half* p) { return __half2float(*p); }
 template <typename T> __device__ __forceinline__ void kv_store(T* p, float v);
+template <> __device__ __forceinline__ void kv_store<__half>(__half* p, float v) { *p = __float2half_rn(v); }
 template <> __device__ __forceinline__ void kv_store<float>(float* p, float v) { *p = v; }
 template <> __device__ __forceinline__ void kv_store<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 
@@ -180,6 +188,10 @@ __global__ void __launch_bounds__(256) dec_attn_kernel(const float* __restrict__
   __shared__ __align__(8) uint64_t bar;
   __shared__ unsigned int ticket;
   const int h = blockIdx.x, b = blockIdx.y, sp = blockIdx.z, S = gridDim.z, tid = threadIdx.x;
+  pdl_launch_dependents();
+  // Under programmatic dependent launch the code up to pdl_wait() overlaps the previous kernel (the QKV GEMM of this layer).  It only
+  // reads the step counter and the KV cache, both last written many kernels ago (every earlier kernel of the chain has completed once
+  // the immediate predecessor runs), so the whole K/V slab of the CTA is already in flight while the GEMM drains.
   const int r = nc + *step_ptr - 1;
   const int n = r + 1;
   const int j0 = sp * DEC_CHUNK;
@@ -197,6 +209,7 @@ __global__ void __launch_bounds__(256) dec_attn_kernel(const float* __restrict__
       bulk_g2s(Vs, vc + (bh * Lmax + j0) * 64, vbytes, &bar);
     }
   }
+  pdl_wait();
   if (tid < 192) {
     const int which = tid >> 6, c = tid & 63;
     if (cnt > 0 && (which == 0 || owns_new)) {
@@ -329,6 +342,8 @@ __global__ void __launch_bounds__(256) dec_sample_kernel(const float* __restrict
   __shared__ float red[8];
   __shared__ float wsum[8];
   __shared__ int found;
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x, tid = threadIdx.x, s = *step_ptr;
   const int B = gridDim.x;
   int np2 = 1;
@@ -440,27 +455,34 @@ __global__ void __launch_bounds__(256) dec_sample_kernel(const float* __restrict
   }
 }
 
-__global__ void dec_advance_kernel(int* step) { *step += 1; }
+__global__ void dec_advance_kernel(int* step) {
+  pdl_launch_dependents();
+  pdl_wait();
+  *step += 1;
+}
 
 // ---------------------------------------------------------------- launchers
 int launch_dec_reduce_ln(const float* partials, int ks, long long zstride, const float* bias, const float* residual, long long res_stride,
                          const float* gamma, const float* beta, float eps, float* x_out, float* y, uint16_t* hi, uint16_t* lo, int rows, int d,
                          cudaStream_t st) {
   if (d % 4 != 0 || d > 1024 || rows < 1) return BEVGEN_ERR_ARG;
-  dec_reduce_ln_kernel<<<rows, 256, 0, st>>>(partials, ks, zstride, bias, residual, res_stride, gamma, beta, eps, x_out, y, hi, lo, d);
+  if (launch_k(dec_reduce_ln_kernel, dim3(rows), dim3(256), 0, st, partials, ks, zstride, bias, residual, res_stride, gamma, beta, eps, x_out, y, hi, lo,
+               d) != cudaSuccess) return BEVGEN_ERR_CUDA;
   return cudaGetLastError() == cudaSuccess ? BEVGEN_OK : BEVGEN_ERR_CUDA;
 }
 int launch_dec_reduce_act(const float* partials, int ks, long long zstride, const float* bias, uint16_t* hi, uint16_t* lo, int rows, int n,
                           int gelu, cudaStream_t st) {
   if (n % 4 != 0 || rows < 1) return BEVGEN_ERR_ARG;
-  dec_reduce_act_kernel<<<(rows * (n / 4) + 255) / 256, 256, 0, st>>>(partials, ks, zstride, bias, hi, lo, rows, n, gelu);
+  if (launch_k(dec_reduce_act_kernel, dim3((rows * (n / 4) + 255) / 256), dim3(256), 0, st, partials, ks, zstride, bias, hi, lo, rows, n, gelu) != cudaSuccess)
+    return BEVGEN_ERR_CUDA;
   return cudaGetLastError() == cudaSuccess ? BEVGEN_OK : BEVGEN_ERR_CUDA;
 }
 int launch_kv_store(const uint16_t* hi, const uint16_t* lo, void* kc, void* vc, int kv_bf16, int B, int Lp, int nrows, int H, int d, int Lmax,
                     cudaStream_t st) {
   if (B < 1 || B > 65535 || nrows < 1 || (Lmax & 127)) return BEVGEN_ERR_ARG;
   dim3 grid(H, B, (nrows + 63) / 64);
-  if (kv_bf16) kv_store_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(hi, lo, (__nv_bfloat16*)kc, (__nv_bfloat16*)vc, Lp, nrows, H, d, Lmax);
+  if (kv_bf16 == 2) kv_store_kernel<__half><<<grid, 256, 0, st>>>(hi, lo, (__half*)kc, (__half*)vc, Lp, nrows, H, d, Lmax);
+  else if (kv_bf16) kv_store_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(hi, lo, (__nv_bfloat16*)kc, (__nv_bfloat16*)vc, Lp, nrows, H, d, Lmax);
   else kv_store_kernel<float><<<grid, 256, 0, st>>>(hi, lo, (float*)kc, (float*)vc, Lp, nrows, H, d, Lmax);
   return cudaGetLastError() == cudaSuccess ? BEVGEN_OK : BEVGEN_ERR_CUDA;
 }
@@ -474,11 +496,15 @@ int launch_dec_attn(const float* qkv_part, int ks, long long zstride, const floa
   if (Lmax > DEC_MAXL || B < 1 || B > 65535 || d != H * 64 || (Lmax & 127) || dec_splits(Lmax) > DEC_MAX_SPLIT) return BEVGEN_ERR_ARG;
   if (ln_gamma != nullptr && (!row_counters || !ln_beta || !ln_hi || d > 1024)) return BEVGEN_ERR_ARG;
   dim3 grid(H, B, dec_splits(Lmax));
-  if (kv_bf16) {
+  if (kv_bf16 == 2) {           // fp16 cache: half the KV bytes of the fp32 cache at ~3e-4 logit error (tests/test_decode_gpu.py)
     const int smem = 2 * 64 * DEC_CHUNK * 2;
-    dec_attn_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>(qkv_part, ks, zstride, bqkv, y, bias, bias_ld, (__nv_bfloat16*)kc, (__nv_bfloat16*)vc,
-                                                            x1, step_ptr, ws, counters, nc, H, d, Lmax, scale, row_counters, ln_gamma, ln_beta,
-                                                            ln_eps, ln_hi, ln_lo);
+    if (launch_k(dec_attn_kernel<__half>, grid, dim3(256), smem, st, qkv_part, ks, zstride, bqkv, y, bias, bias_ld, (__half*)kc, (__half*)vc, x1, step_ptr,
+                 ws, counters, nc, H, d, Lmax, scale, row_counters, ln_gamma, ln_beta, ln_eps, ln_hi, ln_lo) != cudaSuccess) return BEVGEN_ERR_CUDA;
+  } else if (kv_bf16) {
+    const int smem = 2 * 64 * DEC_CHUNK * 2;
+    if (launch_k(dec_attn_kernel<__nv_bfloat16>, grid, dim3(256), smem, st, qkv_part, ks, zstride, bqkv, y, bias, bias_ld, (__nv_bfloat16*)kc,
+                 (__nv_bfloat16*)vc, x1, step_ptr, ws, counters, nc, H, d, Lmax, scale, row_counters, ln_gamma, ln_beta, ln_eps, ln_hi, ln_lo) !=
+        cudaSuccess) return BEVGEN_ERR_CUDA;
   } else {
     const int smem = 2 * 64 * DEC_CHUNK * 4;
     static bool configured = false;
@@ -486,8 +512,8 @@ int launch_dec_attn(const float* qkv_part, int ks, long long zstride, const floa
       if (cudaFuncSetAttribute(dec_attn_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return BEVGEN_ERR_CUDA;
       configured = true;
     }
-    dec_attn_kernel<float><<<grid, 256, smem, st>>>(qkv_part, ks, zstride, bqkv, y, bias, bias_ld, (float*)kc, (float*)vc, x1, step_ptr, ws,
-                                                    counters, nc, H, d, Lmax, scale, row_counters, ln_gamma, ln_beta, ln_eps, ln_hi, ln_lo);
+    if (launch_k(dec_attn_kernel<float>, grid, dim3(256), smem, st, qkv_part, ks, zstride, bqkv, y, bias, bias_ld, (float*)kc, (float*)vc, x1, step_ptr, ws,
+                 counters, nc, H, d, Lmax, scale, row_counters, ln_gamma, ln_beta, ln_eps, ln_hi, ln_lo) != cudaSuccess) return BEVGEN_ERR_CUDA;
   }
   return cudaGetLastError() == cudaSuccess ? BEVGEN_OK : BEVGEN_ERR_CUDA;
 }
@@ -495,12 +521,12 @@ int launch_dec_sample(const float* part, int ks, long long zstride, int vpad, in
                       unsigned long long seed, const long long* forced, const int* fwd, long long* cam_idx, long long* tokens_out, float* trace,
                       float* probs_out, const int* step_ptr, int B, int n_img, int hw, int ncam, cudaStream_t st) {
   if (V > SAMPLE_MAXV || V < 1 || B < 1 || temperature <= 0.f) return BEVGEN_ERR_ARG;
-  dec_sample_kernel<<<B, 256, 0, st>>>(part, ks, zstride, vpad, V, 1.0f / temperature, top_k, greedy, seed, forced, fwd, cam_idx, tokens_out,
-                                       trace, probs_out, step_ptr, n_img, hw, ncam);
+  if (launch_k(dec_sample_kernel, dim3(B), dim3(256), 0, st, part, ks, zstride, vpad, V, 1.0f / temperature, top_k, greedy, seed, forced, fwd, cam_idx,
+               tokens_out, trace, probs_out, step_ptr, n_img, hw, ncam) != cudaSuccess) return BEVGEN_ERR_CUDA;
   return cudaGetLastError() == cudaSuccess ? BEVGEN_OK : BEVGEN_ERR_CUDA;
 }
 int launch_dec_advance(int* step, cudaStream_t st) {
-  dec_advance_kernel<<<1, 1, 0, st>>>(step);
+  if (launch_k(dec_advance_kernel, dim3(1), dim3(1), 0, st, step) != cudaSuccess) return BEVGEN_ERR_CUDA;
   return cudaGetLastError() == cudaSuccess ? BEVGEN_OK : BEVGEN_ERR_CUDA;
 }
 

@@ -76,6 +76,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();            // decode chain: the next kernel may run its prologue while this one streams its weights
+  if (!(warp == 0 && lane == 0)) pdl_wait();    // touch dependent global memory only after the predecessor has completed (the TMA thread
+                                                // waits inside its branch, after prefetching the constant weight operand)
 
   // tile -> coordinates.  n-tile fastest so that CTAs running side by side share the same A tile in L2.
   auto decode_tile = [&](int t, int& z, int& tw, int& th, int& nt) {
@@ -103,6 +106,32 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      // Decode (swap-AB, GF_OUT_T) launches: the A operand is a constant weight matrix, so under programmatic dependent launch its tiles for
+      // the CTA's first output tile are requested BEFORE waiting for the predecessor: the weight stream of this GEMM overlaps the tail
+      // of the previous kernel; only the (tiny, L2-resident) activation tiles are loaded after the wait.
+      int pre = 0;
+      if ((p.flags & GF_OUT_T) && (int)blockIdx.x < total_tiles) {
+        int z, tw, th, nt;
+        decode_tile(blockIdx.x, z, tw, th, nt);
+        if (!tile_skipped(tw, nt)) {
+          const int zo = z / p.z_inner, zi = z % p.z_inner;
+          const int w0 = tw * p.tile_w, h0 = th * p.tile_h;
+          const int kit = k_iters_for(tw);
+          pre = kit < STAGES ? kit : STAGES;
+          for (int it = 0; it < pre; ++it) {
+            const int tap = it / p.kchunks, kc = it % p.kchunks;
+            uint8_t* st = smem + it * Cfg::STAGE_BYTES;
+            mbar_expect_tx(&full_bar[it], Cfg::STAGE_BYTES);
+            const int ac = p.a_c_off + zi * p.a_c_zstride + kc * BK;
+            const int an = zo * p.a_n_mul + zi * p.a_n_zstride + p.tap_dn[tap];
+#pragma unroll
+            for (int o = 0; o < Cfg::NOPS; ++o)
+              tma_load_4d(st + o * A_TILE_BYTES, &p.tmA[o], &full_bar[it], ac, w0 + p.tap_dx[tap], h0 + p.tap_dy[tap], an);
+          }
+        }
+      }
+      pdl_wait();
+      bool first_tile = true;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         int z, tw, th, nt;
         decode_tile(t, z, tw, th, nt);
@@ -112,14 +141,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         const int kit = k_iters_for(tw);
         for (int it = 0; it < kit; ++it) {
           const int tap = it / p.kchunks, kc = it % p.kchunks;
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+          const bool a_done = first_tile && it < pre;           // A tile (and the stage's expect_tx) already issued before the wait
+          if (!a_done) mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = smem + stage * Cfg::STAGE_BYTES;
-          mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          if (!a_done) mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           const int ac = p.a_c_off + zi * p.a_c_zstride + kc * BK;
           const int an = zo * p.a_n_mul + zi * p.a_n_zstride + p.tap_dn[tap];
 #pragma unroll
           for (int o = 0; o < Cfg::NOPS; ++o) {
-            tma_load_4d(st + o * A_TILE_BYTES, &p.tmA[o], &full_bar[stage], ac, w0 + p.tap_dx[tap], h0 + p.tap_dy[tap], an);
+            if (!a_done) tma_load_4d(st + o * A_TILE_BYTES, &p.tmA[o], &full_bar[stage], ac, w0 + p.tap_dx[tap], h0 + p.tap_dy[tap], an);
             uint8_t* bdst = st + Cfg::NOPS * A_TILE_BYTES + o * Cfg::B_TILE_BYTES;
             if (!b_mn) {
               const int bk = p.b_k_off + zi * p.b_k_zstride + kc * BK;
@@ -136,6 +166,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        first_tile = false;
       }
     }
   } else if (warp == 1) {
@@ -439,7 +470,7 @@ static int launch_gemm(const GemmParams& p, int total_tiles, int sm_count, cudaS
     configured = true;
   }
   int grid = total_tiles < sm_count ? total_tiles : sm_count;
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(p);
+  if (launch_k(kern, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, p) != cudaSuccess) return BEVGEN_ERR_CUDA;
   return cudaGetLastError() == cudaSuccess ? BEVGEN_OK : BEVGEN_ERR_CUDA;
 }
 

@@ -7,6 +7,22 @@
 
 namespace bevgen {
 
+// Launch helper for the kernels of the KV-cache decode chain: with g_pdl_enabled (bevgen_set_pdl) the launch carries the programmatic
+// stream-serialization attribute, so the kernel's prologue (barrier init, TMEM allocation, KV-slab prefetch) overlaps the tail of its
+// predecessor; the kernels call pdl_wait() before touching dependent memory.  Works under stream capture (programmatic graph edges).
+extern int g_pdl_enabled;
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_pdl_enabled ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 enum PrepMode : int { PREP_IDENT = 0, PREP_UP2 = 1, PREP_S2D = 2 };
 
 struct PrepParams {

@@ -73,6 +73,8 @@ int launch_layernorm(const float* x, const float* gamma, const float* beta, floa
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) embed_kernel(const EmbedParams p) {
   __shared__ float red[4];
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.y;
   const int s = (p.step_ptr != nullptr ? p.nc + *p.step_ptr - 1 : p.row0) + blockIdx.x;
   float* out = p.out + ((size_t)b * p.nrows + blockIdx.x) * p.d;
@@ -142,7 +144,7 @@ __global__ void __launch_bounds__(128) embed_kernel(const EmbedParams p) {
 
 int launch_embed(const EmbedParams& p, cudaStream_t st) {
   if (p.d % 4 != 0 || p.d > 1024 || p.nrows < 1 || p.B < 1 || p.B > 65535) return BEVGEN_ERR_ARG;
-  embed_kernel<<<dim3(p.nrows, p.B), 128, 0, st>>>(p);
+  if (launch_k(embed_kernel, dim3(p.nrows, p.B), dim3(128), 0, st, p) != cudaSuccess) return BEVGEN_ERR_CUDA;
   return cudaGetLastError() == cudaSuccess ? BEVGEN_OK : BEVGEN_ERR_CUDA;
 }
 

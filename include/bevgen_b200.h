@@ -84,6 +84,10 @@ BEVGEN_API int bevgen_init(int device);                 /* selects nothing, quer
 BEVGEN_API const char* bevgen_last_error(void);
 BEVGEN_API int bevgen_version(void);
 BEVGEN_API int bevgen_sm_count(void);
+/* Programmatic dependent launch for the KV-cache decode chain (gemm_tc, dec_*, embed, sample kernels): when enabled, those kernels are
+ * launched with the programmatic stream-serialization attribute and overlap their prologue with the previous kernel's tail (they call
+ * griddepcontrol.wait before touching dependent memory).  Returns the previous setting.  Process-wide; the sampler brackets its steps. */
+BEVGEN_API int bevgen_set_pdl(int enabled);
 
 BEVGEN_API int bevgen_gemm_tc(const bevgen_gemm_args* args, void* stream);
 

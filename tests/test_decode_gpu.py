@@ -40,7 +40,8 @@ def test_greedy_matches_reference_sampling_loop(golden_dir, use_graph, fuse):
 
 
 def test_teacher_forced_replay_equals_full_forward_reference(golden_dir):
-    """All 1536 cached steps on the 1024-wide model reproduce the reference's full-forward logits (golden rows)."""
+    """All 1536 cached steps on the 1024-wide model (default parity configuration: bf16x3 weights, fp16 KV cache) reproduce the reference's
+    full-forward logits (golden rows)."""
     g = np.load(golden_dir / "gpt_wide2.npz")
     cfg, sd, cam, bev, batch, eng, B = _case("wide2")
     forced = cam.reshape(B, -1)[:, cfg.forward_shuffle_idx]
@@ -58,6 +59,19 @@ def test_teacher_forced_replay_equals_full_forward_reference(golden_dir):
     full = eng.forward(cam.cuda(), bev.cuda(), batch, sampling=True)
     want = full[:, cfg.forward_shuffle_idx.cuda()].permute(1, 0, 2)
     assert (trace - want).abs().max().item() < 2e-4
+
+
+def test_fp32_kv_cache_replay(golden_dir):
+    """The fp32 KV cache (kv_dtype=torch.float32) stays available; the default parity cache is fp16."""
+    g = np.load(golden_dir / "gpt_wide2.npz")
+    cfg, sd, cam, bev, batch, eng, B = _case("wide2")
+    forced = cam.reshape(B, -1)[:, cfg.forward_shuffle_idx]
+    toks, trace = GPTSampler(eng, B, kv_dtype=torch.float32).sample(bev, batch, forced_tokens=forced, trace_logits=True)
+    torch.cuda.synchronize()
+    steps = cfg.backward_shuffle_idx[g["rows"]]
+    err = np.abs(trace[steps].permute(1, 0, 2).cpu().numpy() - g["logits_s"])
+    print(f"[wide2] fp32 KV-cache replay: max {err.max():.2e} mean {err.mean():.2e}")
+    assert err.max() < 1e-3
 
 
 def test_bf16_fast_mode_replay_budget(golden_dir):

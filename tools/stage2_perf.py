@@ -36,7 +36,7 @@ def timed(fn, n):
     return a.elapsed_time(b) / n
 
 
-def run(precision, B=16, layers=24, fwd_iters=3, sample=True):
+def run(precision, B=16, layers=24, fwd_iters=3, sample=True, kv_dtype=None, use_pdl=True):
     cfg = GPTConfig(**{**KW, "num_layers": layers})
     t0 = time.time()
     sd = synth.gpt_state_dict(sizes(cfg), seed=2)
@@ -61,7 +61,8 @@ def run(precision, B=16, layers=24, fwd_iters=3, sample=True):
     afl = 4.0 * B * d * eng._allowed
     res["attention_layer"] = {"ms": ams, "allowed_tflops": afl / ams / 1e9, "dense_equiv_tflops": 4.0 * B * cfg.gpt_block_size ** 2 * d / ams / 1e9}
     if sample:
-        sampler = GPTSampler(eng, B)
+        sampler = GPTSampler(eng, B, kv_dtype=kv_dtype)
+        sampler.use_pdl = use_pdl
         sampler.sample(bev, batch, temperature=1.0, top_k=100, seed=1, steps=64)         # warm-up + graph capture
         ops.Stats.reset()
         torch.cuda.synchronize()
@@ -73,7 +74,7 @@ def run(precision, B=16, layers=24, fwd_iters=3, sample=True):
         torch.cuda.synchronize()
         ms = a.elapsed_time(b)
         byt = sampler.bytes_per_batch()
-        res["sample"] = {"ms": ms, "wall_s": time.time() - t0, "images_per_s": B * 6 / ms * 1e3, "ms_per_token_step": ms / 1536,
+        res["sample"] = {"kv_dtype": str(kv_dtype or "default"), "pdl": use_pdl, "ms": ms, "wall_s": time.time() - t0, "images_per_s": B * 6 / ms * 1e3, "ms_per_token_step": ms / 1536,
                          "algorithmic_GB": byt / 1e9, "achieved_GBps": byt / ms / 1e6, "tokens_ok": bool(int(toks.max()) < 1024)}
     return res
 
@@ -81,7 +82,13 @@ def run(precision, B=16, layers=24, fwd_iters=3, sample=True):
 if __name__ == "__main__":
     out = []
     for prec in sys.argv[1:] or ["fp32x3", "bf16"]:
-        r = run(prec)
+        kv = None
+        if prec.endswith("+kv16"):
+            prec, kv = prec[:-5], torch.float16
+        pdl = True
+        if prec.endswith("-pdl"):
+            prec, pdl = prec[:-4], False
+        r = run(prec, kv_dtype=kv, use_pdl=pdl, fwd_iters=1 if (kv or not pdl) else 3)
         print(json.dumps(r), flush=True)
         out.append(r)
     Path(ROOT / "gpurun_out").mkdir(exist_ok=True)
