@@ -171,7 +171,8 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 // added BEFORE the 1/sqrt(d_head) scale), block softmax and P.V (thread = channel) then run out of shared memory; the CTA leaves an
 // (m, l, o[64]) partial and the last CTA to arrive per (batch, head) merges them: x1 = y + concat_heads(softmax(...) V)
 // (flash-decoding with a fused combine).  Optionally the last head of a batch row applies LayerNorm (ln2) to the finished row.
-template <typename KVT>
+// CK = keys per CTA: 128 (fp32 cache: 64 KB of slabs) or 256 (2-byte caches: the same 64 KB, half as many CTAs, every thread owns a key).
+template <typename KVT, int CK>
 __global__ void __launch_bounds__(256) dec_attn_kernel(const float* __restrict__ qkv_part, int ks, long long zstride,
                                                        const float* __restrict__ bqkv, const float* __restrict__ y,
                                                        const float* __restrict__ bias, int bias_ld, KVT* __restrict__ kc,
@@ -181,9 +182,9 @@ __global__ void __launch_bounds__(256) dec_attn_kernel(const float* __restrict__
                                                        const float* __restrict__ ln_gamma, const float* __restrict__ ln_beta, float ln_eps,
                                                        uint16_t* __restrict__ ln_hi, uint16_t* __restrict__ ln_lo) {
   extern __shared__ __align__(128) uint8_t dsm[];
-  KVT* Ks = reinterpret_cast<KVT*>(dsm);                                  // [64][pitch]
-  KVT* Vs = reinterpret_cast<KVT*>(dsm + 64 * DEC_CHUNK * sizeof(KVT));   // [keys][64]
-  __shared__ float q[64], knew[64], vnew[64], red[8], sc[DEC_CHUNK];
+  KVT* Ks = reinterpret_cast<KVT*>(dsm);                                  // [CK / 128 cache blocks][64][128]
+  KVT* Vs = reinterpret_cast<KVT*>(dsm + 64 * CK * sizeof(KVT));          // [keys][64]
+  __shared__ float q[64], knew[64], vnew[64], red[8], sc[CK];
   __shared__ float opart[4][64];
   __shared__ __align__(8) uint64_t bar;
   __shared__ unsigned int ticket;
@@ -194,18 +195,19 @@ __global__ void __launch_bounds__(256) dec_attn_kernel(const float* __restrict__
   // the immediate predecessor runs), so the whole K/V slab of the CTA is already in flight while the GEMM drains.
   const int r = nc + *step_ptr - 1;
   const int n = r + 1;
-  const int j0 = sp * DEC_CHUNK;
-  const int cnt = max(0, min(n - j0, DEC_CHUNK));          // valid keys of this CTA (key r included if in range)
+  const int j0 = sp * CK;
+  const int cnt = max(0, min(n - j0, CK));                 // valid keys of this CTA (key r included if in range)
   const int pitch = (cnt + 7) & ~7;                        // copied keys: 16-byte granules; stale tail entries are never used
-  const bool owns_new = (r >= j0 && r < j0 + DEC_CHUNK);
+  const bool owns_new = (r >= j0 && r < j0 + CK);
   const size_t bh = (size_t)b * H + h;
   if (tid == 0) {
     mbar_init(&bar, 1);
     fence_barrier_init();
     if (cnt > 0) {
-      const uint32_t kbytes = 64u * DEC_CHUNK * (uint32_t)sizeof(KVT), vbytes = (uint32_t)pitch * 64u * (uint32_t)sizeof(KVT);
+      const uint32_t kblocks = (uint32_t)((cnt + DEC_CHUNK - 1) / DEC_CHUNK);          // 128-key cache blocks touched (consecutive in memory)
+      const uint32_t kbytes = kblocks * 64u * DEC_CHUNK * (uint32_t)sizeof(KVT), vbytes = (uint32_t)pitch * 64u * (uint32_t)sizeof(KVT);
       mbar_expect_tx(&bar, kbytes + vbytes);
-      bulk_g2s(Ks, kc + k_index(bh, 0, j0, Lmax), kbytes, &bar);           // whole 128-key K^T block: one contiguous copy
+      bulk_g2s(Ks, kc + k_index(bh, 0, j0, Lmax), kbytes, &bar);           // whole 128-key K^T blocks: one contiguous copy
       bulk_g2s(Vs, vc + (bh * Lmax + j0) * 64, vbytes, &bar);
     }
   }
@@ -229,17 +231,18 @@ __global__ void __launch_bounds__(256) dec_attn_kernel(const float* __restrict__
   if (cnt > 0) {
     mbar_wait(&bar, 0);
     if (owns_new && tid < 64) {        // the slab may hold a stale copy of the newest key: take it from registers instead
-      kv_store(Ks + tid * DEC_CHUNK + (r - j0), knew[tid]);
+      kv_store(Ks + (((r - j0) >> 7) * 64 + tid) * DEC_CHUNK + ((r - j0) & 127), knew[tid]);
       kv_store(Vs + (size_t)(r - j0) * 64 + tid, vnew[tid]);
     }
     __syncthreads();
     const float* brow = bias ? bias + (size_t)r * bias_ld + j0 : nullptr;
     if (tid < cnt) {
       float d0 = 0.f, d1 = 0.f;
+      const KVT* kcol = Ks + (tid >> 7) * 64 * DEC_CHUNK + (tid & 127);       // this key's column inside its cache block
 #pragma unroll
       for (int c = 0; c < 64; c += 2) {
-        d0 = fmaf(q[c], kv_load(Ks + c * DEC_CHUNK + tid), d0);
-        d1 = fmaf(q[c + 1], kv_load(Ks + (c + 1) * DEC_CHUNK + tid), d1);
+        d0 = fmaf(q[c], kv_load(kcol + c * DEC_CHUNK), d0);
+        d1 = fmaf(q[c + 1], kv_load(kcol + (c + 1) * DEC_CHUNK), d1);
       }
       m = ((d0 + d1) + (brow ? brow[tid] : 0.f)) * scale;
     }
@@ -486,7 +489,7 @@ int launch_kv_store(const uint16_t* hi, const uint16_t* lo, void* kc, void* vc, 
   else kv_store_kernel<float><<<grid, 256, 0, st>>>(hi, lo, (float*)kc, (float*)vc, Lp, nrows, H, d, Lmax);
   return cudaGetLastError() == cudaSuccess ? BEVGEN_OK : BEVGEN_ERR_CUDA;
 }
-static inline int dec_splits(int Lmax) { return (Lmax + DEC_CHUNK - 1) / DEC_CHUNK; }
+static inline int dec_splits(int Lmax, int ck = DEC_CHUNK) { return (Lmax + ck - 1) / ck; }
 int dec_attn_workspace_floats(int B, int H) { return B * H * DEC_MAX_SPLIT * DEC_WS; }
 
 int launch_dec_attn(const float* qkv_part, int ks, long long zstride, const float* bqkv, const float* y, const float* bias, int bias_ld,
@@ -495,24 +498,33 @@ int launch_dec_attn(const float* qkv_part, int ks, long long zstride, const floa
                     uint16_t* ln_hi, uint16_t* ln_lo, int /*sm_count*/, cudaStream_t st) {
   if (Lmax > DEC_MAXL || B < 1 || B > 65535 || d != H * 64 || (Lmax & 127) || dec_splits(Lmax) > DEC_MAX_SPLIT) return BEVGEN_ERR_ARG;
   if (ln_gamma != nullptr && (!row_counters || !ln_beta || !ln_hi || d > 1024)) return BEVGEN_ERR_ARG;
-  dim3 grid(H, B, dec_splits(Lmax));
+  dim3 grid(H, B, dec_splits(Lmax, kv_bf16 ? 256 : DEC_CHUNK));
+  if (kv_bf16) {
+    static bool configured2 = false;
+    if (!configured2) {
+      if (cudaFuncSetAttribute(dec_attn_kernel<__half, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 64 * 256 * 2) != cudaSuccess ||
+          cudaFuncSetAttribute(dec_attn_kernel<__nv_bfloat16, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 64 * 256 * 2) != cudaSuccess)
+        return BEVGEN_ERR_CUDA;
+      configured2 = true;
+    }
+  }
   if (kv_bf16 == 2) {           // fp16 cache: half the KV bytes of the fp32 cache at ~3e-4 logit error (tests/test_decode_gpu.py)
-    const int smem = 2 * 64 * DEC_CHUNK * 2;
-    if (launch_k(dec_attn_kernel<__half>, grid, dim3(256), smem, st, qkv_part, ks, zstride, bqkv, y, bias, bias_ld, (__half*)kc, (__half*)vc, x1, step_ptr,
+    const int smem = 2 * 64 * 256 * 2;
+    if (launch_k(dec_attn_kernel<__half, 256>, grid, dim3(256), smem, st, qkv_part, ks, zstride, bqkv, y, bias, bias_ld, (__half*)kc, (__half*)vc, x1, step_ptr,
                  ws, counters, nc, H, d, Lmax, scale, row_counters, ln_gamma, ln_beta, ln_eps, ln_hi, ln_lo) != cudaSuccess) return BEVGEN_ERR_CUDA;
   } else if (kv_bf16) {
-    const int smem = 2 * 64 * DEC_CHUNK * 2;
-    if (launch_k(dec_attn_kernel<__nv_bfloat16>, grid, dim3(256), smem, st, qkv_part, ks, zstride, bqkv, y, bias, bias_ld, (__nv_bfloat16*)kc,
+    const int smem = 2 * 64 * 256 * 2;
+    if (launch_k(dec_attn_kernel<__nv_bfloat16, 256>, grid, dim3(256), smem, st, qkv_part, ks, zstride, bqkv, y, bias, bias_ld, (__nv_bfloat16*)kc,
                  (__nv_bfloat16*)vc, x1, step_ptr, ws, counters, nc, H, d, Lmax, scale, row_counters, ln_gamma, ln_beta, ln_eps, ln_hi, ln_lo) !=
         cudaSuccess) return BEVGEN_ERR_CUDA;
   } else {
     const int smem = 2 * 64 * DEC_CHUNK * 4;
     static bool configured = false;
     if (!configured) {
-      if (cudaFuncSetAttribute(dec_attn_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return BEVGEN_ERR_CUDA;
+      if (cudaFuncSetAttribute(dec_attn_kernel<float, DEC_CHUNK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return BEVGEN_ERR_CUDA;
       configured = true;
     }
-    if (launch_k(dec_attn_kernel<float>, grid, dim3(256), smem, st, qkv_part, ks, zstride, bqkv, y, bias, bias_ld, (float*)kc, (float*)vc, x1, step_ptr, ws,
+    if (launch_k(dec_attn_kernel<float, DEC_CHUNK>, grid, dim3(256), smem, st, qkv_part, ks, zstride, bqkv, y, bias, bias_ld, (float*)kc, (float*)vc, x1, step_ptr, ws,
                  counters, nc, H, d, Lmax, scale, row_counters, ln_gamma, ln_beta, ln_eps, ln_hi, ln_lo) != cudaSuccess) return BEVGEN_ERR_CUDA;
   }
   return cudaGetLastError() == cudaSuccess ? BEVGEN_OK : BEVGEN_ERR_CUDA;
