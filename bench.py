@@ -303,7 +303,9 @@ def main():
                                     "roofline": {"bound": "hbm", "achieved": r2["sample"]["achieved_GBps"], "peak": hbm_peak, "unit": "GB/s",
                                                  "frac": r2["sample"]["achieved_GBps"] / hbm_peak,
                                                  "algorithmic_GB_per_batch": r2["sample"]["algorithmic_GB"]}},
-                "note": "full-size GPT (24 layers, d=1024, 16 heads, L=1792); KV-cache sampling of 16 scenes x 1536 tokens, top_k=100"}
+                "generate_configs3": r2.get("generate"),
+                "note": "full-size GPT (24 layers, d=1024, 16 heads, L=1792); KV-cache sampling of 16 scenes x 1536 tokens, top_k=100; "
+                        "parity configuration: bf16x3 weights, fp16 KV cache"}
         except Exception as ex:  # the headline line must still be printed
             line["stage2"] = {"error": repr(ex)}
     if world == 1 and not args.no_cpu_baseline:

@@ -399,8 +399,11 @@ __global__ void __launch_bounds__(256) dec_sample_kernel(const float* __restrict
   if (probs_out != nullptr)
     for (int i = tid; i < V; i += 256) probs_out[(size_t)b * V + i] = lg[i] / total;
   int token = 0;
-  if (forced != nullptr) {
-    token = (int)forced[(size_t)b * n_img + s];
+  // forced[b][s] >= 0: teacher forcing / partial decoding (the token is given: ground-truth cameras of
+  // cond_transformer_multi_view.py:161-165,181-182); negative entries are sampled like everything else.  Uniform per CTA.
+  const long long fz = (forced != nullptr) ? forced[(size_t)b * n_img + s] : -1;
+  if (fz >= 0) {
+    token = (int)fz;
   } else if (greedy) {
     // argmax, lowest index on ties
     float best = -1.f;

@@ -221,7 +221,9 @@ BEVGEN_API int bevgen_dec_attention(const float* qkv_partials, int ks, long long
                                     int lmax, float scale, unsigned int* row_counters, const float* ln_gamma, const float* ln_beta, float ln_eps,
                                     void* ln_hi, void* ln_lo, void* stream);
 BEVGEN_API int bevgen_dec_attention_workspace_floats(int batch, int heads);
-/* sampling tail (cond_transformer_multi_view.py:138-142,200-219): logits/T, top-k (ties kept), softmax, multinomial|greedy|forced */
+/* sampling tail (cond_transformer_multi_view.py:138-142,200-219): logits/T, top-k (ties kept), softmax, multinomial|greedy|forced.
+ * forced_tokens[batch][n_img] (decode order, may be NULL): entries >= 0 replace the drawn token (teacher-forced replay, partial decoding of
+ * ground-truth cameras :161-165,181-182); negative entries are sampled. */
 BEVGEN_API int bevgen_sample_topk(const float* logit_partials, int ks, long long zstride, int vpad, int vocab, float temperature, int top_k,
                                   int greedy, unsigned long long seed, const long long* forced_tokens, const int* forward_shuffle_idx,
                                   long long* cam_idx, long long* tokens_out, float* logits_trace, float* probs_out, const int* step_ptr, int batch,

@@ -97,11 +97,20 @@ class Net2NetTransformer(_Base):
         B = x.shape[0]
         if self.skip_sampling:
             return torch.zeros((B, self.cfg.num_cams, self.cfg.num_cam_tokens), dtype=torch.int64, device=c.device)
-        if partial_decoding_idx is not None:
-            raise NotImplementedError("partial decoding (conditioning on ground-truth cameras) is not implemented yet")
         assert not self.transformer.training
+        forced = None
+        if partial_decoding_idx is not None:
+            # the listed cameras keep their ground-truth tokens (reference :161-165) and are skipped by the loop (:181-182); under the
+            # causal mask this is exactly a forced token at their decode positions and a sampled one everywhere else
+            _, z_indices = self.encode_to_z(self.get_input(self.first_stage_key, batch).to(c.device), batch)
+            z_indices = self.expand_all_images(z_indices)                                   # (B, cams, tokens)
+            given = torch.full_like(z_indices, -1)
+            given[:, list(partial_decoding_idx), :] = z_indices[:, list(partial_decoding_idx), :]
+            fwd = torch.as_tensor(self.cfg.forward_shuffle_idx, device=c.device, dtype=torch.int64)
+            forced = given.reshape(B, -1)[:, fwd].contiguous()                              # decode order
         seed = self.sample_seed if self.sample_seed is not None else int(torch.randint(0, 2 ** 62, (1,)).item())
-        out = self.transformer.sampler(B).sample(c, batch, temperature=temperature, top_k=top_k, greedy=not sample, seed=seed)
+        out = self.transformer.sampler(B).sample(c, batch, temperature=temperature, top_k=top_k, greedy=not sample, seed=seed,
+                                                 forced_tokens=forced)
         assert out.max() < self.cfg.vocab_size
         return out
 

@@ -74,6 +74,31 @@ def test_sample_and_log_images(model):
     assert torch.isfinite(model.last_test_loss)
 
 
+def test_partial_decoding_keeps_given_cameras_and_is_consistent(model):
+    """partial_decoding_idx (reference :161-165,181-182): the listed cameras keep their ground-truth tokens, the others are decoded
+    conditioned on them.  Consistency: under the causal mask the greedy token at every decoded position must be the argmax of the
+    teacher-forced logits of the finished sequence (near-ties excepted)."""
+    batch = _batch()
+    x, c = model.get_xc(batch)
+    _, c_idx = model.encode_to_c(c.cuda(), batch)
+    _, z = model.encode_to_z(x.cuda(), batch)
+    z = z.view(1, 6, 256)
+    given = [0, 3]
+    toks = model.sample(torch.zeros(1, 0), c_idx, batch, sample=False, partial_decoding_idx=given)
+    assert toks.shape == (1, 6, 256) and int(toks.max()) < 1024 and int(toks.min()) >= 0
+    assert torch.equal(toks[:, given], z[:, given])
+    free = [i for i in range(6) if i not in given]
+    assert not torch.equal(toks[:, free], z[:, free])
+    logits = model.transformer(toks.clone(), c_idx, batch, sampling=True).view(1, 6, 256, -1)      # (cam,h,w) order
+    top2 = logits.topk(2, dim=-1)
+    clear = (top2.values[..., 0] - top2.values[..., 1]) > 1e-3                                     # positions without a near-tie
+    agree = (top2.indices[..., 0] == toks)[:, free][clear[:, free]]
+    assert agree.numel() > 500 and bool(agree.all())
+    # and without partial decoding nothing is pinned
+    plain = model.sample(torch.zeros(1, 0), c_idx, batch, sample=False)
+    assert not torch.equal(plain[:, given], z[:, given])
+
+
 def test_no_cpu_fallback():
     cfg = GPTConfig(**GPT_SMALL)
     gpt = GPT(cfg)

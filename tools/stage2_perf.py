@@ -74,6 +74,16 @@ def run(precision, B=16, layers=24, fwd_iters=3, sample=True, kv_dtype=None, use
         torch.cuda.synchronize()
         ms = a.elapsed_time(b)
         byt = sampler.bytes_per_batch()
+        # full generation (configs[3]): tokens -> codebook gather -> VQGAN decoder -> denormalise, 6 images per scene
+        from bevgen_b200.vqgan_engine import VQGANEngine
+        dd = synth.vqgan_ddconfig()
+        vq = VQGANEngine(synth.vqgan_state_dict(dd, seed=1), dd, device="cuda:0", precision="bf16" if precision == "bf16" else "f16f8")
+        idx = toks.reshape(-1).contiguous()
+        dec = lambda: vq.decode_indices(idx, B * 6, 16, 16)
+        dec()
+        dms = timed(dec, 2)
+        res["generate"] = {"sample_ms": ms, "vqgan_decode_ms": dms, "images_per_s": B * 6 / (ms + dms) * 1e3,
+                           "note": "KV-cache sampling of B scenes + VQGAN decode of their 6 x 256x256 images (the generate.py hot path)"}
         res["sample"] = {"kv_dtype": str(kv_dtype or "default"), "pdl": use_pdl, "ms": ms, "wall_s": time.time() - t0, "images_per_s": B * 6 / ms * 1e3, "ms_per_token_step": ms / 1536,
                          "algorithmic_GB": byt / 1e9, "achieved_GBps": byt / ms / 1e6, "tokens_ok": bool(int(toks.max()) < 1024)}
     return res
