@@ -6,7 +6,7 @@
 //   warp 0      TMA producer: Q once, K/V tiles through a 2-stage ring, all boxes (64 cols x 128 rows) of the fused qkv planes
 //   warp 1      tcgen05 issuer: S = Q.K^T into a double-buffered TMEM tile, PV = P.V (V read MN-major, no transpose) into a second
 //   warp 2      TMEM allocator
-//   warps 4-11  softmax: thread = (query row, 64-key half): tcgen05.ld S, + fp16 bias row, base-2 online softmax, P -> swizzled smem
+//   warps 4-19  softmax: thread = (query row, 32-key quarter): tcgen05.ld S, + fp16 bias row, base-2 online softmax, P -> swizzled smem
 //               as the A operand of the PV MMA, running O kept in registers (rescaled on the fly), final normalise + residual store.
 // NPASS = 3 keeps fp32-equivalent accuracy (bf16x3 split products for both MMAs, P split into hi/lo); NPASS = 1 is plain bf16.
 #include <cuda_fp16.h>
@@ -19,7 +19,9 @@ namespace bevgen {
 constexpr int AT_BM = 128, AT_BN = 128, AT_DH = 64;
 constexpr int AT_TILE = AT_BM * AT_DH * 2;       // 16 KB: one (128 x 64) bf16 tile
 constexpr int AT_PTILE = AT_BM * AT_BN * 2;      // 32 KB: P (128 x 128) bf16
-constexpr int AT_THREADS = 384;
+constexpr int AT_NPART = 4;                       // softmax threads per query row: each owns 128 / 4 = 32 keys and 64 / 4 = 16 output channels
+constexpr int AT_KPT = AT_BN / AT_NPART, AT_CPT = AT_DH / AT_NPART;
+constexpr int AT_THREADS = 128 + 128 * AT_NPART;  // 4 control warps + 16 softmax warps
 
 template <int NPASS>
 struct AttnCfg {
@@ -27,12 +29,14 @@ struct AttnCfg {
   static constexpr int Q_BYTES = NOPS * AT_TILE;
   static constexpr int KV_STAGE = 2 * NOPS * AT_TILE;           // K + V
   static constexpr int P_BYTES = NOPS * AT_PTILE;
-  static constexpr int SMEM = Q_BYTES + 2 * KV_STAGE + P_BYTES + 1024 + 256 + 128 * 2 * 4;
+  static constexpr int ALIGN_SLACK = (NPASS == 3) ? 768 : 1024;          // NPASS 3 sits 256 B under the 227 KB limit: the kernel traps if the
+                                                                         // dynamic window is less than 256-byte aligned (it starts 1 KB-aligned)
+  static constexpr int SMEM = Q_BYTES + 2 * KV_STAGE + P_BYTES + ALIGN_SLACK + 256 + 128 * AT_NPART * 4;
 };
 
 struct AttnParams {
   CUtensorMap tm[2];        // hi, lo planes of qkv viewed as [B*L rows][3d cols], box (64, 128)
-  const __half* bias;       // [L][L] fp16 or null
+  const uint4* bias;        // tiled, pre-scaled camera bias (see bevgen_attn_fused_fwd) or null
   const float* y;           // [B][L][d]
   float* x1;                // [B][L][d]
   int B, H, L, nc, d;
@@ -40,6 +44,16 @@ struct AttnParams {
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+// 2^x on the MUFU unit (~2 ulp, flushes denormal results): one instruction instead of exp2f's range-handling sequence
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// (v0, v1) -> packed bf16 pair hi (one cvt) and the packed pair of the remainders lo = v - hi
+__device__ __forceinline__ void split_bf16x2(float v0, float v1, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xffff0000u);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(v0 - h0, v1 - h1);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
 
 template <int NPASS>
 __global__ void __launch_bounds__(AT_THREADS, 1) attn_fused_kernel(const __grid_constant__ AttnParams p) {
@@ -47,6 +61,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fused_kernel(const __grid_
   constexpr int NOPS = Cfg::NOPS;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  if ((int)(smem - smem_raw) > Cfg::ALIGN_SLACK) __trap();
   uint8_t* sQ = smem;
   uint8_t* sKV = sQ + Cfg::Q_BYTES;
   uint8_t* sP = sKV + 2 * Cfg::KV_STAGE;
@@ -62,7 +77,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fused_kernel(const __grid_
   uint64_t* pv_done = bars + 12;      // 2
   uint64_t* pv_empty = bars + 14;     // 2
   uint32_t* tmem_slot = (uint32_t*)(bars + 18);
-  float* xmax = (float*)(bars + 32);  // [128 rows][2 halves]
+  float* xmax = (float*)(bars + 32);  // [128 rows][AT_NPART]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nq = p.L / AT_BM;
@@ -82,10 +97,10 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fused_kernel(const __grid_
     mbar_init(q_full, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&k_full[i], 1); mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); mbar_init(&k_empty[i], 1);
-      mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 8);
-      mbar_init(&pv_done[i], 1); mbar_init(&pv_empty[i], 8);
+      mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4 * AT_NPART);
+      mbar_init(&pv_done[i], 1); mbar_init(&pv_empty[i], 4 * AT_NPART);
     }
-    mbar_init(p_full, 8);
+    mbar_init(p_full, 4 * AT_NPART);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);
@@ -114,30 +129,40 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fused_kernel(const __grid_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    // The whole warp runs the warp-uniform control flow (barrier addresses and descriptors stay in uniform registers) and one elected
+    // lane issues the MMAs / commits; descriptors are a constant high word + (address >> 4), so per-k variants are plain increments.
+    // (A lane-0-only branch built each of the 36 descriptors per key tile through R2UR chains and made the issuing thread the limiter.)
+    {
+      uint32_t el;
+      asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(el));
+      const bool elected = el != 0;
       const uint32_t idesc_s = make_idesc_bf16(AT_BM, AT_BN, 0, 0);
       const uint32_t idesc_pv = make_idesc_bf16(AT_BM, AT_DH, 0, 1);
-      const uint32_t q_base = smem_u32(sQ), p_base = smem_u32(sP);
+      const uint64_t qd = make_sdesc_sw128(smem_u32(sQ), 16, 1024);               // K-major: k-step = +32 B
+      const uint64_t kd0 = make_sdesc_sw128(smem_u32(sKV), 16, 1024);
+      const uint64_t pd = make_sdesc_sw128(smem_u32(sP), 16, 1024);
+      const uint64_t vd0 = make_sdesc_sw128(smem_u32(sKV) + NOPS * AT_TILE, 8192, 1024);   // MN-major V: k-step = 16 rows = +2048 B
+      constexpr uint64_t LO = AT_TILE >> 4, PLO = AT_PTILE >> 4, STG = Cfg::KV_STAGE >> 4;
       auto issue_s = [&](int t) {
         const int s = t & 1;
         mbar_wait(&k_full[s], (t >> 1) & 1);
         mbar_wait(&s_empty[s], ((t >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t k_base = smem_u32(sKV + s * Cfg::KV_STAGE);
+        if (elected) {
+          const uint64_t kd = kd0 + (uint64_t)s * STG;
 #pragma unroll
-        for (int k = 0; k < AT_DH / 16; ++k) {
-          const uint64_t qh = make_sdesc_sw128(q_base + k * 32, 16, 1024), kh = make_sdesc_sw128(k_base + k * 32, 16, 1024);
-          if (NPASS == 3) {
-            const uint64_t ql = make_sdesc_sw128(q_base + AT_TILE + k * 32, 16, 1024), kl = make_sdesc_sw128(k_base + AT_TILE + k * 32, 16, 1024);
-            umma_bf16(tS[s], ql, kh, idesc_s, k == 0 ? 0u : 1u);
-            umma_bf16(tS[s], qh, kl, idesc_s, 1u);
-            umma_bf16(tS[s], qh, kh, idesc_s, 1u);
-          } else {
-            umma_bf16(tS[s], qh, kh, idesc_s, k == 0 ? 0u : 1u);
+          for (int k = 0; k < AT_DH / 16; ++k) {
+            if (NPASS == 3) {
+              umma_bf16(tS[s], qd + LO + k * 2, kd + k * 2, idesc_s, k == 0 ? 0u : 1u);
+              umma_bf16(tS[s], qd + k * 2, kd + LO + k * 2, idesc_s, 1u);
+              umma_bf16(tS[s], qd + k * 2, kd + k * 2, idesc_s, 1u);
+            } else {
+              umma_bf16(tS[s], qd + k * 2, kd + k * 2, idesc_s, k == 0 ? 0u : 1u);
+            }
           }
+          umma_commit(&s_full[s]);
+          umma_commit(&k_empty[s]);
         }
-        umma_commit(&s_full[s]);
-        umma_commit(&k_empty[s]);
       };
       mbar_wait(q_full, 0);
       issue_s(0);
@@ -148,58 +173,64 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fused_kernel(const __grid_
         mbar_wait(&v_full[s], (t >> 1) & 1);
         mbar_wait(&pv_empty[s], ((t >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t v_base = smem_u32(sKV + s * Cfg::KV_STAGE + NOPS * AT_TILE);
+        if (elected) {
+          const uint64_t vd = vd0 + (uint64_t)s * STG;
 #pragma unroll
-        for (int k = 0; k < AT_BN / 16; ++k) {
-          const uint32_t pa = p_base + (k >> 2) * AT_TILE + (k & 3) * 32;      // two 64-key chunks of 128 rows x 128 B
-          const uint64_t ph = make_sdesc_sw128(pa, 16, 1024), vh = make_sdesc_sw128(v_base + k * 2048, 8192, 1024);
-          if (NPASS == 3) {
-            const uint64_t pl = make_sdesc_sw128(pa + AT_PTILE, 16, 1024), vl = make_sdesc_sw128(v_base + AT_TILE + k * 2048, 8192, 1024);
-            umma_bf16(tPV[s], pl, vh, idesc_pv, k == 0 ? 0u : 1u);
-            umma_bf16(tPV[s], ph, vl, idesc_pv, 1u);
-            umma_bf16(tPV[s], ph, vh, idesc_pv, 1u);
-          } else {
-            umma_bf16(tPV[s], ph, vh, idesc_pv, k == 0 ? 0u : 1u);
+          for (int k = 0; k < AT_BN / 16; ++k) {
+            const uint64_t pa = pd + (uint64_t)((k >> 2) * (AT_TILE >> 4) + (k & 3) * 2);      // two 64-key chunks of 128 rows x 128 B
+            const uint64_t va = vd + (uint64_t)(k * (2048 >> 4));
+            if (NPASS == 3) {
+              umma_bf16(tPV[s], pa + PLO, va, idesc_pv, k == 0 ? 0u : 1u);
+              umma_bf16(tPV[s], pa, va + LO, idesc_pv, 1u);
+              umma_bf16(tPV[s], pa, va, idesc_pv, 1u);
+            } else {
+              umma_bf16(tPV[s], pa, va, idesc_pv, k == 0 ? 0u : 1u);
+            }
           }
+          umma_commit(&pv_done[s]);
+          umma_commit(&v_empty[s]);
         }
-        umma_commit(&pv_done[s]);
-        umma_commit(&v_empty[s]);
       }
     }
   } else if (warp >= 4) {
     // ===================== softmax / output warps =====================
+    // 16 warps: thread = (query row, quarter `part` of the 128-key tile / of the 64 output channels).  (With 8 warps and 64 keys per thread
+    // the per-thread instruction stream - ~1000 instructions per key tile at two warps per scheduler - was the limiter of the kernel.)
     const int sw = warp - 4;
     const int quarter = warp & 3;                  // TMEM lane quarter accessible by this warp (warp index % 4)
-    const int half = sw >> 2;                      // which 64 keys of the 128-key tile / which 32 of the 64 output channels
+    const int part = sw >> 2;                      // which 32 keys of the 128-key tile / which 16 of the 64 output channels
     const int row = quarter * 32 + lane;           // query row within the tile
     const int gi = m0 + row;                       // sequence position
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-    float o_acc[32];
+    float o_acc[AT_CPT];
 #pragma unroll
-    for (int c = 0; c < 32; ++c) o_acc[c] = 0.f;
+    for (int c = 0; c < AT_CPT; ++c) o_acc[c] = 0.f;
     float m_run = -INFINITY, l_run = 0.f, corr_saved = 0.f;
-    const __half* brow = p.bias ? p.bias + (size_t)gi * p.L : nullptr;
+    // bias tile layout [q tile][key tile][part][16-byte unit u][row][8 x fp16], values already multiplied by scale * log2(e): lanes of a
+    // warp (consecutive rows) read consecutive 16-byte pieces, i.e. every load instruction moves four complete 128-byte lines (a row-major
+    // [L][L] table made each instruction touch 32 lines through the 0-KB L1 of this kernel: 12 % of all stall samples in profiles/r01b)
+    const int nkt = p.L / AT_BN;
+    const uint4* brow = p.bias ? p.bias + ((size_t)(m0 / AT_BM) * nkt * AT_NPART + part) * (AT_KPT / 8) * AT_BM + row : nullptr;
+    float* xrow = xmax + row * AT_NPART;
 
     for (int t = 0; t < T; ++t) {
       const int s = t & 1;
-      const int n0 = t * AT_BN + half * 64;
-      // bias row chunk: 64 fp16 = 128 B, issued before waiting on the MMA
-      uint4 bq[8];
+      // bias row chunk: 32 fp16 = 64 B, issued before waiting on the MMA
+      uint4 bq[AT_KPT / 8];
       if (brow != nullptr) {
-        const uint4* bp = reinterpret_cast<const uint4*>(brow + n0);
+        const uint4* bp = brow + (size_t)t * AT_NPART * (AT_KPT / 8) * AT_BM;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) bq[u] = __ldg(bp + u);
+        for (int u = 0; u < AT_KPT / 8; ++u) bq[u] = __ldg(bp + u * AT_BM);
       }
       mbar_wait(&s_full[s], (t >> 1) & 1);
       tc_fence_after();
-      float tv[64];
+      float tv[AT_KPT];
       {
-        uint32_t r0[32], r1[32];
-        tmem_ld_32x32(tS[s] + lane_off + half * 64, r0);
-        tmem_ld_32x32(tS[s] + lane_off + half * 64 + 32, r1);
+        uint32_t r0[32];
+        tmem_ld_32x32(tS[s] + lane_off + part * AT_KPT, r0);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) { tv[j] = __uint_as_float(r0[j]); tv[32 + j] = __uint_as_float(r1[j]); }
+        for (int j = 0; j < 32; ++j) tv[j] = __uint_as_float(r0[j]);
       }
       tc_fence_before();
       __syncwarp();
@@ -207,31 +238,38 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fused_kernel(const __grid_
       const bool diag = (m0 >= p.nc) && (t == T - 1);       // the only partially masked tile: n0 == m0, allowed iff key <= query
       float mx = -INFINITY;
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
+      for (int u = 0; u < AT_KPT / 8; ++u) {
         const __half2* hb = reinterpret_cast<const __half2*>(&bq[u]);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int j = u * 8 + e * 2;
           float2 bf = brow ? __half22float2(hb[e]) : make_float2(0.f, 0.f);
-          float a0 = (tv[j] + bf.x) * p.scale_log2e, a1 = (tv[j + 1] + bf.y) * p.scale_log2e;
-          if (diag) {
-            if (half * 64 + j > row) a0 = -INFINITY;
-            if (half * 64 + j + 1 > row) a1 = -INFINITY;
-          }
+          const float a0 = fmaf(tv[j], p.scale_log2e, bf.x), a1 = fmaf(tv[j + 1], p.scale_log2e, bf.y);
           tv[j] = a0; tv[j + 1] = a1;
           mx = fmaxf(mx, fmaxf(a0, a1));
         }
       }
-      // exchange the row maximum with the partner thread handling the other 64 keys
-      xmax[row * 2 + half] = mx;
-      named_bar_sync(1 + quarter, 64);
-      mx = fmaxf(mx, xmax[row * 2 + (half ^ 1)]);
-      named_bar_sync(1 + quarter, 64);                      // both partners have read before either slot is rewritten
+      if (diag) {                                            // warp-uniform: only the last tile of an image-row CTA
+        mx = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < AT_KPT; ++j) {
+          if (part * AT_KPT + j > row) tv[j] = -INFINITY;
+          mx = fmaxf(mx, tv[j]);
+        }
+      }
+      // exchange the row maximum with the three partner threads handling the other keys of the row
+      xrow[part] = mx;
+      named_bar_sync(1 + quarter, 32 * AT_NPART);
+      {
+        const float4 m4 = *reinterpret_cast<const float4*>(xrow);
+        mx = fmaxf(fmaxf(m4.x, m4.y), fmaxf(m4.z, m4.w));
+      }
+      named_bar_sync(1 + quarter, 32 * AT_NPART);           // all partners have read before any slot is rewritten
       const float m_new = fmaxf(m_run, mx);                 // finite: every row has key 0 (cond) allowed
-      const float corr = exp2f(m_run - m_new);              // 0 on the first tile
+      const float corr = ex2_approx(m_run - m_new);         // 0 on the first tile
       float psum = 0.f;
 #pragma unroll
-      for (int j = 0; j < 64; ++j) { tv[j] = exp2f(tv[j] - m_new); psum += tv[j]; }
+      for (int j = 0; j < AT_KPT; ++j) { tv[j] = ex2_approx(tv[j] - m_new); psum += tv[j]; }
       l_run = l_run * corr + psum;
       m_run = m_new;
       // fold in the previous tile's P.V (also guarantees the PV MMA finished reading P from smem)
@@ -239,31 +277,26 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fused_kernel(const __grid_
         const int sp = (t - 1) & 1;
         mbar_wait(&pv_done[sp], ((t - 1) >> 1) & 1);
         tc_fence_after();
-        uint32_t r[32];
-        tmem_ld_32x32(tPV[sp] + lane_off + half * 32, r);
+        uint32_t r[16];
+        tmem_ld_32x16(tPV[sp] + lane_off + part * AT_CPT, r);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&pv_empty[sp]);
 #pragma unroll
-        for (int c = 0; c < 32; ++c) o_acc[c] = o_acc[c] * corr_saved + __uint_as_float(r[c]);
+        for (int c = 0; c < AT_CPT; ++c) o_acc[c] = o_acc[c] * corr_saved + __uint_as_float(r[c]);
       }
       corr_saved = corr;
-      // P -> smem, K-major SWIZZLE_128B: row r at r*128 B inside each 64-key chunk, 16-byte unit u stored at u ^ (r & 7)
+      // P -> smem, K-major SWIZZLE_128B: row r at r*128 B inside each 64-key chunk, 16-byte unit u stored at u ^ (r & 7);
+      // this thread's 32 keys are units 4*(part & 1) .. +3 of chunk part >> 1
       {
-        uint8_t* prow = sP + half * AT_TILE + row * 128;
+        uint8_t* prow = sP + (part >> 1) * AT_TILE + row * 128;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < AT_KPT / 8; ++u) {
           uint32_t hh[4], ll[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            __nv_bfloat16 h0, l0, h1, l1;
-            split_bf16(tv[u * 8 + 2 * e], h0, l0);
-            split_bf16(tv[u * 8 + 2 * e + 1], h1, l1);
-            hh[e] = pack_bf16(h0, h1);
-            ll[e] = pack_bf16(l0, l1);
-          }
-          const int us = (u ^ (row & 7)) * 16;
+          for (int e = 0; e < 4; ++e) split_bf16x2(tv[u * 8 + 2 * e], tv[u * 8 + 2 * e + 1], hh[e], ll[e]);
+          const int us = (((part & 1) * 4 + u) ^ (row & 7)) * 16;
           *reinterpret_cast<uint4*>(prow + us) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
           if (NPASS == 3) *reinterpret_cast<uint4*>(prow + AT_PTILE + us) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
         }
@@ -277,21 +310,22 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fused_kernel(const __grid_
       const int sp = (T - 1) & 1;
       mbar_wait(&pv_done[sp], ((T - 1) >> 1) & 1);
       tc_fence_after();
-      uint32_t r[32];
-      tmem_ld_32x32(tPV[sp] + lane_off + half * 32, r);
+      uint32_t r[16];
+      tmem_ld_32x16(tPV[sp] + lane_off + part * AT_CPT, r);
       tmem_ld_wait();
 #pragma unroll
-      for (int c = 0; c < 32; ++c) o_acc[c] = o_acc[c] * corr_saved + __uint_as_float(r[c]);
+      for (int c = 0; c < AT_CPT; ++c) o_acc[c] = o_acc[c] * corr_saved + __uint_as_float(r[c]);
     }
-    // total row sum = own half + partner half
-    xmax[row * 2 + half] = l_run;
-    named_bar_sync(1 + quarter, 64);
-    const float inv = 1.0f / (l_run + xmax[row * 2 + (half ^ 1)]);
-    const size_t off = ((size_t)(b * p.L + gi)) * p.d + h * AT_DH + half * 32;
+    // total row sum over the four partners
+    xrow[part] = l_run;
+    named_bar_sync(1 + quarter, 32 * AT_NPART);
+    const float4 l4 = *reinterpret_cast<const float4*>(xrow);
+    const float inv = 1.0f / ((l4.x + l4.y) + (l4.z + l4.w));
+    const size_t off = ((size_t)(b * p.L + gi)) * p.d + h * AT_DH + part * AT_CPT;
     const float4* yp = reinterpret_cast<const float4*>(p.y + off);
     float4* op = reinterpret_cast<float4*>(p.x1 + off);
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
+    for (int c = 0; c < AT_CPT / 4; ++c) {
       const float4 yv = __ldg(yp + c);
       op[c] = make_float4(yv.x + o_acc[4 * c] * inv, yv.y + o_acc[4 * c + 1] * inv, yv.z + o_acc[4 * c + 2] * inv, yv.w + o_acc[4 * c + 3] * inv);
     }
@@ -320,7 +354,7 @@ int launch_attn_fused(const CUtensorMap* tm_hi, const CUtensorMap* tm_lo, const 
   AttnParams p;
   p.tm[0] = *tm_hi;
   p.tm[1] = tm_lo ? *tm_lo : *tm_hi;
-  p.bias = (const __half*)bias_f16;
+  p.bias = (const uint4*)bias_f16;
   p.y = y; p.x1 = x1;
   p.B = B; p.H = H; p.L = L; p.nc = nc; p.d = d;
   p.scale_log2e = scale * 1.4426950408889634f;

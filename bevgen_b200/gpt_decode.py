@@ -59,8 +59,8 @@ class GPTSampler:
         self.bias_cc = None if e.bias is None else e.bias[: e.nc, : e.nc].contiguous()
         self.mask_cc = e.mask_u8[: e.nc, : e.nc].contiguous()
         full_cc = bool(self.mask_cc.all())      # cond rows see every cond column: the fused kernel's "all cond" case
-        self.bias_cc_f16 = (torch.zeros((e.nc, e.nc), dtype=torch.float16, device=dev) if self.bias_cc is None
-                            else self.bias_cc.to(torch.float16).contiguous()) if full_cc else None
+        self.bias_cc_f16 = ops.tile_attention_bias(torch.zeros((e.nc, e.nc), device=dev) if self.bias_cc is None else self.bias_cc,
+                                                   float(e.dh) ** -0.5) if (full_cc and e.nc % 128 == 0) else None
         self.attn_ws = f32(_lib.load().bevgen_dec_attention_workspace_floats(B, H))
         self.attn_cnt = torch.zeros(B * H, dtype=torch.int32, device=dev)
         self.row_cnt = torch.zeros(B, dtype=torch.int32, device=dev)

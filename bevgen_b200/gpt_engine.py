@@ -91,7 +91,8 @@ class GPTEngine:
         i, j = torch.meshgrid(torch.arange(self.L), torch.arange(self.L), indexing="ij")
         closed = (j < self.nc) | ((i >= self.nc) & (j <= i))
         self.causal = bool(torch.equal(closed, cfg.attention_mask.bool() | closed) and self.npad == 0)   # mask ⊆ [cond | causal]
-        self.bias_f16 = None if self.bias is None else self.bias.to(torch.float16).contiguous()
+        # tiled, pre-scaled fp16 copy for the fused kernel (coalesced 16-byte reads per lane, scale folded into one FFMA per score)
+        self.bias_f16 = None if (self.bias is None or self.L % 128) else ops.tile_attention_bias(self.bias, float(self.dh) ** -0.5)
         self.fused_attention = True          # tcgen05 flash-style kernel when the geometry allows; composed path otherwise
         self._perm_cache = {}
         self._allowed = float(self.mask_u8.sum().item())      # attended (row, col) pairs: algorithmic attention work

@@ -233,6 +233,16 @@ def attn_softmax(S, bias, mask_u8, out_hi, out_lo, L, scale):
                                        _stream()), "attn_softmax")
 
 
+def tile_attention_bias(bias: torch.Tensor, scale: float) -> torch.Tensor:
+    """[L][L] fp32 camera bias -> the tiled, pre-scaled fp16 table bevgen_attn_fused_fwd reads:
+    out[qt][kt][p][u][r][e] = fp16(scale * log2(e) * bias[128 qt + r][128 kt + 32 p + 8 u + e])."""
+    L = bias.shape[0]
+    assert bias.shape == (L, L) and L % 128 == 0
+    n = L // 128
+    b = (bias.float() * (scale * 1.4426950408889634)).to(torch.float16)
+    return b.view(n, 128, n, 4, 4, 8).permute(0, 2, 3, 4, 1, 5).contiguous()
+
+
 def attn_fused_fwd(qkv_hi, qkv_lo, B, L, H, d, n_cond, bias_f16, y, x1, scale, npass, algo_flops=0.0):
     lib = _lib.init()
     _chk_cuda(qkv_hi, qkv_lo, bias_f16, y, x1)

@@ -190,10 +190,12 @@ BEVGEN_API int bevgen_attn_softmax(const float* s, const float* bias, const unsi
 
 /* Fused attention forward (one kernel for sparse_self_attention.py:153-176 + the residual add of mingpt_sparse.py:250):
  *   x1[b,i,h*64:(h+1)*64] = y[...] + sum_j softmax_j(scale * (q_i.k_j + bias[i][j])) v_j,  allowed(i,j) = j < n_cond || (i >= n_cond && j <= i)
- * q/k/v are the column blocks [0,d), [d,2d), [2d,3d) of the fused qkv bf16 planes [batch][seq_len][3d]; bias is fp16 [seq_len][seq_len]
- * (pre-scale, shared by batch and heads) or NULL.  seq_len and n_cond must be multiples of 128, d = heads*64. */
+ * q/k/v are the column blocks [0,d), [d,2d), [2d,3d) of the fused qkv bf16 planes [batch][seq_len][3d].  bias_tiled (shared by batch
+ * and heads, or NULL) is the camera bias already multiplied by scale * log2(e), fp16, in 128 x 128 tiles laid out for coalesced reads:
+ *   bias_tiled[qt][kt][p][u][r][e] = fp16(scale * log2(e) * bias[128*qt + r][128*kt + 32*p + 8*u + e]),  p, u < 4, r < 128, e < 8
+ * (`bevgen_b200.ops.tile_attention_bias`).  seq_len and n_cond must be multiples of 128, d = heads*64. */
 BEVGEN_API int bevgen_attn_fused_fwd(const void* qkv_hi, const void* qkv_lo, int batch, int seq_len, int heads, int d, int n_cond,
-                                     const void* bias_f16, const float* y, float* x1, float scale, int npass, void* stream);
+                                     const void* bias_tiled, const float* y, float* x1, float scale, int npass, void* stream);
 
 /* ---------------------------------------------------------------- KV-cache autoregressive decode
  * Replaces the per-token full forward of Net2NetTransformer.sample (modules/stage2/cond_transformer_multi_view.py:154-227)
