@@ -290,7 +290,7 @@ def main():
             del model, x_dev
             torch.cuda.empty_cache()
             from tools.stage2_perf import run as stage2_run
-            r2 = stage2_run("bf16" if args.precision == "bf16" else "fp32x3", B=args.scenes)
+            r2 = stage2_run({"bf16": "bf16", "fp32x3": "fp32x3", "f16f8": "f16f8"}[args.precision], B=args.scenes)
             hbm_peak = hbm
             line["stage2"] = {
                 "forward_configs2": {"samples_per_s": r2["forward"]["samples_per_s"], "ms_per_batch": r2["forward"]["ms"], "batch": args.scenes,
@@ -305,7 +305,8 @@ def main():
                                                  "algorithmic_GB_per_batch": r2["sample"]["algorithmic_GB"]}},
                 "generate_configs3": r2.get("generate"),
                 "note": "full-size GPT (24 layers, d=1024, 16 heads, L=1792); KV-cache sampling of 16 scenes x 1536 tokens, top_k=100; "
-                        "parity configuration: bf16x3 weights, fp16 KV cache"}
+                        "parity configuration: forward = bf16x3 GEMMs / attention with the MLP GEMMs as f16f8 (when --precision f16f8), "
+                        "decode = bf16x3 weights, fp16 KV cache"}
         except Exception as ex:  # the headline line must still be printed
             line["stage2"] = {"error": repr(ex)}
     if world == 1 and not args.no_cpu_baseline:

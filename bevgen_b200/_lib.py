@@ -10,7 +10,7 @@ _HERE = Path(__file__).resolve().parent
 LIB_PATH = _HERE / "libbevgen_b200.so"
 MAX_TAPS = 9
 
-GF_GELU, GF_OUT_NCHW, GF_B_MN, GF_CAUSAL_SKIP, GF_CAUSAL_KLIMIT, GF_OUT_T = 1, 2, 4, 8, 16, 32
+GF_GELU, GF_OUT_NCHW, GF_B_MN, GF_CAUSAL_SKIP, GF_CAUSAL_KLIMIT, GF_OUT_T, GF_OUT_F16F8 = 1, 2, 4, 8, 16, 32, 64
 PREP_IDENT, PREP_UP2, PREP_S2D = 0, 1, 2
 
 
@@ -44,6 +44,7 @@ class GemmArgs(C.Structure):
         ("fin_gamma", C.c_void_p), ("fin_beta", C.c_void_p),
         ("fin_eps", C.c_float),
         ("fin_counters", C.c_void_p),
+        ("lo_scale", C.c_float),
     ]
 
 
@@ -79,6 +80,7 @@ SIGNATURES = {
     "bevgen_codebook_gather": (_i, [_vp, _vp, _ll, _i, _i, _vp, _vp]),
     "bevgen_denormalize": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "bevgen_layernorm": (_i, [_vp, _ll, _i, _ll, _vp, _vp, _f, _vp, _vp, _vp, _vp]),
+    "bevgen_layernorm_f16f8": (_i, [_vp, _ll, _i, _ll, _vp, _vp, _f, _vp, _vp, _vp, _vp]),
     "bevgen_embed_assemble": (_i, [C.POINTER(EmbedArgs), _vp]),
     "bevgen_attn_softmax": (_i, [_vp, _vp, _vp, _ll, _i, _i, _f, _vp, _vp, _vp]),
     "bevgen_attn_fused_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _f, _i, _vp]),

@@ -86,8 +86,12 @@ BEVGEN_API int bevgen_gemm_tc(const bevgen_gemm_args* a, void* stream) {
   if (rc) return rc;
   const int bn = a->bn, npass = a->npass;
   if (!(bn == 16 || bn == 64 || bn == 128)) return fail(BEVGEN_ERR_ARG, "bn must be 16, 64 or 128 (got %d)", bn);
-  if (!(npass == 1 || npass == 3)) return fail(BEVGEN_ERR_ARG, "npass must be 1 or 3 (got %d)", npass);
-  if (npass == 3 && (a->a_lo == nullptr || a->b_lo == nullptr)) return fail(BEVGEN_ERR_ARG, "npass=3 needs lo planes");
+  if (!(npass >= 1 && npass <= 3)) return fail(BEVGEN_ERR_ARG, "npass must be 1, 2 or 3 (got %d)", npass);
+  if (npass >= 2 && (a->a_lo == nullptr || a->b_lo == nullptr)) return fail(BEVGEN_ERR_ARG, "npass=%d needs lo / pair planes", npass);
+  if (npass == 2 && (bn != 128 || (a->flags & BEVGEN_GF_B_MN) || !(a->lo_scale > 0.f)))
+    return fail(BEVGEN_ERR_ARG, "npass=2 (f16f8) needs bn = 128, a K-major B operand and lo_scale > 0");
+  if ((a->flags & BEVGEN_GF_OUT_F16F8) && (!a->out_hi || !a->out_lo || (a->ldc & 63) || (a->n_cols & 31) || (a->flags & BEVGEN_GF_OUT_NCHW)))
+    return fail(BEVGEN_ERR_ARG, "f16f8 output planes need out_hi + out_lo, ldc %% 64 == 0 and n_cols %% 32 == 0");
   if (a->ntaps < 1 || a->ntaps > BEVGEN_MAX_TAPS) return fail(BEVGEN_ERR_ARG, "ntaps %d out of range", a->ntaps);
   if (a->k <= 0 || a->k % 64 != 0) return fail(BEVGEN_ERR_ARG, "k (%d) must be a positive multiple of 64", a->k);
   if (a->tile_w * a->tile_h != 128 || a->tile_w > 256 || a->tile_h > 256) return fail(BEVGEN_ERR_ARG, "tile %dx%d != 128 pixels", a->tile_w, a->tile_h);
@@ -103,7 +107,7 @@ BEVGEN_API int bevgen_gemm_tc(const bevgen_gemm_args* a, void* stream) {
   memset(&p, 0, sizeof(p));
   const void* aplanes[2] = {a->a_hi, a->a_lo};
   const void* bplanes[2] = {a->b_hi, a->b_lo};
-  for (int o = 0; o < (npass == 3 ? 2 : 1); ++o) {
+  for (int o = 0; o < (npass >= 2 ? 2 : 1); ++o) {
     uint64_t ad[4] = {(uint64_t)a->a_c, (uint64_t)a->a_w, (uint64_t)a->a_h, (uint64_t)a->a_n};
     uint64_t as[3] = {(uint64_t)a->a_c * 2, (uint64_t)a->a_c * a->a_w * 2, (uint64_t)a->a_c * a->a_w * a->a_h * 2};
     uint32_t ab[4] = {64, (uint32_t)a->tile_w, (uint32_t)a->tile_h, 1};
@@ -130,7 +134,7 @@ BEVGEN_API int bevgen_gemm_tc(const bevgen_gemm_args* a, void* stream) {
   p.out_zo_stride = a->out_zo_stride; p.out_zi_stride = a->out_zi_stride; p.ldc = a->ldc;
   p.bias = a->bias; p.residual = a->residual; p.out_f32 = a->out_f32;
   p.out_hi = (uint16_t*)a->out_hi; p.out_lo = (uint16_t*)a->out_lo;
-  p.flags = a->flags; p.causal_ncond = a->causal_ncond;
+  p.flags = a->flags; p.causal_ncond = a->causal_ncond; p.lo_scale = a->lo_scale;
   p.fin_mode = a->fin_mode;
   if (a->fin_mode != 0) {
     if (!(a->flags & BEVGEN_GF_OUT_T) || a->z_outer != 1 || !a->fin_counters || !a->fin_hi || a->fin_rows < 1 || a->fin_rows > a->n_cols)
@@ -314,7 +318,15 @@ BEVGEN_API int bevgen_layernorm(const float* x, long long rows, int d, long long
                                 float* y, void* out_hi, void* out_lo, void* stream) {
   if (!x || !gamma || !beta || (!y && !out_hi)) return fail(BEVGEN_ERR_ARG, "layernorm: bad args");
   if (x_row_stride % 4 != 0) return fail(BEVGEN_ERR_ARG, "layernorm: row stride must be a multiple of 4");
-  CHECK_LAUNCH(launch_layernorm(x, gamma, beta, y, (uint16_t*)out_hi, (uint16_t*)out_lo, rows, d, x_row_stride, eps, (cudaStream_t)stream), "layernorm");
+  CHECK_LAUNCH(launch_layernorm(x, gamma, beta, y, (uint16_t*)out_hi, (uint16_t*)out_lo, rows, d, x_row_stride, eps, 0, (cudaStream_t)stream), "layernorm");
+}
+
+BEVGEN_API int bevgen_layernorm_f16f8(const float* x, long long rows, int d, long long x_row_stride, const float* gamma, const float* beta, float eps,
+                                      float* y, void* out_f16, void* out_f8pair, void* stream) {
+  if (!x || !gamma || !beta || !out_f16 || !out_f8pair) return fail(BEVGEN_ERR_ARG, "layernorm_f16f8: bad args");
+  if (x_row_stride % 4 != 0) return fail(BEVGEN_ERR_ARG, "layernorm: row stride must be a multiple of 4");
+  CHECK_LAUNCH(launch_layernorm(x, gamma, beta, y, (uint16_t*)out_f16, (uint16_t*)out_f8pair, rows, d, x_row_stride, eps, 1, (cudaStream_t)stream),
+               "layernorm_f16f8");
 }
 
 BEVGEN_API int bevgen_embed_assemble(const bevgen_embed_args* a, void* stream) {

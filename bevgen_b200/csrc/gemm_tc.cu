@@ -4,9 +4,15 @@
 //   * nn.Linear layers ([M,K] x [N,K]^T) and batched, channel-sliced products (Q.K^T, P.V).
 // D[128 x BN] accumulates in TMEM (fp32, double buffered); operands are staged by TMA into SWIZZLE_128B
 // shared-memory tiles.  NPASS=3 runs the bf16x3 split product (A_hi.B_hi + A_lo.B_hi + A_hi.B_lo) that
-// reproduces fp32 results to ~1e-5; NPASS=1 is plain bf16.
+// reproduces fp32 results to ~1e-5; NPASS=1 is plain bf16; NPASS=2 is the f16f8 split product (one fp16 MMA + two e4m3 MMAs per
+// k-step, K-major operands only): plane 0 of each operand is fp16, plane 1 the packed e4m3 pair (per 64-element k chunk 64 bytes of
+// the 2^13-scaled fp16 remainder [A] / the S-scaled value [B] followed by 64 bytes of the value [A] / the scaled remainder [B], see
+// ops.pack_f16f8); the e4m3 correction sum has its own TMEM accumulator and is folded in by the epilogue (x lo_scale).
 // Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane), warp 2 = TMEM allocator,
 // warps 4-7 = epilogue (TMEM -> registers -> bias/activation/residual -> global).
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
+
 #include "common.cuh"
 #include "kernels.cuh"
 #include "gemm_tc.cuh"
@@ -21,11 +27,13 @@ constexpr int GEMM_THREADS = 256;
 template <int BN, int NPASS>
 struct GemmCfg {
   static constexpr int B_TILE_BYTES = (BN < 8 ? 8 : BN) * BK * 2;
-  static constexpr int NOPS = (NPASS == 3) ? 2 : 1;  // hi (+ lo) planes per operand
+  static constexpr int NOPS = (NPASS >= 2) ? 2 : 1;  // hi (+ lo / e4m3 pair) planes per operand
+  static constexpr int NACC = (NPASS == 2) ? 2 : 1;  // accumulators per tile (f16f8: main + e4m3 correction)
   static constexpr int STAGE_BYTES = NOPS * (A_TILE_BYTES + B_TILE_BYTES);
   static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-  static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  static constexpr int ACC_COLS = 2 * NACC * BN;      // double-buffered
+  static constexpr int TMEM_COLS = (ACC_COLS <= 32) ? 32 : (ACC_COLS <= 64) ? 64 : (ACC_COLS <= 128) ? 128 : (ACC_COLS <= 256) ? 256 : 512;
 };
 
 template <int BN, int NPASS>
@@ -55,7 +63,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA[0]);
     tma_prefetch_desc(&p.tmB[0]);
-    if (NPASS == 3) {
+    if (NPASS >= 2) {
       tma_prefetch_desc(&p.tmA[1]);
       tma_prefetch_desc(&p.tmB[1]);
     }
@@ -177,7 +185,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       uint32_t el;
       asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(el));
       const bool elected = el != 0;
-      const uint32_t idesc = make_idesc_bf16(BM, BN < 8 ? 8 : BN, 0, b_mn ? 1 : 0);
+      // NPASS == 2: A/B format field 0 = F16 under kind::f16 and = E4M3 under kind::f8f6f4 (same descriptor bits)
+      const uint32_t idesc = (NPASS == 2) ? (make_idesc_bf16(BM, BN < 8 ? 8 : BN, 0, 0) & ~((1u << 7) | (1u << 10)))
+                                          : make_idesc_bf16(BM, BN < 8 ? 8 : BN, 0, b_mn ? 1 : 0);
       const uint64_t adesc0 = make_sdesc_sw128(smem_u32(smem), 16, 1024);
       const uint64_t bdesc0 = b_mn ? make_sdesc_sw128(smem_u32(smem) + Cfg::NOPS * A_TILE_BYTES, 8192, 1024)
                                    : make_sdesc_sw128(smem_u32(smem) + Cfg::NOPS * A_TILE_BYTES, 16, 1024);
@@ -193,14 +203,24 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         if (tile_skipped(tw, nt)) continue;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
+        const uint32_t d_tmem = tmem_base + acc * (Cfg::NACC * BN);
         const int kit = k_iters_for(tw);
         for (int it = 0; it < kit; ++it) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint64_t a_st = adesc0 + (uint64_t)(stage * (Cfg::STAGE_BYTES >> 4));
           const uint64_t b_st = bdesc0 + (uint64_t)(stage * (Cfg::STAGE_BYTES >> 4));
-          if (elected) {
+          if (elected && NPASS == 2) {
+            // x*w ~= x16*w16 (accumulator 0) + [xlo8*w8 + x8*wlo8] * lo_scale (accumulator 1, e4m3 MMAs of K = 32 at twice the rate)
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) umma_bf16(d_tmem, a_st + k * 2, b_st + k * 2, idesc, (it == 0 && k == 0) ? 0u : 1u);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              umma_f8(d_tmem + BN, a_st + ALO + k * 2, b_st + BLO + k * 2, idesc, (it == 0 && k == 0) ? 0u : 1u);
+              umma_f8(d_tmem + BN, a_st + ALO + 4 + k * 2, b_st + BLO + 4 + k * 2, idesc, 1u);
+            }
+            umma_commit(&empty_bar[stage]);
+          } else if (elected) {
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) {
               // K-major SW128: 8-row groups 1024 B apart (SBO), k-advance = 32 B inside the swizzle row.
@@ -243,7 +263,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
 
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (Cfg::NACC * BN);
       constexpr int CH = (BN >= 32) ? 32 : 16;
 #pragma unroll 1
       for (int c = 0; c < BN; c += CH) {
@@ -251,12 +271,26 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         if (CH == 32) {
           uint32_t r[32];
           tmem_ld_32x32(taddr + c, r);
+          if (NPASS == 2) {
+            uint32_t r2[32];
+            tmem_ld_32x32(taddr + BN + c, r2);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(fmaf(__uint_as_float(r2[j]), p.lo_scale, __uint_as_float(r[j])));
+          }
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
         } else {
           uint32_t r[16];
           tmem_ld_32x16(taddr + c, r);
+          if (NPASS == 2) {
+            uint32_t r2[16];
+            tmem_ld_32x16(taddr + BN + c, r2);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(fmaf(__uint_as_float(r2[j]), p.lo_scale, __uint_as_float(r[j])));
+          }
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
@@ -310,7 +344,35 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
 #pragma unroll
             for (int j = 0; j < CH / 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           }
-          if (p.out_hi != nullptr) {
+          if (p.out_hi != nullptr && (p.flags & GF_OUT_F16F8)) {
+            // operand planes of a following f16f8 GEMM: fp16 plane [row][ldc] + e4m3 pair plane [row][2*ldc bytes]; this 32-column chunk is
+            // half of a 64-element k chunk: remainders at byte (col/64)*128 + col%64, values 64 bytes further
+            if (CH == 32) {
+              uint4* hp = reinterpret_cast<uint4*>(p.out_hi + roff + c);
+              uint8_t* pp = reinterpret_cast<uint8_t*>(p.out_lo) + (roff - n0) * 2 + ((n0 + c) >> 6) * 128 + ((n0 + c) & 63);
+              uint32_t l8[8], x8[8];
+#pragma unroll
+              for (int j = 0; j < CH / 8; ++j) {
+                uint32_t h[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float v0 = v[8 * j + 2 * e], v1 = v[8 * j + 2 * e + 1];
+                  const __half2 h2 = __floats2half2_rn(v0, v1);
+                  h[e] = *reinterpret_cast<const uint32_t*>(&h2);
+                  const float2 hf = __half22float2(h2);
+                  const uint32_t lo2 = __nv_cvt_float2_to_fp8x2(make_float2((v0 - hf.x) * 8192.0f, (v1 - hf.y) * 8192.0f), __NV_SATFINITE, __NV_E4M3);
+                  const uint32_t xx2 = __nv_cvt_float2_to_fp8x2(make_float2(v0, v1), __NV_SATFINITE, __NV_E4M3);
+                  if (e & 1) { l8[2 * j + (e >> 1)] |= lo2 << 16; x8[2 * j + (e >> 1)] |= xx2 << 16; }
+                  else { l8[2 * j + (e >> 1)] = lo2; x8[2 * j + (e >> 1)] = xx2; }
+                }
+                hp[j] = make_uint4(h[0], h[1], h[2], h[3]);
+              }
+              reinterpret_cast<uint4*>(pp)[0] = make_uint4(l8[0], l8[1], l8[2], l8[3]);
+              reinterpret_cast<uint4*>(pp)[1] = make_uint4(l8[4], l8[5], l8[6], l8[7]);
+              reinterpret_cast<uint4*>(pp + 64)[0] = make_uint4(x8[0], x8[1], x8[2], x8[3]);
+              reinterpret_cast<uint4*>(pp + 64)[1] = make_uint4(x8[4], x8[5], x8[6], x8[7]);
+            }
+          } else if (p.out_hi != nullptr) {
             uint4* hp = reinterpret_cast<uint4*>(p.out_hi + roff + c);
             uint4* lp = (p.out_lo != nullptr) ? reinterpret_cast<uint4*>(p.out_lo + roff + c) : nullptr;
 #pragma unroll
@@ -480,7 +542,7 @@ int gemm_tc_dispatch(const GemmParams& p, int bn, int npass, int sm_count, cudaS
   if (total <= 0) return BEVGEN_ERR_ARG;
 #define CASE(BN_, NP_) \
   if (bn == BN_ && npass == NP_) return launch_gemm<BN_, NP_>(p, total, sm_count, stream);
-  CASE(128, 3) CASE(128, 1) CASE(64, 3) CASE(64, 1) CASE(16, 3) CASE(16, 1)
+  CASE(128, 3) CASE(128, 2) CASE(128, 1) CASE(64, 3) CASE(64, 1) CASE(16, 3) CASE(16, 1)
 #undef CASE
   return BEVGEN_ERR_ARG;
 }

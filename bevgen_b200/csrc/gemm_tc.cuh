@@ -15,6 +15,7 @@ enum GemmFlags : int {
   GF_B_MN = 4,        // B operand is MN-major in global memory: [k rows][n cols] (e.g. V in P.V)
   GF_CAUSAL_SKIP = 8, // skip output tiles entirely outside the [cond | causal] support (attention scores)
   GF_OUT_T = 32,      // swap-AB decode GEMMs: store D^T, out[z][col][row] fp32, no bias/act/residual (split-K partials)
+  GF_OUT_F16F8 = 64,  // out_hi / out_lo are the fp16 plane and the e4m3 pair plane of a following f16f8 GEMM (instead of bf16 hi / lo)
   GF_CAUSAL_KLIMIT = 16, // reduction index = key index: stop at max(ncond, last row of the tile + 1) (P.V)
 };
 
@@ -40,6 +41,7 @@ struct GemmParams {
   uint16_t* out_hi;     // bf16 split outputs (same indexing), or null
   uint16_t* out_lo;
   int flags;
+  float lo_scale;       // npass == 2: scale of the e4m3 correction accumulator = 1 / (2^13 * S), S = weight scale of ops.pack_f16f8
   int causal_ncond;     // GF_CAUSAL_SKIP: columns < ncond always allowed; else col <= row
   // ---- split-K finalize fused into GF_OUT_T launches (decode): the last CTA to finish a row tile reduces the partials
   int fin_mode;               // 0 none | 1 planes = act(sum + bias) | 2 x = sum + bias + residual, then LayerNorm by the last tile

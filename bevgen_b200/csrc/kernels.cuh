@@ -73,7 +73,7 @@ int launch_vq_nearest(const float* z, const float* cb, const float* zz, const fl
                       int D, cudaStream_t st);
 
 int launch_layernorm(const float* x, const float* gamma, const float* beta, float* y, uint16_t* hi, uint16_t* lo, long long rows, int d,
-                     long long x_row_stride, float eps, cudaStream_t st);
+                     long long x_row_stride, float eps, int f16f8, cudaStream_t st);
 int launch_embed(const EmbedParams& p, cudaStream_t st);
 int launch_attn_softmax(const float* S, const float* bias, const uint8_t* mask, uint16_t* hi, uint16_t* lo, long long zrows, int L, int Lk,
                         float scale, cudaStream_t st);

@@ -1,5 +1,8 @@
 // Stage-2 transformer helper kernels (HBM-bound, coalesced): input-embedding assembly, LayerNorm (+ bf16 split),
 // masked/biased attention softmax.  The GEMMs and attention products run in gemm_tc.cu / attn kernels.
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
+
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -12,7 +15,7 @@ namespace bevgen {
 template <int NV>  // float4 per lane
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, float* __restrict__ y, uint16_t* __restrict__ hi,
-                                                        uint16_t* __restrict__ lo, long long rows, long long x_row_stride, float eps) {
+                                                        uint16_t* __restrict__ lo, long long rows, long long x_row_stride, float eps, int f16f8) {
   constexpr int D = NV * 128;
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -43,7 +46,21 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
     o.x = v[j].x * rstd * g.x + b.x; o.y = v[j].y * rstd * g.y + b.y;
     o.z = v[j].z * rstd * g.z + b.z; o.w = v[j].w * rstd * g.w + b.w;
     if (y != nullptr) reinterpret_cast<float4*>(y + row * D)[c4] = o;
-    if (hi != nullptr) {
+    if (hi != nullptr && f16f8) {
+      // operand planes of an f16f8 GEMM (gemm_tc npass = 2): fp16 plane + e4m3 pair plane (per 64-column chunk: 64 bytes of 2^13-scaled
+      // fp16 remainders, then 64 bytes of values)
+      const __half2 ha = __floats2half2_rn(o.x, o.y), hb = __floats2half2_rn(o.z, o.w);
+      reinterpret_cast<uint2*>(hi + row * D)[c4] = make_uint2(*reinterpret_cast<const uint32_t*>(&ha), *reinterpret_cast<const uint32_t*>(&hb));
+      const float2 fa = __half22float2(ha), fb = __half22float2(hb);
+      const uint32_t l8 = (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2((o.x - fa.x) * 8192.0f, (o.y - fa.y) * 8192.0f), __NV_SATFINITE, __NV_E4M3) |
+                          ((uint32_t)__nv_cvt_float2_to_fp8x2(make_float2((o.z - fb.x) * 8192.0f, (o.w - fb.y) * 8192.0f), __NV_SATFINITE, __NV_E4M3) << 16);
+      const uint32_t x8 = (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2(o.x, o.y), __NV_SATFINITE, __NV_E4M3) |
+                          ((uint32_t)__nv_cvt_float2_to_fp8x2(make_float2(o.z, o.w), __NV_SATFINITE, __NV_E4M3) << 16);
+      const int col = c4 * 4;
+      uint8_t* pp = reinterpret_cast<uint8_t*>(lo) + row * (2 * D) + (col >> 6) * 128 + (col & 63);
+      *reinterpret_cast<uint32_t*>(pp) = l8;
+      *reinterpret_cast<uint32_t*>(pp + 64) = x8;
+    } else if (hi != nullptr) {
       __nv_bfloat16 h0, l0, h1, l1, h2, l2, h3, l3;
       split_bf16(o.x, h0, l0); split_bf16(o.y, h1, l1); split_bf16(o.z, h2, l2); split_bf16(o.w, h3, l3);
       reinterpret_cast<uint2*>(hi + row * D)[c4] = make_uint2(pack_bf16(h0, h1), pack_bf16(h2, h3));
@@ -53,11 +70,11 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 }
 
 int launch_layernorm(const float* x, const float* gamma, const float* beta, float* y, uint16_t* hi, uint16_t* lo, long long rows, int d,
-                     long long x_row_stride, float eps, cudaStream_t st) {
-  if (d % 128 != 0 || d > 1024 || rows < 1) return BEVGEN_ERR_ARG;
+                     long long x_row_stride, float eps, int f16f8, cudaStream_t st) {
+  if (d % 128 != 0 || d > 1024 || rows < 1 || (f16f8 && (!hi || !lo))) return BEVGEN_ERR_ARG;
   const unsigned grid = (unsigned)((rows + 7) / 8);
   switch (d / 128) {
-#define LN_CASE(N) case N: layernorm_kernel<N><<<grid, 256, 0, st>>>(x, gamma, beta, y, hi, lo, rows, x_row_stride, eps); break;
+#define LN_CASE(N) case N: layernorm_kernel<N><<<grid, 256, 0, st>>>(x, gamma, beta, y, hi, lo, rows, x_row_stride, eps, f16f8); break;
     LN_CASE(1) LN_CASE(2) LN_CASE(3) LN_CASE(4) LN_CASE(5) LN_CASE(6) LN_CASE(7) LN_CASE(8)
 #undef LN_CASE
   }

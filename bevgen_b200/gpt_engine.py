@@ -30,9 +30,12 @@ def _planes_of(w, npass, dev, min_rows=128):
 
 class GPTEngine:
     def __init__(self, state_dict, cfg, device="cuda", precision="fp32x3", layouts=None):
-        assert precision in ("fp32x3", "bf16")
+        # "fp32x3": every GEMM is the bf16x3 split product; "f16f8" (parity mode): the two MLP GEMMs (73 % of the linear FLOPs) form the
+        # same fp32-equivalent product as 1 fp16 + 2 e4m3 MMAs (2/3 of the tensor time / energy), everything else stays bf16x3; "bf16": fast mode
+        assert precision in ("fp32x3", "f16f8", "bf16")
         self.cfg, self.precision = cfg, precision
-        self.npass = 3 if precision == "fp32x3" else 1
+        self.npass = 1 if precision == "bf16" else 3
+        self.mlp_f16f8 = precision == "f16f8"
         self.dev = torch.device(device)
         dev, sd = self.dev, state_dict
         d = cfg.num_embed
@@ -58,6 +61,9 @@ class GPTEngine:
                 wqkv=_planes_of(wqkv, self.npass, dev), bqkv=bqkv.to(dev, torch.float32).contiguous(),
                 w1=_planes_of(sd[f"{p}.mlp.0.weight"], self.npass, dev), b1=f32(f"{p}.mlp.0.bias"),
                 w2=_planes_of(sd[f"{p}.mlp.2.weight"], self.npass, dev), b2=f32(f"{p}.mlp.2.bias")))
+            if self.mlp_f16f8:       # (fp16 plane, e4m3 pair plane, lo_scale) of the MLP weights for the npass = 2 GEMM
+                self.layers[-1]["w1_f8"] = ops.pack_f16f8(sd[f"{p}.mlp.0.weight"].to(dev, torch.float32).contiguous())
+                self.layers[-1]["w2_f8"] = ops.pack_f16f8(sd[f"{p}.mlp.2.weight"].to(dev, torch.float32).contiguous())
         self.ln_f = (f32("ln_f.weight"), f32("ln_f.bias"))
         self.vocab = sd["head.weight"].shape[0]
         self.whead = _planes_of(sd["head.weight"], self.npass, dev)
@@ -104,12 +110,12 @@ class GPTEngine:
         return hi, lo
 
     def _linear(self, a, w, n_cols, rows, k, bias=None, residual=None, out_f32=None, out_planes=None, flags=0, taps=((0, 0, 0),),
-                a_dims=None, out_w=None, z_outer=1, out_zo_stride=0):
+                a_dims=None, out_w=None, z_outer=1, out_zo_stride=0, npass=None, lo_scale=0.0):
         a_hi, a_lo = a
         oh, ol = out_planes if out_planes is not None else (None, None)
         ops.gemm_tc(a_hi=a_hi, a_lo=a_lo, a_dims=a_dims or (1, 1, rows, k), b_hi=w[0], b_lo=w[1], k=k, n_cols=n_cols, taps=taps,
                     out_w=out_w or rows, z_outer=z_outer, out_zo_stride=out_zo_stride, ldc=n_cols, bias=bias, residual=residual,
-                    out_f32=out_f32, out_hi=oh, out_lo=ol, flags=flags, bn=128, npass=self.npass)
+                    out_f32=out_f32, out_hi=oh, out_lo=ol, flags=flags, bn=128, npass=self.npass if npass is None else npass, lo_scale=lo_scale)
 
     def embed(self, cam_idx, bev_idx, batch, sampling, row0=0, nrows=None, out=None):
         B = bev_idx.shape[0]
@@ -176,11 +182,21 @@ class GPTEngine:
         if on_qkv is not None:
             on_qkv(qkv)
         x1 = self.attention(qkv, y, B, L, **(attn_kw or {}))
+        x2 = torch.empty_like(x)
+        if self.mlp_f16f8 and d % 128 == 0:
+            # MLP as f16f8 GEMMs: LayerNorm and the GELU epilogue write the fp16 + e4m3-pair operand planes directly
+            u8 = lambda r, c: torch.empty((r, c), dtype=torch.uint8, device=self.dev)
+            f16 = lambda r, c: torch.empty((r, c), dtype=torch.float16, device=self.dev)
+            zp, hp = (f16(rows, d), u8(rows, 2 * d)), (f16(rows, 4 * d), u8(rows, 8 * d))
+            ops.layernorm(x1, *lw["ln2"], out_hi=zp[0], out_lo=zp[1], f16f8=True)
+            w1, w2 = lw["w1_f8"], lw["w2_f8"]
+            self._linear(zp, w1[:2], 4 * d, rows, d, bias=lw["b1"], out_planes=hp, flags=ops.GF_GELU | ops.GF_OUT_F16F8, npass=2, lo_scale=w1[2])
+            self._linear(hp, w2[:2], d, rows, 4 * d, bias=lw["b2"], residual=x1, out_f32=x2, npass=2, lo_scale=w2[2])
+            return x2
         zp = self._planes((rows, d))
         ops.layernorm(x1, *lw["ln2"], out_hi=zp[0], out_lo=zp[1])
         hp = self._planes((rows, 4 * d))
         self._linear(zp, lw["w1"], 4 * d, rows, d, bias=lw["b1"], out_planes=hp, flags=ops.GF_GELU)
-        x2 = torch.empty_like(x)
         self._linear(hp, lw["w2"], d, rows, 4 * d, bias=lw["b2"], residual=x1, out_f32=x2)
         return x2
 

@@ -6,7 +6,7 @@ import math
 import torch
 
 from . import _lib
-from ._lib import (GF_B_MN, GF_CAUSAL_KLIMIT, GF_CAUSAL_SKIP, GF_GELU, GF_OUT_NCHW, GF_OUT_T, PREP_IDENT, PREP_S2D, PREP_UP2,  # noqa: F401
+from ._lib import (GF_B_MN, GF_CAUSAL_KLIMIT, GF_CAUSAL_SKIP, GF_GELU, GF_OUT_F16F8, GF_OUT_NCHW, GF_OUT_T, PREP_IDENT, PREP_S2D, PREP_UP2,  # noqa: F401
                    EmbedArgs, GemmArgs)
 
 
@@ -69,6 +69,19 @@ def pack_f16f8(w2d: torch.Tensor):
     return w16.contiguous(), pair.reshape(rows, 2 * cin).contiguous(), 1.0 / (2.0 ** F8_ACT_LO_SHIFT * s)
 
 
+def pack_act_f16f8(a: torch.Tensor):
+    """fp32 activations [rows][k] (k % 64 == 0) -> the A-operand planes of an npass = 2 GEMM, as bevgen_layernorm_f16f8 / the
+    BEVGEN_GF_OUT_F16F8 epilogue write them: (fp16 [rows][k], uint8 [rows][2k]: per 64-chunk 64 B e4m3((a - a16) * 2^13) then 64 B e4m3(a))."""
+    rows, k = a.shape
+    assert k % 64 == 0
+    a = a.float()
+    a16 = a.to(torch.float16)
+    lo8 = ((a - a16.float()) * 2.0 ** F8_ACT_LO_SHIFT).clamp(-448.0, 448.0).to(torch.float8_e4m3fn)
+    x8 = a.clamp(-448.0, 448.0).to(torch.float8_e4m3fn)
+    pair = torch.stack([lo8.view(torch.uint8).view(rows, k // 64, 64), x8.view(torch.uint8).view(rows, k // 64, 64)], 2)
+    return a16.contiguous(), pair.reshape(rows, 2 * k).contiguous()
+
+
 def pack_f16f8_block(w2d: torch.Tensor):
     """Weights for the 16x16-block f16f8 kernel (bevgen_conv3x3_fused_f16f8, block16=1): (w16s fp16(w * S * 2^7), pair [rows][2*cin] uint8 with,
     per 32-channel slice, 32 bytes e4m3(w * S) then 32 bytes e4m3((w - w16) * S * 2^13), lo_scale = 1 / (2^13 * S))."""
@@ -92,7 +105,7 @@ TAPS_3X3 = [(kw - 1, kh - 1) for kh in range(3) for kw in range(3)]
 def gemm_tc(*, a_hi, a_lo, a_dims, b_hi, b_lo, k, n_cols, taps=((0, 0, 0),), a_n_mul=1, a_n_zstride=0, a_c_off=0, a_c_zstride=0,
             b_k_off=0, b_k_zstride=0, b_row_zstride=0, b_row_tapstride=0, z_inner=1, z_outer=1, tile=(128, 1),
             out_w, out_h=1, out_zo_stride=0, out_zi_stride=0, ldc, bias=None, residual=None, out_f32=None, out_hi=None,
-            out_lo=None, flags=0, causal_ncond=0, bn=128, npass=3, algo_flops=None, fin=None):
+            out_lo=None, flags=0, causal_ncond=0, bn=128, npass=3, algo_flops=None, fin=None, lo_scale=0.0):
     lib = _lib.init()
     _chk_cuda(a_hi, a_lo, b_hi, b_lo, bias, residual, out_f32, out_hi, out_lo)
     g = GemmArgs()
@@ -114,6 +127,7 @@ def gemm_tc(*, a_hi, a_lo, a_dims, b_hi, b_lo, k, n_cols, taps=((0, 0, 0),), a_n
     g.bias, g.residual = _ptr(bias), _ptr(residual)
     g.out_f32, g.out_hi, g.out_lo = _ptr(out_f32), _ptr(out_hi), _ptr(out_lo)
     g.flags, g.causal_ncond, g.bn, g.npass = flags, causal_ncond, bn, npass
+    g.lo_scale = float(lo_scale)
     if fin is not None:        # fused split-K finalize (decode): dict(mode, rows, counters, hi, lo, bias, gelu, resid, x, y, gamma, beta, eps)
         g.fin_mode, g.fin_gelu, g.fin_rows = fin["mode"], int(fin.get("gelu", 0)), fin["rows"]
         g.fin_bias, g.fin_resid = _ptr(fin.get("bias")), _ptr(fin.get("resid"))
@@ -207,15 +221,16 @@ def denormalize(x_nchw, out, mean, std):
     _lib.check(lib.bevgen_denormalize(_ptr(x_nchw), _ptr(out), n, c, h * w, m, s, _stream()), "denormalize")
 
 
-def layernorm(x, gamma, beta, y=None, out_hi=None, out_lo=None, eps=1e-5, rows=None, row_stride=None):
+def layernorm(x, gamma, beta, y=None, out_hi=None, out_lo=None, eps=1e-5, rows=None, row_stride=None, f16f8=False):
+    """f16f8: out_hi / out_lo receive the fp16 plane and the e4m3 pair plane (operands of an npass = 2 GEMM)."""
     lib = _lib.init()
     Stats.launches += 1
     _chk_cuda(gamma, beta, y, out_hi, out_lo)
     d = gamma.numel()
     rows = x.numel() // d if rows is None else rows
     row_stride = d if row_stride is None else row_stride
-    _lib.check(lib.bevgen_layernorm(_ptr(x), rows, d, row_stride, _ptr(gamma), _ptr(beta), eps, _ptr(y), _ptr(out_hi), _ptr(out_lo), _stream()),
-               "layernorm")
+    fn = lib.bevgen_layernorm_f16f8 if f16f8 else lib.bevgen_layernorm
+    _lib.check(fn(_ptr(x), rows, d, row_stride, _ptr(gamma), _ptr(beta), eps, _ptr(y), _ptr(out_hi), _ptr(out_lo), _stream()), "layernorm")
 
 
 def embed_assemble(args: "EmbedArgs"):

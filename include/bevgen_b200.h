@@ -36,6 +36,7 @@ extern "C" {
 #define BEVGEN_GF_B_MN 4        /* B operand is [k rows][n cols] in memory (V in P.V) */
 #define BEVGEN_GF_CAUSAL_SKIP 8 /* skip output tiles outside the [cond | causal] support (Q.K^T) */
 #define BEVGEN_GF_OUT_T 32 /* store D^T: out_f32[z][col][row] (swap-AB decode GEMMs, split-K partials; no bias/act/residual) */
+#define BEVGEN_GF_OUT_F16F8 64 /* out_hi / out_lo receive the fp16 plane and the e4m3 pair plane (operands of a following npass = 2 GEMM) */
 #define BEVGEN_GF_CAUSAL_KLIMIT 16 /* reduction over keys stops at max(ncond, last tile row + 1) (P.V) */
 
 /* prep modes */
@@ -69,7 +70,8 @@ typedef struct {
   int flags;
   int causal_ncond;
   int bn;                               /* N tile: 16, 64 or 128 */
-  int npass;                            /* 1 (bf16) or 3 (bf16x3 ~ fp32) */
+  int npass;                            /* 1 (bf16), 3 (bf16x3 ~ fp32) or 2 (f16f8 ~ fp32: a_hi / b_hi are fp16 planes, a_lo / b_lo the e4m3 pair planes
+                                           of ops.pack_f16f8 / BEVGEN_GF_OUT_F16F8 / bevgen_layernorm_f16f8; K-major B, bn = 128 only) */
   /* split-K finalize fused into BEVGEN_GF_OUT_T launches: the last CTA per 128-feature tile reduces the z_inner partials */
   int fin_mode;                         /* 0 none; 1: planes = act(sum + bias); 2: x = sum + bias + residual, then LayerNorm(x) */
   int fin_gelu, fin_rows;
@@ -78,6 +80,7 @@ typedef struct {
   const float* fin_gamma; const float* fin_beta;
   float fin_eps;
   unsigned int* fin_counters;           /* [ceil(out_w/128) + 1] uint32, zeroed once by the caller (self-resetting) */
+  float lo_scale;                       /* npass == 2: 1 / (2^13 * S), S = weight scale (ops.pack_f16f8) */
 } bevgen_gemm_args;
 
 BEVGEN_API int bevgen_init(int device);                 /* selects nothing, queries: SM count, arch check, driver entry points */
@@ -159,6 +162,10 @@ BEVGEN_API int bevgen_denormalize(const float* x, float* out, int n, int c, int 
  * and bf16 planes [rows][d] (optional). d % 128 == 0, d <= 1024. */
 BEVGEN_API int bevgen_layernorm(const float* x, long long rows, int d, long long x_row_stride, const float* gamma, const float* beta, float eps,
                                 float* y, void* out_hi, void* out_lo, void* stream);
+/* Same LayerNorm writing the operand planes of an f16f8 GEMM (bevgen_gemm_tc, npass = 2): out_f16 [rows][d] fp16 and out_f8pair
+ * [rows][2*d bytes]: per 64-column chunk 64 bytes e4m3((y - fp16(y)) * 2^13) followed by 64 bytes e4m3(y). */
+BEVGEN_API int bevgen_layernorm_f16f8(const float* x, long long rows, int d, long long x_row_stride, const float* gamma, const float* beta, float eps,
+                                      float* y, void* out_f16, void* out_f8pair, void* stream);
 
 /* Input-embedding assembly of GPT.forward (mingpt_sparse.py:319-373) for sequence rows [row0, row0+nrows):
  * token + ray embedding (L2-normalised) + position embeddings, decode-order permutation, [cond | img | pad] concat. */

@@ -63,7 +63,7 @@ class Block(nn.Module):
 
 
 class GPT(nn.Module):
-    def __init__(self, cfg: GPTConfig, precision="fp32x3", **kwargs):
+    def __init__(self, cfg: GPTConfig, precision="f16f8", **kwargs):
         super().__init__()
         self.cfg = cfg
         self.precision = precision

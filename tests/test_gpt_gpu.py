@@ -35,10 +35,12 @@ def test_embed_vs_oracle():
     assert ((eng.embed(cam.cuda(), bev.cuda(), batch, True).cpu() - want).abs() / (1 + want.abs())).max().item() < 2e-6
 
 
+@pytest.mark.parametrize("precision", ["fp32x3", "f16f8"])
 @pytest.mark.parametrize("name", ["small", "padded", "wide2"])
-def test_forward_fp32x3_vs_reference_golden(name, golden_dir):
+def test_forward_fp32x3_vs_reference_golden(name, precision, golden_dir):
+    """Both parity modes (bf16x3 everywhere / fp16 + 2 x e4m3 MLP GEMMs) against the reference's logits at the 1e-3 bar."""
     g = np.load(golden_dir / f"gpt_{name}.npz")
-    cfg, sd, cam, bev, batch, eng = _case(name)
+    cfg, sd, cam, bev, batch, eng = _case(name, precision)
     rows = g["rows"]
     tf, hid = eng.forward(cam.clone().cuda(), bev.cuda(), batch, sampling=False, return_hidden=True)
     s = eng.forward(cam.cuda(), bev.cuda(), batch, sampling=True)
@@ -47,7 +49,7 @@ def test_forward_fp32x3_vs_reference_golden(name, golden_dir):
     e_hl = np.abs(hid[-1][:, ::97].cpu().numpy() - g["hidden_last_rows"]).max()
     e_tf = np.abs(tf[:, rows].cpu().numpy() - g["logits_tf"]).max()
     e_s = np.abs(s[:, rows].cpu().numpy() - g["logits_s"]).max()
-    print(f"[{name}] fp32x3: hidden0 {e_h0:.2e} hidden_last {e_hl:.2e} logits tf {e_tf:.2e} sampling {e_s:.2e} (|logit| max {float(g['logits_tf_absmax']):.2f})")
+    print(f"[{name}] {precision}: hidden0 {e_h0:.2e} hidden_last {e_hl:.2e} logits tf {e_tf:.2e} sampling {e_s:.2e} (|logit| max {float(g['logits_tf_absmax']):.2f})")
     assert e_h0 < LOGIT_TOL and e_hl < LOGIT_TOL and e_tf < LOGIT_TOL and e_s < LOGIT_TOL
     assert abs(tf.double().mean().item() - float(g["logits_tf_mean"])) < 1e-5
 

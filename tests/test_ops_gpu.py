@@ -398,3 +398,64 @@ def test_conv3x3_fused_f16f8(N_, H, W, Cin, Cout, mode, block16):
         o = out.double().permute(0, 3, 1, 2).reshape(N_, 32, -1)
         want = torch.stack([o.sum(-1), (o * o).sum(-1)], -1).reshape(-1)
         assert ((osums - want).abs() / (1 + want.abs())).max().item() < 1e-5
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 128, 64), (1000, 256, 320), (384, 512, 1024)])
+def test_linear_f16f8(M, N, K):
+    """gemm_tc npass = 2: fp16 + 2 x e4m3 split product with host-packed operand planes; error bound ~2^-15 per product."""
+    g = torch.Generator().manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g).to(dev())
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(dev())
+    bias = torch.randn(N, generator=g).to(dev())
+    res = torch.randn(M, N, generator=g).to(dev())
+    a16, apair = ops.pack_act_f16f8(a)
+    w16, wpair, lo_scale = ops.pack_f16f8(w)
+    out = torch.full((M, N), float("nan"), device=dev())
+    ops.gemm_tc(a_hi=a16, a_lo=apair, a_dims=(1, 1, M, K), b_hi=w16, b_lo=wpair, k=K, n_cols=N, out_w=M, ldc=N, bias=bias, residual=res,
+                out_f32=out, bn=128, npass=2, lo_scale=lo_scale)
+    torch.cuda.synchronize()
+    ref = a.double() @ w.double().t() + bias.double() + res.double()
+    err = (out.double() - ref).abs().max().item()
+    assert torch.isfinite(out).all()
+    assert err < 6e-5 * K ** 0.5, f"max err {err}"
+
+
+def test_f16f8_plane_producers_chain():
+    """LayerNorm -> f16f8 planes -> GEMM + GELU -> f16f8 planes (epilogue) -> GEMM: the operand planes written by the kernels decode back to
+    the fp32 values (fp16 + e4m3 remainder / 2^13) and the chain matches an fp64 reference."""
+    M, D = 320, 256
+    g = torch.Generator().manual_seed(3)
+    x = (torch.randn(M, D, generator=g) * 2 + 0.5).to(dev())
+    gamma, beta = (1 + 0.1 * torch.randn(D, generator=g)).to(dev()), (0.1 * torch.randn(D, generator=g)).to(dev())
+    w1 = (torch.randn(4 * D, D, generator=g) / D ** 0.5).to(dev())
+    b1 = (0.1 * torch.randn(4 * D, generator=g)).to(dev())
+    w2 = (torch.randn(D, 4 * D, generator=g) / (4 * D) ** 0.5).to(dev())
+    y = torch.empty(M, D, device=dev())
+    z16, zpair = torch.zeros(M, D, dtype=torch.float16, device=dev()), torch.zeros(M, 2 * D, dtype=torch.uint8, device=dev())
+    ops.layernorm(x, gamma, beta, y=y, out_hi=z16, out_lo=zpair, f16f8=True)
+    torch.cuda.synchronize()
+    y_ref = F.layer_norm(x.double(), (D,), gamma.double(), beta.double(), 1e-5)
+    assert (y.double() - y_ref).abs().max().item() < 1e-5
+
+    def decode(p16, pair):        # value represented by the planes
+        k = p16.shape[1]
+        pr = pair.view(p16.shape[0], k // 64, 2, 64)
+        lo = pr[:, :, 0].reshape(p16.shape[0], k).view(torch.float8_e4m3fn).double() / 8192.0
+        x8 = pr[:, :, 1].reshape(p16.shape[0], k).view(torch.float8_e4m3fn).double()
+        return p16.double() + lo, x8
+    zv, z8 = decode(z16, zpair)
+    assert ((zv - y_ref).abs() <= 2.0 ** -15 * y_ref.abs() + 1e-6).all()           # fp16 + e4m3 remainder: 2^-12 * 2^-4 relative, + fp32 LN rounding
+    assert ((z8 - y_ref).abs() <= 0.0625 * y_ref.abs() + 2e-3).all()                  # e4m3: 3 mantissa bits
+    h16, hpair = torch.zeros(M, 4 * D, dtype=torch.float16, device=dev()), torch.zeros(M, 8 * D, dtype=torch.uint8, device=dev())
+    w1p, w2p = ops.pack_f16f8(w1), ops.pack_f16f8(w2)
+    ops.gemm_tc(a_hi=z16, a_lo=zpair, a_dims=(1, 1, M, D), b_hi=w1p[0], b_lo=w1p[1], k=D, n_cols=4 * D, out_w=M, ldc=4 * D, bias=b1,
+                out_hi=h16, out_lo=hpair, flags=ops.GF_GELU | ops.GF_OUT_F16F8, bn=128, npass=2, lo_scale=w1p[2])
+    out = torch.empty(M, D, device=dev())
+    ops.gemm_tc(a_hi=h16, a_lo=hpair, a_dims=(1, 1, M, 4 * D), b_hi=w2p[0], b_lo=w2p[1], k=4 * D, n_cols=D, out_w=M, ldc=D, residual=x,
+                out_f32=out, bn=128, npass=2, lo_scale=w2p[2])
+    torch.cuda.synchronize()
+    h_ref = F.gelu(y_ref @ w1.double().t() + b1.double())
+    hv, _ = decode(h16, hpair)
+    assert ((hv - h_ref).abs() <= 2.0 ** -14 * h_ref.abs() + 1e-4).all()
+    ref = h_ref @ w2.double().t() + x.double()
+    assert (out.double() - ref).abs().max().item() < 3e-4

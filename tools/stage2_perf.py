@@ -91,7 +91,7 @@ def run(precision, B=16, layers=24, fwd_iters=3, sample=True, kv_dtype=None, use
 
 if __name__ == "__main__":
     out = []
-    for prec in sys.argv[1:] or ["fp32x3", "bf16"]:
+    for prec in sys.argv[1:] or ["f16f8", "fp32x3", "bf16"]:
         kv = None
         if prec.endswith("+kv16"):
             prec, kv = prec[:-5], torch.float16
