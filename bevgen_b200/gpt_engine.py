@@ -30,7 +30,7 @@ def _planes_of(w, npass, dev, min_rows=128):
 
 class GPTEngine:
     def __init__(self, state_dict, cfg, device="cuda", precision="fp32x3", layouts=None):
-        # "fp32x3": every GEMM is the bf16x3 split product; "f16f8" (parity mode): the two MLP GEMMs (73 % of the linear FLOPs) form the
+        # "fp32x3": every GEMM is the bf16x3 split product; "f16f8" (parity mode): the QKV and the two MLP GEMMs form the
         # same fp32-equivalent product as 1 fp16 + 2 e4m3 MMAs (2/3 of the tensor time / energy), everything else stays bf16x3; "bf16": fast mode
         assert precision in ("fp32x3", "f16f8", "bf16")
         self.cfg, self.precision = cfg, precision
@@ -61,7 +61,8 @@ class GPTEngine:
                 wqkv=_planes_of(wqkv, self.npass, dev), bqkv=bqkv.to(dev, torch.float32).contiguous(),
                 w1=_planes_of(sd[f"{p}.mlp.0.weight"], self.npass, dev), b1=f32(f"{p}.mlp.0.bias"),
                 w2=_planes_of(sd[f"{p}.mlp.2.weight"], self.npass, dev), b2=f32(f"{p}.mlp.2.bias")))
-            if self.mlp_f16f8:       # (fp16 plane, e4m3 pair plane, lo_scale) of the MLP weights for the npass = 2 GEMM
+            if self.mlp_f16f8:       # (fp16 plane, e4m3 pair plane, lo_scale) of the QKV / MLP weights for the npass = 2 GEMM
+                self.layers[-1]["wqkv_f8"] = ops.pack_f16f8(wqkv.to(dev, torch.float32).contiguous())
                 self.layers[-1]["w1_f8"] = ops.pack_f16f8(sd[f"{p}.mlp.0.weight"].to(dev, torch.float32).contiguous())
                 self.layers[-1]["w2_f8"] = ops.pack_f16f8(sd[f"{p}.mlp.2.weight"].to(dev, torch.float32).contiguous())
         self.ln_f = (f32("ln_f.weight"), f32("ln_f.bias"))
@@ -175,10 +176,16 @@ class GPTEngine:
         d = self.d
         rows = B * L
         y = torch.empty_like(x)
-        yp = self._planes((rows, d))
-        ops.layernorm(x, *lw["ln1"], y=y, out_hi=yp[0], out_lo=yp[1])
         qkv = self._planes((B, L, 3 * d))
-        self._linear(yp, lw["wqkv"], 3 * d, rows, d, bias=lw["bqkv"], out_planes=qkv)
+        if self.mlp_f16f8 and d % 128 == 0:
+            yp = (torch.empty((rows, d), dtype=torch.float16, device=self.dev), torch.empty((rows, 2 * d), dtype=torch.uint8, device=self.dev))
+            ops.layernorm(x, *lw["ln1"], y=y, out_hi=yp[0], out_lo=yp[1], f16f8=True)
+            wq = lw["wqkv_f8"]
+            self._linear(yp, wq[:2], 3 * d, rows, d, bias=lw["bqkv"], out_planes=qkv, npass=2, lo_scale=wq[2])     # output planes stay bf16 hi/lo
+        else:
+            yp = self._planes((rows, d))
+            ops.layernorm(x, *lw["ln1"], y=y, out_hi=yp[0], out_lo=yp[1])
+            self._linear(yp, lw["wqkv"], 3 * d, rows, d, bias=lw["bqkv"], out_planes=qkv)
         if on_qkv is not None:
             on_qkv(qkv)
         x1 = self.attention(qkv, y, B, L, **(attn_kw or {}))
