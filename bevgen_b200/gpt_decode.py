@@ -29,8 +29,8 @@ def _kslice(K):
 class GPTSampler:
     def __init__(self, engine, batch_size, kv_dtype=None):
         self.eng = e = engine
-        if not e.causal:
-            raise NotImplementedError("KV-cache decoding needs the [cond | causal] mask (causal_order=True, no pad tokens)")
+        if not e.decode_causal:
+            raise NotImplementedError("KV-cache decoding needs the [cond | causal] mask on the real tokens (causal_order=True)")
         self.B = B = batch_size
         self.Bp = ((B + 15) // 16) * 16
         dev, d, H = e.dev, e.d, e.H

@@ -98,6 +98,11 @@ class GPTEngine:
         i, j = torch.meshgrid(torch.arange(self.L), torch.arange(self.L), indexing="ij")
         closed = (j < self.nc) | ((i >= self.nc) & (j <= i))
         self.causal = bool(torch.equal(closed, cfg.attention_mask.bool() | closed) and self.npad == 0)   # mask ⊆ [cond | causal]
+        # KV-cache decoding only needs the closed form on the REAL rows / columns: trailing pad tokens (non-square latents padded to the
+        # block size, mask_generator.py:197-205) are never queried and never visible to a real row, so they are simply ignored
+        real = self.nc + self.n_img
+        am = cfg.attention_mask.bool()
+        self.decode_causal = bool(torch.equal(am[:real, :real], closed[:real, :real]) and not am[:real, real:].any())
         # tiled, pre-scaled fp16 copy for the fused kernel (coalesced 16-byte reads per lane, scale folded into one FFMA per score)
         self.bias_f16 = None if (self.bias is None or self.L % 128) else ops.tile_attention_bias(self.bias, float(self.dh) ** -0.5)
         self.fused_attention = True          # tcgen05 flash-style kernel when the geometry allows; composed path otherwise

@@ -39,6 +39,21 @@ def test_greedy_matches_reference_sampling_loop(golden_dir, use_graph, fuse):
     assert (toks.reshape(B, -1)[:, cfg.forward_shuffle_idx[4:]] == cfg.vocab_size).all()      # untouched positions stay PAD
 
 
+def test_padded_geometry_decodes_like_the_reference_loop():
+    """Non-square latents (7 x 9 per camera, 378 image tokens + 6 pad tokens): the trailing pad tokens are invisible to every real row, so
+    the KV-cache sampler must reproduce the reference's full-forward loop (oracle restatement, pinned by the gpt_padded golden)."""
+    cfg, sd, cam, bev, batch, eng, B = _case("padded")
+    assert cfg.num_pad_tokens > 0
+    geo = gpt_oracle.geo_from_config(cfg)
+    steps = 5
+    want_x, want_rows = gpt_oracle.sample_reference_loop({k: v.cpu() for k, v in sd.items()}, geo, bev, batch, steps)
+    toks, trace = GPTSampler(eng, B).sample(bev, batch, greedy=True, steps=steps, trace_logits=True)
+    torch.cuda.synchronize()
+    got = trace.permute(1, 0, 2).cpu()
+    assert (got - want_rows).abs().max().item() < 1e-3
+    assert torch.equal(toks.cpu(), want_x)
+
+
 def test_teacher_forced_replay_equals_full_forward_reference(golden_dir):
     """All 1536 cached steps on the 1024-wide model (default parity configuration: bf16x3 weights, fp16 KV cache) reproduce the reference's
     full-forward logits (golden rows)."""
