@@ -314,6 +314,13 @@ BEVGEN_API int bevgen_denormalize(const float* x, float* out, int n, int c, int 
   CHECK_LAUNCH(launch_denorm(x, out, n, c, pixels, mean3, std3, g_sm_count, (cudaStream_t)stream), "denormalize");
 }
 
+BEVGEN_API int bevgen_to_uint8_hwc(const float* x_nchw, void* out_nhwc_u8, int n, int c, int pixels, void* stream) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  if (!x_nchw || !out_nhwc_u8) return fail(BEVGEN_ERR_ARG, "to_uint8_hwc: bad args");
+  CHECK_LAUNCH(launch_to_uint8_hwc(x_nchw, (uint8_t*)out_nhwc_u8, n, c, pixels, g_sm_count, (cudaStream_t)stream), "to_uint8_hwc");
+}
+
 BEVGEN_API int bevgen_layernorm(const float* x, long long rows, int d, long long x_row_stride, const float* gamma, const float* beta, float eps,
                                 float* y, void* out_hi, void* out_lo, void* stream) {
   if (!x || !gamma || !beta || (!y && !out_hi)) return fail(BEVGEN_ERR_ARG, "layernorm: bad args");

@@ -323,6 +323,23 @@ int launch_gather_rows(const float* table, const long long* idx, float* out, lon
   return cudaGetLastError() == cudaSuccess ? BEVGEN_OK : BEVGEN_ERR_CUDA;
 }
 
+// fp32 NCHW images in [0,1] -> uint8 NHWC (round to nearest), the layout image encoders want; a quarter of the D2H bytes of the fp32 tensor.
+__global__ void to_uint8_hwc_kernel(const float* __restrict__ x, uint8_t* __restrict__ out, size_t total, int C, int P) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t n = i / ((size_t)C * P), r = i % ((size_t)C * P);
+    const int px = (int)(r / C), c = (int)(r % C);                      // output order: pixel-major, channel fastest
+    const float v = __ldg(x + (n * C + c) * P + px);
+    out[i] = (uint8_t)__float2int_rn(fminf(fmaxf(v, 0.f), 1.f) * 255.0f);
+  }
+}
+
+int launch_to_uint8_hwc(const float* x, uint8_t* out, int N, int C, int P, int sm_count, cudaStream_t st) {
+  if (N < 1 || C < 1 || P < 1) return BEVGEN_ERR_ARG;
+  const size_t total = (size_t)N * C * P;
+  to_uint8_hwc_kernel<<<grid_for(total, 256, sm_count), 256, 0, st>>>(x, out, total, C, P);
+  return cudaGetLastError() == cudaSuccess ? BEVGEN_OK : BEVGEN_ERR_CUDA;
+}
+
 int launch_denorm(const float* x, float* out, int N, int C, int P, const float* mean, const float* std_, int sm_count, cudaStream_t st) {
   if (C != 3) return BEVGEN_ERR_ARG;
   size_t total = (size_t)N * C * P;

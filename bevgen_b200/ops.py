@@ -211,6 +211,17 @@ def codebook_gather(codebook, idx, out):
                                           _stream()), "codebook_gather")
 
 
+def to_uint8_hwc(x_nchw, out=None):
+    """fp32 (N, C, H, W) in [0, 1] on the GPU -> uint8 (N, H, W, C)."""
+    lib = _lib.init()
+    Stats.launches += 1
+    n, c, h, w = x_nchw.shape
+    out = torch.empty((n, h, w, c), dtype=torch.uint8, device=x_nchw.device) if out is None else out
+    _chk_cuda(x_nchw, out)
+    _lib.check(lib.bevgen_to_uint8_hwc(_ptr(x_nchw), _ptr(out), n, c, h * w, _stream()), "to_uint8_hwc")
+    return out
+
+
 def denormalize(x_nchw, out, mean, std):
     lib = _lib.init()
     Stats.launches += 1

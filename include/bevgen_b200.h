@@ -155,6 +155,9 @@ BEVGEN_API int bevgen_codebook_gather(const float* codebook, const long long* id
 
 /* bev_utils/util.py:97-118 denormalize_tensor(keep_tensor=True) on fp32 NCHW, 3 channels */
 BEVGEN_API int bevgen_denormalize(const float* x, float* out, int n, int c, int pixels, const float* mean3, const float* std3, void* stream);
+/* fp32 NCHW images in [0,1] -> uint8 NHWC, round to nearest (the device half of GenerateImages.save_raw_data / save_img,
+ * utils/callback.py:28-30,72-132: what leaves the GPU is a quarter of the fp32 bytes, already in the layout the JPEG encoder wants). */
+BEVGEN_API int bevgen_to_uint8_hwc(const float* x_nchw, void* out_nhwc_u8, int n, int c, int pixels, void* stream);
 
 /* ---------------------------------------------------------------- stage-2 transformer */
 
