@@ -348,9 +348,10 @@ BEVGEN_API int bevgen_embed_assemble(const bevgen_embed_args* a, void* stream) {
 }
 
 BEVGEN_API int bevgen_attn_softmax(const float* s, const float* bias, const unsigned char* mask, long long zrows, int L, int Lk, float scale,
-                                   void* out_hi, void* out_lo, void* stream) {
+                                   void* out_hi, void* out_lo, const unsigned char* layout, int heads, int block, int layout_ld, void* stream) {
   if (!s || !mask || !out_hi) return fail(BEVGEN_ERR_ARG, "attn_softmax: bad args");
-  CHECK_LAUNCH(launch_attn_softmax(s, bias, mask, (uint16_t*)out_hi, (uint16_t*)out_lo, zrows, L, Lk, scale, (cudaStream_t)stream), "attn_softmax");
+  CHECK_LAUNCH(launch_attn_softmax(s, bias, mask, (uint16_t*)out_hi, (uint16_t*)out_lo, zrows, L, Lk, scale, layout, heads, block, layout_ld,
+                                   (cudaStream_t)stream), "attn_softmax");
 }
 
 BEVGEN_API int bevgen_attn_fused_fwd(const void* qkv_hi, const void* qkv_lo, int batch, int seq_len, int heads, int d, int n_cond,
@@ -400,14 +401,14 @@ BEVGEN_API int bevgen_dec_attention(const float* qkv_partials, int ks, long long
                                     const float* camera_bias, int bias_ld, void* k_cache, void* v_cache, int kv_bf16, float* x1,
                                     const int* step_ptr, float* workspace, unsigned int* counters, int batch, int n_cond, int heads, int d,
                                     int lmax, float scale, unsigned int* row_counters, const float* ln_gamma, const float* ln_beta, float ln_eps,
-                                    void* ln_hi, void* ln_lo, void* stream) {
+                                    void* ln_hi, void* ln_lo, const unsigned char* layout, int layout_block, int layout_ld, void* stream) {
   int rc0 = ensure_init();
   if (rc0) return rc0;
   if (!qkv_partials || !qkv_bias || !y || !k_cache || !v_cache || !x1 || !step_ptr || !workspace || !counters || ks < 1)
     return fail(BEVGEN_ERR_ARG, "dec_attention: bad args");
   CHECK_LAUNCH(launch_dec_attn(qkv_partials, ks, zstride, qkv_bias, y, camera_bias, bias_ld, k_cache, v_cache, kv_bf16, x1, step_ptr, workspace,
                                counters, batch, n_cond, heads, d, lmax, scale, row_counters, ln_gamma, ln_beta, ln_eps, (uint16_t*)ln_hi,
-                               (uint16_t*)ln_lo, g_sm_count, (cudaStream_t)stream), "dec_attention");
+                               (uint16_t*)ln_lo, layout, layout_block, layout_ld, g_sm_count, (cudaStream_t)stream), "dec_attention");
 }
 
 BEVGEN_API int bevgen_dec_attention_workspace_floats(int batch, int heads) { return dec_attn_workspace_floats(batch, heads); }

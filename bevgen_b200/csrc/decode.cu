@@ -180,7 +180,8 @@ __global__ void __launch_bounds__(256) dec_attn_kernel(const float* __restrict__
                                                        float* __restrict__ ws, unsigned int* __restrict__ counters, int nc, int H, int d,
                                                        int Lmax, float scale, unsigned int* __restrict__ row_counters,
                                                        const float* __restrict__ ln_gamma, const float* __restrict__ ln_beta, float ln_eps,
-                                                       uint16_t* __restrict__ ln_hi, uint16_t* __restrict__ ln_lo) {
+                                                       uint16_t* __restrict__ ln_hi, uint16_t* __restrict__ ln_lo,
+                                                       const uint8_t* __restrict__ layout, int lay_blk, int lay_ld) {
   extern __shared__ __align__(128) uint8_t dsm[];
   KVT* Ks = reinterpret_cast<KVT*>(dsm);                                  // [CK / 128 cache blocks][64][128]
   KVT* Vs = reinterpret_cast<KVT*>(dsm + 64 * CK * sizeof(KVT));          // [keys][64]
@@ -245,10 +246,12 @@ __global__ void __launch_bounds__(256) dec_attn_kernel(const float* __restrict__
         d1 = fmaf(q[c + 1], kv_load(kcol + (c + 1) * DEC_CHUNK), d1);
       }
       m = ((d0 + d1) + (brow ? brow[tid] : 0.f)) * scale;
+      // per-head block layout (density < 1): key block (j0 + tid) / blk of query block r / blk absent -> not attended
+      if (layout != nullptr && !layout[((size_t)h * lay_ld + r / lay_blk) * lay_ld + (j0 + tid) / lay_blk]) m = -INFINITY;
     }
     const float mloc = block_max_256(m, red);
     float e = 0.f;
-    if (tid < cnt) { e = expf(m - mloc); sc[tid] = e; }
+    if (tid < cnt) { e = (m == -INFINITY) ? 0.f : expf(m - mloc); sc[tid] = e; }
     sum = block_sum_256(e, red);       // its barriers publish sc[]
     m = mloc;
     const int g = tid >> 6, c = tid & 63;
@@ -498,9 +501,10 @@ int dec_attn_workspace_floats(int B, int H) { return B * H * DEC_MAX_SPLIT * DEC
 int launch_dec_attn(const float* qkv_part, int ks, long long zstride, const float* bqkv, const float* y, const float* bias, int bias_ld,
                     void* kc, void* vc, int kv_bf16, float* x1, const int* step_ptr, float* ws, unsigned int* counters, int B, int nc, int H,
                     int d, int Lmax, float scale, unsigned int* row_counters, const float* ln_gamma, const float* ln_beta, float ln_eps,
-                    uint16_t* ln_hi, uint16_t* ln_lo, int /*sm_count*/, cudaStream_t st) {
+                    uint16_t* ln_hi, uint16_t* ln_lo, const uint8_t* layout, int lay_blk, int lay_ld, int /*sm_count*/, cudaStream_t st) {
   if (Lmax > DEC_MAXL || B < 1 || B > 65535 || d != H * 64 || (Lmax & 127) || dec_splits(Lmax) > DEC_MAX_SPLIT) return BEVGEN_ERR_ARG;
   if (ln_gamma != nullptr && (!row_counters || !ln_beta || !ln_hi || d > 1024)) return BEVGEN_ERR_ARG;
+  if (layout != nullptr && (lay_blk < 1 || lay_ld < 1)) return BEVGEN_ERR_ARG;
   dim3 grid(H, B, dec_splits(Lmax, kv_bf16 ? 256 : DEC_CHUNK));
   if (kv_bf16) {
     static bool configured2 = false;
@@ -514,11 +518,11 @@ int launch_dec_attn(const float* qkv_part, int ks, long long zstride, const floa
   if (kv_bf16 == 2) {           // fp16 cache: half the KV bytes of the fp32 cache at ~3e-4 logit error (tests/test_decode_gpu.py)
     const int smem = 2 * 64 * 256 * 2;
     if (launch_k(dec_attn_kernel<__half, 256>, grid, dim3(256), smem, st, qkv_part, ks, zstride, bqkv, y, bias, bias_ld, (__half*)kc, (__half*)vc, x1, step_ptr,
-                 ws, counters, nc, H, d, Lmax, scale, row_counters, ln_gamma, ln_beta, ln_eps, ln_hi, ln_lo) != cudaSuccess) return BEVGEN_ERR_CUDA;
+                 ws, counters, nc, H, d, Lmax, scale, row_counters, ln_gamma, ln_beta, ln_eps, ln_hi, ln_lo, layout, lay_blk, lay_ld) != cudaSuccess) return BEVGEN_ERR_CUDA;
   } else if (kv_bf16) {
     const int smem = 2 * 64 * 256 * 2;
     if (launch_k(dec_attn_kernel<__nv_bfloat16, 256>, grid, dim3(256), smem, st, qkv_part, ks, zstride, bqkv, y, bias, bias_ld, (__nv_bfloat16*)kc,
-                 (__nv_bfloat16*)vc, x1, step_ptr, ws, counters, nc, H, d, Lmax, scale, row_counters, ln_gamma, ln_beta, ln_eps, ln_hi, ln_lo) !=
+                 (__nv_bfloat16*)vc, x1, step_ptr, ws, counters, nc, H, d, Lmax, scale, row_counters, ln_gamma, ln_beta, ln_eps, ln_hi, ln_lo, layout, lay_blk, lay_ld) !=
         cudaSuccess) return BEVGEN_ERR_CUDA;
   } else {
     const int smem = 2 * 64 * DEC_CHUNK * 4;
@@ -528,7 +532,7 @@ int launch_dec_attn(const float* qkv_part, int ks, long long zstride, const floa
       configured = true;
     }
     if (launch_k(dec_attn_kernel<float, DEC_CHUNK>, grid, dim3(256), smem, st, qkv_part, ks, zstride, bqkv, y, bias, bias_ld, (float*)kc, (float*)vc, x1, step_ptr, ws,
-                 counters, nc, H, d, Lmax, scale, row_counters, ln_gamma, ln_beta, ln_eps, ln_hi, ln_lo) != cudaSuccess) return BEVGEN_ERR_CUDA;
+                 counters, nc, H, d, Lmax, scale, row_counters, ln_gamma, ln_beta, ln_eps, ln_hi, ln_lo, layout, lay_blk, lay_ld) != cudaSuccess) return BEVGEN_ERR_CUDA;
   }
   return cudaGetLastError() == cudaSuccess ? BEVGEN_OK : BEVGEN_ERR_CUDA;
 }

@@ -77,7 +77,7 @@ int launch_layernorm(const float* x, const float* gamma, const float* beta, floa
                      long long x_row_stride, float eps, int f16f8, cudaStream_t st);
 int launch_embed(const EmbedParams& p, cudaStream_t st);
 int launch_attn_softmax(const float* S, const float* bias, const uint8_t* mask, uint16_t* hi, uint16_t* lo, long long zrows, int L, int Lk,
-                        float scale, cudaStream_t st);
+                        float scale, const uint8_t* layout, int H, int blk, int lay_ld, cudaStream_t st);
 
 struct ConvHaloParams {
   CUtensorMap tmA[2];      // 5D (c8, w, h, chunk, n), box (8, 10, 18, 8, 1), no swizzle
@@ -123,7 +123,7 @@ int launch_kv_store(const uint16_t* hi, const uint16_t* lo, void* kc, void* vc, 
 int launch_dec_attn(const float* qkv_part, int ks, long long zstride, const float* bqkv, const float* y, const float* bias, int bias_ld,
                     void* kc, void* vc, int kv_bf16, float* x1, const int* step_ptr, float* ws, unsigned int* counters, int B, int nc, int H,
                     int d, int Lmax, float scale, unsigned int* row_counters, const float* ln_gamma, const float* ln_beta, float ln_eps,
-                    uint16_t* ln_hi, uint16_t* ln_lo, int sm_count, cudaStream_t st);
+                    uint16_t* ln_hi, uint16_t* ln_lo, const uint8_t* layout, int lay_blk, int lay_ld, int sm_count, cudaStream_t st);
 int dec_attn_workspace_floats(int B, int H);
 int launch_dec_sample(const float* part, int ks, long long zstride, int vpad, int V, float temperature, int top_k, int greedy,
                       unsigned long long seed, const long long* forced, const int* fwd, long long* cam_idx, long long* tokens_out, float* trace,

@@ -174,11 +174,14 @@ constexpr int ATT_MAXJ = 80;  // L <= 2560
 
 __global__ void __launch_bounds__(256) attn_softmax_kernel(const float* __restrict__ S, const float* __restrict__ bias,
                                                            const uint8_t* __restrict__ mask, uint16_t* __restrict__ hi,
-                                                           uint16_t* __restrict__ lo, long long zrows, int L, int Lk, float scale) {
+                                                           uint16_t* __restrict__ lo, long long zrows, int L, int Lk, float scale,
+                                                           const uint8_t* __restrict__ layout, int H, int blk, int lay_ld) {
   const int lane = threadIdx.x & 31;
   const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= zrows) return;
   const int i = (int)(r % L);
+  // per-head block layout (sparse_self_attention.py:59-60,153-173, density < 1): key block c / blk of query block i / blk present?
+  const uint8_t* lr = layout ? layout + ((size_t)((r / L) % H) * lay_ld + i / blk) * lay_ld : nullptr;
   const float* sr = S + r * Lk;
   const float* br = bias ? bias + (size_t)i * Lk : nullptr;
   const uint8_t* mr = mask + (size_t)i * Lk;
@@ -190,7 +193,7 @@ __global__ void __launch_bounds__(256) attn_softmax_kernel(const float* __restri
     if (j < per) {
       const int c = j * 32 + lane;
       float x = -INFINITY;
-      if (c < Lk && mr[c]) x = (sr[c] + (br ? br[c] : 0.f)) * scale;
+      if (c < Lk && mr[c] && (lr == nullptr || lr[c / blk])) x = (sr[c] + (br ? br[c] : 0.f)) * scale;
       v[j] = x;
       m = fmaxf(m, x);
     }
@@ -221,9 +224,9 @@ __global__ void __launch_bounds__(256) attn_softmax_kernel(const float* __restri
 }
 
 int launch_attn_softmax(const float* S, const float* bias, const uint8_t* mask, uint16_t* hi, uint16_t* lo, long long zrows, int L, int Lk,
-                        float scale, cudaStream_t st) {
-  if (Lk > 32 * ATT_MAXJ || Lk < 1 || zrows < 1) return BEVGEN_ERR_ARG;
-  attn_softmax_kernel<<<(unsigned)((zrows + 7) / 8), 256, 0, st>>>(S, bias, mask, hi, lo, zrows, L, Lk, scale);
+                        float scale, const uint8_t* layout, int H, int blk, int lay_ld, cudaStream_t st) {
+  if (Lk > 32 * ATT_MAXJ || Lk < 1 || zrows < 1 || (layout && (H < 1 || blk < 1 || lay_ld * blk < L || lay_ld * blk < Lk))) return BEVGEN_ERR_ARG;
+  attn_softmax_kernel<<<(unsigned)((zrows + 7) / 8), 256, 0, st>>>(S, bias, mask, hi, lo, zrows, L, Lk, scale, layout, H, blk, lay_ld);
   return cudaGetLastError() == cudaSuccess ? BEVGEN_OK : BEVGEN_ERR_CUDA;
 }
 

@@ -61,6 +61,9 @@ class GPTSampler:
         full_cc = bool(self.mask_cc.all())      # cond rows see every cond column: the fused kernel's "all cond" case
         self.bias_cc_f16 = ops.tile_attention_bias(torch.zeros((e.nc, e.nc), device=dev) if self.bias_cc is None else self.bias_cc,
                                                    float(e.dh) ** -0.5) if (full_cc and e.nc % 128 == 0) else None
+        # per-layer block layouts (density < 1): full [H][nb][nb] for the decode rows, contiguous cond x cond corner for the prefill
+        ncb = e.nc // e.layout_block
+        self.lay_cc = None if e.layouts is None else [l[:, :ncb, :ncb].contiguous() for l in e.layouts]
         self.attn_ws = f32(_lib.load().bevgen_dec_attention_workspace_floats(B, H))
         self.attn_cnt = torch.zeros(B * H, dtype=torch.int32, device=dev)
         self.row_cnt = torch.zeros(B, dtype=torch.int32, device=dev)
@@ -140,7 +143,8 @@ class GPTSampler:
                                                 _ptr(self.attn_cnt), self.B, e.nc, H, d, self.Lmax, float(e.dh) ** -0.5,
                                                 _ptr(self.row_cnt) if f2 else None, _ptr(lw["ln2"][0]) if f2 else None,
                                                 _ptr(lw["ln2"][1]) if f2 else None, 1e-5, _ptr(self.zp[0]) if f2 else None,
-                                                _ptr(self.zp[1]) if f2 else None, _stream()), "dec_attention")
+                                                _ptr(self.zp[1]) if f2 else None, _ptr(lw.get("layout")), e.layout_block,
+                                                0 if lw.get("layout") is None else lw["layout"].shape[-1], _stream()), "dec_attention")
             last = li == len(e.layers) - 1
             nxt = e.ln_f if last else e.layers[li + 1]["ln1"]
             if fz:
@@ -175,7 +179,8 @@ class GPTSampler:
                 _lib.check(lib.bevgen_kv_store(_ptr(qkv[0]), _ptr(qkv[1]), _ptr(self.kc[li]), _ptr(self.vc[li]), self.kv_bf16, B, nc, nc, e.H, d,
                                                self.Lmax, _stream()), "kv_store")
             x = e.block(x, lw, B, nc, attn_kw=dict(bias=self.bias_cc, mask=self.mask_cc, causal=False, allowed=float(nc * nc),
-                                                    fused_cond=self.bias_cc_f16), on_qkv=store)
+                                                    fused_cond=self.bias_cc_f16, layout=None if self.lay_cc is None else self.lay_cc[li]),
+                        on_qkv=store)
         # logits of decode-order token 0 come from the last conditioning row (mingpt_sparse.py:390)
         self._last = x
         self._reduce_ln(None, 0, None, x.view(-1)[(nc - 1) * d:], nc * d, e.ln_f, None, self.fp)

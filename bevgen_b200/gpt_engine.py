@@ -48,8 +48,18 @@ class GPTEngine:
         if self.dh != 64:
             raise ValueError(f"head size {self.dh}: the attention kernels are built for d_head = 64")
         self.L, self.nc, self.n_img, self.npad = cfg.gpt_block_size, cfg.num_cond_tokens, cfg.num_img_tokens, cfg.num_pad_tokens
-        if layouts is not None and not cfg.layout_covers_mask(layouts):
-            raise NotImplementedError("block layouts that remove allowed positions (density < 1) are a 'next' row (SURVEY §8f-2)")
+        # Per-head block layouts (DeepSpeed SparsityConfig; density < 1 configs, one layout per layer: [layers][heads][nb][nb] or a single
+        # [heads][nb][nb] shared by all layers).  Layouts that cover the mask (density = 1) change nothing and are dropped; otherwise
+        # the layers run the composed attention path / the layout-aware decode kernel (the fused kernel covers the closed-form mask only).
+        self.layouts = None
+        if layouts is not None:
+            lay = torch.as_tensor(layouts)
+            lay = lay[None].expand(cfg.num_layers, *lay.shape) if lay.dim() == 3 else lay
+            if lay.shape[0] != cfg.num_layers:
+                raise ValueError(f"expected {cfg.num_layers} per-layer layouts, got {lay.shape[0]}")
+            if not all(cfg.layout_covers_mask(l) for l in lay):
+                self.layouts = (lay != 0).to(self.dev, torch.uint8).contiguous()
+        self.layout_block = cfg.sparse_block_size
         f32 = lambda k: sd[k].detach().to(dev, torch.float32).contiguous()
         self.layers = []
         for i in range(cfg.num_layers):
@@ -108,6 +118,9 @@ class GPTEngine:
         self.fused_attention = True          # tcgen05 flash-style kernel when the geometry allows; composed path otherwise
         self._perm_cache = {}
         self._allowed = float(self.mask_u8.sum().item())      # attended (row, col) pairs: algorithmic attention work
+        if self.layouts is not None:
+            for i, lw in enumerate(self.layers):
+                lw["layout"] = self.layouts[i]
 
     # ------------------------------------------------------------------ helpers
     def _planes(self, shape):
@@ -141,11 +154,13 @@ class GPTEngine:
         ops.embed_assemble(a)
         return out
 
-    def attention(self, qkv, y, B, L, bias="full", mask=None, causal=None, allowed=None, fused_cond=None):
+    def attention(self, qkv, y, B, L, bias="full", mask=None, causal=None, allowed=None, fused_cond=None, layout=None):
         """qkv planes [B, L, 3d]; returns x1 = y + concat_heads(softmax(scale*(QK^T + bias))V) as fp32 [B, L, d].
         bias/mask default to the full-sequence camera bias and attention mask; the KV-cache prefill passes the cond x cond blocks."""
         d, H, dh = self.d, self.H, self.dh
-        if self.fused_attention and isinstance(bias, str) and mask is None and self.causal and L % 128 == 0 and self.nc % 128 == 0:
+        if layout is not None:
+            fused_cond = None
+        if self.fused_attention and layout is None and isinstance(bias, str) and mask is None and self.causal and L % 128 == 0 and self.nc % 128 == 0:
             x1 = torch.empty((B, L, d), dtype=torch.float32, device=self.dev)
             ops.attn_fused_fwd(qkv[0], qkv[1], B, L, H, d, self.nc, self.bias_f16, y, x1, float(dh) ** -0.5, self.npass,
                                algo_flops=4.0 * B * H * dh * self._allowed)
@@ -168,7 +183,7 @@ class GPTEngine:
                     out_zi_stride=L * L, ldc=L, out_f32=S, flags=cz, causal_ncond=self.nc, bn=128, npass=self.npass,
                     algo_flops=2.0 * B * H * dh * allowed)
         p_hi, p_lo = self._planes((B, H, L, L))
-        ops.attn_softmax(S, bias, mask, p_hi, p_lo, L, float(dh) ** -0.5)
+        ops.attn_softmax(S, bias, mask, p_hi, p_lo, L, float(dh) ** -0.5, layout=layout, heads=H, block=self.layout_block)
         x1 = torch.empty((B, L, d), dtype=torch.float32, device=self.dev)
         kz = ops.GF_CAUSAL_KLIMIT if causal else 0
         ops.gemm_tc(a_hi=p_hi, a_lo=p_lo, a_dims=(B * H, 1, L, L), b_hi=flat(q_hi), b_lo=flat(q_lo), k=L, n_cols=dh, a_n_mul=H, a_n_zstride=1,
@@ -193,7 +208,10 @@ class GPTEngine:
             self._linear(yp, lw["wqkv"], 3 * d, rows, d, bias=lw["bqkv"], out_planes=qkv)
         if on_qkv is not None:
             on_qkv(qkv)
-        x1 = self.attention(qkv, y, B, L, **(attn_kw or {}))
+        akw = dict(attn_kw or {})
+        if "layout" not in akw and lw.get("layout") is not None:
+            akw["layout"] = lw["layout"]
+        x1 = self.attention(qkv, y, B, L, **akw)
         x2 = torch.empty_like(x)
         if self.mlp_f16f8 and d % 128 == 0:
             # MLP as f16f8 GEMMs: LayerNorm and the GELU epilogue write the fp16 + e4m3-pair operand planes directly

@@ -250,13 +250,14 @@ def embed_assemble(args: "EmbedArgs"):
     _lib.check(lib.bevgen_embed_assemble(C.byref(args), _stream()), "embed_assemble")
 
 
-def attn_softmax(S, bias, mask_u8, out_hi, out_lo, L, scale):
+def attn_softmax(S, bias, mask_u8, out_hi, out_lo, L, scale, layout=None, heads=1, block=16):
+    """layout: optional uint8 [heads][nb][nb] per-head block layout (density < 1); rows of S are ordered [batch][head][query]."""
     lib = _lib.init()
     Stats.launches += 1
-    _chk_cuda(S, bias, mask_u8, out_hi, out_lo)
+    _chk_cuda(S, bias, mask_u8, out_hi, out_lo, layout)
     Lk = S.shape[-1]
     _lib.check(lib.bevgen_attn_softmax(_ptr(S), _ptr(bias), _ptr(mask_u8), S.numel() // Lk, L, Lk, float(scale), _ptr(out_hi), _ptr(out_lo),
-                                       _stream()), "attn_softmax")
+                                       _ptr(layout), heads, block, 0 if layout is None else layout.shape[-1], _stream()), "attn_softmax")
 
 
 def tile_attention_bias(bias: torch.Tensor, scale: float) -> torch.Tensor:

@@ -196,7 +196,10 @@ BEVGEN_API int bevgen_embed_assemble(const bevgen_embed_args* args, void* stream
 /* P = softmax_j(scale * (S + bias)) over mask != 0, zeros elsewhere (sparse_self_attention.py:153-173, dense form).
  * S fp32 [zrows][Lk] with zrows = batch*heads*L rows, bias fp32 [L][Lk] or NULL, mask uint8 [L][Lk]. */
 BEVGEN_API int bevgen_attn_softmax(const float* s, const float* bias, const unsigned char* mask, long long zrows, int L, int Lk, float scale,
-                                   void* out_hi, void* out_lo, void* stream);
+                                   void* out_hi, void* out_lo, const unsigned char* layout, int heads, int block, int layout_ld, void* stream);
+/* layout (may be NULL): per-head block layout of DeepSpeed's SparsityConfig (sparse_self_attention.py:59-60; density < 1 configs),
+ * uint8 [heads][layout_ld][layout_ld], nonzero = the (query block, key block) pair of `block` x `block` positions is attended; rows of s
+ * are ordered [batch][head][query]. */
 
 /* Fused attention forward (one kernel for sparse_self_attention.py:153-176 + the residual add of mingpt_sparse.py:250):
  *   x1[b,i,h*64:(h+1)*64] = y[...] + sum_j softmax_j(scale * (q_i.k_j + bias[i][j])) v_j,  allowed(i,j) = j < n_cond || (i >= n_cond && j <= i)
@@ -231,7 +234,9 @@ BEVGEN_API int bevgen_dec_attention(const float* qkv_partials, int ks, long long
                                     const float* camera_bias, int bias_ld, void* k_cache, void* v_cache, int kv_bf16, float* x1,
                                     const int* step_ptr, float* workspace, unsigned int* counters, int batch, int n_cond, int heads, int d,
                                     int lmax, float scale, unsigned int* row_counters, const float* ln_gamma, const float* ln_beta, float ln_eps,
-                                    void* ln_hi, void* ln_lo, void* stream);
+                                    void* ln_hi, void* ln_lo, const unsigned char* layout, int layout_block, int layout_ld, void* stream);
+/* layout (may be NULL): this layer's per-head block layout uint8 [heads][layout_ld][layout_ld] (density < 1), see bevgen_attn_softmax.
+ * k/v cache element type: kv_bf16 = 0 fp32, 1 bf16, 2 fp16. */
 BEVGEN_API int bevgen_dec_attention_workspace_floats(int batch, int heads);
 /* sampling tail (cond_transformer_multi_view.py:138-142,200-219): logits/T, top-k (ties kept), softmax, multinomial|greedy|forced.
  * forced_tokens[batch][n_img] (decode order, may be NULL): entries >= 0 replace the drawn token (teacher-forced replay, partial decoding of

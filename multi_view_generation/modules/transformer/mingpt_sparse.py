@@ -109,7 +109,9 @@ class GPT(nn.Module):
         key = (p.device, self.precision, tuple(q._version for q in self.parameters()))
         if self._engine is None or self._engine_key != key:
             sd = {k: v.detach() for k, v in self.state_dict().items()}
-            layouts = self.blocks[0].attention.sparse_self_attention.master_layout if self.cfg.density < 1.0 else None
+            # one layout per layer (each CustomSparseSelfAttention draws / loads its own master_layout, reference :143-154,177)
+            layouts = (torch.stack([blk.attention.sparse_self_attention.master_layout for blk in self.blocks])
+                       if self.cfg.density < 1.0 else None)
             self._engine = GPTEngine(sd, self.cfg, device=p.device, precision=self.precision, layouts=layouts)
             self._engine_key, self._samplers = key, {}
         return self._engine

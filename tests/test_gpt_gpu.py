@@ -91,3 +91,42 @@ def test_fused_attention_matches_composed(npass):
     print(f"[npass={npass}] fused err {e_f:.2e} composed err {e_c:.2e}")
     assert torch.isfinite(fused).all()
     assert e_f < (3e-4 if npass == 3 else 3e-2)
+
+
+def _random_layouts(cfg, seed=0, keep=0.5):
+    """Per-layer, per-head block layouts that REMOVE allowed positions (density < 1) but keep the diagonal and the first key block,
+    so that no row is fully masked (an all-masked row is NaN in the reference too, README.md:113)."""
+    nb = cfg.gpt_block_size // cfg.sparse_block_size
+    g = torch.Generator().manual_seed(seed)
+    lay = torch.rand(cfg.num_layers, cfg.num_heads, nb, nb, generator=g) < keep
+    lay |= torch.eye(nb, dtype=torch.bool)[None, None]
+    lay[..., 0] = True
+    return lay.long()
+
+
+def test_block_sparse_layouts_forward_and_decode_vs_oracle():
+    """per-head block layouts of density < 1 (sparse_self_attention.py:59-60,153-173).  Teacher-forced forward against the
+    CPU oracle's dense restatement with the same layouts, and the KV-cache sampler replaying the same tokens against that forward."""
+    from bevgen_b200.gpt_decode import GPTSampler
+    kw, B = GPT_CASES["small"]
+    cfg = GPTConfig(**kw)
+    sd = synth.gpt_state_dict(gpt_sizes(cfg), seed=2)
+    cam, bev, batch = synth.stage2_inputs(B, cfg.num_cams, cfg.num_cam_tokens, cfg.num_cond_tokens, cfg.vocab_size, cfg.cond_vocab_size, seed=4)
+    layouts = _random_layouts(cfg)
+    assert not cfg.layout_covers_mask(layouts[0])
+    eng = GPTEngine(sd, cfg, device="cuda:0", precision="fp32x3", layouts=layouts)
+    assert eng.layouts is not None
+    got = eng.forward(cam.cuda(), bev.cuda(), batch, sampling=True)
+    dense = GPTEngine(sd, cfg, device="cuda:0", precision="fp32x3").forward(cam.cuda(), bev.cuda(), batch, sampling=True)
+    geo = gpt_oracle.geo_from_config(cfg)
+    with torch.no_grad():
+        want = gpt_oracle.forward({k: v.cpu() for k, v in sd.items()}, geo, cam, bev, batch, sampling=True, layouts=layouts)
+    err = (got.cpu() - want).abs().max().item()
+    print(f"[small, density<1] logits err vs oracle {err:.2e}; change vs dense {(got - dense).abs().max().item():.2e}")
+    assert err < LOGIT_TOL
+    assert (got - dense).abs().max().item() > 10 * LOGIT_TOL          # the layouts really removed attended positions
+    forced = cam.reshape(B, -1)[:, cfg.forward_shuffle_idx]
+    toks, trace = GPTSampler(eng, B).sample(bev, batch, forced_tokens=forced, trace_logits=True, steps=300)
+    torch.cuda.synchronize()
+    ref_rows = got[:, cfg.forward_shuffle_idx.cuda()[:300]].permute(1, 0, 2)
+    assert (trace[:300] - ref_rows).abs().max().item() < 2e-4
