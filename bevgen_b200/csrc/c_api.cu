@@ -314,6 +314,17 @@ BEVGEN_API int bevgen_denormalize(const float* x, float* out, int n, int c, int 
   CHECK_LAUNCH(launch_denorm(x, out, n, c, pixels, mean3, std3, g_sm_count, (cudaStream_t)stream), "denormalize");
 }
 
+BEVGEN_API int bevgen_conv_in3(const float* x_nchw, const float* weight_oihw, const float* bias, float* out_nhwc, double* gn_sums, int n, int h, int w,
+                               int cout, void* stream) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  if (!x_nchw || !weight_oihw || !out_nhwc) return fail(BEVGEN_ERR_ARG, "conv_in3: bad args");
+  if (!(cout == 64 || cout == 128)) return fail(BEVGEN_ERR_ARG, "conv_in3: cout must be 64 or 128 (got %d)", cout);
+  if (gn_sums != nullptr && cudaMemsetAsync(gn_sums, 0, (size_t)n * 64 * sizeof(double), (cudaStream_t)stream) != cudaSuccess)
+    return fail(BEVGEN_ERR_CUDA, "conv_in3: memset failed");
+  CHECK_LAUNCH(launch_conv_in3(x_nchw, weight_oihw, bias, out_nhwc, gn_sums, n, h, w, cout, g_sm_count, (cudaStream_t)stream), "conv_in3");
+}
+
 BEVGEN_API int bevgen_to_uint8_hwc(const float* x_nchw, void* out_nhwc_u8, int n, int c, int pixels, void* stream) {
   int rc = ensure_init();
   if (rc) return rc;

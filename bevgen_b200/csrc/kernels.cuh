@@ -67,6 +67,8 @@ int launch_im2col3x3(const float* x, uint16_t* hi, uint16_t* lo, int N, int Cin,
 int launch_transpose(const float* src, float* dst, int N, int R, int Cc, cudaStream_t st);
 int launch_softmax_rows(const float* s, uint16_t* hi, uint16_t* lo, long long rows, int cols, int out_ld, float scale, cudaStream_t st);
 int launch_gather_rows(const float* table, const long long* idx, float* out, long long rows, int D, int n_table, int sm_count, cudaStream_t st);
+int launch_conv_in3(const float* x, const float* w, const float* bias, float* out, double* gn_sums, int N, int H, int W, int Cout, int sm_count,
+                    cudaStream_t st);
 int launch_to_uint8_hwc(const float* x, uint8_t* out, int N, int C, int P, int sm_count, cudaStream_t st);
 int launch_denorm(const float* x, float* out, int N, int C, int P, const float* mean, const float* std_, int sm_count, cudaStream_t st);
 int launch_row_sqnorm(const float* x, float* out, int rows, int D, cudaStream_t st);

@@ -211,6 +211,25 @@ def codebook_gather(codebook, idx, out):
                                           _stream()), "codebook_gather")
 
 
+def conv_in3(x_nchw, weight_oihw, bias, out_nhwc, gn_sums=None):
+    """Encoder.conv_in for 3-channel inputs: direct fp32 conv NCHW -> NHWC (+ GroupNorm statistics of the output)."""
+    lib = _lib.init()
+    _chk_cuda(x_nchw, weight_oihw, bias, out_nhwc, gn_sums)
+    n, cin, h, w = x_nchw.shape
+    cout = weight_oihw.shape[0]
+    assert cin == 3 and tuple(weight_oihw.shape) == (cout, 3, 3, 3)
+    Stats.launches += 1
+    Stats.gemm_launches += 1
+    flops = 2.0 * n * h * w * cout * 27
+    Stats.gemm_flops += flops
+    call = lambda: _lib.check(lib.bevgen_conv_in3(_ptr(x_nchw), _ptr(weight_oihw), _ptr(bias), _ptr(out_nhwc), _ptr(gn_sums), n, h, w, cout, _stream()),
+                              "conv_in3")
+    if Stats.timer is not None:
+        Stats.timer("conv_small", call, flops)
+    else:
+        call()
+
+
 def to_uint8_hwc(x_nchw, out=None):
     """fp32 (N, C, H, W) in [0, 1] on the GPU -> uint8 (N, H, W, C)."""
     lib = _lib.init()

@@ -66,6 +66,7 @@ class VQGANEngine:
         self.dd = dict(ddconfig)
         self.n_embed, self.embed_dim = n_embed, embed_dim
         self.sd = state_dict
+        self.use_direct_conv_in = True  # RGB conv_in: direct CUDA-core kernel (conv_small.cu) instead of im2col + tcgen05 GEMM
         self.use_block16 = True       # bf16 mode: 16x16-block weight-stationary conv kernel on the large feature maps
         self.use_two_cta = True       # cta_group::2 conv kernel (clusters of two CTAs share each weight tile)
         self.use_fused = True         # conv reads fp32 activations directly; GroupNorm/swish/split/upsample fused into its operand path
@@ -275,10 +276,19 @@ class VQGANEngine:
         """fp32 NCHW image -> fp32 NHWC latent (N, h, w, z_channels)."""
         x_nchw = x_nchw.to(self.dev, torch.float32).contiguous()
         n, cin, H, W = x_nchw.shape
-        hi, lo = self._planes((n, H, W, 64))
-        ops.im2col3x3(x_nchw, hi, lo)
         pc_in = self._conv("encoder.conv_in", True)
-        h = self._gemm_conv((hi, lo), pc_in, self._TAPS1, (n, H, W, 64), (n, H, W), algo_flops=2.0 * n * H * W * pc_in.cout * 9 * cin)
+        if self.use_direct_conv_in and cin == 3 and pc_in.cout in (64, 128):
+            # RGB conv_in as a direct fp32 conv (exact, no im2col plane) with the GroupNorm statistics of its output fused
+            if "conv_in_w32" not in self.w:
+                self.w["conv_in_w32"] = self.sd["encoder.conv_in.weight"].to(self.dev, torch.float32).contiguous()
+            h = torch.empty((n, H, W, pc_in.cout), dtype=torch.float32, device=self.dev)
+            sums = torch.empty(n * 64, dtype=torch.float64, device=self.dev)
+            ops.conv_in3(x_nchw, self.w["conv_in_w32"], pc_in.bias, h, gn_sums=sums)
+            h._gn_sums = sums
+        else:
+            hi, lo = self._planes((n, H, W, 64))
+            ops.im2col3x3(x_nchw, hi, lo)
+            h = self._gemm_conv((hi, lo), pc_in, self._TAPS1, (n, H, W, 64), (n, H, W), algo_flops=2.0 * n * H * W * pc_in.cout * 9 * cin)
         for l in range(self.nlev):
             for b in range(self.nres):
                 h = self.resnet_block(h, f"encoder.down.{l}.block.{b}")

@@ -155,6 +155,11 @@ BEVGEN_API int bevgen_codebook_gather(const float* codebook, const long long* id
 
 /* bev_utils/util.py:97-118 denormalize_tensor(keep_tensor=True) on fp32 NCHW, 3 channels */
 BEVGEN_API int bevgen_denormalize(const float* x, float* out, int n, int c, int pixels, const float* mean3, const float* std3, void* stream);
+/* Encoder.conv_in for RGB inputs (stage1/model.py:355-359): 3x3 "same" conv fp32 NCHW [n][3][h][w] -> fp32 NHWC [n][h][w][cout],
+ * cout = 64 or 128, weights OIHW fp32 as stored in the checkpoint, exact fp32 FMA on the CUDA cores (the implicit-GEMM form pads K = 27
+ * to 64 and needs a 1.6 GB im2col plane per 96 images).  gn_sums (may be NULL): GroupNorm(32) statistics of the output [n][32][2]. */
+BEVGEN_API int bevgen_conv_in3(const float* x_nchw, const float* weight_oihw, const float* bias, float* out_nhwc, double* gn_sums, int n, int h, int w,
+                               int cout, void* stream);
 /* fp32 NCHW images in [0,1] -> uint8 NHWC, round to nearest (the device half of GenerateImages.save_raw_data / save_img,
  * utils/callback.py:28-30,72-132: what leaves the GPU is a quarter of the fp32 bytes, already in the layout the JPEG encoder wants). */
 BEVGEN_API int bevgen_to_uint8_hwc(const float* x_nchw, void* out_nhwc_u8, int n, int c, int pixels, void* stream);

@@ -459,3 +459,24 @@ def test_f16f8_plane_producers_chain():
     assert ((hv - h_ref).abs() <= 2.0 ** -14 * h_ref.abs() + 1e-4).all()
     ref = h_ref @ w2.double().t() + x.double()
     assert (out.double() - ref).abs().max().item() < 3e-4
+
+
+@pytest.mark.parametrize("N_,H,W,Cout", [(2, 64, 64, 128), (3, 37, 70, 64), (1, 256, 256, 128)])
+def test_conv_in3_direct(N_, H, W, Cout):
+    """Direct fp32 conv_in (NCHW RGB -> NHWC, bias, fused GroupNorm statistics) vs torch conv2d."""
+    g = torch.Generator().manual_seed(H + W + Cout)
+    x = torch.randn(N_, 3, H, W, generator=g).to(dev())
+    w = (torch.randn(Cout, 3, 3, 3, generator=g) / 27 ** 0.5).to(dev())
+    b = torch.randn(Cout, generator=g).to(dev())
+    out = torch.full((N_, H, W, Cout), float("nan"), device=dev())
+    sums = torch.full((N_ * 64,), float("nan"), dtype=torch.float64, device=dev())
+    ops.conv_in3(x, w, b, out, gn_sums=sums)
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.double(), w.double(), b.double(), padding=1)
+    assert torch.isfinite(out).all()
+    err = (out.double().permute(0, 3, 1, 2) - ref).abs().max().item()
+    assert err < 1e-5, f"max err {err}"
+    o = out.double().permute(0, 3, 1, 2).reshape(N_, 32, -1)
+    want = torch.stack([o.sum(-1), (o * o).sum(-1)], -1).reshape(-1)
+    rel = ((sums - want).abs() / (1 + want.abs())).max().item()
+    assert rel < 1e-5, f"gn sums rel err {rel}"
