@@ -325,6 +325,16 @@ BEVGEN_API int bevgen_conv_in3(const float* x_nchw, const float* weight_oihw, co
   CHECK_LAUNCH(launch_conv_in3(x_nchw, weight_oihw, bias, out_nhwc, gn_sums, n, h, w, cout, g_sm_count, (cudaStream_t)stream), "conv_in3");
 }
 
+BEVGEN_API int bevgen_conv_out3(const float* x_nhwc, int n, int h, int w, int c, const float* affine, int swish, const float* weight_oihw,
+                                const float* bias, float* out_nchw, void* stream) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  if (!x_nhwc || !weight_oihw || !out_nchw) return fail(BEVGEN_ERR_ARG, "conv_out3: bad args");
+  if (!(c == 64 || c == 128)) return fail(BEVGEN_ERR_ARG, "conv_out3: c must be 64 or 128 (got %d)", c);
+  if (((uintptr_t)x_nhwc & 15) != 0) return fail(BEVGEN_ERR_ARG, "conv_out3: x must be 16-byte aligned");
+  CHECK_LAUNCH(launch_conv_out3(x_nhwc, affine, swish, weight_oihw, bias, out_nchw, n, h, w, c, g_sm_count, (cudaStream_t)stream), "conv_out3");
+}
+
 BEVGEN_API int bevgen_to_uint8_hwc(const float* x_nchw, void* out_nhwc_u8, int n, int c, int pixels, void* stream) {
   int rc = ensure_init();
   if (rc) return rc;

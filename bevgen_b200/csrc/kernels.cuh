@@ -69,6 +69,8 @@ int launch_softmax_rows(const float* s, uint16_t* hi, uint16_t* lo, long long ro
 int launch_gather_rows(const float* table, const long long* idx, float* out, long long rows, int D, int n_table, int sm_count, cudaStream_t st);
 int launch_conv_in3(const float* x, const float* w, const float* bias, float* out, double* gn_sums, int N, int H, int W, int Cout, int sm_count,
                     cudaStream_t st);
+int launch_conv_out3(const float* x, const float* affine, int swish, const float* w, const float* bias, float* out, int N, int H, int W, int C,
+                     int sm_count, cudaStream_t st);
 int launch_to_uint8_hwc(const float* x, uint8_t* out, int N, int C, int P, int sm_count, cudaStream_t st);
 int launch_denorm(const float* x, float* out, int N, int C, int P, const float* mean, const float* std_, int sm_count, cudaStream_t st);
 int launch_row_sqnorm(const float* x, float* out, int rows, int D, cudaStream_t st);

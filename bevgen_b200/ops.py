@@ -230,6 +230,24 @@ def conv_in3(x_nchw, weight_oihw, bias, out_nhwc, gn_sums=None):
         call()
 
 
+def conv_out3(x_nhwc, weight_oihw, bias, out_nchw, affine=None, swish=False):
+    """Decoder.conv_out for 3-channel outputs: GroupNorm-apply + swish + direct fp32 3x3 conv, NHWC -> NCHW."""
+    lib = _lib.init()
+    _chk_cuda(x_nhwc, weight_oihw, bias, out_nchw, affine)
+    n, h, w, c = x_nhwc.shape
+    assert tuple(weight_oihw.shape) == (3, c, 3, 3)
+    Stats.launches += 1
+    Stats.gemm_launches += 1
+    flops = 2.0 * n * h * w * 3 * c * 9
+    Stats.gemm_flops += flops
+    call = lambda: _lib.check(lib.bevgen_conv_out3(_ptr(x_nhwc), n, h, w, c, _ptr(affine), int(swish), _ptr(weight_oihw), _ptr(bias), _ptr(out_nchw),
+                                                   _stream()), "conv_out3")
+    if Stats.timer is not None:
+        Stats.timer("conv_small", call, flops)
+    else:
+        call()
+
+
 def to_uint8_hwc(x_nchw, out=None):
     """fp32 (N, C, H, W) in [0, 1] on the GPU -> uint8 (N, H, W, C)."""
     lib = _lib.init()

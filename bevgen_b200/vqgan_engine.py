@@ -66,6 +66,7 @@ class VQGANEngine:
         self.dd = dict(ddconfig)
         self.n_embed, self.embed_dim = n_embed, embed_dim
         self.sd = state_dict
+        self.use_direct_conv_out = True # RGB conv_out: norm_out + swish + direct CUDA-core conv in one kernel (conv_small.cu)
         self.use_direct_conv_in = True  # RGB conv_in: direct CUDA-core kernel (conv_small.cu) instead of im2col + tcgen05 GEMM
         self.use_block16 = True       # bf16 mode: 16x16-block weight-stationary conv kernel on the large feature maps
         self.use_two_cta = True       # cta_group::2 conv kernel (clusters of two CTAs share each weight tile)
@@ -316,6 +317,22 @@ class VQGANEngine:
             if l != 0:
                 h = self.upsample(h, f"decoder.up.{l}.upsample")
         pc = self._conv("decoder.conv_out")
+        if self.use_direct_conv_out and pc.cout == 3 and h.shape[-1] in (64, 128):
+            # RGB conv_out: GroupNorm-apply + swish + direct fp32 conv in one kernel, NHWC in -> NCHW image out (conv_small.cu)
+            n, hh, ww, c = h.shape
+            gamma, beta = self._norm("decoder.norm_out")
+            sums = getattr(h, "_gn_sums", None)
+            if sums is None:
+                sums = torch.empty(n * 64, dtype=torch.float64, device=self.dev)
+                mr = torch.empty(n * 64, dtype=torch.float32, device=self.dev)
+                ops.groupnorm_stats(h, sums, mr, 1e-6)
+            affine = torch.empty((n, c, 2), dtype=torch.float32, device=self.dev)
+            ops.groupnorm_affine(sums, gamma, beta, affine, n, hh * ww, c, 1e-6)
+            if "conv_out_w32" not in self.w:
+                self.w["conv_out_w32"] = self.sd["decoder.conv_out.weight"].to(self.dev, torch.float32).contiguous()
+            out = torch.empty((n, 3, hh, ww), dtype=torch.float32, device=self.dev)
+            ops.conv_out3(h, self.w["conv_out_w32"], pc.bias, out, affine=affine, swish=True)
+            return out
         if pc.cout < 16:      # image-like outputs (3 / 7 channels): the epilogue writes NCHW directly
             return self.conv3x3(h, "decoder.conv_out", norm="decoder.norm_out", swish=True, nchw=True)
         return self.nhwc_to_nchw(self.conv3x3(h, "decoder.conv_out", norm="decoder.norm_out", swish=True))

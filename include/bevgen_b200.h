@@ -160,6 +160,11 @@ BEVGEN_API int bevgen_denormalize(const float* x, float* out, int n, int c, int 
  * to 64 and needs a 1.6 GB im2col plane per 96 images).  gn_sums (may be NULL): GroupNorm(32) statistics of the output [n][32][2]. */
 BEVGEN_API int bevgen_conv_in3(const float* x_nchw, const float* weight_oihw, const float* bias, float* out_nhwc, double* gn_sums, int n, int h, int w,
                                int cout, void* stream);
+/* Decoder.norm_out -> swish -> conv_out for RGB outputs (stage1/model.py:500-504,533-536): fp32 NHWC [n][h][w][c] (c = 64 or 128) ->
+ * fp32 NCHW [n][3][h][w]; affine = per-(image, channel) GroupNorm (scale, shift) from bevgen_groupnorm_affine or NULL, swish applied
+ * when nonzero; weights OIHW [3][c][3][3] fp32; exact fp32 FMA on the CUDA cores, the input is read once. */
+BEVGEN_API int bevgen_conv_out3(const float* x_nhwc, int n, int h, int w, int c, const float* affine, int swish, const float* weight_oihw,
+                                const float* bias, float* out_nchw, void* stream);
 /* fp32 NCHW images in [0,1] -> uint8 NHWC, round to nearest (the device half of GenerateImages.save_raw_data / save_img,
  * utils/callback.py:28-30,72-132: what leaves the GPU is a quarter of the fp32 bytes, already in the layout the JPEG encoder wants). */
 BEVGEN_API int bevgen_to_uint8_hwc(const float* x_nchw, void* out_nhwc_u8, int n, int c, int pixels, void* stream);

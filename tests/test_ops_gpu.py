@@ -480,3 +480,31 @@ def test_conv_in3_direct(N_, H, W, Cout):
     want = torch.stack([o.sum(-1), (o * o).sum(-1)], -1).reshape(-1)
     rel = ((sums - want).abs() / (1 + want.abs())).max().item()
     assert rel < 1e-5, f"gn sums rel err {rel}"
+
+
+@pytest.mark.parametrize("N_,H,W,C", [(2, 32, 32, 128), (3, 21, 50, 64), (1, 128, 128, 128)])
+def test_conv_out3_direct(N_, H, W, C):
+    """norm_out + swish + conv_out (C -> 3) in one direct fp32 kernel, NHWC -> NCHW, vs torch."""
+    g = torch.Generator().manual_seed(H + W + C)
+    x = (torch.randn(N_, C, H, W, generator=g) * 1.3 + 0.2).to(dev())
+    w = (torch.randn(3, C, 3, 3, generator=g) / (9 * C) ** 0.5).to(dev())
+    b = torch.randn(3, generator=g).to(dev())
+    gamma, beta = (1 + 0.2 * torch.randn(C, generator=g)).to(dev()), (0.2 * torch.randn(C, generator=g)).to(dev())
+    x_nhwc = x.permute(0, 2, 3, 1).contiguous()
+    sums = torch.empty(N_ * 64, dtype=torch.float64, device=dev())
+    mr = torch.empty(N_ * 64, dtype=torch.float32, device=dev())
+    ops.groupnorm_stats(x_nhwc, sums, mr, 1e-6)
+    affine = torch.empty(N_, C, 2, device=dev())
+    ops.groupnorm_affine(sums, gamma, beta, affine, N_, H * W, C, 1e-6)
+    out = torch.full((N_, 3, H, W), float("nan"), device=dev())
+    ops.conv_out3(x_nhwc, w, b, out, affine=affine, swish=True)
+    torch.cuda.synchronize()
+    a = F.group_norm(x.double(), 32, gamma.double(), beta.double(), eps=1e-6)
+    ref = F.conv2d(a * torch.sigmoid(a), w.double(), b.double(), padding=1)
+    assert torch.isfinite(out).all()
+    err = (out.double() - ref).abs().max().item()
+    assert err < 2e-5, f"max err {err}"
+    # no normalisation / activation
+    ops.conv_out3(x_nhwc, w, b, out)
+    torch.cuda.synchronize()
+    assert (out.double() - F.conv2d(x.double(), w.double(), b.double(), padding=1)).abs().max().item() < 2e-5
