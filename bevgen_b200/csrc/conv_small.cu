@@ -161,31 +161,41 @@ __global__ void __launch_bounds__(128, 3) conv_out3_kernel(const float* __restri
       aff_n = n;
     }
     __syncthreads();                                       // previous tile fully consumed
-    // ---- staging: warp handles halo pixels warp, warp + 4, ...; lane = its CPL channels (the same channels it owns in the compute phase)
-    for (int hp = warp; hp < CO_HH * CO_HW; hp += 4) {
-      const int gh = th * CO_TH - 1 + hp / CO_HW, gw = tw * CO_TW - 1 + hp % CO_HW;
-      float v[CPL];
+    // ---- staging: warp handles halo pixels warp, warp + 4, ...; lane = its CPL channels (the same channels it owns in the compute phase).
+    // Loads are issued nine pixels at a time before any of them is consumed (27 pixels per warp = 3 batches): memory-level parallelism.
+    constexpr int SB = 9;
+    static_assert((CO_HH * CO_HW) % (4 * SB) == 0, "halo pixels must split into whole batches");
+#pragma unroll 1
+    for (int b0 = 0; b0 < CO_HH * CO_HW / 4; b0 += SB) {
+      float v[SB][CPL];
+      bool ok[SB];
 #pragma unroll
-      for (int j = 0; j < CPL; ++j) v[j] = 0.f;
-      if (gh >= 0 && gh < H && gw >= 0 && gw < W) {
-        const float* src = x + (((size_t)n * H + gh) * W + gw) * C + lane * CPL;
-        if (CPL == 4) { const float4 q = *reinterpret_cast<const float4*>(src); v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w; }
-        else { const float2 q = *reinterpret_cast<const float2*>(src); v[0] = q.x; v[1] = q.y; }
+      for (int i = 0; i < SB; ++i) {
+        const int hp = warp + 4 * (b0 + i);
+        const int gh = th * CO_TH - 1 + hp / CO_HW, gw = tw * CO_TW - 1 + hp % CO_HW;
+        ok[i] = gh >= 0 && gh < H && gw >= 0 && gw < W;
+        const float* src = x + (((size_t)n * H + (ok[i] ? gh : 0)) * W + (ok[i] ? gw : 0)) * C + lane * CPL;
+        if (CPL == 4) { const float4 q = *reinterpret_cast<const float4*>(src); v[i][0] = q.x; v[i][1] = q.y; v[i][2] = q.z; v[i][3] = q.w; }
+        else { const float2 q = *reinterpret_cast<const float2*>(src); v[i][0] = q.x; v[i][1] = q.y; }
+      }
+#pragma unroll
+      for (int i = 0; i < SB; ++i) {
+        const int hp = warp + 4 * (b0 + i);
 #pragma unroll
         for (int j = 0; j < CPL; ++j) {
-          float a = fmaf(v[j], sc[j], sf[j]);
+          float a = fmaf(v[i][j], sc[j], sf[j]);
           if (swish) {
             float ex, rc;
             asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(a * -1.4426950408889634f));
             asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(1.0f + ex));
             a *= rc;
           }
-          v[j] = a;
+          v[i][j] = ok[i] ? a : 0.f;                        // zero padding applies after the transform
         }
+        float* dst = halo + (size_t)hp * C + lane * CPL;
+        if (CPL == 4) *reinterpret_cast<float4*>(dst) = make_float4(v[i][0], v[i][1], v[i][2], v[i][3]);
+        else *reinterpret_cast<float2*>(dst) = make_float2(v[i][0], v[i][1]);
       }
-      float* dst = halo + (size_t)hp * C + lane * CPL;
-      if (CPL == 4) *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-      else *reinterpret_cast<float2*>(dst) = make_float2(v[0], v[1]);
     }
     __syncthreads();
     // ---- compute: warp = output row th*4 + warp
