@@ -257,7 +257,7 @@ def main():
         g[1] += 1
     dom_flops, (dom_ms, dom_n) = max(groups.items(), key=lambda kv: kv[1][0]) if groups else (0, (0.0, 0))
     achieved = dom_flops / (dom_ms / dom_n / 1e3) / 1e12 if dom_n else 0.0
-    # DRAM traffic of that launch from the committed ncu capture (profiles/r01_conv_fused_ncu_full_summary.json): 3.60 GB read + 3.18 GB written
+    # DRAM traffic of that launch from the committed ncu capture (profiles/r01b_conv_fused2_f16f8_ncu_full_summary.json): 3.60 GB read + 3.18 GB written
     dom_traffic = 6.78e9 if abs(dom_flops - 2.0 * n_img * 256 * 256 * 128 * 128 * 9) < 1e6 and n_img == 96 else None
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -277,7 +277,7 @@ def main():
                                         f"{dom_n} launches/step, {dom_ms / max(dom_n, 1):.3f} ms each (CUDA events, launching stream)",
                      "achieved": achieved, "peak": sustained, "unit": "TFLOP/s", "frac": achieved / sustained,
                      "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({how})", "traffic": dom_traffic,
-                     "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r01_conv_fused_ncu_full_summary.json "
+                     "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r01b_conv_fused2_f16f8_ncu_full_summary.json "
                                        "(algorithmic bytes: 3.22 GB fp32 in + 3.22 GB fp32 out)",
                      # tensor time per algorithmic FLOP relative to one bf16 pass: bf16x3 = 3, f16f8 = 1 fp16 + 2 e4m3 at twice the rate = 2
                      "executed_mma_multiplier": MULT[args.precision],

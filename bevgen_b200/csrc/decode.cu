@@ -272,12 +272,16 @@ __global__ void __launch_bounds__(256) dec_attn_kernel(const float* __restrict__
     wp[4 + tid] = (opart[0][tid] + opart[1][tid]) + (opart[2][tid] + opart[3][tid]);
     if (tid == 0) { wp[0] = m; wp[1] = sum; }
   }
-  __threadfence();
+  // publish the partial: the CTA barrier orders the 64 writers before thread 0, whose single gpu-scope fence + atomic releases them
+  // (fence cumulativity) - one MEMBAR per CTA instead of one per warp, which was 10 % of the kernel's stall samples
   __syncthreads();
-  if (tid == 0) ticket = atomicAdd(&counters[bh], 1u);
+  if (tid == 0) {
+    __threadfence();
+    ticket = atomicAdd(&counters[bh], 1u);
+    __threadfence();                       // acquire side for the last CTA: the other CTAs' partials are visible after the barrier below
+  }
   __syncthreads();
   if (ticket != (unsigned)(S - 1)) return;
-  __threadfence();
   if (tid < 64) {
     const volatile float* wv = ws + bh * S * DEC_WS;
     float M = -INFINITY;
@@ -295,12 +299,14 @@ __global__ void __launch_bounds__(256) dec_attn_kernel(const float* __restrict__
   }
   if (ln_gamma == nullptr) return;
   // ---- fused LayerNorm (ln2) of the finished row: the last head of batch row b normalises x1[b,:] into the MLP operand planes
-  __threadfence();
   __syncthreads();
-  if (tid == 0) ticket = atomicAdd(&row_counters[b], 1u);
+  if (tid == 0) {
+    __threadfence();
+    ticket = atomicAdd(&row_counters[b], 1u);
+    __threadfence();
+  }
   __syncthreads();
   if (ticket != (unsigned)(H - 1)) return;
-  __threadfence();
   const bool act = tid < (d >> 2);
   float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
   if (act) v = __ldcg(reinterpret_cast<const float4*>(x1 + (size_t)b * d) + tid);
