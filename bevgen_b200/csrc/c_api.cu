@@ -350,11 +350,36 @@ BEVGEN_API int bevgen_layernorm(const float* x, long long rows, int d, long long
 }
 
 BEVGEN_API int bevgen_layernorm_f16f8(const float* x, long long rows, int d, long long x_row_stride, const float* gamma, const float* beta, float eps,
-                                      float* y, void* out_f16, void* out_f8pair, void* stream) {
+                                      float* y, void* out_f16, void* out_f8pair, int scaled, void* stream) {
   if (!x || !gamma || !beta || !out_f16 || !out_f8pair) return fail(BEVGEN_ERR_ARG, "layernorm_f16f8: bad args");
   if (x_row_stride % 4 != 0) return fail(BEVGEN_ERR_ARG, "layernorm: row stride must be a multiple of 4");
-  CHECK_LAUNCH(launch_layernorm(x, gamma, beta, y, (uint16_t*)out_f16, (uint16_t*)out_f8pair, rows, d, x_row_stride, eps, 1, (cudaStream_t)stream),
-               "layernorm_f16f8");
+  CHECK_LAUNCH(launch_layernorm(x, gamma, beta, y, (uint16_t*)out_f16, (uint16_t*)out_f8pair, rows, d, x_row_stride, eps, scaled ? 2 : 1,
+                                (cudaStream_t)stream), "layernorm_f16f8");
+}
+
+BEVGEN_API int bevgen_linear_f16f8(const void* a16, const void* apair, const void* w16, const void* wpair, long long M, int N, int K, float out_scale,
+                                   const float* bias, int gelu, const float* residual, float* out_f32, void* out_hi, void* out_lo, void* out_f16,
+                                   void* out_pair, void* stream) {
+  if (ensure_init() != BEVGEN_OK) return BEVGEN_ERR_DRIVER;
+  if (!a16 || !apair || !w16 || !wpair || M < 1 || M > 0x7fffffffLL) return fail(BEVGEN_ERR_ARG, "linear_f16f8: bad args");
+  if (N < 32 || N % 32 != 0 || K < 64 || K % 64 != 0) return fail(BEVGEN_ERR_ARG, "linear_f16f8: need N %% 32 == 0 and K %% 64 == 0 (N=%d K=%d)", N, K);
+  if ((out_hi == nullptr) != (out_lo == nullptr) || (out_f16 == nullptr) != (out_pair == nullptr) || (!out_f32 && !out_hi && !out_f16))
+    return fail(BEVGEN_ERR_ARG, "linear_f16f8: outputs must be fp32 and/or a complete pair of planes");
+  bevgen::GemmPairParams p{};
+  const void* ap[2] = {a16, apair};
+  const void* wp[2] = {w16, wpair};
+  const uint64_t ad[2] = {(uint64_t)K, (uint64_t)M}, wd[2] = {(uint64_t)K, (uint64_t)N}, st[1] = {(uint64_t)K * 2};
+  const uint32_t box[2] = {64, 128};
+  int rc;
+  for (int o = 0; o < 2; ++o) {
+    rc = make_tmap(&p.tmA[o], ap[o], 2, ad, st, box);
+    if (rc != BEVGEN_OK) return rc;
+    rc = make_tmap(&p.tmW[o], wp[o], 2, wd, st, box);
+    if (rc != BEVGEN_OK) return rc;
+  }
+  p.M = (int)M; p.N = N; p.K = K; p.out_scale = out_scale; p.bias = bias; p.gelu = gelu; p.residual = residual; p.out_f32 = out_f32;
+  p.out_hi = (uint16_t*)out_hi; p.out_lo = (uint16_t*)out_lo; p.out_f16 = (uint16_t*)out_f16; p.out_pair = out_pair;
+  CHECK_LAUNCH(bevgen::launch_gemm_pair_f16f8(p, g_sm_count, (cudaStream_t)stream), "linear_f16f8");
 }
 
 BEVGEN_API int bevgen_embed_assemble(const bevgen_embed_args* a, void* stream) {

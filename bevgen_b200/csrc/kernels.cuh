@@ -114,6 +114,22 @@ int launch_conv_fused2(const ConvFusedParams& p, int npass, int sm_count, cudaSt
 int launch_conv_fused3(const ConvFusedParams& p, int npass, int sm_count, cudaStream_t st);   // 2-CTA clusters, 16x16 blocks; tmW box = (32, 64), SWIZZLE_64B
 int launch_gn_affine(const double* sums, const float* gamma, const float* beta, float* affine, int N, int pixels, int C, float eps, cudaStream_t st);
 
+struct GemmPairParams {
+  CUtensorMap tmA[2];      // A16s / Apair: 2D (k, row), box (64, 128), SWIZZLE_128B
+  CUtensorMap tmW[2];      // W16s / Wpair: 2D (k, out feature), box (64, 128)
+  int M, N, K;
+  float out_scale;         // 1 / (2^13 * S)
+  const float* bias;       // [N] or null
+  int gelu;
+  const float* residual;   // [M][N] or null
+  float* out_f32;          // [M][N] or null
+  uint16_t* out_hi;        // bf16 hi / lo planes [M][N] or null (both)
+  uint16_t* out_lo;
+  uint16_t* out_f16;       // scaled f16f8 planes for a following GEMM: fp16(y * 2^6) [M][N] + e4m3 pair plane [M][2N bytes], or null (both)
+  void* out_pair;
+};
+int launch_gemm_pair_f16f8(const GemmPairParams& p, int sm_count, cudaStream_t st);
+
 int launch_attn_fused(const CUtensorMap* tm_hi, const CUtensorMap* tm_lo, const void* bias_f16, const float* y, float* x1, int B, int H, int L,
                       int nc, int d, float scale, int npass, cudaStream_t st);
 

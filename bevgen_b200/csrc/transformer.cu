@@ -49,9 +49,12 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
     if (hi != nullptr && f16f8) {
       // operand planes of an f16f8 GEMM (gemm_tc npass = 2): fp16 plane + e4m3 pair plane (per 64-column chunk: 64 bytes of 2^13-scaled
       // fp16 remainders, then 64 bytes of values)
-      const __half2 ha = __floats2half2_rn(o.x, o.y), hb = __floats2half2_rn(o.z, o.w);
+      // f16f8 == 2: the fp16 plane holds 2^6 * y (single-accumulator convention of gemm_pair.cu); remainders are against the unscaled value
+      const float sc = f16f8 == 2 ? 64.0f : 1.0f, isc = f16f8 == 2 ? 0.015625f : 1.0f;
+      const __half2 ha = __floats2half2_rn(o.x * sc, o.y * sc), hb = __floats2half2_rn(o.z * sc, o.w * sc);
       reinterpret_cast<uint2*>(hi + row * D)[c4] = make_uint2(*reinterpret_cast<const uint32_t*>(&ha), *reinterpret_cast<const uint32_t*>(&hb));
-      const float2 fa = __half22float2(ha), fb = __half22float2(hb);
+      float2 fa = __half22float2(ha), fb = __half22float2(hb);
+      fa.x *= isc; fa.y *= isc; fb.x *= isc; fb.y *= isc;
       const uint32_t l8 = (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2((o.x - fa.x) * 8192.0f, (o.y - fa.y) * 8192.0f), __NV_SATFINITE, __NV_E4M3) |
                           ((uint32_t)__nv_cvt_float2_to_fp8x2(make_float2((o.z - fb.x) * 8192.0f, (o.w - fb.y) * 8192.0f), __NV_SATFINITE, __NV_E4M3) << 16);
       const uint32_t x8 = (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2(o.x, o.y), __NV_SATFINITE, __NV_E4M3) |

@@ -29,13 +29,14 @@ def _planes_of(w, npass, dev, min_rows=128):
 
 
 class GPTEngine:
-    def __init__(self, state_dict, cfg, device="cuda", precision="fp32x3", layouts=None):
+    def __init__(self, state_dict, cfg, device="cuda", precision="fp32x3", layouts=None, use_pair_gemm=True):
         # "fp32x3": every GEMM is the bf16x3 split product; "f16f8" (parity mode): the QKV and the two MLP GEMMs form the
         # same fp32-equivalent product as 1 fp16 + 2 e4m3 MMAs (2/3 of the tensor time / energy), everything else stays bf16x3; "bf16": fast mode
         assert precision in ("fp32x3", "f16f8", "bf16")
         self.cfg, self.precision = cfg, precision
         self.npass = 1 if precision == "bf16" else 3
         self.mlp_f16f8 = precision == "f16f8"
+        self.use_pair_gemm = use_pair_gemm and self.mlp_f16f8      # QKV / MLP linears on the 2-CTA 256x256 f16f8 GEMM instead of gemm_tc npass = 2
         self.dev = torch.device(device)
         dev, sd = self.dev, state_dict
         d = cfg.num_embed
@@ -75,6 +76,10 @@ class GPTEngine:
                 self.layers[-1]["wqkv_f8"] = ops.pack_f16f8(wqkv.to(dev, torch.float32).contiguous())
                 self.layers[-1]["w1_f8"] = ops.pack_f16f8(sd[f"{p}.mlp.0.weight"].to(dev, torch.float32).contiguous())
                 self.layers[-1]["w2_f8"] = ops.pack_f16f8(sd[f"{p}.mlp.2.weight"].to(dev, torch.float32).contiguous())
+                if self.use_pair_gemm:   # scaled single-accumulator operands of the 2-CTA GEMM (gemm_pair.cu)
+                    self.layers[-1]["wqkv_p"] = ops.pack_linear_f16f8(wqkv.to(dev, torch.float32).contiguous())
+                    self.layers[-1]["w1_p"] = ops.pack_linear_f16f8(sd[f"{p}.mlp.0.weight"].to(dev, torch.float32).contiguous())
+                    self.layers[-1]["w2_p"] = ops.pack_linear_f16f8(sd[f"{p}.mlp.2.weight"].to(dev, torch.float32).contiguous())
         self.ln_f = (f32("ln_f.weight"), f32("ln_f.bias"))
         self.vocab = sd["head.weight"].shape[0]
         self.whead = _planes_of(sd["head.weight"], self.npass, dev)
@@ -197,11 +202,16 @@ class GPTEngine:
         rows = B * L
         y = torch.empty_like(x)
         qkv = self._planes((B, L, 3 * d))
+        pair = self.use_pair_gemm and d % 128 == 0
         if self.mlp_f16f8 and d % 128 == 0:
             yp = (torch.empty((rows, d), dtype=torch.float16, device=self.dev), torch.empty((rows, 2 * d), dtype=torch.uint8, device=self.dev))
-            ops.layernorm(x, *lw["ln1"], y=y, out_hi=yp[0], out_lo=yp[1], f16f8=True)
-            wq = lw["wqkv_f8"]
-            self._linear(yp, wq[:2], 3 * d, rows, d, bias=lw["bqkv"], out_planes=qkv, npass=2, lo_scale=wq[2])     # output planes stay bf16 hi/lo
+            ops.layernorm(x, *lw["ln1"], y=y, out_hi=yp[0], out_lo=yp[1], f16f8=True, scaled=pair)
+            if pair:
+                wq = lw["wqkv_p"]
+                ops.linear_f16f8(yp[0], yp[1], wq[0], wq[1], wq[2], rows, 3 * d, d, bias=lw["bqkv"], out_hi=qkv[0], out_lo=qkv[1])
+            else:
+                wq = lw["wqkv_f8"]
+                self._linear(yp, wq[:2], 3 * d, rows, d, bias=lw["bqkv"], out_planes=qkv, npass=2, lo_scale=wq[2])     # output planes stay bf16 hi/lo
         else:
             yp = self._planes((rows, d))
             ops.layernorm(x, *lw["ln1"], y=y, out_hi=yp[0], out_lo=yp[1])
@@ -218,7 +228,12 @@ class GPTEngine:
             u8 = lambda r, c: torch.empty((r, c), dtype=torch.uint8, device=self.dev)
             f16 = lambda r, c: torch.empty((r, c), dtype=torch.float16, device=self.dev)
             zp, hp = (f16(rows, d), u8(rows, 2 * d)), (f16(rows, 4 * d), u8(rows, 8 * d))
-            ops.layernorm(x1, *lw["ln2"], out_hi=zp[0], out_lo=zp[1], f16f8=True)
+            ops.layernorm(x1, *lw["ln2"], out_hi=zp[0], out_lo=zp[1], f16f8=True, scaled=pair)
+            if pair:
+                w1, w2 = lw["w1_p"], lw["w2_p"]
+                ops.linear_f16f8(zp[0], zp[1], w1[0], w1[1], w1[2], rows, 4 * d, d, bias=lw["b1"], gelu=True, out_f16=hp[0], out_pair=hp[1])
+                ops.linear_f16f8(hp[0], hp[1], w2[0], w2[1], w2[2], rows, d, 4 * d, bias=lw["b2"], residual=x1, out_f32=x2)
+                return x2
             w1, w2 = lw["w1_f8"], lw["w2_f8"]
             self._linear(zp, w1[:2], 4 * d, rows, d, bias=lw["b1"], out_planes=hp, flags=ops.GF_GELU | ops.GF_OUT_F16F8, npass=2, lo_scale=w1[2])
             self._linear(hp, w2[:2], d, rows, 4 * d, bias=lw["b2"], residual=x1, out_f32=x2, npass=2, lo_scale=w2[2])

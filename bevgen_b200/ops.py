@@ -269,16 +269,69 @@ def denormalize(x_nchw, out, mean, std):
     _lib.check(lib.bevgen_denormalize(_ptr(x_nchw), _ptr(out), n, c, h * w, m, s, _stream()), "denormalize")
 
 
-def layernorm(x, gamma, beta, y=None, out_hi=None, out_lo=None, eps=1e-5, rows=None, row_stride=None, f16f8=False):
-    """f16f8: out_hi / out_lo receive the fp16 plane and the e4m3 pair plane (operands of an npass = 2 GEMM)."""
+def layernorm(x, gamma, beta, y=None, out_hi=None, out_lo=None, eps=1e-5, rows=None, row_stride=None, f16f8=False, scaled=False):
+    """f16f8: out_hi / out_lo receive the fp16 plane and the e4m3 pair plane (operands of an npass = 2 GEMM); scaled: the fp16 plane holds
+    2^6 * y (operand convention of linear_f16f8)."""
     lib = _lib.init()
     Stats.launches += 1
     _chk_cuda(gamma, beta, y, out_hi, out_lo)
     d = gamma.numel()
     rows = x.numel() // d if rows is None else rows
     row_stride = d if row_stride is None else row_stride
-    fn = lib.bevgen_layernorm_f16f8 if f16f8 else lib.bevgen_layernorm
-    _lib.check(fn(_ptr(x), rows, d, row_stride, _ptr(gamma), _ptr(beta), eps, _ptr(y), _ptr(out_hi), _ptr(out_lo), _stream()), "layernorm")
+    if f16f8:
+        _lib.check(lib.bevgen_layernorm_f16f8(_ptr(x), rows, d, row_stride, _ptr(gamma), _ptr(beta), eps, _ptr(y), _ptr(out_hi), _ptr(out_lo),
+                                              1 if scaled else 0, _stream()), "layernorm_f16f8")
+    else:
+        _lib.check(lib.bevgen_layernorm(_ptr(x), rows, d, row_stride, _ptr(gamma), _ptr(beta), eps, _ptr(y), _ptr(out_hi), _ptr(out_lo), _stream()),
+                   "layernorm")
+
+
+def pack_linear_f16f8(w2d: torch.Tensor):
+    """nn.Linear weight [out][in] (in % 64 == 0) -> operands of linear_f16f8: (w16s = fp16(w * S * 2^7), pair [out][2*in] uint8 with, per
+    64-element chunk, 64 bytes e4m3(w * S) then 64 bytes e4m3((w - w16) * S * 2^13), out_scale = 1 / (2^13 * S))."""
+    rows, cin = w2d.shape
+    assert cin % 64 == 0
+    w = w2d.float()
+    amax = float(w.abs().max().item())
+    e = 6 if amax == 0.0 else min(max(6 - math.ceil(math.log2(amax)), -16), 24)
+    s = 2.0 ** e
+    w16s = (w * (s * 128.0)).to(torch.float16)
+    w16 = w16s.float() / (s * 128.0)
+    w8 = (w * s).clamp(-448.0, 448.0).to(torch.float8_e4m3fn)
+    wlo8 = ((w - w16) * (s * 2.0 ** F8_ACT_LO_SHIFT)).clamp(-448.0, 448.0).to(torch.float8_e4m3fn)
+    pair = torch.stack([w8.view(torch.uint8).view(rows, cin // 64, 64), wlo8.view(torch.uint8).view(rows, cin // 64, 64)], 2)
+    return w16s.contiguous(), pair.reshape(rows, 2 * cin).contiguous(), 1.0 / (2.0 ** F8_ACT_LO_SHIFT * s)
+
+
+def pack_act_f16f8_scaled(a: torch.Tensor):
+    """fp32 activations [rows][k] -> the scaled A planes of linear_f16f8 (fp16(a * 2^6), pair plane as pack_act_f16f8 against the unscaled a16)."""
+    rows, k = a.shape
+    assert k % 64 == 0
+    a = a.float()
+    a16s = (a * 64.0).to(torch.float16)
+    lo8 = ((a - a16s.float() / 64.0) * 2.0 ** F8_ACT_LO_SHIFT).clamp(-448.0, 448.0).to(torch.float8_e4m3fn)
+    x8 = a.clamp(-448.0, 448.0).to(torch.float8_e4m3fn)
+    pair = torch.stack([lo8.view(torch.uint8).view(rows, k // 64, 64), x8.view(torch.uint8).view(rows, k // 64, 64)], 2)
+    return a16s.contiguous(), pair.reshape(rows, 2 * k).contiguous()
+
+
+def linear_f16f8(a16, apair, w16, wpair, out_scale, M, N, K, bias=None, gelu=False, residual=None, out_f32=None, out_hi=None, out_lo=None,
+                 out_f16=None, out_pair=None):
+    """y = act(a @ w.T + bias) (+ residual) on the 2-CTA f16f8 GEMM (gemm_pair.cu): operands from layernorm(..., f16f8=True, scaled=True) /
+    a previous linear_f16f8(out_f16=, out_pair=) and pack_linear_f16f8.  Outputs: fp32 and/or bf16 hi/lo planes and/or scaled f16f8 planes."""
+    lib = _lib.init()
+    Stats.launches += 1
+    _chk_cuda(a16, apair, w16, wpair, bias, residual, out_f32, out_hi, out_lo, out_f16, out_pair)
+    flops = 2.0 * M * N * K
+    Stats.gemm_launches += 1
+    Stats.gemm_flops += flops
+    call = lambda: _lib.check(lib.bevgen_linear_f16f8(_ptr(a16), _ptr(apair), _ptr(w16), _ptr(wpair), M, N, K, out_scale, _ptr(bias),
+                                                      1 if gelu else 0, _ptr(residual), _ptr(out_f32), _ptr(out_hi), _ptr(out_lo), _ptr(out_f16),
+                                                      _ptr(out_pair), _stream()), "linear_f16f8")
+    if Stats.timer is not None:
+        Stats.timer("linear_f16f8", call, flops)
+    else:
+        call()
 
 
 def embed_assemble(args: "EmbedArgs"):

@@ -178,7 +178,18 @@ BEVGEN_API int bevgen_layernorm(const float* x, long long rows, int d, long long
 /* Same LayerNorm writing the operand planes of an f16f8 GEMM (bevgen_gemm_tc, npass = 2): out_f16 [rows][d] fp16 and out_f8pair
  * [rows][2*d bytes]: per 64-column chunk 64 bytes e4m3((y - fp16(y)) * 2^13) followed by 64 bytes e4m3(y). */
 BEVGEN_API int bevgen_layernorm_f16f8(const float* x, long long rows, int d, long long x_row_stride, const float* gamma, const float* beta, float eps,
-                                      float* y, void* out_f16, void* out_f8pair, void* stream);
+                                      float* y, void* out_f16, void* out_f8pair, int scaled, void* stream);
+/* scaled != 0: the fp16 plane holds 2^6 * y (the e4m3 remainders stay relative to the unscaled fp16 value): A operand of bevgen_linear_f16f8. */
+
+/* nn.Linear on the 2-CTA f16f8 GEMM (csrc/gemm_pair.cu; replaces the c_attn / mlp[0] / mlp[2] Linear calls of Block.forward,
+ * mingpt_sparse.py:170-175,231-237 at fp32-equivalent precision): out[M][N] = act(A . W^T * out_scale + bias) (+ residual).
+ * a16 [M][K] fp16(a * 2^6) and apair [M][2K bytes] come from bevgen_layernorm_f16f8(scaled = 1) or a previous call's out_f16 / out_pair;
+ * w16 [N][K] = fp16(w * S * 2^7), wpair [N][2K bytes] = per 64-element chunk 64 B e4m3(w * S) then 64 B e4m3((w - w16) * S * 2^13),
+ * out_scale = 1 / (2^13 * S) (ops.pack_linear_f16f8).  Needs |a| < 1024, N % 32 == 0, K % 64 == 0.
+ * Outputs (any non-empty subset): out_f32 [M][N]; bf16 planes out_hi / out_lo [M][N]; scaled f16f8 planes out_f16 [M][N] + out_pair [M][2N]. */
+BEVGEN_API int bevgen_linear_f16f8(const void* a16, const void* apair, const void* w16, const void* wpair, long long M, int N, int K, float out_scale,
+                                   const float* bias, int gelu, const float* residual, float* out_f32, void* out_hi, void* out_lo, void* out_f16,
+                                   void* out_pair, void* stream);
 
 /* Input-embedding assembly of GPT.forward (mingpt_sparse.py:319-373) for sequence rows [row0, row0+nrows):
  * token + ray embedding (L2-normalised) + position embeddings, decode-order permutation, [cond | img | pad] concat. */

@@ -461,6 +461,59 @@ def test_f16f8_plane_producers_chain():
     assert (out.double() - ref).abs().max().item() < 3e-4
 
 
+@pytest.mark.parametrize("M,N,K", [(256, 256, 64), (1000, 224, 320), (3584, 768, 256), (700, 1024, 1024), (130, 32, 4096)])
+def test_linear_pair_f16f8(M, N, K):
+    """gemm_pair.cu (2-CTA 256x256 tiles, one accumulator, pre-scaled operands) vs fp64, with ragged M / N tails, bias and residual."""
+    g = torch.Generator().manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g).to(dev())
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(dev())
+    bias = torch.randn(N, generator=g).to(dev())
+    res = torch.randn(M, N, generator=g).to(dev())
+    a16, apair = ops.pack_act_f16f8_scaled(a)
+    w16, wpair, sc = ops.pack_linear_f16f8(w)
+    out = torch.full((M, N), float("nan"), device=dev())
+    ops.linear_f16f8(a16, apair, w16, wpair, sc, M, N, K, bias=bias, residual=res, out_f32=out)
+    torch.cuda.synchronize()
+    ref = a.double() @ w.double().t() + bias.double() + res.double()
+    assert torch.isfinite(out).all()
+    err = (out.double() - ref).abs().max().item()
+    assert err < 6e-5 * K ** 0.5, f"max err {err}"
+
+
+def test_linear_pair_f16f8_chain_and_planes():
+    """scaled LayerNorm planes -> pair GEMM + GELU -> scaled f16f8 planes -> pair GEMM (+ residual), and the bf16 hi / lo output planes."""
+    M, D = 600, 256
+    g = torch.Generator().manual_seed(5)
+    x = (torch.randn(M, D, generator=g) * 2 + 0.5).to(dev())
+    gamma, beta = (1 + 0.1 * torch.randn(D, generator=g)).to(dev()), (0.1 * torch.randn(D, generator=g)).to(dev())
+    w1 = (torch.randn(4 * D, D, generator=g) / D ** 0.5).to(dev())
+    b1 = (0.1 * torch.randn(4 * D, generator=g)).to(dev())
+    w2 = (torch.randn(D, 4 * D, generator=g) / (4 * D) ** 0.5).to(dev())
+    z16, zpair = torch.zeros(M, D, dtype=torch.float16, device=dev()), torch.zeros(M, 2 * D, dtype=torch.uint8, device=dev())
+    ops.layernorm(x, gamma, beta, out_hi=z16, out_lo=zpair, f16f8=True, scaled=True)
+    y_ref = F.layer_norm(x.double(), (D,), gamma.double(), beta.double(), 1e-5)
+
+    def decode(p16, pair):
+        k = p16.shape[1]
+        pr = pair.view(p16.shape[0], k // 64, 2, 64)
+        lo = pr[:, :, 0].reshape(p16.shape[0], k).view(torch.float8_e4m3fn).double() / 8192.0
+        return p16.double() / 64.0 + lo
+    torch.cuda.synchronize()
+    assert ((decode(z16, zpair) - y_ref).abs() <= 2.0 ** -15 * y_ref.abs() + 1e-6).all()
+    w1p, w2p = ops.pack_linear_f16f8(w1), ops.pack_linear_f16f8(w2)
+    h16, hpair = torch.zeros(M, 4 * D, dtype=torch.float16, device=dev()), torch.zeros(M, 8 * D, dtype=torch.uint8, device=dev())
+    hhi, hlo = torch.zeros(M, 4 * D, dtype=torch.bfloat16, device=dev()), torch.zeros(M, 4 * D, dtype=torch.bfloat16, device=dev())
+    ops.linear_f16f8(z16, zpair, w1p[0], w1p[1], w1p[2], M, 4 * D, D, bias=b1, gelu=True, out_f16=h16, out_pair=hpair, out_hi=hhi, out_lo=hlo)
+    out = torch.empty(M, D, device=dev())
+    ops.linear_f16f8(h16, hpair, w2p[0], w2p[1], w2p[2], M, D, 4 * D, residual=x, out_f32=out)
+    torch.cuda.synchronize()
+    h_ref = F.gelu(y_ref @ w1.double().t() + b1.double())
+    assert ((decode(h16, hpair) - h_ref).abs() <= 2.0 ** -14 * h_ref.abs() + 1e-4).all()
+    assert ((hhi.double() + hlo.double() - h_ref).abs() <= 2.0 ** -14 * h_ref.abs() + 1e-4).all()
+    ref = h_ref @ w2.double().t() + x.double()
+    assert (out.double() - ref).abs().max().item() < 3e-4
+
+
 @pytest.mark.parametrize("N_,H,W,Cout", [(2, 64, 64, 128), (3, 37, 70, 64), (1, 256, 256, 128)])
 def test_conv_in3_direct(N_, H, W, Cout):
     """Direct fp32 conv_in (NCHW RGB -> NHWC, bias, fused GroupNorm statistics) vs torch conv2d."""
