@@ -87,7 +87,7 @@ SIGNATURES = {
     "bevgen_linear_f16f8": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _i, _f, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "bevgen_embed_assemble": (_i, [C.POINTER(EmbedArgs), _vp]),
     "bevgen_attn_softmax": (_i, [_vp, _vp, _vp, _ll, _i, _i, _f, _vp, _vp, _vp, _i, _i, _i, _vp]),
-    "bevgen_attn_fused_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _f, _i, _vp]),
+    "bevgen_attn_fused_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _f, _i, _vp, _vp]),
     "bevgen_dec_reduce_ln": (_i, [_vp, _i, _ll, _vp, _vp, _ll, _vp, _vp, _f, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     "bevgen_dec_reduce_act": (_i, [_vp, _i, _ll, _vp, _i, _vp, _vp, _i, _i, _vp]),
     "bevgen_kv_store": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),

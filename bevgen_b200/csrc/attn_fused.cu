@@ -41,6 +41,8 @@ struct AttnParams {
   float* x1;                // [B][L][d]
   int B, H, L, nc, d;
   float scale_log2e;        // d_head^-1/2 * log2(e)
+  const unsigned long long* layout64;   // block-sparse layouts (density < 1) or null: [H][L/128 query tiles][L/128 key tiles], bit (8*rb + kb)
+                                       // = the (16-row, 16-key) sub-block (rb, kb) of the tile is in the head's layout; 0 = tile skipped
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
@@ -88,6 +90,15 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fused_kernel(const __grid_
   const int m0 = qt * AT_BM;
   const int T = (m0 < p.nc) ? (p.nc / AT_BN) : (m0 / AT_BN + 1);
   const int row0 = b * p.L;           // first row of this batch element in the [B*L, 3d] view
+  // key tiles this CTA visits: inside the [cond | causal] support and (with layouts) holding at least one block of the head's layout.
+  // Every role walks the same bit list; pipeline stages and phases follow the visit counter `it`, addresses the tile index t.
+  const unsigned long long* lay = p.layout64 ? p.layout64 + ((size_t)h * nq + qt) * (p.L / AT_BN) : nullptr;
+  uint32_t tiles = T >= 32 ? 0xffffffffu : ((1u << T) - 1u);
+  if (lay != nullptr) {
+    uint32_t m = 0;
+    for (int t = 0; t < T; ++t) m |= (lay[t] != 0 ? 1u : 0u) << t;
+    tiles = m;
+  }
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tm[0]);
@@ -115,14 +126,16 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fused_kernel(const __grid_
       mbar_expect_tx(q_full, Cfg::Q_BYTES);
 #pragma unroll
       for (int o = 0; o < NOPS; ++o) tma_load_2d(sQ + o * AT_TILE, &p.tm[o], q_full, h * AT_DH, row0 + m0);
-      for (int t = 0; t < T; ++t) {
-        const int s = t & 1;
+      int it = 0;
+      for (uint32_t m = tiles; m != 0; m &= m - 1, ++it) {
+        const int t = __ffs(m) - 1;
+        const int s = it & 1;
         uint8_t* st = sKV + s * Cfg::KV_STAGE;
-        mbar_wait(&k_empty[s], ((t >> 1) & 1) ^ 1);
+        mbar_wait(&k_empty[s], ((it >> 1) & 1) ^ 1);
         mbar_expect_tx(&k_full[s], NOPS * AT_TILE);
 #pragma unroll
         for (int o = 0; o < NOPS; ++o) tma_load_2d(st + o * AT_TILE, &p.tm[o], &k_full[s], p.d + h * AT_DH, row0 + t * AT_BN);
-        mbar_wait(&v_empty[s], ((t >> 1) & 1) ^ 1);
+        mbar_wait(&v_empty[s], ((it >> 1) & 1) ^ 1);
         mbar_expect_tx(&v_full[s], NOPS * AT_TILE);
 #pragma unroll
         for (int o = 0; o < NOPS; ++o) tma_load_2d(st + (NOPS + o) * AT_TILE, &p.tm[o], &v_full[s], 2 * p.d + h * AT_DH, row0 + t * AT_BN);
@@ -143,10 +156,10 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fused_kernel(const __grid_
       const uint64_t pd = make_sdesc_sw128(smem_u32(sP), 16, 1024);
       const uint64_t vd0 = make_sdesc_sw128(smem_u32(sKV) + NOPS * AT_TILE, 8192, 1024);   // MN-major V: k-step = 16 rows = +2048 B
       constexpr uint64_t LO = AT_TILE >> 4, PLO = AT_PTILE >> 4, STG = Cfg::KV_STAGE >> 4;
-      auto issue_s = [&](int t) {
-        const int s = t & 1;
-        mbar_wait(&k_full[s], (t >> 1) & 1);
-        mbar_wait(&s_empty[s], ((t >> 1) & 1) ^ 1);
+      auto issue_s = [&](int it) {                 // stages / phases depend on the visit counter only
+        const int s = it & 1;
+        mbar_wait(&k_full[s], (it >> 1) & 1);
+        mbar_wait(&s_empty[s], ((it >> 1) & 1) ^ 1);
         tc_fence_after();
         if (elected) {
           const uint64_t kd = kd0 + (uint64_t)s * STG;
@@ -164,14 +177,15 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fused_kernel(const __grid_
           umma_commit(&k_empty[s]);
         }
       };
+      const int NT = __popc(tiles);
       mbar_wait(q_full, 0);
-      issue_s(0);
-      for (int t = 0; t < T; ++t) {
-        if (t + 1 < T) issue_s(t + 1);
-        const int s = t & 1;
-        mbar_wait(p_full, t & 1);
-        mbar_wait(&v_full[s], (t >> 1) & 1);
-        mbar_wait(&pv_empty[s], ((t >> 1) & 1) ^ 1);
+      if (NT > 0) issue_s(0);
+      for (int it = 0; it < NT; ++it) {
+        if (it + 1 < NT) issue_s(it + 1);
+        const int s = it & 1;
+        mbar_wait(p_full, it & 1);
+        mbar_wait(&v_full[s], (it >> 1) & 1);
+        mbar_wait(&pv_empty[s], ((it >> 1) & 1) ^ 1);
         tc_fence_after();
         if (elected) {
           const uint64_t vd = vd0 + (uint64_t)s * STG;
@@ -213,8 +227,10 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fused_kernel(const __grid_
     const uint4* brow = p.bias ? p.bias + ((size_t)(m0 / AT_BM) * nkt * AT_NPART + part) * (AT_KPT / 8) * AT_BM + row : nullptr;
     float* xrow = xmax + row * AT_NPART;
 
-    for (int t = 0; t < T; ++t) {
-      const int s = t & 1;
+    int it = 0;
+    for (uint32_t tm = tiles; tm != 0; tm &= tm - 1, ++it) {
+      const int t = __ffs(tm) - 1;
+      const int s = it & 1;
       // bias row chunk: 32 fp16 = 64 B, issued before waiting on the MMA
       uint4 bq[AT_KPT / 8];
       if (brow != nullptr) {
@@ -222,7 +238,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fused_kernel(const __grid_
 #pragma unroll
         for (int u = 0; u < AT_KPT / 8; ++u) bq[u] = __ldg(bp + u * AT_BM);
       }
-      mbar_wait(&s_full[s], (t >> 1) & 1);
+      mbar_wait(&s_full[s], (it >> 1) & 1);
       tc_fence_after();
       float tv[AT_KPT];
       {
@@ -257,6 +273,17 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fused_kernel(const __grid_
           mx = fmaxf(mx, tv[j]);
         }
       }
+      if (lay != nullptr) {        // this row's 16-row block x this thread's two 16-key blocks
+        const uint32_t two = (uint32_t)(lay[t] >> (((row >> 4) << 3) + part * 2)) & 3u;
+        if (two != 3u) {
+          mx = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < AT_KPT; ++j) {
+            if (!((two >> (j >> 4)) & 1u)) tv[j] = -INFINITY;
+            mx = fmaxf(mx, tv[j]);
+          }
+        }
+      }
       // exchange the row maximum with the three partner threads handling the other keys of the row
       xrow[part] = mx;
       named_bar_sync(1 + quarter, 32 * AT_NPART);
@@ -265,17 +292,18 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fused_kernel(const __grid_
         mx = fmaxf(fmaxf(m4.x, m4.y), fmaxf(m4.z, m4.w));
       }
       named_bar_sync(1 + quarter, 32 * AT_NPART);           // all partners have read before any slot is rewritten
-      const float m_new = fmaxf(m_run, mx);                 // finite: every row has key 0 (cond) allowed
-      const float corr = ex2_approx(m_run - m_new);         // 0 on the first tile
+      const float m_new = fmaxf(m_run, mx);                 // finite without layouts (every row has key 0 allowed); with layouts a row's first
+      const float m_sub = (m_new == -INFINITY) ? 0.f : m_new;   // visited tile may hold none of its blocks: keep exp(-inf - m) = 0 well defined
+      const float corr = ex2_approx(m_run - m_sub);         // 0 on the first tile
       float psum = 0.f;
 #pragma unroll
-      for (int j = 0; j < AT_KPT; ++j) { tv[j] = ex2_approx(tv[j] - m_new); psum += tv[j]; }
+      for (int j = 0; j < AT_KPT; ++j) { tv[j] = ex2_approx(tv[j] - m_sub); psum += tv[j]; }
       l_run = l_run * corr + psum;
       m_run = m_new;
       // fold in the previous tile's P.V (also guarantees the PV MMA finished reading P from smem)
-      if (t > 0) {
-        const int sp = (t - 1) & 1;
-        mbar_wait(&pv_done[sp], ((t - 1) >> 1) & 1);
+      if (it > 0) {
+        const int sp = (it - 1) & 1;
+        mbar_wait(&pv_done[sp], ((it - 1) >> 1) & 1);
         tc_fence_after();
         uint32_t r[16];
         tmem_ld_32x16(tPV[sp] + lane_off + part * AT_CPT, r);
@@ -306,9 +334,9 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fused_kernel(const __grid_
       if (lane == 0) mbar_arrive(p_full);
     }
     // last tile's P.V
-    {
-      const int sp = (T - 1) & 1;
-      mbar_wait(&pv_done[sp], ((T - 1) >> 1) & 1);
+    if (it > 0) {
+      const int sp = (it - 1) & 1;
+      mbar_wait(&pv_done[sp], ((it - 1) >> 1) & 1);
       tc_fence_after();
       uint32_t r[16];
       tmem_ld_32x16(tPV[sp] + lane_off + part * AT_CPT, r);
@@ -320,7 +348,8 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fused_kernel(const __grid_
     xrow[part] = l_run;
     named_bar_sync(1 + quarter, 32 * AT_NPART);
     const float4 l4 = *reinterpret_cast<const float4*>(xrow);
-    const float inv = 1.0f / ((l4.x + l4.y) + (l4.z + l4.w));
+    const float lsum = (l4.x + l4.y) + (l4.z + l4.w);
+    const float inv = lsum > 0.f ? 1.0f / lsum : 0.f;          // a row without any attended key (degenerate layout) contributes nothing
     const size_t off = ((size_t)(b * p.L + gi)) * p.d + h * AT_DH + part * AT_CPT;
     const float4* yp = reinterpret_cast<const float4*>(p.y + off);
     float4* op = reinterpret_cast<float4*>(p.x1 + off);
@@ -349,8 +378,8 @@ static int launch_attn(const AttnParams& p, cudaStream_t st) {
 }
 
 int launch_attn_fused(const CUtensorMap* tm_hi, const CUtensorMap* tm_lo, const void* bias_f16, const float* y, float* x1, int B, int H, int L,
-                      int nc, int d, float scale, int npass, cudaStream_t st) {
-  if (L % AT_BM != 0 || nc % AT_BN != 0 || nc < AT_BN || nc > L || d != H * AT_DH) return BEVGEN_ERR_ARG;
+                      int nc, int d, float scale, int npass, const unsigned long long* layout64, cudaStream_t st) {
+  if (L % AT_BM != 0 || nc % AT_BN != 0 || nc < AT_BN || nc > L || d != H * AT_DH || L / AT_BN > 32) return BEVGEN_ERR_ARG;
   AttnParams p;
   p.tm[0] = *tm_hi;
   p.tm[1] = tm_lo ? *tm_lo : *tm_hi;
@@ -358,6 +387,7 @@ int launch_attn_fused(const CUtensorMap* tm_hi, const CUtensorMap* tm_lo, const 
   p.y = y; p.x1 = x1;
   p.B = B; p.H = H; p.L = L; p.nc = nc; p.d = d;
   p.scale_log2e = scale * 1.4426950408889634f;
+  p.layout64 = layout64;
   return npass == 3 ? launch_attn<3>(p, st) : launch_attn<1>(p, st);
 }
 

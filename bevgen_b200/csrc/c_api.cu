@@ -401,12 +401,14 @@ BEVGEN_API int bevgen_attn_softmax(const float* s, const float* bias, const unsi
 }
 
 BEVGEN_API int bevgen_attn_fused_fwd(const void* qkv_hi, const void* qkv_lo, int batch, int seq_len, int heads, int d, int n_cond,
-                                     const void* bias_f16, const float* y, float* x1, float scale, int npass, void* stream) {
+                                     const void* bias_f16, const float* y, float* x1, float scale, int npass, const unsigned long long* layout64,
+                                     void* stream) {
   int rc = ensure_init();
   if (rc) return rc;
   if (!qkv_hi || !y || !x1 || (npass == 3 && !qkv_lo) || !(npass == 1 || npass == 3)) return fail(BEVGEN_ERR_ARG, "attn_fused_fwd: bad args");
   if (seq_len % 128 != 0 || n_cond % 128 != 0 || n_cond < 128 || n_cond > seq_len || d != heads * 64)
     return fail(BEVGEN_ERR_ARG, "attn_fused_fwd: needs seq_len, n_cond multiples of 128 and d_head = 64 (got L=%d nc=%d d=%d H=%d)", seq_len, n_cond, d, heads);
+  if (seq_len > 4096) return fail(BEVGEN_ERR_ARG, "attn_fused_fwd: seq_len %d > 4096", seq_len);
   CUtensorMap tm[2];
   const void* planes[2] = {qkv_hi, qkv_lo};
   for (int o = 0; o < (npass == 3 ? 2 : 1); ++o) {
@@ -417,7 +419,7 @@ BEVGEN_API int bevgen_attn_fused_fwd(const void* qkv_hi, const void* qkv_lo, int
     if (rc) return rc;
   }
   CHECK_LAUNCH(launch_attn_fused(&tm[0], npass == 3 ? &tm[1] : nullptr, bias_f16, y, x1, batch, heads, seq_len, n_cond, d, scale, npass,
-                                 (cudaStream_t)stream), "attn_fused_fwd");
+                                 layout64, (cudaStream_t)stream), "attn_fused_fwd");
 }
 
 /* ---------------------------------------------------------------- KV-cache decode */

@@ -131,7 +131,7 @@ struct GemmPairParams {
 int launch_gemm_pair_f16f8(const GemmPairParams& p, int sm_count, cudaStream_t st);
 
 int launch_attn_fused(const CUtensorMap* tm_hi, const CUtensorMap* tm_lo, const void* bias_f16, const float* y, float* x1, int B, int H, int L,
-                      int nc, int d, float scale, int npass, cudaStream_t st);
+                      int nc, int d, float scale, int npass, const unsigned long long* layout64, cudaStream_t st);
 
 int launch_dec_reduce_ln(const float* partials, int ks, long long zstride, const float* bias, const float* residual, long long res_stride,
                          const float* gamma, const float* beta, float eps, float* x_out, float* y, uint16_t* hi, uint16_t* lo, int rows, int d,

@@ -51,7 +51,8 @@ class GPTEngine:
         self.L, self.nc, self.n_img, self.npad = cfg.gpt_block_size, cfg.num_cond_tokens, cfg.num_img_tokens, cfg.num_pad_tokens
         # Per-head block layouts (DeepSpeed SparsityConfig; density < 1 configs, one layout per layer: [layers][heads][nb][nb] or a single
         # [heads][nb][nb] shared by all layers).  Layouts that cover the mask (density = 1) change nothing and are dropped; otherwise
-        # the layers run the composed attention path / the layout-aware decode kernel (the fused kernel covers the closed-form mask only).
+        # the fused kernel ANDs its closed-form mask with a 16-position bit table of the layout and skips empty key tiles (block sizes 16 /
+        # 32 / 64 / 128); the composed attention path and the decode kernel take the uint8 layout itself.
         self.layouts = None
         if layouts is not None:
             lay = torch.as_tensor(layouts)
@@ -124,8 +125,11 @@ class GPTEngine:
         self._perm_cache = {}
         self._allowed = float(self.mask_u8.sum().item())      # attended (row, col) pairs: algorithmic attention work
         if self.layouts is not None:
+            fusable = self.layout_block in (16, 32, 64, 128) and self.L % 128 == 0 and self.L <= 4096
             for i, lw in enumerate(self.layers):
                 lw["layout"] = self.layouts[i]
+                # the fused kernel's 16-position bit table: key tiles without any block of the head's layout are skipped
+                lw["layout64"] = ops.layout_to_tiles64(self.layouts[i], self.layout_block, self.L) if fusable else None
 
     # ------------------------------------------------------------------ helpers
     def _planes(self, shape):
@@ -159,16 +163,17 @@ class GPTEngine:
         ops.embed_assemble(a)
         return out
 
-    def attention(self, qkv, y, B, L, bias="full", mask=None, causal=None, allowed=None, fused_cond=None, layout=None):
+    def attention(self, qkv, y, B, L, bias="full", mask=None, causal=None, allowed=None, fused_cond=None, layout=None, layout64=None):
         """qkv planes [B, L, 3d]; returns x1 = y + concat_heads(softmax(scale*(QK^T + bias))V) as fp32 [B, L, d].
         bias/mask default to the full-sequence camera bias and attention mask; the KV-cache prefill passes the cond x cond blocks."""
         d, H, dh = self.d, self.H, self.dh
         if layout is not None:
             fused_cond = None
-        if self.fused_attention and layout is None and isinstance(bias, str) and mask is None and self.causal and L % 128 == 0 and self.nc % 128 == 0:
+        if (self.fused_attention and (layout is None or layout64 is not None) and isinstance(bias, str) and mask is None and self.causal
+                and L % 128 == 0 and self.nc % 128 == 0):
             x1 = torch.empty((B, L, d), dtype=torch.float32, device=self.dev)
             ops.attn_fused_fwd(qkv[0], qkv[1], B, L, H, d, self.nc, self.bias_f16, y, x1, float(dh) ** -0.5, self.npass,
-                               algo_flops=4.0 * B * H * dh * self._allowed)
+                               algo_flops=4.0 * B * H * dh * self._allowed, layout64=layout64 if layout is not None else None)
             return x1
         if self.fused_attention and fused_cond is not None and L % 128 == 0:
             x1 = torch.empty((B, L, d), dtype=torch.float32, device=self.dev)
@@ -221,6 +226,7 @@ class GPTEngine:
         akw = dict(attn_kw or {})
         if "layout" not in akw and lw.get("layout") is not None:
             akw["layout"] = lw["layout"]
+            akw["layout64"] = lw.get("layout64")
         x1 = self.attention(qkv, y, B, L, **akw)
         x2 = torch.empty_like(x)
         if self.mlp_f16f8 and d % 128 == 0:

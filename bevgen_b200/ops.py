@@ -360,12 +360,23 @@ def tile_attention_bias(bias: torch.Tensor, scale: float) -> torch.Tensor:
     return b.view(n, 128, n, 4, 4, 8).permute(0, 2, 3, 4, 1, 5).contiguous()
 
 
-def attn_fused_fwd(qkv_hi, qkv_lo, B, L, H, d, n_cond, bias_f16, y, x1, scale, npass, algo_flops=0.0):
+def layout_to_tiles64(layout: torch.Tensor, block: int, L: int) -> torch.Tensor:
+    """DeepSpeed block layout uint8 [H][nb][nb] (block in 16 / 32 / 64 / 128, nb * block >= L) -> the fused attention kernel's table
+    int64 [H][L/128][L/128]: bit 8*rb + kb = sub-block (16 query rows rb, 16 keys kb) of the 128 x 128 tile is attended."""
+    assert block in (16, 32, 64, 128) and L % 128 == 0
+    H = layout.shape[0]
+    n16, rep, nt = L // 16, block // 16, L // 128
+    fine = (layout != 0).repeat_interleave(rep, 1).repeat_interleave(rep, 2)[:, :n16, :n16]        # [H][L/16][L/16]
+    t = fine.reshape(H, nt, 8, nt, 8).permute(0, 1, 3, 2, 4).reshape(H, nt, nt, 64).to(torch.int64)
+    return (t << torch.arange(64, device=layout.device, dtype=torch.int64)).sum(-1).contiguous()      # bit 63 wraps into the sign
+
+
+def attn_fused_fwd(qkv_hi, qkv_lo, B, L, H, d, n_cond, bias_f16, y, x1, scale, npass, algo_flops=0.0, layout64=None):
     lib = _lib.init()
-    _chk_cuda(qkv_hi, qkv_lo, bias_f16, y, x1)
+    _chk_cuda(qkv_hi, qkv_lo, bias_f16, y, x1, layout64)
     Stats.launches += 1
     call = lambda: _lib.check(lib.bevgen_attn_fused_fwd(_ptr(qkv_hi), _ptr(qkv_lo), B, L, H, d, n_cond, _ptr(bias_f16), _ptr(y), _ptr(x1),
-                                                        float(scale), npass, _stream()), "attn_fused_fwd")
+                                                        float(scale), npass, _ptr(layout64), _stream()), "attn_fused_fwd")
     if Stats.timer is not None:
         Stats.timer("attn_fused", call, algo_flops)
     else:

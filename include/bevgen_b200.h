@@ -227,9 +227,15 @@ BEVGEN_API int bevgen_attn_softmax(const float* s, const float* bias, const unsi
  * q/k/v are the column blocks [0,d), [d,2d), [2d,3d) of the fused qkv bf16 planes [batch][seq_len][3d].  bias_tiled (shared by batch
  * and heads, or NULL) is the camera bias already multiplied by scale * log2(e), fp16, in 128 x 128 tiles laid out for coalesced reads:
  *   bias_tiled[qt][kt][p][u][r][e] = fp16(scale * log2(e) * bias[128*qt + r][128*kt + 32*p + 8*u + e]),  p, u < 4, r < 128, e < 8
- * (`bevgen_b200.ops.tile_attention_bias`).  seq_len and n_cond must be multiples of 128, d = heads*64. */
+ * (`bevgen_b200.ops.tile_attention_bias`).  seq_len and n_cond must be multiples of 128, seq_len <= 4096, d = heads*64.
+ * layout64 (NULL = dense [cond | causal] support): DeepSpeed block-sparse layouts of the density < 1 configs (sparse_self_attention.py:59-60,
+ * mask_generator.py:217-228) at 16-position granularity, uint64 [heads][seq_len/128][seq_len/128]: bit (8*rb + kb) of entry [h][qt][kt] =
+ * the head attends from query rows 128*qt + 16*rb .. +15 to keys 128*kt + 16*kb .. +15 (`ops.layout_to_tiles64`; sparse_block_size 16 (the
+ * reference's configs/model/stage_2.yaml:22), 32, 64 or 128).
+ * allowed(i,j) is ANDed with it; key tiles whose entry is 0 are skipped (no loads, no MMAs). */
 BEVGEN_API int bevgen_attn_fused_fwd(const void* qkv_hi, const void* qkv_lo, int batch, int seq_len, int heads, int d, int n_cond,
-                                     const void* bias_tiled, const float* y, float* x1, float scale, int npass, void* stream);
+                                     const void* bias_tiled, const float* y, float* x1, float scale, int npass, const unsigned long long* layout64,
+                                     void* stream);
 
 /* ---------------------------------------------------------------- KV-cache autoregressive decode
  * Replaces the per-token full forward of Net2NetTransformer.sample (modules/stage2/cond_transformer_multi_view.py:154-227)

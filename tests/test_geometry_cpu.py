@@ -51,3 +51,23 @@ def test_errors():
         GPTConfig(**{**kw, "num_cams": 5})
     with pytest.raises(NotImplementedError):
         GPTConfig(**{**kw, "legacy_prob_matrix": False})
+
+
+@pytest.mark.parametrize("block", [16, 32, 64, 128])
+def test_layout_bit_table_for_fused_attention(block):
+    """ops.layout_to_tiles64: the 16-position bit table the fused attention kernel ANDs with its closed-form mask reproduces the DeepSpeed
+    block layout (sparse_self_attention.py:59-60) element for element, for every supported sparse_block_size."""
+    from bevgen_b200 import ops
+    L, H = 1792, 3
+    nb = -(-L // block)
+    g = torch.Generator().manual_seed(block)
+    lay = (torch.rand(H, nb, nb, generator=g) < 0.4).to(torch.uint8)
+    table = ops.layout_to_tiles64(lay, block, L)
+    assert table.shape == (H, L // 128, L // 128) and table.dtype == torch.int64
+    i = torch.arange(L)
+    want = lay[:, (i // block)[:, None], (i // block)[None, :]].bool()                           # [H][L][L]
+    e = table[:, (i // 128)[:, None], (i // 128)[None, :]]                                       # [H][L][L] int64
+    bit = (8 * ((i % 128) // 16))[:, None] + ((i % 128) // 16)[None, :]
+    got = ((e >> bit) & 1).bool()
+    assert torch.equal(got, want)
+    assert torch.equal(table == 0, ~want.reshape(H, L // 128, 128, L // 128, 128).any(4).any(2))  # zero entry <=> tile skipped

@@ -125,6 +125,13 @@ def test_block_sparse_layouts_forward_and_decode_vs_oracle():
     print(f"[small, density<1] logits err vs oracle {err:.2e}; change vs dense {(got - dense).abs().max().item():.2e}")
     assert err < LOGIT_TOL
     assert (got - dense).abs().max().item() > 10 * LOGIT_TOL          # the layouts really removed attended positions
+    # the forward above ran the fused kernel with the 16-position layout table (key tiles without layout blocks skipped); the composed
+    # path (scores -> masked softmax -> P.V) must agree with it
+    assert eng.layers[0]["layout64"] is not None
+    eng.fused_attention = False
+    composed = eng.forward(cam.cuda(), bev.cuda(), batch, sampling=True)
+    eng.fused_attention = True
+    assert (got - composed).abs().max().item() < 2e-4
     forced = cam.reshape(B, -1)[:, cfg.forward_shuffle_idx]
     toks, trace = GPTSampler(eng, B).sample(bev, batch, forced_tokens=forced, trace_logits=True, steps=300)
     torch.cuda.synchronize()
