@@ -171,6 +171,43 @@ def golden_gpt():
             print("gpt sample4", torch.stack(toks, 1).tolist())
 
 
+MASKGIT_DEPTH = 2
+
+
+def golden_maskgit():
+    """MaskGitTransformerMultiView.forward (logits + embed, masked and unmasked ids) and MaskGit.generate with a SelfCritic
+    (muse_maskgit_pytorch.py:283-366,511-627), reference on CPU, seeded global RNG for the gumbel / critic noise."""
+    mg = ref_import.muse()
+    m = ref_import.stage2()
+    kw, B = GPT_SMALL, 1
+    cfg = m.GPTConfig(**kw)
+    heads = cfg.num_heads
+    tr = mg.MaskGitTransformerMultiView(num_tokens=cfg.vocab_size, dim=cfg.num_embed, seq_len=tuple(cfg.cam_latent_res), depth=MASKGIT_DEPTH,
+                                        dim_head=64, heads=heads, ff_mult=4, cfg=cfg)
+    model = mg.MaskGit(image_size=tuple(cfg.cam_latent_res), transformer=tr, self_token_critic=True).eval()
+    sd = synth.maskgit_state_dict(_sizes(cfg), MASKGIT_DEPTH, heads, seed=3)
+    crit = {k: sd.pop(k) for k in ("to_pred.weight", "to_pred.bias")}
+    missing, unexpected = tr.load_state_dict(sd, strict=False)
+    assert not unexpected and all(k.endswith(".beta") or k == "bev_grid" for k in missing), (missing, unexpected)
+    model.token_critic.to_pred.load_state_dict({"weight": crit["to_pred.weight"], "bias": crit["to_pred.bias"]})
+    cam, bev, batch = synth.stage2_inputs(B, cfg.num_cams, cfg.num_cam_tokens, cfg.num_cond_tokens, cfg.vocab_size, cfg.cond_vocab_size, seed=6)
+    ids = cam.reshape(B * cfg.num_cams, cfg.num_cam_tokens).clone()
+    g = torch.Generator().manual_seed(5)
+    ids[torch.rand(ids.shape, generator=g) < 0.6] = tr.mask_id
+    with torch.no_grad():
+        logits, emb = tr(ids, return_embed=True, conditioning_token_ids=bev, batch=batch)
+        guided = tr.forward_with_cond_scale(ids, conditioning_token_ids=bev, batch=batch, cond_scale=3.0)
+        assert torch.equal(guided, logits)          # eval mode: the "null" pass equals the conditional pass (:341)
+        torch.manual_seed(1234)
+        gen = model.generate(cond_images=bev, fmap_size=tuple(cfg.cam_latent_res), batch=batch, timesteps=6)
+    cols = np.arange(0, cfg.num_cam_tokens, 7)
+    np.savez_compressed(OUT / "maskgit_small.npz", ids=ids.numpy().astype(np.int32), cols=cols, logits=logits[:, cols].numpy(),
+                        embed=emb[:, cols].numpy(), logits_absmax=np.float64(logits.abs().max().item()),
+                        logits_mean=np.float64(logits.double().mean().item()), generated=gen.numpy().astype(np.int32),
+                        gen_seed=np.int64(1234), gen_steps=np.int64(6))
+    print("maskgit", tuple(logits.shape), float(logits.abs().max()), "generated", tuple(gen.shape), int(gen.max()))
+
+
 def golden_topk():
     """Net2NetTransformer.top_k_logits (cond_transformer_multi_view.py:138-142) + softmax on fixed logits, incl. ties."""
     g = torch.Generator().manual_seed(11)
@@ -188,6 +225,9 @@ def golden_topk():
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "maskgit":
+        golden_maskgit()
+        sys.exit(0)
     assert ref_import.available(), "run in the build container (needs /root/reference)"
     OUT.mkdir(parents=True, exist_ok=True)
     which = sys.argv[1:] or ["vq", "vqgan", "topk", "gptconfig", "gpt"]

@@ -105,6 +105,25 @@ def stage2():
     return mingpt_sparse
 
 
+def muse():
+    """Returns the reference's stage2/muse_maskgit_pytorch module (MaskGitTransformerMultiView, SelfCritic, MaskGit), unmodified.  The
+    lucidrains `muse_maskgit_pytorch` package it imports two unused symbols from (:16-17) is absent offline and stubbed."""
+    stage2()
+    for n in ["muse_maskgit_pytorch", "muse_maskgit_pytorch.vqgan_vae", "muse_maskgit_pytorch.t5"]:
+        if n not in sys.modules:
+            sys.modules[n] = mock.MagicMock()
+    try:
+        import beartype  # noqa: F401
+    except Exception:
+        bt = types.ModuleType("beartype")
+        bt.beartype = lambda f: f
+        sys.modules["beartype"] = bt
+    import torchvision.transforms as T
+    if isinstance(sys.modules.get("torchvision"), mock.MagicMock):
+        pass
+    return _load_by_path("ref_muse_maskgit", "multi_view_generation/modules/stage2/muse_maskgit_pytorch.py")
+
+
 def release_stage2():
     """Drop the reference package from sys.modules / sys.path so our drop-in package can be imported."""
     global _stage2_cache

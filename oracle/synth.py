@@ -177,3 +177,40 @@ def stage2_inputs(batch, num_cams=6, cam_tokens=256, cond_tokens=256, vocab=1024
 def image_batch(n, c=3, h=256, w=256, seed=0):
     g = torch.Generator().manual_seed(2000 + seed)
     return torch.randn(n, c, h, w, generator=g)
+
+
+def maskgit_keys(c, depth, heads, dim_head=64, ff_mult=4):
+    """(key, shape, kind) of the reference MaskGitTransformerMultiView state dict (muse_maskgit_pytorch.py:90-129,171-247), the unused
+    `norm.*` / `self_cond_to_init_embed.*` members included so that load_state_dict(strict) finds every parameter."""
+    d, L, inner, ffi = c["num_embed"], c["gpt_block_size"], heads * dim_head, int(c["num_embed"] * ff_mult * 2 / 3)
+    out = [("token_emb.weight", (c["vocab_size"] + 1, d), "small"), ("pos_emb.weight", (c["num_img_tokens"], d), "small"),
+           ("cond_token_emb.weight", (c["cond_vocab_size"], d), "small"), ("cond_pos_emb.weight", (c["num_cond_tokens"], d), "small")]
+
+    def ff(p):
+        return [(f"{p}.0.gamma", (d,), "norm_w"), (f"{p}.1.weight", (2 * ffi, d), "weight"), (f"{p}.3.gamma", (ffi,), "norm_w"),
+                (f"{p}.4.weight", (d, ffi), "weight")]
+    for i in range(depth):
+        for a in (0, 1):
+            p = f"transformer_blocks.layers.{i}.{a}"
+            out += [(f"{p}.norm.gamma", (d,), "norm_w"), (f"{p}.null_kv", (2, heads, 1, dim_head), "embedding"),
+                    (f"{p}.to_q.weight", (inner, d), "weight"), (f"{p}.to_kv.weight", (2 * inner, d), "weight"),
+                    (f"{p}.q_scale", (dim_head,), "norm_w"), (f"{p}.k_scale", (dim_head,), "norm_w"), (f"{p}.to_out.weight", (d, inner), "weight")]
+        out += ff(f"transformer_blocks.layers.{i}.2")
+    out += [("transformer_blocks.norm.gamma", (d,), "norm_w"), ("norm.gamma", (d,), "norm_w"), ("to_logits.weight", (c["vocab_size"], d), "small")]
+    out += ff("self_cond_to_init_embed")
+    out += [("img_embed.weight", (d, 4, 1, 1), "weight"), ("cam_embed.weight", (d, 4, 1, 1), "weight"),
+            ("bev_embed.weight", (d, 2, 1, 1), "weight"), ("bev_embed.bias", (d,), "bias"),
+            ("bev_cam_pos_emb", (1, c["num_cams"], c["num_cond_tokens"], d), "small"), ("camera_bias_emb", (1, L * (L + 1) // 2), "bias_emb")]
+    return out
+
+
+def maskgit_state_dict(c, depth, heads, seed=0, critic=True):
+    """Seeded MaskGit transformer weights (keys as in the reference) plus, with `critic`, the SelfCritic head `to_pred.*`
+    (muse_maskgit_pytorch.py:371-375)."""
+    sd = OrderedDict()
+    for k, shp, kind in maskgit_keys(c, depth, heads):
+        sd[k] = tensor_for(k, shp, seed, kind)
+    if critic:
+        sd["to_pred.weight"] = tensor_for("to_pred.weight", (1, c["num_embed"]), seed, "weight")
+        sd["to_pred.bias"] = tensor_for("to_pred.bias", (1,), seed, "bias")
+    return sd

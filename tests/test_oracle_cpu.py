@@ -105,3 +105,36 @@ def test_topk_oracle(golden_dir):
     p = gpt_oracle.sample_probs(torch.from_numpy(g["logits"]), 1.0, int(g["k"]))
     np.testing.assert_allclose(p.numpy(), g["probs"], rtol=0, atol=1e-7)
     assert np.array_equal((p > 0).sum(-1).numpy(), g["kept"])
+
+
+def _maskgit_case():
+    from oracle import maskgit_oracle  # noqa: F401
+    cfg = GPTConfig(**GPT_SMALL)
+    sd = synth.maskgit_state_dict(gpt_sizes(cfg), 2, cfg.num_heads, seed=3)
+    cam, bev, batch = synth.stage2_inputs(1, cfg.num_cams, cfg.num_cam_tokens, cfg.num_cond_tokens, cfg.vocab_size, cfg.cond_vocab_size, seed=6)
+    return cfg, sd, bev, batch
+
+
+def cpu_noise(kind, step, shape):
+    """Same draws, in the same order, as the reference's gumbel_noise / uniform helpers on a seeded CPU generator."""
+    return torch.zeros(shape).float().uniform_(0, 1)
+
+
+def test_maskgit_oracle_forward_and_generate(golden_dir):
+    """the MaskGit restatement against the unmodified reference (muse_maskgit_pytorch.py) - logits / embeddings of one
+    forward on partly masked ids, and the token ids of a 6-step `generate` with the SelfCritic replaying the reference's RNG draws."""
+    from oracle import maskgit_oracle
+    g = np.load(golden_dir / "maskgit_small.npz")
+    cfg, sd, bev, batch = _maskgit_case()
+    geo = gpt_oracle.geo_from_config(cfg)
+    ids = torch.from_numpy(g["ids"]).long()
+    with torch.no_grad():
+        logits, emb = maskgit_oracle.forward(sd, geo, ids, bev, batch, 2, cfg.num_heads)
+    cols = g["cols"]
+    assert (logits[:, cols] - torch.from_numpy(g["logits"])).abs().max().item() < 2e-5
+    assert (emb[:, cols] - torch.from_numpy(g["embed"])).abs().max().item() < 2e-5
+    assert abs(logits.double().mean().item() - float(g["logits_mean"])) < 1e-6
+    torch.manual_seed(int(g["gen_seed"]))
+    with torch.no_grad():
+        gen = maskgit_oracle.generate(sd, geo, bev, batch, 2, cfg.num_heads, cpu_noise, timesteps=int(g["gen_steps"]))
+    assert np.array_equal(gen.numpy().astype(np.int32), g["generated"])
