@@ -422,6 +422,20 @@ BEVGEN_API int bevgen_attn_fused_fwd(const void* qkv_hi, const void* qkv_lo, int
                                  layout64, (cudaStream_t)stream), "attn_fused_fwd");
 }
 
+/* ---------------------------------------------------------------- MaskGit variant */
+BEVGEN_API int bevgen_mg_head_planes(const float* src, long long src_ld, int src_col0, int n_src, const float* null_vec, const float* scale,
+                                     void* out_hi, void* out_lo, int batch, int dst_rows, int has_null, int heads, void* stream) {
+  if (!src || !out_hi) return fail(BEVGEN_ERR_ARG, "mg_head_planes: bad args");
+  CHECK_LAUNCH(launch_mg_head_planes(src, src_ld, src_col0, n_src, null_vec, scale, (uint16_t*)out_hi, (uint16_t*)out_lo, batch, dst_rows,
+                                     has_null, heads, (cudaStream_t)stream), "mg_head_planes");
+}
+
+BEVGEN_API int bevgen_mg_geglu_ln(const float* h, const float* gamma, void* out_hi, void* out_lo, long long rows, int f, int f_pad, float eps,
+                                  void* stream) {
+  if (!h || !gamma || !out_hi) return fail(BEVGEN_ERR_ARG, "mg_geglu_ln: bad args");
+  CHECK_LAUNCH(launch_mg_geglu_ln(h, gamma, (uint16_t*)out_hi, (uint16_t*)out_lo, rows, f, f_pad, eps, (cudaStream_t)stream), "mg_geglu_ln");
+}
+
 /* ---------------------------------------------------------------- KV-cache decode */
 BEVGEN_API int bevgen_dec_reduce_ln(const float* partials, int ks, long long zstride, const float* bias, const float* residual,
                                     long long residual_row_stride, const float* gamma, const float* beta, float eps, float* x_out, float* y,

@@ -130,6 +130,9 @@ struct GemmPairParams {
 };
 int launch_gemm_pair_f16f8(const GemmPairParams& p, int sm_count, cudaStream_t st);
 
+int launch_mg_head_planes(const float* src, long long src_ld, int src_col0, int n_src, const float* null_vec, const float* scale, uint16_t* hi,
+                          uint16_t* lo, int B, int dst_rows, int has_null, int H, cudaStream_t st);
+int launch_mg_geglu_ln(const float* hin, const float* gamma, uint16_t* hi, uint16_t* lo, long long rows, int f, int f_pad, float eps, cudaStream_t st);
 int launch_attn_fused(const CUtensorMap* tm_hi, const CUtensorMap* tm_lo, const void* bias_f16, const float* y, float* x1, int B, int H, int L,
                       int nc, int d, float scale, int npass, const unsigned long long* layout64, cudaStream_t st);
 

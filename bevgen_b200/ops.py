@@ -452,3 +452,19 @@ def groupnorm_affine(sums, gamma, beta, affine, n, pixels, c, eps=1e-6):
     Stats.launches += 1
     _chk_cuda(sums, gamma, beta, affine)
     _lib.check(lib.bevgen_groupnorm_affine(_ptr(sums), _ptr(gamma), _ptr(beta), n, pixels, c, eps, _ptr(affine), _stream()), "groupnorm_affine")
+
+
+def mg_head_planes(src, src_ld, src_col0, n_src, out_hi, out_lo, batch, dst_rows, heads, null_vec=None, scale=None):
+    """MaskGit attention operand planes (bevgen_mg_head_planes): head split, optional null row, optional cosine-sim normalisation."""
+    lib = _lib.init()
+    Stats.launches += 1
+    _chk_cuda(src, out_hi, out_lo, null_vec, scale)
+    _lib.check(lib.bevgen_mg_head_planes(_ptr(src), src_ld, src_col0, n_src, _ptr(null_vec), _ptr(scale), _ptr(out_hi), _ptr(out_lo), batch,
+                                         dst_rows, 0 if null_vec is None else 1, heads, _stream()), "mg_head_planes")
+
+
+def mg_geglu_ln(h, gamma, out_hi, out_lo, rows, f, f_pad, eps=1e-5):
+    lib = _lib.init()
+    Stats.launches += 1
+    _chk_cuda(h, gamma, out_hi, out_lo)
+    _lib.check(lib.bevgen_mg_geglu_ln(_ptr(h), _ptr(gamma), _ptr(out_hi), _ptr(out_lo), rows, f, f_pad, eps, _stream()), "mg_geglu_ln")

@@ -237,6 +237,21 @@ BEVGEN_API int bevgen_attn_fused_fwd(const void* qkv_hi, const void* qkv_lo, int
                                      const void* bias_tiled, const float* y, float* x1, float scale, int npass, const unsigned long long* layout64,
                                      void* stream);
 
+/* ---------------------------------------------------------------- MaskGit stage-2 variant
+ * The bidirectional decoder of modules/stage2/muse_maskgit_pytorch.py runs its Linear layers and the Q.K^T / P.V products on
+ * bevgen_gemm_tc, LayerNorm on bevgen_layernorm, the biased softmax on bevgen_attn_softmax; these two produce the operand planes between. */
+
+/* Attention.forward :137-154 (head split, null key / value, cosine-sim normalisation): per (row, head) 64-vector of
+ * src[(b*n_src + r) * src_ld + src_col0 + h*64 ..], optionally x / max(|x|, 1e-12) * scale[0..63] (scale == NULL: plain copy), to bf16
+ * hi / lo planes [batch][dst_rows][heads*64].  has_null: destination row 0 = null_vec[h][0..63] (same normalisation), source rows follow
+ * from row 1, rows above n_src + 1 are zero (key padding up to the GEMM tile; the caller masks them in the softmax). */
+BEVGEN_API int bevgen_mg_head_planes(const float* src, long long src_ld, int src_col0, int n_src, const float* null_vec, const float* scale,
+                                     void* out_hi, void* out_lo, int batch, int dst_rows, int has_null, int heads, void* stream);
+/* FeedForward :72-88 between its Linear layers: u = h[:, f:2f] * gelu(h[:, 0:f]); planes = LayerNorm_f(u) * gamma (eps, biased variance),
+ * bf16 hi / lo [rows][f_pad], columns f .. f_pad-1 zero.  f_pad <= 3072. */
+BEVGEN_API int bevgen_mg_geglu_ln(const float* h, const float* gamma, void* out_hi, void* out_lo, long long rows, int f, int f_pad, float eps,
+                                  void* stream);
+
 /* ---------------------------------------------------------------- KV-cache autoregressive decode
  * Replaces the per-token full forward of Net2NetTransformer.sample (modules/stage2/cond_transformer_multi_view.py:154-227)
  * with the cached formulation of SURVEY.md §3.4.  All kernels read the step counter s from device memory (one CUDA graph

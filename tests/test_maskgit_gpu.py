@@ -1,0 +1,87 @@
+"""the MaskGit stage-2 variant on the CUDA library against goldens minted from the unmodified reference
+(modules/stage2/muse_maskgit_pytorch.py) and against the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+from bevgen_b200.gpt_config import GPTConfig
+from oracle import gpt_oracle, maskgit_oracle, synth
+from tests.cases import GPT_SMALL, gpt_sizes
+
+pytestmark = pytest.mark.gpu
+LOGIT_TOL = 1e-3          # north_star's floating-point bar
+
+
+def _case(B=1, precision="fp32x3"):
+    from bevgen_b200.maskgit_engine import MaskGitEngine
+    cfg = GPTConfig(**GPT_SMALL)
+    sd = synth.maskgit_state_dict(gpt_sizes(cfg), 2, cfg.num_heads, seed=3)
+    critic = {"weight": sd.pop("to_pred.weight"), "bias": sd.pop("to_pred.bias")}
+    cam, bev, batch = synth.stage2_inputs(B, cfg.num_cams, cfg.num_cam_tokens, cfg.num_cond_tokens, cfg.vocab_size, cfg.cond_vocab_size, seed=6)
+    eng = MaskGitEngine(sd, cfg, depth=2, heads=cfg.num_heads, device="cuda:0", precision=precision, critic=critic)
+    sd_all = dict(sd, **{"to_pred.weight": critic["weight"], "to_pred.bias": critic["bias"]})
+    return cfg, sd_all, cam, bev, batch, eng
+
+
+def test_forward_vs_reference_golden(golden_dir):
+    g = np.load(golden_dir / "maskgit_small.npz")
+    cfg, sd, cam, bev, batch, eng = _case()
+    ids = torch.from_numpy(g["ids"]).long()
+    logits, emb = eng.forward(ids.cuda(), bev.cuda(), batch)
+    torch.cuda.synchronize()
+    cols = g["cols"]
+    e_l = (logits[:, cols].cpu() - torch.from_numpy(g["logits"])).abs().max().item()
+    e_e = (emb[:, cols].cpu() - torch.from_numpy(g["embed"])).abs().max().item()
+    print(f"[maskgit small] logits err {e_l:.2e} (absmax {float(g['logits_absmax']):.2f}), embed err {e_e:.2e}")
+    assert torch.isfinite(logits).all()
+    assert e_l < LOGIT_TOL and e_e < LOGIT_TOL
+    assert abs(logits.double().mean().item() - float(g["logits_mean"])) < 1e-4
+
+
+def test_forward_batch2_and_critic_vs_oracle():
+    cfg, sd, cam, bev, batch, eng = _case(B=2)
+    ids = cam.reshape(2 * cfg.num_cams, cfg.num_cam_tokens).clone()
+    gen = torch.Generator().manual_seed(9)
+    ids[torch.rand(ids.shape, generator=gen) < 0.5] = cfg.vocab_size
+    geo = gpt_oracle.geo_from_config(cfg)
+    with torch.no_grad():
+        want_l, want_e = maskgit_oracle.forward(sd, geo, ids, bev, batch, 2, cfg.num_heads)
+        want_s = (want_e @ sd["to_pred.weight"].t() + sd["to_pred.bias"])[..., 0]
+    logits, emb = eng.forward(ids.cuda(), bev.cuda(), batch)
+    scores = eng.critic_scores(ids.cuda(), bev.cuda(), batch)
+    torch.cuda.synchronize()
+    assert (logits.cpu() - want_l).abs().max().item() < LOGIT_TOL
+    assert (emb.cpu() - want_e).abs().max().item() < LOGIT_TOL
+    assert (scores.cpu() - want_s).abs().max().item() < LOGIT_TOL
+
+
+def test_generate_replays_the_reference_draws(golden_dir):
+    """6-step generate with the SelfCritic, fed the same uniform draws as the reference's seeded CPU run: every de-masking step's logits
+    match the oracle's on the oracle's own ids, and the final token ids equal the reference's golden ids."""
+    g = np.load(golden_dir / "maskgit_small.npz")
+    cfg, sd, cam, bev, batch, eng = _case()
+    geo = gpt_oracle.geo_from_config(cfg)
+    steps = int(g["gen_steps"])
+    draws = []
+
+    def rec_noise(kind, step, shape):
+        u = torch.zeros(shape).float().uniform_(0, 1)
+        draws.append(u)
+        return u
+    torch.manual_seed(int(g["gen_seed"]))
+    otrace = []
+    with torch.no_grad():
+        want = maskgit_oracle.generate(sd, geo, bev, batch, 2, cfg.num_heads, rec_noise, timesteps=steps, trace=otrace)
+    assert np.array_equal(want.numpy().astype(np.int32), g["generated"])
+    it = iter(draws)
+    trace = []
+    got = eng.generate(bev, batch, timesteps=steps, noise=lambda kind, step, shape: next(it), trace=trace)
+    torch.cuda.synchronize()
+    for (oi, ol), (gi, gl) in zip(otrace, trace):
+        if torch.equal(oi, gi.cpu()):                      # same input ids -> logits within the bar
+            assert (ol - gl.cpu()).abs().max().item() < LOGIT_TOL
+    same = (got.cpu() == want).float().mean().item()
+    print(f"[maskgit generate] identical tokens {same:.4f}")
+    assert torch.equal(trace[0][0].cpu(), otrace[0][0])
+    assert same == 1.0
+    assert int(got.max()) < cfg.vocab_size
