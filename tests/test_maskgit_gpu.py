@@ -85,3 +85,37 @@ def test_generate_replays_the_reference_draws(golden_dir):
     assert torch.equal(trace[0][0].cpu(), otrace[0][0])
     assert same == 1.0
     assert int(got.max()) < cfg.vocab_size
+
+
+def test_module_under_the_reference_import_path(golden_dir):
+    """multi_view_generation.modules.stage2.muse_maskgit_pytorch: reference constructor arguments and state_dict keys (every key of the
+    reference's transformer loads, only its non-trainable buffers are absent from the synthetic dict), forward / generate on the engine."""
+    from multi_view_generation.modules.stage2 import muse_maskgit_pytorch as m
+    g = np.load(golden_dir / "maskgit_small.npz")
+    cfg = GPTConfig(**GPT_SMALL)
+    tr = m.MaskGitTransformerMultiView(num_tokens=cfg.vocab_size, dim=cfg.num_embed, seq_len=tuple(cfg.cam_latent_res), depth=2, dim_head=64,
+                                       heads=cfg.num_heads, ff_mult=4, cfg=cfg)
+    mg = m.MaskGit(image_size=tuple(cfg.cam_latent_res), transformer=tr, self_token_critic=True).eval()
+    sd = synth.maskgit_state_dict(gpt_sizes(cfg), 2, cfg.num_heads, seed=3)
+    crit = {k[len("to_pred."):]: sd.pop(k) for k in ("to_pred.weight", "to_pred.bias")}
+    missing, unexpected = tr.load_state_dict(sd, strict=False)
+    assert not unexpected and all(k.endswith(".beta") or k == "bev_grid" for k in missing)
+    mg.token_critic.to_pred.load_state_dict(crit)
+    with pytest.raises(RuntimeError):
+        tr(torch.from_numpy(g["ids"]).long(), conditioning_token_ids=torch.zeros(1, 256, dtype=torch.long), batch={})     # no CPU fallback
+    mg = mg.cuda()
+    cam, bev, batch = synth.stage2_inputs(1, cfg.num_cams, cfg.num_cam_tokens, cfg.num_cond_tokens, cfg.vocab_size, cfg.cond_vocab_size, seed=6)
+    ids = torch.from_numpy(g["ids"]).long().cuda()
+    logits, emb = tr(ids, return_embed=True, conditioning_token_ids=bev.cuda(), batch=batch)
+    guided = tr.forward_with_cond_scale(ids, conditioning_token_ids=bev.cuda(), batch=batch, cond_scale=3.0)
+    assert torch.equal(guided, logits)
+    assert (logits[:, g["cols"]].cpu() - torch.from_numpy(g["logits"])).abs().max().item() < LOGIT_TOL
+    mg.sample_seed = 7
+    a = mg.generate(cond_images=bev.cuda(), fmap_size=tuple(cfg.cam_latent_res), batch=batch, timesteps=4)
+    b = mg.generate(cond_images=bev.cuda(), fmap_size=tuple(cfg.cam_latent_res), batch=batch, timesteps=4)
+    assert a.shape == (cfg.num_cams, 16, 16) and torch.equal(a, b) and int(a.max()) < cfg.vocab_size and int(a.min()) >= 0
+    # partial decoding: given cameras keep their tokens
+    init = torch.full((cfg.num_cams, cfg.num_cam_tokens), mg.mask_id, dtype=torch.long, device="cuda")
+    init[2] = cam.reshape(cfg.num_cams, -1)[2].cuda()
+    c = mg.generate(init_ids=init, cond_images=bev.cuda(), fmap_size=tuple(cfg.cam_latent_res), batch=batch, timesteps=4)
+    assert torch.equal(c.reshape(cfg.num_cams, -1)[2], init[2])
