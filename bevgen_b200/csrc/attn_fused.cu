@@ -37,8 +37,10 @@ struct AttnCfg {
 struct AttnParams {
   CUtensorMap tm[2];        // hi, lo planes of qkv viewed as [B*L rows][3d cols], box (64, 128)
   const uint4* bias;        // tiled, pre-scaled camera bias (see bevgen_attn_fused_fwd) or null
-  const float* y;           // [B][L][d]
-  float* x1;                // [B][L][d]
+  const float* y;           // [B][L][d] residual input or null
+  float* x1;                // [B][L][d] fp32 output or null
+  uint16_t* o_hi;           // bf16 hi / lo output planes [B][L][d] or null (operand of a following GEMM: the MaskGit to_out Linear)
+  uint16_t* o_lo;
   int B, H, L, nc, d;
   float scale_log2e;        // d_head^-1/2 * log2(e)
   const unsigned long long* layout64;   // block-sparse layouts (density < 1) or null: [H][L/128 query tiles][L/128 key tiles], bit (8*rb + kb)
@@ -351,12 +353,30 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fused_kernel(const __grid_
     const float lsum = (l4.x + l4.y) + (l4.z + l4.w);
     const float inv = lsum > 0.f ? 1.0f / lsum : 0.f;          // a row without any attended key (degenerate layout) contributes nothing
     const size_t off = ((size_t)(b * p.L + gi)) * p.d + h * AT_DH + part * AT_CPT;
-    const float4* yp = reinterpret_cast<const float4*>(p.y + off);
-    float4* op = reinterpret_cast<float4*>(p.x1 + off);
 #pragma unroll
-    for (int c = 0; c < AT_CPT / 4; ++c) {
-      const float4 yv = __ldg(yp + c);
-      op[c] = make_float4(yv.x + o_acc[4 * c] * inv, yv.y + o_acc[4 * c + 1] * inv, yv.z + o_acc[4 * c + 2] * inv, yv.w + o_acc[4 * c + 3] * inv);
+    for (int c = 0; c < AT_CPT; ++c) o_acc[c] *= inv;
+    if (p.y != nullptr) {
+      const float4* yp = reinterpret_cast<const float4*>(p.y + off);
+#pragma unroll
+      for (int c = 0; c < AT_CPT / 4; ++c) {
+        const float4 yv = __ldg(yp + c);
+        o_acc[4 * c] += yv.x; o_acc[4 * c + 1] += yv.y; o_acc[4 * c + 2] += yv.z; o_acc[4 * c + 3] += yv.w;
+      }
+    }
+    if (p.x1 != nullptr) {
+      float4* op = reinterpret_cast<float4*>(p.x1 + off);
+#pragma unroll
+      for (int c = 0; c < AT_CPT / 4; ++c) op[c] = make_float4(o_acc[4 * c], o_acc[4 * c + 1], o_acc[4 * c + 2], o_acc[4 * c + 3]);
+    }
+    if (p.o_hi != nullptr) {
+      uint32_t hh[AT_CPT / 2], ll[AT_CPT / 2];
+#pragma unroll
+      for (int c = 0; c < AT_CPT / 2; ++c) split_bf16x2(o_acc[2 * c], o_acc[2 * c + 1], hh[c], ll[c]);
+#pragma unroll
+      for (int c = 0; c < AT_CPT / 8; ++c) {
+        reinterpret_cast<uint4*>(p.o_hi + off)[c] = make_uint4(hh[4 * c], hh[4 * c + 1], hh[4 * c + 2], hh[4 * c + 3]);
+        if (p.o_lo != nullptr) reinterpret_cast<uint4*>(p.o_lo + off)[c] = make_uint4(ll[4 * c], ll[4 * c + 1], ll[4 * c + 2], ll[4 * c + 3]);
+      }
     }
   }
   tc_fence_before();
@@ -378,7 +398,7 @@ static int launch_attn(const AttnParams& p, cudaStream_t st) {
 }
 
 int launch_attn_fused(const CUtensorMap* tm_hi, const CUtensorMap* tm_lo, const void* bias_f16, const float* y, float* x1, int B, int H, int L,
-                      int nc, int d, float scale, int npass, const unsigned long long* layout64, cudaStream_t st) {
+                      int nc, int d, float scale, int npass, const unsigned long long* layout64, uint16_t* out_hi, uint16_t* out_lo, cudaStream_t st) {
   if (L % AT_BM != 0 || nc % AT_BN != 0 || nc < AT_BN || nc > L || d != H * AT_DH || L / AT_BN > 32) return BEVGEN_ERR_ARG;
   AttnParams p;
   p.tm[0] = *tm_hi;
@@ -388,6 +408,7 @@ int launch_attn_fused(const CUtensorMap* tm_hi, const CUtensorMap* tm_lo, const 
   p.B = B; p.H = H; p.L = L; p.nc = nc; p.d = d;
   p.scale_log2e = scale * 1.4426950408889634f;
   p.layout64 = layout64;
+  p.o_hi = out_hi; p.o_lo = out_lo;
   return npass == 3 ? launch_attn<3>(p, st) : launch_attn<1>(p, st);
 }
 

@@ -402,10 +402,10 @@ BEVGEN_API int bevgen_attn_softmax(const float* s, const float* bias, const unsi
 
 BEVGEN_API int bevgen_attn_fused_fwd(const void* qkv_hi, const void* qkv_lo, int batch, int seq_len, int heads, int d, int n_cond,
                                      const void* bias_f16, const float* y, float* x1, float scale, int npass, const unsigned long long* layout64,
-                                     void* stream) {
+                                     void* out_hi, void* out_lo, void* stream) {
   int rc = ensure_init();
   if (rc) return rc;
-  if (!qkv_hi || !y || !x1 || (npass == 3 && !qkv_lo) || !(npass == 1 || npass == 3)) return fail(BEVGEN_ERR_ARG, "attn_fused_fwd: bad args");
+  if (!qkv_hi || (!x1 && !out_hi) || (npass == 3 && !qkv_lo) || !(npass == 1 || npass == 3)) return fail(BEVGEN_ERR_ARG, "attn_fused_fwd: bad args");
   if (seq_len % 128 != 0 || n_cond % 128 != 0 || n_cond < 128 || n_cond > seq_len || d != heads * 64)
     return fail(BEVGEN_ERR_ARG, "attn_fused_fwd: needs seq_len, n_cond multiples of 128 and d_head = 64 (got L=%d nc=%d d=%d H=%d)", seq_len, n_cond, d, heads);
   if (seq_len > 4096) return fail(BEVGEN_ERR_ARG, "attn_fused_fwd: seq_len %d > 4096", seq_len);
@@ -419,15 +419,16 @@ BEVGEN_API int bevgen_attn_fused_fwd(const void* qkv_hi, const void* qkv_lo, int
     if (rc) return rc;
   }
   CHECK_LAUNCH(launch_attn_fused(&tm[0], npass == 3 ? &tm[1] : nullptr, bias_f16, y, x1, batch, heads, seq_len, n_cond, d, scale, npass,
-                                 layout64, (cudaStream_t)stream), "attn_fused_fwd");
+                                 layout64, (uint16_t*)out_hi, (uint16_t*)out_lo, (cudaStream_t)stream), "attn_fused_fwd");
 }
 
 /* ---------------------------------------------------------------- MaskGit variant */
-BEVGEN_API int bevgen_mg_head_planes(const float* src, long long src_ld, int src_col0, int n_src, const float* null_vec, const float* scale,
-                                     void* out_hi, void* out_lo, int batch, int dst_rows, int has_null, int heads, void* stream) {
+BEVGEN_API int bevgen_mg_head_planes(const float* src, long long src_ld, int src_col0, int n_src, int src_batch_rows, const float* null_vec,
+                                     const float* scale, void* out_hi, void* out_lo, int batch, int dst_rows, long long dst_ld, int dst_col0,
+                                     int has_null, int heads, void* stream) {
   if (!src || !out_hi) return fail(BEVGEN_ERR_ARG, "mg_head_planes: bad args");
-  CHECK_LAUNCH(launch_mg_head_planes(src, src_ld, src_col0, n_src, null_vec, scale, (uint16_t*)out_hi, (uint16_t*)out_lo, batch, dst_rows,
-                                     has_null, heads, (cudaStream_t)stream), "mg_head_planes");
+  CHECK_LAUNCH(launch_mg_head_planes(src, src_ld, src_col0, n_src, src_batch_rows, null_vec, scale, (uint16_t*)out_hi, (uint16_t*)out_lo, batch,
+                                     dst_rows, dst_ld, dst_col0, has_null, heads, (cudaStream_t)stream), "mg_head_planes");
 }
 
 BEVGEN_API int bevgen_mg_geglu_ln(const float* h, const float* gamma, void* out_hi, void* out_lo, long long rows, int f, int f_pad, float eps,

@@ -103,6 +103,14 @@ class MaskGitEngine:
             m[:, : n_keys + 1] = 1
             return t.contiguous(), m.contiguous()
         self.bias_self, self.mask_self = table(None if bias is None else bias[self.nc:, self.nc:], self.n_img, self.lk_self)
+        # self-attention on the fused flash-style kernel: q | k | v share one plane of lk_self rows per scene (query i at row i, null key at
+        # row 0, key j at row j + 1), dense support (n_cond = seq_len), padding keys switched off by -inf entries of the tiled bias table
+        self.fused_self = self.lk_self <= 4096
+        if self.fused_self:
+            full = torch.zeros(self.lk_self, self.lk_self, device=dev)
+            full[: self.n_img] = self.bias_self
+            full[:, self.n_img + 1:] = float("-inf")
+            self.bias_self_tiled = ops.tile_attention_bias(full, self.scale)
         self.bias_cross, self.mask_cross = table(None if bias is None else bias[self.nc:, : self.nc], self.nc, self.lk_cross)
 
     # ------------------------------------------------------------------ helpers
@@ -143,6 +151,22 @@ class MaskGitEngine:
         self._linear(op, aw["wout"], self.d, B * n, inner, residual=residual, out_f32=out)
         return out
 
+    def _attend_self_fused(self, qkv, aw, B, residual):
+        """Self-attention through bevgen_attn_fused_fwd (no score matrix in HBM): operand planes [B][lk][3*inner], output planes -> to_out."""
+        n, H, inner, lk = self.n_img, self.H, self.inner, self.lk_self
+        fp = self._planes((B * lk, 3 * inner))
+        ops.mg_head_planes(qkv, 3 * inner, 0, n, fp[0], fp[1], B, lk, H, scale=aw["q_scale"], dst_ld=3 * inner, dst_col0=0)
+        ops.mg_head_planes(qkv, 3 * inner, inner, n, fp[0], fp[1], B, lk, H, null_vec=aw["null_k"], scale=aw["k_scale"], dst_ld=3 * inner, dst_col0=inner)
+        ops.mg_head_planes(qkv, 3 * inner, 2 * inner, n, fp[0], fp[1], B, lk, H, null_vec=aw["null_v"], dst_ld=3 * inner, dst_col0=2 * inner)
+        op = self._planes((B * lk, inner))
+        ops.attn_fused_fwd(fp[0], fp[1], B, lk, H, inner, lk, self.bias_self_tiled, None, None, self.scale, self.npass,
+                           algo_flops=4.0 * B * H * 64 * float(n) * (n + 1), out_hi=op[0], out_lo=op[1])
+        out = torch.empty((B * n, self.d), dtype=torch.float32, device=self.dev)
+        # rows n .. lk-1 of every scene are padding queries: the GEMM reads the [B][lk] plane and stores the first n rows of each scene
+        ops.gemm_tc(a_hi=op[0], a_lo=op[1], a_dims=(B, 1, lk, inner), b_hi=aw["wout"][0], b_lo=aw["wout"][1], k=inner, n_cols=self.d, out_w=n,
+                    z_outer=B, out_zo_stride=n * self.d, ldc=self.d, residual=residual, out_f32=out, bn=128, npass=self.npass)
+        return out
+
     def embed(self, ids, cond_ids, batch):
         """-> (x fp32 [B*n_img, d], context planes [B*nc, d])."""
         B = cond_ids.shape[0]
@@ -177,7 +201,10 @@ class MaskGitEngine:
             yp = self._ln_planes(x, sa["gamma"], rows)
             qkv = torch.empty((rows, 3 * inner), dtype=torch.float32, device=self.dev)
             self._linear(yp, sa["wqkv"], 3 * inner, rows, d, out_f32=qkv)
-            x = self._attend(qkv, 3 * inner, 0, qkv, 3 * inner, inner, 2 * inner, n, self.lk_self, sa, self.bias_self, self.mask_self, B, x)
+            if self.fused_self:
+                x = self._attend_self_fused(qkv, sa, B, x)
+            else:
+                x = self._attend(qkv, 3 * inner, 0, qkv, 3 * inner, inner, 2 * inner, n, self.lk_self, sa, self.bias_self, self.mask_self, B, x)
             del qkv
             yp = self._ln_planes(x, ca["gamma"], rows)
             q = torch.empty((rows, inner), dtype=torch.float32, device=self.dev)

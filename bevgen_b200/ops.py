@@ -371,12 +371,12 @@ def layout_to_tiles64(layout: torch.Tensor, block: int, L: int) -> torch.Tensor:
     return (t << torch.arange(64, device=layout.device, dtype=torch.int64)).sum(-1).contiguous()      # bit 63 wraps into the sign
 
 
-def attn_fused_fwd(qkv_hi, qkv_lo, B, L, H, d, n_cond, bias_f16, y, x1, scale, npass, algo_flops=0.0, layout64=None):
+def attn_fused_fwd(qkv_hi, qkv_lo, B, L, H, d, n_cond, bias_f16, y, x1, scale, npass, algo_flops=0.0, layout64=None, out_hi=None, out_lo=None):
     lib = _lib.init()
-    _chk_cuda(qkv_hi, qkv_lo, bias_f16, y, x1, layout64)
+    _chk_cuda(qkv_hi, qkv_lo, bias_f16, y, x1, layout64, out_hi, out_lo)
     Stats.launches += 1
     call = lambda: _lib.check(lib.bevgen_attn_fused_fwd(_ptr(qkv_hi), _ptr(qkv_lo), B, L, H, d, n_cond, _ptr(bias_f16), _ptr(y), _ptr(x1),
-                                                        float(scale), npass, _ptr(layout64), _stream()), "attn_fused_fwd")
+                                                        float(scale), npass, _ptr(layout64), _ptr(out_hi), _ptr(out_lo), _stream()), "attn_fused_fwd")
     if Stats.timer is not None:
         Stats.timer("attn_fused", call, algo_flops)
     else:
@@ -454,13 +454,15 @@ def groupnorm_affine(sums, gamma, beta, affine, n, pixels, c, eps=1e-6):
     _lib.check(lib.bevgen_groupnorm_affine(_ptr(sums), _ptr(gamma), _ptr(beta), n, pixels, c, eps, _ptr(affine), _stream()), "groupnorm_affine")
 
 
-def mg_head_planes(src, src_ld, src_col0, n_src, out_hi, out_lo, batch, dst_rows, heads, null_vec=None, scale=None):
+def mg_head_planes(src, src_ld, src_col0, n_src, out_hi, out_lo, batch, dst_rows, heads, null_vec=None, scale=None, src_batch_rows=None,
+                   dst_ld=None, dst_col0=0):
     """MaskGit attention operand planes (bevgen_mg_head_planes): head split, optional null row, optional cosine-sim normalisation."""
     lib = _lib.init()
     Stats.launches += 1
     _chk_cuda(src, out_hi, out_lo, null_vec, scale)
-    _lib.check(lib.bevgen_mg_head_planes(_ptr(src), src_ld, src_col0, n_src, _ptr(null_vec), _ptr(scale), _ptr(out_hi), _ptr(out_lo), batch,
-                                         dst_rows, 0 if null_vec is None else 1, heads, _stream()), "mg_head_planes")
+    _lib.check(lib.bevgen_mg_head_planes(_ptr(src), src_ld, src_col0, n_src, n_src if src_batch_rows is None else src_batch_rows, _ptr(null_vec),
+                                         _ptr(scale), _ptr(out_hi), _ptr(out_lo), batch, dst_rows, 64 * heads if dst_ld is None else dst_ld, dst_col0,
+                                         0 if null_vec is None else 1, heads, _stream()), "mg_head_planes")
 
 
 def mg_geglu_ln(h, gamma, out_hi, out_lo, rows, f, f_pad, eps=1e-5):

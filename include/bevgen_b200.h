@@ -235,18 +235,22 @@ BEVGEN_API int bevgen_attn_softmax(const float* s, const float* bias, const unsi
  * allowed(i,j) is ANDed with it; key tiles whose entry is 0 are skipped (no loads, no MMAs). */
 BEVGEN_API int bevgen_attn_fused_fwd(const void* qkv_hi, const void* qkv_lo, int batch, int seq_len, int heads, int d, int n_cond,
                                      const void* bias_tiled, const float* y, float* x1, float scale, int npass, const unsigned long long* layout64,
-                                     void* stream);
+                                     void* out_hi, void* out_lo, void* stream);
+/* y may be NULL (no residual); the result goes to x1 (fp32) and / or to bf16 hi / lo planes out_hi / out_lo [batch][seq_len][d] (the A operand of
+ * a following bevgen_gemm_tc: MaskGit's to_out Linear).  n_cond == seq_len gives dense (bidirectional) attention: MaskGit self-attention
+ * runs it with the null key as key 0 and -inf bias entries on the padding keys. */
 
 /* ---------------------------------------------------------------- MaskGit stage-2 variant
  * The bidirectional decoder of modules/stage2/muse_maskgit_pytorch.py runs its Linear layers and the Q.K^T / P.V products on
  * bevgen_gemm_tc, LayerNorm on bevgen_layernorm, the biased softmax on bevgen_attn_softmax; these two produce the operand planes between. */
 
 /* Attention.forward :137-154 (head split, null key / value, cosine-sim normalisation): per (row, head) 64-vector of
- * src[(b*n_src + r) * src_ld + src_col0 + h*64 ..], optionally x / max(|x|, 1e-12) * scale[0..63] (scale == NULL: plain copy), to bf16
- * hi / lo planes [batch][dst_rows][heads*64].  has_null: destination row 0 = null_vec[h][0..63] (same normalisation), source rows follow
+ * src[(b*src_batch_rows + r) * src_ld + src_col0 + h*64 ..], optionally x / max(|x|, 1e-12) * scale[0..63] (scale == NULL: plain copy), to bf16
+ * hi / lo planes of [batch][dst_rows] rows with pitch dst_ld elements, heads at columns dst_col0 + 64 h (q | k | v may share one plane).  has_null: destination row 0 = null_vec[h][0..63] (same normalisation), source rows follow
  * from row 1, rows above n_src + 1 are zero (key padding up to the GEMM tile; the caller masks them in the softmax). */
-BEVGEN_API int bevgen_mg_head_planes(const float* src, long long src_ld, int src_col0, int n_src, const float* null_vec, const float* scale,
-                                     void* out_hi, void* out_lo, int batch, int dst_rows, int has_null, int heads, void* stream);
+BEVGEN_API int bevgen_mg_head_planes(const float* src, long long src_ld, int src_col0, int n_src, int src_batch_rows, const float* null_vec,
+                                     const float* scale, void* out_hi, void* out_lo, int batch, int dst_rows, long long dst_ld, int dst_col0,
+                                     int has_null, int heads, void* stream);
 /* FeedForward :72-88 between its Linear layers: u = h[:, f:2f] * gelu(h[:, 0:f]); planes = LayerNorm_f(u) * gamma (eps, biased variance),
  * bf16 hi / lo [rows][f_pad], columns f .. f_pad-1 zero.  f_pad <= 3072. */
 BEVGEN_API int bevgen_mg_geglu_ln(const float* h, const float* gamma, void* out_hi, void* out_lo, long long rows, int f, int f_pad, float eps,
