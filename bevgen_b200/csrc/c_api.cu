@@ -431,10 +431,10 @@ BEVGEN_API int bevgen_mg_head_planes(const float* src, long long src_ld, int src
                                      dst_rows, dst_ld, dst_col0, has_null, heads, (cudaStream_t)stream), "mg_head_planes");
 }
 
-BEVGEN_API int bevgen_mg_geglu_ln(const float* h, const float* gamma, void* out_hi, void* out_lo, long long rows, int f, int f_pad, float eps,
-                                  void* stream) {
+BEVGEN_API int bevgen_mg_geglu_ln(const float* h, long long h_ld, const float* gamma, void* out_hi, void* out_lo, long long rows, int f, int f_pad,
+                                  float eps, int f16f8, void* stream) {
   if (!h || !gamma || !out_hi) return fail(BEVGEN_ERR_ARG, "mg_geglu_ln: bad args");
-  CHECK_LAUNCH(launch_mg_geglu_ln(h, gamma, (uint16_t*)out_hi, (uint16_t*)out_lo, rows, f, f_pad, eps, (cudaStream_t)stream), "mg_geglu_ln");
+  CHECK_LAUNCH(launch_mg_geglu_ln(h, h_ld, gamma, (uint16_t*)out_hi, (uint16_t*)out_lo, rows, f, f_pad, eps, f16f8, (cudaStream_t)stream), "mg_geglu_ln");
 }
 
 /* ---------------------------------------------------------------- KV-cache decode */

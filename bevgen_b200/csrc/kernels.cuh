@@ -132,7 +132,8 @@ int launch_gemm_pair_f16f8(const GemmPairParams& p, int sm_count, cudaStream_t s
 
 int launch_mg_head_planes(const float* src, long long src_ld, int src_col0, int n_src, int src_batch_rows, const float* null_vec, const float* scale,
                           uint16_t* hi, uint16_t* lo, int B, int dst_rows, long long dst_ld, int dst_col0, int has_null, int H, cudaStream_t st);
-int launch_mg_geglu_ln(const float* hin, const float* gamma, uint16_t* hi, uint16_t* lo, long long rows, int f, int f_pad, float eps, cudaStream_t st);
+int launch_mg_geglu_ln(const float* hin, long long h_ld, const float* gamma, uint16_t* hi, uint16_t* lo, long long rows, int f, int f_pad, float eps,
+                       int f16f8, cudaStream_t st);
 int launch_attn_fused(const CUtensorMap* tm_hi, const CUtensorMap* tm_lo, const void* bias_f16, const float* y, float* x1, int B, int H, int L,
                       int nc, int d, float scale, int npass, const unsigned long long* layout64, uint16_t* out_hi, uint16_t* out_lo, cudaStream_t st);
 

@@ -1,5 +1,8 @@
 // Helper kernels of the MaskGit stage-2 variant (reference modules/stage2/muse_maskgit_pytorch.py).  The GEMMs of that
 // variant run on gemm_tc, LayerNorm / softmax on transformer.cu; these two kernels are the operand-plane producers in between.
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
+
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -66,12 +69,15 @@ int launch_mg_head_planes(const float* src, long long src_ld, int src_col0, int 
 // ------------------------------------------------------------------------------------------------
 constexpr int GEGLU_MAX = 12;
 
-__global__ void __launch_bounds__(256) mg_geglu_ln_kernel(const float* __restrict__ hin, const float* __restrict__ gamma, uint16_t* __restrict__ hi,
-                                                          uint16_t* __restrict__ lo, int f, int f_pad, float eps) {
+// f16f8 != 0: the planes are the scaled f16f8 operand of bevgen_linear_f16f8 instead (fp16(y * 2^6) [rows][f_pad] + e4m3 pair plane
+// [rows][2 f_pad bytes]: per 64-column chunk 64 bytes e4m3((y - y16) * 2^13) then 64 bytes e4m3(y)); h_ld = pitch of the input rows.
+__global__ void __launch_bounds__(256) mg_geglu_ln_kernel(const float* __restrict__ hin, long long h_ld, const float* __restrict__ gamma,
+                                                          uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, int f, int f_pad, float eps,
+                                                          int f16f8) {
   __shared__ float red[8];
   __shared__ float bc;
   const long long row = blockIdx.x;
-  const float* xr = hin + row * 2 * f;
+  const float* xr = hin + row * h_ld;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float u[GEGLU_MAX];
   float s = 0.f;
@@ -106,6 +112,14 @@ __global__ void __launch_bounds__(256) mg_geglu_ln_kernel(const float* __restric
     const int c = j * 256 + tid;
     if (c < f_pad) {
       const float y = c < f ? (u[j] - mean) * rstd * __ldg(gamma + c) : 0.f;
+      if (f16f8) {
+        const __half hs = __float2half_rn(y * 64.0f);
+        reinterpret_cast<__half*>(hi)[row * f_pad + c] = hs;
+        uint8_t* pp = reinterpret_cast<uint8_t*>(lo) + row * 2 * f_pad + (c >> 6) * 128 + (c & 63);
+        pp[0] = (uint8_t)__nv_cvt_float_to_fp8(fmaf(__half2float(hs), -128.0f, y * 8192.0f), __NV_SATFINITE, __NV_E4M3);
+        pp[64] = (uint8_t)__nv_cvt_float_to_fp8(y, __NV_SATFINITE, __NV_E4M3);
+        continue;
+      }
       __nv_bfloat16 h0, l0;
       split_bf16(y, h0, l0);
       hi[row * f_pad + c] = __bfloat16_as_ushort(h0);
@@ -114,9 +128,10 @@ __global__ void __launch_bounds__(256) mg_geglu_ln_kernel(const float* __restric
   }
 }
 
-int launch_mg_geglu_ln(const float* hin, const float* gamma, uint16_t* hi, uint16_t* lo, long long rows, int f, int f_pad, float eps, cudaStream_t st) {
-  if (rows < 1 || f < 1 || f_pad < f || f_pad > 256 * GEGLU_MAX) return BEVGEN_ERR_ARG;
-  mg_geglu_ln_kernel<<<(unsigned)rows, 256, 0, st>>>(hin, gamma, hi, lo, f, f_pad, eps);
+int launch_mg_geglu_ln(const float* hin, long long h_ld, const float* gamma, uint16_t* hi, uint16_t* lo, long long rows, int f, int f_pad, float eps,
+                       int f16f8, cudaStream_t st) {
+  if (rows < 1 || f < 1 || f_pad < f || f_pad > 256 * GEGLU_MAX || h_ld < 2LL * f || (f16f8 && (!lo || (f_pad & 63)))) return BEVGEN_ERR_ARG;
+  mg_geglu_ln_kernel<<<(unsigned)rows, 256, 0, st>>>(hin, h_ld, gamma, hi, lo, f, f_pad, eps, f16f8);
   return cudaGetLastError() == cudaSuccess ? BEVGEN_OK : BEVGEN_ERR_CUDA;
 }
 

@@ -22,14 +22,17 @@ from .gpt_engine import _planes_of
 
 class MaskGitEngine:
     def __init__(self, state_dict, cfg, depth, heads, dim_head=64, ff_mult=4, device="cuda", precision="fp32x3", critic=None):
-        assert precision in ("fp32x3", "bf16")
+        # "fp32x3": every GEMM is the bf16x3 split product on gemm_tc; "f16f8" (default parity mode): the large Linear layers (self q|k|v,
+        # cross q, both feed-forward layers = 86 % of the linear FLOPs) run on the 2-CTA f16f8 GEMM (gemm_pair.cu), the rest stays bf16x3
+        assert precision in ("fp32x3", "f16f8", "bf16")
         if dim_head != 64:
             raise ValueError("the attention kernels are built for d_head = 64")
         if cfg.num_pad_tokens != 0:
             raise ValueError("MaskGit needs gpt_block_size == num_cond_tokens + num_img_tokens (the reference slices the camera bias "
                              "with that assumption, muse_maskgit_pytorch.py:150-156); use sparse_block_size=1 as its config does")
         self.cfg, self.precision = cfg, precision
-        self.npass = 3 if precision == "fp32x3" else 1
+        self.npass = 1 if precision == "bf16" else 3
+        self.pair = precision == "f16f8"
         self.dev = dev = torch.device(device)
         sd = state_dict
         self.d = d = cfg.num_embed
@@ -38,6 +41,7 @@ class MaskGitEngine:
         self.nc, self.n_img, self.L = cfg.num_cond_tokens, cfg.num_img_tokens, cfg.gpt_block_size
         self.f = int(d * ff_mult * 2 / 3)
         self.f_pad = -(-self.f // 64) * 64
+        self.n1_pad = -(-2 * self.f // 32) * 32
         if d % 128 or d > 1024 or self.f_pad > 3072:
             raise ValueError(f"unsupported width {d}")
         self.vocab = sd["to_logits.weight"].shape[0]
@@ -62,6 +66,13 @@ class MaskGitEngine:
             w2 = torch.zeros(d, self.f_pad, device=dev)
             w2[:, : self.f] = sd[f"{p}.2.4.weight"].detach().to(dev, torch.float32)
             lw["ff"] = dict(gamma0=f32(f"{p}.2.0.gamma"), w1=pl(sd[f"{p}.2.1.weight"]), gamma3=f32(f"{p}.2.3.gamma"), w2=pl(w2))
+            if self.pair:
+                pk = lambda w: ops.pack_linear_f16f8(w.detach().to(dev, torch.float32).contiguous())
+                lw["self"]["wqkv_p"] = pk(torch.cat([sd[f"{p}.0.to_q.weight"], sd[f"{p}.0.to_kv.weight"]], 0))
+                lw["cross"]["wq_p"] = pk(sd[f"{p}.1.to_q.weight"])
+                w1 = torch.zeros(self.n1_pad, d, device=dev)            # output features padded to the GEMM's 32-column epilogue chunk
+                w1[: 2 * self.f] = sd[f"{p}.2.1.weight"].detach().to(dev, torch.float32)
+                lw["ff"]["w1_p"], lw["ff"]["w2_p"] = pk(w1), pk(w2)
             self.layers.append(lw)
         self.gamma_f = f32("transformer_blocks.norm.gamma")
         self.w_logits = pl(sd["to_logits.weight"])
@@ -103,6 +114,7 @@ class MaskGitEngine:
             m[:, : n_keys + 1] = 1
             return t.contiguous(), m.contiguous()
         self.bias_self, self.mask_self = table(None if bias is None else bias[self.nc:, self.nc:], self.n_img, self.lk_self)
+        self.bias_cross, self.mask_cross = table(None if bias is None else bias[self.nc:, : self.nc], self.nc, self.lk_cross)
         # self-attention on the fused flash-style kernel: q | k | v share one plane of lk_self rows per scene (query i at row i, null key at
         # row 0, key j at row j + 1), dense support (n_cond = seq_len), padding keys switched off by -inf entries of the tiled bias table
         self.fused_self = self.lk_self <= 4096
@@ -111,7 +123,16 @@ class MaskGitEngine:
             full[: self.n_img] = self.bias_self
             full[:, self.n_img + 1:] = float("-inf")
             self.bias_self_tiled = ops.tile_attention_bias(full, self.scale)
-        self.bias_cross, self.mask_cross = table(None if bias is None else bias[self.nc:, : self.nc], self.nc, self.lk_cross)
+            # cross-attention on the same kernel and geometry: the context keys (null + n_cond, padded to lk_cross) occupy the first
+            # key tiles, the layout table (SURVEY 8f-2 mechanism) makes every role skip the remaining ones
+            full = torch.zeros(self.lk_self, self.lk_self, device=dev)
+            full[: self.n_img, : self.lk_cross] = self.bias_cross
+            full[:, self.nc + 1:] = float("-inf")
+            self.bias_cross_tiled = ops.tile_attention_bias(full, self.scale)
+            nt = self.lk_self // 128
+            t = torch.zeros(self.H, nt, nt, dtype=torch.int64, device=dev)
+            t[:, :, : self.lk_cross // 128] = -1
+            self.cross_tiles = t.contiguous()
 
     # ------------------------------------------------------------------ helpers
     def _planes(self, shape):
@@ -124,10 +145,17 @@ class MaskGitEngine:
         ops.gemm_tc(a_hi=a[0], a_lo=a[1], a_dims=(1, 1, rows, k), b_hi=w[0], b_lo=w[1], k=k, n_cols=n_cols, out_w=rows, ldc=n_cols, bias=bias,
                     residual=residual, out_f32=out_f32, out_hi=oh, out_lo=ol, bn=128, npass=self.npass)
 
-    def _ln_planes(self, x, gamma, rows, y=None):
+    def _ln_planes(self, x, gamma, rows, y=None, f16f8=False):
+        if f16f8:       # scaled fp16 plane + e4m3 pair plane: A operand of bevgen_linear_f16f8
+            yp = (torch.empty((rows, self.d), dtype=torch.float16, device=self.dev), torch.empty((rows, 2 * self.d), dtype=torch.uint8, device=self.dev))
+            ops.layernorm(x, gamma, self.zero_d, y=y, out_hi=yp[0], out_lo=yp[1], rows=rows, f16f8=True, scaled=True)
+            return yp
         yp = self._planes((rows, self.d))
         ops.layernorm(x, gamma, self.zero_d, y=y, out_hi=yp[0], out_lo=yp[1], rows=rows)
         return yp
+
+    def _pair_linear(self, a, w, n_cols, rows, k, residual=None, out_f32=None):
+        ops.linear_f16f8(a[0], a[1], w[0], w[1], w[2], rows, n_cols, k, residual=residual, out_f32=out_f32)
 
     def _attend(self, q_src, q_ld, q_col0, kv_src, kv_ld, k_col0, v_col0, n_kv, lk, aw, bias, mask, B, residual):
         """softmax(8 * l2norm(q).l2norm(k) + bias) v over [null | n_kv keys], then to_out + residual -> fp32 [B*n_img, d]."""
@@ -167,6 +195,20 @@ class MaskGitEngine:
                     z_outer=B, out_zo_stride=n * self.d, ldc=self.d, residual=residual, out_f32=out, bn=128, npass=self.npass)
         return out
 
+    def _attend_cross_fused(self, q, kv, aw, B, residual):
+        n, H, inner, lk = self.n_img, self.H, self.inner, self.lk_self
+        fp = self._planes((B * lk, 3 * inner))
+        ops.mg_head_planes(q, inner, 0, n, fp[0], fp[1], B, lk, H, scale=aw["q_scale"], dst_ld=3 * inner, dst_col0=0)
+        ops.mg_head_planes(kv, 2 * inner, 0, self.nc, fp[0], fp[1], B, lk, H, null_vec=aw["null_k"], scale=aw["k_scale"], dst_ld=3 * inner, dst_col0=inner)
+        ops.mg_head_planes(kv, 2 * inner, inner, self.nc, fp[0], fp[1], B, lk, H, null_vec=aw["null_v"], dst_ld=3 * inner, dst_col0=2 * inner)
+        op = self._planes((B * lk, inner))
+        ops.attn_fused_fwd(fp[0], fp[1], B, lk, H, inner, lk, self.bias_cross_tiled, None, None, self.scale, self.npass,
+                           algo_flops=4.0 * B * H * 64 * float(n) * (self.nc + 1), layout64=self.cross_tiles, out_hi=op[0], out_lo=op[1])
+        out = torch.empty((B * n, self.d), dtype=torch.float32, device=self.dev)
+        ops.gemm_tc(a_hi=op[0], a_lo=op[1], a_dims=(B, 1, lk, inner), b_hi=aw["wout"][0], b_lo=aw["wout"][1], k=inner, n_cols=self.d, out_w=n,
+                    z_outer=B, out_zo_stride=n * self.d, ldc=self.d, residual=residual, out_f32=out, bn=128, npass=self.npass)
+        return out
+
     def embed(self, ids, cond_ids, batch):
         """-> (x fp32 [B*n_img, d], context planes [B*nc, d])."""
         B = cond_ids.shape[0]
@@ -198,28 +240,46 @@ class MaskGitEngine:
         x, ctx = self.embed(ids, cond_ids, batch)
         for lw in self.layers:
             sa, ca, ff = lw["self"], lw["cross"], lw["ff"]
-            yp = self._ln_planes(x, sa["gamma"], rows)
+            yp = self._ln_planes(x, sa["gamma"], rows, f16f8=self.pair)
             qkv = torch.empty((rows, 3 * inner), dtype=torch.float32, device=self.dev)
-            self._linear(yp, sa["wqkv"], 3 * inner, rows, d, out_f32=qkv)
+            if self.pair:
+                self._pair_linear(yp, sa["wqkv_p"], 3 * inner, rows, d, out_f32=qkv)
+            else:
+                self._linear(yp, sa["wqkv"], 3 * inner, rows, d, out_f32=qkv)
             if self.fused_self:
                 x = self._attend_self_fused(qkv, sa, B, x)
             else:
                 x = self._attend(qkv, 3 * inner, 0, qkv, 3 * inner, inner, 2 * inner, n, self.lk_self, sa, self.bias_self, self.mask_self, B, x)
             del qkv
-            yp = self._ln_planes(x, ca["gamma"], rows)
+            yp = self._ln_planes(x, ca["gamma"], rows, f16f8=self.pair)
             q = torch.empty((rows, inner), dtype=torch.float32, device=self.dev)
-            self._linear(yp, ca["wq"], inner, rows, d, out_f32=q)
+            if self.pair:
+                self._pair_linear(yp, ca["wq_p"], inner, rows, d, out_f32=q)
+            else:
+                self._linear(yp, ca["wq"], inner, rows, d, out_f32=q)
             kv = torch.empty((B * self.nc, 2 * inner), dtype=torch.float32, device=self.dev)
             self._linear(ctx, ca["wkv"], 2 * inner, B * self.nc, d, out_f32=kv)
-            x = self._attend(q, inner, 0, kv, 2 * inner, 0, inner, self.nc, self.lk_cross, ca, self.bias_cross, self.mask_cross, B, x)
-            yp = self._ln_planes(x, ff["gamma0"], rows)
-            h = torch.empty((rows, 2 * self.f), dtype=torch.float32, device=self.dev)
-            self._linear(yp, ff["w1"], 2 * self.f, rows, d, out_f32=h)
-            gp = self._planes((rows, self.f_pad))
-            ops.mg_geglu_ln(h, ff["gamma3"], gp[0], gp[1], rows, self.f, self.f_pad)
-            del h
+            if self.fused_self:
+                x = self._attend_cross_fused(q, kv, ca, B, x)
+            else:
+                x = self._attend(q, inner, 0, kv, 2 * inner, 0, inner, self.nc, self.lk_cross, ca, self.bias_cross, self.mask_cross, B, x)
+            yp = self._ln_planes(x, ff["gamma0"], rows, f16f8=self.pair)
             x2 = torch.empty_like(x)
-            self._linear(gp, ff["w2"], d, rows, self.f_pad, residual=x, out_f32=x2)
+            if self.pair:
+                h = torch.empty((rows, self.n1_pad), dtype=torch.float32, device=self.dev)
+                self._pair_linear(yp, ff["w1_p"], self.n1_pad, rows, d, out_f32=h)
+                gp = (torch.empty((rows, self.f_pad), dtype=torch.float16, device=self.dev),
+                      torch.empty((rows, 2 * self.f_pad), dtype=torch.uint8, device=self.dev))
+                ops.mg_geglu_ln(h, ff["gamma3"], gp[0], gp[1], rows, self.f, self.f_pad, h_ld=self.n1_pad, f16f8=True)
+                del h
+                self._pair_linear(gp, ff["w2_p"], d, rows, self.f_pad, residual=x, out_f32=x2)
+            else:
+                h = torch.empty((rows, 2 * self.f), dtype=torch.float32, device=self.dev)
+                self._linear(yp, ff["w1"], 2 * self.f, rows, d, out_f32=h)
+                gp = self._planes((rows, self.f_pad))
+                ops.mg_geglu_ln(h, ff["gamma3"], gp[0], gp[1], rows, self.f, self.f_pad)
+                del h
+                self._linear(gp, ff["w2"], d, rows, self.f_pad, residual=x, out_f32=x2)
             x = x2
         emb = torch.empty_like(x)
         ep = self._ln_planes(x, self.gamma_f, rows, y=emb)

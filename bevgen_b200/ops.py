@@ -465,8 +465,9 @@ def mg_head_planes(src, src_ld, src_col0, n_src, out_hi, out_lo, batch, dst_rows
                                          0 if null_vec is None else 1, heads, _stream()), "mg_head_planes")
 
 
-def mg_geglu_ln(h, gamma, out_hi, out_lo, rows, f, f_pad, eps=1e-5):
+def mg_geglu_ln(h, gamma, out_hi, out_lo, rows, f, f_pad, eps=1e-5, h_ld=None, f16f8=False):
     lib = _lib.init()
     Stats.launches += 1
     _chk_cuda(h, gamma, out_hi, out_lo)
-    _lib.check(lib.bevgen_mg_geglu_ln(_ptr(h), _ptr(gamma), _ptr(out_hi), _ptr(out_lo), rows, f, f_pad, eps, _stream()), "mg_geglu_ln")
+    _lib.check(lib.bevgen_mg_geglu_ln(_ptr(h), 2 * f if h_ld is None else h_ld, _ptr(gamma), _ptr(out_hi), _ptr(out_lo), rows, f, f_pad, eps,
+                                      1 if f16f8 else 0, _stream()), "mg_geglu_ln")

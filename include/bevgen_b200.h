@@ -251,10 +251,11 @@ BEVGEN_API int bevgen_attn_fused_fwd(const void* qkv_hi, const void* qkv_lo, int
 BEVGEN_API int bevgen_mg_head_planes(const float* src, long long src_ld, int src_col0, int n_src, int src_batch_rows, const float* null_vec,
                                      const float* scale, void* out_hi, void* out_lo, int batch, int dst_rows, long long dst_ld, int dst_col0,
                                      int has_null, int heads, void* stream);
-/* FeedForward :72-88 between its Linear layers: u = h[:, f:2f] * gelu(h[:, 0:f]); planes = LayerNorm_f(u) * gamma (eps, biased variance),
- * bf16 hi / lo [rows][f_pad], columns f .. f_pad-1 zero.  f_pad <= 3072. */
-BEVGEN_API int bevgen_mg_geglu_ln(const float* h, const float* gamma, void* out_hi, void* out_lo, long long rows, int f, int f_pad, float eps,
-                                  void* stream);
+/* FeedForward :72-88 between its Linear layers: u = h[:, f:2f] * gelu(h[:, 0:f]) on rows of pitch h_ld; planes = LayerNorm_f(u) * gamma
+ * (eps, biased variance), bf16 hi / lo [rows][f_pad], columns f .. f_pad-1 zero, f_pad <= 3072.  f16f8 != 0: out_hi / out_lo are instead the
+ * scaled fp16 plane and the e4m3 pair plane of a following bevgen_linear_f16f8 (f_pad % 64 == 0). */
+BEVGEN_API int bevgen_mg_geglu_ln(const float* h, long long h_ld, const float* gamma, void* out_hi, void* out_lo, long long rows, int f, int f_pad,
+                                  float eps, int f16f8, void* stream);
 
 /* ---------------------------------------------------------------- KV-cache autoregressive decode
  * Replaces the per-token full forward of Net2NetTransformer.sample (modules/stage2/cond_transformer_multi_view.py:154-227)

@@ -54,7 +54,7 @@ class TransformerBlocks(nn.Module):
 
 class TransformerMultiView(nn.Module):
     def __init__(self, *, num_tokens, dim, seq_len, dim_out=None, self_cond=False, add_mask_id=False, cfg: Optional[GPTConfig] = None,
-                 precision="fp32x3", **kwargs):
+                 precision="f16f8", **kwargs):
         super().__init__()
         if self_cond:
             raise NotImplementedError("self-conditioning is off in the reference's config (muse_stage_two_multi_view.yaml) and not built")

@@ -23,16 +23,17 @@ def _case(B=1, precision="fp32x3"):
     return cfg, sd_all, cam, bev, batch, eng
 
 
-def test_forward_vs_reference_golden(golden_dir):
+@pytest.mark.parametrize("precision", ["fp32x3", "f16f8"])
+def test_forward_vs_reference_golden(precision, golden_dir):
     g = np.load(golden_dir / "maskgit_small.npz")
-    cfg, sd, cam, bev, batch, eng = _case()
+    cfg, sd, cam, bev, batch, eng = _case(precision=precision)
     ids = torch.from_numpy(g["ids"]).long()
     logits, emb = eng.forward(ids.cuda(), bev.cuda(), batch)
     torch.cuda.synchronize()
     cols = g["cols"]
     e_l = (logits[:, cols].cpu() - torch.from_numpy(g["logits"])).abs().max().item()
     e_e = (emb[:, cols].cpu() - torch.from_numpy(g["embed"])).abs().max().item()
-    print(f"[maskgit small] logits err {e_l:.2e} (absmax {float(g['logits_absmax']):.2f}), embed err {e_e:.2e}")
+    print(f"[maskgit small {precision}] logits err {e_l:.2e} (absmax {float(g['logits_absmax']):.2f}), embed err {e_e:.2e}")
     assert torch.isfinite(logits).all()
     assert e_l < LOGIT_TOL and e_e < LOGIT_TOL
     assert abs(logits.double().mean().item() - float(g["logits_mean"])) < 1e-4

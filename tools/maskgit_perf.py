@@ -11,7 +11,7 @@ from oracle import synth
 from tests.cases import GPT_KW, gpt_sizes
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 2
-prec = sys.argv[2] if len(sys.argv) > 2 else "fp32x3"
+prec = sys.argv[2] if len(sys.argv) > 2 else "f16f8"
 kw = {**GPT_KW, "num_layers": 14, "sparse_block_size": 1, "cam_latent_res": (14, 25), "cam_res": (224, 400)}
 cfg = GPTConfig(**kw)
 sd = synth.maskgit_state_dict(gpt_sizes(cfg), 14, 16, seed=1)

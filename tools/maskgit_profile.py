@@ -13,7 +13,7 @@ kw = {**GPT_KW, "num_layers": 14, "sparse_block_size": 1, "cam_latent_res": (14,
 cfg = GPTConfig(**kw)
 sd = synth.maskgit_state_dict(gpt_sizes(cfg), 14, 16, seed=1)
 critic = {"weight": sd.pop("to_pred.weight"), "bias": sd.pop("to_pred.bias")}
-eng = MaskGitEngine(sd, cfg, depth=14, heads=16, device="cuda:0", critic=critic)
+eng = MaskGitEngine(sd, cfg, depth=14, heads=16, device="cuda:0", critic=critic, precision=sys.argv[2] if len(sys.argv) > 2 else "f16f8")
 cam, bev, batch = synth.stage2_inputs(B, cfg.num_cams, cfg.num_cam_tokens, cfg.num_cond_tokens, cfg.vocab_size, cfg.cond_vocab_size, seed=0)
 ids, bev = cam.reshape(B * cfg.num_cams, -1).cuda(), bev.cuda()
 batch = {k: v.cuda() for k, v in batch.items()}
