@@ -309,6 +309,12 @@ def main():
                         "decode = bf16x3 weights, fp16 KV cache"}
         except Exception as ex:  # the headline line must still be printed
             line["stage2"] = {"error": repr(ex)}
+        try:   # the MaskGit variant's generate at the reference config's size (reported beside the headline)
+            torch.cuda.empty_cache()
+            from tools.maskgit_perf import run as maskgit_run
+            line["maskgit"] = maskgit_run(8, args.precision)
+        except Exception as ex:
+            line["maskgit"] = {"error": repr(ex)}
     if world == 1 and not args.no_cpu_baseline:
         rate, cores, sec = cpu_reference_rate(8)
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
