@@ -117,22 +117,22 @@ class MaskGitEngine:
         self.bias_cross, self.mask_cross = table(None if bias is None else bias[self.nc:, : self.nc], self.nc, self.lk_cross)
         # self-attention on the fused flash-style kernel: q | k | v share one plane of lk_self rows per scene (query i at row i, null key at
         # row 0, key j at row j + 1), dense support (n_cond = seq_len), padding keys switched off by -inf entries of the tiled bias table
-        self.fused_self = self.lk_self <= 4096
+        self.lk_f = max(self.lk_self, self.lk_cross)          # rows per scene of the fused kernel's shared q | k | v plane
+        self.fused_self = self.lk_f <= 4096
         if self.fused_self:
-            full = torch.zeros(self.lk_self, self.lk_self, device=dev)
-            full[: self.n_img] = self.bias_self
-            full[:, self.n_img + 1:] = float("-inf")
-            self.bias_self_tiled = ops.tile_attention_bias(full, self.scale)
-            # cross-attention on the same kernel and geometry: the context keys (null + n_cond, padded to lk_cross) occupy the first
-            # key tiles, the layout table (SURVEY 8f-2 mechanism) makes every role skip the remaining ones
-            full = torch.zeros(self.lk_self, self.lk_self, device=dev)
-            full[: self.n_img, : self.lk_cross] = self.bias_cross
-            full[:, self.nc + 1:] = float("-inf")
-            self.bias_cross_tiled = ops.tile_attention_bias(full, self.scale)
-            nt = self.lk_self // 128
-            t = torch.zeros(self.H, nt, nt, dtype=torch.int64, device=dev)
-            t[:, :, : self.lk_cross // 128] = -1
-            self.cross_tiles = t.contiguous()
+            nt = self.lk_f // 128
+
+            def fused_tables(tab, n_keys, lk):
+                full = torch.zeros(self.lk_f, self.lk_f, device=dev)
+                full[: self.n_img, :lk] = tab
+                full[:, n_keys + 1:] = float("-inf")
+                t = torch.zeros(self.H, nt, nt, dtype=torch.int64, device=dev)
+                t[:, :, : lk // 128] = -1
+                return ops.tile_attention_bias(full, self.scale), (None if lk == self.lk_f else t.contiguous())
+            self.bias_self_tiled, self.self_tiles = fused_tables(self.bias_self, self.n_img, self.lk_self)
+            # cross-attention on the same kernel and geometry: the context keys (null + n_cond, padded to lk_cross) occupy the first key
+            # tiles, the layout table (SURVEY 8f-2 mechanism) makes every role skip the remaining ones
+            self.bias_cross_tiled, self.cross_tiles = fused_tables(self.bias_cross, self.nc, self.lk_cross)
 
     # ------------------------------------------------------------------ helpers
     def _planes(self, shape):
@@ -181,14 +181,14 @@ class MaskGitEngine:
 
     def _attend_self_fused(self, qkv, aw, B, residual):
         """Self-attention through bevgen_attn_fused_fwd (no score matrix in HBM): operand planes [B][lk][3*inner], output planes -> to_out."""
-        n, H, inner, lk = self.n_img, self.H, self.inner, self.lk_self
+        n, H, inner, lk = self.n_img, self.H, self.inner, self.lk_f
         fp = self._planes((B * lk, 3 * inner))
         ops.mg_head_planes(qkv, 3 * inner, 0, n, fp[0], fp[1], B, lk, H, scale=aw["q_scale"], dst_ld=3 * inner, dst_col0=0)
         ops.mg_head_planes(qkv, 3 * inner, inner, n, fp[0], fp[1], B, lk, H, null_vec=aw["null_k"], scale=aw["k_scale"], dst_ld=3 * inner, dst_col0=inner)
         ops.mg_head_planes(qkv, 3 * inner, 2 * inner, n, fp[0], fp[1], B, lk, H, null_vec=aw["null_v"], dst_ld=3 * inner, dst_col0=2 * inner)
         op = self._planes((B * lk, inner))
         ops.attn_fused_fwd(fp[0], fp[1], B, lk, H, inner, lk, self.bias_self_tiled, None, None, self.scale, self.npass,
-                           algo_flops=4.0 * B * H * 64 * float(n) * (n + 1), out_hi=op[0], out_lo=op[1])
+                           algo_flops=4.0 * B * H * 64 * float(n) * (n + 1), layout64=self.self_tiles, out_hi=op[0], out_lo=op[1])
         out = torch.empty((B * n, self.d), dtype=torch.float32, device=self.dev)
         # rows n .. lk-1 of every scene are padding queries: the GEMM reads the [B][lk] plane and stores the first n rows of each scene
         ops.gemm_tc(a_hi=op[0], a_lo=op[1], a_dims=(B, 1, lk, inner), b_hi=aw["wout"][0], b_lo=aw["wout"][1], k=inner, n_cols=self.d, out_w=n,
@@ -196,7 +196,7 @@ class MaskGitEngine:
         return out
 
     def _attend_cross_fused(self, q, kv, aw, B, residual):
-        n, H, inner, lk = self.n_img, self.H, self.inner, self.lk_self
+        n, H, inner, lk = self.n_img, self.H, self.inner, self.lk_f
         fp = self._planes((B * lk, 3 * inner))
         ops.mg_head_planes(q, inner, 0, n, fp[0], fp[1], B, lk, H, scale=aw["q_scale"], dst_ld=3 * inner, dst_col0=0)
         ops.mg_head_planes(kv, 2 * inner, 0, self.nc, fp[0], fp[1], B, lk, H, null_vec=aw["null_k"], scale=aw["k_scale"], dst_ld=3 * inner, dst_col0=inner)

@@ -120,3 +120,30 @@ def test_module_under_the_reference_import_path(golden_dir):
     init[2] = cam.reshape(cfg.num_cams, -1)[2].cuda()
     c = mg.generate(init_ids=init, cond_images=bev.cuda(), fmap_size=tuple(cfg.cam_latent_res), batch=batch, timesteps=4)
     assert torch.equal(c.reshape(cfg.num_cams, -1)[2], init[2])
+
+
+@pytest.mark.parametrize("precision", ["fp32x3", "f16f8"])
+def test_small_rig_with_fewer_image_than_context_tokens(precision):
+    """3 cameras x 7x9 latents (189 image tokens, 256 context tokens, sparse_block_size 1 as in the reference's MaskGit config): the shared
+    q | k | v plane is sized by the cross-attention keys, self-attention skips the key tiles beyond its own; checked against the oracle."""
+    from bevgen_b200.maskgit_engine import MaskGitEngine
+    kw = {**GPT_SMALL, "num_cams": 3, "cam_names": "NUSCENES_ABLATION_CAMERAS", "cam_latent_res": (7, 9), "cam_res": (112, 144), "sparse_block_size": 1}
+    cfg = GPTConfig(**kw)
+    assert cfg.num_pad_tokens == 0
+    sd = synth.maskgit_state_dict(gpt_sizes(cfg), 2, cfg.num_heads, seed=8)
+    critic = {"weight": sd.pop("to_pred.weight"), "bias": sd.pop("to_pred.bias")}
+    B = 2
+    cam, bev, batch = synth.stage2_inputs(B, cfg.num_cams, cfg.num_cam_tokens, cfg.num_cond_tokens, cfg.vocab_size, cfg.cond_vocab_size, seed=2)
+    ids = cam.reshape(B * cfg.num_cams, cfg.num_cam_tokens).clone()
+    ids[:, ::3] = cfg.vocab_size
+    eng = MaskGitEngine(sd, cfg, depth=2, heads=cfg.num_heads, device="cuda:0", precision=precision, critic=critic)
+    assert eng.lk_f == 384 and eng.lk_self == 256 and eng.self_tiles is not None
+    with torch.no_grad():
+        want_l, want_e = maskgit_oracle.forward(sd, gpt_oracle.geo_from_config(cfg), ids, bev, batch, 2, cfg.num_heads)
+    logits, emb = eng.forward(ids.cuda(), bev.cuda(), batch)
+    torch.cuda.synchronize()
+    assert (logits.cpu() - want_l).abs().max().item() < LOGIT_TOL
+    assert (emb.cpu() - want_e).abs().max().item() < LOGIT_TOL
+    eng.fused_self = False                        # composed Q.K^T -> softmax -> P.V path agrees
+    l2, _ = eng.forward(ids.cuda(), bev.cuda(), batch)
+    assert (l2 - logits).abs().max().item() < 2e-4
