@@ -173,25 +173,26 @@ def main():
         quant, _, (_, _, idx) = model.encode(x_dev, None)
         return model.decode(quant), idx
 
-    def step_e2e():
-        xd = x_host.to(dev, non_blocking=True)
-        quant, _, (_, _, idx) = model.encode(xd, None)
-        rec = model.decode(quant)
-        rec_host.copy_(rec, non_blocking=True)
-        idx_host.copy_(idx, non_blocking=True)
+    from bevgen_b200.host_pipeline import RoundTripPipeline
+    pipe = RoundTripPipeline(model, dev, x_host)
+
+    def step_e2e():     # every step uploads its pinned input and downloads its result; the copies ride on side streams (host_pipeline.py)
+        pipe.submit(x_host, rec_host, idx_host, next_x_host=x_host)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, steps, finalize=None):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         w0 = time.time()
         e0.record()
         for _ in range(steps):
             fn()
+        if finalize is not None:
+            finalize()          # the timed stream waits for the last result copy
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -220,7 +221,8 @@ def main():
         return
     for _ in range(2):
         step_e2e()
-    ms_e2e, _, _ = timed(step_e2e, args.steps)
+    pipe.drain()
+    ms_e2e, _, _ = timed(step_e2e, args.steps, finalize=pipe.drain)
     e2e_value = world * n_img * args.steps / (ms_e2e / 1e3)
 
     # ---- per-launch CUDA-event timing of the dominant kernel (tcgen05 implicit GEMM), on the launching stream

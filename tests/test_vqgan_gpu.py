@@ -75,3 +75,32 @@ def test_decode_nchw_roundtrip_helpers():
     assert torch.equal(eng.nchw_to_nhwc(q_nchw), zq)
     want = vqgan_oracle.get_codebook_entry(idx.cpu(), (n, H // 16, W // 16, 256), sd)
     assert torch.equal(q_nchw.cpu(), want)
+
+
+@pytest.mark.gpu
+def test_host_round_trip_pipeline_matches_direct_calls():
+    """bevgen_b200.host_pipeline.RoundTripPipeline (uploads / downloads on side streams, two input slots) returns, for a sequence of
+    different pinned batches, exactly what encode -> decode on a resident copy of each batch returns."""
+    from bevgen_b200.host_pipeline import RoundTripPipeline
+    from multi_view_generation.modules.stage1.vqgan import VQModel
+
+    class _NoLoss(torch.nn.Module):
+        def forward(self, *a, **k):
+            raise RuntimeError("training loss is out of scope")
+    dd = synth.vqgan_ddconfig(in_channels=3, ch=64, resolution=64)
+    model = VQModel(dd, _NoLoss(), 1024, 256, (64, 64), (4, 4), 16, precision="f16f8")
+    model.load_state_dict(synth.vqgan_state_dict(dd, seed=1))
+    model = model.cuda().eval()
+    xs = [synth.image_batch(4, 3, 64, 64, seed=s).pin_memory() for s in range(4)]
+    recs = [torch.empty(4, 3, 64, 64).pin_memory() for _ in xs]
+    idxs = [torch.empty(4 * 16, dtype=torch.int64).pin_memory() for _ in xs]
+    pipe = RoundTripPipeline(model, "cuda:0", xs[0])
+    for i, x in enumerate(xs):
+        pipe.submit(x, recs[i], idxs[i], next_x_host=xs[i + 1] if i + 1 < len(xs) else None)
+    pipe.drain()
+    torch.cuda.synchronize()
+    for i, x in enumerate(xs):
+        quant, _, (_, _, idx) = model.encode(x.cuda(), None)
+        rec = model.decode(quant)
+        assert torch.equal(idx.cpu().reshape(-1), idxs[i])
+        assert torch.equal(rec.cpu(), recs[i])
