@@ -147,3 +147,39 @@ def test_small_rig_with_fewer_image_than_context_tokens(precision):
     eng.fused_self = False                        # composed Q.K^T -> softmax -> P.V path agrees
     l2, _ = eng.forward(ids.cuda(), bev.cuda(), batch)
     assert (l2 - logits).abs().max().item() < 2e-4
+
+
+def test_net2net_muse_wrapper_generates_images():
+    """cond_transformer_multi_view_muse.Net2NetTransformer (reference :28-286): sample / log_images with both VQGANs and the MaskGit decoder
+    under the reference's import paths; the given camera of a partial decoding keeps its ground-truth tokens."""
+    from multi_view_generation.modules.losses.vqperceptual import DummyLoss
+    from multi_view_generation.modules.stage1.vqgan import VQModel, VQSegmentationModel
+    from multi_view_generation.modules.stage2 import muse_maskgit_pytorch as m
+    from multi_view_generation.modules.stage2.cond_transformer_multi_view_muse import Net2NetTransformer
+    cfg = GPTConfig(**{**GPT_SMALL, "vocab_size": 1024, "cond_vocab_size": 1024})
+    tr = m.MaskGitTransformerMultiView(num_tokens=cfg.vocab_size, dim=cfg.num_embed, seq_len=tuple(cfg.cam_latent_res), depth=2, dim_head=64,
+                                       heads=cfg.num_heads, ff_mult=4, cfg=cfg)
+    mg = m.MaskGit(image_size=tuple(cfg.cam_latent_res), transformer=tr, self_token_critic=True)
+    sd = synth.maskgit_state_dict(gpt_sizes(cfg), 2, cfg.num_heads, seed=3)
+    mg.token_critic.to_pred.load_state_dict({"weight": sd.pop("to_pred.weight"), "bias": sd.pop("to_pred.bias")})
+    tr.load_state_dict(sd, strict=False)
+    dd, ddb = synth.vqgan_ddconfig(ch=64), synth.vqgan_ddconfig(ch=64, in_channels=7)
+    fs = VQModel(dd, DummyLoss(), 1024, 256, (256, 256), (16, 16), 256)
+    fs.load_state_dict(synth.vqgan_state_dict(dd, seed=1))
+    cs = VQSegmentationModel(7, ddb, DummyLoss(), 1024, 256, (256, 256), (16, 16), 256)
+    cs.load_state_dict(synth.vqgan_state_dict(ddb, seed=5), strict=False)
+    model = Net2NetTransformer(mg, fs, cs, cfg, sample_iterations=4).cuda().eval()
+    mg.sample_seed = 3
+    g = torch.Generator().manual_seed(0)
+    batch = {"image": torch.randn(1, 6, 256, 256, 3, generator=g), "segmentation": (torch.rand(1, 256, 256, 7, generator=g) > 0.5).float(),
+             "intrinsics_inv": torch.randn(1, 6, 3, 3, generator=g), "extrinsics_inv": torch.randn(1, 6, 4, 4, generator=g)}
+    out = model.test_step(batch, 0)
+    for k in ("gen", "rec", "gt"):
+        assert out[k].shape == (1, 6, 3, 256, 256)
+        assert float(out[k].min()) >= 0.0 and float(out[k].max()) <= 1.0
+    x, c = model.get_xc(batch)
+    _, c_idx = model.encode_to_c(c.cuda(), batch)
+    _, z_idx = model.encode_to_z(x.cuda(), batch)
+    ids = model.sample(c_idx, batch, partial_decoding_idx=[1, 4])
+    assert ids.shape == (6, 16, 16) and int(ids.max()) < 1024
+    assert torch.equal(ids.reshape(6, -1)[[1, 4]], z_idx.reshape(6, -1)[[1, 4]])
