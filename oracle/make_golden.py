@@ -206,6 +206,9 @@ def golden_maskgit():
                         logits_mean=np.float64(logits.double().mean().item()), generated=gen.numpy().astype(np.int32),
                         gen_seed=np.int64(1234), gen_steps=np.int64(6))
     print("maskgit", tuple(logits.shape), float(logits.abs().max()), "generated", tuple(gen.shape), int(gen.max()))
+    import json
+    json.dump({k: list(v.shape) for k, v in model.state_dict().items()}, open(OUT / "maskgit_small_state_dict_keys.json", "w"), indent=0,
+              sort_keys=True)       # checkpoint-compatibility fixture: keys + shapes of MaskGit(...).state_dict()
 
 
 def golden_topk():

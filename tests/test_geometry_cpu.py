@@ -71,3 +71,20 @@ def test_layout_bit_table_for_fused_attention(block):
     got = ((e >> bit) & 1).bool()
     assert torch.equal(got, want)
     assert torch.equal(table == 0, ~want.reshape(H, L // 128, 128, L // 128, 128).any(4).any(2))  # zero entry <=> tile skipped
+
+
+def test_maskgit_module_state_dict_matches_the_reference():
+    """Checkpoint compatibility of the MaskGit variant: `MaskGit(...).state_dict()` of the drop-in modules has exactly the keys and shapes
+    of the reference's (minted from the unmodified muse_maskgit_pytorch.py with the same constructor arguments; includes the SelfCritic
+    head, which the reference registers both as `token_critic.net.*` and `transformer.*`)."""
+    import json
+    from pathlib import Path
+    from multi_view_generation.modules.stage2 import muse_maskgit_pytorch as m
+    from tests.cases import GPT_SMALL
+    want = json.load(open(Path(__file__).parent / "golden" / "maskgit_small_state_dict_keys.json"))
+    cfg = GPTConfig(**GPT_SMALL)
+    tr = m.MaskGitTransformerMultiView(num_tokens=cfg.vocab_size, dim=cfg.num_embed, seq_len=tuple(cfg.cam_latent_res), depth=2, dim_head=64,
+                                       heads=cfg.num_heads, ff_mult=4, cfg=cfg)
+    model = m.MaskGit(image_size=tuple(cfg.cam_latent_res), transformer=tr, self_token_critic=True)
+    got = {k: list(v.shape) for k, v in model.state_dict().items()}
+    assert got == want, (sorted(set(want) - set(got))[:5], sorted(set(got) - set(want))[:5])
