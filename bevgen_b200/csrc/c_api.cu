@@ -422,6 +422,13 @@ BEVGEN_API int bevgen_attn_fused_fwd(const void* qkv_hi, const void* qkv_lo, int
                                  layout64, (uint16_t*)out_hi, (uint16_t*)out_lo, (cudaStream_t)stream), "attn_fused_fwd");
 }
 
+BEVGEN_API int bevgen_ray_embed_add(float* h_nhwc, const float* intrinsics_inv, const float* extrinsics_inv, const float* pixel, const float* img_embed_w,
+                                    const float* cam_embed_w, int n_images, int hw, int d, void* stream) {
+  if (!h_nhwc || !intrinsics_inv || !extrinsics_inv || !pixel || !img_embed_w || !cam_embed_w) return fail(BEVGEN_ERR_ARG, "ray_embed_add: null argument");
+  CHECK_LAUNCH(launch_ray_embed_add(h_nhwc, intrinsics_inv, extrinsics_inv, pixel, img_embed_w, cam_embed_w, n_images, hw, d, (cudaStream_t)stream),
+               "ray_embed_add");
+}
+
 /* ---------------------------------------------------------------- MaskGit variant */
 BEVGEN_API int bevgen_mg_head_planes(const float* src, long long src_ld, int src_col0, int n_src, int src_batch_rows, const float* null_vec,
                                      const float* scale, void* out_hi, void* out_lo, int batch, int dst_rows, long long dst_ld, int dst_col0,

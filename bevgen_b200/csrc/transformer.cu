@@ -162,6 +162,52 @@ __global__ void __launch_bounds__(128) embed_kernel(const EmbedParams p) {
   for (int c = tid; c < p.d; c += 128, ++n) out[c] = (e[c] + g[n] * inv) + pos[c];
 }
 
+// ------------------------------------------------------------------------------------------------
+// Stage-1 geometric embedding (VQModel.encode with geometric_embedding=True, modules/stage1/vqgan.py:87-109): the encoder output of
+// image n = (scene, camera) gets, per latent pixel, the L2-normalised  img_embed(E_inv (I_inv pixel ; 1)) - cam_embed(E_inv[:, 3])
+// added in place (h is NHWC fp32).  One CTA (128 threads) per (image, pixel); same arithmetic as the image rows of embed_kernel.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) ray_embed_add_kernel(float* __restrict__ h, const float* __restrict__ I_inv, const float* __restrict__ E_inv,
+                                                            const float* __restrict__ pixel, const float* __restrict__ img_w,
+                                                            const float* __restrict__ cam_w, int hw, int d) {
+  __shared__ float red[4];
+  const int px = blockIdx.x, n = blockIdx.y, tid = threadIdx.x;
+  float* out = h + ((size_t)n * hw + px) * d;
+  const float* I = I_inv + (size_t)n * 9;
+  const float* E = E_inv + (size_t)n * 16;
+  const float* pix = pixel + (size_t)px * 3;
+  float cv[4], ray[4];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) cv[r] = I[r * 3 + 0] * pix[0] + I[r * 3 + 1] * pix[1] + I[r * 3 + 2] * pix[2];
+  cv[3] = 1.0f;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) ray[r] = E[r * 4 + 0] * cv[0] + E[r * 4 + 1] * cv[1] + E[r * 4 + 2] * cv[2] + E[r * 4 + 3] * cv[3];
+  float g[8];
+  float ss = 0.f;
+  int k = 0;
+  for (int c = tid; c < d; c += 128, ++k) {
+    const float4 wi = __ldg(reinterpret_cast<const float4*>(img_w) + c);
+    const float4 wc = __ldg(reinterpret_cast<const float4*>(cam_w) + c);
+    const float de = wi.x * ray[0] + wi.y * ray[1] + wi.z * ray[2] + wi.w * ray[3];
+    const float ce = wc.x * E[3] + wc.y * E[7] + wc.z * E[11] + wc.w * E[15];
+    g[k] = de - ce;
+    ss += g[k] * g[k];
+  }
+  for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if ((tid & 31) == 0) red[tid >> 5] = ss;
+  __syncthreads();
+  const float inv = 1.0f / (sqrtf(red[0] + red[1] + red[2] + red[3]) + 1e-7f);
+  k = 0;
+  for (int c = tid; c < d; c += 128, ++k) out[c] += g[k] * inv;
+}
+
+int launch_ray_embed_add(float* h, const float* I_inv, const float* E_inv, const float* pixel, const float* img_w, const float* cam_w, int n_images,
+                         int hw, int d, cudaStream_t st) {
+  if (d < 1 || d > 1024 || n_images < 1 || n_images > 65535 || hw < 1) return BEVGEN_ERR_ARG;
+  ray_embed_add_kernel<<<dim3(hw, n_images), 128, 0, st>>>(h, I_inv, E_inv, pixel, img_w, cam_w, hw, d);
+  return cudaGetLastError() == cudaSuccess ? BEVGEN_OK : BEVGEN_ERR_CUDA;
+}
+
 int launch_embed(const EmbedParams& p, cudaStream_t st) {
   if (p.d % 4 != 0 || p.d > 1024 || p.nrows < 1 || p.B < 1 || p.B > 65535) return BEVGEN_ERR_ARG;
   if (launch_k(embed_kernel, dim3(p.nrows, p.B), dim3(128), 0, st, p) != cudaSuccess) return BEVGEN_ERR_CUDA;

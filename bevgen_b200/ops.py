@@ -471,3 +471,15 @@ def mg_geglu_ln(h, gamma, out_hi, out_lo, rows, f, f_pad, eps=1e-5, h_ld=None, f
     _chk_cuda(h, gamma, out_hi, out_lo)
     _lib.check(lib.bevgen_mg_geglu_ln(_ptr(h), 2 * f if h_ld is None else h_ld, _ptr(gamma), _ptr(out_hi), _ptr(out_lo), rows, f, f_pad, eps,
                                       1 if f16f8 else 0, _stream()), "mg_geglu_ln")
+
+
+def ray_embed_add(h_nhwc, intrinsics_inv, extrinsics_inv, pixel, img_w, cam_w):
+    """Stage-1 geometric embedding added in place to the NHWC encoder output (bevgen_ray_embed_add)."""
+    lib = _lib.init()
+    Stats.launches += 1
+    _chk_cuda(h_nhwc, intrinsics_inv, extrinsics_inv, pixel, img_w, cam_w)
+    n, hh, ww, d = h_nhwc.shape
+    if intrinsics_inv.numel() != n * 9 or extrinsics_inv.numel() != n * 16 or pixel.numel() != hh * ww * 3:
+        raise ValueError("ray_embed_add: camera matrices / pixel plane do not match the latent shape")
+    _lib.check(lib.bevgen_ray_embed_add(_ptr(h_nhwc), _ptr(intrinsics_inv), _ptr(extrinsics_inv), _ptr(pixel), _ptr(img_w), _ptr(cam_w), n, hh * ww, d,
+                                        _stream()), "ray_embed_add")

@@ -339,9 +339,26 @@ class VQGANEngine:
 
     # ------------------------------------------------------------------ VQModel-level entry points
     @torch.no_grad()
-    def encode(self, x_nchw):
-        """VQModel.encode -> (zq NHWC fp32 (N,h,w,e), idx int64 (N*h*w,), pre-quant h NHWC)."""
-        h = self.conv1x1(self.encoder(x_nchw), "quant_conv")
+    def encode(self, x_nchw, batch=None, cam_res=None):
+        """VQModel.encode -> (zq NHWC fp32 (N,h,w,e), idx int64 (N*h*w,), pre-quant h NHWC).  With `img_embed.weight` among the weights
+        (geometric_embedding=True, vqgan.py:87-109) `batch` must carry intrinsics_inv / extrinsics_inv ([b, cam, 3, 3] / [b, cam, 4, 4]) and
+        cam_res = (image height, image width): the ray embedding is added to the encoder output before quant_conv."""
+        henc = self.encoder(x_nchw)
+        if "img_embed.weight" in self.sd:
+            if batch is None or cam_res is None:
+                raise ValueError("this VQGAN was built with geometric_embedding=True: encode needs the batch's camera matrices and cam_res")
+            n, hh, ww, d = henc.shape
+            key = ("ray_pixel", hh, ww, tuple(cam_res))
+            if key not in self.w:
+                xs, ys = torch.linspace(0, 1, ww), torch.linspace(0, 1, hh)
+                gx, gy = torch.meshgrid((xs, ys), indexing="xy")
+                self.w[key] = torch.stack([gx * cam_res[1], gy * cam_res[0], torch.ones_like(gx)], -1).reshape(hh * ww, 3).to(self.dev).contiguous()
+                self.w["ray_img_w"] = self.sd["img_embed.weight"].to(self.dev, torch.float32).reshape(d, 4).contiguous()
+                self.w["ray_cam_w"] = self.sd["cam_embed.weight"].to(self.dev, torch.float32).reshape(d, 4).contiguous()
+            I_inv = batch["intrinsics_inv"].to(self.dev, torch.float32).reshape(-1, 3, 3).contiguous()
+            E_inv = batch["extrinsics_inv"].to(self.dev, torch.float32).reshape(-1, 4, 4).contiguous()
+            ops.ray_embed_add(henc, I_inv, E_inv, self.w[key], self.w["ray_img_w"], self.w["ray_cam_w"])
+        h = self.conv1x1(henc, "quant_conv")
         n, hh, ww, e = h.shape
         rows = n * hh * ww
         idx = torch.empty(rows, dtype=torch.int64, device=self.dev)

@@ -240,6 +240,13 @@ BEVGEN_API int bevgen_attn_fused_fwd(const void* qkv_hi, const void* qkv_lo, int
  * a following bevgen_gemm_tc: MaskGit's to_out Linear).  n_cond == seq_len gives dense (bidirectional) attention: MaskGit self-attention
  * runs it with the null key as key 0 and -inf bias entries on the padding keys. */
 
+/* Stage-1 geometric embedding (VQModel.encode with geometric_embedding=True, modules/stage1/vqgan.py:87-109; the default of
+ * configs/model/stage_1_cam.yaml): h_nhwc [n_images][hw][d] fp32 += normalize(img_embed(E_inv (I_inv pixel ; 1)) - cam_embed(E_inv[:, 3])) per
+ * image (= scene x camera; intrinsics_inv [n_images][3][3], extrinsics_inv [n_images][4][4]) and latent pixel (pixel [hw][3] =
+ * (x * image_width, y * image_height, 1)); img_embed_w / cam_embed_w are the [d][4] weights of the two bias-free 1x1 convs.  d <= 1024. */
+BEVGEN_API int bevgen_ray_embed_add(float* h_nhwc, const float* intrinsics_inv, const float* extrinsics_inv, const float* pixel, const float* img_embed_w,
+                                    const float* cam_embed_w, int n_images, int hw, int d, void* stream);
+
 /* ---------------------------------------------------------------- MaskGit stage-2 variant
  * The bidirectional decoder of modules/stage2/muse_maskgit_pytorch.py runs its Linear layers and the Q.K^T / P.V products on
  * bevgen_gemm_tc, LayerNorm on bevgen_layernorm, the biased softmax on bevgen_attn_softmax; these two produce the operand planes between. */

@@ -23,15 +23,24 @@ class VQModel(_Base):
                  ckpt_path=None, ignore_keys=[], image_key="image", colorize_nlabels=None, monitor=None, remap=None,
                  sane_index_shape=False, denormalize=True, legacy=True, precision="f16f8", **kwargs):
         super().__init__()
-        if geometric_embedding:
-            raise NotImplementedError("geometric_embedding=True (stage-1 ray embedding) is a 'next' row (SURVEY §8f-4)")
         self.image_key, self.denormalize = image_key, denormalize
+        self.cam_res = tuple(cam_res)
         self.ddconfig = dict(ddconfig)
         self.encoder = Encoder(**ddconfig)
         self.decoder = Decoder(**ddconfig)
         self.loss = lossconfig
         self.geometric_embedding = geometric_embedding
         self.n_embed, self.embed_dim = n_embed, embed_dim
+        if geometric_embedding:      # reference :62-69: ray / camera-centre embeddings added to the encoder output
+            if cam_emd_dim != ddconfig["z_channels"]:
+                raise ValueError("geometric_embedding adds a cam_emd_dim-channel embedding to the z_channels-channel encoder output")
+            fh, fw = cam_latent_res
+            xs, ys = torch.linspace(0, 1, fw), torch.linspace(0, 1, fh)
+            gx, gy = torch.meshgrid((xs, ys), indexing="xy")
+            plane = torch.stack([gx * cam_res[1], gy * cam_res[0], torch.ones_like(gx)], 0)[None, None]          # 1 1 3 h w
+            self.register_buffer("image_plane", plane.contiguous(), persistent=False)
+            self.img_embed = nn.Conv2d(4, cam_emd_dim, 1, bias=False)
+            self.cam_embed = nn.Conv2d(4, cam_emd_dim, 1, bias=False)
         self.quantize = VectorQuantizer(n_embed, embed_dim, beta=0.25, remap=remap, sane_index_shape=sane_index_shape, legacy=legacy)
         self.quant_conv = nn.Conv2d(ddconfig["z_channels"], embed_dim, 1)
         self.post_quant_conv = nn.Conv2d(embed_dim, ddconfig["z_channels"], 1)
@@ -62,7 +71,7 @@ class VQModel(_Base):
     @torch.no_grad()
     def encode(self, x, batch=None):
         eng = self.engine()
-        zq, idx, h = eng.encode(x)
+        zq, idx, h = eng.encode(x, batch, self.cam_res) if self.geometric_embedding else eng.encode(x)
         mse = torch.mean((zq - h) ** 2)
         emb_loss = mse + self.quantize.beta * mse          # value of quantize.py:290-295 (legacy and non-legacy coincide at inference)
         if self.quantize.sane_index_shape:

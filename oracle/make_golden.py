@@ -117,6 +117,39 @@ def golden_vqgan():
         print("vqgan", name, tuple(rec.shape), "min top-2 gap", (top2[:, 1] - top2[:, 0]).min().item())
 
 
+def golden_vqgan_geometric():
+    """VQModel(geometric_embedding=True).encode / decode (vqgan.py:62-69,84-121; the default of configs/model/stage_1_cam.yaml) run through
+    the reference's own LightningModule class on 2 scenes x 3 cameras of 64x64 pixels."""
+    rv = ref_import.vqgan()
+    dd = synth.vqgan_ddconfig(in_channels=3, ch=64, resolution=64)
+    sd = synth.vqgan_state_dict(dd, seed=4, geometric=True)
+    model = rv.VQModel(dd, None, 1024, 256, (64, 64), (4, 4), 256, geometric_embedding=True).eval()
+    missing, unexpected = model.load_state_dict(sd, strict=True)
+    g = torch.Generator().manual_seed(21)
+    x = synth.image_batch(6, 3, 64, 64, seed=9)
+    batch = {"intrinsics_inv": torch.randn(2, 3, 3, 3, generator=g) * 0.01, "extrinsics_inv": torch.randn(2, 3, 4, 4, generator=g)}
+    pre = []
+    hook = model.quant_conv.register_forward_hook(lambda mod, i, o: pre.append(o.detach()))
+    with torch.no_grad():
+        quant, _, (_, _, idx) = model.encode(x.clone(), batch)
+        rec = model.decode(quant)
+        plain, _, (_, _, idx_plain) = rv.VQModel.encode(_NoGeo(model), x.clone(), batch)
+    hook.remove()
+    assert not torch.equal(idx, idx_plain)              # the embedding really changes the tokens
+    np.savez_compressed(OUT / "vqgan_geometric.npz", h=pre[0].numpy(), idx=idx.numpy().astype(np.int32), rec=rec.numpy(), x_crc=crc(x),
+                        intrinsics_inv=batch["intrinsics_inv"].numpy(), extrinsics_inv=batch["extrinsics_inv"].numpy())
+    print("vqgan geometric", tuple(rec.shape), "tokens changed by the embedding:", int((idx != idx_plain).sum()), "of", idx.numel())
+
+
+class _NoGeo:
+    """Attribute proxy that turns geometric_embedding off for one call of the reference's encode (to show the branch matters)."""
+    def __init__(self, m):
+        self._m = m
+
+    def __getattr__(self, k):
+        return False if k == "geometric_embedding" else getattr(self._m, k)
+
+
 def _sizes(cfg):
     return dict(num_embed=cfg.num_embed, gpt_block_size=cfg.gpt_block_size, num_img_tokens=cfg.num_img_tokens,
                 num_cond_tokens=cfg.num_cond_tokens, num_cams=cfg.num_cams, vocab_size=cfg.vocab_size,
@@ -230,6 +263,9 @@ def golden_topk():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "maskgit":
         golden_maskgit()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "vqgan_geometric":
+        golden_vqgan_geometric()
         sys.exit(0)
     assert ref_import.available(), "run in the build container (needs /root/reference)"
     OUT.mkdir(parents=True, exist_ok=True)

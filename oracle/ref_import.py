@@ -124,6 +124,47 @@ def muse():
     return _load_by_path("ref_muse_maskgit", "multi_view_generation/modules/stage2/muse_maskgit_pytorch.py")
 
 
+_STUB_ROOTS = {"pytorch_lightning", "hydra", "omegaconf", "rich", "lpips", "kornia", "torchmetrics", "taming", "image_utils", "wandb", "cv2",
+               "nuscenes", "pyquaternion", "shapely", "av2", "seaborn", "matplotlib", "PIL", "imageio", "lightning_utilities",
+               "lightning_fabric", "deepspeed", "descartes", "skimage"}
+
+
+def vqgan():
+    """Returns the reference's modules/stage1/vqgan.py (the LightningModule VQModel itself, unmodified).  pytorch_lightning, hydra and the
+    logging / plotting packages it pulls in through multi_view_generation.utils are absent offline: a meta-path finder answers every import
+    below those roots with a MagicMock package, `pytorch_lightning.LightningModule` being a bare nn.Module."""
+    import importlib.abc
+    import importlib.machinery
+    stage2()
+
+    class _LM(torch.nn.Module):
+        pass
+
+    class _Loader(importlib.abc.Loader):
+        def create_module(self, spec):
+            m = mock.MagicMock(name=spec.name)
+            m.__path__, m.__name__, m.__spec__ = [], spec.name, spec
+            if spec.name == "pytorch_lightning":
+                m.LightningModule = _LM
+            return m
+
+        def exec_module(self, module):
+            pass
+
+    class _RefStubFinder(importlib.abc.MetaPathFinder):
+        def find_spec(self, name, path, target=None):
+            if name.split(".")[0] in _STUB_ROOTS:
+                return importlib.machinery.ModuleSpec(name, _Loader(), is_package=True)
+            return None
+    for k in [k for k in sys.modules if k.split(".")[0] in _STUB_ROOTS]:
+        del sys.modules[k]
+    if not any(type(f).__name__ == "_RefStubFinder" for f in sys.meta_path):
+        sys.meta_path.insert(0, _RefStubFinder())
+    import multi_view_generation.utils  # noqa: F401  (first: the reference has a utils <-> vqgan import cycle that only resolves in this order)
+    from multi_view_generation.modules.stage1 import vqgan as rv
+    return rv
+
+
 def release_stage2():
     """Drop the reference package from sys.modules / sys.path so our drop-in package can be imported."""
     global _stage2_cache

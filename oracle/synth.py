@@ -118,8 +118,11 @@ def vqgan_keys(dd, n_embed=1024, embed_dim=256):
     return out
 
 
-def vqgan_state_dict(dd, seed=0, n_embed=1024, embed_dim=256, codebook="normal"):
+def vqgan_state_dict(dd, seed=0, n_embed=1024, embed_dim=256, codebook="normal", geometric=False):
     sd = OrderedDict()
+    if geometric:      # VQModel(geometric_embedding=True): 1x1 convs of the ray / camera-centre embedding (vqgan.py:68-69), cam_emd_dim = z_channels
+        for k in ("img_embed.weight", "cam_embed.weight"):
+            sd[k] = tensor_for(k, (dd["z_channels"], 4, 1, 1), seed, "weight")
     for k, shp in vqgan_keys(dd, n_embed, embed_dim):
         if k == "quantize.embedding.weight":
             if codebook == "normal":      # separated codes: bit-exact argmin is well defined

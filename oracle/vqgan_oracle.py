@@ -105,9 +105,34 @@ def vq_nearest(z_nchw, codebook):
     return z_q, idx, d
 
 
-def encode(x, sd):
-    """VQModel.encode (vqgan.py:84-116) -> (quant NCHW, idx flat int64, pre-quant h)."""
-    h = _conv(encoder(x, sd), sd, "quant_conv")
+def ray_embedding(sd, batch, cam_res, lat_res):
+    """vqgan.py:62-69,87-109 (geometric_embedding=True): per camera and latent pixel the L2-normalised difference between the embedded
+    viewing ray  img_embed(E_inv (I_inv (x*W, y*H, 1); 1))  and the embedded camera centre  cam_embed(E_inv[:, 3])  -> (b*cam, d, h, w).
+    Note the stage-1 plane scales x by the image WIDTH and y by the HEIGHT (cam_res = (H, W)), unlike stage 2 (mingpt_sparse.py)."""
+    fh, fw = lat_res
+    xs, ys = torch.linspace(0, 1, fw), torch.linspace(0, 1, fh)
+    gx, gy = torch.meshgrid((xs, ys), indexing="xy")
+    pix = torch.stack([gx * cam_res[1], gy * cam_res[0], torch.ones_like(gx)], 0).reshape(3, fh * fw)      # 3 (h w)
+    I_inv = batch["intrinsics_inv"].float().reshape(-1, 3, 3)
+    E_inv = batch["extrinsics_inv"].float().reshape(-1, 4, 4)
+    d = sd["img_embed.weight"].shape[0]
+    cam = I_inv @ pix                                                   # n 3 (h w)
+    cam = torch.cat([cam, torch.ones_like(cam[:, :1])], 1)              # n 4 (h w)
+    ray = E_inv @ cam                                                   # n 4 (h w)
+    d_embed = torch.einsum("dk,nkp->ndp", sd["img_embed.weight"].reshape(d, 4), ray)
+    c_embed = torch.einsum("dk,nk->nd", sd["cam_embed.weight"].reshape(d, 4), E_inv[:, :, 3])
+    e = d_embed - c_embed[:, :, None]
+    e = e / (e.norm(dim=1, keepdim=True) + 1e-7)
+    return e.reshape(-1, d, fh, fw)
+
+
+def encode(x, sd, batch=None, cam_res=None):
+    """VQModel.encode (vqgan.py:84-116) -> (quant NCHW, idx flat int64, pre-quant h).  With `img_embed.weight` in sd and a batch the
+    geometric_embedding=True branch adds the ray embedding to the encoder output before quant_conv."""
+    h = encoder(x, sd)
+    if batch is not None and "img_embed.weight" in sd:
+        h = h + ray_embedding(sd, batch, cam_res, h.shape[-2:])
+    h = _conv(h, sd, "quant_conv")
     z_q, idx, _ = vq_nearest(h, sd["quantize.embedding.weight"])
     return z_q, idx, h
 

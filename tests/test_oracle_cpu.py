@@ -138,3 +138,22 @@ def test_maskgit_oracle_forward_and_generate(golden_dir):
     with torch.no_grad():
         gen = maskgit_oracle.generate(sd, geo, bev, batch, 2, cfg.num_heads, cpu_noise, timesteps=int(g["gen_steps"]))
     assert np.array_equal(gen.numpy().astype(np.int32), g["generated"])
+
+
+def test_vqgan_geometric_embedding_oracle(golden_dir):
+    """VQModel(geometric_embedding=True) - the default of configs/model/stage_1_cam.yaml - minted through the reference's own
+    LightningModule class (vqgan.py:62-69,84-121): pre-quantisation latent, token ids and reconstruction."""
+    g = np.load(golden_dir / "vqgan_geometric.npz")
+    dd = synth.vqgan_ddconfig(in_channels=3, ch=64, resolution=64)
+    sd = synth.vqgan_state_dict(dd, seed=4, geometric=True)
+    x = synth.image_batch(6, 3, 64, 64, seed=9)
+    assert zlib.crc32(x.numpy().tobytes()) == int(g["x_crc"])
+    batch = {"intrinsics_inv": torch.from_numpy(g["intrinsics_inv"]), "extrinsics_inv": torch.from_numpy(g["extrinsics_inv"])}
+    with torch.no_grad():
+        quant, idx, h = vqgan_oracle.encode(x, sd, batch, cam_res=(64, 64))
+        rec = vqgan_oracle.decode(quant, sd)
+        _, idx_plain, _ = vqgan_oracle.encode(x, sd)
+    assert np.abs(h.numpy() - g["h"]).max() < 2e-5
+    assert np.array_equal(idx.numpy().astype(np.int32), g["idx"].reshape(-1))
+    assert np.abs(rec.numpy() - g["rec"]).max() < 2e-5
+    assert not torch.equal(idx, idx_plain)

@@ -104,3 +104,30 @@ def test_host_round_trip_pipeline_matches_direct_calls():
         rec = model.decode(quant)
         assert torch.equal(idx.cpu().reshape(-1), idxs[i])
         assert torch.equal(rec.cpu(), recs[i])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["fp32x3", "f16f8"])
+def test_geometric_embedding_vs_reference_golden(precision, golden_dir):
+    """VQModel(geometric_embedding=True) (default of configs/model/stage_1_cam.yaml) against the golden minted through the
+    reference's own VQModel class: latent within 1e-3, token ids bit-exact, reconstruction within 1e-3; state_dict keys as the reference's."""
+    from multi_view_generation.modules.stage1.vqgan import VQModel
+    g = np.load(golden_dir / "vqgan_geometric.npz")
+    dd = synth.vqgan_ddconfig(in_channels=3, ch=64, resolution=64)
+    sd = synth.vqgan_state_dict(dd, seed=4, geometric=True)
+    model = VQModel(dd, None, 1024, 256, (64, 64), (4, 4), 256, geometric_embedding=True, precision=precision)
+    model.load_state_dict(sd, strict=True)                       # same keys as the reference's module (image_plane is non-persistent there too)
+    model = model.cuda().eval()
+    x = synth.image_batch(6, 3, 64, 64, seed=9)
+    batch = {"intrinsics_inv": torch.from_numpy(g["intrinsics_inv"]), "extrinsics_inv": torch.from_numpy(g["extrinsics_inv"])}
+    quant, _, (_, _, idx) = model.encode(x.cuda(), batch)
+    rec = model.decode(quant)
+    h = model.engine().encode(x.cuda(), batch, (64, 64))[2]
+    torch.cuda.synchronize()
+    err_h = np.abs(model.engine().nhwc_to_nchw(h).cpu().numpy() - g["h"]).max()
+    err_r = np.abs(rec.cpu().numpy() - g["rec"]).max()
+    print(f"[geometric {precision}] latent err {err_h:.2e}, rec err {err_r:.2e}")
+    assert err_h < 1e-3 and err_r < 1e-3
+    assert np.array_equal(idx.cpu().numpy().astype(np.int32).reshape(-1), g["idx"].reshape(-1))
+    with pytest.raises(ValueError):
+        model.engine().encode(x.cuda())                          # camera matrices are required in this mode
