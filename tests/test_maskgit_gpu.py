@@ -183,3 +183,26 @@ def test_net2net_muse_wrapper_generates_images():
     ids = model.sample(c_idx, batch, partial_decoding_idx=[1, 4])
     assert ids.shape == (6, 16, 16) and int(ids.max()) < 1024
     assert torch.equal(ids.reshape(6, -1)[[1, 4]], z_idx.reshape(6, -1)[[1, 4]])
+
+
+def test_reference_geometry_14x25_vs_oracle():
+    """The geometry of the reference's MaskGit config (6 cameras x 14x25 latents = 2100 image tokens, sparse_block_size 1): ragged 128-row
+    tiles everywhere (2100 queries, 2101 / 257 keys in 2176-row planes), checked against the oracle at reduced width."""
+    from bevgen_b200.maskgit_engine import MaskGitEngine
+    kw = {**GPT_SMALL, "cam_latent_res": (14, 25), "cam_res": (224, 400), "sparse_block_size": 1}
+    cfg = GPTConfig(**kw)
+    assert cfg.num_img_tokens == 2100 and cfg.num_pad_tokens == 0
+    sd = synth.maskgit_state_dict(gpt_sizes(cfg), 2, cfg.num_heads, seed=11)
+    critic = {"weight": sd.pop("to_pred.weight"), "bias": sd.pop("to_pred.bias")}
+    cam, bev, batch = synth.stage2_inputs(1, cfg.num_cams, cfg.num_cam_tokens, cfg.num_cond_tokens, cfg.vocab_size, cfg.cond_vocab_size, seed=3)
+    ids = cam.reshape(cfg.num_cams, cfg.num_cam_tokens).clone()
+    ids[:, 1::2] = cfg.vocab_size
+    eng = MaskGitEngine(sd, cfg, depth=2, heads=cfg.num_heads, device="cuda:0", precision="f16f8", critic=critic)
+    assert eng.lk_f == 2176
+    with torch.no_grad():
+        want_l, want_e = maskgit_oracle.forward(sd, gpt_oracle.geo_from_config(cfg), ids, bev, batch, 2, cfg.num_heads)
+    logits, emb = eng.forward(ids.cuda(), bev.cuda(), batch)
+    torch.cuda.synchronize()
+    assert torch.isfinite(logits).all()
+    assert (logits.cpu() - want_l).abs().max().item() < LOGIT_TOL
+    assert (emb.cpu() - want_e).abs().max().item() < LOGIT_TOL
