@@ -431,11 +431,11 @@ BEVGEN_API int bevgen_ray_embed_add(float* h_nhwc, const float* intrinsics_inv, 
 
 /* ---------------------------------------------------------------- MaskGit variant */
 BEVGEN_API int bevgen_mg_head_planes(const float* src, long long src_ld, int src_col0, int n_src, int src_batch_rows, const float* null_vec,
-                                     const float* scale, void* out_hi, void* out_lo, int batch, int dst_rows, long long dst_ld, int dst_col0,
-                                     int has_null, int heads, void* stream) {
+                                     const float* scale, void* out_hi, void* out_lo, int batch, int dst_rows, int dst_batch_rows, long long dst_ld,
+                                     int dst_col0, int has_null, int heads, void* stream) {
   if (!src || !out_hi) return fail(BEVGEN_ERR_ARG, "mg_head_planes: bad args");
   CHECK_LAUNCH(launch_mg_head_planes(src, src_ld, src_col0, n_src, src_batch_rows, null_vec, scale, (uint16_t*)out_hi, (uint16_t*)out_lo, batch,
-                                     dst_rows, dst_ld, dst_col0, has_null, heads, (cudaStream_t)stream), "mg_head_planes");
+                                     dst_rows, dst_batch_rows, dst_ld, dst_col0, has_null, heads, (cudaStream_t)stream), "mg_head_planes");
 }
 
 BEVGEN_API int bevgen_mg_geglu_ln(const float* h, long long h_ld, const float* gamma, void* out_hi, void* out_lo, long long rows, int f, int f_pad,

@@ -12,14 +12,14 @@ namespace bevgen {
 // Attention.forward :137-154: per (row, head) 64-vector, optional cosine-sim normalisation (F.normalize, eps 1e-12) times a learned
 // per-channel scale, written as bf16 hi / lo operand planes.  With has_null the destination holds, per batch element, row 0 = the
 // head's null key / value (normalised the same way), rows 1 .. n_src = the source rows, rows above = zeros (key padding up to the GEMM
-// tile; masked in the softmax).  Source rows of batch b start at row b * src_batch_rows; the destination is [batch][dst_rows] rows of
-// pitch dst_ld with the heads at columns dst_col0 + 64 h (so q | k | v can share one fused plane).  One warp per (row, head).
+// tile; masked in the softmax).  Source rows of batch b start at row b * src_batch_rows; the destination is dst_rows rows per batch element
+// (batch stride dst_batch_rows rows) of pitch dst_ld with the heads at columns dst_col0 + 64 h (so q | k | v can share one fused plane).  One warp per (row, head).
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) mg_head_planes_kernel(const float* __restrict__ src, long long src_ld, int src_col0, int n_src,
                                                              int src_batch_rows, const float* __restrict__ null_vec,
                                                              const float* __restrict__ scale, uint16_t* __restrict__ hi,
-                                                             uint16_t* __restrict__ lo, int dst_rows, long long dst_ld, int dst_col0,
-                                                             int has_null, int H, long long total) {
+                                                             uint16_t* __restrict__ lo, int dst_rows, int dst_batch_rows, long long dst_ld,
+                                                             int dst_col0, int has_null, int H, long long total) {
   const long long w = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (w >= total) return;
   const int lane = threadIdx.x & 31;
@@ -47,18 +47,19 @@ __global__ void __launch_bounds__(256) mg_head_planes_kernel(const float* __rest
   __nv_bfloat16 h0, l0, h1, l1;
   split_bf16(v.x, h0, l0);
   split_bf16(v.y, h1, l1);
-  const size_t off = (size_t)drow * dst_ld + dst_col0 + h * 64 + lane * 2;
+  const size_t off = ((size_t)b * dst_batch_rows + r) * dst_ld + dst_col0 + h * 64 + lane * 2;
   *reinterpret_cast<uint32_t*>(hi + off) = pack_bf16(h0, h1);
   if (lo != nullptr) *reinterpret_cast<uint32_t*>(lo + off) = pack_bf16(l0, l1);
 }
 
 int launch_mg_head_planes(const float* src, long long src_ld, int src_col0, int n_src, int src_batch_rows, const float* null_vec, const float* scale,
-                          uint16_t* hi, uint16_t* lo, int B, int dst_rows, long long dst_ld, int dst_col0, int has_null, int H, cudaStream_t st) {
-  if (B < 1 || H < 1 || dst_rows < n_src + has_null || src_batch_rows < n_src || (has_null && !null_vec) || (src_ld & 1) || (src_col0 & 1) ||
+                          uint16_t* hi, uint16_t* lo, int B, int dst_rows, int dst_batch_rows, long long dst_ld, int dst_col0, int has_null, int H,
+                          cudaStream_t st) {
+  if (B < 1 || H < 1 || dst_rows < n_src + has_null || dst_batch_rows < dst_rows || src_batch_rows < n_src || (has_null && !null_vec) || (src_ld & 1) || (src_col0 & 1) ||
       (dst_ld & 1) || (dst_col0 & 1) || dst_ld < dst_col0 + 64LL * H)
     return BEVGEN_ERR_ARG;
   const long long total = (long long)B * dst_rows * H;
-  mg_head_planes_kernel<<<(unsigned)((total + 7) / 8), 256, 0, st>>>(src, src_ld, src_col0, n_src, src_batch_rows, null_vec, scale, hi, lo, dst_rows, dst_ld, dst_col0, has_null, H, total);
+  mg_head_planes_kernel<<<(unsigned)((total + 7) / 8), 256, 0, st>>>(src, src_ld, src_col0, n_src, src_batch_rows, null_vec, scale, hi, lo, dst_rows, dst_batch_rows, dst_ld, dst_col0, has_null, H, total);
   return cudaGetLastError() == cudaSuccess ? BEVGEN_OK : BEVGEN_ERR_CUDA;
 }
 

@@ -199,8 +199,12 @@ class MaskGitEngine:
         n, H, inner, lk = self.n_img, self.H, self.inner, self.lk_f
         fp = self._planes((B * lk, 3 * inner))
         ops.mg_head_planes(q, inner, 0, n, fp[0], fp[1], B, lk, H, scale=aw["q_scale"], dst_ld=3 * inner, dst_col0=0)
-        ops.mg_head_planes(kv, 2 * inner, 0, self.nc, fp[0], fp[1], B, lk, H, null_vec=aw["null_k"], scale=aw["k_scale"], dst_ld=3 * inner, dst_col0=inner)
-        ops.mg_head_planes(kv, 2 * inner, inner, self.nc, fp[0], fp[1], B, lk, H, null_vec=aw["null_v"], dst_ld=3 * inner, dst_col0=2 * inner)
+        # only the first lk_cross key rows of each scene are ever loaded (the layout table skips the other key tiles)
+        kr = self.lk_cross
+        ops.mg_head_planes(kv, 2 * inner, 0, self.nc, fp[0], fp[1], B, kr, H, null_vec=aw["null_k"], scale=aw["k_scale"], dst_ld=3 * inner, dst_col0=inner,
+                           dst_batch_rows=lk)
+        ops.mg_head_planes(kv, 2 * inner, inner, self.nc, fp[0], fp[1], B, kr, H, null_vec=aw["null_v"], dst_ld=3 * inner, dst_col0=2 * inner,
+                           dst_batch_rows=lk)
         op = self._planes((B * lk, inner))
         ops.attn_fused_fwd(fp[0], fp[1], B, lk, H, inner, lk, self.bias_cross_tiled, None, None, self.scale, self.npass,
                            algo_flops=4.0 * B * H * 64 * float(n) * (self.nc + 1), layout64=self.cross_tiles, out_hi=op[0], out_lo=op[1])

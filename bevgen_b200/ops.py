@@ -455,13 +455,14 @@ def groupnorm_affine(sums, gamma, beta, affine, n, pixels, c, eps=1e-6):
 
 
 def mg_head_planes(src, src_ld, src_col0, n_src, out_hi, out_lo, batch, dst_rows, heads, null_vec=None, scale=None, src_batch_rows=None,
-                   dst_ld=None, dst_col0=0):
+                   dst_ld=None, dst_col0=0, dst_batch_rows=None):
     """MaskGit attention operand planes (bevgen_mg_head_planes): head split, optional null row, optional cosine-sim normalisation."""
     lib = _lib.init()
     Stats.launches += 1
     _chk_cuda(src, out_hi, out_lo, null_vec, scale)
     _lib.check(lib.bevgen_mg_head_planes(_ptr(src), src_ld, src_col0, n_src, n_src if src_batch_rows is None else src_batch_rows, _ptr(null_vec),
-                                         _ptr(scale), _ptr(out_hi), _ptr(out_lo), batch, dst_rows, 64 * heads if dst_ld is None else dst_ld, dst_col0,
+                                         _ptr(scale), _ptr(out_hi), _ptr(out_lo), batch, dst_rows, dst_rows if dst_batch_rows is None else dst_batch_rows,
+                                         64 * heads if dst_ld is None else dst_ld, dst_col0,
                                          0 if null_vec is None else 1, heads, _stream()), "mg_head_planes")
 
 

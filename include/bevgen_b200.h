@@ -253,11 +253,11 @@ BEVGEN_API int bevgen_ray_embed_add(float* h_nhwc, const float* intrinsics_inv, 
 
 /* Attention.forward :137-154 (head split, null key / value, cosine-sim normalisation): per (row, head) 64-vector of
  * src[(b*src_batch_rows + r) * src_ld + src_col0 + h*64 ..], optionally x / max(|x|, 1e-12) * scale[0..63] (scale == NULL: plain copy), to bf16
- * hi / lo planes of [batch][dst_rows] rows with pitch dst_ld elements, heads at columns dst_col0 + 64 h (q | k | v may share one plane).  has_null: destination row 0 = null_vec[h][0..63] (same normalisation), source rows follow
+ * hi / lo planes: dst_rows rows per batch element (batch stride dst_batch_rows >= dst_rows rows) with pitch dst_ld elements, heads at columns dst_col0 + 64 h (q | k | v may share one plane).  has_null: destination row 0 = null_vec[h][0..63] (same normalisation), source rows follow
  * from row 1, rows above n_src + 1 are zero (key padding up to the GEMM tile; the caller masks them in the softmax). */
 BEVGEN_API int bevgen_mg_head_planes(const float* src, long long src_ld, int src_col0, int n_src, int src_batch_rows, const float* null_vec,
-                                     const float* scale, void* out_hi, void* out_lo, int batch, int dst_rows, long long dst_ld, int dst_col0,
-                                     int has_null, int heads, void* stream);
+                                     const float* scale, void* out_hi, void* out_lo, int batch, int dst_rows, int dst_batch_rows, long long dst_ld,
+                                     int dst_col0, int has_null, int heads, void* stream);
 /* FeedForward :72-88 between its Linear layers: u = h[:, f:2f] * gelu(h[:, 0:f]) on rows of pitch h_ld; planes = LayerNorm_f(u) * gamma
  * (eps, biased variance), bf16 hi / lo [rows][f_pad], columns f .. f_pad-1 zero, f_pad <= 3072.  f16f8 != 0: out_hi / out_lo are instead the
  * scaled fp16 plane and the e4m3 pair plane of a following bevgen_linear_f16f8 (f_pad % 64 == 0). */
