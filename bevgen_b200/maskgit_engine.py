@@ -304,9 +304,44 @@ class MaskGitEngine:
         self._linear(self._last_embed_planes, self.critic[0], 1, rows, self.d, bias=self.critic[1], out_f32=out)
         return out.view(-1, self.cfg.num_cam_tokens)
 
+    # ------------------------------------------------------------------ CUDA-graph replay of the two forwards of a generate step
+    def _graphs(self, cond_ids, batch, use_critic):
+        """One captured graph per (batch size, critic) holding [forward -> logits] and, with the critic, [forward -> scores] on static
+        input buffers: a forward is ~400 launches, and at 2 scenes the launch overhead is a sixth of the step."""
+        B = cond_ids.shape[0]
+        key = (B, bool(use_critic))
+        g = self._graph_cache.get(key) if hasattr(self, "_graph_cache") else None
+        if g is None:
+            if not hasattr(self, "_graph_cache"):
+                self._graph_cache = {}
+            st = {"ids": torch.full((B * self.cfg.num_cams, self.cfg.num_cam_tokens), self.mask_id, dtype=torch.int64, device=self.dev),
+                  "cond": torch.zeros((B, self.nc), dtype=torch.int64, device=self.dev),
+                  "batch": {"intrinsics_inv": torch.zeros((B, self.cfg.num_cams, 3, 3), device=self.dev),
+                            "extrinsics_inv": torch.zeros((B, self.cfg.num_cams, 4, 4), device=self.dev)}}
+            side = torch.cuda.Stream(self.dev)
+            side.wait_stream(torch.cuda.current_stream(self.dev))
+            with torch.cuda.stream(side):          # warm-up outside capture (lazy kernel attribute setup, allocator pools)
+                self.forward(st["ids"], st["cond"], st["batch"])
+                if use_critic:
+                    self.critic_scores(st["ids"], st["cond"], st["batch"])
+            torch.cuda.current_stream(self.dev).wait_stream(side)
+            st["g_fwd"] = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(st["g_fwd"]):
+                st["logits"], _ = self.forward(st["ids"], st["cond"], st["batch"])
+            if use_critic:
+                st["g_crit"] = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(st["g_crit"], pool=st["g_fwd"].pool()):
+                    st["scores"] = self.critic_scores(st["ids"], st["cond"], st["batch"])
+            self._graph_cache = {key: st}           # one live set of static buffers
+            g = st
+        g["cond"].copy_(cond_ids)
+        g["batch"]["intrinsics_inv"].copy_(batch["intrinsics_inv"].to(self.dev, torch.float32))
+        g["batch"]["extrinsics_inv"].copy_(batch["extrinsics_inv"].to(self.dev, torch.float32))
+        return g
+
     @torch.no_grad()
     def generate(self, cond_ids, batch, timesteps=18, temperature=1.0, topk_filter_thres=0.9, critic_noise_scale=1.0, init_ids=None,
-                 use_critic=None, noise=None, generator=None, trace=None):
+                 use_critic=None, noise=None, generator=None, trace=None, use_graph=True):
         """MaskGit.generate (:511-627).  noise(kind, step, shape) -> uniform(0, 1) tensor (tests replay the reference's draws); default:
         torch.rand on the device.  The token bookkeeping between the forwards (top-k, scatter, gumbel arg-max) is a handful of torch
         calls on [b*cam, hw(, vocab)] tensors."""
@@ -324,12 +359,18 @@ class MaskGitEngine:
             init_ids = init_ids.to(dev)
             init_mask = init_ids != self.mask_id
         k = math.ceil((1 - topk_filter_thres) * self.vocab)
+        gr = self._graphs(cond_ids, batch, use_critic) if use_graph else None
         for step, (t, until_x0) in enumerate(zip(torch.linspace(0, 1, timesteps), reversed(range(timesteps)))):
             n_mask = max(int((torch.cos(t * math.pi * 0.5) * hw).item()), 1)
             ids = ids.scatter(1, scores.topk(n_mask, dim=-1).indices, self.mask_id)
             if init_ids is not None:
                 ids[init_mask] = init_ids[init_mask]
-            logits, _ = self.forward(ids, cond_ids, batch)
+            if gr is not None:
+                gr["ids"].copy_(ids)
+                gr["g_fwd"].replay()
+                logits = gr["logits"]
+            else:
+                logits, _ = self.forward(ids, cond_ids, batch)
             if trace is not None:
                 trace.append((ids.clone(), logits.clone()))
             temp = temperature * (until_x0 / timesteps)
@@ -341,7 +382,12 @@ class MaskGitEngine:
             is_mask = ids == self.mask_id
             ids = torch.where(is_mask, pred, ids)
             if use_critic:
-                scores = self.critic_scores(ids, cond_ids, batch)
+                if gr is not None:
+                    gr["ids"].copy_(ids)
+                    gr["g_crit"].replay()
+                    scores = gr["scores"]
+                else:
+                    scores = self.critic_scores(ids, cond_ids, batch)
                 scores = scores + (noise("critic", step, tuple(scores.shape)).to(dev) - 0.5) * critic_noise_scale * (until_x0 / timesteps)
             else:
                 scores = 1 - logits.softmax(-1).gather(2, pred[..., None])[..., 0]
