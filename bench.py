@@ -1,14 +1,22 @@
 #!/usr/bin/env python
-"""bench.py — multi-view images/s of the stage-1 VQGAN hot path (BASELINE.json configs[1]) on N B200s.
+"""bench.py — multi-view images/s of BEVGen's generate.py hot path (BASELINE.json configs[3] on one B200, configs[4] on N) .
 
-Contract (see the task statement): `python bench.py --gpus N --steps K --warmup W` prints ONE JSON line from rank 0.
-A step = one encode -> quantise -> decode pass over 16 scenes x 6 cameras = 96 RGB 256x256 images per GPU (weak scaling:
-scenes are independent, no data-path collective; weights are NCCL-broadcast once at start-up).
-  value     images/s with the batch already resident in HBM (CUDA events, max over ranks)
-  e2e       same through the public VQModel.encode/decode API with pinned HOST buffers (H2D + D2H inside the timed region)
-  roofline  tcgen05 GEMM kernel: algorithmic conv/GEMM FLOPs per launch / CUDA-event launch time vs measured bf16 peak
-  cpu_baseline  the CPU oracle (port of the reference's PyTorch path) on a bounded sample, host cores stated
-`--impl reference` times that CPU path alone (rank 0 only).
+Contract (task statement): `python bench.py --gpus N --steps K --warmup W` prints ONE JSON line from rank 0.
+A step = ONE `Net2NetTransformer.test_step(batch)` call (what generate.py's trainer.test runs per batch, reference
+modules/stage2/cond_transformer_multi_view.py:378-384,479-544) on 16 synthetic scenes per GPU:
+    batch dict (6 x 256x256 RGB + 256x256x7 BEV map + camera matrices per scene)
+      -> RGB VQGAN encode (96 images) + BEV VQGAN encode (16 maps) -> teacher-forced forward + CE loss (the test/loss it logs)
+      -> reconstruction decode (96 images) -> KV-cache autoregressive sampling of 16 x 1536 tokens (top-k 100, multinomial)
+      -> VQGAN decode of the 96 generated images -> de-normalise  => {'gen','rec','gt'}
+  value     generated images/s with the batch dict already resident in HBM (CUDA events, barrier both sides, max over ranks)
+  e2e       same through the same public call with pinned HOST tensors in and `gen` + `rec` copied back to pinned host memory
+            inside the timed region (the headline against the reference arm)
+  roofline  the KV-cache decode loop (97 % of the step): SURVEY 8d algorithmic bytes (556 MB of bf16-equivalent weights x 1536 steps
+            + bf16-equivalent KV reads = 3.33 TB per 16 scenes) / CUDA-event time of the loop, against the measured HBM copy bandwidth
+  cpu_baseline / --impl reference   the reference algorithm (one full 1792-token forward per generated token, no KV cache) through the
+            CPU oracle port on the host cores, a bounded number of loop iterations extrapolated to 1536 (flagged)
+Sub-objects (N = 1 only): stage-1 round trip (configs[1]) and teacher-forced forward (configs[2]) with their own rooflines, a same-box
+eager-PyTorch GPU baseline, the MaskGit variant.  Weak scaling: scenes are independent, 16 per rank, weights NCCL-broadcast once.
 """
 import argparse
 import json
@@ -25,9 +33,20 @@ sys.path.insert(0, str(ROOT))
 
 METRIC = "multi_view_images_per_sec"
 UNIT = "images/s"
-SCENES, CAMS, RES = 16, 6, 256
-WORKLOAD = ("configs[1]: stage-1 RGB VQGAN encode->quantize->decode, 6-cam 256x256, batch=16 scenes "
-            "(96 images) per GPU, synthetic seeded weights (no checkpoints offline)")
+SCENES, CAMS, RES, TOKENS = 16, 6, 256, 1536
+WORKLOAD = ("configs[3] (1 GPU) / configs[4] (N GPUs): full autoregressive generate.py hot path = Net2NetTransformer.test_step on 16 scenes "
+            "per GPU: 6-cam 256x256 RGB + BEV cond -> VQGAN encodes, teacher-forced loss, KV-cache sampling of 1536 tokens/scene "
+            "(24-layer d=1024 GPT, top-k 100), VQGAN decode of 96 generated + 96 reconstructed images; synthetic seeded weights and inputs")
+CONFIG = {"workload": WORKLOAD, "scenes_per_gpu": SCENES, "images_per_scene": CAMS, "tokens_per_scene": TOKENS,
+          "gpt": "24 layers, d=1024, 16 heads, L=1792, density 1.0", "vqgan": "ch=128, ch_mult [1,1,2,2,4], 256x256 -> 16x16 latents, 1024 codes",
+          "l2": "per-step working set (1.1 GB packed weights + 2.8 GB KV cache + 3.2 GB activations) exceeds the 126 MB L2; no explicit flush"}
+ALGO_BYTES_8D = 24 * 11 * 1024 * 1024 * 2 + 1024 * 1024 * 2          # 556 MB of weights per decode step (bf16, head included)
+
+
+def algo_bytes_decode(scenes, steps=TOKENS, nc=256, layers=24, d=1024):
+    """weights once per step + bf16 KV reads 24*2*n*d*2 B per sample with n = 257 + t."""
+    kv = sum(layers * 2 * (nc + 1 + t) * d * 2 for t in range(steps)) * scenes
+    return ALGO_BYTES_8D * steps + kv
 
 
 def peaks():
@@ -79,120 +98,228 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference_rate(n_images, steps=1, warmup=0):
-    """CPU oracle (restatement of the reference's PyTorch path, oracle/vqgan_oracle.py) on all host cores."""
+# ------------------------------------------------------------------------------------------------ workload
+def gpt_kw(layers=24):
+    return dict(embd_pdrop=0., resid_pdrop=0., attn_pdrop=0., n_unmasked=0, num_cams=6, vocab_size=1024, cond_vocab_size=1024, hidden_size=1024,
+                num_embed=1024, num_heads=16, num_layers=layers, backend="deepspeed", sparse_block_size=16, window_len=32, cam_res=(256, 256),
+                cam_latent_res=(16, 16), plot=False, causal_order=True, camera_bias=True, image_embed=True, bev_embed=True,
+                bev_latent_res=(16, 16), density=1.0, cam_names="NUSCENES_CAMERAS", dataset="NUSCENES")
+
+
+def gpt_sizes(cfg):
+    return dict(num_embed=cfg.num_embed, gpt_block_size=cfg.gpt_block_size, num_img_tokens=cfg.num_img_tokens, num_cond_tokens=cfg.num_cond_tokens,
+                num_cams=cfg.num_cams, vocab_size=cfg.vocab_size, cond_vocab_size=cfg.cond_vocab_size, num_layers=cfg.num_layers)
+
+
+def host_batch(scenes, rank=0, pin=True):
+    """The batch dict generate.py's dataloader would hand over (SURVEY 8b schema), seeded: scene s / camera c = image 6 s + c of
+    synth.image_batch(96, seed=100 + rank) - the tensor the parity goldens (tests/golden/vqgan_config2_*.npz) were minted on."""
     import torch
-    from oracle import synth, vqgan_oracle
+    from oracle import synth          # seeded inputs only
+    x = synth.image_batch(scenes * CAMS, 3, RES, RES, seed=100 + rank)
+    seg = (synth.image_batch(scenes, 7, RES, RES, seed=300 + rank) > 0).float()
+    _, _, mats = synth.stage2_inputs(scenes, seed=rank)
+    b = {"image": x.view(scenes, CAMS, 3, RES, RES).permute(0, 1, 3, 4, 2).contiguous(), "segmentation": seg.permute(0, 2, 3, 1).contiguous(),
+         "intrinsics_inv": mats["intrinsics_inv"].contiguous(), "extrinsics_inv": mats["extrinsics_inv"].contiguous()}
+    if pin:
+        b = {k: v.pin_memory() for k, v in b.items()}
+    b["sample_token"] = [f"scene{rank}_{i}" for i in range(scenes)]
+    return b
+
+
+def build_model(precision, dev, load_weights=True):
+    """Net2NetTransformer(GPT 24 x 1024, RGB VQModel, BEV VQSegmentationModel) under the reference's import paths, seeded weights."""
+    import torch
+    from multi_view_generation.modules.losses.vqperceptual import DummyLoss
+    from multi_view_generation.modules.stage1.vqgan import VQModel, VQSegmentationModel
+    from multi_view_generation.modules.stage2.cond_transformer_multi_view import Net2NetTransformer
+    from multi_view_generation.modules.transformer.mingpt_sparse import GPT, GPTConfig
+    from oracle import synth          # seeded weights only
+    cfg = GPTConfig(**gpt_kw())
+    gpt = GPT(cfg, precision=precision)
+    dd, ddb = synth.vqgan_ddconfig(), synth.vqgan_ddconfig(in_channels=7)
+    fs = VQModel(dd, DummyLoss(), 1024, 256, (RES, RES), (16, 16), 256, precision=precision)
+    cs = VQSegmentationModel(7, ddb, DummyLoss(), 1024, 256, (RES, RES), (16, 16), 256, precision=precision)
+    if load_weights:
+        gpt.load_state_dict(synth.gpt_state_dict(gpt_sizes(cfg), seed=2), strict=False)
+        fs.load_state_dict(synth.vqgan_state_dict(dd, seed=1))
+        cs.load_state_dict(synth.vqgan_state_dict(ddb, seed=1), strict=False)
+    model = Net2NetTransformer(gpt, fs, cs, top_k=100).to(dev).eval()
+    model.sample_seed = 1234
+    return model
+
+
+# ------------------------------------------------------------------------------------------------ reference arm / CPU baseline
+def cpu_reference(loop_steps, warmup, stage1_images=2):
+    """The reference ALGORITHM on the host cores through the CPU oracle port (oracle/gpt_oracle.py, oracle/vqgan_oracle.py; pinned to the
+    reference by tests/golden): per generated token ONE full 1792-token forward of the 24-layer GPT for one scene (no KV cache,
+    cond_transformer_multi_view.py:172-219) + top-k / softmax / multinomial.  `loop_steps` iterations are timed and extrapolated to the
+    1536 of a scene; the stage-1 work of a scene (7 encodes, 12 decodes) is timed on `stage1_images` images and scaled."""
+    import torch
+    from bevgen_b200.gpt_config import GPTConfig
+    from oracle import gpt_oracle, synth, vqgan_oracle
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    cfg = GPTConfig(**gpt_kw())
+    geo = gpt_oracle.geo_from_config(cfg)
+    sd = synth.gpt_state_dict(gpt_sizes(cfg), seed=2)
+    _, bev, mats = synth.stage2_inputs(1, seed=0)
     dd = synth.vqgan_ddconfig()
-    sd = synth.vqgan_state_dict(dd, seed=1)
-    x = synth.image_batch(n_images, 3, RES, RES, seed=7)
+    vsd = synth.vqgan_state_dict(dd, seed=1)
+    x = synth.image_batch(stage1_images, 3, RES, RES, seed=100)
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        quant, idx, _ = vqgan_oracle.encode(x, vsd)
+        t_enc = (time.perf_counter() - t0) / stage1_images
+        t0 = time.perf_counter()
+        vqgan_oracle.decode(quant, vsd)
+        t_dec = (time.perf_counter() - t0) / stage1_images
+    stage1_s = 7 * t_enc + 12 * t_dec            # 6 camera + 1 BEV encode; 6 reconstruction + 6 generated decodes
+    ncam, ntok = cfg.num_cams, cfg.num_cam_tokens
+    xtok = torch.full((1, ncam, ntok), cfg.vocab_size, dtype=torch.int64)
+    g = torch.Generator().manual_seed(0)
     times = []
     with torch.no_grad():
-        for i in range(warmup + steps):
+        for t in range(warmup + loop_steps):
+            j = int(cfg.forward_shuffle_idx[t])
+            i, k = j // ntok, j % ntok
             t0 = time.perf_counter()
-            quant, idx, _ = vqgan_oracle.encode(x, sd)
-            rec = vqgan_oracle.decode(quant, sd)
+            logits = gpt_oracle.forward(sd, geo, xtok, bev, mats, sampling=True).view(1, ncam, ntok, -1)[:, i, k]
+            p = gpt_oracle.sample_probs(logits, 1.0, 100)
+            xtok[:, i, k] = torch.multinomial(p, 1, generator=g)[:, 0]
             dt = time.perf_counter() - t0
-            if i >= warmup:
+            if t >= warmup:
                 times.append(dt)
-    total = sum(times)
-    return n_images * len(times) / total, cores, total / len(times)
+    step_s = sum(times) / len(times)
+    scene_s = stage1_s + step_s * (TOKENS + 1)          # + the teacher-forced forward of shared_step
+    return {"images_per_s": CAMS / scene_s, "cores": cores, "loop_step_s": step_s, "stage1_s_per_scene": stage1_s, "scene_s_extrapolated": scene_s,
+            "timed_loop_steps": len(times)}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = 4
-    rate, cores, sec = cpu_reference_rate(sample, steps=args.steps, warmup=args.warmup)
-    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "device": "host CPU"},
-            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{sample} images 256x256 per step (encode+quantize+decode), torch CPU fp32, {cores} threads"},
-            "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    r = cpu_reference(args.steps, args.warmup)
+    sample = (f"reference algorithm, 1 scene: {r['timed_loop_steps']} timed iterations of the sample loop (one 24-layer 1792-token forward each, "
+              f"{r['loop_step_s']:.2f} s/iteration) extrapolated x1537, + stage-1 of the scene measured on 2 images ({r['stage1_s_per_scene']:.1f} s); "
+              f"torch CPU fp32, {r['cores']} threads; EXTRAPOLATED: a full scene would take {r['scene_s_extrapolated'] / 3600:.2f} h")
+    line = {"impl": "reference", "metric": METRIC, "value": r["images_per_s"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": r["loop_step_s"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "extrapolated": True,
+            "config": {**CONFIG, "parallelism": f"scene-sharded x{args.gpus} (16 scenes per GPU), weights broadcast once, no data-path collective"},
+            "step_definition": "one iteration of the reference's sample loop for one scene (a bounded sample of the workload: the full step is 1536 of them per scene x 16 scenes)",
+            "cpu_baseline": {"value": r["images_per_s"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": sample},
+            "e2e": {"value": r["images_per_s"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------ output self-check
+def self_check(model, batch_dev, out, rank):
+    """After the timed loop: the step's outputs against the committed reference goldens (rank 0's batch is the tensor they were minted on)."""
+    import numpy as np
+    import torch
+    from oracle import vqgan_oracle
+    res = {}
+    gen, rec = out["gen"], out["rec"]
+    res["shapes_ok"] = tuple(gen.shape) == (SCENES, CAMS, 3, RES, RES) and tuple(rec.shape) == tuple(gen.shape)
+    res["gen_finite_in_0_1"] = bool(torch.isfinite(gen).all() and gen.min() >= 0 and gen.max() <= 1)
+    if rank != 0:
+        return res
+    try:
+        g = np.load(ROOT / "tests" / "golden" / "vqgan_config2_rgb.npz")
+        gb = np.load(ROOT / "tests" / "golden" / "vqgan_config2_bev.npz")
+        x, c = model.get_xc(batch_dev)
+        _, zi = model.encode_to_z(x, batch_dev)
+        _, ci = model.encode_to_c(c, batch_dev)
+        mism = int((zi.reshape(-1)[:2048].cpu().numpy() != g["idx"]).sum())
+        mism_b = int((ci.reshape(-1)[:512].cpu().numpy() != gb["idx"]).sum())
+        want = vqgan_oracle.denormalize(torch.from_numpy(g["rec_sub"]))
+        rec8 = rec.reshape(-1, 3, RES, RES)[:8, :, ::8, ::8].cpu()
+        res.update(rgb_token_mismatches_vs_reference_golden=f"{mism}/2048", bev_token_mismatches_vs_reference_golden=f"{mism_b}/512",
+                   rec_max_err_vs_reference_golden=float((rec8 - want).abs().max()) if mism == 0 else None,
+                   loss_finite=bool(torch.isfinite(model.last_test_loss)), loss=float(model.last_test_loss))
+        res["ok"] = bool(res["shapes_ok"] and res["gen_finite_in_0_1"] and mism <= 2 and mism_b <= 1 and res["loss_finite"]
+                         and (res["rec_max_err_vs_reference_golden"] is None or res["rec_max_err_vs_reference_golden"] < 1e-3))
+    except Exception as ex:      # the bench line must still be printed
+        res["error"] = repr(ex)
+    return res
+
+
+# ------------------------------------------------------------------------------------------------ main
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="f16f8", choices=["f16f8", "fp32x3", "bf16"],
-                    help="f16f8 (default, parity mode): 3x3 convs = 1 fp16 + 2 e4m3 MMAs per product, everything else bf16x3; fp32x3: bf16x3 "
-                         "everywhere (parity mode); bf16: single pass (fast mode, misses the 1e-3 bar)")
-    ap.add_argument("--scenes", type=int, default=SCENES)
+                    help="f16f8 / fp32x3: parity modes (fp32-equivalent split products, 1e-3 bar); bf16: single pass (fast mode, misses the bar)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-stage2", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the configs[1]/[2] sub-objects, the torch GPU baseline and MaskGit")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         return run_reference(args)
+    args.warmup = max(args.warmup, 3)
 
     import torch
     import torch.distributed as dist
     from bevgen_b200 import ops
-    from multi_view_generation.modules.losses.vqperceptual import DummyLoss
-    from multi_view_generation.modules.stage1.vqgan import VQModel
-    from oracle import synth   # weights/input generator only (test infrastructure shared with the parity tests)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    bcast = {"ms": 0.0, "bytes": 0}
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        t = torch.ones(1, device=dev)
+        dist.all_reduce(t)                     # NCCL communicator set-up + first-collective cost stays out of the broadcast stopwatch
+        torch.cuda.synchronize()
 
-    # ---- model: weights generated on rank 0, NCCL-broadcast (weights only; the data path has no collective)
-    dd = synth.vqgan_ddconfig()
-    model = VQModel(dd, DummyLoss(), 1024, 256, (RES, RES), (16, 16), 256, precision=args.precision)
-    if rank == 0:
-        model.load_state_dict(synth.vqgan_state_dict(dd, seed=1))
-    model = model.to(dev).eval()
-    bcast_ms = 0.0
+    # ---- model: weights generated on rank 0 only, NCCL-broadcast (weights + integer layout buffers; the data path has no collective)
+    model = build_model(args.precision, dev, load_weights=(rank == 0))
     if world > 1:
         from bevgen_b200.sharding import broadcast_module_weights
+        dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        broadcast_module_weights(model, src=0)
+        bcast["bytes"] = broadcast_module_weights(model, src=0)
         torch.cuda.synchronize()
-        bcast_ms = (time.perf_counter() - t0) * 1e3
+        bcast["ms"] = (time.perf_counter() - t0) * 1e3
 
-    n_img = args.scenes * CAMS
-    x_host = synth.image_batch(n_img, 3, RES, RES, seed=100 + rank).pin_memory()
-    x_dev = x_host.to(dev)
-    rec_host = torch.empty((n_img, 3, RES, RES), dtype=torch.float32).pin_memory()
-    idx_host = torch.empty((n_img * 256,), dtype=torch.int64).pin_memory()
+    batch_host = host_batch(SCENES, rank)
+    batch_dev = model.batch_to_device(batch_host)
+    n_img = SCENES * CAMS
+    gen_host = torch.empty((SCENES, CAMS, 3, RES, RES), dtype=torch.float32).pin_memory()
+    rec_host = torch.empty_like(gen_host).pin_memory()
+    h2d = sum(v.numel() * v.element_size() for v in batch_host.values() if torch.is_tensor(v))
+    d2h = gen_host.numel() * 4 + rec_host.numel() * 4 + 4
+    last = {}
 
     def step_resident():
-        quant, _, (_, _, idx) = model.encode(x_dev, None)
-        return model.decode(quant), idx
+        last["out"] = model.test_step(batch_dev, 0)
 
-    from bevgen_b200.host_pipeline import RoundTripPipeline
-    pipe = RoundTripPipeline(model, dev, x_host)
-
-    def step_e2e():     # every step uploads its pinned input and downloads its result; the copies ride on side streams (host_pipeline.py)
-        pipe.submit(x_host, rec_host, idx_host, next_x_host=x_host)
+    def step_e2e():          # host tensors in (one async upload inside test_step), generated + reconstructed images and the loss back on the host
+        out = model.test_step(batch_host, 0)
+        gen_host.copy_(out["gen"], non_blocking=True)
+        rec_host.copy_(out["rec"], non_blocking=True)
+        last["loss"] = float(model.last_test_loss)          # device -> host read of the step's metric (synchronises the step)
+        last["out"] = out
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, finalize=None):
+    def timed(fn, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         w0 = time.time()
         e0.record()
         for _ in range(steps):
             fn()
-        if finalize is not None:
-            finalize()          # the timed stream waits for the last result copy
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -209,120 +336,67 @@ def main():
         sampler.start()
         time.sleep(0.3)
     ops.Stats.reset()
+    smp = model.transformer.sampler(SCENES)
+    smp.timing = []                                   # the sampler records CUDA events around its decode loop (launching stream)
     ms, w0, w1 = timed(step_resident, args.steps)
     launches = ops.Stats.launches
-    step_flops = ops.Stats.gemm_flops / args.steps
     clocks = sampler.stop(w0, w1) if rank == 0 else None
     value = world * n_img * args.steps / (ms / 1e3)
+    decode_ms = [a.elapsed_time(b) for a, b in smp.timing]
+    smp.timing = None
 
-    lite = os.environ.get("BENCH_LITE") == "1"     # profiler runs: timed steps only
-    if lite:
-        print(json.dumps({"lite": True, "value": value, "gpu_launches": launches, "ms_per_step": ms / args.steps}), flush=True)
-        return
-    for _ in range(2):
-        step_e2e()
-    pipe.drain()
-    ms_e2e, _, _ = timed(step_e2e, args.steps, finalize=pipe.drain)
+    step_e2e()
+    ms_e2e, _, _ = timed(step_e2e, args.steps)
     e2e_value = world * n_img * args.steps / (ms_e2e / 1e3)
-
-    # ---- per-launch CUDA-event timing of the dominant kernel (tcgen05 implicit GEMM), on the launching stream
-    gemm_ms, gemm_fl, pairs = 0.0, 0.0, []
-    if rank == 0:
-        def timer(kind, launch, flops):
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            launch()
-            b.record()
-            pairs.append((a, b, flops))
-        ops.Stats.timer = timer
-        step_resident()
-        ops.Stats.timer = None
-        torch.cuda.synchronize()
-        gemm_ms = sum(a.elapsed_time(b) for a, b, _ in pairs)
-        gemm_fl = sum(f for _, _, f in pairs)
-    if world > 1:
-        dist.barrier()
+    check = self_check(model, batch_dev, last["out"], rank)
+    e2e_host_ok = bool(torch.isfinite(gen_host).all()) and float(gen_host.max()) <= 1.0
 
     if rank != 0:
         if world > 1:
+            dist.barrier()
             dist.destroy_process_group()
         return
 
     sustained, burst, hbm, how = peaks()
-    MULT = {"fp32x3": 3, "f16f8": 2, "bf16": 1}
-    agg_achieved = gemm_fl / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
-    # dominant kernel = the launch shape with the largest total time (here: conv_fused 128->128 3x3 at 256x256 over 96 images)
-    groups = {}
-    for a, b, f in pairs:
-        g = groups.setdefault(round(f), [0.0, 0])
-        g[0] += a.elapsed_time(b)
-        g[1] += 1
-    dom_flops, (dom_ms, dom_n) = max(groups.items(), key=lambda kv: kv[1][0]) if groups else (0, (0.0, 0))
-    achieved = dom_flops / (dom_ms / dom_n / 1e3) / 1e12 if dom_n else 0.0
-    # DRAM traffic of that launch from the committed ncu capture (profiles/r01b_conv_fused2_f16f8_ncu_full_summary.json): 3.60 GB read + 3.18 GB written
-    dom_traffic = 6.78e9 if abs(dom_flops - 2.0 * n_img * 256 * 256 * 128 * 128 * 9) < 1e6 and n_img == 96 else None
+    dec_ms = statistics.mean(decode_ms) if decode_ms else float("nan")
+    algo = algo_bytes_decode(SCENES)
+    achieved = algo / (dec_ms / 1e3) / 1e9
+    packed = smp.bytes_per_batch()
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": {"f16f8": "fp16 + 2 x e4m3 split product in the 3x3 convs, bf16x3 elsewhere (fp32-equivalent, fp32 accumulate)",
-                  "fp32x3": "bf16x3 (fp32-equivalent split product, fp32 accumulate)", "bf16": "bf16"}[args.precision],
+        "dtype": {"f16f8": "fp32-equivalent split products (fp16 + e4m3 residual planes / bf16x3, fp32 accumulate), fp16 KV cache",
+                  "fp32x3": "bf16x3 split products (fp32-equivalent, fp32 accumulate), fp16 KV cache", "bf16": "bf16"}[args.precision],
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "images_per_gpu_per_step": n_img, "precision": args.precision,
-                   "l2": "working set (3.2 GB fp32 per 128-ch 256x256 activation) exceeds the 126 MB L2; no explicit flush",
-                   "parallelism": f"scene-sharded x{world} (weights NCCL broadcast {bcast_ms:.1f} ms, no data-path collective)"},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4,
-                "d2h_bytes_per_step": rec_host.numel() * 4 + idx_host.numel() * 8, "ms_per_step": ms_e2e / args.steps},
+        "config": {**CONFIG, "parallelism": f"scene-sharded x{world} (16 scenes per GPU), weights broadcast once, no data-path collective"},
+        "precision": args.precision,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
+                "api": "Net2NetTransformer.test_step(host batch dict) + gen/rec/loss copied to pinned host memory", "host_result_ok": e2e_host_ok},
         "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "conv_fused_kernel + gemm_tc_kernel (tcgen05 implicit-GEMM family: every conv / 1x1 / attention product of the step)",
-                     "dominant_launch": f"3x3 conv 128->128 at 256x256 over {n_img} images: {dom_flops / 1e12:.3f} TFLOP algorithmic per launch, "
-                                        f"{dom_n} launches/step, {dom_ms / max(dom_n, 1):.3f} ms each (CUDA events, launching stream)",
-                     "achieved": achieved, "peak": sustained, "unit": "TFLOP/s", "frac": achieved / sustained,
-                     "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({how})", "traffic": dom_traffic,
-                     "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r01b_conv_fused2_f16f8_ncu_full_summary.json "
-                                       "(algorithmic bytes: 3.22 GB fp32 in + 3.22 GB fp32 out)",
-                     # tensor time per algorithmic FLOP relative to one bf16 pass: bf16x3 = 3, f16f8 = 1 fp16 + 2 e4m3 at twice the rate = 2
-                     "executed_mma_multiplier": MULT[args.precision],
-                     "executed_tflops_bf16_equivalent": achieved * MULT[args.precision],
-                     "family_launches_per_step": len(pairs), "family_ms_per_step": gemm_ms, "family_achieved_tflops": agg_achieved,
-                     "family_share_of_step": gemm_ms / (ms / args.steps), "algorithmic_gflop_per_image": step_flops / n_img / 1e9},
+        "self_check": check,
+        "weights_broadcast": {**bcast, "value_including_broadcast": world * n_img * args.steps / ((ms + bcast["ms"]) / 1e3)},
+        "roofline": {"bound": "hbm", "kernel": smp.kernel_name, "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
+                     "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({how})",
+                     "algorithmic_bytes_per_launch": algo / TOKENS if smp.launches_per_token == 1 else algo,
+                     "algorithmic_bytes": f"SURVEY 8d config 4: 556 MB weights x {TOKENS} steps + bf16 KV reads = {algo / 1e12:.3f} TB per {SCENES} scenes",
+                     "decode_loop_ms": dec_ms, "ms_per_token_step": dec_ms / (TOKENS - 1), "share_of_step": dec_ms / (ms / args.steps),
+                     "launches_per_token_step": smp.launches_per_token,
+                     "bytes_in_the_shipped_format": packed, "achieved_in_shipped_format_GBps": packed / (dec_ms / 1e3) / 1e9,
+                     "traffic": smp.ncu_traffic_bytes, "traffic_source": smp.ncu_traffic_source},
     }
-    if world == 1 and not args.no_stage2:
-        try:   # BASELINE configs[2]/[3]: stage-2 teacher-forced forward and KV-cache sampling (reported beside the headline)
-            del model, x_dev
-            torch.cuda.empty_cache()
-            from tools.stage2_perf import run as stage2_run
-            r2 = stage2_run({"bf16": "bf16", "fp32x3": "fp32x3", "f16f8": "f16f8"}[args.precision], B=args.scenes)
-            hbm_peak = hbm
-            line["stage2"] = {
-                "forward_configs2": {"samples_per_s": r2["forward"]["samples_per_s"], "ms_per_batch": r2["forward"]["ms"], "batch": args.scenes,
-                                     "algorithmic_tflops": r2["forward"]["algorithmic_tflops"],
-                                     "attention_layer_ms": r2["attention_layer"]["ms"],
-                                     "attention_tflops_allowed_only": r2["attention_layer"]["allowed_tflops"],
-                                     "attention_tflops_dense_equiv": r2["attention_layer"]["dense_equiv_tflops"]},
-                "sample_configs3": {"images_per_s": r2["sample"]["images_per_s"], "ms_per_batch": r2["sample"]["ms"],
-                                    "ms_per_token_step": r2["sample"]["ms_per_token_step"],
-                                    "roofline": {"bound": "hbm", "achieved": r2["sample"]["achieved_GBps"], "peak": hbm_peak, "unit": "GB/s",
-                                                 "frac": r2["sample"]["achieved_GBps"] / hbm_peak,
-                                                 "algorithmic_GB_per_batch": r2["sample"]["algorithmic_GB"]}},
-                "generate_configs3": r2.get("generate"),
-                "note": "full-size GPT (24 layers, d=1024, 16 heads, L=1792); KV-cache sampling of 16 scenes x 1536 tokens, top_k=100; "
-                        "parity configuration: forward = bf16x3 GEMMs / attention with the MLP GEMMs as f16f8 (when --precision f16f8), "
-                        "decode = bf16x3 weights, fp16 KV cache"}
-        except Exception as ex:  # the headline line must still be printed
-            line["stage2"] = {"error": repr(ex)}
-        try:   # the MaskGit variant's generate at the reference config's size (reported beside the headline)
-            torch.cuda.empty_cache()
-            from tools.maskgit_perf import run as maskgit_run
-            line["maskgit"] = maskgit_run(8, args.precision)
-        except Exception as ex:
-            line["maskgit"] = {"error": repr(ex)}
-    if world == 1 and not args.no_cpu_baseline:
-        rate, cores, sec = cpu_reference_rate(8)
-        line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": f"8 images 256x256, one encode+quantize+decode pass ({sec:.1f} s), torch CPU fp32, {cores} threads"}
+    if not args.no_extras and world == 1:
+        from tools import bench_extras
+        del last["out"]
+        line.update(bench_extras.run(model, batch_dev, args.precision, sustained, hbm))
+    if not args.no_cpu_baseline and world == 1:
+        r = cpu_reference(2, 1)
+        line["cpu_baseline"] = {"value": r["images_per_s"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+                                "sample": (f"reference algorithm (no KV cache), 1 scene: 2 timed iterations of the sample loop ({r['loop_step_s']:.2f} s each) "
+                                           f"extrapolated x1537 + stage-1 measured on 2 images; torch CPU fp32, {r['cores']} threads; EXTRAPOLATED")}
     print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

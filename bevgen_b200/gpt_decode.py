@@ -75,7 +75,14 @@ class GPTSampler:
         self.use_pdl = True              # programmatic dependent launch along the decode chain (bevgen_set_pdl)
         self.graph = None
         self._graph_key = None
+        self._graph_launches = 0
         self.trace = None
+        self.timing = None               # bench hook: a list -> sample() appends a (start, end) CUDA-event pair around its decode loop
+        # bench / roofline metadata of the decode loop
+        self.kernel_name = "decode step = CUDA graph of swap-AB tcgen05 GEMMs + dec_attn_kernel + dec_reduce_* (146 launches per token)"
+        self.launches_per_token = 146
+        self.ncu_traffic_bytes = None
+        self.ncu_traffic_source = "profiles/r01b_decode_step_launches_fp16kv.csv lists the launches; no dram__bytes capture of the whole chain"
 
     # ------------------------------------------------------------------ launches
     def _gemm_t(self, w, xp, n_out, K, part, fin=None):
@@ -207,6 +214,9 @@ class GPTSampler:
         key = (bev_idx.data_ptr(), batch["intrinsics_inv"].data_ptr(), batch["extrinsics_inv"].data_ptr(), float(temperature), top_k, greedy,
                seed, None if forced is None else forced.data_ptr(), None if self.trace is None else self.trace.data_ptr())
         done = 1
+        if self.timing is not None:
+            ev0 = torch.cuda.Event(enable_timing=True)
+            ev0.record()
         if steps > 1:
             self._step(args, temperature, top_k, greedy, seed, forced)    # eager step 1 (also warms every kernel variant up)
             done = 2
@@ -215,16 +225,24 @@ class GPTSampler:
                 self._hold = (bev_idx, batch, forced, self.trace)         # keep the captured buffers alive
                 g = torch.cuda.CUDAGraph()
                 snap = (self.step.clone(), self.cam_idx.clone(), self.tokens.clone())
+                n0 = ops.Stats.launches
                 with torch.cuda.graph(g):
                     self._step(args, temperature, top_k, greedy, seed, forced)
+                self._graph_launches = ops.Stats.launches - n0
+                ops.Stats.launches = n0                                   # capture does not launch
                 # capture does not execute, but be safe if a driver replays it: restore the state
                 self.step.copy_(snap[0]); self.cam_idx.copy_(snap[1]); self.tokens.copy_(snap[2])
                 self.graph, self._graph_key = g, key
             for _ in range(done, steps):
                 self.graph.replay()
+            ops.Stats.launches += (steps - done) * self._graph_launches
         else:
             for _ in range(done, steps):
                 self._step(args, temperature, top_k, greedy, seed, forced)
+        if self.timing is not None:
+            ev1 = torch.cuda.Event(enable_timing=True)
+            ev1.record()
+            self.timing.append((ev0, ev1))
         out = self.cam_idx.clone()
         return (out, self.trace[:steps]) if trace_logits else out
 

@@ -119,8 +119,23 @@ class GPTEngine:
         real = self.nc + self.n_img
         am = cfg.attention_mask.bool()
         self.decode_causal = bool(torch.equal(am[:real, :real], closed[:real, :real]) and not am[:real, real:].any())
+        # Padded geometries (non-square latents: nuScenes-native 14x25 -> L = 2368 with 12 pad tokens, mask_generator.py:197-205; and any
+        # L that is not a multiple of the 128-row attention tile): the forward runs on Lrun = roundup(L, 128) rows per sample.  Rows
+        # beyond the real tokens (the reference's pad tokens + our extension rows) carry the PAD embedding; no real row ever attends to
+        # them (the closed form [cond | causal] holds on the real rows), their own outputs are never read (the reference slices them
+        # off, mingpt_sparse.py:387), so the fused kernel's closed-form mask applies unchanged and S is never materialised.
+        self.Lrun = self.L
+        self.fused_pad = bool(self.decode_causal and not self.causal and self.nc % 128 == 0)
+        if self.fused_pad:
+            self.Lrun = ((self.L + 127) // 128) * 128
         # tiled, pre-scaled fp16 copy for the fused kernel (coalesced 16-byte reads per lane, scale folded into one FFMA per score)
-        self.bias_f16 = None if (self.bias is None or self.L % 128) else ops.tile_attention_bias(self.bias, float(self.dh) ** -0.5)
+        self.bias_f16 = None
+        if self.bias is not None and self.Lrun % 128 == 0:
+            bpad = self.bias
+            if self.Lrun != self.L:
+                bpad = torch.zeros((self.Lrun, self.Lrun), dtype=torch.float32, device=dev)
+                bpad[: self.L, : self.L] = self.bias
+            self.bias_f16 = ops.tile_attention_bias(bpad, float(self.dh) ** -0.5)
         self.fused_attention = True          # tcgen05 flash-style kernel when the geometry allows; composed path otherwise
         self._perm_cache = {}
         self._allowed = float(self.mask_u8.sum().item())      # attended (row, col) pairs: algorithmic attention work
@@ -169,8 +184,8 @@ class GPTEngine:
         d, H, dh = self.d, self.H, self.dh
         if layout is not None:
             fused_cond = None
-        if (self.fused_attention and (layout is None or layout64 is not None) and isinstance(bias, str) and mask is None and self.causal
-                and L % 128 == 0 and self.nc % 128 == 0):
+        if (self.fused_attention and (layout is None or layout64 is not None) and isinstance(bias, str) and mask is None
+                and (self.causal or (self.fused_pad and layout is None)) and L % 128 == 0 and self.nc % 128 == 0):
             x1 = torch.empty((B, L, d), dtype=torch.float32, device=self.dev)
             ops.attn_fused_fwd(qkv[0], qkv[1], B, L, H, d, self.nc, self.bias_f16, y, x1, float(dh) ** -0.5, self.npass,
                                algo_flops=4.0 * B * H * dh * self._allowed, layout64=layout64 if layout is not None else None)
@@ -260,13 +275,14 @@ class GPTEngine:
     @torch.no_grad()
     def forward(self, cam_idx, bev_idx, batch, sampling, return_hidden=False):
         """-> logits fp32 [B, n_img, vocab] in (cam, h, w) order (GPT.forward)."""
-        B, L, d = bev_idx.shape[0], self.L, self.d
-        x = self.embed(cam_idx, bev_idx, batch, sampling)
+        B, d = bev_idx.shape[0], self.d
+        L = self.Lrun if (self.fused_attention and self.layouts is None) else self.L      # padded geometries: see __init__
+        x = self.embed(cam_idx, bev_idx, batch, sampling, nrows=L)
         hidden = []
         for lw in self.layers:
             x = self.block(x, lw, B, L)
             if return_hidden:
-                hidden.append(x)
+                hidden.append(x[:, : self.L])
         fp = self._planes((B, L, d))
         ops.layernorm(x, *self.ln_f, out_hi=fp[0], out_lo=fp[1])
         # head on rows n_cond-1 .. n_cond+n_img-2 only (position p predicts token p+1, :390): a row-shifted 1-tap GEMM

@@ -53,7 +53,11 @@ class RoundTripPipeline:
             self.ev_out.record(self.s_out)
         self.n += 1
 
-    def drain(self):
-        """Make the current stream wait for every outstanding result copy (call before reading the host buffers / stopping a timer)."""
+    def drain(self, block_host: bool = True):
+        """Wait for every outstanding result copy.  The current stream always waits (so a CUDA-event timer recorded after drain()
+        covers the copies); with `block_host` (default) the HOST blocks too, after which the pinned result buffers are safe to read.
+        `block_host=False` is the stream-only variant for timing loops that synchronise later."""
         if self.ev_out is not None:
             torch.cuda.current_stream(self.dev).wait_event(self.ev_out)
+            if block_host:
+                self.ev_out.synchronize()

@@ -1,8 +1,9 @@
 """Multi-GPU plumbing: one process per GPU (torch.distributed), scenes sharded contiguously across ranks, weights broadcast
 once from rank 0 (NCCL over NVLink on GPUs, gloo in CPU tests).  The data path has NO collective: scenes are independent
-(no cross-sample op anywhere on the hot path; GroupNorm / LayerNorm are per sample), and the attention block layout is
-built deterministically from the config on every rank, so the reference's only collective — dist.broadcast(master_layout),
-modules/transformer/sparse_self_attention.py:50-52 — disappears."""
+(no cross-sample op anywhere on the hot path; GroupNorm / LayerNorm are per sample).  The attention block layouts are RNG-free
+only at density = 1.0; for density < 1 they are drawn with torch.multinomial from the global RNG (like the reference), so the
+integer `master_layout` buffers travel with the weights in the same start-up broadcast — the reference's only collective,
+dist.broadcast(master_layout) (modules/transformer/sparse_self_attention.py:50-52), folded into it."""
 import torch
 import torch.distributed as dist
 
@@ -15,11 +16,15 @@ def scene_shard(n_scenes: int, rank: int, world: int):
 
 
 def broadcast_module_weights(module: torch.nn.Module, src: int = 0, bucket_bytes: int = 256 << 20):
-    """Broadcast parameters AND persistent buffers of `module` from `src`, packed into large flat buckets (NVSwitch gives
-    every peer full bandwidth, so buckets are sized for launch latency, not for link count).  Returns bytes sent."""
+    """Broadcast parameters AND buffers (floating point and integer, e.g. `master_layout`) of `module` from `src`, packed into
+    large flat buckets per dtype (NVSwitch gives every peer full bandwidth, so buckets are sized for launch latency, not for
+    link count).  The copies go through `Tensor.copy_` under no_grad (bumping `_version`) and every pre-packed engine below
+    `module` is dropped afterwards (engine_cache.invalidate_all).  Returns bytes sent."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return 0
-    tensors = [p.data for p in module.parameters()] + [b for _, b in module.named_buffers() if b is not None and b.is_floating_point()]
+    from .engine_cache import invalidate_all
+    tensors = list(module.parameters()) + [b for _, b in module.named_buffers() if b is not None]
+    tensors.sort(key=lambda t: str(t.dtype))          # stable: one run of buckets per dtype
     total, i = 0, 0
     while i < len(tensors):
         dtype, dev = tensors[i].dtype, tensors[i].device
@@ -28,13 +33,14 @@ def broadcast_module_weights(module: torch.nn.Module, src: int = 0, bucket_bytes
             group.append(tensors[i])
             nbytes += tensors[i].numel() * tensors[i].element_size()
             i += 1
-        flat = torch.cat([t.reshape(-1) for t in group])
-        dist.broadcast(flat, src=src)
-        o = 0
-        for t in group:
-            t.copy_(flat[o:o + t.numel()].view_as(t))
-            o += t.numel()
+        with torch.no_grad():
+            flat = torch.cat([t.detach().reshape(-1) for t in group])
+            dist.broadcast(flat, src=src)
+            if dist.get_rank() != src:
+                for t, piece in zip(group, flat.split([t.numel() for t in group])):
+                    t.copy_(piece.view_as(t))
         total += nbytes
+    invalidate_all(module)
     return total
 
 

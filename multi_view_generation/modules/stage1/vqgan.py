@@ -7,6 +7,7 @@ checkpoints load unchanged.  All arithmetic runs in the bevgen_b200 kernels; tra
 import torch
 import torch.nn as nn
 
+from bevgen_b200.engine_cache import EngineCacheMixin
 from multi_view_generation import utils
 from multi_view_generation.modules.stage1.model import Decoder, Encoder
 from multi_view_generation.modules.stage1.quantize import VectorQuantizer2 as VectorQuantizer
@@ -18,7 +19,7 @@ except Exception:  # pragma: no cover
     _Base = nn.Module
 
 
-class VQModel(_Base):
+class VQModel(EngineCacheMixin, _Base):
     def __init__(self, ddconfig, lossconfig, n_embed, embed_dim, cam_res, cam_latent_res, cam_emd_dim, geometric_embedding=False,
                  ckpt_path=None, ignore_keys=[], image_key="image", colorize_nlabels=None, monitor=None, remap=None,
                  sane_index_shape=False, denormalize=True, legacy=True, precision="f16f8", **kwargs):
@@ -60,7 +61,7 @@ class VQModel(_Base):
         p = self.quant_conv.weight
         if not p.is_cuda:
             raise RuntimeError("bevgen_b200 VQModel runs on a CUDA device only (no CPU fallback): call .cuda() first")
-        key = (p.device, self.precision, tuple(q._version for q in self.parameters()))
+        key = self._engine_cache_key(p.device, self.precision)       # (data_ptr, _version) of every parameter and buffer
         if self._engine is None or self._engine_key != key:
             sd = {k: v.detach() for k, v in self.state_dict().items() if k != "colorize"}
             self._engine = VQGANEngine(sd, self.ddconfig, self.n_embed, self.embed_dim, device=p.device, precision=self.precision)

@@ -73,7 +73,9 @@ class Net2NetTransformer(_Base):
         _, c_indices = self.encode_to_c(c, batch)
         z_indices = self.expand_all_images(z_indices)
         target = z_indices.reshape(z_indices.shape[0], -1).clone()
-        logits = self.transformer(z_indices, c_indices, batch, sampling=False)
+        # GPT.forward overwrites the last token of its argument with PAD (reference mingpt_sparse.py:328-329): hand it a copy, the
+        # encoder's index tensor may be shared with log_images through the test_step memo
+        logits = self.transformer(z_indices.clone(), c_indices, batch, sampling=False)
         return logits.contiguous(), target.contiguous()
 
     def top_k_logits(self, logits, k):
@@ -105,7 +107,8 @@ class Net2NetTransformer(_Base):
             _, z_indices = self.encode_to_z(self.get_input(self.first_stage_key, batch).to(c.device), batch)
             z_indices = self.expand_all_images(z_indices)                                   # (B, cams, tokens)
             given = torch.full_like(z_indices, -1)
-            given[:, list(partial_decoding_idx), :] = z_indices[:, list(partial_decoding_idx), :]
+            cams = [int(i) for i in partial_decoding_idx]
+            given[:, cams, :] = z_indices[:, cams, :]
             fwd = torch.as_tensor(self.cfg.forward_shuffle_idx, device=c.device, dtype=torch.int64)
             forced = given.reshape(B, -1)[:, fwd].contiguous()                              # decode order
         seed = self.sample_seed if self.sample_seed is not None else int(torch.randint(0, 2 ** 62, (1,)).item())
@@ -120,7 +123,7 @@ class Net2NetTransformer(_Base):
 
     @torch.no_grad()
     def encode_to_z(self, x, batch):
-        quant_z, _, info = self.first_stage_model.encode(x, batch)
+        quant_z, _, info = self._memo_call("z", x, lambda: self.first_stage_model.encode(x, batch))
         indices = self.permuter(info[2].view(quant_z.shape[0], -1))
         return quant_z, indices
 
@@ -128,7 +131,7 @@ class Net2NetTransformer(_Base):
     def encode_to_c(self, c, batch):
         if self.downsample_cond_size > -1:
             c = F.interpolate(c, size=(self.downsample_cond_size, self.downsample_cond_size))
-        quant_c, _, [_, _, indices] = self.cond_stage_model.encode(c, batch)
+        quant_c, _, (_, _, indices) = self._memo_call("c", c, lambda: self.cond_stage_model.encode(c, batch))
         return quant_c, indices.view(c.shape[0], -1)
 
     @torch.no_grad()
@@ -138,6 +141,9 @@ class Net2NetTransformer(_Base):
         return self.first_stage_model.decode_indices(index.reshape(-1), bhwc)      # get_codebook_entry + decode, NHWC throughout
 
     def get_input(self, key, batch):
+        memo = getattr(self, "_step_memo", None)
+        if memo is not None and memo.get(("in", key, id(batch[key]))) is not None:
+            return memo[("in", key, id(batch[key]))]
         x = batch[key]
         if x.dtype == torch.double or x.dtype == torch.uint8:
             x = x.float()
@@ -146,7 +152,28 @@ class Net2NetTransformer(_Base):
             if len(x.shape) == 4:
                 x = x[None, ...]
             x = self.combine_all_images(x)
-        return x.contiguous()
+        x = x.contiguous()
+        if memo is not None:
+            memo[("in", key, id(batch[key]))] = x
+        return x
+
+    def _memo_call(self, tag, x, fn):
+        """Within one test_step the reference encodes the same images twice (shared_step and log_images); the results are identical, so
+        the second call returns the first one's tensors.  Outside test_step (no memo) every call computes."""
+        memo = getattr(self, "_step_memo", None)
+        if memo is None:
+            return fn()
+        key = (tag, x.data_ptr(), tuple(x.shape))
+        if key not in memo:
+            memo[key] = fn()
+        return memo[key]
+
+    def batch_to_device(self, batch):
+        """One asynchronous upload of the tensors the hot path reads (pinned host memory -> no staging copy); everything else in the
+        dict (cam_name, sample_token, ...) is passed through untouched."""
+        dev = self._dev()
+        keys = (self.first_stage_key, self.cond_stage_key, "intrinsics_inv", "extrinsics_inv")
+        return {k: (v.to(dev, non_blocking=True) if (k in keys and torch.is_tensor(v) and not v.is_cuda) else v) for k, v in batch.items()}
 
     def get_xc(self, batch, N=None):
         x, c = self.get_input(self.first_stage_key, batch), self.get_input(self.cond_stage_key, batch)
@@ -163,11 +190,18 @@ class Net2NetTransformer(_Base):
         return sum(F.cross_entropy(l.view(-1, l.shape[-1]), t.view(-1)) for l, t in zip(logits, target)) / len(logits)
 
     def test_step(self, batch, batch_idx=0):
-        loss = self.shared_step(batch, batch_idx)
-        if hasattr(self, "log") and _Base is not torch.nn.Module:
-            self.log("test/loss", loss, prog_bar=True, on_step=False, on_epoch=True)
-        self.last_test_loss = loss
-        return self.log_images(batch, generate_only=True, top_k=self.top_k)
+        """generate.py's per-batch call (reference :378-384): teacher-forced loss, then log_images(generate_only=True).  The batch is
+        uploaded once and the stage-1 encodes are shared between the two halves."""
+        batch = self.batch_to_device(batch)
+        self._step_memo = {}
+        try:
+            loss = self.shared_step(batch, batch_idx)
+            if hasattr(self, "log") and _Base is not torch.nn.Module:
+                self.log("test/loss", loss, prog_bar=True, on_step=False, on_epoch=True)
+            self.last_test_loss = loss
+            return self.log_images(batch, generate_only=True, top_k=self.top_k)
+        finally:
+            self._step_memo = None
 
     @torch.no_grad()
     def log_images(self, batch, temperature=None, top_k=None, callback=None, generate_only=False, **kwargs):
@@ -180,10 +214,36 @@ class Net2NetTransformer(_Base):
         _, c_indices = self.encode_to_c(c, batch)
         zshape = quant_z.shape
         rec = util.denormalize_tensor(self.decode_to_img(z_indices, zshape), keep_tensor=True)
+        partial_decoding_idx = self._draw_partial_decoding_idx()
         index_sample = self.sample(self.expand_all_images(z_indices)[:, :0], c_indices, batch,
                                    temperature=temperature if temperature is not None else 1.0, sample=True,
-                                   top_k=top_k if top_k is not None else 100)
+                                   top_k=top_k if top_k is not None else 100,
+                                   callback=callback if callback is not None else (lambda k: None),
+                                   partial_decoding_idx=partial_decoding_idx)
         gen = util.denormalize_tensor(self.decode_to_img(self.combine_all_images(index_sample), zshape), keep_tensor=True)
         gt = util.denormalize_tensor(x, keep_tensor=True)
+        gen = self.expand_all_images(gen)
+        if partial_decoding_idx is not None:
+            # reference :526-529: the cameras that kept their ground-truth tokens are framed in green (3 px, colour (0, 249, 0));
+            # the text overlays drawn on the GT panels (:530-533, third-party image_utils) are visualisation only and not reproduced
+            kept = gen[:, partial_decoding_idx]
+            colour = torch.tensor([0.0, 249.0 / 255.0, 0.0], device=gen.device, dtype=gen.dtype).view(1, 1, 3, 1, 1)
+            frame = torch.ones(kept.shape[-2:], dtype=torch.bool, device=gen.device)
+            frame[3:-3, 3:-3] = False
+            gen[:, partial_decoding_idx] = torch.where(frame, colour.expand_as(kept), kept)
         log.info("Generating images took %.3f s", time.time() - start)
-        return {"gen": self.expand_all_images(gen), "rec": self.expand_all_images(rec), "gt": self.expand_all_images(gt)}
+        return {"gen": gen, "rec": self.expand_all_images(rec), "gt": self.expand_all_images(gt)}
+
+    def _draw_partial_decoding_idx(self):
+        """Which cameras keep their ground-truth tokens (reference log_images :503-515): mode 2 = one or two random cameras, mode 3 =
+        [0] or [0, 2] with equal probability, mode 4 = [3, 0, 2], any other truthy value = one random camera; None when off."""
+        if not self.partial_decoding:
+            return None
+        n = self.transformer.cfg.num_cams
+        if self.partial_decoding == 2:
+            return torch.randint(n, (int(torch.randint(1, 3, ()).item()),))
+        if self.partial_decoding == 3:
+            return torch.tensor([0]) if torch.rand(()).item() > 0.5 else torch.tensor([0, 2])
+        if self.partial_decoding == 4:
+            return torch.tensor([3, 0, 2])
+        return torch.randint(n, (1,))

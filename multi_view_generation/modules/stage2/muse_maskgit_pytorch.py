@@ -10,6 +10,7 @@ from typing import Callable, Iterable, Optional
 import torch
 from torch import nn
 
+from bevgen_b200.engine_cache import EngineCacheMixin, fingerprint
 from multi_view_generation.modules.transformer.mingpt_sparse import GPTConfig, get_bev_grid
 
 
@@ -52,7 +53,7 @@ class TransformerBlocks(nn.Module):
         self.norm = LayerNorm(dim)
 
 
-class TransformerMultiView(nn.Module):
+class TransformerMultiView(EngineCacheMixin, nn.Module):
     def __init__(self, *, num_tokens, dim, seq_len, dim_out=None, self_cond=False, add_mask_id=False, cfg: Optional[GPTConfig] = None,
                  precision="f16f8", **kwargs):
         super().__init__()
@@ -90,8 +91,8 @@ class TransformerMultiView(nn.Module):
         p = self.to_logits.weight
         if not p.is_cuda:
             raise RuntimeError("bevgen_b200 MaskGit runs on a CUDA device only (no CPU fallback): call .cuda() first")
-        cw = None if critic is None else tuple(q._version for q in critic.parameters())
-        key = (p.device, self.precision, tuple(q._version for q in self.parameters()), cw)
+        cw = None if critic is None else fingerprint(critic)
+        key = (self._engine_cache_key(p.device, self.precision), cw)
         if self._engine is None or self._engine_key != key:
             sd = {k: v.detach() for k, v in self.state_dict().items()}
             cr = None if critic is None else {"weight": critic.weight.detach(), "bias": critic.bias.detach()}

@@ -9,6 +9,7 @@ import logging
 import torch
 import torch.nn as nn
 
+from bevgen_b200.engine_cache import EngineCacheMixin
 from bevgen_b200.geometry_torch import bev_grid as _bev_grid
 from bevgen_b200.geometry_torch import generate_grid  # noqa: F401
 from bevgen_b200.geometry_torch import image_plane as _image_plane
@@ -62,7 +63,7 @@ class Block(nn.Module):
                                  nn.Dropout(cfg.resid_pdrop))
 
 
-class GPT(nn.Module):
+class GPT(EngineCacheMixin, nn.Module):
     def __init__(self, cfg: GPTConfig, precision="f16f8", **kwargs):
         super().__init__()
         self.cfg = cfg
@@ -106,7 +107,7 @@ class GPT(nn.Module):
         p = self.head.weight
         if not p.is_cuda:
             raise RuntimeError("bevgen_b200 GPT runs on a CUDA device only (no CPU fallback): call .cuda() first")
-        key = (p.device, self.precision, tuple(q._version for q in self.parameters()))
+        key = self._engine_cache_key(p.device, self.precision)       # parameters AND buffers (master_layout) by (data_ptr, _version)
         if self._engine is None or self._engine_key != key:
             sd = {k: v.detach() for k, v in self.state_dict().items()}
             # one layout per layer (each CustomSparseSelfAttention draws / loads its own master_layout, reference :143-154,177)

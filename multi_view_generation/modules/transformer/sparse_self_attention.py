@@ -2,8 +2,9 @@
 
 Only the state that callers touch is kept: the per-head block layout buffer `master_layout` (logged by
 Net2NetTransformer.on_test_start and present in checkpoints).  The arithmetic — QK^T + camera bias (added BEFORE the
-1/sqrt(d_head) scale) + mask + softmax + PV — runs in the bevgen_b200 attention kernels; the layout is built identically on
-every rank from the config, so the reference's `dist.broadcast(master_layout)` (:50-52) is unnecessary.
+1/sqrt(d_head) scale) + mask + softmax + PV — runs in the bevgen_b200 attention kernels.  At density = 1.0 the layout is RNG-free
+and identical on every rank; at density < 1 it is drawn from the global RNG, and the reference's `dist.broadcast(master_layout)`
+(:50-52) happens inside bevgen_b200.sharding.broadcast_module_weights, which ships integer buffers with the weights.
 """
 import torch.nn as nn
 

@@ -204,6 +204,78 @@ def golden_gpt():
             print("gpt sample4", torch.stack(toks, 1).tolist())
 
 
+def golden_vqgan_config2():
+    """BASELINE configs[1] shapes: ch=128 VQGAN at 256x256.  RGB: the first 8 images of the benchmark's 96-image batch (synth.image_batch(96,
+    seed=100)); BEV tokenizer (7 channels): 2 scenes.  h / rec are stored sub-sampled (channel / pixel strides), idx in full."""
+    for name, cin, n, seed_x in (("config2_rgb", 3, 8, 100), ("config2_bev", 7, 2, 300)):
+        dd = synth.vqgan_ddconfig(in_channels=cin, ch=128)
+        sd = synth.vqgan_state_dict(dd, seed=1)
+        enc, dec, vq, qc, pqc = _ref_vqgan(dd, sd)
+        x = synth.image_batch(96 if cin == 3 else 16, cin, 256, 256, seed=seed_x)[:n].contiguous()
+        if cin == 7:
+            x = (x > 0).float()                      # BEV segmentation maps are {0, 1} (SURVEY 8b batch schema)
+        with torch.no_grad():
+            h = qc(enc(x))
+            quant, _, (_, _, idx) = vq(h)
+            rec = dec(pqc(vq.get_codebook_entry(idx, (n, 16, 16, 256))))
+        d = torch.cdist(h.permute(0, 2, 3, 1).reshape(-1, 256), sd["quantize.embedding.weight"])
+        top2 = d.topk(2, largest=False).values
+        np.savez_compressed(OUT / f"vqgan_{name}.npz", h_sub=h[:, ::8].numpy(), idx=idx.numpy().astype(np.int32),
+                            rec_sub=rec[:, :, ::8, ::8].numpy(), rec_row=rec[:, :, 100].numpy(), x_crc=crc(x),
+                            rec_absmax=np.float64(rec.abs().max().item()), rec_mean=np.float64(rec.double().mean().item()),
+                            gap=(top2[:, 1] - top2[:, 0]).numpy(), min_gap=np.float64((top2[:, 1] - top2[:, 0]).min().item()))
+        print("vqgan", name, tuple(rec.shape), "min top-2 gap", (top2[:, 1] - top2[:, 0]).min().item())
+
+
+def _gpt_case_golden(m, name, kw, B, Bgen, layouts_from_reference=False, seed_in=4):
+    """One reference GPT forward (teacher-forced + sampling) on the first B samples of a Bgen-sample seeded input batch."""
+    torch.manual_seed(0)
+    cfg = m.GPTConfig(**kw)
+    model = m.GPT(cfg).eval()
+    sd = synth.gpt_state_dict(_sizes(cfg), seed=2)
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected and all("master_layout" in k or k == "bev_grid" for k in missing), (missing, unexpected)
+    cam, bev, batch = synth.stage2_inputs(Bgen, cfg.num_cams, cfg.num_cam_tokens, cfg.num_cond_tokens, cfg.vocab_size, cfg.cond_vocab_size, seed=seed_in)
+    cam, bev, batch = cam[:B].contiguous(), bev[:B].contiguous(), {k: v[:B].contiguous() for k, v in batch.items()}
+    hid = []
+    hooks = [blk.register_forward_hook(lambda mod, i, o: hid.append(o[0].detach())) for blk in model.blocks]
+    with torch.no_grad():
+        logits_tf = model(cam.clone(), bev, batch, sampling=False)
+        hid_tf = [h.clone() for h in hid]
+        hid.clear()
+        logits_s = model(cam.clone(), bev, batch, sampling=True)
+    for h in hooks:
+        h.remove()
+    n = logits_tf.shape[1]
+    rows = np.unique(np.concatenate([np.arange(0, n, 61), [0, 1, n - 2, n - 1]])).astype(np.int64)
+    extra = {}
+    if layouts_from_reference:
+        lay = torch.stack([blk.attention.sparse_self_attention.master_layout for blk in model.blocks])       # (layers, heads, nb, nb)
+        extra = dict(layout_bits=np.packbits(lay.numpy().astype(bool)), layout_shape=np.array(lay.shape),
+                     layout_density=np.float64(lay.float().mean().item()))
+    np.savez_compressed(OUT / f"gpt_{name}.npz", rows=rows, logits_tf=logits_tf[:, rows].numpy(), logits_s=logits_s[:, rows].numpy(),
+                        logits_tf_mean=np.float64(logits_tf.double().mean().item()), logits_tf_absmax=np.float64(logits_tf.abs().max().item()),
+                        hidden0_rows=hid_tf[0][:, ::97].numpy(), hidden_last_rows=hid_tf[-1][:, ::97].numpy(), cam_crc=crc(cam), B=np.int64(B),
+                        Bgen=np.int64(Bgen), **extra)
+    print("gpt", name, tuple(logits_tf.shape), float(logits_tf.abs().max()), {k: float(v) for k, v in extra.items() if k == "layout_density"})
+
+
+def golden_gpt_full():
+    """BASELINE configs[2] model: 24 layers, d=1024, 16 heads, L=1792 - the first 2 samples of the benchmark's B=16 seeded batch."""
+    _gpt_case_golden(ref_import.stage2(), "full24", {**GPT_KW, "num_layers": 24}, 2, 16, seed_in=0)
+
+
+def golden_gpt_variants():
+    """SURVEY 8f-2 / 8f-4 pinned to the reference: block-sparse layouts of density 0.25 and 0.5 DRAWN BY THE REFERENCE (per layer, per head;
+    mask_generator.py:217-228) and stored with the logits; 3-camera Argoverse rig; AR decoder on the nuScenes-native 14x25 latents (L=2368,
+    12 pad tokens)."""
+    m = ref_import.stage2()
+    _gpt_case_golden(m, "small_density25", {**GPT_SMALL, "density": 0.25}, 2, 2, layouts_from_reference=True)
+    _gpt_case_golden(m, "small_density50", {**GPT_SMALL, "density": 0.5}, 1, 1, layouts_from_reference=True)
+    _gpt_case_golden(m, "small_argo3", {**GPT_SMALL, "num_cams": 3, "cam_names": "ARGOVERSE_FRONT_CAMERAS", "dataset": "ARGOVERSE"}, 2, 2)
+    _gpt_case_golden(m, "small_nusc14x25", {**GPT_SMALL, "cam_latent_res": (14, 25), "cam_res": (224, 400)}, 1, 1)
+
+
 MASKGIT_DEPTH = 2
 
 
@@ -280,3 +352,9 @@ if __name__ == "__main__":
         golden_gptconfig()
     if "gpt" in which:
         golden_gpt()
+    if "vqgan_config2" in which:
+        golden_vqgan_config2()
+    if "gpt_full" in which:
+        golden_gpt_full()
+    if "gpt_variants" in which:
+        golden_gpt_variants()

@@ -7,7 +7,7 @@ import torch
 
 from bevgen_b200.gpt_config import GPTConfig
 from oracle import gpt_oracle, synth, vqgan_oracle
-from tests.cases import GPT_CASES, GPT_SMALL, VQGAN_CASES, gpt_sizes
+from tests.cases import GPT_CASES, GPT_SMALL, GPT_VARIANTS, VQGAN_CASES, golden_layouts, gpt_sizes, gpt_variant_inputs
 
 
 def crc(t):
@@ -44,6 +44,44 @@ def test_vqgan_oracle(name, golden_dir):
     np.testing.assert_allclose(h.numpy(), g["h"], rtol=0, atol=2e-5)
     assert np.array_equal(idx.numpy(), g["idx"])
     np.testing.assert_allclose(rec.numpy(), g["rec"], rtol=0, atol=2e-5)
+
+
+def test_vqgan_oracle_at_benchmark_resolution(golden_dir):
+    """BASELINE configs[1] shape (ch=128, 256x256): the first 2 of the golden's 8 images (GroupNorm is per image, so a prefix is exact)."""
+    g = np.load(golden_dir / "vqgan_config2_rgb.npz")
+    dd = synth.vqgan_ddconfig(in_channels=3, ch=128)
+    sd = synth.vqgan_state_dict(dd, seed=1)
+    x8 = synth.image_batch(96, 3, 256, 256, seed=100)[:8].contiguous()
+    assert crc(x8) == int(g["x_crc"])
+    x = x8[:2]
+    with torch.no_grad():
+        quant, idx, h = vqgan_oracle.encode(x, sd)
+        rec = vqgan_oracle.decode(quant, sd)
+    np.testing.assert_allclose(h[:, ::8].numpy(), g["h_sub"][:2], rtol=0, atol=2e-5)
+    assert np.array_equal(idx.numpy(), g["idx"][:512])
+    np.testing.assert_allclose(rec[:, :, ::8, ::8].numpy(), g["rec_sub"][:2], rtol=0, atol=3e-5)
+    np.testing.assert_allclose(rec[:, :, 100].numpy(), g["rec_row"][:2], rtol=0, atol=3e-5)
+
+
+@pytest.mark.parametrize("name", ["small_density25", "small_density50", "small_argo3", "small_nusc14x25"])
+def test_gpt_oracle_variants(name, golden_dir):
+    """SURVEY 8f-2 / 8f-4 pinned to the reference: layouts of density < 1 drawn by the reference itself, the 3-camera Argoverse rig,
+    and the nuScenes-native 14x25 latents (L = 2368, 12 pad tokens)."""
+    g = np.load(golden_dir / f"gpt_{name}.npz")
+    cfg, sd, cam, bev, batch = gpt_variant_inputs(name, synth, GPTConfig)
+    assert crc(cam) == int(g["cam_crc"])
+    layouts = golden_layouts(g) if GPT_VARIANTS[name][4] else None
+    geo = gpt_oracle.geo_from_config(cfg)
+    with torch.no_grad():
+        tf, hid = gpt_oracle.forward(sd, geo, cam, bev, batch, sampling=False, return_hidden=True, layouts=layouts)
+        s = gpt_oracle.forward(sd, geo, cam, bev, batch, sampling=True, layouts=layouts)
+    rows = g["rows"]
+    np.testing.assert_allclose(tf[:, rows].numpy(), g["logits_tf"], rtol=0, atol=2e-5)
+    np.testing.assert_allclose(s[:, rows].numpy(), g["logits_s"], rtol=0, atol=2e-5)
+    np.testing.assert_allclose(hid[-1][:, ::97].numpy(), g["hidden_last_rows"], rtol=0, atol=2e-5)
+    if layouts is not None:
+        dense = gpt_oracle.forward(sd, geo, cam, bev, batch, sampling=True)
+        assert (dense - s).abs().max().item() > 1e-2          # the reference-drawn layouts really remove attended positions
 
 
 def _gpt_case(name):

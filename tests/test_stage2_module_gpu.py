@@ -47,12 +47,16 @@ def test_forward_contract_and_oracle(model):
         _, ci, _ = vqgan_oracle.encode(c, sd_c)
     agree = (zi.view(1, -1) == target.cpu()).float().mean().item()
     assert agree > 0.99, agree
+    c_ours = model.encode_to_c(c.cuda(), batch)[1].cpu()
+    assert (ci.view(1, -1) == c_ours).float().mean().item() > 0.99
+    # a18: the transformer leg is checked UNCONDITIONALLY - the oracle is fed the module's own tokens, so a near-tie in the VQ argmin
+    # (asserted > 99 % agreement above) cannot hide a logits error
     geo = gpt_oracle.geo_from_config(model.cfg)
     sd_t = {k: v.cpu() for k, v in model.transformer.state_dict().items()}
     with torch.no_grad():
-        want = gpt_oracle.forward(sd_t, geo, target.cpu().view(1, 6, 256).clone(), ci.view(1, -1), batch, sampling=False)
-    if agree == 1.0 and torch.equal(ci.view(1, -1), model.encode_to_c(c.cuda(), batch)[1].cpu()):
-        assert (logits.cpu() - want).abs().max().item() < 1e-3
+        want = gpt_oracle.forward(sd_t, geo, target.cpu().view(1, 6, 256).clone(), c_ours, batch, sampling=False)
+    err = (logits.cpu() - want).abs().max().item()
+    assert err < 1e-3, err
     loss = model.shared_step(batch)
     assert torch.isfinite(loss)
 
@@ -72,6 +76,37 @@ def test_sample_and_log_images(model):
         assert out[k].shape == (1, 6, 3, 256, 256)
         assert float(out[k].min()) >= 0.0 and float(out[k].max()) <= 1.0
     assert torch.isfinite(model.last_test_loss)
+    # a20: the three image sets against the CPU oracle (reference log_images :489-497,525-527 + bev_utils/util.py:97-118)
+    x, _ = model.get_xc(batch)
+    sd_f = {k: v.cpu() for k, v in model.first_stage_model.state_dict().items()}
+    mean, std = torch.tensor([0.4265, 0.4489, 0.4769]).view(1, 3, 1, 1), torch.tensor([0.2053, 0.2206, 0.2578]).view(1, 3, 1, 1)
+    denorm = lambda t: (t * std + mean).clamp(0, 1)
+    _, z_idx = model.encode_to_z(x.cuda(), batch)
+    with torch.no_grad():
+        rec_want = denorm(vqgan_oracle.decode(vqgan_oracle.get_codebook_entry(z_idx.reshape(-1).cpu(), (6, 16, 16, 256), sd_f), sd_f))
+        gen_want = denorm(vqgan_oracle.decode(vqgan_oracle.get_codebook_entry(toks.reshape(-1).cpu(), (6, 16, 16, 256), sd_f), sd_f))
+    e_rec = (out["rec"][0].cpu() - rec_want).abs().max().item()
+    e_gen = (out["gen"][0].cpu() - gen_want).abs().max().item()      # sample_seed is fixed: test_step drew the same tokens as `toks`
+    e_gt = (out["gt"][0].cpu() - denorm(x)).abs().max().item()
+    print(f"log_images vs oracle: rec {e_rec:.2e} gen {e_gen:.2e} gt {e_gt:.2e}")
+    assert e_rec < 1e-3 and e_gen < 1e-3 and e_gt < 1e-6
+
+
+def test_log_images_partial_decoding_modes(model):
+    """log_images draws partial_decoding_idx like the reference (:503-515) and passes it to sample; mode 4 = cameras [3, 0, 2]
+    keep their ground-truth tokens, i.e. their generated image is the reconstruction (inside the 3-px green frame)."""
+    batch = _batch()
+    model.partial_decoding = 4
+    try:
+        out = model.log_images(batch, generate_only=True, top_k=100)
+    finally:
+        model.partial_decoding = None
+    kept, free = [3, 0, 2], [1, 4, 5]
+    inner = (slice(None), slice(None), slice(None), slice(3, -3), slice(3, -3))
+    assert torch.equal(out["gen"][:, kept][inner], out["rec"][:, kept][inner])
+    assert not torch.equal(out["gen"][:, free][inner], out["rec"][:, free][inner])
+    frame = out["gen"][0, 3, :, 0, :]                       # top row of a kept camera: (0, 249/255, 0)
+    assert torch.allclose(frame, torch.tensor([0.0, 249.0 / 255.0, 0.0], device=frame.device).view(3, 1).expand_as(frame))
 
 
 def test_partial_decoding_keeps_given_cameras_and_is_consistent(model):
