@@ -55,6 +55,24 @@ class EmbedArgs(C.Structure):
                [(n, C.c_int) for n in ("B", "ncam", "hw", "nc", "n_img", "L", "d", "vocab", "pad_last", "bev_embed", "row0", "nrows")]
 
 
+class DecodeLayer(C.Structure):
+    """bevgen_decode_layer (include/bevgen_b200.h): one entry per transformer block, uploaded as a device array."""
+    _fields_ = [(n, C.c_void_p) for n in ("w_qkv", "w_1", "w_2", "b_qkv", "b_1", "b_2", "ln1_g", "ln1_b", "ln2_g", "ln2_b", "k_cache", "v_cache",
+                                          "layout")] + [(n, C.c_float) for n in ("s_qkv", "s_1", "s_2", "pad_")]
+
+
+class DecodeArgs(C.Structure):
+    """bevgen_decode_args (include/bevgen_b200.h)."""
+    _fields_ = [("layers", C.c_void_p), ("n_layers", C.c_int), ("w_head", C.c_void_p), ("s_head", C.c_float), ("lnf_g", C.c_void_p), ("lnf_b", C.c_void_p)] + \
+               [(n, C.c_int) for n in ("batch", "d", "heads", "vocab", "n_cond", "n_img", "lmax", "ncam", "hw", "step_begin", "step_end")] + \
+               [(n, C.c_void_p) for n in ("cam_idx", "x_tok_emb", "x_pos_emb", "img_embed_w", "cam_embed_w", "intrinsics_inv", "extrinsics_inv", "pixel",
+                                          "forward_shuffle_idx", "camera_bias")] + \
+               [("bias_ld", C.c_int), ("scale", C.c_float), ("temperature", C.c_float), ("top_k", C.c_int), ("greedy", C.c_int),
+                ("seed", C.c_ulonglong), ("forced_tokens", C.c_void_p), ("tokens_out", C.c_void_p), ("logits_trace", C.c_void_p),
+                ("layout_block", C.c_int), ("layout_ld", C.c_int), ("workspace", C.c_void_p), ("counters", C.c_void_p),
+                ("debug", C.c_void_p), ("profile", C.c_void_p)]
+
+
 _vp, _i, _f, _ll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
 
 # name -> (restype, argtypes); must list every symbol declared in include/bevgen_b200.h
@@ -99,6 +117,9 @@ SIGNATURES = {
     "bevgen_dec_attention_workspace_floats": (_i, [_i, _i]),
     "bevgen_sample_topk": (_i, [_vp, _i, _ll, _i, _i, _f, _i, _i, C.c_ulonglong, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "bevgen_dec_advance": (_i, [_vp, _vp]),
+    "bevgen_decode_persistent": (_i, [C.POINTER(DecodeArgs), _vp]),
+    "bevgen_decode_workspace": (_i, [_i, _i, _i, _i, C.POINTER(_ll), C.POINTER(_ll)]),
+    "bevgen_pack_decode_linear": (_ll, [_vp, _i, _i, _i, _i, _f, _vp, _vp]),
 }
 
 _lib = None

@@ -7,7 +7,7 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 LIB = HERE / "libbevgen_b200.so"
-SOURCES = ["c_api.cu", "gemm_tc.cu", "elementwise.cu", "vq.cu", "transformer.cu", "decode.cu", "attn_fused.cu", "conv_halo.cu", "conv_fused.cu", "conv_fused2.cu", "conv_fused3.cu", "conv_small.cu", "gemm_pair.cu", "maskgit.cu"]
+SOURCES = ["c_api.cu", "gemm_tc.cu", "elementwise.cu", "vq.cu", "transformer.cu", "decode.cu", "decode_persistent.cu", "attn_fused.cu", "conv_halo.cu", "conv_fused.cu", "conv_fused2.cu", "conv_fused3.cu", "conv_small.cu", "gemm_pair.cu", "maskgit.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--use_fast_math=false",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 

@@ -497,4 +497,43 @@ BEVGEN_API int bevgen_dec_advance(int* step_ptr, void* stream) {
   CHECK_LAUNCH(launch_dec_advance(step_ptr, (cudaStream_t)stream), "dec_advance");
 }
 
+BEVGEN_API int bevgen_decode_workspace(int batch, int d, int heads, int vocab, long long* n_floats, long long* n_counters) {
+  if (!n_floats || !n_counters || batch < 1 || d < 64 || heads < 1 || vocab < 1) return fail(BEVGEN_ERR_ARG, "decode_workspace: bad argument");
+  decode_workspace_sizes(batch, d, heads, vocab, n_floats, n_counters);
+  return BEVGEN_OK;
+}
+
+BEVGEN_API long long bevgen_pack_decode_linear(const float* w, int n_rows, int ld, int d, int n_quarters, float lo_mul, void* out, void* stream) {
+  if (n_rows < 1 || d < 64 || d % 64 != 0 || n_quarters < 1) return fail(BEVGEN_ERR_ARG, "pack_decode_linear: bad shape");
+  const long long bytes = decode_packed_bytes(n_rows, d, n_quarters);
+  if (out == nullptr) return bytes;
+  if (!w) return fail(BEVGEN_ERR_ARG, "pack_decode_linear: null weight");
+  const int rc = launch_pack_decode_linear(w, n_rows, ld, d, n_quarters, lo_mul, out, (cudaStream_t)stream);
+  if (rc != BEVGEN_OK) return fail(rc, "pack_decode_linear: launch failed");
+  return bytes;
+}
+
+BEVGEN_API int bevgen_decode_persistent(const bevgen_decode_args* a, void* stream) {
+  if (!a || !a->layers || !a->w_head || !a->lnf_g || !a->lnf_b || !a->cam_idx || !a->x_tok_emb || !a->x_pos_emb || !a->forward_shuffle_idx ||
+      !a->workspace || !a->counters)
+    return fail(BEVGEN_ERR_ARG, "decode_persistent: null argument");
+  if (a->img_embed_w && (!a->cam_embed_w || !a->intrinsics_inv || !a->extrinsics_inv || !a->pixel))
+    return fail(BEVGEN_ERR_ARG, "decode_persistent: ray embedding inputs missing");
+  if (g_sm_count < 16) return fail(BEVGEN_ERR_ARCH, "decode_persistent: needs at least 16 SMs");
+  static_assert(sizeof(bevgen_decode_layer) == sizeof(DecodeLayer), "bevgen_decode_layer and DecodeLayer must have the same layout");
+  DecodeParams p = {};
+  p.layers = reinterpret_cast<const DecodeLayer*>(a->layers);
+  p.n_layers = a->n_layers;
+  p.w_head = (const uint8_t*)a->w_head; p.s_head = a->s_head; p.lnf_g = a->lnf_g; p.lnf_b = a->lnf_b;
+  p.B = a->batch; p.d = a->d; p.H = a->heads; p.vocab = a->vocab; p.nc = a->n_cond; p.n_img = a->n_img; p.Lmax = a->lmax; p.ncam = a->ncam; p.hw = a->hw;
+  p.step_begin = a->step_begin; p.step_end = a->step_end;
+  p.cam_idx = a->cam_idx; p.x_tok_emb = a->x_tok_emb; p.x_pos_emb = a->x_pos_emb; p.img_embed_w = a->img_embed_w; p.cam_embed_w = a->cam_embed_w;
+  p.I_inv = a->intrinsics_inv; p.E_inv = a->extrinsics_inv; p.pixel = a->pixel; p.fwd = a->forward_shuffle_idx;
+  p.bias = a->camera_bias; p.bias_ld = a->bias_ld; p.scale = a->scale; p.temperature = a->temperature;
+  p.top_k = a->top_k; p.greedy = a->greedy; p.seed = a->seed; p.forced = a->forced_tokens; p.tokens_out = a->tokens_out; p.trace = a->logits_trace;
+  p.lay_blk = a->layout_block; p.lay_ld = a->layout_ld;
+  p.debug = a->debug; p.profile = a->profile;
+  CHECK_LAUNCH(launch_decode_persistent(p, a->workspace, a->counters, g_sm_count, (cudaStream_t)stream), "decode_persistent");
+}
+
 }  // extern "C"

@@ -1,0 +1,1024 @@
+// Persistent KV-cache decode kernel: ONE launch runs every remaining token step of Net2NetTransformer.sample
+// (reference modules/stage2/cond_transformer_multi_view.py:154-227; cached formulation of SURVEY.md §3.4) for up to 16 scenes:
+//   per step:  24 x { LN1 -> QKV linear -> single-row attention over the KV cache (+ append) -> LN2 -> MLP1 + GELU -> MLP2 + residual }
+//              -> LN_f -> head -> top-k / softmax / multinomial -> embedding of the drawn token -> next step.
+// One CTA per SM (148), 16 consumer warps + 1 producer warp.  The path is HBM-bound (per step: every weight once + the whole KV cache),
+// so the design is a BYTE STREAM per SM: every CTA owns a fixed, contiguous slab of each weight matrix (8-row units, packed CTA-major in
+// mma fragment order by bevgen_pack_decode_linear) and a contiguous range of (scene, head, 128-key block) attention units; the producer
+// warp walks that fixed sequence with cp.async.bulk into a 5 x 32 KB shared-memory ring and runs AHEAD of the grid barriers (the bytes
+// do not depend on the activations), so HBM keeps streaming while the consumers synchronise.  Phases are separated by a grid-wide
+// barrier (monotonic counter, release/acquire at gpu scope); the small activation vectors (16 x d fp32) are exchanged through L2.
+//   * linears: mma.sync m16n8k16 (A = the 16 batch rows as fp16 hi + lo planes built in registers straight from the fp32 vector,
+//     B = 8 weight rows per unit as fp16 + an e4m3 residual plane -> 3 bytes / weight at fp32-equivalent accuracy: x_hi*w16 + x_lo*w16
+//     + x_hi*w8/S, fp32 accumulate).  The tensor work per step is 30 GFLOP - tcgen05 would buy nothing here, the bytes are the cost.
+//   * attention: CUDA cores on the staged K^T (64 x 128) / V (128 x 64) fp16 blocks, flash-decoding partials merged per (scene, head)
+//     by the last arriving CTA (ticket), camera-bias row added BEFORE the 1/sqrt(d_head) scale (sparse_self_attention.py:155-168).
+//   * split outputs (MLP2 K-quarters, attention key ranges) are finalised by the last arriver in a FIXED order -> bit-reproducible.
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
+
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace bevgen {
+
+constexpr int DP_CONSUMERS = 512;
+constexpr int DP_THREADS = DP_CONSUMERS + 32;
+constexpr int DP_NSLOT = 5;
+constexpr int DP_SLOT_BYTES = 32768;
+constexpr int DP_KG_BYTES = 1536;                       // one 64-wide k-group of an 8-row unit: 2 x 512 B fp16 + 512 B e4m3
+constexpr int DP_MAXU = 4;                              // units per reduction batch
+constexpr int DP_RED_FLOATS = DP_MAXU * 16 * 128;       // 32 KB
+constexpr int DP_MAXL = 2560;
+constexpr int DP_MAXBH = 8;                             // (scene, head) pairs one CTA may touch in an attention phase
+constexpr int DP_MAXATT = 48;                           // attention units per CTA and phase
+constexpr int DP_PART = 68;                             // floats per attention partial: m, l, -, -, o[64]
+constexpr int DP_MAXPARTS = 24;                         // CTAs sharing one (scene, head)
+constexpr int DP_MAXV = 4096;
+
+struct DpSmem {
+  uint8_t ring[DP_NSLOT][DP_SLOT_BYTES];
+  float red[DP_RED_FLOATS];                             // GEMM cross-warp reduction | attention scratch | sampling scratch
+  float biasrow[DP_MAXL];
+  float2 stat[2][16][16];                               // LayerNorm (sum, sum of squares) per warp and row, double-buffered
+  float red16[16];
+  float att_tab[DP_MAXATT][DP_PART];
+  alignas(8) uint64_t full[DP_NSLOT];
+  alignas(8) uint64_t empty[DP_NSLOT];
+  unsigned int flags[DP_MAXATT];
+  int found;
+  volatile unsigned int rel[DP_NSLOT];                  // unit number last released from each slot (see ring_wait_prev_released)
+  volatile unsigned int att_epoch;                      // attention phases whose closing grid barrier the consumers have passed (producer gate)
+  unsigned int where[4];                                // step, layer, phase of the consumers (diagnostics)
+  unsigned long long fine[8];                           // thread 0: ns in a-frag load | linear ring wait | linear mma + epilogue | attention prologue | attention ring wait | attention unit math | attention merge
+  unsigned int* debug;                                  // optional pinned host buffer: filled before a timeout trap
+};
+
+static_assert(sizeof(DpSmem) <= 232448, "DpSmem exceeds the 227 KB of shared memory a CTA can have on sm_100a");
+
+// ------------------------------------------------------------------------------------------------ small helpers
+__device__ __forceinline__ void bar_consumers() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+__device__ __forceinline__ void bar_group(int g) { asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory"); }
+
+__device__ __forceinline__ void dp_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+               "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ unsigned long long dp_globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(unsigned int* p, unsigned int v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ unsigned long long atom_add_acq_rel_u64(unsigned long long* p, unsigned long long v) {
+  unsigned long long old;
+  asm volatile("atom.acq_rel.gpu.global.add.u64 %0, [%1], %2;" : "=l"(old) : "l"(p), "l"(v) : "memory");
+  return old;
+}
+__device__ __forceinline__ unsigned int atom_add_acq_rel_u32(unsigned int* p, unsigned int v) {
+  unsigned int old;
+  asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+  return old;
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// Before a timeout trap: leave (code, CTA, step, layer, phase, a, b) in the caller's pinned host buffer so the failure can be located
+__device__ __noinline__ void dp_fail(const DpSmem& sm, unsigned int code, unsigned int a, unsigned int b) {
+  volatile unsigned int* dbg = sm.debug;
+  if (dbg != nullptr && atomicCAS(const_cast<unsigned int*>(sm.debug), 0u, code) == 0u) {
+    dbg[1] = blockIdx.x; dbg[2] = sm.where[0]; dbg[3] = sm.where[1]; dbg[4] = sm.where[2]; dbg[5] = a; dbg[6] = b; dbg[7] = threadIdx.x;
+    __threadfence_system();
+  }
+  __trap();
+}
+
+// Grid-wide barrier over the consumer threads of all CTAs (all CTAs are co-resident: one per SM, cooperative launch).  `target` is
+// the running arrival count this CTA expects; the counter only grows (zeroed by the host before the launch).  A protocol bug or a
+// lost CTA becomes a trap after ~4 s instead of a hung GPU.
+__device__ __forceinline__ void grid_sync(DpSmem& sm, unsigned int* counter, unsigned int& target, unsigned int nctas) {
+  bar_consumers();
+  target += nctas;
+  if (threadIdx.x == 0) {
+    red_release_gpu_add(counter, 1u);
+    const unsigned long long t0 = dp_globaltimer();
+    unsigned int polls = 0, seen;
+    while ((seen = ld_acquire_gpu(counter)) < target) {
+      if ((++polls & 1023u) == 0 && dp_globaltimer() - t0 > 4000000000ull) dp_fail(sm, 1u, seen, target);
+    }
+  }
+  bar_consumers();
+}
+
+__device__ __forceinline__ void mma_f16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t e4m3x2_to_f16x2(uint16_t v) {
+  const __half2_raw h = __nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)v, __NV_E4M3);
+  return (uint32_t)h.x | ((uint32_t)h.y << 16);
+}
+// x -> fp16 hi, lo with x ~= hi + lo (22 significant bits)
+__device__ __forceinline__ void split_f16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
+  const __half l0 = __float2half_rn(x0 - __half2float(h0)), l1 = __float2half_rn(x1 - __half2float(h1));
+  hi = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+  lo = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+}
+
+__device__ __forceinline__ void part_range(int U, int& u0, int& u1) {
+  u0 = (int)(((long long)blockIdx.x * U) / gridDim.x);
+  u1 = (int)(((long long)(blockIdx.x + 1) * U) / gridDim.x);
+}
+__device__ __forceinline__ int cta_of_unit(int u, int U) { return (int)((((long long)(u + 1)) * gridDim.x - 1) / U); }
+
+__device__ __forceinline__ float consumers_sum(float v, float* red16) {
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  bar_consumers();
+  if ((threadIdx.x & 31) == 0) red16[threadIdx.x >> 5] = v;
+  bar_consumers();
+  float t = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) t += red16[i];
+  return t;
+}
+__device__ __forceinline__ float consumers_max(float v, float* red16) {
+  for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  bar_consumers();
+  if ((threadIdx.x & 31) == 0) red16[threadIdx.x >> 5] = v;
+  bar_consumers();
+  float t = red16[0];
+#pragma unroll
+  for (int i = 1; i < 16; ++i) t = fmaxf(t, red16[i]);
+  return t;
+}
+
+// mbarrier wait with a wall-clock bound: a ring-protocol bug traps after ~4 s instead of hanging the GPU
+__device__ __forceinline__ void dp_mbar_wait(DpSmem& sm, uint64_t* bar, uint32_t parity, unsigned int code, unsigned int seq) {
+  if (mbar_try_wait(bar, parity)) return;
+  const unsigned long long t0 = dp_globaltimer();
+  unsigned int spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 255u) == 0 && dp_globaltimer() - t0 > 4000000000ull) dp_fail(sm, code, seq, parity);
+  }
+}
+// ring bookkeeping shared by the producer and the consumers: unit number `seq` lives in slot seq % NSLOT, phase (seq / NSLOT) & 1
+__device__ __forceinline__ void ring_wait_full(DpSmem& sm, unsigned int seq) { dp_mbar_wait(sm, &sm.full[seq % DP_NSLOT], (seq / DP_NSLOT) & 1u, 2u, seq); }
+__device__ __forceinline__ void ring_release(DpSmem& sm, unsigned int seq) {
+  sm.rel[seq % DP_NSLOT] = seq;
+  __threadfence_block();
+  mbar_arrive(&sm.empty[seq % DP_NSLOT]);
+}
+// mbarrier parity waits alias modulo 2 rounds.  A single in-order consumer can never be a round early, but the attention phase has four
+// warp groups taking units out of order: a group could test full[slot] for round j + 1 while round j has not even landed, and the
+// parity test would answer with round j - 1's completion.  So a group first waits until the slot's previous occupant (unit seq - NSLOT)
+// has been RELEASED (then round j is over and round j + 2 cannot start before this unit is released): the parity wait is unambiguous.
+__device__ __forceinline__ void ring_wait_prev_released(DpSmem& sm, unsigned int seq) {
+  if (seq < (unsigned)DP_NSLOT) return;
+  const unsigned int want = seq - DP_NSLOT, slot = seq % DP_NSLOT;
+  if (sm.rel[slot] == want) return;
+  const unsigned long long t0 = dp_globaltimer();
+  unsigned int spins = 0;
+  while (sm.rel[slot] != want) {
+    if ((++spins & 4095u) == 0 && dp_globaltimer() - t0 > 4000000000ull) dp_fail(sm, 4u, seq, sm.rel[slot]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ producer
+__device__ void dp_producer(const DecodeParams& p, DpSmem& sm) {
+  unsigned int seq = 0;
+  const int d = p.d, KG = d >> 6;
+  const uint32_t unit_bytes = (uint32_t)KG * DP_KG_BYTES;
+  auto stream_units = [&](const uint8_t* base, int U) {
+    int u0, u1;
+    part_range(U, u0, u1);
+    for (int u = u0; u < u1; ++u, ++seq) {
+      const unsigned int slot = seq % DP_NSLOT;
+      if (seq >= (unsigned)DP_NSLOT) dp_mbar_wait(sm, &sm.empty[slot], ((seq / DP_NSLOT) - 1u) & 1u, 3u, seq);
+      mbar_expect_tx(&sm.full[slot], unit_bytes);
+      dp_bulk_g2s(sm.ring[slot], base + (size_t)u * unit_bytes, unit_bytes, &sm.full[slot]);
+    }
+  };
+  for (int s = p.step_begin; s < p.step_end; ++s) {
+    const int n = p.nc + s, nblk = (n + 127) >> 7;
+    for (int l = 0; l < p.n_layers; ++l) {
+      const DecodeLayer& L = p.layers[l];
+      stream_units(L.w_qkv, 3 * d / 8);
+      {  // attention units: (scene, head, 128-key block)
+        const int U = p.B * p.H * nblk;
+        int u0, u1;
+        part_range(U, u0, u1);
+        if (s > p.step_begin && u1 > u0) {
+          // The blocks hold keys appended during step s - 1 (by any CTA): do not run ahead of the grid barrier that closed attention
+          // phase (s - 1, l).  With 24 layers the ring (5 units) never reaches that far back; tiny models (a few units per step) do.
+          const unsigned int need = (unsigned)(s - 1 - p.step_begin) * (unsigned)p.n_layers + (unsigned)l + 1u;
+          if (sm.att_epoch < need) {
+            const unsigned long long t0 = dp_globaltimer();
+            unsigned int spins = 0;
+            while (sm.att_epoch < need) {
+              if ((++spins & 4095u) == 0 && dp_globaltimer() - t0 > 4000000000ull) dp_fail(sm, 5u, need, sm.att_epoch);
+            }
+          }
+          fence_proxy_async_all();          // generic-proxy stores of other SMs (ordered by the grid barrier) -> this thread's async-proxy reads
+        }
+        for (int u = u0; u < u1; ++u, ++seq) {
+          const unsigned int slot = seq % DP_NSLOT;
+          if (seq >= (unsigned)DP_NSLOT) dp_mbar_wait(sm, &sm.empty[slot], ((seq / DP_NSLOT) - 1u) & 1u, 3u, seq);
+          const int bh = u / nblk, blk = u - bh * nblk;
+          const int cnt = min(128, n - blk * 128);
+          const uint32_t kbytes = 64u * 128u * 2u, vbytes = (uint32_t)cnt * 128u;
+          mbar_expect_tx(&sm.full[slot], kbytes + vbytes);
+          const __half* kc = reinterpret_cast<const __half*>(L.kc) + ((size_t)bh * (p.Lmax >> 7) + blk) * (64 * 128);
+          const __half* vc = reinterpret_cast<const __half*>(L.vc) + ((size_t)bh * p.Lmax + (size_t)blk * 128) * 64;
+          dp_bulk_g2s(sm.ring[slot], kc, kbytes, &sm.full[slot]);
+          dp_bulk_g2s(sm.ring[slot] + kbytes, vc, vbytes, &sm.full[slot]);
+        }
+      }
+      stream_units(L.w_1, 4 * d / 8);
+      stream_units(L.w_2, 4 * (d / 8));
+    }
+    stream_units(p.w_head, p.vpad / 8);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ linear phase (consumers)
+enum { EPI_QKV = 0, EPI_MLP1 = 1, EPI_MLP2 = 2, EPI_HEAD = 3 };
+
+// Loads this warp's 16 x 64 block of the activation vector src[16][ld] (columns col0 + 64 w ...) in mma A-fragment order, optionally
+// LayerNorms the rows (two-pass statistics exchanged through shared memory), and leaves the fp16 hi / lo fragments in registers.
+__device__ __forceinline__ void load_a_frags(const DecodeParams& p, DpSmem& sm, const float* __restrict__ src, int ld, int col0, const float* gamma,
+                                             const float* beta, float* y_out, uint32_t (&ahi)[4][4], uint32_t (&alo)[4][4], unsigned int& lnpar) {
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int KG = p.d >> 6;
+  const bool active = w < KG;
+  if (gamma != nullptr && active && lane < 4) {      // this warp's 64 gamma / beta values (2 x 2 lines): in L1 by the time the statistics are known
+    const float* pf = (lane < 2 ? gamma : beta) + w * 64 + (lane & 1) * 32;
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(pf));
+  }
+  float x[4][8];
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[ks][j] = 0.f;
+    if (active) {
+      const int c = col0 + w * 64 + ks * 16 + 2 * t;
+      if (g < p.B) {
+        const float2 v0 = __ldcg(reinterpret_cast<const float2*>(src + (size_t)g * ld + c));
+        const float2 v1 = __ldcg(reinterpret_cast<const float2*>(src + (size_t)g * ld + c + 8));
+        x[ks][0] = v0.x; x[ks][1] = v0.y; x[ks][4] = v1.x; x[ks][5] = v1.y;
+      }
+      if (g + 8 < p.B) {
+        const float2 v0 = __ldcg(reinterpret_cast<const float2*>(src + (size_t)(g + 8) * ld + c));
+        const float2 v1 = __ldcg(reinterpret_cast<const float2*>(src + (size_t)(g + 8) * ld + c + 8));
+        x[ks][2] = v0.x; x[ks][3] = v0.y; x[ks][6] = v1.x; x[ks][7] = v1.y;
+      }
+    }
+  }
+  if (gamma != nullptr) {
+    // One-pass LayerNorm statistics, shifted by the row's first element (no cancellation in E[(x-K)^2] - E[x-K]^2): every warp
+    // contributes (sum, sum of squares) of its 64 columns, ONE barrier, every thread then adds the d/64 contributions of its two rows.
+    // stat[] is double-buffered (lnpar toggles per call), so no trailing barrier is needed before the next call overwrites it.
+    const float k0 = (g < p.B) ? __ldcg(src + (size_t)g * ld + col0) : 0.f;
+    const float k1 = (g + 8 < p.B) ? __ldcg(src + (size_t)(g + 8) * ld + col0) : 0.f;
+    float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+    if (active) {
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        x[ks][0] -= k0; x[ks][1] -= k0; x[ks][4] -= k0; x[ks][5] -= k0;
+        x[ks][2] -= k1; x[ks][3] -= k1; x[ks][6] -= k1; x[ks][7] -= k1;
+        s0 += (x[ks][0] + x[ks][1]) + (x[ks][4] + x[ks][5]);
+        s1 += (x[ks][2] + x[ks][3]) + (x[ks][6] + x[ks][7]);
+        q0 += (x[ks][0] * x[ks][0] + x[ks][1] * x[ks][1]) + (x[ks][4] * x[ks][4] + x[ks][5] * x[ks][5]);
+        q1 += (x[ks][2] * x[ks][2] + x[ks][3] * x[ks][3]) + (x[ks][6] * x[ks][6] + x[ks][7] * x[ks][7]);
+      }
+    }
+    s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+    q0 += __shfl_xor_sync(0xffffffffu, q0, 1); q0 += __shfl_xor_sync(0xffffffffu, q0, 2);
+    q1 += __shfl_xor_sync(0xffffffffu, q1, 1); q1 += __shfl_xor_sync(0xffffffffu, q1, 2);
+    float2 (*st)[16] = sm.stat[lnpar & 1u];
+    lnpar ^= 1u;
+    if (t == 0) { st[w][g] = make_float2(s0, q0); st[w][g + 8] = make_float2(s1, q1); }
+    bar_consumers();
+    float S0 = 0.f, Q0 = 0.f, S1 = 0.f, Q1 = 0.f;
+    for (int i = 0; i < KG; ++i) {
+      const float2 a = st[i][g], b2 = st[i][g + 8];
+      S0 += a.x; Q0 += a.y; S1 += b2.x; Q1 += b2.y;
+    }
+    const float inv_d = 1.0f / (float)p.d;
+    const float m0 = S0 * inv_d, m1 = S1 * inv_d;                      // mean of (x - K)
+    const float r0 = rsqrtf(fmaxf(Q0 * inv_d - m0 * m0, 0.f) + 1e-5f), r1 = rsqrtf(fmaxf(Q1 * inv_d - m1 * m1, 0.f) + 1e-5f);
+    if (active) {
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const int c = w * 64 + ks * 16 + 2 * t;
+        const float2 ga = __ldg(reinterpret_cast<const float2*>(gamma + c)), gb = __ldg(reinterpret_cast<const float2*>(gamma + c + 8));
+        const float2 ba = __ldg(reinterpret_cast<const float2*>(beta + c)), bb = __ldg(reinterpret_cast<const float2*>(beta + c + 8));
+        x[ks][0] = (x[ks][0] - m0) * r0 * ga.x + ba.x; x[ks][1] = (x[ks][1] - m0) * r0 * ga.y + ba.y;
+        x[ks][4] = (x[ks][4] - m0) * r0 * gb.x + bb.x; x[ks][5] = (x[ks][5] - m0) * r0 * gb.y + bb.y;
+        x[ks][2] = (x[ks][2] - m1) * r1 * ga.x + ba.x; x[ks][3] = (x[ks][3] - m1) * r1 * ga.y + ba.y;
+        x[ks][6] = (x[ks][6] - m1) * r1 * gb.x + bb.x; x[ks][7] = (x[ks][7] - m1) * r1 * gb.y + bb.y;
+        // the normalised vector is needed again (x1 = y + attention): CTA c < KG publishes the 64 columns of its warp c
+        if (y_out != nullptr && (int)blockIdx.x == w) {
+          if (g < p.B) {
+            *reinterpret_cast<float2*>(y_out + (size_t)g * p.d + c) = make_float2(x[ks][0], x[ks][1]);
+            *reinterpret_cast<float2*>(y_out + (size_t)g * p.d + c + 8) = make_float2(x[ks][4], x[ks][5]);
+          }
+          if (g + 8 < p.B) {
+            *reinterpret_cast<float2*>(y_out + (size_t)(g + 8) * p.d + c) = make_float2(x[ks][2], x[ks][3]);
+            *reinterpret_cast<float2*>(y_out + (size_t)(g + 8) * p.d + c + 8) = make_float2(x[ks][6], x[ks][7]);
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    split_f16x2(x[ks][0], x[ks][1], ahi[ks][0], alo[ks][0]);
+    split_f16x2(x[ks][2], x[ks][3], ahi[ks][1], alo[ks][1]);
+    split_f16x2(x[ks][4], x[ks][5], ahi[ks][2], alo[ks][2]);
+    split_f16x2(x[ks][6], x[ks][7], ahi[ks][3], alo[ks][3]);
+  }
+}
+
+// One linear layer: out[b][row] = sum_k act[b][k] * W[row][k] for this CTA's units.  `seq` advances by the units consumed.
+template <int EPI>
+__device__ void linear_phase(const DecodeParams& p, DpSmem& sm, unsigned int& seq, unsigned int& lnpar, const float* src, int src_ld, const float* gamma,
+                             const float* beta, float* y_out, int U, float inv_s, const float* bias, const DecodeLayer* L) {
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  const int d = p.d, KG = d >> 6, units_per_q = d >> 3;
+  int u0, u1;
+  part_range(U, u0, u1);
+  uint32_t ahi[4][4], alo[4][4];
+  int cur_q = -1;
+  unsigned long long tf = dp_globaltimer();
+  auto fine = [&](int k) { if (tid == 0) { const unsigned long long now = dp_globaltimer(); sm.fine[k] += now - tf; tf = now; } };
+  if (EPI != EPI_MLP2) load_a_frags(p, sm, src, src_ld, 0, gamma, beta, y_out, ahi, alo, lnpar);
+  fine(0);
+  for (int ub = u0; ub < u1; ub += DP_MAXU) {
+    const int nb = min(DP_MAXU, u1 - ub);
+    for (int i = 0; i < nb; ++i, ++seq) {
+      const int u = ub + i;
+      if (EPI == EPI_MLP2) {
+        const int q = u / units_per_q;
+        if (q != cur_q) { load_a_frags(p, sm, src, src_ld, q * d, nullptr, nullptr, nullptr, ahi, alo, lnpar); cur_q = q; fine(0); }
+      }
+      ring_wait_full(sm, seq);
+      fine(1);
+      if (w < KG) {
+        const uint8_t* base = sm.ring[seq % DP_NSLOT] + w * DP_KG_BYTES + lane * 16;
+        const uint4 h0 = *reinterpret_cast<const uint4*>(base), h1 = *reinterpret_cast<const uint4*>(base + 512);
+        const uint4 lo = *reinterpret_cast<const uint4*>(base + 1024);
+        // three independent accumulator chains: x_hi * w16, x_lo * w16, x_hi * w8 (the last one scaled by 1 / S afterwards)
+        float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f}, acc2[4] = {0.f, 0.f, 0.f, 0.f};
+        mma_f16(acc0, ahi[0], h0.x, h0.y); mma_f16(acc2, alo[0], h0.x, h0.y);
+        mma_f16(acc1, ahi[0], e4m3x2_to_f16x2((uint16_t)(lo.x & 0xffffu)), e4m3x2_to_f16x2((uint16_t)(lo.x >> 16)));
+        mma_f16(acc0, ahi[1], h0.z, h0.w); mma_f16(acc2, alo[1], h0.z, h0.w);
+        mma_f16(acc1, ahi[1], e4m3x2_to_f16x2((uint16_t)(lo.y & 0xffffu)), e4m3x2_to_f16x2((uint16_t)(lo.y >> 16)));
+        mma_f16(acc0, ahi[2], h1.x, h1.y); mma_f16(acc2, alo[2], h1.x, h1.y);
+        mma_f16(acc1, ahi[2], e4m3x2_to_f16x2((uint16_t)(lo.z & 0xffffu)), e4m3x2_to_f16x2((uint16_t)(lo.z >> 16)));
+        mma_f16(acc0, ahi[3], h1.z, h1.w); mma_f16(acc2, alo[3], h1.z, h1.w);
+        mma_f16(acc1, ahi[3], e4m3x2_to_f16x2((uint16_t)(lo.w & 0xffffu)), e4m3x2_to_f16x2((uint16_t)(lo.w >> 16)));
+        *reinterpret_cast<float4*>(&sm.red[((i * 16 + w) * 32 + lane) * 4]) =
+            make_float4((acc0[0] + acc2[0]) + acc1[0] * inv_s, (acc0[1] + acc2[1]) + acc1[1] * inv_s, (acc0[2] + acc2[2]) + acc1[2] * inv_s,
+                        (acc0[3] + acc2[3]) + acc1[3] * inv_s);
+      }
+      bar_consumers();                      // every warp has consumed the slot (the MMAs depend on the shared-memory loads)
+      if (tid == 0) ring_release(sm, seq);
+    }
+    // ---- epilogue of the batch: element e of unit i -> lane e/4, register e%4 -> (batch row, weight row)
+    for (int idx = tid; idx < nb * 128; idx += DP_CONSUMERS) {
+      const int i = idx >> 7, e = idx & 127;
+      float v = 0.f;
+      for (int ww = 0; ww < KG; ++ww) v += sm.red[(i * 16 + ww) * 128 + e];
+      const int ln = e >> 2, j = e & 3;
+      const int b = (ln >> 2) + ((j & 2) ? 8 : 0), nrow = 2 * (ln & 3) + (j & 1);
+      const int u = ub + i;
+      if (b < p.B) {
+        if (EPI == EPI_QKV) {
+          const int row = u * 8 + nrow;
+          p.QKV[(size_t)b * 3 * d + row] = v + __ldg(bias + row);
+        } else if (EPI == EPI_MLP1) {
+          const int row = u * 8 + nrow;
+          p.Hbuf[(size_t)b * 4 * d + row] = gelu_erf(v + __ldg(bias + row));
+        } else if (EPI == EPI_MLP2) {
+          const int q = u / units_per_q, row = (u - q * units_per_q) * 8 + nrow;
+          p.P2[((size_t)q * 16 + b) * d + row] = v;
+        } else {
+          const int row = u * 8 + nrow;
+          if (row < p.vocab) p.LOGITS[(size_t)b * p.vocab + row] = v;
+        }
+      }
+    }
+    if (EPI == EPI_MLP2) {
+      // the four K-quarters of an 8-row unit live in (up to) four CTAs: the last to arrive adds them in quarter order
+      bar_consumers();
+      if (tid < nb) {
+        const int u = ub + tid, ru = u % units_per_q;
+        const unsigned int tk = atom_add_acq_rel_u32(&p.tick_mlp2[ru], 1u);      // releases the CTA's partials (ordered by the barrier above)
+        sm.flags[tid] = (tk == 3u) ? 1u : 0u;
+        if (tk == 3u) p.tick_mlp2[ru] = 0u;
+      }
+      bar_consumers();
+      for (int idx = tid; idx < nb * 128; idx += DP_CONSUMERS) {
+        const int i = idx >> 7, e = idx & 127;
+        if (!sm.flags[i]) continue;
+        const int b = e >> 3, nrow = e & 7;
+        if (b >= p.B) continue;
+        const int row = ((ub + i) % units_per_q) * 8 + nrow;
+        float v = __ldcg(p.X1 + (size_t)b * d + row) + __ldg(bias + row);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v += __ldcg(p.P2 + ((size_t)q * 16 + b) * d + row);
+        p.X[(size_t)b * d + row] = v;
+      }
+    }
+    bar_consumers();                        // red[] / flags[] are reused by the next batch or phase
+  }
+  fine(2);
+}
+
+// ------------------------------------------------------------------------------------------------ attention phase (consumers)
+__device__ void attention_phase(const DecodeParams& p, DpSmem& sm, unsigned int& seq, const DecodeLayer& L, int s, bool load_bias) {
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  const int d = p.d, H = p.H;
+  const int n = p.nc + s, r = n - 1, nblk = (n + 127) >> 7;
+  const int U = p.B * H * nblk;
+  int u0, u1;
+  part_range(U, u0, u1);
+  const int nun = u1 - u0;
+  unsigned long long tf = dp_globaltimer();
+  auto fine = [&](int k) { if (tid == 0) { const unsigned long long now = dp_globaltimer(); sm.fine[k] += now - tf; tf = now; } };
+  // scratch carved out of red[]
+  float* qs = sm.red;                                  // [MAXBH][64]   q of every touched (scene, head)
+  float* kn = qs + DP_MAXBH * 64;                      // [MAXBH][64]   newest key
+  float* vn = kn + DP_MAXBH * 64;                      // [MAXBH][64]   newest value
+  float* ps = vn + DP_MAXBH * 64;                      // [4][128]      probabilities of the group's block
+  float* pd = ps + 4 * 128;                            // [4][2][128]   partial dot products (two channel halves)
+  float* op = pd + 4 * 2 * 128;                        // [4][4][64]    P.V partials of the four key quarters
+  float* gr = op + 4 * 4 * 64;                         // [4][4]        group reductions
+  if (load_bias) {
+    for (int j = tid; j < n; j += DP_CONSUMERS) sm.biasrow[j] = p.bias ? __ldg(p.bias + (size_t)r * p.bias_ld + j) : 0.f;
+  }
+  const int bh_first = nun > 0 ? u0 / nblk : 0, bh_last = nun > 0 ? (u1 - 1) / nblk : -1;
+  const int nbh = bh_last - bh_first + 1;
+  if (nun > 0) {
+    for (int i = tid; i < nbh * 192; i += DP_CONSUMERS) {
+      const int bi = i / 192, which = (i % 192) >> 6, c = i & 63;
+      const int bh = bh_first + bi, b = bh / H, h = bh - b * H;
+      const int last_u = bh * nblk + nblk - 1;                      // the unit holding the newest key r
+      const bool owns_new = last_u >= u0 && last_u < u1;
+      if (which == 0 || owns_new) {
+        const float v = __ldcg(p.QKV + (size_t)b * 3 * d + which * d + h * 64 + c);
+        if (which == 0) qs[bi * 64 + c] = v;
+        else if (which == 1) {
+          kn[bi * 64 + c] = v;
+          reinterpret_cast<__half*>(L.kc)[(((size_t)bh * (p.Lmax >> 7) + (r >> 7)) * 64 + c) * 128 + (r & 127)] = __float2half_rn(v);
+        } else {
+          vn[bi * 64 + c] = v;
+          reinterpret_cast<__half*>(L.vc)[((size_t)bh * p.Lmax + r) * 64 + c] = __float2half_rn(v);
+        }
+      }
+    }
+    fence_proxy_async_all();             // the appended key / value will be read by cp.async.bulk (async proxy) in the next step
+  }
+  bar_consumers();
+  fine(3);
+  const int grp = w >> 2, tg = tid & 127, wg = w & 3;
+  for (int i = grp; i < nun; i += 4) {
+    const int u = u0 + i, bh = u / nblk, blk = u - bh * nblk, bi = bh - bh_first;
+    const int j0 = blk << 7, cnt = min(128, n - j0);
+    const unsigned int sq = seq + (unsigned)i;
+    ring_wait_prev_released(sm, sq);
+    ring_wait_full(sm, sq);
+    fine(4);
+    __half* Ks = reinterpret_cast<__half*>(sm.ring[sq % DP_NSLOT]);                 // [64 channels][128 keys]
+    __half* Vs = Ks + 64 * 128;                                                     // [cnt keys][64 channels]
+    if (blk == nblk - 1) {               // the staged copy of key r is stale: take it from the freshly computed k / v
+      if (tg < 64) {
+        Ks[tg * 128 + (r - j0)] = __float2half_rn(kn[bi * 64 + tg]);
+        Vs[(r - j0) * 64 + tg] = __float2half_rn(vn[bi * 64 + tg]);
+        fence_proxy_async();             // generic-proxy writes into a slot the async proxy (cp.async.bulk) refills later
+      }
+      bar_group(grp);
+    }
+    // ---- q . K^T: thread = (key pair, channel half); 32 conflict-free half2 loads against 32 q values held in registers
+    {
+      const int kp = tg & 63, ch = tg >> 6;
+      float qr[32];
+      const float4* q4 = reinterpret_cast<const float4*>(qs + bi * 64 + ch * 32);
+#pragma unroll
+      for (int c4 = 0; c4 < 8; ++c4) {
+        const float4 t4 = q4[c4];
+        qr[4 * c4] = t4.x; qr[4 * c4 + 1] = t4.y; qr[4 * c4 + 2] = t4.z; qr[4 * c4 + 3] = t4.w;
+      }
+      const __half2* K2 = reinterpret_cast<const __half2*>(Ks) + (size_t)(ch * 32) * 64 + kp;
+      float ax0 = 0.f, ay0 = 0.f, ax1 = 0.f, ay1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < 32; c += 2) {
+        const float2 ka = __half22float2(K2[c * 64]), kb = __half22float2(K2[(c + 1) * 64]);
+        ax0 = fmaf(qr[c], ka.x, ax0); ay0 = fmaf(qr[c], ka.y, ay0);
+        ax1 = fmaf(qr[c + 1], kb.x, ax1); ay1 = fmaf(qr[c + 1], kb.y, ay1);
+      }
+      *reinterpret_cast<float2*>(pd + (grp * 2 + ch) * 128 + 2 * kp) = make_float2(ax0 + ax1, ay0 + ay1);
+    }
+    bar_group(grp);
+    // ---- scores and block softmax: thread = key
+    float sc = -INFINITY;
+    if (tg < cnt) {
+      sc = ((pd[(grp * 2) * 128 + tg] + pd[(grp * 2 + 1) * 128 + tg]) + sm.biasrow[j0 + tg]) * p.scale;
+      if (L.layout != nullptr) {
+        const int h = bh % H;
+        if (!L.layout[((size_t)h * p.lay_ld + r / p.lay_blk) * p.lay_ld + (j0 + tg) / p.lay_blk]) sc = -INFINITY;
+      }
+    }
+    float m = sc;
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) gr[grp * 4 + wg] = m;
+    bar_group(grp);
+    m = fmaxf(fmaxf(gr[grp * 4], gr[grp * 4 + 1]), fmaxf(gr[grp * 4 + 2], gr[grp * 4 + 3]));
+    const float e = (sc == -INFINITY) ? 0.f : expf(sc - m);
+    ps[grp * 128 + tg] = e;
+    float su = e;
+    for (int o = 16; o; o >>= 1) su += __shfl_xor_sync(0xffffffffu, su, o);
+    bar_group(grp);                       // gr[] max values consumed, ps[] published
+    if (lane == 0) gr[grp * 4 + wg] = su;
+    // ---- P . V: thread = (channel pair, key quarter); rows >= cnt of the slot are stale bytes and must not be touched
+    {
+      const int ja = wg * 32, jb = min(cnt, ja + 32);
+      const __half2* V2 = reinterpret_cast<const __half2*>(Vs) + lane;
+      const float* pr = ps + grp * 128;
+      float ox0 = 0.f, oy0 = 0.f, ox1 = 0.f, oy1 = 0.f;
+      if (jb - ja == 32) {
+#pragma unroll
+        for (int jj = 0; jj < 32; jj += 4) {
+          const float4 p4 = *reinterpret_cast<const float4*>(pr + ja + jj);
+          const float2 v0 = __half22float2(V2[(ja + jj) * 32]), v1 = __half22float2(V2[(ja + jj + 1) * 32]);
+          const float2 v2 = __half22float2(V2[(ja + jj + 2) * 32]), v3 = __half22float2(V2[(ja + jj + 3) * 32]);
+          ox0 = fmaf(p4.x, v0.x, ox0); oy0 = fmaf(p4.x, v0.y, oy0);
+          ox1 = fmaf(p4.y, v1.x, ox1); oy1 = fmaf(p4.y, v1.y, oy1);
+          ox0 = fmaf(p4.z, v2.x, ox0); oy0 = fmaf(p4.z, v2.y, oy0);
+          ox1 = fmaf(p4.w, v3.x, ox1); oy1 = fmaf(p4.w, v3.y, oy1);
+        }
+      } else {
+        for (int j = ja; j < jb; ++j) {
+          const float2 v0 = __half22float2(V2[j * 32]);
+          ox0 = fmaf(pr[j], v0.x, ox0); oy0 = fmaf(pr[j], v0.y, oy0);
+        }
+      }
+      *reinterpret_cast<float2*>(op + (grp * 4 + wg) * 64 + 2 * lane) = make_float2(ox0 + ox1, oy0 + oy1);
+    }
+    bar_group(grp);
+    if (tg < 64)
+      sm.att_tab[i][4 + tg] = (op[(grp * 4) * 64 + tg] + op[(grp * 4 + 1) * 64 + tg]) + (op[(grp * 4 + 2) * 64 + tg] + op[(grp * 4 + 3) * 64 + tg]);
+    if (tg == 0) {
+      sm.att_tab[i][0] = m;
+      sm.att_tab[i][1] = (gr[grp * 4] + gr[grp * 4 + 1]) + (gr[grp * 4 + 2] + gr[grp * 4 + 3]);
+    }
+    bar_group(grp);                       // the slot and the group scratch are free again
+    if (tg == 0) ring_release(sm, sq);
+    fine(5);
+  }
+  seq += (unsigned)nun;
+  bar_consumers();
+  fine(5);
+  // ---- merge the units of each (scene, head) this CTA touched; one warp per pair, 2 channels per lane
+  for (int bi = w; bi < nbh; bi += 16) {
+    const int bh = bh_first + bi, b = bh / H, h = bh - b * H;
+    const int ua = max(u0, bh * nblk), ub = min(u1, (bh + 1) * nblk);
+    float M = -INFINITY;
+    for (int u = ua; u < ub; ++u) M = fmaxf(M, sm.att_tab[u - u0][0]);
+    float Ls = 0.f, o0 = 0.f, o1 = 0.f;
+    for (int u = ua; u < ub; ++u) {
+      const float* tb = sm.att_tab[u - u0];
+      const float wgt = (tb[0] == -INFINITY) ? 0.f : expf(tb[0] - M);
+      Ls += tb[1] * wgt;
+      o0 += tb[4 + lane] * wgt;
+      o1 += tb[4 + 32 + lane] * wgt;
+    }
+    const size_t xi = (size_t)b * d + h * 64;
+    if (ub - ua == nblk) {               // every key block of this (scene, head) was ours
+      p.X1[xi + lane] = __ldcg(p.Y + xi + lane) + o0 / Ls;
+      p.X1[xi + 32 + lane] = __ldcg(p.Y + xi + 32 + lane) + o1 / Ls;
+      continue;
+    }
+    // Shared with other CTAs: leave the merged partial in the slot of our first block and add (1 << slot) << 32 | blocks to the pair's
+    // 64-bit ticket with ONE acq_rel atomic (releases the partial, acquires the others').  Whoever brings the block count to nblk
+    // merges the partials in slot order (the high word says which slots were written): deterministic, no waiting.
+    const int slot = ua - bh * nblk;
+    float* pp = p.ATTP + ((size_t)bh * DP_MAXPARTS + slot) * DP_PART;
+    pp[4 + lane] = o0;
+    pp[4 + 32 + lane] = o1;
+    if (lane == 0) { pp[0] = M; pp[1] = Ls; }
+    __syncwarp();
+    unsigned long long tk = 0ull;
+    if (lane == 0) tk = atom_add_acq_rel_u64(p.tick_att + bh, ((unsigned long long)(1u << slot) << 32) | (unsigned long long)(ub - ua));
+    tk = __shfl_sync(0xffffffffu, tk, 0);
+    tk += ((unsigned long long)(1u << slot) << 32) | (unsigned long long)(ub - ua);
+    if ((unsigned int)(tk & 0xffffffffull) != (unsigned)nblk) continue;
+    unsigned int mask = (unsigned int)(tk >> 32);
+    const float* base = p.ATTP + (size_t)bh * DP_MAXPARTS * DP_PART;
+    float MM = -INFINITY, LL = 0.f, a0 = 0.f, a1 = 0.f;
+    while (mask) {
+      const int i = __ffs(mask) - 1;
+      mask &= mask - 1u;
+      const float mi = __ldcg(base + i * DP_PART), li = __ldcg(base + i * DP_PART + 1);
+      const float x0 = __ldcg(base + i * DP_PART + 4 + lane), x1 = __ldcg(base + i * DP_PART + 4 + 32 + lane);
+      const float Mn = fmaxf(MM, mi);
+      const float wo = (MM == -INFINITY) ? 0.f : expf(MM - Mn), wn = (mi == -INFINITY) ? 0.f : expf(mi - Mn);
+      LL = LL * wo + li * wn;
+      a0 = a0 * wo + x0 * wn;
+      a1 = a1 * wo + x1 * wn;
+      MM = Mn;
+    }
+    p.X1[xi + lane] = __ldcg(p.Y + xi + lane) + a0 / LL;
+    p.X1[xi + 32 + lane] = __ldcg(p.Y + xi + 32 + lane) + a1 / LL;
+    if (lane == 0) p.tick_att[bh] = 0ull;
+  }
+  fine(6);
+}
+
+// ------------------------------------------------------------------------------------------------ sampling + embedding (CTA b < B)
+__device__ __forceinline__ void dp_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4]) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// Same tail as dec_sample_kernel (decode.cu): logits / T, top-k keeping ties with the k-th value, softmax, Philox multinomial | greedy |
+// forced token (cond_transformer_multi_view.py:138-142,200-219).  Returns the token (uniform over the consumer threads).
+__device__ int sample_row(const DecodeParams& p, DpSmem& sm, int b, int s) {
+  const int tid = threadIdx.x, V = p.vocab;
+  float* lg = sm.red;
+  int* hist = reinterpret_cast<int*>(sm.red + DP_MAXV);          // 256 bins of the radix select
+  const float inv_t = 1.0f / p.temperature;
+  for (int i = tid; i < V; i += DP_CONSUMERS) {
+    float v = __ldcg(p.LOGITS + (size_t)b * V + i);
+    if (p.trace != nullptr) p.trace[((size_t)s * p.B + b) * V + i] = v;
+    lg[i] = v * inv_t;
+  }
+  bar_consumers();
+  float thr = -INFINITY;
+  if (p.top_k > 0 && p.top_k < V) {
+    // k-th largest value by a 4-pass, 8-bit radix select on the order-preserving integer image of the floats (exactly the value a
+    // descending sort would leave at position k - 1, so ties with it are kept like the reference's `out < v[..., [-1]]` filter)
+    unsigned int prefix = 0u, known = 0u;
+    int krem = p.top_k;
+    for (int pass = 3; pass >= 0; --pass) {
+      for (int i = tid; i < 256; i += DP_CONSUMERS) hist[i] = 0;
+      bar_consumers();
+      for (int i = tid; i < V; i += DP_CONSUMERS) {
+        const unsigned int u = __float_as_uint(lg[i]);
+        const unsigned int key = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+        if ((key & known) == prefix) atomicAdd(&hist[(key >> (8 * pass)) & 255u], 1);
+      }
+      bar_consumers();
+      if (tid < 32) {                      // lane owns bins 8 lane .. 8 lane + 7; suffix sums run from the top bin down
+        int c[8], local = 0;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { c[e] = hist[tid * 8 + e]; local += c[e]; }
+        int incl = local;                  // elements in this lane's bins and all higher lanes' bins
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_down_sync(0xffffffffu, incl, o);
+          if (tid + o < 32) incl += t;
+        }
+        const int above = incl - local;
+        if (above < krem && krem <= incl) {
+          int acc = above;
+#pragma unroll
+          for (int e = 7; e >= 0; --e) {
+            if (acc + c[e] >= krem) { sm.flags[0] = (unsigned)(tid * 8 + e); sm.flags[1] = (unsigned)(krem - acc); break; }
+            acc += c[e];
+          }
+        }
+      }
+      bar_consumers();
+      prefix |= sm.flags[0] << (8 * pass);
+      known |= 255u << (8 * pass);
+      krem = (int)sm.flags[1];
+    }
+    thr = __uint_as_float((prefix & 0x80000000u) ? (prefix & 0x7fffffffu) : ~prefix);
+  }
+  float m = -INFINITY;
+  for (int i = tid; i < V; i += DP_CONSUMERS) m = fmaxf(m, lg[i]);
+  m = consumers_max(m, sm.red16);
+  const int per = (V + DP_CONSUMERS - 1) / DP_CONSUMERS;
+  float local = 0.f;
+  for (int e = 0; e < per; ++e) {
+    const int i = tid * per + e;
+    if (i < V) {
+      const float pr = (lg[i] >= thr) ? expf(lg[i] - m) : 0.f;
+      lg[i] = pr;
+      local += pr;
+    }
+  }
+  const float total = consumers_sum(local, sm.red16);
+  const long long fz = (p.forced != nullptr) ? p.forced[(size_t)b * p.n_img + s] : -1;
+  int token = 0;
+  if (fz >= 0) {
+    token = (int)fz;
+  } else if (p.greedy) {
+    float best = -1.f;
+    int bi = 0;
+    for (int i = tid; i < V; i += DP_CONSUMERS)
+      if (lg[i] > best) { best = lg[i]; bi = i; }
+    for (int o = 16; o; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    bar_consumers();
+    if ((tid & 31) == 0) { sm.red16[tid >> 5] = best; sm.flags[tid >> 5] = (unsigned)bi; }
+    bar_consumers();
+    best = sm.red16[0]; bi = (int)sm.flags[0];
+    for (int ww = 1; ww < 16; ++ww)
+      if (sm.red16[ww] > best || (sm.red16[ww] == best && (int)sm.flags[ww] < bi)) { best = sm.red16[ww]; bi = (int)sm.flags[ww]; }
+    token = bi;
+  } else {
+    uint32_t rnd[4];
+    dp_philox((uint32_t)s, (uint32_t)b, 0u, 0u, (uint32_t)p.seed, (uint32_t)(p.seed >> 32), rnd);
+    const float u = ((rnd[0] >> 8) + 0.5f) * (1.0f / 16777216.0f) * total;
+    float incl = local;
+    for (int o = 1; o < 32; o <<= 1) {
+      const float tt = __shfl_up_sync(0xffffffffu, incl, o);
+      if ((tid & 31) >= o) incl += tt;
+    }
+    bar_consumers();
+    if ((tid & 31) == 31) sm.red16[tid >> 5] = incl;
+    if (tid == 0) sm.found = V;
+    bar_consumers();
+    float base = 0.f;
+    for (int ww = 0; ww < (tid >> 5); ++ww) base += sm.red16[ww];
+    float run = base + incl - local;
+    for (int e = 0; e < per; ++e) {
+      const int i = tid * per + e;
+      if (i < V && lg[i] > 0.f) {
+        run += lg[i];
+        if (run > u) { atomicMin(&sm.found, i); break; }
+      }
+    }
+    bar_consumers();
+    token = sm.found;
+    if (token >= V) {
+      int last = 0;
+      for (int i = 0; i < V; ++i) if (lg[i] > 0.f) last = i;
+      token = last;
+    }
+  }
+  bar_consumers();
+  return token;
+}
+
+// Embedding of decode-order image token `sdec` (value tok) of scene b -> X[b][:] (mingpt_sparse.py:332-350; same arithmetic as embed_kernel)
+__device__ void embed_row(const DecodeParams& p, DpSmem& sm, int b, int sdec, long long tok) {
+  const int tid = threadIdx.x, d = p.d;
+  const int j = p.fwd[sdec];
+  const int cam = j / p.hw, px = j - cam * p.hw;
+  const float* e = p.x_tok_emb + (size_t)tok * d;
+  const float* pos = p.x_pos_emb + (size_t)j * d;
+  float* out = p.X + (size_t)b * d;
+  if (p.img_embed_w == nullptr) {
+    for (int c = tid; c < d; c += DP_CONSUMERS) out[c] = e[c] + pos[c];
+    return;
+  }
+  const float* I = p.I_inv + ((size_t)b * p.ncam + cam) * 9;
+  const float* E = p.E_inv + ((size_t)b * p.ncam + cam) * 16;
+  const float* pix = p.pixel + (size_t)px * 3;
+  float cv[4], ray[4];
+#pragma unroll
+  for (int rr = 0; rr < 3; ++rr) cv[rr] = I[rr * 3 + 0] * pix[0] + I[rr * 3 + 1] * pix[1] + I[rr * 3 + 2] * pix[2];
+  cv[3] = 1.0f;
+#pragma unroll
+  for (int rr = 0; rr < 4; ++rr) ray[rr] = E[rr * 4 + 0] * cv[0] + E[rr * 4 + 1] * cv[1] + E[rr * 4 + 2] * cv[2] + E[rr * 4 + 3] * cv[3];
+  float gv[2];
+  float ss = 0.f;
+  int k = 0;
+  for (int c = tid; c < d; c += DP_CONSUMERS, ++k) {
+    const float4 wi = __ldg(reinterpret_cast<const float4*>(p.img_embed_w) + c);
+    const float4 wc = __ldg(reinterpret_cast<const float4*>(p.cam_embed_w) + c);
+    const float de = wi.x * ray[0] + wi.y * ray[1] + wi.z * ray[2] + wi.w * ray[3];
+    const float ce = wc.x * E[3] + wc.y * E[7] + wc.z * E[11] + wc.w * E[15];
+    gv[k] = de - ce;
+    ss += gv[k] * gv[k];
+  }
+  ss = consumers_sum(ss, sm.red16);
+  const float inv = 1.0f / (sqrtf(ss) + 1e-7f);
+  k = 0;
+  for (int c = tid; c < d; c += DP_CONSUMERS, ++k) out[c] = (e[c] + gv[k] * inv) + pos[c];
+}
+
+// ------------------------------------------------------------------------------------------------ the kernel
+__global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(const DecodeParams p) {
+  extern __shared__ __align__(1024) uint8_t dp_raw[];
+  DpSmem& sm = *reinterpret_cast<DpSmem*>(dp_raw);
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    for (int i = 0; i < DP_NSLOT; ++i) { mbar_init(&sm.full[i], 1); mbar_init(&sm.empty[i], 1); }
+    fence_barrier_init();
+    sm.debug = p.debug;
+    sm.where[0] = sm.where[1] = sm.where[2] = 0u;
+    for (int i = 0; i < DP_NSLOT; ++i) sm.rel[i] = 0xffffffffu;
+    for (int i = 0; i < 8; ++i) sm.fine[i] = 0ull;
+    sm.att_epoch = 0u;
+  }
+  __syncthreads();
+  if (tid >= DP_CONSUMERS) {
+    if (tid == DP_CONSUMERS) dp_producer(p, sm);
+    return;
+  }
+  unsigned int seq = 0, bar_target = 0, lnpar = 0;
+  const unsigned int G = gridDim.x;
+  const int d = p.d;
+  // X <- embedding of the token drawn at step step_begin - 1 (it is already in the token grid)
+  if ((int)blockIdx.x < p.B) {
+    const int b = blockIdx.x, sdec = p.step_begin - 1;
+    const int j = p.fwd[sdec];
+    embed_row(p, sm, b, sdec, p.cam_idx[((size_t)b * p.ncam + j / p.hw) * p.hw + (j % p.hw)]);
+  }
+  grid_sync(sm, p.barrier, bar_target, G);
+  // optional per-CTA profile: nanoseconds spent in each phase body and in each phase's grid barrier, summed over the launch
+  unsigned long long prof[12];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) prof[i] = 0ull;
+  unsigned long long tmark = dp_globaltimer();
+  auto mark = [&](int slot, unsigned int step, unsigned int layer, unsigned int phase) {
+    if (tid == 0) {
+      const unsigned long long now = dp_globaltimer();
+      prof[slot] += now - tmark;
+      tmark = now;
+      sm.where[0] = step; sm.where[1] = layer; sm.where[2] = phase;
+    }
+  };
+  for (int s = p.step_begin; s < p.step_end; ++s) {
+    for (int l = 0; l < p.n_layers; ++l) {
+      const DecodeLayer& L = p.layers[l];
+      mark(11, s, l, 0);
+      linear_phase<EPI_QKV>(p, sm, seq, lnpar, p.X, d, L.ln1_g, L.ln1_b, p.Y, 3 * d / 8, L.s_qkv, L.b_qkv, &L);
+      mark(0, s, l, 1);
+      grid_sync(sm, p.barrier, bar_target, G);
+      mark(1, s, l, 2);
+      attention_phase(p, sm, seq, L, s, l == 0);
+      mark(2, s, l, 3);
+      grid_sync(sm, p.barrier, bar_target, G);
+      if (tid == 0) sm.att_epoch = (unsigned)(s - p.step_begin) * (unsigned)p.n_layers + (unsigned)l + 1u;      // every CTA's appends of (s, l) are visible
+      mark(3, s, l, 4);
+      linear_phase<EPI_MLP1>(p, sm, seq, lnpar, p.X1, d, L.ln2_g, L.ln2_b, nullptr, 4 * d / 8, L.s_1, L.b_1, &L);
+      mark(4, s, l, 5);
+      grid_sync(sm, p.barrier, bar_target, G);
+      mark(5, s, l, 6);
+      linear_phase<EPI_MLP2>(p, sm, seq, lnpar, p.Hbuf, 4 * d, nullptr, nullptr, nullptr, 4 * (d / 8), L.s_2, L.b_2, &L);
+      mark(6, s, l, 7);
+      grid_sync(sm, p.barrier, bar_target, G);
+      mark(7, s, l, 8);
+    }
+    linear_phase<EPI_HEAD>(p, sm, seq, lnpar, p.X, d, p.lnf_g, p.lnf_b, nullptr, p.vpad / 8, p.s_head, nullptr, nullptr);
+    mark(8, s, p.n_layers, 9);
+    grid_sync(sm, p.barrier, bar_target, G);
+    mark(9, s, p.n_layers, 10);
+    if ((int)blockIdx.x < p.B) {
+      const int b = blockIdx.x;
+      const int token = sample_row(p, sm, b, s);
+      if (tid == 0) {
+        const int j = p.fwd[s];
+        p.cam_idx[((size_t)b * p.ncam + j / p.hw) * p.hw + (j % p.hw)] = token;
+        if (p.tokens_out != nullptr) p.tokens_out[(size_t)b * p.n_img + s] = token;
+      }
+      if (s + 1 < p.step_end) embed_row(p, sm, b, s, token);
+    }
+    mark(10, s, p.n_layers, 11);
+    grid_sync(sm, p.barrier, bar_target, G);
+  }
+  if (tid == 0 && p.profile != nullptr) {
+#pragma unroll
+    for (int i = 0; i < 12; ++i) p.profile[(size_t)blockIdx.x * 20 + i] = prof[i];
+    for (int i = 0; i < 8; ++i) p.profile[(size_t)blockIdx.x * 20 + 12 + i] = sm.fine[i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ weight packing
+// W [n_rows][ld] fp32 (row-major, K contiguous) -> units of 8 rows x d columns in mma B-fragment order (see the header of this file):
+// unit u = quarter * ceil8(n_rows) / 8 + row_unit covers columns quarter * d .. quarter * d + d - 1.  One thread per 16-byte chunk.
+__global__ void pack_decode_linear_kernel(const float* __restrict__ W, int n_rows, int ld, int d, int n_quarters, float lo_mul,
+                                          uint8_t* __restrict__ out, long long n_chunks) {
+  const long long ci = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (ci >= n_chunks) return;
+  const int KG = d >> 6;
+  const int lane = (int)(ci & 31);
+  const int part = (int)((ci >> 5) % 3);
+  const long long ukg = (ci >> 5) / 3;
+  const int kg = (int)(ukg % KG);
+  const long long u = ukg / KG;
+  const int units_per_q = (n_rows + 7) >> 3;
+  const int q = (int)(u / units_per_q), ru = (int)(u % units_per_q);
+  const int g = lane >> 2, t = lane & 3;
+  const int row = ru * 8 + g;
+  const float* wr = W + (size_t)row * ld + (size_t)q * d + kg * 64;
+  const bool ok = row < n_rows;
+  uint4 o;
+  if (part < 2) {
+    uint32_t r[4];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int k0 = (2 * part + e) * 16 + 2 * t;
+      const float a = ok ? wr[k0] : 0.f, b = ok ? wr[k0 + 1] : 0.f, c = ok ? wr[k0 + 8] : 0.f, dd = ok ? wr[k0 + 9] : 0.f;
+      r[2 * e] = (uint32_t)__half_as_ushort(__float2half_rn(a)) | ((uint32_t)__half_as_ushort(__float2half_rn(b)) << 16);
+      r[2 * e + 1] = (uint32_t)__half_as_ushort(__float2half_rn(c)) | ((uint32_t)__half_as_ushort(__float2half_rn(dd)) << 16);
+    }
+    o = make_uint4(r[0], r[1], r[2], r[3]);
+  } else {
+    uint32_t r[4];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const int k0 = ks * 16 + 2 * t;
+      const int kk[4] = {k0, k0 + 1, k0 + 8, k0 + 9};
+      uint32_t v = 0;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float wv = ok ? wr[kk[e]] : 0.f;
+        const float res = (wv - __half2float(__float2half_rn(wv))) * lo_mul;
+        v |= (uint32_t)__nv_cvt_float_to_fp8(res, __NV_SATFINITE, __NV_E4M3) << (8 * e);
+      }
+      r[ks] = v;
+    }
+    o = make_uint4(r[0], r[1], r[2], r[3]);
+  }
+  reinterpret_cast<uint4*>(out)[ci] = o;
+}
+
+int launch_pack_decode_linear(const float* W, int n_rows, int ld, int d, int n_quarters, float lo_mul, void* out, cudaStream_t st) {
+  if (d % 64 != 0 || d < 64 || d > 1024 || n_rows < 1 || n_quarters < 1 || ld < n_quarters * d) return BEVGEN_ERR_ARG;
+  const long long units = (long long)n_quarters * ((n_rows + 7) / 8);
+  const long long chunks = units * (d / 64) * 96;
+  pack_decode_linear_kernel<<<(unsigned)((chunks + 255) / 256), 256, 0, st>>>(W, n_rows, ld, d, n_quarters, lo_mul, (uint8_t*)out, chunks);
+  return cudaGetLastError() == cudaSuccess ? BEVGEN_OK : BEVGEN_ERR_CUDA;
+}
+
+long long decode_packed_bytes(int n_rows, int d, int n_quarters) {
+  return (long long)n_quarters * ((n_rows + 7) / 8) * (d / 64) * DP_KG_BYTES;
+}
+
+void decode_workspace_sizes(int B, int d, int H, int vocab, long long* n_floats, long long* n_counters) {
+  const long long vpad = (vocab + 7) / 8 * 8;
+  *n_floats = 16LL * d * 3 /*X, Y, X1*/ + 16LL * 3 * d /*QKV*/ + 16LL * 4 * d /*H*/ + 4LL * 16 * d /*P2*/ + 16LL * vpad /*LOGITS*/ +
+              (long long)B * H * DP_MAXPARTS * DP_PART;
+  *n_counters = 64 + 2LL * B * H + d / 8;
+}
+
+int launch_decode_persistent(DecodeParams p, float* ws, unsigned int* counters, int sm_count, cudaStream_t st) {
+  const int d = p.d;
+  if (p.B < 1 || p.B > 16 || d % 64 != 0 || d < 64 || d > 1024 || p.H * 64 != d || p.vocab < 1 || p.vocab > DP_MAXV || p.Lmax > DP_MAXL || (p.Lmax & 127) ||
+      p.n_layers < 1 || p.step_begin < 1 || p.step_end > p.n_img || p.step_begin > p.step_end || p.nc + p.n_img > p.Lmax || p.temperature <= 0.f)
+    return BEVGEN_ERR_ARG;
+  if (p.step_begin == p.step_end) return BEVGEN_OK;
+  const int G = sm_count;
+  const int nblk_max = p.Lmax >> 7;
+  if ((p.B * p.H * nblk_max + G - 1) / G + 1 > DP_MAXATT) return BEVGEN_ERR_ARG;
+  if ((p.B * p.H + G - 1) / G + 2 > DP_MAXBH) return BEVGEN_ERR_ARG;
+  p.vpad = (p.vocab + 7) / 8 * 8;
+  float* f = ws;
+  p.X = f; f += 16 * d;
+  p.Y = f; f += 16 * d;
+  p.X1 = f; f += 16 * d;
+  p.QKV = f; f += 16 * 3 * d;
+  p.Hbuf = f; f += 16 * 4 * d;
+  p.P2 = f; f += 4 * 16 * d;
+  p.LOGITS = f; f += 16 * p.vpad;
+  p.ATTP = f;
+  p.barrier = counters;
+  p.tick_att = reinterpret_cast<unsigned long long*>(counters + 64);          // 64-bit tickets (8-byte aligned: the buffer is 256-byte aligned)
+  p.tick_mlp2 = counters + 64 + 2 * p.B * p.H;
+  if (cudaMemsetAsync(counters, 0, sizeof(unsigned int) * (64 + 2 * (size_t)p.B * p.H + d / 8), st) != cudaSuccess) return BEVGEN_ERR_CUDA;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(decode_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DpSmem)) != cudaSuccess) return BEVGEN_ERR_CUDA;
+    configured = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(G);
+  cfg.blockDim = dim3(DP_THREADS);
+  cfg.dynamicSmemBytes = sizeof(DpSmem);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;          // all CTAs co-resident (the grid barrier depends on it)
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (cudaLaunchKernelEx(&cfg, decode_persistent_kernel, p) != cudaSuccess) return BEVGEN_ERR_CUDA;
+  return cudaGetLastError() == cudaSuccess ? BEVGEN_OK : BEVGEN_ERR_CUDA;
+}
+
+}  // namespace bevgen

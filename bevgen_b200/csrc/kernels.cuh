@@ -157,4 +157,48 @@ int launch_dec_sample(const float* part, int ks, long long zstride, int vpad, in
                       float* probs_out, const int* step_ptr, int B, int n_img, int hw, int ncam, cudaStream_t st);
 int launch_dec_advance(int* step, cudaStream_t st);
 
+// ---------------------------------------------------------------- persistent KV-cache decode kernel (decode_persistent.cu)
+struct DecodeLayer {               // one per transformer block, array in DEVICE memory (mirrors bevgen_decode_layer)
+  const uint8_t* w_qkv;            // packed by launch_pack_decode_linear: [3d/8 units][d/64][1536 B]
+  const uint8_t* w_1;              // [4d/8 units]
+  const uint8_t* w_2;              // [4 K-quarters][d/8 units]
+  const float *b_qkv, *b_1, *b_2, *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+  void* kc;                        // fp16 K cache [B][H][Lmax/128][64][128]
+  void* vc;                        // fp16 V cache [B][H][Lmax][64]
+  const uint8_t* layout;           // optional per-head block layout [H][lay_ld][lay_ld]
+  float s_qkv, s_1, s_2, pad_;     // 1 / S of the e4m3 residual planes
+};
+struct DecodeParams {
+  const DecodeLayer* layers;
+  int n_layers;
+  const uint8_t* w_head;
+  float s_head;
+  const float *lnf_g, *lnf_b;
+  int B, d, H, vocab, vpad, nc, n_img, Lmax, ncam, hw;
+  int step_begin, step_end;        // decode-order tokens [step_begin, step_end) are produced; token step_begin - 1 is already in cam_idx
+  long long* cam_idx;              // [B][ncam][hw] token grid (read for the first embedding, written per step)
+  const float *x_tok_emb, *x_pos_emb, *img_embed_w, *cam_embed_w, *I_inv, *E_inv, *pixel;
+  const int* fwd;                  // forward_shuffle_idx
+  const float* bias;               // camera bias [L][bias_ld] (may be NULL)
+  int bias_ld;
+  float scale, temperature;
+  int top_k, greedy;
+  unsigned long long seed;
+  const long long* forced;         // [B][n_img] or NULL
+  long long* tokens_out;           // [B][n_img] or NULL
+  float* trace;                    // [n_img][B][vocab] or NULL
+  int lay_blk, lay_ld;
+  // workspace (filled by the launcher)
+  float *X, *Y, *X1, *QKV, *Hbuf, *P2, *LOGITS, *ATTP;
+  unsigned int *barrier, *tick_mlp2;
+  unsigned long long* tick_att;
+  unsigned int* debug;             // optional pinned HOST buffer (8 uint32, zeroed): timeout diagnostics written before the trap
+  unsigned long long* profile;     // optional [grid][20] nanoseconds per phase (bodies and grid barriers), device memory
+};
+int launch_decode_persistent(DecodeParams p, float* ws, unsigned int* counters, int sm_count, cudaStream_t st);
+int launch_pack_decode_linear(const float* W, int n_rows, int ld, int d, int n_quarters, float lo_mul, void* out, cudaStream_t st);
+long long decode_packed_bytes(int n_rows, int d, int n_quarters);
+void decode_workspace_sizes(int B, int d, int H, int vocab, long long* n_floats, long long* n_counters);
+
+
 }  // namespace bevgen

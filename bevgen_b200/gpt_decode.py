@@ -5,13 +5,19 @@ Equivalence (checked by tests/test_decode_gpu.py against the re
 mask allowed(i,j) = (j < n_cond) or (i >= n_cond and j <= i), the 256 conditioning rows only see each other, so they are
 prefilled once; every generated token then needs one new row attending to the cached keys with one camera-bias row.
 
-Per step (captured once as a CUDA graph and replayed 1535 times, the step counter lives in device memory):
+Default path (batch <= 16, fp16 cache): ONE launch of the persistent kernel (csrc/decode_persistent.cu, bevgen_decode_persistent) runs all
+remaining token steps - one CTA per SM, weights streamed once per step from a 3-byte fragment-ordered format, grid barriers between
+phases, sampling and the next token's embedding inside the kernel.  The per-launch chain below is kept as the fallback for larger
+batches / other cache types and as a cross-check in the tests (`sampler.persistent = False`).
+
+Per step of the fallback (captured once as a CUDA graph and replayed 1535 times, the step counter lives in device memory):
   embed(row) -> [reduce+LayerNorm] -> 24 x { swap-AB tcgen05 GEMM (Wqkv) -> decode attention (append K/V, softmax, P.V, +residual)
   -> LayerNorm -> GEMM (W1) -> reduce+GELU -> GEMM (W2) -> reduce+bias+residual+LayerNorm } -> GEMM (head) -> top-k sample.
 The weight GEMMs stream each weight matrix exactly once per step (HBM-bound: weights are the 128-row MMA operand, the 16
 batch rows are the N=16 operand); split-K spreads every matrix over ~100 CTAs.
 """
 import ctypes as C
+import math
 
 import torch
 
@@ -73,16 +79,121 @@ class GPTSampler:
         self.fuse_finalize = False       # split-K finalize inside the GEMMs (one tail CTA) measured slower than separate reduce kernels
         self.fuse_ln2 = True             # ln2 applied by the last head CTA of the decode-attention kernel
         self.use_pdl = True              # programmatic dependent launch along the decode chain (bevgen_set_pdl)
+        self.persistent = bool(B <= 16 and kvt == torch.float16)      # one persistent launch for all token steps
+        self._pk = None
         self.graph = None
         self._graph_key = None
         self._graph_launches = 0
         self.trace = None
         self.timing = None               # bench hook: a list -> sample() appends a (start, end) CUDA-event pair around its decode loop
         # bench / roofline metadata of the decode loop
-        self.kernel_name = "decode step = CUDA graph of swap-AB tcgen05 GEMMs + dec_attn_kernel + dec_reduce_* (146 launches per token)"
-        self.launches_per_token = 146
         self.ncu_traffic_bytes = None
-        self.ncu_traffic_source = "profiles/r01b_decode_step_launches_fp16kv.csv lists the launches; no dram__bytes capture of the whole chain"
+        self.ncu_traffic_source = None
+
+    PROFILE_SLOTS = ("qkv", "qkv_barrier", "attention", "attention_barrier", "mlp1", "mlp1_barrier", "mlp2", "mlp2_barrier", "head", "head_barrier",
+                     "sample_embed", "sample_barrier",
+                     "fine_afrag", "fine_linear_ring_wait", "fine_linear_math", "fine_attn_prologue", "fine_attn_ring_wait", "fine_attn_unit_math", "fine_attn_merge",
+                     "fine_unused")
+
+    def last_profile(self):
+        """Per-phase milliseconds of the last persistent launch (mean over CTAs; the kernel's own %globaltimer marks)."""
+        if not self._pk or "prof" not in self._pk:
+            return None
+        t = self._pk["prof"].double().mean(0) / 1e6
+        return {k: float(v) for k, v in zip(self.PROFILE_SLOTS, t.tolist())}
+
+    def last_failure(self):
+        """(code, cta, step, layer, phase, a, b, thread) left by a timed-out wait of the persistent kernel, or None."""
+        if not self._pk or "dbg" not in self._pk or int(self._pk["dbg"][0]) == 0:
+            return None
+        return tuple(int(v) & 0xffffffff for v in self._pk["dbg"].tolist())
+
+    @property
+    def kernel_name(self):
+        return ("decode_persistent_kernel (one launch for all token steps)" if self.persistent else
+                "decode step = CUDA graph of swap-AB tcgen05 GEMMs + dec_attn_kernel + dec_reduce_* (146 launches per token)")
+
+    @property
+    def launches_per_token(self):
+        return 1.0 / max(self.eng.n_img - 1, 1) if self.persistent else 146
+
+    # ------------------------------------------------------------------ persistent kernel
+    def _pack_linear(self, w, n_quarters=1):
+        """fp32 [rows][ld] -> the kernel's 3-byte format (fp16 plane + e4m3 plane of (w - fp16(w)) * 2^e), bevgen_pack_decode_linear."""
+        lib, e = _lib.init(), self.eng
+        w = w.detach().to(e.dev, torch.float32).contiguous()
+        rows, ld = w.shape
+        amax = float(w.abs().max())
+        ex = 0 if amax == 0.0 else min(max(19 - math.floor(math.log2(amax)), -20), 40)      # max |residual| * 2^ex <= 256 (e4m3 saturates at 448)
+        lo_mul = 2.0 ** ex
+        nbytes = lib.bevgen_pack_decode_linear(None, rows, ld, e.d, n_quarters, lo_mul, None, None)
+        if nbytes <= 0:
+            _lib.check(int(nbytes), "pack_decode_linear")
+        out = torch.empty(int(nbytes), dtype=torch.uint8, device=e.dev)
+        ops.Stats.launches += 1
+        rc = lib.bevgen_pack_decode_linear(_ptr(w), rows, ld, e.d, n_quarters, lo_mul, _ptr(out), _stream())
+        if rc != nbytes:
+            _lib.check(int(rc), "pack_decode_linear")
+        return out, 1.0 / lo_mul
+
+    def _build_persistent(self):
+        lib, e = _lib.init(), self.eng
+        sd, d = e.sd, e.d
+        keep, arr = [], (_lib.DecodeLayer * len(e.layers))()
+        for i, lw in enumerate(e.layers):
+            p = f"blocks.{i}"
+            wqkv = torch.cat([sd[f"{p}.attention.{n}.weight"].detach().to(e.dev, torch.float32) for n in ("query", "key", "value")], 0)
+            pq, sq = self._pack_linear(wqkv)
+            del wqkv
+            p1, s1 = self._pack_linear(sd[f"{p}.mlp.0.weight"])
+            p2, s2 = self._pack_linear(sd[f"{p}.mlp.2.weight"], n_quarters=4)
+            keep += [pq, p1, p2]
+            a = arr[i]
+            a.w_qkv, a.w_1, a.w_2 = pq.data_ptr(), p1.data_ptr(), p2.data_ptr()
+            a.b_qkv, a.b_1, a.b_2 = lw["bqkv"].data_ptr(), lw["b1"].data_ptr(), lw["b2"].data_ptr()
+            a.ln1_g, a.ln1_b, a.ln2_g, a.ln2_b = lw["ln1"][0].data_ptr(), lw["ln1"][1].data_ptr(), lw["ln2"][0].data_ptr(), lw["ln2"][1].data_ptr()
+            a.k_cache, a.v_cache = self.kc[i].data_ptr(), self.vc[i].data_ptr()
+            a.layout = None if lw.get("layout") is None else lw["layout"].data_ptr()
+            a.s_qkv, a.s_1, a.s_2 = sq, s1, s2
+        ph, sh = self._pack_linear(sd["head.weight"])
+        layers_dev = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(e.dev)
+        nf, ncnt = C.c_longlong(), C.c_longlong()
+        _lib.check(lib.bevgen_decode_workspace(self.B, d, e.H, e.vocab, C.byref(nf), C.byref(ncnt)), "decode_workspace")
+        ws = torch.zeros(nf.value, dtype=torch.float32, device=e.dev)
+        cnt = torch.zeros(ncnt.value, dtype=torch.int32, device=e.dev)
+        self._pk = dict(keep=keep, layers=layers_dev, head=ph, s_head=sh, ws=ws, cnt=cnt,
+                        weight_bytes=sum(t.numel() for t in keep) + ph.numel())
+
+    def _run_persistent(self, batch, step_begin, step_end, temperature, top_k, greedy, seed, forced):
+        lib, e = _lib.init(), self.eng
+        if self._pk is None:
+            self._build_persistent()
+        pk = self._pk
+        a = _lib.DecodeArgs()
+        a.layers, a.n_layers = pk["layers"].data_ptr(), len(e.layers)
+        a.w_head, a.s_head, a.lnf_g, a.lnf_b = pk["head"].data_ptr(), pk["s_head"], e.ln_f[0].data_ptr(), e.ln_f[1].data_ptr()
+        a.batch, a.d, a.heads, a.vocab, a.n_cond, a.n_img, a.lmax = self.B, e.d, e.H, e.vocab, e.nc, e.n_img, self.Lmax
+        a.ncam, a.hw, a.step_begin, a.step_end = e.cfg.num_cams, e.cfg.num_cam_tokens, step_begin, step_end
+        a.cam_idx, a.x_tok_emb, a.x_pos_emb = self.cam_idx.data_ptr(), e.x_tok_emb.data_ptr(), e.x_pos_emb.data_ptr()
+        if e.image_embed:
+            a.img_embed_w, a.cam_embed_w = e.img_w.data_ptr(), e.cam_w.data_ptr()
+            a.intrinsics_inv, a.extrinsics_inv, a.pixel = batch["intrinsics_inv"].data_ptr(), batch["extrinsics_inv"].data_ptr(), e.pixel.data_ptr()
+        a.forward_shuffle_idx = e.fwd.data_ptr()
+        a.camera_bias, a.bias_ld = (None, 0) if e.bias is None else (e.bias.data_ptr(), e.L)
+        a.scale, a.temperature, a.top_k, a.greedy, a.seed = float(e.dh) ** -0.5, float(temperature), int(top_k or 0), int(greedy), int(seed) & (2 ** 64 - 1)
+        a.forced_tokens = None if forced is None else forced.data_ptr()
+        a.tokens_out = self.tokens.data_ptr()
+        a.logits_trace = None if self.trace is None else self.trace.data_ptr()
+        a.layout_block = e.layout_block
+        a.layout_ld = 0 if e.layouts is None else e.layouts.shape[-1]
+        a.workspace, a.counters = pk["ws"].data_ptr(), pk["cnt"].data_ptr()
+        if "dbg" not in pk:
+            pk["dbg"] = torch.zeros(8, dtype=torch.int32).pin_memory()           # readable by the host after a time-out trap
+            pk["prof"] = torch.zeros((lib.bevgen_sm_count(), 20), dtype=torch.int64, device=e.dev)
+        pk["dbg"].zero_()
+        a.debug, a.profile = pk["dbg"].data_ptr(), pk["prof"].data_ptr()
+        ops.Stats.launches += 1
+        _lib.check(lib.bevgen_decode_persistent(C.byref(a), _stream()), "decode_persistent")
 
     # ------------------------------------------------------------------ launches
     def _gemm_t(self, w, xp, n_out, K, part, fin=None):
@@ -217,7 +328,11 @@ class GPTSampler:
         if self.timing is not None:
             ev0 = torch.cuda.Event(enable_timing=True)
             ev0.record()
-        if steps > 1:
+        if self.persistent and steps > 1:
+            self._hold = (bev_idx, batch, forced, self.trace)
+            self._run_persistent(batch, 1, steps, temperature, top_k, greedy, seed, forced)
+            done = steps
+        if steps > done and done == 1:
             self._step(args, temperature, top_k, greedy, seed, forced)    # eager step 1 (also warms every kernel variant up)
             done = 2
         if use_graph and steps > done:
@@ -250,7 +365,7 @@ class GPTSampler:
         """Algorithmic HBM bytes of one full sample(): weights streamed once per step + KV cache reads."""
         e = self.eng
         steps = e.n_img if steps is None else steps
-        wbytes = (2 if e.npass == 1 else 4) * (len(e.layers) * 12 * e.d * e.d + e.vocab * e.d)
+        wbytes = (3 if self.persistent else (2 if e.npass == 1 else 4)) * (len(e.layers) * 12 * e.d * e.d + e.vocab * e.d)
         kvb = 2 if self.kv_bf16 else 4        # bf16 / fp16 caches are 2 bytes per element
         kv = sum(len(e.layers) * 2 * (e.nc + t) * e.d * kvb for t in range(1, steps)) * self.B
         return wbytes * steps + kv

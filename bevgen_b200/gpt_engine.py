@@ -39,6 +39,7 @@ class GPTEngine:
         self.use_pair_gemm = use_pair_gemm and self.mlp_f16f8      # QKV / MLP linears on the 2-CTA 256x256 f16f8 GEMM instead of gemm_tc npass = 2
         self.dev = torch.device(device)
         dev, sd = self.dev, state_dict
+        self.sd = state_dict                 # kept by reference: the KV-cache sampler packs its own 3-byte weight format from the fp32 values
         d = cfg.num_embed
         if d % 128 != 0 or d > 1024:
             raise ValueError(f"num_embed={d}: the sm_100a kernels need a multiple of 128, at most 1024")
@@ -173,7 +174,7 @@ class GPTEngine:
         a.img_embed_w = self.img_w.data_ptr() if self.image_embed else None
         a.cam_embed_w = self.cam_w.data_ptr() if self.image_embed else None
         a.forward_shuffle_idx, a.pixel, a.out = self.fwd.data_ptr(), self.pixel.data_ptr(), out.data_ptr()
-        a.B, a.ncam, a.hw, a.nc, a.n_img, a.L, a.d, a.vocab = B, self.cfg.num_cams, self.cfg.num_cam_tokens, self.nc, self.n_img, self.L, self.d, self.cfg.vocab_size
+        a.B, a.ncam, a.hw, a.nc, a.n_img, a.L, a.d, a.vocab = B, self.cfg.num_cams, self.cfg.num_cam_tokens, self.nc, self.n_img, max(self.L, row0 + nrows), self.d, self.cfg.vocab_size
         a.pad_last, a.bev_embed, a.row0, a.nrows = int(not sampling), int(self.bev_embed), row0, nrows
         ops.embed_assemble(a)
         return out

@@ -301,6 +301,57 @@ BEVGEN_API int bevgen_sample_topk(const float* logit_partials, int ks, long long
                                   int n_img, int hw, int ncam, void* stream);
 BEVGEN_API int bevgen_dec_advance(int* step_ptr, void* stream);
 
+/* ---------------------------------------------------------------- persistent KV-cache decode kernel
+ * ONE launch runs decode steps [step_begin, step_end) of Net2NetTransformer.sample (cond_transformer_multi_view.py:154-227) for up to
+ * 16 scenes: per step all transformer blocks (mingpt_sparse.py:240-253 with the single-row attention of sparse_self_attention.py:153-176
+ * over the fp16 KV cache), ln_f + head (:385-391), the top-k / softmax / multinomial tail (:200-219) and the embedding of the drawn token
+ * (:332-350).  One CTA per SM; weights stream once per step from the packed format below; phases are separated by grid barriers.  The
+ * caches must have been prefilled (bevgen_kv_store) and token step_begin - 1 must be in cam_idx.  kv caches are fp16. */
+typedef struct bevgen_decode_layer {
+  const void* w_qkv;                 /* bevgen_pack_decode_linear of [3d][d] (q | k | v rows) */
+  const void* w_1;                   /* of mlp.0.weight [4d][d] */
+  const void* w_2;                   /* of mlp.2.weight [d][4d] with n_quarters = 4 */
+  const float* b_qkv; const float* b_1; const float* b_2;
+  const float* ln1_g; const float* ln1_b; const float* ln2_g; const float* ln2_b;
+  void* k_cache; void* v_cache;      /* this layer's caches, layouts as bevgen_kv_store */
+  const unsigned char* layout;       /* optional block layout [heads][layout_ld][layout_ld] */
+  float s_qkv, s_1, s_2, pad_;       /* 1 / lo_mul of the three packings */
+} bevgen_decode_layer;
+
+typedef struct bevgen_decode_args {
+  const bevgen_decode_layer* layers; /* DEVICE array of n_layers entries */
+  int n_layers;
+  const void* w_head;                /* packed head.weight [vocab][d] */
+  float s_head;
+  const float* lnf_g; const float* lnf_b;
+  int batch, d, heads, vocab, n_cond, n_img, lmax, ncam, hw;
+  int step_begin, step_end;
+  long long* cam_idx;                /* [batch][ncam][hw] */
+  const float* x_tok_emb; const float* x_pos_emb; const float* img_embed_w; const float* cam_embed_w;
+  const float* intrinsics_inv; const float* extrinsics_inv; const float* pixel;
+  const int* forward_shuffle_idx;
+  const float* camera_bias; int bias_ld;
+  float scale, temperature;
+  int top_k, greedy;
+  unsigned long long seed;
+  const long long* forced_tokens;    /* [batch][n_img] decode order, entries >= 0 replace the draw; may be NULL */
+  long long* tokens_out;             /* [batch][n_img] or NULL */
+  float* logits_trace;               /* [n_img][batch][vocab] or NULL */
+  int layout_block, layout_ld;
+  float* workspace;                  /* bevgen_decode_workspace(...) floats */
+  unsigned int* counters;            /* bevgen_decode_workspace(...) uint32 (zeroed by the call) */
+  unsigned int* debug;               /* optional pinned HOST buffer of 8 zeroed uint32: a barrier / ring time-out (4 s) leaves (code, CTA, step, layer, phase, ...) here before trapping */
+  unsigned long long* profile;       /* optional device buffer [sm_count][20]: ns per phase body / grid barrier, summed over the launch */
+} bevgen_decode_args;
+
+BEVGEN_API int bevgen_decode_persistent(const bevgen_decode_args* args, void* stream);
+BEVGEN_API int bevgen_decode_workspace(int batch, int d, int heads, int vocab, long long* n_floats, long long* n_counters);
+/* Weight packing for the kernel above (a bevgen_pack_* entry point of SURVEY 8b): w [n_rows][ld] fp32 -> 8-row x d-column units in
+ * mma.m16n8k16 B-fragment order, fp16 plane + e4m3 plane of (w - fp16(w)) * lo_mul, 3 bytes per weight.  n_quarters > 1 splits the
+ * columns into n_quarters ranges of d (MLP2).  Returns the byte count when out == NULL. */
+BEVGEN_API long long bevgen_pack_decode_linear(const float* w, int n_rows, int ld, int d, int n_quarters, float lo_mul, void* out, void* stream);
+
+
 #ifdef __cplusplus
 }
 #endif

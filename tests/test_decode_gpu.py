@@ -28,6 +28,7 @@ def test_greedy_matches_reference_sampling_loop(golden_dir, use_graph, fuse):
     g = np.load(golden_dir / "gpt_small_sample4.npz")
     cfg, sd, cam, bev, batch, eng, B = _case("small")
     sampler = GPTSampler(eng, B)
+    sampler.persistent = False           # this test pins the per-launch fallback chain (eager / graph, fused / separate reductions)
     sampler.fuse_finalize = fuse
     toks, trace = sampler.sample(bev, batch, greedy=True, steps=4, trace_logits=True, use_graph=use_graph)
     torch.cuda.synchronize()
@@ -37,6 +38,20 @@ def test_greedy_matches_reference_sampling_loop(golden_dir, use_graph, fuse):
     fwd = cfg.forward_shuffle_idx[:4]
     assert np.array_equal(toks.reshape(B, -1)[:, fwd].cpu().numpy(), g["tokens"])
     assert (toks.reshape(B, -1)[:, cfg.forward_shuffle_idx[4:]] == cfg.vocab_size).all()      # untouched positions stay PAD
+
+
+def test_greedy_matches_reference_sampling_loop_persistent(golden_dir):
+    """The same 4 greedy steps through the default path (persistent kernel)."""
+    g = np.load(golden_dir / "gpt_small_sample4.npz")
+    cfg, sd, cam, bev, batch, eng, B = _case("small")
+    sampler = GPTSampler(eng, B)
+    assert sampler.persistent
+    toks, trace = sampler.sample(bev, batch, greedy=True, steps=4, trace_logits=True)
+    torch.cuda.synchronize()
+    err = np.abs(trace.permute(1, 0, 2).cpu().numpy() - g["logits"]).max()
+    assert err < 1e-3, f"logit rows max err {err}"
+    assert np.array_equal(toks.reshape(B, -1)[:, cfg.forward_shuffle_idx[:4]].cpu().numpy(), g["tokens"])
+    assert (toks.reshape(B, -1)[:, cfg.forward_shuffle_idx[4:]] == cfg.vocab_size).all()
 
 
 def test_padded_geometry_decodes_like_the_reference_loop():
