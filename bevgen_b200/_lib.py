@@ -57,13 +57,13 @@ class EmbedArgs(C.Structure):
 
 class DecodeLayer(C.Structure):
     """bevgen_decode_layer (include/bevgen_b200.h): one entry per transformer block, uploaded as a device array."""
-    _fields_ = [(n, C.c_void_p) for n in ("w_qkv", "w_1", "w_2", "b_qkv", "b_1", "b_2", "ln1_g", "ln1_b", "ln2_g", "ln2_b", "k_cache", "v_cache",
+    _fields_ = [(n, C.c_void_p) for n in ("w_qkv", "w_1", "w_2", "c1_qkv", "c2_qkv", "c2_2", "ln1_g", "ln1_b", "c1_1", "c2_1", "k_cache", "v_cache",
                                           "layout")] + [(n, C.c_float) for n in ("s_qkv", "s_1", "s_2", "pad_")]
 
 
 class DecodeArgs(C.Structure):
     """bevgen_decode_args (include/bevgen_b200.h)."""
-    _fields_ = [("layers", C.c_void_p), ("n_layers", C.c_int), ("w_head", C.c_void_p), ("s_head", C.c_float), ("lnf_g", C.c_void_p), ("lnf_b", C.c_void_p)] + \
+    _fields_ = [("layers", C.c_void_p), ("n_layers", C.c_int), ("w_head", C.c_void_p), ("s_head", C.c_float), ("c1_head", C.c_void_p), ("c2_head", C.c_void_p)] + \
                [(n, C.c_int) for n in ("batch", "d", "heads", "vocab", "n_cond", "n_img", "lmax", "ncam", "hw", "step_begin", "step_end")] + \
                [(n, C.c_void_p) for n in ("cam_idx", "x_tok_emb", "x_pos_emb", "img_embed_w", "cam_embed_w", "intrinsics_inv", "extrinsics_inv", "pixel",
                                           "forward_shuffle_idx", "camera_bias")] + \

@@ -514,7 +514,7 @@ BEVGEN_API long long bevgen_pack_decode_linear(const float* w, int n_rows, int l
 }
 
 BEVGEN_API int bevgen_decode_persistent(const bevgen_decode_args* a, void* stream) {
-  if (!a || !a->layers || !a->w_head || !a->lnf_g || !a->lnf_b || !a->cam_idx || !a->x_tok_emb || !a->x_pos_emb || !a->forward_shuffle_idx ||
+  if (!a || !a->layers || !a->w_head || !a->c1_head || !a->c2_head || !a->cam_idx || !a->x_tok_emb || !a->x_pos_emb || !a->forward_shuffle_idx ||
       !a->workspace || !a->counters)
     return fail(BEVGEN_ERR_ARG, "decode_persistent: null argument");
   if (a->img_embed_w && (!a->cam_embed_w || !a->intrinsics_inv || !a->extrinsics_inv || !a->pixel))
@@ -524,7 +524,7 @@ BEVGEN_API int bevgen_decode_persistent(const bevgen_decode_args* a, void* strea
   DecodeParams p = {};
   p.layers = reinterpret_cast<const DecodeLayer*>(a->layers);
   p.n_layers = a->n_layers;
-  p.w_head = (const uint8_t*)a->w_head; p.s_head = a->s_head; p.lnf_g = a->lnf_g; p.lnf_b = a->lnf_b;
+  p.w_head = (const uint8_t*)a->w_head; p.s_head = a->s_head; p.c1_head = a->c1_head; p.c2_head = a->c2_head;
   p.B = a->batch; p.d = a->d; p.H = a->heads; p.vocab = a->vocab; p.nc = a->n_cond; p.n_img = a->n_img; p.Lmax = a->lmax; p.ncam = a->ncam; p.hw = a->hw;
   p.step_begin = a->step_begin; p.step_end = a->step_end;
   p.cam_idx = a->cam_idx; p.x_tok_emb = a->x_tok_emb; p.x_pos_emb = a->x_pos_emb; p.img_embed_w = a->img_embed_w; p.cam_embed_w = a->cam_embed_w;

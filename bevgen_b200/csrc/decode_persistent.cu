@@ -7,12 +7,18 @@
 // mma fragment order by bevgen_pack_decode_linear) and a contiguous range of (scene, head, 128-key block) attention units; the producer
 // warp walks that fixed sequence with cp.async.bulk into a 5 x 32 KB shared-memory ring and runs AHEAD of the grid barriers (the bytes
 // do not depend on the activations), so HBM keeps streaming while the consumers synchronise.  Phases are separated by a grid-wide
-// barrier (monotonic counter, release/acquire at gpu scope); the small activation vectors (16 x d fp32) are exchanged through L2.
-//   * linears: mma.sync m16n8k16 (A = the 16 batch rows as fp16 hi + lo planes built in registers straight from the fp32 vector,
-//     B = 8 weight rows per unit as fp16 + an e4m3 residual plane -> 3 bytes / weight at fp32-equivalent accuracy: x_hi*w16 + x_lo*w16
-//     + x_hi*w8/S, fp32 accumulate).  The tensor work per step is 30 GFLOP - tcgen05 would buy nothing here, the bytes are the cost.
-//   * attention: CUDA cores on the staged K^T (64 x 128) / V (128 x 64) fp16 blocks, flash-decoding partials merged per (scene, head)
-//     by the last arriving CTA (ticket), camera-bias row added BEFORE the 1/sqrt(d_head) scale (sparse_self_attention.py:155-168).
+// barrier (monotonic counter, release/acquire at gpu scope; 1.24 us measured floor, tools/micro).
+//   * activations (16 x d) travel through L2 ALREADY SPLIT into fp16 hi + lo planes in mma A-fragment order: whoever finalises an
+//     output element writes it there, and every CTA fetches the vector it needs with ONE cp.async.bulk (148 CTAs reading the same 64 KB
+//     cost 0.58 us through the TMA engine against 2.7 us with ld.global, tools/micro/decode_micro.cu) followed by 8 shared-memory loads
+//     per lane.  LayerNorm is applied LAZILY: gamma is folded into the packed weights, the linear runs on the raw vector, and the
+//     epilogue applies  rstd_b * (acc - mean_b * c1_n) + c2_n  with c1_n = sum_k gamma_k W_nk, c2_n = bias_n + sum_k beta_k W_nk; the row
+//     statistics come from per-unit partial sums the finalisers leave next to the vector (fixed order -> deterministic).
+//   * linears: mma.sync m16n8k16, A = the 16 batch rows (fp16 hi + lo), B = 8 weight rows per unit as fp16 + an e4m3 residual plane
+//     -> 3 bytes / weight at fp32-equivalent accuracy: x_hi*w16 + x_lo*w16 + x_hi*w8/S, fp32 accumulate (2 cycles / MMA / SM measured).
+//   * attention: CUDA cores on the staged K^T (64 x 128) / V (128 x 64) fp16 blocks with conflict-free half2 loads, flash-decoding
+//     partials merged per (scene, head) by the last arriving CTA (one acq_rel ticket), camera-bias row added BEFORE the 1/sqrt(d_head)
+//     scale (sparse_self_attention.py:155-168).
 //   * split outputs (MLP2 K-quarters, attention key ranges) are finalised by the last arriver in a FIXED order -> bit-reproducible.
 #include <cuda_fp16.h>
 #include <cuda_fp8.h>
@@ -28,29 +34,35 @@ constexpr int DP_NSLOT = 5;
 constexpr int DP_SLOT_BYTES = 32768;
 constexpr int DP_KG_BYTES = 1536;                       // one 64-wide k-group of an 8-row unit: 2 x 512 B fp16 + 512 B e4m3
 constexpr int DP_MAXU = 4;                              // units per reduction batch
-constexpr int DP_RED_FLOATS = DP_MAXU * 16 * 128;       // 32 KB
+constexpr int DP_ACT_BYTES = 65536;                     // one 16 x 1024 activation vector as fp16 hi + lo fragments
 constexpr int DP_MAXL = 2560;
 constexpr int DP_MAXBH = 8;                             // (scene, head) pairs one CTA may touch in an attention phase
 constexpr int DP_MAXATT = 48;                           // attention units per CTA and phase
 constexpr int DP_PART = 68;                             // floats per attention partial: m, l, -, -, o[64]
 constexpr int DP_MAXPARTS = 24;                         // CTAs sharing one (scene, head)
 constexpr int DP_MAXV = 4096;
+// layout of the attention scratch inside DpSmem::act (floats)
+constexpr int DP_A_QS = 0, DP_A_KN = DP_A_QS + DP_MAXBH * 64, DP_A_VN = DP_A_KN + DP_MAXBH * 64, DP_A_PS = DP_A_VN + DP_MAXBH * 64,
+              DP_A_PD = DP_A_PS + 4 * 128, DP_A_OP = DP_A_PD + 4 * 2 * 128, DP_A_GR = DP_A_OP + 4 * 4 * 64, DP_A_TAB = DP_A_GR + 16,
+              DP_A_BIAS = DP_A_TAB + DP_MAXATT * DP_PART, DP_A_END = DP_A_BIAS + DP_MAXL;
+static_assert(DP_A_END * 4 <= DP_ACT_BYTES, "attention scratch does not fit the activation buffer");
+static_assert(DP_MAXU * 16 * 128 * 4 <= DP_ACT_BYTES && (DP_MAXV + 256) * 4 <= DP_ACT_BYTES, "reduction / sampling scratch does not fit");
 
 struct DpSmem {
   uint8_t ring[DP_NSLOT][DP_SLOT_BYTES];
-  float red[DP_RED_FLOATS];                             // GEMM cross-warp reduction | attention scratch | sampling scratch
-  float biasrow[DP_MAXL];
-  float2 stat[2][16][16];                               // LayerNorm (sum, sum of squares) per warp and row, double-buffered
+  // activation staging (TMA destination, read once into registers) | GEMM cross-warp reduction | attention scratch | sampling scratch
+  alignas(128) uint8_t act[DP_ACT_BYTES];
+  float2 rowstat[2][16];                                // (mean, rstd) per batch row: [0] of X (LN1 / ln_f), [1] of X1 (LN2)
   float red16[16];
-  float att_tab[DP_MAXATT][DP_PART];
   alignas(8) uint64_t full[DP_NSLOT];
   alignas(8) uint64_t empty[DP_NSLOT];
+  alignas(8) uint64_t act_bar;
   unsigned int flags[DP_MAXATT];
   int found;
   volatile unsigned int rel[DP_NSLOT];                  // unit number last released from each slot (see ring_wait_prev_released)
   volatile unsigned int att_epoch;                      // attention phases whose closing grid barrier the consumers have passed (producer gate)
   unsigned int where[4];                                // step, layer, phase of the consumers (diagnostics)
-  unsigned long long fine[8];                           // thread 0: ns in a-frag load | linear ring wait | linear mma + epilogue | attention prologue | attention ring wait | attention unit math | attention merge
+  unsigned long long fine[8];                           // thread 0: ns in activation fetch | linear ring wait | linear mma + epilogue | attention prologue | attention ring wait | attention unit math | attention merge
   unsigned int* debug;                                  // optional pinned host buffer: filled before a timeout trap
 };
 
@@ -194,7 +206,7 @@ __device__ __forceinline__ void ring_wait_prev_released(DpSmem& sm, unsigned int
 }
 
 // ------------------------------------------------------------------------------------------------ producer
-__device__ void dp_producer(const DecodeParams& p, DpSmem& sm) {
+__device__ __noinline__ void dp_producer(const DecodeParams& p, DpSmem& sm) {
   unsigned int seq = 0;
   const int d = p.d, KG = d >> 6;
   const uint32_t unit_bytes = (uint32_t)KG * DP_KG_BYTES;
@@ -250,128 +262,90 @@ __device__ void dp_producer(const DecodeParams& p, DpSmem& sm) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------ activation vectors in fragment order
+// A [16 x d] vector lives in global memory as d/64 k-groups of 4 KB: [k-group][j = 0..3: fp16 hi of k-step j | 4..7: fp16 lo][lane][16 B],
+// the 16 bytes of a lane being its four mma A registers (a0: row g, cols 2t,2t+1 | a1: row g+8 | a2: row g, cols 2t+8,2t+9 | a3: row g+8).
+__device__ __forceinline__ int frag_off(int b, int c) {
+  const int kg = c >> 6, ks = (c >> 4) & 3, cc = c & 15;
+  const int lane = ((b & 7) << 2) | ((cc & 7) >> 1), reg = (b >> 3) | ((cc >> 3) << 1);
+  return kg * 4096 + ks * 512 + lane * 16 + reg * 4 + (cc & 1) * 2;
+}
+__device__ __forceinline__ void store_frag(uint8_t* __restrict__ base, int b, int c, float x) {
+  const __half hi = __float2half_rn(x);
+  const __half lo = __float2half_rn(x - __half2float(hi));
+  const int off = frag_off(b, c);
+  *reinterpret_cast<__half*>(base + off) = hi;
+  *reinterpret_cast<__half*>(base + off + 2048) = lo;
+}
+
 // ------------------------------------------------------------------------------------------------ linear phase (consumers)
 enum { EPI_QKV = 0, EPI_MLP1 = 1, EPI_MLP2 = 2, EPI_HEAD = 3 };
 
-// Loads this warp's 16 x 64 block of the activation vector src[16][ld] (columns col0 + 64 w ...) in mma A-fragment order, optionally
-// LayerNorms the rows (two-pass statistics exchanged through shared memory), and leaves the fp16 hi / lo fragments in registers.
-__device__ __forceinline__ void load_a_frags(const DecodeParams& p, DpSmem& sm, const float* __restrict__ src, int ld, int col0, const float* gamma,
-                                             const float* beta, float* y_out, uint32_t (&ahi)[4][4], uint32_t (&alo)[4][4], unsigned int& lnpar) {
-  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  const int KG = p.d >> 6;
-  const bool active = w < KG;
-  if (gamma != nullptr && active && lane < 4) {      // this warp's 64 gamma / beta values (2 x 2 lines): in L1 by the time the statistics are known
-    const float* pf = (lane < 2 ? gamma : beta) + w * 64 + (lane & 1) * 32;
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(pf));
-  }
-  float x[4][8];
-#pragma unroll
-  for (int ks = 0; ks < 4; ++ks) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) x[ks][j] = 0.f;
-    if (active) {
-      const int c = col0 + w * 64 + ks * 16 + 2 * t;
-      if (g < p.B) {
-        const float2 v0 = __ldcg(reinterpret_cast<const float2*>(src + (size_t)g * ld + c));
-        const float2 v1 = __ldcg(reinterpret_cast<const float2*>(src + (size_t)g * ld + c + 8));
-        x[ks][0] = v0.x; x[ks][1] = v0.y; x[ks][4] = v1.x; x[ks][5] = v1.y;
-      }
-      if (g + 8 < p.B) {
-        const float2 v0 = __ldcg(reinterpret_cast<const float2*>(src + (size_t)(g + 8) * ld + c));
-        const float2 v1 = __ldcg(reinterpret_cast<const float2*>(src + (size_t)(g + 8) * ld + c + 8));
-        x[ks][2] = v0.x; x[ks][3] = v0.y; x[ks][6] = v1.x; x[ks][7] = v1.y;
-      }
+// LayerNorm statistics of the 16 rows from the finalisers' partial sums ps[row][part][2] = (sum, sum of squares): warp w = row w.
+__device__ __forceinline__ void combine_row_stats(const DecodeParams& p, DpSmem& sm, const float* __restrict__ ps, int nparts, int which) {
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float S = 0.f, Q = 0.f;
+  if (w < p.B) {
+    for (int i = lane; i < nparts; i += 32) {
+      const float2 v = __ldcg(reinterpret_cast<const float2*>(ps) + (size_t)w * nparts + i);
+      S += v.x; Q += v.y;
     }
   }
-  if (gamma != nullptr) {
-    // One-pass LayerNorm statistics, shifted by the row's first element (no cancellation in E[(x-K)^2] - E[x-K]^2): every warp
-    // contributes (sum, sum of squares) of its 64 columns, ONE barrier, every thread then adds the d/64 contributions of its two rows.
-    // stat[] is double-buffered (lnpar toggles per call), so no trailing barrier is needed before the next call overwrites it.
-    const float k0 = (g < p.B) ? __ldcg(src + (size_t)g * ld + col0) : 0.f;
-    const float k1 = (g + 8 < p.B) ? __ldcg(src + (size_t)(g + 8) * ld + col0) : 0.f;
-    float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-    if (active) {
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
-        x[ks][0] -= k0; x[ks][1] -= k0; x[ks][4] -= k0; x[ks][5] -= k0;
-        x[ks][2] -= k1; x[ks][3] -= k1; x[ks][6] -= k1; x[ks][7] -= k1;
-        s0 += (x[ks][0] + x[ks][1]) + (x[ks][4] + x[ks][5]);
-        s1 += (x[ks][2] + x[ks][3]) + (x[ks][6] + x[ks][7]);
-        q0 += (x[ks][0] * x[ks][0] + x[ks][1] * x[ks][1]) + (x[ks][4] * x[ks][4] + x[ks][5] * x[ks][5]);
-        q1 += (x[ks][2] * x[ks][2] + x[ks][3] * x[ks][3]) + (x[ks][6] * x[ks][6] + x[ks][7] * x[ks][7]);
-      }
-    }
-    s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
-    s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
-    q0 += __shfl_xor_sync(0xffffffffu, q0, 1); q0 += __shfl_xor_sync(0xffffffffu, q0, 2);
-    q1 += __shfl_xor_sync(0xffffffffu, q1, 1); q1 += __shfl_xor_sync(0xffffffffu, q1, 2);
-    float2 (*st)[16] = sm.stat[lnpar & 1u];
-    lnpar ^= 1u;
-    if (t == 0) { st[w][g] = make_float2(s0, q0); st[w][g + 8] = make_float2(s1, q1); }
-    bar_consumers();
-    float S0 = 0.f, Q0 = 0.f, S1 = 0.f, Q1 = 0.f;
-    for (int i = 0; i < KG; ++i) {
-      const float2 a = st[i][g], b2 = st[i][g + 8];
-      S0 += a.x; Q0 += a.y; S1 += b2.x; Q1 += b2.y;
-    }
-    const float inv_d = 1.0f / (float)p.d;
-    const float m0 = S0 * inv_d, m1 = S1 * inv_d;                      // mean of (x - K)
-    const float r0 = rsqrtf(fmaxf(Q0 * inv_d - m0 * m0, 0.f) + 1e-5f), r1 = rsqrtf(fmaxf(Q1 * inv_d - m1 * m1, 0.f) + 1e-5f);
-    if (active) {
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
-        const int c = w * 64 + ks * 16 + 2 * t;
-        const float2 ga = __ldg(reinterpret_cast<const float2*>(gamma + c)), gb = __ldg(reinterpret_cast<const float2*>(gamma + c + 8));
-        const float2 ba = __ldg(reinterpret_cast<const float2*>(beta + c)), bb = __ldg(reinterpret_cast<const float2*>(beta + c + 8));
-        x[ks][0] = (x[ks][0] - m0) * r0 * ga.x + ba.x; x[ks][1] = (x[ks][1] - m0) * r0 * ga.y + ba.y;
-        x[ks][4] = (x[ks][4] - m0) * r0 * gb.x + bb.x; x[ks][5] = (x[ks][5] - m0) * r0 * gb.y + bb.y;
-        x[ks][2] = (x[ks][2] - m1) * r1 * ga.x + ba.x; x[ks][3] = (x[ks][3] - m1) * r1 * ga.y + ba.y;
-        x[ks][6] = (x[ks][6] - m1) * r1 * gb.x + bb.x; x[ks][7] = (x[ks][7] - m1) * r1 * gb.y + bb.y;
-        // the normalised vector is needed again (x1 = y + attention): CTA c < KG publishes the 64 columns of its warp c
-        if (y_out != nullptr && (int)blockIdx.x == w) {
-          if (g < p.B) {
-            *reinterpret_cast<float2*>(y_out + (size_t)g * p.d + c) = make_float2(x[ks][0], x[ks][1]);
-            *reinterpret_cast<float2*>(y_out + (size_t)g * p.d + c + 8) = make_float2(x[ks][4], x[ks][5]);
-          }
-          if (g + 8 < p.B) {
-            *reinterpret_cast<float2*>(y_out + (size_t)(g + 8) * p.d + c) = make_float2(x[ks][2], x[ks][3]);
-            *reinterpret_cast<float2*>(y_out + (size_t)(g + 8) * p.d + c + 8) = make_float2(x[ks][6], x[ks][7]);
-          }
-        }
-      }
-    }
-  }
-#pragma unroll
-  for (int ks = 0; ks < 4; ++ks) {
-    split_f16x2(x[ks][0], x[ks][1], ahi[ks][0], alo[ks][0]);
-    split_f16x2(x[ks][2], x[ks][3], ahi[ks][1], alo[ks][1]);
-    split_f16x2(x[ks][4], x[ks][5], ahi[ks][2], alo[ks][2]);
-    split_f16x2(x[ks][6], x[ks][7], ahi[ks][3], alo[ks][3]);
+  for (int o = 16; o; o >>= 1) { S += __shfl_xor_sync(0xffffffffu, S, o); Q += __shfl_xor_sync(0xffffffffu, Q, o); }
+  if (lane == 0) {
+    const float inv_d = 1.0f / (float)p.d, mean = S * inv_d;
+    sm.rowstat[which][w] = make_float2(mean, rsqrtf(fmaxf(Q * inv_d - mean * mean, 0.f) + 1e-5f));
   }
 }
 
-// One linear layer: out[b][row] = sum_k act[b][k] * W[row][k] for this CTA's units.  `seq` advances by the units consumed.
-template <int EPI>
-__device__ void linear_phase(const DecodeParams& p, DpSmem& sm, unsigned int& seq, unsigned int& lnpar, const float* src, int src_ld, const float* gamma,
-                             const float* beta, float* y_out, int U, float inv_s, const float* bias, const DecodeLayer* L) {
+// One linear layer on this CTA's units: acc[b][row] = sum_k act[b][k] * W'[row][k]; `seq` advances by the units consumed.
+//   frag_src: the activation vector(s) in fragment order (MLP2: four K-quarters of 16 x d each)
+//   stats / nparts / which: partial sums for the lazy LayerNorm (nullptr: none), see combine_row_stats
+__device__ __noinline__ void linear_phase(const DecodeParams& p, DpSmem& sm, unsigned int& seq, unsigned int& act_par, const int epi, const uint8_t* __restrict__ frag_src,
+                             const float* __restrict__ stats, int nparts, int which, int U, float inv_s, const float* __restrict__ c1,
+                             const float* __restrict__ c2) {
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
   const int d = p.d, KG = d >> 6, units_per_q = d >> 3;
+  const uint32_t vec_bytes = (uint32_t)KG * 4096u;
+  float* red = reinterpret_cast<float*>(sm.act);
   int u0, u1;
   part_range(U, u0, u1);
-  uint32_t ahi[4][4], alo[4][4];
-  int cur_q = -1;
   unsigned long long tf = dp_globaltimer();
   auto fine = [&](int k) { if (tid == 0) { const unsigned long long now = dp_globaltimer(); sm.fine[k] += now - tf; tf = now; } };
-  if (EPI != EPI_MLP2) load_a_frags(p, sm, src, src_ld, 0, gamma, beta, y_out, ahi, alo, lnpar);
-  fine(0);
-  for (int ub = u0; ub < u1; ub += DP_MAXU) {
-    const int nb = min(DP_MAXU, u1 - ub);
-    for (int i = 0; i < nb; ++i, ++seq) {
-      const int u = ub + i;
-      if (EPI == EPI_MLP2) {
-        const int q = u / units_per_q;
-        if (q != cur_q) { load_a_frags(p, sm, src, src_ld, q * d, nullptr, nullptr, nullptr, ahi, alo, lnpar); cur_q = q; fine(0); }
+  if (stats != nullptr) combine_row_stats(p, sm, stats, nparts, which);      // visible after the first barrier below
+  uint32_t ahi[4][4], alo[4][4];
+  int cur_q = -1, u = u0;
+  bool first = true;
+  while (first || u < u1) {
+    // ---- (re)load the A fragments: one bulk copy of the vector into shared memory, eight 16-byte loads per lane
+    const int q = (epi == EPI_MLP2 && u < u1) ? u / units_per_q : 0;
+    if (u < u1 && (first || q != cur_q)) {
+      if (tid == 0) {
+        fence_proxy_async();               // act[] was last written through the generic proxy (scratch); order that before the async-proxy refill
+        mbar_expect_tx(&sm.act_bar, vec_bytes);
+        dp_bulk_g2s(sm.act, frag_src + (size_t)q * vec_bytes, vec_bytes, &sm.act_bar);
       }
+      dp_mbar_wait(sm, &sm.act_bar, act_par & 1u, 6u, (unsigned)u);
+      act_par ^= 1u;
+      if (w < KG) {
+        const uint8_t* base = sm.act + w * 4096 + lane * 16;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint4 h4 = *reinterpret_cast<const uint4*>(base + j * 512), l4 = *reinterpret_cast<const uint4*>(base + 2048 + j * 512);
+          ahi[j][0] = h4.x; ahi[j][1] = h4.y; ahi[j][2] = h4.z; ahi[j][3] = h4.w;
+          alo[j][0] = l4.x; alo[j][1] = l4.y; alo[j][2] = l4.z; alo[j][3] = l4.w;
+        }
+      }
+      cur_q = q;
+      fine(0);
+    }
+    first = false;
+    bar_consumers();                        // fragments are in registers (act[] becomes the reduction scratch); row statistics are published
+    if (u >= u1) break;
+    // ---- a batch of up to DP_MAXU units of the same K-quarter
+    const int ub = u;
+    int nb = 0;
+    while (nb < DP_MAXU && u < u1 && (epi != EPI_MLP2 || u / units_per_q == cur_q)) {
       ring_wait_full(sm, seq);
       fine(1);
       if (w < KG) {
@@ -388,66 +362,90 @@ __device__ void linear_phase(const DecodeParams& p, DpSmem& sm, unsigned int& se
         mma_f16(acc1, ahi[2], e4m3x2_to_f16x2((uint16_t)(lo.z & 0xffffu)), e4m3x2_to_f16x2((uint16_t)(lo.z >> 16)));
         mma_f16(acc0, ahi[3], h1.z, h1.w); mma_f16(acc2, alo[3], h1.z, h1.w);
         mma_f16(acc1, ahi[3], e4m3x2_to_f16x2((uint16_t)(lo.w & 0xffffu)), e4m3x2_to_f16x2((uint16_t)(lo.w >> 16)));
-        *reinterpret_cast<float4*>(&sm.red[((i * 16 + w) * 32 + lane) * 4]) =
+        *reinterpret_cast<float4*>(&red[((nb * 16 + w) * 32 + lane) * 4]) =
             make_float4((acc0[0] + acc2[0]) + acc1[0] * inv_s, (acc0[1] + acc2[1]) + acc1[1] * inv_s, (acc0[2] + acc2[2]) + acc1[2] * inv_s,
                         (acc0[3] + acc2[3]) + acc1[3] * inv_s);
       }
       bar_consumers();                      // every warp has consumed the slot (the MMAs depend on the shared-memory loads)
       if (tid == 0) ring_release(sm, seq);
+      ++nb; ++u; ++seq;
     }
-    // ---- epilogue of the batch: element e of unit i -> lane e/4, register e%4 -> (batch row, weight row)
-    for (int idx = tid; idx < nb * 128; idx += DP_CONSUMERS) {
-      const int i = idx >> 7, e = idx & 127;
+    // ---- epilogue of the batch: element e of unit i -> lane e/4, register e%4 -> (batch row, weight row); at most one element per thread
+    const int idx = tid;
+    const bool has = idx < nb * 128;
+    const int i = idx >> 7, e = idx & 127;
+    const int ln = e >> 2, j = e & 3;
+    const int b = (ln >> 2) + ((j & 2) ? 8 : 0), nrow = 2 * (ln & 3) + (j & 1);
+    const int uu = ub + i;
+    if (has && b < p.B) {
       float v = 0.f;
-      for (int ww = 0; ww < KG; ++ww) v += sm.red[(i * 16 + ww) * 128 + e];
-      const int ln = e >> 2, j = e & 3;
-      const int b = (ln >> 2) + ((j & 2) ? 8 : 0), nrow = 2 * (ln & 3) + (j & 1);
-      const int u = ub + i;
-      if (b < p.B) {
-        if (EPI == EPI_QKV) {
-          const int row = u * 8 + nrow;
-          p.QKV[(size_t)b * 3 * d + row] = v + __ldg(bias + row);
-        } else if (EPI == EPI_MLP1) {
-          const int row = u * 8 + nrow;
-          p.Hbuf[(size_t)b * 4 * d + row] = gelu_erf(v + __ldg(bias + row));
-        } else if (EPI == EPI_MLP2) {
-          const int q = u / units_per_q, row = (u - q * units_per_q) * 8 + nrow;
-          p.P2[((size_t)q * 16 + b) * d + row] = v;
-        } else {
-          const int row = u * 8 + nrow;
-          if (row < p.vocab) p.LOGITS[(size_t)b * p.vocab + row] = v;
-        }
+      for (int ww = 0; ww < KG; ++ww) v += red[(i * 16 + ww) * 128 + e];
+      if (epi == EPI_MLP2) {
+        const int row = (uu - cur_q * units_per_q) * 8 + nrow;
+        p.P2[((size_t)cur_q * 16 + b) * d + row] = v;
+      } else {
+        const int row = uu * 8 + nrow;
+        const float2 st = sm.rowstat[which][b];
+        v = st.y * (v - st.x * __ldg(c1 + row)) + __ldg(c2 + row);             // lazy LayerNorm + bias
+        if (epi == EPI_QKV) p.QKV[(size_t)b * 3 * d + row] = v;
+        else if (epi == EPI_MLP1) { const int qq = row / d; store_frag(p.HF + (size_t)qq * vec_bytes, b, row - qq * d, gelu_erf(v)); }
+        else if (row < p.vocab) p.LOGITS[(size_t)b * p.vocab + row] = v;
       }
     }
-    if (EPI == EPI_MLP2) {
-      // the four K-quarters of an 8-row unit live in (up to) four CTAs: the last to arrive adds them in quarter order
+    if (epi == EPI_MLP2) {
+      // the four K-quarters of an 8-row unit live in (up to) four CTAs: the last to arrive adds them in quarter order, writes the new
+      // residual stream (fp32 + fragment order) and the unit's partial LayerNorm sums
       bar_consumers();
       if (tid < nb) {
-        const int u = ub + tid, ru = u % units_per_q;
+        const int ru = (ub + tid) % units_per_q;
         const unsigned int tk = atom_add_acq_rel_u32(&p.tick_mlp2[ru], 1u);      // releases the CTA's partials (ordered by the barrier above)
         sm.flags[tid] = (tk == 3u) ? 1u : 0u;
         if (tk == 3u) p.tick_mlp2[ru] = 0u;
       }
       bar_consumers();
-      for (int idx = tid; idx < nb * 128; idx += DP_CONSUMERS) {
-        const int i = idx >> 7, e = idx & 127;
-        if (!sm.flags[i]) continue;
-        const int b = e >> 3, nrow = e & 7;
-        if (b >= p.B) continue;
-        const int row = ((ub + i) % units_per_q) * 8 + nrow;
-        float v = __ldcg(p.X1 + (size_t)b * d + row) + __ldg(bias + row);
+      const int fb = e >> 3, fn = e & 7;                                       // finalisation mapping: 8 consecutive lanes = one batch row
+      const bool fin = has && sm.flags[i] != 0u && fb < p.B;
+      float v = 0.f;
+      const int ru = uu % units_per_q, row = ru * 8 + fn;
+      if (fin) {
+        v = __ldcg(p.X1 + (size_t)fb * d + row) + __ldg(c2 + row);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) v += __ldcg(p.P2 + ((size_t)q * 16 + b) * d + row);
-        p.X[(size_t)b * d + row] = v;
+        for (int qq = 0; qq < 4; ++qq) v += __ldcg(p.P2 + ((size_t)qq * 16 + fb) * d + row);
+        p.X[(size_t)fb * d + row] = v;
+        store_frag(p.XF, fb, row, v);
       }
+      float sv = v, qv = v * v;
+      sv += __shfl_xor_sync(0xffffffffu, sv, 1); qv += __shfl_xor_sync(0xffffffffu, qv, 1);
+      sv += __shfl_xor_sync(0xffffffffu, sv, 2); qv += __shfl_xor_sync(0xffffffffu, qv, 2);
+      sv += __shfl_xor_sync(0xffffffffu, sv, 4); qv += __shfl_xor_sync(0xffffffffu, qv, 4);
+      if (fin && fn == 0) *reinterpret_cast<float2*>(p.PSX + ((size_t)fb * units_per_q + ru) * 2) = make_float2(sv, qv);
     }
-    bar_consumers();                        // red[] / flags[] are reused by the next batch or phase
+    bar_consumers();                        // the reduction scratch / flags[] are reused by the next batch, fetch or phase
   }
   fine(2);
 }
 
 // ------------------------------------------------------------------------------------------------ attention phase (consumers)
-__device__ void attention_phase(const DecodeParams& p, DpSmem& sm, unsigned int& seq, const DecodeLayer& L, int s, bool load_bias) {
+// The finished attention output of (scene b, head h), two channels per lane: x1 = LN1(x) + attention (Block.forward takes the residual from
+// the LayerNorm OUTPUT, mingpt_sparse.py:242-245) -> fp32 X1 (MLP2's residual), fragment-ordered X1F (MLP1's operand) and this head's
+// partial LayerNorm sums of the row.
+__device__ __forceinline__ void finish_head(const DecodeParams& p, const DpSmem& sm, const DecodeLayer& L, int b, int h, int lane, float o0, float o1) {
+  const int c0 = h * 64 + lane, c1 = c0 + 32;
+  const float2 st = sm.rowstat[0][b];
+  const size_t xi = (size_t)b * p.d;
+  const float y0 = (__ldcg(p.X + xi + c0) - st.x) * st.y * __ldg(L.ln1_g + c0) + __ldg(L.ln1_b + c0);
+  const float y1 = (__ldcg(p.X + xi + c1) - st.x) * st.y * __ldg(L.ln1_g + c1) + __ldg(L.ln1_b + c1);
+  const float x0 = y0 + o0, x1 = y1 + o1;
+  p.X1[xi + c0] = x0;
+  p.X1[xi + c1] = x1;
+  store_frag(p.X1F, b, c0, x0);
+  store_frag(p.X1F, b, c1, x1);
+  float sv = x0 + x1, qv = x0 * x0 + x1 * x1;
+  for (int o = 16; o; o >>= 1) { sv += __shfl_xor_sync(0xffffffffu, sv, o); qv += __shfl_xor_sync(0xffffffffu, qv, o); }
+  if (lane == 0) *reinterpret_cast<float2*>(p.PSX1 + ((size_t)b * p.H + h) * 2) = make_float2(sv, qv);
+}
+
+__device__ __noinline__ void attention_phase(const DecodeParams& p, DpSmem& sm, unsigned int& seq, unsigned int& act_par, const DecodeLayer& L, int s) {
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
   const int d = p.d, H = p.H;
   const int n = p.nc + s, r = n - 1, nblk = (n + 127) >> 7;
@@ -457,16 +455,30 @@ __device__ void attention_phase(const DecodeParams& p, DpSmem& sm, unsigned int&
   const int nun = u1 - u0;
   unsigned long long tf = dp_globaltimer();
   auto fine = [&](int k) { if (tid == 0) { const unsigned long long now = dp_globaltimer(); sm.fine[k] += now - tf; tf = now; } };
-  // scratch carved out of red[]
-  float* qs = sm.red;                                  // [MAXBH][64]   q of every touched (scene, head)
-  float* kn = qs + DP_MAXBH * 64;                      // [MAXBH][64]   newest key
-  float* vn = kn + DP_MAXBH * 64;                      // [MAXBH][64]   newest value
-  float* ps = vn + DP_MAXBH * 64;                      // [4][128]      probabilities of the group's block
-  float* pd = ps + 4 * 128;                            // [4][2][128]   partial dot products (two channel halves)
-  float* op = pd + 4 * 2 * 128;                        // [4][4][64]    P.V partials of the four key quarters
-  float* gr = op + 4 * 4 * 64;                         // [4][4]        group reductions
-  if (load_bias) {
-    for (int j = tid; j < n; j += DP_CONSUMERS) sm.biasrow[j] = p.bias ? __ldg(p.bias + (size_t)r * p.bias_ld + j) : 0.f;
+  // scratch carved out of act[] (free between the linear phases)
+  float* fa = reinterpret_cast<float*>(sm.act);
+  float* qs = fa + DP_A_QS;                            // [MAXBH][64]   q of every touched (scene, head)
+  float* kn = fa + DP_A_KN;                            // [MAXBH][64]   newest key
+  float* vn = fa + DP_A_VN;                            // [MAXBH][64]   newest value
+  float* ps = fa + DP_A_PS;                            // [4][128]      probabilities of the group's block
+  float* pd = fa + DP_A_PD;                            // [4][2][128]   partial dot products (two channel halves)
+  float* op = fa + DP_A_OP;                            // [4][4][64]    P.V partials of the four key quarters
+  float* gr = fa + DP_A_GR;                            // [4][4]        group reductions
+  float (*att_tab)[DP_PART] = reinterpret_cast<float (*)[DP_PART]>(fa + DP_A_TAB);
+  float* biasrow = fa + DP_A_BIAS;                     // camera-bias row r (one bulk copy per phase; zeros without a bias)
+  if (nun > 0) {
+    const bool tma_ok = p.bias != nullptr && (p.bias_ld & 3) == 0;
+    if (tma_ok) {
+      const uint32_t bytes = (uint32_t)((n + 3) & ~3) * 4u;
+      if (tid == 0) {
+        fence_proxy_async();
+        mbar_expect_tx(&sm.act_bar, bytes);
+        dp_bulk_g2s(biasrow, p.bias + (size_t)r * p.bias_ld, bytes, &sm.act_bar);
+      }
+    } else {
+      for (int j = tid; j < n; j += DP_CONSUMERS) biasrow[j] = p.bias ? __ldg(p.bias + (size_t)r * p.bias_ld + j) : 0.f;
+    }
+    if (tma_ok) { dp_mbar_wait(sm, &sm.act_bar, act_par & 1u, 7u, (unsigned)n); act_par ^= 1u; }
   }
   const int bh_first = nun > 0 ? u0 / nblk : 0, bh_last = nun > 0 ? (u1 - 1) / nblk : -1;
   const int nbh = bh_last - bh_first + 1;
@@ -534,7 +546,7 @@ __device__ void attention_phase(const DecodeParams& p, DpSmem& sm, unsigned int&
     // ---- scores and block softmax: thread = key
     float sc = -INFINITY;
     if (tg < cnt) {
-      sc = ((pd[(grp * 2) * 128 + tg] + pd[(grp * 2 + 1) * 128 + tg]) + sm.biasrow[j0 + tg]) * p.scale;
+      sc = ((pd[(grp * 2) * 128 + tg] + pd[(grp * 2 + 1) * 128 + tg]) + biasrow[j0 + tg]) * p.scale;
       if (L.layout != nullptr) {
         const int h = bh % H;
         if (!L.layout[((size_t)h * p.lay_ld + r / p.lay_blk) * p.lay_ld + (j0 + tg) / p.lay_blk]) sc = -INFINITY;
@@ -578,10 +590,10 @@ __device__ void attention_phase(const DecodeParams& p, DpSmem& sm, unsigned int&
     }
     bar_group(grp);
     if (tg < 64)
-      sm.att_tab[i][4 + tg] = (op[(grp * 4) * 64 + tg] + op[(grp * 4 + 1) * 64 + tg]) + (op[(grp * 4 + 2) * 64 + tg] + op[(grp * 4 + 3) * 64 + tg]);
+      att_tab[i][4 + tg] = (op[(grp * 4) * 64 + tg] + op[(grp * 4 + 1) * 64 + tg]) + (op[(grp * 4 + 2) * 64 + tg] + op[(grp * 4 + 3) * 64 + tg]);
     if (tg == 0) {
-      sm.att_tab[i][0] = m;
-      sm.att_tab[i][1] = (gr[grp * 4] + gr[grp * 4 + 1]) + (gr[grp * 4 + 2] + gr[grp * 4 + 3]);
+      att_tab[i][0] = m;
+      att_tab[i][1] = (gr[grp * 4] + gr[grp * 4 + 1]) + (gr[grp * 4 + 2] + gr[grp * 4 + 3]);
     }
     bar_group(grp);                       // the slot and the group scratch are free again
     if (tg == 0) ring_release(sm, sq);
@@ -595,19 +607,17 @@ __device__ void attention_phase(const DecodeParams& p, DpSmem& sm, unsigned int&
     const int bh = bh_first + bi, b = bh / H, h = bh - b * H;
     const int ua = max(u0, bh * nblk), ub = min(u1, (bh + 1) * nblk);
     float M = -INFINITY;
-    for (int u = ua; u < ub; ++u) M = fmaxf(M, sm.att_tab[u - u0][0]);
+    for (int u = ua; u < ub; ++u) M = fmaxf(M, att_tab[u - u0][0]);
     float Ls = 0.f, o0 = 0.f, o1 = 0.f;
     for (int u = ua; u < ub; ++u) {
-      const float* tb = sm.att_tab[u - u0];
+      const float* tb = att_tab[u - u0];
       const float wgt = (tb[0] == -INFINITY) ? 0.f : expf(tb[0] - M);
       Ls += tb[1] * wgt;
       o0 += tb[4 + lane] * wgt;
       o1 += tb[4 + 32 + lane] * wgt;
     }
-    const size_t xi = (size_t)b * d + h * 64;
     if (ub - ua == nblk) {               // every key block of this (scene, head) was ours
-      p.X1[xi + lane] = __ldcg(p.Y + xi + lane) + o0 / Ls;
-      p.X1[xi + 32 + lane] = __ldcg(p.Y + xi + 32 + lane) + o1 / Ls;
+      finish_head(p, sm, L, b, h, lane, o0 / Ls, o1 / Ls);
       continue;
     }
     // Shared with other CTAs: leave the merged partial in the slot of our first block and add (1 << slot) << 32 | blocks to the pair's
@@ -639,8 +649,7 @@ __device__ void attention_phase(const DecodeParams& p, DpSmem& sm, unsigned int&
       a1 = a1 * wo + x1 * wn;
       MM = Mn;
     }
-    p.X1[xi + lane] = __ldcg(p.Y + xi + lane) + a0 / LL;
-    p.X1[xi + 32 + lane] = __ldcg(p.Y + xi + 32 + lane) + a1 / LL;
+    finish_head(p, sm, L, b, h, lane, a0 / LL, a1 / LL);
     if (lane == 0) p.tick_att[bh] = 0ull;
   }
   fine(6);
@@ -661,10 +670,10 @@ __device__ __forceinline__ void dp_philox(uint32_t c0, uint32_t c1, uint32_t c2,
 
 // Same tail as dec_sample_kernel (decode.cu): logits / T, top-k keeping ties with the k-th value, softmax, Philox multinomial | greedy |
 // forced token (cond_transformer_multi_view.py:138-142,200-219).  Returns the token (uniform over the consumer threads).
-__device__ int sample_row(const DecodeParams& p, DpSmem& sm, int b, int s) {
+__device__ __noinline__ int sample_row(const DecodeParams& p, DpSmem& sm, int b, int s) {
   const int tid = threadIdx.x, V = p.vocab;
-  float* lg = sm.red;
-  int* hist = reinterpret_cast<int*>(sm.red + DP_MAXV);          // 256 bins of the radix select
+  float* lg = reinterpret_cast<float*>(sm.act);
+  int* hist = reinterpret_cast<int*>(sm.act) + DP_MAXV;          // 256 bins of the radix select
   const float inv_t = 1.0f / p.temperature;
   for (int i = tid; i < V; i += DP_CONSUMERS) {
     float v = __ldcg(p.LOGITS + (size_t)b * V + i);
@@ -783,42 +792,53 @@ __device__ int sample_row(const DecodeParams& p, DpSmem& sm, int b, int s) {
   return token;
 }
 
-// Embedding of decode-order image token `sdec` (value tok) of scene b -> X[b][:] (mingpt_sparse.py:332-350; same arithmetic as embed_kernel)
-__device__ void embed_row(const DecodeParams& p, DpSmem& sm, int b, int sdec, long long tok) {
+// Embedding of decode-order image token `sdec` (value tok) of scene b (mingpt_sparse.py:332-350; same arithmetic as embed_kernel)
+// -> the residual-stream row in fp32 (X), in fragment order (XF) and its LayerNorm sums (PSX: the whole row in part 0, zeros elsewhere).
+__device__ __noinline__ void embed_row(const DecodeParams& p, DpSmem& sm, int b, int sdec, long long tok) {
   const int tid = threadIdx.x, d = p.d;
   const int j = p.fwd[sdec];
   const int cam = j / p.hw, px = j - cam * p.hw;
   const float* e = p.x_tok_emb + (size_t)tok * d;
   const float* pos = p.x_pos_emb + (size_t)j * d;
   float* out = p.X + (size_t)b * d;
-  if (p.img_embed_w == nullptr) {
-    for (int c = tid; c < d; c += DP_CONSUMERS) out[c] = e[c] + pos[c];
-    return;
+  float gv[2] = {0.f, 0.f};
+  float inv = 0.f;
+  if (p.img_embed_w != nullptr) {
+    const float* I = p.I_inv + ((size_t)b * p.ncam + cam) * 9;
+    const float* E = p.E_inv + ((size_t)b * p.ncam + cam) * 16;
+    const float* pix = p.pixel + (size_t)px * 3;
+    float cv[4], ray[4];
+#pragma unroll
+    for (int rr = 0; rr < 3; ++rr) cv[rr] = I[rr * 3 + 0] * pix[0] + I[rr * 3 + 1] * pix[1] + I[rr * 3 + 2] * pix[2];
+    cv[3] = 1.0f;
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) ray[rr] = E[rr * 4 + 0] * cv[0] + E[rr * 4 + 1] * cv[1] + E[rr * 4 + 2] * cv[2] + E[rr * 4 + 3] * cv[3];
+    float ss = 0.f;
+    int k = 0;
+    for (int c = tid; c < d; c += DP_CONSUMERS, ++k) {
+      const float4 wi = __ldg(reinterpret_cast<const float4*>(p.img_embed_w) + c);
+      const float4 wc = __ldg(reinterpret_cast<const float4*>(p.cam_embed_w) + c);
+      const float de = wi.x * ray[0] + wi.y * ray[1] + wi.z * ray[2] + wi.w * ray[3];
+      const float ce = wc.x * E[3] + wc.y * E[7] + wc.z * E[11] + wc.w * E[15];
+      gv[k] = de - ce;
+      ss += gv[k] * gv[k];
+    }
+    ss = consumers_sum(ss, sm.red16);
+    inv = 1.0f / (sqrtf(ss) + 1e-7f);
   }
-  const float* I = p.I_inv + ((size_t)b * p.ncam + cam) * 9;
-  const float* E = p.E_inv + ((size_t)b * p.ncam + cam) * 16;
-  const float* pix = p.pixel + (size_t)px * 3;
-  float cv[4], ray[4];
-#pragma unroll
-  for (int rr = 0; rr < 3; ++rr) cv[rr] = I[rr * 3 + 0] * pix[0] + I[rr * 3 + 1] * pix[1] + I[rr * 3 + 2] * pix[2];
-  cv[3] = 1.0f;
-#pragma unroll
-  for (int rr = 0; rr < 4; ++rr) ray[rr] = E[rr * 4 + 0] * cv[0] + E[rr * 4 + 1] * cv[1] + E[rr * 4 + 2] * cv[2] + E[rr * 4 + 3] * cv[3];
-  float gv[2];
-  float ss = 0.f;
+  float sv = 0.f, qv = 0.f;
   int k = 0;
   for (int c = tid; c < d; c += DP_CONSUMERS, ++k) {
-    const float4 wi = __ldg(reinterpret_cast<const float4*>(p.img_embed_w) + c);
-    const float4 wc = __ldg(reinterpret_cast<const float4*>(p.cam_embed_w) + c);
-    const float de = wi.x * ray[0] + wi.y * ray[1] + wi.z * ray[2] + wi.w * ray[3];
-    const float ce = wc.x * E[3] + wc.y * E[7] + wc.z * E[11] + wc.w * E[15];
-    gv[k] = de - ce;
-    ss += gv[k] * gv[k];
+    const float x = (e[c] + gv[k] * inv) + pos[c];
+    out[c] = x;
+    store_frag(p.XF, b, c, x);
+    sv += x; qv += x * x;
   }
-  ss = consumers_sum(ss, sm.red16);
-  const float inv = 1.0f / (sqrtf(ss) + 1e-7f);
-  k = 0;
-  for (int c = tid; c < d; c += DP_CONSUMERS, ++k) out[c] = (e[c] + gv[k] * inv) + pos[c];
+  sv = consumers_sum(sv, sm.red16);
+  qv = consumers_sum(qv, sm.red16);
+  const int nparts = d >> 3;
+  float2* ps = reinterpret_cast<float2*>(p.PSX) + (size_t)b * nparts;
+  for (int i = tid; i < nparts; i += DP_CONSUMERS) ps[i] = (i == 0) ? make_float2(sv, qv) : make_float2(0.f, 0.f);
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
@@ -828,6 +848,7 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(const 
   const int tid = threadIdx.x;
   if (tid == 0) {
     for (int i = 0; i < DP_NSLOT; ++i) { mbar_init(&sm.full[i], 1); mbar_init(&sm.empty[i], 1); }
+    mbar_init(&sm.act_bar, 1);
     fence_barrier_init();
     sm.debug = p.debug;
     sm.where[0] = sm.where[1] = sm.where[2] = 0u;
@@ -840,9 +861,9 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(const 
     if (tid == DP_CONSUMERS) dp_producer(p, sm);
     return;
   }
-  unsigned int seq = 0, bar_target = 0, lnpar = 0;
+  unsigned int seq = 0, bar_target = 0, act_par = 0;
   const unsigned int G = gridDim.x;
-  const int d = p.d;
+  const int d = p.d, H = p.H;
   // X <- embedding of the token drawn at step step_begin - 1 (it is already in the token grid)
   if ((int)blockIdx.x < p.B) {
     const int b = blockIdx.x, sdec = p.step_begin - 1;
@@ -867,25 +888,25 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(const 
     for (int l = 0; l < p.n_layers; ++l) {
       const DecodeLayer& L = p.layers[l];
       mark(11, s, l, 0);
-      linear_phase<EPI_QKV>(p, sm, seq, lnpar, p.X, d, L.ln1_g, L.ln1_b, p.Y, 3 * d / 8, L.s_qkv, L.b_qkv, &L);
+      linear_phase(p, sm, seq, act_par, EPI_QKV, p.XF, p.PSX, d >> 3, 0, 3 * d / 8, L.s_qkv, L.c1_qkv, L.c2_qkv);
       mark(0, s, l, 1);
       grid_sync(sm, p.barrier, bar_target, G);
       mark(1, s, l, 2);
-      attention_phase(p, sm, seq, L, s, l == 0);
+      attention_phase(p, sm, seq, act_par, L, s);
       mark(2, s, l, 3);
       grid_sync(sm, p.barrier, bar_target, G);
       if (tid == 0) sm.att_epoch = (unsigned)(s - p.step_begin) * (unsigned)p.n_layers + (unsigned)l + 1u;      // every CTA's appends of (s, l) are visible
       mark(3, s, l, 4);
-      linear_phase<EPI_MLP1>(p, sm, seq, lnpar, p.X1, d, L.ln2_g, L.ln2_b, nullptr, 4 * d / 8, L.s_1, L.b_1, &L);
+      linear_phase(p, sm, seq, act_par, EPI_MLP1, p.X1F, p.PSX1, H, 1, 4 * d / 8, L.s_1, L.c1_1, L.c2_1);
       mark(4, s, l, 5);
       grid_sync(sm, p.barrier, bar_target, G);
       mark(5, s, l, 6);
-      linear_phase<EPI_MLP2>(p, sm, seq, lnpar, p.Hbuf, 4 * d, nullptr, nullptr, nullptr, 4 * (d / 8), L.s_2, L.b_2, &L);
+      linear_phase(p, sm, seq, act_par, EPI_MLP2, p.HF, nullptr, 0, 0, 4 * (d / 8), L.s_2, nullptr, L.c2_2);
       mark(6, s, l, 7);
       grid_sync(sm, p.barrier, bar_target, G);
       mark(7, s, l, 8);
     }
-    linear_phase<EPI_HEAD>(p, sm, seq, lnpar, p.X, d, p.lnf_g, p.lnf_b, nullptr, p.vpad / 8, p.s_head, nullptr, nullptr);
+    linear_phase(p, sm, seq, act_par, EPI_HEAD, p.XF, p.PSX, d >> 3, 0, p.vpad / 8, p.s_head, p.c1_head, p.c2_head);
     mark(8, s, p.n_layers, 9);
     grid_sync(sm, p.barrier, bar_target, G);
     mark(9, s, p.n_layers, 10);
@@ -973,8 +994,8 @@ long long decode_packed_bytes(int n_rows, int d, int n_quarters) {
 
 void decode_workspace_sizes(int B, int d, int H, int vocab, long long* n_floats, long long* n_counters) {
   const long long vpad = (vocab + 7) / 8 * 8;
-  *n_floats = 16LL * d * 3 /*X, Y, X1*/ + 16LL * 3 * d /*QKV*/ + 16LL * 4 * d /*H*/ + 4LL * 16 * d /*P2*/ + 16LL * vpad /*LOGITS*/ +
-              (long long)B * H * DP_MAXPARTS * DP_PART;
+  *n_floats = 16LL * d * 2 /*X, X1*/ + 16LL * 3 * d /*QKV*/ + 4LL * 16 * d /*P2*/ + 16LL * vpad /*LOGITS*/ + 16LL * (d / 8) * 2 + 16LL * H * 2 /*PSX, PSX1*/ +
+              16LL * d * 2 /*XF, X1F*/ + 4LL * 16 * d /*HF*/ + (long long)B * H * DP_MAXPARTS * DP_PART;
   *n_counters = 64 + 2LL * B * H + d / 8;
 }
 
@@ -991,12 +1012,15 @@ int launch_decode_persistent(DecodeParams p, float* ws, unsigned int* counters, 
   p.vpad = (p.vocab + 7) / 8 * 8;
   float* f = ws;
   p.X = f; f += 16 * d;
-  p.Y = f; f += 16 * d;
   p.X1 = f; f += 16 * d;
   p.QKV = f; f += 16 * 3 * d;
-  p.Hbuf = f; f += 16 * 4 * d;
   p.P2 = f; f += 4 * 16 * d;
   p.LOGITS = f; f += 16 * p.vpad;
+  p.PSX = f; f += 16 * (d / 8) * 2;
+  p.PSX1 = f; f += 16 * p.H * 2;
+  p.XF = reinterpret_cast<uint8_t*>(f); f += 16 * d;          // 16 x d x (2 + 2) bytes
+  p.X1F = reinterpret_cast<uint8_t*>(f); f += 16 * d;
+  p.HF = reinterpret_cast<uint8_t*>(f); f += 4 * 16 * d;
   p.ATTP = f;
   p.barrier = counters;
   p.tick_att = reinterpret_cast<unsigned long long*>(counters + 64);          // 64-bit tickets (8-byte aligned: the buffer is 256-byte aligned)

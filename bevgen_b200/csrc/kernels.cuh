@@ -159,10 +159,16 @@ int launch_dec_advance(int* step, cudaStream_t st);
 
 // ---------------------------------------------------------------- persistent KV-cache decode kernel (decode_persistent.cu)
 struct DecodeLayer {               // one per transformer block, array in DEVICE memory (mirrors bevgen_decode_layer)
-  const uint8_t* w_qkv;            // packed by launch_pack_decode_linear: [3d/8 units][d/64][1536 B]
-  const uint8_t* w_1;              // [4d/8 units]
-  const uint8_t* w_2;              // [4 K-quarters][d/8 units]
-  const float *b_qkv, *b_1, *b_2, *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+  const uint8_t* w_qkv;            // packed by launch_pack_decode_linear from gamma1-scaled [3d][d]: [3d/8 units][d/64][1536 B]
+  const uint8_t* w_1;              // gamma2-scaled mlp.0.weight: [4d/8 units]
+  const uint8_t* w_2;              // mlp.2.weight: [4 K-quarters][d/8 units]
+  const float* c1_qkv;             // [3d] sum_k gamma1_k W_nk           (lazy LayerNorm: out = rstd * (acc - mean * c1) + c2)
+  const float* c2_qkv;             // [3d] bias_n + sum_k beta1_k W_nk
+  const float* c2_2;               // [d]  mlp.2.bias
+  const float* ln1_g;              // [d]  LayerNorm 1 (the residual is taken from its output)
+  const float* ln1_b;
+  const float* c1_1;               // [4d] sum_k gamma2_k W1_nk
+  const float* c2_1;               // [4d] bias1_n + sum_k beta2_k W1_nk
   void* kc;                        // fp16 K cache [B][H][Lmax/128][64][128]
   void* vc;                        // fp16 V cache [B][H][Lmax][64]
   const uint8_t* layout;           // optional per-head block layout [H][lay_ld][lay_ld]
@@ -171,9 +177,9 @@ struct DecodeLayer {               // one per transformer block, array in DEVICE
 struct DecodeParams {
   const DecodeLayer* layers;
   int n_layers;
-  const uint8_t* w_head;
+  const uint8_t* w_head;           // gamma_f-scaled head.weight
   float s_head;
-  const float *lnf_g, *lnf_b;
+  const float *c1_head, *c2_head;  // [vpad] lazy ln_f constants
   int B, d, H, vocab, vpad, nc, n_img, Lmax, ncam, hw;
   int step_begin, step_end;        // decode-order tokens [step_begin, step_end) are produced; token step_begin - 1 is already in cam_idx
   long long* cam_idx;              // [B][ncam][hw] token grid (read for the first embedding, written per step)
@@ -189,7 +195,8 @@ struct DecodeParams {
   float* trace;                    // [n_img][B][vocab] or NULL
   int lay_blk, lay_ld;
   // workspace (filled by the launcher)
-  float *X, *Y, *X1, *QKV, *Hbuf, *P2, *LOGITS, *ATTP;
+  float *X, *X1, *QKV, *P2, *LOGITS, *PSX, *PSX1, *ATTP;
+  uint8_t *XF, *X1F, *HF;          // activation vectors in mma A-fragment order (fp16 hi + lo)
   unsigned int *barrier, *tick_mlp2;
   unsigned long long* tick_att;
   unsigned int* debug;             // optional pinned HOST buffer (8 uint32, zeroed): timeout diagnostics written before the trap

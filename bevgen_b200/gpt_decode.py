@@ -136,6 +136,22 @@ class GPTSampler:
             _lib.check(int(rc), "pack_decode_linear")
         return out, 1.0 / lo_mul
 
+    def _fold_ln(self, w, gamma, beta, bias):
+        """Lazy LayerNorm (decode_persistent.cu): LN(x) W^T + b = rstd * (x W'^T - mean * c1) + c2 with W' = W * gamma (per input column),
+        c1_n = sum_k W'_nk, c2_n = b_n + sum_k beta_k W_nk.  The constants are summed in fp64."""
+        e = self.eng
+        w = w.detach().to(e.dev, torch.float32)
+        wg = (w * gamma.to(e.dev, torch.float32)[None, :]).contiguous()
+        c1 = wg.double().sum(1).float()
+        c2 = (w.double() @ beta.to(e.dev).double()).float()
+        if bias is not None:
+            c2 = c2 + bias.detach().to(e.dev, torch.float32)
+        rows = ((w.shape[0] + 7) // 8) * 8
+        if rows != w.shape[0]:
+            c1 = torch.cat([c1, c1.new_zeros(rows - w.shape[0])])
+            c2 = torch.cat([c2, c2.new_zeros(rows - w.shape[0])])
+        return wg, c1.contiguous(), c2.contiguous()
+
     def _build_persistent(self):
         lib, e = _lib.init(), self.eng
         sd, d = e.sd, e.d
@@ -143,26 +159,31 @@ class GPTSampler:
         for i, lw in enumerate(e.layers):
             p = f"blocks.{i}"
             wqkv = torch.cat([sd[f"{p}.attention.{n}.weight"].detach().to(e.dev, torch.float32) for n in ("query", "key", "value")], 0)
-            pq, sq = self._pack_linear(wqkv)
-            del wqkv
-            p1, s1 = self._pack_linear(sd[f"{p}.mlp.0.weight"])
+            wq, c1q, c2q = self._fold_ln(wqkv, lw["ln1"][0], lw["ln1"][1], lw["bqkv"])
+            pq, sq = self._pack_linear(wq)
+            del wqkv, wq
+            w1, c11, c21 = self._fold_ln(sd[f"{p}.mlp.0.weight"], lw["ln2"][0], lw["ln2"][1], lw["b1"])
+            p1, s1 = self._pack_linear(w1)
+            del w1
             p2, s2 = self._pack_linear(sd[f"{p}.mlp.2.weight"], n_quarters=4)
-            keep += [pq, p1, p2]
+            keep += [pq, p1, p2, c1q, c2q, c11, c21]
             a = arr[i]
             a.w_qkv, a.w_1, a.w_2 = pq.data_ptr(), p1.data_ptr(), p2.data_ptr()
-            a.b_qkv, a.b_1, a.b_2 = lw["bqkv"].data_ptr(), lw["b1"].data_ptr(), lw["b2"].data_ptr()
-            a.ln1_g, a.ln1_b, a.ln2_g, a.ln2_b = lw["ln1"][0].data_ptr(), lw["ln1"][1].data_ptr(), lw["ln2"][0].data_ptr(), lw["ln2"][1].data_ptr()
+            a.c1_qkv, a.c2_qkv, a.c2_2 = c1q.data_ptr(), c2q.data_ptr(), lw["b2"].data_ptr()
+            a.ln1_g, a.ln1_b, a.c1_1, a.c2_1 = lw["ln1"][0].data_ptr(), lw["ln1"][1].data_ptr(), c11.data_ptr(), c21.data_ptr()
             a.k_cache, a.v_cache = self.kc[i].data_ptr(), self.vc[i].data_ptr()
             a.layout = None if lw.get("layout") is None else lw["layout"].data_ptr()
             a.s_qkv, a.s_1, a.s_2 = sq, s1, s2
-        ph, sh = self._pack_linear(sd["head.weight"])
+        wh, c1h, c2h = self._fold_ln(sd["head.weight"], e.ln_f[0], e.ln_f[1], None)
+        ph, sh = self._pack_linear(wh)
+        del wh
         layers_dev = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(e.dev)
         nf, ncnt = C.c_longlong(), C.c_longlong()
         _lib.check(lib.bevgen_decode_workspace(self.B, d, e.H, e.vocab, C.byref(nf), C.byref(ncnt)), "decode_workspace")
         ws = torch.zeros(nf.value, dtype=torch.float32, device=e.dev)
         cnt = torch.zeros(ncnt.value, dtype=torch.int32, device=e.dev)
-        self._pk = dict(keep=keep, layers=layers_dev, head=ph, s_head=sh, ws=ws, cnt=cnt,
-                        weight_bytes=sum(t.numel() for t in keep) + ph.numel())
+        self._pk = dict(keep=keep, layers=layers_dev, head=ph, s_head=sh, c1_head=c1h, c2_head=c2h, ws=ws, cnt=cnt,
+                        weight_bytes=sum(t.numel() for t in keep[0::7] + keep[1::7] + keep[2::7]) + ph.numel())
 
     def _run_persistent(self, batch, step_begin, step_end, temperature, top_k, greedy, seed, forced):
         lib, e = _lib.init(), self.eng
@@ -171,7 +192,7 @@ class GPTSampler:
         pk = self._pk
         a = _lib.DecodeArgs()
         a.layers, a.n_layers = pk["layers"].data_ptr(), len(e.layers)
-        a.w_head, a.s_head, a.lnf_g, a.lnf_b = pk["head"].data_ptr(), pk["s_head"], e.ln_f[0].data_ptr(), e.ln_f[1].data_ptr()
+        a.w_head, a.s_head, a.c1_head, a.c2_head = pk["head"].data_ptr(), pk["s_head"], pk["c1_head"].data_ptr(), pk["c2_head"].data_ptr()
         a.batch, a.d, a.heads, a.vocab, a.n_cond, a.n_img, a.lmax = self.B, e.d, e.H, e.vocab, e.nc, e.n_img, self.Lmax
         a.ncam, a.hw, a.step_begin, a.step_end = e.cfg.num_cams, e.cfg.num_cam_tokens, step_begin, step_end
         a.cam_idx, a.x_tok_emb, a.x_pos_emb = self.cam_idx.data_ptr(), e.x_tok_emb.data_ptr(), e.x_pos_emb.data_ptr()

@@ -308,11 +308,16 @@ BEVGEN_API int bevgen_dec_advance(int* step_ptr, void* stream);
  * (:332-350).  One CTA per SM; weights stream once per step from the packed format below; phases are separated by grid barriers.  The
  * caches must have been prefilled (bevgen_kv_store) and token step_begin - 1 must be in cam_idx.  kv caches are fp16. */
 typedef struct bevgen_decode_layer {
-  const void* w_qkv;                 /* bevgen_pack_decode_linear of [3d][d] (q | k | v rows) */
-  const void* w_1;                   /* of mlp.0.weight [4d][d] */
+  const void* w_qkv;                 /* bevgen_pack_decode_linear of [3d][d] (q | k | v rows), columns pre-multiplied by ln1.weight */
+  const void* w_1;                   /* of mlp.0.weight [4d][d], columns pre-multiplied by ln2.weight */
   const void* w_2;                   /* of mlp.2.weight [d][4d] with n_quarters = 4 */
-  const float* b_qkv; const float* b_1; const float* b_2;
-  const float* ln1_g; const float* ln1_b; const float* ln2_g; const float* ln2_b;
+  /* lazy LayerNorm: the linears run on the raw residual stream, the epilogue applies rstd_b * (acc - mean_b * c1_n) + c2_n */
+  const float* c1_qkv;               /* [3d] sum_k ln1.weight_k * W_nk */
+  const float* c2_qkv;               /* [3d] bias_n + sum_k ln1.bias_k * W_nk */
+  const float* c2_2;                 /* [d]  mlp.2.bias */
+  const float* ln1_g; const float* ln1_b;   /* [d] ln1 itself: Block.forward takes the attention residual from the LayerNorm output */
+  const float* c1_1;                 /* [4d] sum_k ln2.weight_k * W1_nk */
+  const float* c2_1;                 /* [4d] mlp.0.bias_n + sum_k ln2.bias_k * W1_nk */
   void* k_cache; void* v_cache;      /* this layer's caches, layouts as bevgen_kv_store */
   const unsigned char* layout;       /* optional block layout [heads][layout_ld][layout_ld] */
   float s_qkv, s_1, s_2, pad_;       /* 1 / lo_mul of the three packings */
@@ -321,9 +326,9 @@ typedef struct bevgen_decode_layer {
 typedef struct bevgen_decode_args {
   const bevgen_decode_layer* layers; /* DEVICE array of n_layers entries */
   int n_layers;
-  const void* w_head;                /* packed head.weight [vocab][d] */
+  const void* w_head;                /* packed head.weight [vocab][d], columns pre-multiplied by ln_f.weight */
   float s_head;
-  const float* lnf_g; const float* lnf_b;
+  const float* c1_head; const float* c2_head;   /* [ceil8(vocab)] lazy ln_f constants (as c1_qkv / c2_qkv, no bias) */
   int batch, d, heads, vocab, n_cond, n_img, lmax, ncam, hw;
   int step_begin, step_end;
   long long* cam_idx;                /* [batch][ncam][hw] */
