@@ -20,6 +20,8 @@
 //     partials merged per (scene, head) by the last arriving CTA (one acq_rel ticket), camera-bias row added BEFORE the 1/sqrt(d_head)
 //     scale (sparse_self_attention.py:155-168).
 //   * split outputs (MLP2 K-quarters, attention key ranges) are finalised by the last arriver in a FIXED order -> bit-reproducible.
+#include <cstdlib>
+
 #include <cuda_fp16.h>
 #include <cuda_fp8.h>
 
@@ -33,20 +35,22 @@ constexpr int DP_THREADS = DP_CONSUMERS + 32;
 constexpr int DP_NSLOT = 5;
 constexpr int DP_SLOT_BYTES = 32768;
 constexpr int DP_KG_BYTES = 1536;                       // one 64-wide k-group of an 8-row unit: 2 x 512 B fp16 + 512 B e4m3
-constexpr int DP_MAXU = 4;                              // units per reduction batch
+constexpr int DP_MAXU = 4;                              // units per reduction batch (16 warps x 128 partial sums each)
 constexpr int DP_ACT_BYTES = 65536;                     // one 16 x 1024 activation vector as fp16 hi + lo fragments
 constexpr int DP_MAXL = 2560;
-constexpr int DP_MAXBH = 8;                             // (scene, head) pairs one CTA may touch in an attention phase
-constexpr int DP_MAXATT = 48;                           // attention units per CTA and phase
+constexpr int DP_MAXBH = 4;                             // (scene, head) pairs per CTA: pairs blockIdx.x, blockIdx.x + grid, ...
 constexpr int DP_PART = 68;                             // floats per attention partial: m, l, -, -, o[64]
-constexpr int DP_MAXPARTS = 24;                         // CTAs sharing one (scene, head)
 constexpr int DP_MAXV = 4096;
-// layout of the attention scratch inside DpSmem::act (floats)
-constexpr int DP_A_QS = 0, DP_A_KN = DP_A_QS + DP_MAXBH * 64, DP_A_VN = DP_A_KN + DP_MAXBH * 64, DP_A_PS = DP_A_VN + DP_MAXBH * 64,
-              DP_A_PD = DP_A_PS + 4 * 128, DP_A_OP = DP_A_PD + 4 * 2 * 128, DP_A_GR = DP_A_OP + 4 * 4 * 64, DP_A_TAB = DP_A_GR + 16,
-              DP_A_BIAS = DP_A_TAB + DP_MAXATT * DP_PART, DP_A_END = DP_A_BIAS + DP_MAXL;
+constexpr int DP_MAXLB = DP_MAXL / 16;                  // layout blocks per row at the smallest block size (16)
+// act[] outside the activation fetches (float offsets).  Lower 32 KB: cross-warp reduction scratch of the linears | attention scratch;
+// upper part: the camera-bias row (requested right after the QKV phase, i.e. while the lower half is still the QKV reduction scratch)
+// and the layout row of every pair.
+constexpr int DP_A_QS = 0, DP_A_KN = DP_A_QS + DP_MAXBH * 64, DP_A_VN = DP_A_KN + DP_MAXBH * 64, DP_A_PW = DP_A_VN + DP_MAXBH * 64,
+              DP_A_TAB = DP_A_PW + 16 * 128, DP_A_LOW_END = DP_A_TAB + DP_MAXBH * 16 * DP_PART;
+constexpr int DP_A_BIAS = 8192, DP_A_LAY = DP_A_BIAS + DP_MAXL, DP_A_END = DP_A_LAY + DP_MAXBH * DP_MAXLB / 4;
+static_assert(DP_A_LOW_END <= DP_A_BIAS && DP_MAXU * 16 * 128 <= DP_A_BIAS, "scratch overlaps the prefetched camera-bias row");
 static_assert(DP_A_END * 4 <= DP_ACT_BYTES, "attention scratch does not fit the activation buffer");
-static_assert(DP_MAXU * 16 * 128 * 4 <= DP_ACT_BYTES && (DP_MAXV + 256) * 4 <= DP_ACT_BYTES, "reduction / sampling scratch does not fit");
+static_assert((DP_MAXV + 256) * 4 <= DP_ACT_BYTES, "sampling scratch does not fit");
 
 struct DpSmem {
   uint8_t ring[DP_NSLOT][DP_SLOT_BYTES];
@@ -57,12 +61,15 @@ struct DpSmem {
   alignas(8) uint64_t full[DP_NSLOT];
   alignas(8) uint64_t empty[DP_NSLOT];
   alignas(8) uint64_t act_bar;
-  unsigned int flags[DP_MAXATT];
+  alignas(8) uint64_t bias_bar;
+  unsigned int flags[48];
+  unsigned int slotcnt[DP_NSLOT];                       // warps done with a slot shared by several consumer warps
   int found;
   volatile unsigned int rel[DP_NSLOT];                  // unit number last released from each slot (see ring_wait_prev_released)
   volatile unsigned int att_epoch;                      // attention phases whose closing grid barrier the consumers have passed (producer gate)
   unsigned int where[4];                                // step, layer, phase of the consumers (diagnostics)
-  unsigned long long fine[8];                           // thread 0: ns in activation fetch | linear ring wait | linear mma + epilogue | attention prologue | attention ring wait | attention unit math | attention merge
+  unsigned long long prof[12];                          // thread 0: ns per phase body / grid barrier (see GPTSampler.PROFILE_SLOTS)
+  unsigned long long fine[20];                          // thread 0: ns in activation fetch | linear ring wait | linear mma + epilogue | attention prologue | attention ring wait (warp 0) | attention units | attention merge | MLP2
   unsigned int* debug;                                  // optional pinned host buffer: filled before a timeout trap
 };
 
@@ -117,6 +124,7 @@ __device__ __noinline__ void dp_fail(const DpSmem& sm, unsigned int code, unsign
 // the running arrival count this CTA expects; the counter only grows (zeroed by the host before the launch).  A protocol bug or a
 // lost CTA becomes a trap after ~4 s instead of a hung GPU.
 __device__ __forceinline__ void grid_sync(DpSmem& sm, unsigned int* counter, unsigned int& target, unsigned int nctas) {
+  fence_proxy_async();                      // this thread's generic-proxy writes of act[] (scratch) before a later async-proxy refill
   bar_consumers();
   target += nctas;
   if (threadIdx.x == 0) {
@@ -147,9 +155,14 @@ __device__ __forceinline__ void split_f16x2(float x0, float x1, uint32_t& hi, ui
   lo = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
 }
 
+// The consumer phases are inlined into one loop nest; without this the compiler hoists every phase's thread- and size-derived constants
+// out of the step / layer loops and spills them.  Values that pass through an (empty) volatile asm are recomputed where they are used.
+__device__ __forceinline__ int opaque(int v) { asm volatile("" : "+r"(v)); return v; }
+
 __device__ __forceinline__ void part_range(int U, int& u0, int& u1) {
-  u0 = (int)(((long long)blockIdx.x * U) / gridDim.x);
-  u1 = (int)(((long long)(blockIdx.x + 1) * U) / gridDim.x);
+  const int bx = opaque((int)blockIdx.x), g = opaque((int)gridDim.x);
+  u0 = (int)(((long long)bx * U) / g);
+  u1 = (int)(((long long)(bx + 1) * U) / g);
 }
 __device__ __forceinline__ int cta_of_unit(int u, int U) { return (int)((((long long)(u + 1)) * gridDim.x - 1) / U); }
 
@@ -205,60 +218,96 @@ __device__ __forceinline__ void ring_wait_prev_released(DpSmem& sm, unsigned int
   }
 }
 
+// A slot consumed by `nwarps` independent warps: each calls this from lane 0 after its last read; the last one hands the slot back.
+__device__ __forceinline__ void ring_release_shared(DpSmem& sm, unsigned int seq, unsigned int nwarps) {
+  __threadfence_block();
+  const unsigned int slot = seq % DP_NSLOT;
+  if (nwarps == 1u) { ring_release(sm, seq); return; }
+  if (atomicAdd(&sm.slotcnt[slot], 1u) == nwarps - 1u) {
+    sm.slotcnt[slot] = 0u;
+    ring_release(sm, seq);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ producer
+// The byte stream of this CTA, in exactly the order its consumers take it (both sides derive it from blockIdx alone):
+//   per layer: QKV units [part_range(3d/8)] | every 128-key block of the CTA's (scene, head) pairs | MLP1 units [part_range(4d/8)] |
+//              for every owned MLP2 row unit [part_range(d/8)]: its four K-quarters;   per step: head units [part_range(vpad/8)].
 __device__ __noinline__ void dp_producer(const DecodeParams& p, DpSmem& sm) {
   unsigned int seq = 0;
-  const int d = p.d, KG = d >> 6;
+  const int d = p.d, KG = d >> 6, upq = d >> 3;
   const uint32_t unit_bytes = (uint32_t)KG * DP_KG_BYTES;
+  unsigned long long tw = 0ull, ta = 0ull, te = 0ull;
+  auto issue_unit = [&](const uint8_t* src) {
+    const unsigned int slot = seq % DP_NSLOT;
+    if (seq >= (unsigned)DP_NSLOT) {
+      const unsigned long long t0 = dp_globaltimer();
+      dp_mbar_wait(sm, &sm.empty[slot], ((seq / DP_NSLOT) - 1u) & 1u, 3u, seq);
+      tw += dp_globaltimer() - t0;
+    }
+    if (p.dbg & 8) mbar_arrive(&sm.full[slot]);
+    else {
+      mbar_expect_tx(&sm.full[slot], unit_bytes);
+      dp_bulk_g2s(sm.ring[slot], src, unit_bytes, &sm.full[slot]);
+    }
+    ++seq;
+  };
   auto stream_units = [&](const uint8_t* base, int U) {
     int u0, u1;
     part_range(U, u0, u1);
-    for (int u = u0; u < u1; ++u, ++seq) {
-      const unsigned int slot = seq % DP_NSLOT;
-      if (seq >= (unsigned)DP_NSLOT) dp_mbar_wait(sm, &sm.empty[slot], ((seq / DP_NSLOT) - 1u) & 1u, 3u, seq);
-      mbar_expect_tx(&sm.full[slot], unit_bytes);
-      dp_bulk_g2s(sm.ring[slot], base + (size_t)u * unit_bytes, unit_bytes, &sm.full[slot]);
-    }
+    for (int u = u0; u < u1; ++u) issue_unit(base + (size_t)u * unit_bytes);
   };
+  const int BH = p.B * p.H;
+  int r0, r1;
+  part_range(upq, r0, r1);
   for (int s = p.step_begin; s < p.step_end; ++s) {
     const int n = p.nc + s, nblk = (n + 127) >> 7;
     for (int l = 0; l < p.n_layers; ++l) {
       const DecodeLayer& L = p.layers[l];
       stream_units(L.w_qkv, 3 * d / 8);
-      {  // attention units: (scene, head, 128-key block)
-        const int U = p.B * p.H * nblk;
-        int u0, u1;
-        part_range(U, u0, u1);
-        if (s > p.step_begin && u1 > u0) {
-          // The blocks hold keys appended during step s - 1 (by any CTA): do not run ahead of the grid barrier that closed attention
-          // phase (s - 1, l).  With 24 layers the ring (5 units) never reaches that far back; tiny models (a few units per step) do.
+      if ((int)blockIdx.x < BH) {  // attention units: every 128-key block of this CTA's (scene, head) pairs
+        if (s > p.step_begin) {
+          // The blocks hold keys appended during step s - 1: do not run ahead of the grid barrier that closed attention phase (s - 1, l).
+          // With 24 layers the ring (5 units) never reaches that far back; tiny models (a few units per step) do.
           const unsigned int need = (unsigned)(s - 1 - p.step_begin) * (unsigned)p.n_layers + (unsigned)l + 1u;
           if (sm.att_epoch < need) {
             const unsigned long long t0 = dp_globaltimer();
+            const unsigned long long te0 = t0;
             unsigned int spins = 0;
             while (sm.att_epoch < need) {
               if ((++spins & 4095u) == 0 && dp_globaltimer() - t0 > 4000000000ull) dp_fail(sm, 5u, need, sm.att_epoch);
             }
+            te += dp_globaltimer() - te0;
           }
-          fence_proxy_async_all();          // generic-proxy stores of other SMs (ordered by the grid barrier) -> this thread's async-proxy reads
+          fence_proxy_async_all();          // generic-proxy stores (ordered by the grid barrier) -> this thread's async-proxy reads
         }
-        for (int u = u0; u < u1; ++u, ++seq) {
-          const unsigned int slot = seq % DP_NSLOT;
-          if (seq >= (unsigned)DP_NSLOT) dp_mbar_wait(sm, &sm.empty[slot], ((seq / DP_NSLOT) - 1u) & 1u, 3u, seq);
-          const int bh = u / nblk, blk = u - bh * nblk;
-          const int cnt = min(128, n - blk * 128);
-          const uint32_t kbytes = 64u * 128u * 2u, vbytes = (uint32_t)cnt * 128u;
-          mbar_expect_tx(&sm.full[slot], kbytes + vbytes);
-          const __half* kc = reinterpret_cast<const __half*>(L.kc) + ((size_t)bh * (p.Lmax >> 7) + blk) * (64 * 128);
-          const __half* vc = reinterpret_cast<const __half*>(L.vc) + ((size_t)bh * p.Lmax + (size_t)blk * 128) * 64;
-          dp_bulk_g2s(sm.ring[slot], kc, kbytes, &sm.full[slot]);
-          dp_bulk_g2s(sm.ring[slot] + kbytes, vc, vbytes, &sm.full[slot]);
+        for (int bh = blockIdx.x; bh < BH; bh += gridDim.x) {
+          for (int blk = 0; blk < nblk; ++blk, ++seq) {
+            const unsigned int slot = seq % DP_NSLOT;
+            if (seq >= (unsigned)DP_NSLOT) {
+              const unsigned long long t0 = dp_globaltimer();
+              dp_mbar_wait(sm, &sm.empty[slot], ((seq / DP_NSLOT) - 1u) & 1u, 3u, seq);
+              ta += dp_globaltimer() - t0;
+            }
+            const int cnt = min(128, n - blk * 128);
+            const uint32_t kbytes = 64u * 128u * 2u, vbytes = (uint32_t)cnt * 128u;
+            if (p.dbg & 8) { mbar_arrive(&sm.full[slot]); continue; }
+            mbar_expect_tx(&sm.full[slot], kbytes + vbytes);
+            const __half* kc = reinterpret_cast<const __half*>(L.kc) + ((size_t)bh * (p.Lmax >> 7) + blk) * (64 * 128);
+            const __half* vc = reinterpret_cast<const __half*>(L.vc) + ((size_t)bh * p.Lmax + (size_t)blk * 128) * 64;
+            dp_bulk_g2s(sm.ring[slot], kc, kbytes, &sm.full[slot]);
+            dp_bulk_g2s(sm.ring[slot] + kbytes, vc, vbytes, &sm.full[slot]);
+          }
         }
       }
       stream_units(L.w_1, 4 * d / 8);
-      stream_units(L.w_2, 4 * (d / 8));
+      for (int ru = r0; ru < r1; ++ru)      // MLP2: the CTA's 8 output rows, the four K-quarters in turn
+        for (int q = 0; q < 4; ++q) issue_unit(L.w_2 + ((size_t)q * upq + ru) * unit_bytes);
     }
     stream_units(p.w_head, p.vpad / 8);
+  }
+  if (p.profile != nullptr) {            // producer: ns blocked on a full ring (weight units | attention units), on the epoch gate
+    p.profile[(size_t)blockIdx.x * 32 + 22] = tw; p.profile[(size_t)blockIdx.x * 32 + 23] = ta; p.profile[(size_t)blockIdx.x * 32 + 24] = te;
   }
 }
 
@@ -298,119 +347,161 @@ __device__ __forceinline__ void combine_row_stats(const DecodeParams& p, DpSmem&
   }
 }
 
-// One linear layer on this CTA's units: acc[b][row] = sum_k act[b][k] * W'[row][k]; `seq` advances by the units consumed.
-//   frag_src: the activation vector(s) in fragment order (MLP2: four K-quarters of 16 x d each)
-//   stats / nparts / which: partial sums for the lazy LayerNorm (nullptr: none), see combine_row_stats
+// The CTA's copy of an activation vector (fragment order, in act[]) -> the A registers of warp w's 64-wide k-group
+__device__ __forceinline__ void load_afrag(const DpSmem& sm, int w, int lane, uint32_t (&ahi)[4][4], uint32_t (&alo)[4][4]) {
+  const uint8_t* base = sm.act + w * 4096 + lane * 16;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint4 h4 = *reinterpret_cast<const uint4*>(base + j * 512), l4 = *reinterpret_cast<const uint4*>(base + 2048 + j * 512);
+    ahi[j][0] = h4.x; ahi[j][1] = h4.y; ahi[j][2] = h4.z; ahi[j][3] = h4.w;
+    alo[j][0] = l4.x; alo[j][1] = l4.y; alo[j][2] = l4.z; alo[j][3] = l4.w;
+  }
+}
+// Warp w's k-group of one staged 8-row unit: three independent accumulator chains x_hi * w16, x_hi * w8 (scaled by 1 / S afterwards), x_lo * w16
+__device__ __forceinline__ void unit_mma(const uint8_t* slot, int w, int lane, const uint32_t (&ahi)[4][4], const uint32_t (&alo)[4][4], float (&acc0)[4],
+                                         float (&acc1)[4], float (&acc2)[4]) {
+  const uint8_t* base = slot + w * DP_KG_BYTES + lane * 16;
+  const uint4 h0 = *reinterpret_cast<const uint4*>(base), h1 = *reinterpret_cast<const uint4*>(base + 512);
+  const uint4 lo = *reinterpret_cast<const uint4*>(base + 1024);
+  mma_f16(acc0, ahi[0], h0.x, h0.y); mma_f16(acc2, alo[0], h0.x, h0.y);
+  mma_f16(acc1, ahi[0], e4m3x2_to_f16x2((uint16_t)(lo.x & 0xffffu)), e4m3x2_to_f16x2((uint16_t)(lo.x >> 16)));
+  mma_f16(acc0, ahi[1], h0.z, h0.w); mma_f16(acc2, alo[1], h0.z, h0.w);
+  mma_f16(acc1, ahi[1], e4m3x2_to_f16x2((uint16_t)(lo.y & 0xffffu)), e4m3x2_to_f16x2((uint16_t)(lo.y >> 16)));
+  mma_f16(acc0, ahi[2], h1.x, h1.y); mma_f16(acc2, alo[2], h1.x, h1.y);
+  mma_f16(acc1, ahi[2], e4m3x2_to_f16x2((uint16_t)(lo.z & 0xffffu)), e4m3x2_to_f16x2((uint16_t)(lo.z >> 16)));
+  mma_f16(acc0, ahi[3], h1.z, h1.w); mma_f16(acc2, alo[3], h1.z, h1.w);
+  mma_f16(acc1, ahi[3], e4m3x2_to_f16x2((uint16_t)(lo.w & 0xffffu)), e4m3x2_to_f16x2((uint16_t)(lo.w >> 16)));
+}
+
+// One linear layer (QKV, MLP1, head) on this CTA's units: acc[b][row] = sum_k act[b][k] * W'[row][k]; `seq` advances by the units consumed.
+// Warp w owns the k-group w of EVERY unit (its A fragments stay in registers for the whole phase), takes a unit as soon as it has landed
+// and hands the slot back through a shared-memory counter (no CTA barrier per unit); the 16 partial sums of up to DP_MAXU units are added
+// once, one output element per thread, whose epilogue constants were requested before the MMAs.
+//   frag_src: the activation vector in fragment order;  stats / nparts / which: partial sums of the lazy LayerNorm, see combine_row_stats
 __device__ __noinline__ void linear_phase(const DecodeParams& p, DpSmem& sm, unsigned int& seq, unsigned int& act_par, const int epi, const uint8_t* __restrict__ frag_src,
                              const float* __restrict__ stats, int nparts, int which, int U, float inv_s, const float* __restrict__ c1,
                              const float* __restrict__ c2) {
-  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
-  const int d = p.d, KG = d >> 6, units_per_q = d >> 3;
+  const int tid = opaque((int)threadIdx.x), w = tid >> 5, lane = tid & 31;
+  const int d = opaque(p.d), KG = d >> 6;
   const uint32_t vec_bytes = (uint32_t)KG * 4096u;
   float* red = reinterpret_cast<float*>(sm.act);
   int u0, u1;
   part_range(U, u0, u1);
   unsigned long long tf = dp_globaltimer();
   auto fine = [&](int k) { if (tid == 0) { const unsigned long long now = dp_globaltimer(); sm.fine[k] += now - tf; tf = now; } };
-  if (stats != nullptr) combine_row_stats(p, sm, stats, nparts, which);      // visible after the first barrier below
+  const bool fetch = !(p.dbg & 4);
+  if (u1 > u0 && tid == 0 && fetch) {
+    fence_proxy_async();
+    mbar_expect_tx(&sm.act_bar, vec_bytes);
+    dp_bulk_g2s(sm.act, frag_src, vec_bytes, &sm.act_bar);
+  }
+  if (stats != nullptr) combine_row_stats(p, sm, stats, nparts, which);      // read by this phase's epilogue and (LN1) by the attention phase: both behind a barrier
+  if (u1 == u0) return;
+  if (fetch) {
+    dp_mbar_wait(sm, &sm.act_bar, act_par & 1u, 6u, (unsigned)u0);
+    act_par ^= 1u;
+  }
   uint32_t ahi[4][4], alo[4][4];
-  int cur_q = -1, u = u0;
-  bool first = true;
-  while (first || u < u1) {
-    // ---- (re)load the A fragments: one bulk copy of the vector into shared memory, eight 16-byte loads per lane
-    const int q = (epi == EPI_MLP2 && u < u1) ? u / units_per_q : 0;
-    if (u < u1 && (first || q != cur_q)) {
-      if (tid == 0) {
-        fence_proxy_async();               // act[] was last written through the generic proxy (scratch); order that before the async-proxy refill
-        mbar_expect_tx(&sm.act_bar, vec_bytes);
-        dp_bulk_g2s(sm.act, frag_src + (size_t)q * vec_bytes, vec_bytes, &sm.act_bar);
-      }
-      dp_mbar_wait(sm, &sm.act_bar, act_par & 1u, 6u, (unsigned)u);
-      act_par ^= 1u;
-      if (w < KG) {
-        const uint8_t* base = sm.act + w * 4096 + lane * 16;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint4 h4 = *reinterpret_cast<const uint4*>(base + j * 512), l4 = *reinterpret_cast<const uint4*>(base + 2048 + j * 512);
-          ahi[j][0] = h4.x; ahi[j][1] = h4.y; ahi[j][2] = h4.z; ahi[j][3] = h4.w;
-          alo[j][0] = l4.x; alo[j][1] = l4.y; alo[j][2] = l4.z; alo[j][3] = l4.w;
-        }
-      }
-      cur_q = q;
-      fine(0);
-    }
-    first = false;
-    bar_consumers();                        // fragments are in registers (act[] becomes the reduction scratch); row statistics are published
-    if (u >= u1) break;
-    // ---- a batch of up to DP_MAXU units of the same K-quarter
-    const int ub = u;
-    int nb = 0;
-    while (nb < DP_MAXU && u < u1 && (epi != EPI_MLP2 || u / units_per_q == cur_q)) {
-      ring_wait_full(sm, seq);
-      fine(1);
-      if (w < KG) {
-        const uint8_t* base = sm.ring[seq % DP_NSLOT] + w * DP_KG_BYTES + lane * 16;
-        const uint4 h0 = *reinterpret_cast<const uint4*>(base), h1 = *reinterpret_cast<const uint4*>(base + 512);
-        const uint4 lo = *reinterpret_cast<const uint4*>(base + 1024);
-        // three independent accumulator chains: x_hi * w16, x_lo * w16, x_hi * w8 (the last one scaled by 1 / S afterwards)
+  if (w < KG) load_afrag(sm, w, lane, ahi, alo);
+  fine(0);
+  bar_consumers();                          // fragments are in registers: act[] becomes the reduction scratch; row statistics are published
+  // output element of a unit owned by this thread: element e -> lane e / 4, register e % 4 of the accumulator fragment -> (batch row, weight row)
+  const int ui = tid >> 7, e = tid & 127;
+  const int ln = e >> 2, j = e & 3;
+  const int b = (ln >> 2) + ((j & 2) ? 8 : 0), nrow = 2 * (ln & 3) + (j & 1);
+  for (int ub = u0; ub < u1; ub += DP_MAXU) {
+    const int nb = min(DP_MAXU, u1 - ub);
+    const bool has = ui < nb && b < p.B;
+    const int row = (ub + ui) * 8 + nrow;
+    float c1v = 0.f, c2v = 0.f;
+    if (has) { c1v = __ldg(c1 + row); c2v = __ldg(c2 + row); }
+    if (w < KG) {
+      for (int k = 0; k < nb; ++k) {
+        const unsigned int sq = seq + (unsigned)k;
+        ring_wait_full(sm, sq);
+        fine(1);
         float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f}, acc2[4] = {0.f, 0.f, 0.f, 0.f};
-        mma_f16(acc0, ahi[0], h0.x, h0.y); mma_f16(acc2, alo[0], h0.x, h0.y);
-        mma_f16(acc1, ahi[0], e4m3x2_to_f16x2((uint16_t)(lo.x & 0xffffu)), e4m3x2_to_f16x2((uint16_t)(lo.x >> 16)));
-        mma_f16(acc0, ahi[1], h0.z, h0.w); mma_f16(acc2, alo[1], h0.z, h0.w);
-        mma_f16(acc1, ahi[1], e4m3x2_to_f16x2((uint16_t)(lo.y & 0xffffu)), e4m3x2_to_f16x2((uint16_t)(lo.y >> 16)));
-        mma_f16(acc0, ahi[2], h1.x, h1.y); mma_f16(acc2, alo[2], h1.x, h1.y);
-        mma_f16(acc1, ahi[2], e4m3x2_to_f16x2((uint16_t)(lo.z & 0xffffu)), e4m3x2_to_f16x2((uint16_t)(lo.z >> 16)));
-        mma_f16(acc0, ahi[3], h1.z, h1.w); mma_f16(acc2, alo[3], h1.z, h1.w);
-        mma_f16(acc1, ahi[3], e4m3x2_to_f16x2((uint16_t)(lo.w & 0xffffu)), e4m3x2_to_f16x2((uint16_t)(lo.w >> 16)));
-        *reinterpret_cast<float4*>(&red[((nb * 16 + w) * 32 + lane) * 4]) =
+        if (!(p.dbg & 2)) unit_mma(sm.ring[sq % DP_NSLOT], w, lane, ahi, alo, acc0, acc1, acc2);
+        if (lane == 0) ring_release_shared(sm, sq, (unsigned)KG);      // issued after the MMAs, i.e. after every lane's loads have returned
+        *reinterpret_cast<float4*>(&red[((k * 16 + w) * 32 + lane) * 4]) =
             make_float4((acc0[0] + acc2[0]) + acc1[0] * inv_s, (acc0[1] + acc2[1]) + acc1[1] * inv_s, (acc0[2] + acc2[2]) + acc1[2] * inv_s,
                         (acc0[3] + acc2[3]) + acc1[3] * inv_s);
-      }
-      bar_consumers();                      // every warp has consumed the slot (the MMAs depend on the shared-memory loads)
-      if (tid == 0) ring_release(sm, seq);
-      ++nb; ++u; ++seq;
-    }
-    // ---- epilogue of the batch: element e of unit i -> lane e/4, register e%4 -> (batch row, weight row); at most one element per thread
-    const int idx = tid;
-    const bool has = idx < nb * 128;
-    const int i = idx >> 7, e = idx & 127;
-    const int ln = e >> 2, j = e & 3;
-    const int b = (ln >> 2) + ((j & 2) ? 8 : 0), nrow = 2 * (ln & 3) + (j & 1);
-    const int uu = ub + i;
-    if (has && b < p.B) {
-      float v = 0.f;
-      for (int ww = 0; ww < KG; ++ww) v += red[(i * 16 + ww) * 128 + e];
-      if (epi == EPI_MLP2) {
-        const int row = (uu - cur_q * units_per_q) * 8 + nrow;
-        p.P2[((size_t)cur_q * 16 + b) * d + row] = v;
-      } else {
-        const int row = uu * 8 + nrow;
-        const float2 st = sm.rowstat[which][b];
-        v = st.y * (v - st.x * __ldg(c1 + row)) + __ldg(c2 + row);             // lazy LayerNorm + bias
-        if (epi == EPI_QKV) p.QKV[(size_t)b * 3 * d + row] = v;
-        else if (epi == EPI_MLP1) { const int qq = row / d; store_frag(p.HF + (size_t)qq * vec_bytes, b, row - qq * d, gelu_erf(v)); }
-        else if (row < p.vocab) p.LOGITS[(size_t)b * p.vocab + row] = v;
+        fine(2);
       }
     }
-    if (epi == EPI_MLP2) {
-      // the four K-quarters of an 8-row unit live in (up to) four CTAs: the last to arrive adds them in quarter order, writes the new
-      // residual stream (fp32 + fragment order) and the unit's partial LayerNorm sums
-      bar_consumers();
-      if (tid < nb) {
-        const int ru = (ub + tid) % units_per_q;
-        const unsigned int tk = atom_add_acq_rel_u32(&p.tick_mlp2[ru], 1u);      // releases the CTA's partials (ordered by the barrier above)
-        sm.flags[tid] = (tk == 3u) ? 1u : 0u;
-        if (tk == 3u) p.tick_mlp2[ru] = 0u;
-      }
-      bar_consumers();
-      const int fb = e >> 3, fn = e & 7;                                       // finalisation mapping: 8 consecutive lanes = one batch row
-      const bool fin = has && sm.flags[i] != 0u && fb < p.B;
+    seq += (unsigned)nb;
+    bar_consumers();
+    if (has) {
       float v = 0.f;
-      const int ru = uu % units_per_q, row = ru * 8 + fn;
+      for (int ww = 0; ww < KG; ++ww) v += red[(ui * 16 + ww) * 128 + e];
+      const float2 st = sm.rowstat[which][b];
+      v = st.y * (v - st.x * c1v) + c2v;                                       // lazy LayerNorm + bias
+      if (epi == EPI_QKV) p.QKV[(size_t)b * 3 * d + row] = v;
+      else if (epi == EPI_MLP1) { const int qq = row / d; store_frag(p.HF + (size_t)qq * vec_bytes, b, row - qq * d, gelu_erf(v)); }
+      else if (row < p.vocab) p.LOGITS[(size_t)b * p.vocab + row] = v;
+    }
+    if (ub + DP_MAXU < u1) bar_consumers();   // the reduction scratch is reused by the next batch
+  }
+  fine(2);
+}
+
+// MLP2 + residual: the CTA owns 8 output rows over the whole K = 4d (four K-quarters = four units and four activation vectors in turn; the
+// next quarter's vector is requested as soon as this one is in registers), so the new residual row segment, its fragment-order copy and the
+// unit's LayerNorm partial sums are finished here - no cross-CTA partials.
+__device__ __noinline__ void mlp2_phase(const DecodeParams& p, DpSmem& sm, unsigned int& seq, unsigned int& act_par, const DecodeLayer& L) {
+  const int tid = opaque((int)threadIdx.x), w = tid >> 5, lane = tid & 31;
+  const int d = opaque(p.d), KG = d >> 6, upq = d >> 3;
+  const uint32_t vec_bytes = (uint32_t)KG * 4096u;
+  float* red = reinterpret_cast<float*>(sm.act);
+  int r0, r1;
+  part_range(upq, r0, r1);
+  if (r0 == r1) return;
+  unsigned long long tf = dp_globaltimer();
+  auto fine = [&](int k) { if (tid == 0) { const unsigned long long now = dp_globaltimer(); sm.fine[k] += now - tf; tf = now; } };
+  const int fb = tid >> 3, fn = tid & 7;                 // finalisation mapping (threads 0..127): 8 consecutive lanes = one batch row
+  for (int ru = r0; ru < r1; ++ru) {
+    const bool fetch = !(p.dbg & 4);
+    if (tid == 0 && fetch) {
+      fence_proxy_async();
+      mbar_expect_tx(&sm.act_bar, vec_bytes);
+      dp_bulk_g2s(sm.act, p.HF, vec_bytes, &sm.act_bar);
+    }
+    const int row = ru * 8 + fn;
+    const bool fin = tid < 128 && fb < p.B;
+    float base = 0.f;
+    if (fin) base = __ldcg(p.X1 + (size_t)fb * d + row) + __ldg(L.c2_2 + row);
+    float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f}, acc2[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int q = 0; q < 4; ++q) {
+      if (fetch) {
+        dp_mbar_wait(sm, &sm.act_bar, act_par & 1u, 6u, (unsigned)(ru * 4 + q));
+        act_par ^= 1u;
+      }
+      uint32_t ahi[4][4], alo[4][4];
+      if (w < KG) load_afrag(sm, w, lane, ahi, alo);
+      bar_consumers();                      // act[] is free again
+      if (q < 3 && tid == 0 && fetch) {
+        mbar_expect_tx(&sm.act_bar, vec_bytes);
+        dp_bulk_g2s(sm.act, p.HF + (size_t)(q + 1) * vec_bytes, vec_bytes, &sm.act_bar);
+      }
+      if (w < KG) {
+        ring_wait_full(sm, seq);
+        if (!(p.dbg & 2)) unit_mma(sm.ring[seq % DP_NSLOT], w, lane, ahi, alo, acc0, acc1, acc2);
+        if (lane == 0) ring_release_shared(sm, seq, (unsigned)KG);
+      }
+      ++seq;
+    }
+    if (w < KG)
+      *reinterpret_cast<float4*>(&red[(w * 32 + lane) * 4]) =
+          make_float4((acc0[0] + acc2[0]) + acc1[0] * L.s_2, (acc0[1] + acc2[1]) + acc1[1] * L.s_2, (acc0[2] + acc2[2]) + acc1[2] * L.s_2,
+                      (acc0[3] + acc2[3]) + acc1[3] * L.s_2);
+    bar_consumers();
+    if (tid < 128) {
+      // (batch row fb, weight row fn) lives in lane 4 (fb % 8) + fn / 2, register 2 (fb / 8) + fn % 2 of the accumulator fragment
+      const int ee = ((((fb & 7) << 2) | (fn >> 1)) << 2) | (((fb >> 3) << 1) | (fn & 1));
+      float v = 0.f;
+      for (int ww = 0; ww < KG; ++ww) v += red[ww * 128 + ee];
+      v = fin ? base + v : 0.f;
       if (fin) {
-        v = __ldcg(p.X1 + (size_t)fb * d + row) + __ldg(c2 + row);
-#pragma unroll
-        for (int qq = 0; qq < 4; ++qq) v += __ldcg(p.P2 + ((size_t)qq * 16 + fb) * d + row);
         p.X[(size_t)fb * d + row] = v;
         store_frag(p.XF, fb, row, v);
       }
@@ -418,11 +509,12 @@ __device__ __noinline__ void linear_phase(const DecodeParams& p, DpSmem& sm, uns
       sv += __shfl_xor_sync(0xffffffffu, sv, 1); qv += __shfl_xor_sync(0xffffffffu, qv, 1);
       sv += __shfl_xor_sync(0xffffffffu, sv, 2); qv += __shfl_xor_sync(0xffffffffu, qv, 2);
       sv += __shfl_xor_sync(0xffffffffu, sv, 4); qv += __shfl_xor_sync(0xffffffffu, qv, 4);
-      if (fin && fn == 0) *reinterpret_cast<float2*>(p.PSX + ((size_t)fb * units_per_q + ru) * 2) = make_float2(sv, qv);
+      if (fin && fn == 0) *reinterpret_cast<float2*>(p.PSX + ((size_t)fb * upq + ru) * 2) = make_float2(sv, qv);
     }
-    bar_consumers();                        // the reduction scratch / flags[] are reused by the next batch, fetch or phase
+    fence_proxy_async();
+    bar_consumers();                        // the scratch is overwritten by the next vector
   }
-  fine(2);
+  fine(7);
 }
 
 // ------------------------------------------------------------------------------------------------ attention phase (consumers)
@@ -445,212 +537,200 @@ __device__ __forceinline__ void finish_head(const DecodeParams& p, const DpSmem&
   if (lane == 0) *reinterpret_cast<float2*>(p.PSX1 + ((size_t)b * p.H + h) * 2) = make_float2(sv, qv);
 }
 
-__device__ __noinline__ void attention_phase(const DecodeParams& p, DpSmem& sm, unsigned int& seq, unsigned int& act_par, const DecodeLayer& L, int s) {
-  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
-  const int d = p.d, H = p.H;
+// One CTA owns whole (scene, head) pairs (pairs blockIdx.x, blockIdx.x + grid, ...: no partial results cross CTAs).  A staged 128-key block
+// belongs to a group of four warps, each warp to 32 of its keys from the moment the block lands until the slot goes back - no barrier inside
+// a block: lane = (key pair, channel half) for q . K^T (4-byte loads of the transposed block against q broadcast from shared memory, one
+// shuffle joins the halves), half-warp online softmax, lane = (key mod 4, 8 channels) for P . V (16-byte loads of the value rows,
+// probabilities through a 128-byte per-warp scratch).  Blocks go round-robin over the four groups, every warp keeps a running
+// (max, sum, o[64]) per pair and leaves it in a table that one warp per pair merges in warp order.
+__device__ __noinline__ void attention_phase(const DecodeParams& p, DpSmem& sm, unsigned int& seq, unsigned int& bias_par, const DecodeLayer& L, int s) {
+  const int tid = opaque((int)threadIdx.x), w = tid >> 5, lane = tid & 31;
+  const int d = opaque(p.d), H = opaque(p.H), BH = p.B * H, G = opaque((int)gridDim.x), bx = opaque((int)blockIdx.x);
   const int n = p.nc + s, r = n - 1, nblk = (n + 127) >> 7;
-  const int U = p.B * H * nblk;
-  int u0, u1;
-  part_range(U, u0, u1);
-  const int nun = u1 - u0;
+  const int npairs = bx < BH ? (BH - 1 - bx) / G + 1 : 0;
+  if (npairs == 0) return;
+  const int nun = npairs * nblk;
   unsigned long long tf = dp_globaltimer();
   auto fine = [&](int k) { if (tid == 0) { const unsigned long long now = dp_globaltimer(); sm.fine[k] += now - tf; tf = now; } };
-  // scratch carved out of act[] (free between the linear phases)
   float* fa = reinterpret_cast<float*>(sm.act);
-  float* qs = fa + DP_A_QS;                            // [MAXBH][64]   q of every touched (scene, head)
+  float* qs = fa + DP_A_QS;                            // [MAXBH][64]   q of every pair
   float* kn = fa + DP_A_KN;                            // [MAXBH][64]   newest key
   float* vn = fa + DP_A_VN;                            // [MAXBH][64]   newest value
-  float* ps = fa + DP_A_PS;                            // [4][128]      probabilities of the group's block
-  float* pd = fa + DP_A_PD;                            // [4][2][128]   partial dot products (two channel halves)
-  float* op = fa + DP_A_OP;                            // [4][4][64]    P.V partials of the four key quarters
-  float* gr = fa + DP_A_GR;                            // [4][4]        group reductions
-  float (*att_tab)[DP_PART] = reinterpret_cast<float (*)[DP_PART]>(fa + DP_A_TAB);
-  float* biasrow = fa + DP_A_BIAS;                     // camera-bias row r (one bulk copy per phase; zeros without a bias)
-  if (nun > 0) {
-    const bool tma_ok = p.bias != nullptr && (p.bias_ld & 3) == 0;
-    if (tma_ok) {
-      const uint32_t bytes = (uint32_t)((n + 3) & ~3) * 4u;
-      if (tid == 0) {
-        fence_proxy_async();
-        mbar_expect_tx(&sm.act_bar, bytes);
-        dp_bulk_g2s(biasrow, p.bias + (size_t)r * p.bias_ld, bytes, &sm.act_bar);
-      }
+  float* tab = fa + DP_A_TAB;                          // [MAXBH][16][DP_PART] running partial of every (pair, warp)
+  float* biasrow = fa + DP_A_BIAS;                     // camera-bias row r (requested after the QKV phase; zeros without a bias)
+  uint8_t* layrow = reinterpret_cast<uint8_t*>(fa + DP_A_LAY);      // [MAXBH][DP_MAXLB] layout row of query block r / lay_blk per pair
+  const bool tma_bias = p.bias != nullptr && (p.bias_ld & 3) == 0;
+  // ---- prologue: q / newest key / newest value of every pair (the latter two also appended to the cache), table reset, layout rows
+  if (!tma_bias)
+    for (int j = tid; j < n; j += DP_CONSUMERS) biasrow[j] = p.bias ? __ldg(p.bias + (size_t)r * p.bias_ld + j) : 0.f;
+  for (int i = tid; i < npairs * 192; i += DP_CONSUMERS) {
+    const int k = i / 192, which = (i % 192) >> 6, c = i & 63;
+    const int bh = bx + k * G, b = bh / H, h = bh - b * H;
+    const float v = __ldcg(p.QKV + (size_t)b * 3 * d + which * d + h * 64 + c);
+    if (which == 0) qs[k * 64 + c] = v;
+    else if (which == 1) {
+      kn[k * 64 + c] = v;
+      reinterpret_cast<__half*>(L.kc)[(((size_t)bh * (p.Lmax >> 7) + (r >> 7)) * 64 + c) * 128 + (r & 127)] = __float2half_rn(v);
     } else {
-      for (int j = tid; j < n; j += DP_CONSUMERS) biasrow[j] = p.bias ? __ldg(p.bias + (size_t)r * p.bias_ld + j) : 0.f;
+      vn[k * 64 + c] = v;
+      reinterpret_cast<__half*>(L.vc)[((size_t)bh * p.Lmax + r) * 64 + c] = __float2half_rn(v);
     }
-    if (tma_ok) { dp_mbar_wait(sm, &sm.act_bar, act_par & 1u, 7u, (unsigned)n); act_par ^= 1u; }
   }
-  const int bh_first = nun > 0 ? u0 / nblk : 0, bh_last = nun > 0 ? (u1 - 1) / nblk : -1;
-  const int nbh = bh_last - bh_first + 1;
-  if (nun > 0) {
-    for (int i = tid; i < nbh * 192; i += DP_CONSUMERS) {
-      const int bi = i / 192, which = (i % 192) >> 6, c = i & 63;
-      const int bh = bh_first + bi, b = bh / H, h = bh - b * H;
-      const int last_u = bh * nblk + nblk - 1;                      // the unit holding the newest key r
-      const bool owns_new = last_u >= u0 && last_u < u1;
-      if (which == 0 || owns_new) {
-        const float v = __ldcg(p.QKV + (size_t)b * 3 * d + which * d + h * 64 + c);
-        if (which == 0) qs[bi * 64 + c] = v;
-        else if (which == 1) {
-          kn[bi * 64 + c] = v;
-          reinterpret_cast<__half*>(L.kc)[(((size_t)bh * (p.Lmax >> 7) + (r >> 7)) * 64 + c) * 128 + (r & 127)] = __float2half_rn(v);
-        } else {
-          vn[bi * 64 + c] = v;
-          reinterpret_cast<__half*>(L.vc)[((size_t)bh * p.Lmax + r) * 64 + c] = __float2half_rn(v);
-        }
-      }
+  for (int i = tid; i < npairs * 16; i += DP_CONSUMERS) { tab[i * DP_PART] = -INFINITY; tab[i * DP_PART + 1] = 0.f; }
+  if (L.layout != nullptr) {
+    const int nlb = (n + p.lay_blk - 1) / p.lay_blk;
+    for (int i = tid; i < npairs * nlb; i += DP_CONSUMERS) {
+      const int k = i / nlb, jb = i - k * nlb;
+      const int h = (bx + k * G) % H;
+      layrow[k * DP_MAXLB + jb] = L.layout[((size_t)h * p.lay_ld + r / p.lay_blk) * p.lay_ld + jb];
     }
-    fence_proxy_async_all();             // the appended key / value will be read by cp.async.bulk (async proxy) in the next step
   }
+  fence_proxy_async_all();               // the appended key / value will be read by cp.async.bulk (async proxy) in the next step
+  if (tma_bias) { dp_mbar_wait(sm, &sm.bias_bar, bias_par & 1u, 7u, (unsigned)n); bias_par ^= 1u; }
   bar_consumers();
   fine(3);
-  const int grp = w >> 2, tg = tid & 127, wg = w & 3;
+  // ---- blocks: local unit i = pair k * nblk + block -> warp group i % 4; warp q4 of the group owns keys 32 q4 .. 32 q4 + 31 of the block
+  // (all 16 warps busy on four blocks at a time: the shared-memory latency is hidden by the other warps of the scheduler)
+  const int grp = w >> 2, q4 = w & 3, kbase = 32 * q4;
+  const int kp = lane & 15, chh = lane >> 4;           // q . K^T: lane = (key pair, channel half)
+  const int kq = lane >> 3, cg = lane & 7;             // P . V:   lane = (key mod 4, channel group of 8)
+  float* pwq = fa + DP_A_PW + w * 32;
+  int cur = -1;
+  float m_run = -INFINITY, l_run = 0.f, o[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) o[c] = 0.f;
+  auto flush = [&](int k) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      o[c] += __shfl_xor_sync(0xffffffffu, o[c], 8);
+      o[c] += __shfl_xor_sync(0xffffffffu, o[c], 16);
+    }
+    float* t = tab + (k * 16 + w) * DP_PART;
+    if (lane < 8) {
+      *reinterpret_cast<float4*>(t + 4 + lane * 8) = make_float4(o[0], o[1], o[2], o[3]);
+      *reinterpret_cast<float4*>(t + 8 + lane * 8) = make_float4(o[4], o[5], o[6], o[7]);
+    }
+    if (lane == 0) { t[0] = m_run; t[1] = l_run; }
+  };
   for (int i = grp; i < nun; i += 4) {
-    const int u = u0 + i, bh = u / nblk, blk = u - bh * nblk, bi = bh - bh_first;
+    const int k = i / nblk, blk = i - k * nblk;
+    if (k != cur) {
+      if (cur >= 0) flush(cur);
+      cur = k; m_run = -INFINITY; l_run = 0.f;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) o[c] = 0.f;
+    }
     const int j0 = blk << 7, cnt = min(128, n - j0);
     const unsigned int sq = seq + (unsigned)i;
+    if (w == 0) fine(5);
     ring_wait_prev_released(sm, sq);
+    if (w == 0) fine(8);
     ring_wait_full(sm, sq);
-    fine(4);
-    __half* Ks = reinterpret_cast<__half*>(sm.ring[sq % DP_NSLOT]);                 // [64 channels][128 keys]
-    __half* Vs = Ks + 64 * 128;                                                     // [cnt keys][64 channels]
-    if (blk == nblk - 1) {               // the staged copy of key r is stale: take it from the freshly computed k / v
-      if (tg < 64) {
-        Ks[tg * 128 + (r - j0)] = __float2half_rn(kn[bi * 64 + tg]);
-        Vs[(r - j0) * 64 + tg] = __float2half_rn(vn[bi * 64 + tg]);
+    if (w == 0) fine(4);
+    if (kbase < cnt && !(p.dbg & 1)) {
+      __half* Ks = reinterpret_cast<__half*>(sm.ring[sq % DP_NSLOT]);               // [64 channels][128 keys]
+      __half* Vs = Ks + 64 * 128;                                                   // [cnt keys][64 channels]
+      const int jr = r - j0;
+      if (blk == nblk - 1 && jr >= kbase && jr < kbase + 32) {      // the staged copy of key r is stale: take it from the freshly computed k / v
+        Ks[lane * 128 + jr] = __float2half_rn(kn[k * 64 + lane]);
+        Ks[(lane + 32) * 128 + jr] = __float2half_rn(kn[k * 64 + lane + 32]);
+        *reinterpret_cast<__half2*>(Vs + jr * 64 + 2 * lane) = __floats2half2_rn(vn[k * 64 + 2 * lane], vn[k * 64 + 2 * lane + 1]);
         fence_proxy_async();             // generic-proxy writes into a slot the async proxy (cp.async.bulk) refills later
+        __syncwarp();
       }
-      bar_group(grp);
-    }
-    // ---- q . K^T: thread = (key pair, channel half); 32 conflict-free half2 loads against 32 q values held in registers
-    {
-      const int kp = tg & 63, ch = tg >> 6;
-      float qr[32];
-      const float4* q4 = reinterpret_cast<const float4*>(qs + bi * 64 + ch * 32);
+      // ---- scores of keys kbase + 2 kp, + 1: each half-warp sums 32 channels
+      float a0 = 0.f, a1 = 0.f;
+      {
+        const float4* q4p = reinterpret_cast<const float4*>(qs + k * 64 + chh * 32);
+        const uint32_t* K2 = reinterpret_cast<const uint32_t*>(Ks) + (chh * 32) * 64 + 16 * q4 + kp;      // + c * 64: channel chh * 32 + c
 #pragma unroll
-      for (int c4 = 0; c4 < 8; ++c4) {
-        const float4 t4 = q4[c4];
-        qr[4 * c4] = t4.x; qr[4 * c4 + 1] = t4.y; qr[4 * c4 + 2] = t4.z; qr[4 * c4 + 3] = t4.w;
-      }
-      const __half2* K2 = reinterpret_cast<const __half2*>(Ks) + (size_t)(ch * 32) * 64 + kp;
-      float ax0 = 0.f, ay0 = 0.f, ax1 = 0.f, ay1 = 0.f;
+        for (int c4 = 0; c4 < 8; ++c4) {
+          const float4 qv = q4p[c4];
+          const float qq[4] = {qv.x, qv.y, qv.z, qv.w};
 #pragma unroll
-      for (int c = 0; c < 32; c += 2) {
-        const float2 ka = __half22float2(K2[c * 64]), kb = __half22float2(K2[(c + 1) * 64]);
-        ax0 = fmaf(qr[c], ka.x, ax0); ay0 = fmaf(qr[c], ka.y, ay0);
-        ax1 = fmaf(qr[c + 1], kb.x, ax1); ay1 = fmaf(qr[c + 1], kb.y, ay1);
-      }
-      *reinterpret_cast<float2*>(pd + (grp * 2 + ch) * 128 + 2 * kp) = make_float2(ax0 + ax1, ay0 + ay1);
-    }
-    bar_group(grp);
-    // ---- scores and block softmax: thread = key
-    float sc = -INFINITY;
-    if (tg < cnt) {
-      sc = ((pd[(grp * 2) * 128 + tg] + pd[(grp * 2 + 1) * 128 + tg]) + biasrow[j0 + tg]) * p.scale;
-      if (L.layout != nullptr) {
-        const int h = bh % H;
-        if (!L.layout[((size_t)h * p.lay_ld + r / p.lay_blk) * p.lay_ld + (j0 + tg) / p.lay_blk]) sc = -INFINITY;
-      }
-    }
-    float m = sc;
-    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if (lane == 0) gr[grp * 4 + wg] = m;
-    bar_group(grp);
-    m = fmaxf(fmaxf(gr[grp * 4], gr[grp * 4 + 1]), fmaxf(gr[grp * 4 + 2], gr[grp * 4 + 3]));
-    const float e = (sc == -INFINITY) ? 0.f : expf(sc - m);
-    ps[grp * 128 + tg] = e;
-    float su = e;
-    for (int o = 16; o; o >>= 1) su += __shfl_xor_sync(0xffffffffu, su, o);
-    bar_group(grp);                       // gr[] max values consumed, ps[] published
-    if (lane == 0) gr[grp * 4 + wg] = su;
-    // ---- P . V: thread = (channel pair, key quarter); rows >= cnt of the slot are stale bytes and must not be touched
-    {
-      const int ja = wg * 32, jb = min(cnt, ja + 32);
-      const __half2* V2 = reinterpret_cast<const __half2*>(Vs) + lane;
-      const float* pr = ps + grp * 128;
-      float ox0 = 0.f, oy0 = 0.f, ox1 = 0.f, oy1 = 0.f;
-      if (jb - ja == 32) {
-#pragma unroll
-        for (int jj = 0; jj < 32; jj += 4) {
-          const float4 p4 = *reinterpret_cast<const float4*>(pr + ja + jj);
-          const float2 v0 = __half22float2(V2[(ja + jj) * 32]), v1 = __half22float2(V2[(ja + jj + 1) * 32]);
-          const float2 v2 = __half22float2(V2[(ja + jj + 2) * 32]), v3 = __half22float2(V2[(ja + jj + 3) * 32]);
-          ox0 = fmaf(p4.x, v0.x, ox0); oy0 = fmaf(p4.x, v0.y, oy0);
-          ox1 = fmaf(p4.y, v1.x, ox1); oy1 = fmaf(p4.y, v1.y, oy1);
-          ox0 = fmaf(p4.z, v2.x, ox0); oy0 = fmaf(p4.z, v2.y, oy0);
-          ox1 = fmaf(p4.w, v3.x, ox1); oy1 = fmaf(p4.w, v3.y, oy1);
+          for (int cc = 0; cc < 4; ++cc) {
+            const uint32_t kk = K2[(c4 * 4 + cc) * 64];
+            const float2 kf = __half22float2(*reinterpret_cast<const __half2*>(&kk));
+            a0 = fmaf(qq[cc], kf.x, a0); a1 = fmaf(qq[cc], kf.y, a1);
+          }
         }
-      } else {
-        for (int j = ja; j < jb; ++j) {
-          const float2 v0 = __half22float2(V2[j * 32]);
-          ox0 = fmaf(pr[j], v0.x, ox0); oy0 = fmaf(pr[j], v0.y, oy0);
+        a0 += __shfl_xor_sync(0xffffffffu, a0, 16);
+        a1 += __shfl_xor_sync(0xffffffffu, a1, 16);
+      }
+      const int key0 = kbase + 2 * kp;
+      float sc0, sc1;
+      {
+        const float2 b2 = *reinterpret_cast<const float2*>(biasrow + j0 + key0);
+        sc0 = (a0 + b2.x) * p.scale; sc1 = (a1 + b2.y) * p.scale;
+        bool ok0 = key0 < cnt, ok1 = key0 + 1 < cnt;
+        if (L.layout != nullptr) {
+          ok0 = ok0 && layrow[k * DP_MAXLB + (j0 + key0) / p.lay_blk] != 0;
+          ok1 = ok1 && layrow[k * DP_MAXLB + (j0 + key0 + 1) / p.lay_blk] != 0;
+        }
+        if (!ok0) sc0 = -INFINITY;
+        if (!ok1) sc1 = -INFINITY;
+      }
+      float mb = fmaxf(sc0, sc1);
+      for (int of = 8; of; of >>= 1) mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, of));
+      const float m_new = fmaxf(m_run, mb);
+      const float p0 = (sc0 == -INFINITY) ? 0.f : expf(sc0 - m_new), p1 = (sc1 == -INFINITY) ? 0.f : expf(sc1 - m_new);
+      float su = p0 + p1;
+      for (int of = 8; of; of >>= 1) su += __shfl_xor_sync(0xffffffffu, su, of);
+      const float corr = (m_run == -INFINITY) ? 0.f : expf(m_run - m_new);
+      l_run = l_run * corr + su;
+      m_run = m_new;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) o[c] *= corr;
+      if (chh == 0) *reinterpret_cast<float2*>(pwq + 2 * kp) = make_float2(p0, p1);
+      __syncwarp();
+      // ---- P . V over the warp's keys; rows >= cnt of the slot are stale bytes and must not be touched
+      {
+        const uint4* V8 = reinterpret_cast<const uint4*>(Vs) + (kbase + kq) * 8 + cg;         // + ii * 32: key kbase + 4 ii + kq
+        const float* pk = pwq + kq;
+        auto fma8 = [&](float pv, const uint4& vv) {
+          const float2 v01 = __half22float2(*reinterpret_cast<const __half2*>(&vv.x)), v23 = __half22float2(*reinterpret_cast<const __half2*>(&vv.y));
+          const float2 v45 = __half22float2(*reinterpret_cast<const __half2*>(&vv.z)), v67 = __half22float2(*reinterpret_cast<const __half2*>(&vv.w));
+          o[0] = fmaf(pv, v01.x, o[0]); o[1] = fmaf(pv, v01.y, o[1]); o[2] = fmaf(pv, v23.x, o[2]); o[3] = fmaf(pv, v23.y, o[3]);
+          o[4] = fmaf(pv, v45.x, o[4]); o[5] = fmaf(pv, v45.y, o[5]); o[6] = fmaf(pv, v67.x, o[6]); o[7] = fmaf(pv, v67.y, o[7]);
+        };
+        const int nk = min(32, cnt - kbase);
+        if (nk == 32) {
+#pragma unroll
+          for (int ii = 0; ii < 8; ++ii) fma8(pk[4 * ii], V8[ii * 32]);
+        } else {
+          const int nit = (nk + 3) >> 2;
+          for (int ii = 0; ii < nit; ++ii)
+            if (4 * ii + kq < nk) fma8(pk[4 * ii], V8[ii * 32]);
         }
       }
-      *reinterpret_cast<float2*>(op + (grp * 4 + wg) * 64 + 2 * lane) = make_float2(ox0 + ox1, oy0 + oy1);
     }
-    bar_group(grp);
-    if (tg < 64)
-      att_tab[i][4 + tg] = (op[(grp * 4) * 64 + tg] + op[(grp * 4 + 1) * 64 + tg]) + (op[(grp * 4 + 2) * 64 + tg] + op[(grp * 4 + 3) * 64 + tg]);
-    if (tg == 0) {
-      att_tab[i][0] = m;
-      att_tab[i][1] = (gr[grp * 4] + gr[grp * 4 + 1]) + (gr[grp * 4 + 2] + gr[grp * 4 + 3]);
-    }
-    bar_group(grp);                       // the slot and the group scratch are free again
-    if (tg == 0) ring_release(sm, sq);
-    fine(5);
+    __syncwarp();                         // every lane is done with the slot and with pw[]
+    if (lane == 0) ring_release_shared(sm, sq, 4u);
+    if (w == 0) fine(5);
   }
+  if (cur >= 0) flush(cur);
   seq += (unsigned)nun;
-  bar_consumers();
   fine(5);
-  // ---- merge the units of each (scene, head) this CTA touched; one warp per pair, 2 channels per lane
-  for (int bi = w; bi < nbh; bi += 16) {
-    const int bh = bh_first + bi, b = bh / H, h = bh - b * H;
-    const int ua = max(u0, bh * nblk), ub = min(u1, (bh + 1) * nblk);
+  bar_consumers();
+  fine(9);
+  // ---- merge the 16 per-warp partials of each pair (fixed order), 2 channels per lane
+  if (w < npairs) {
+    const int bh = bx + w * G, b = bh / H, h = bh - b * H;
+    const float* t = tab + (w * 16) * DP_PART;
     float M = -INFINITY;
-    for (int u = ua; u < ub; ++u) M = fmaxf(M, att_tab[u - u0][0]);
+#pragma unroll
+    for (int ww = 0; ww < 16; ++ww) M = fmaxf(M, t[ww * DP_PART]);
     float Ls = 0.f, o0 = 0.f, o1 = 0.f;
-    for (int u = ua; u < ub; ++u) {
-      const float* tb = att_tab[u - u0];
-      const float wgt = (tb[0] == -INFINITY) ? 0.f : expf(tb[0] - M);
+#pragma unroll
+    for (int ww = 0; ww < 16; ++ww) {
+      const float* tb = t + ww * DP_PART;
+      if (tb[0] == -INFINITY) continue;     // a warp without a block of this pair (its o[] is whatever the scratch held)
+      const float wgt = expf(tb[0] - M);
       Ls += tb[1] * wgt;
       o0 += tb[4 + lane] * wgt;
       o1 += tb[4 + 32 + lane] * wgt;
     }
-    if (ub - ua == nblk) {               // every key block of this (scene, head) was ours
-      finish_head(p, sm, L, b, h, lane, o0 / Ls, o1 / Ls);
-      continue;
-    }
-    // Shared with other CTAs: leave the merged partial in the slot of our first block and add (1 << slot) << 32 | blocks to the pair's
-    // 64-bit ticket with ONE acq_rel atomic (releases the partial, acquires the others').  Whoever brings the block count to nblk
-    // merges the partials in slot order (the high word says which slots were written): deterministic, no waiting.
-    const int slot = ua - bh * nblk;
-    float* pp = p.ATTP + ((size_t)bh * DP_MAXPARTS + slot) * DP_PART;
-    pp[4 + lane] = o0;
-    pp[4 + 32 + lane] = o1;
-    if (lane == 0) { pp[0] = M; pp[1] = Ls; }
-    __syncwarp();
-    unsigned long long tk = 0ull;
-    if (lane == 0) tk = atom_add_acq_rel_u64(p.tick_att + bh, ((unsigned long long)(1u << slot) << 32) | (unsigned long long)(ub - ua));
-    tk = __shfl_sync(0xffffffffu, tk, 0);
-    tk += ((unsigned long long)(1u << slot) << 32) | (unsigned long long)(ub - ua);
-    if ((unsigned int)(tk & 0xffffffffull) != (unsigned)nblk) continue;
-    unsigned int mask = (unsigned int)(tk >> 32);
-    const float* base = p.ATTP + (size_t)bh * DP_MAXPARTS * DP_PART;
-    float MM = -INFINITY, LL = 0.f, a0 = 0.f, a1 = 0.f;
-    while (mask) {
-      const int i = __ffs(mask) - 1;
-      mask &= mask - 1u;
-      const float mi = __ldcg(base + i * DP_PART), li = __ldcg(base + i * DP_PART + 1);
-      const float x0 = __ldcg(base + i * DP_PART + 4 + lane), x1 = __ldcg(base + i * DP_PART + 4 + 32 + lane);
-      const float Mn = fmaxf(MM, mi);
-      const float wo = (MM == -INFINITY) ? 0.f : expf(MM - Mn), wn = (mi == -INFINITY) ? 0.f : expf(mi - Mn);
-      LL = LL * wo + li * wn;
-      a0 = a0 * wo + x0 * wn;
-      a1 = a1 * wo + x1 * wn;
-      MM = Mn;
-    }
-    finish_head(p, sm, L, b, h, lane, a0 / LL, a1 / LL);
-    if (lane == 0) p.tick_att[bh] = 0ull;
+    finish_head(p, sm, L, b, h, lane, o0 / Ls, o1 / Ls);
   }
   fine(6);
 }
@@ -842,18 +922,20 @@ __device__ __noinline__ void embed_row(const DecodeParams& p, DpSmem& sm, int b,
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
-__global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(const DecodeParams p) {
+__global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(const __grid_constant__ DecodeParams p) {
   extern __shared__ __align__(1024) uint8_t dp_raw[];
   DpSmem& sm = *reinterpret_cast<DpSmem*>(dp_raw);
   const int tid = threadIdx.x;
   if (tid == 0) {
     for (int i = 0; i < DP_NSLOT; ++i) { mbar_init(&sm.full[i], 1); mbar_init(&sm.empty[i], 1); }
     mbar_init(&sm.act_bar, 1);
+    mbar_init(&sm.bias_bar, 1);
     fence_barrier_init();
     sm.debug = p.debug;
     sm.where[0] = sm.where[1] = sm.where[2] = 0u;
-    for (int i = 0; i < DP_NSLOT; ++i) sm.rel[i] = 0xffffffffu;
-    for (int i = 0; i < 8; ++i) sm.fine[i] = 0ull;
+    for (int i = 0; i < DP_NSLOT; ++i) { sm.rel[i] = 0xffffffffu; sm.slotcnt[i] = 0u; }
+    for (int i = 0; i < 20; ++i) sm.fine[i] = 0ull;
+    for (int i = 0; i < 12; ++i) sm.prof[i] = 0ull;
     sm.att_epoch = 0u;
   }
   __syncthreads();
@@ -861,9 +943,11 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(const 
     if (tid == DP_CONSUMERS) dp_producer(p, sm);
     return;
   }
-  unsigned int seq = 0, bar_target = 0, act_par = 0;
+  unsigned int seq = 0, bar_target = 0, act_par = 0, bias_par = 0;
   const unsigned int G = gridDim.x;
   const int d = p.d, H = p.H;
+  const bool has_pairs = (int)blockIdx.x < p.B * H;
+  const bool tma_bias = p.bias != nullptr && (p.bias_ld & 3) == 0;
   // X <- embedding of the token drawn at step step_begin - 1 (it is already in the token grid)
   if ((int)blockIdx.x < p.B) {
     const int b = blockIdx.x, sdec = p.step_begin - 1;
@@ -872,14 +956,11 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(const 
   }
   grid_sync(sm, p.barrier, bar_target, G);
   // optional per-CTA profile: nanoseconds spent in each phase body and in each phase's grid barrier, summed over the launch
-  unsigned long long prof[12];
-#pragma unroll
-  for (int i = 0; i < 12; ++i) prof[i] = 0ull;
   unsigned long long tmark = dp_globaltimer();
   auto mark = [&](int slot, unsigned int step, unsigned int layer, unsigned int phase) {
     if (tid == 0) {
       const unsigned long long now = dp_globaltimer();
-      prof[slot] += now - tmark;
+      sm.prof[slot] += now - tmark;
       tmark = now;
       sm.where[0] = step; sm.where[1] = layer; sm.where[2] = phase;
     }
@@ -889,10 +970,17 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(const 
       const DecodeLayer& L = p.layers[l];
       mark(11, s, l, 0);
       linear_phase(p, sm, seq, act_par, EPI_QKV, p.XF, p.PSX, d >> 3, 0, 3 * d / 8, L.s_qkv, L.c1_qkv, L.c2_qkv);
+      if (tid == 0 && has_pairs && tma_bias) {
+        // camera-bias row of this step -> upper half of act[] (free since the fragments went to registers); waited for in the attention phase
+        const int n = p.nc + s;
+        const uint32_t bytes = (uint32_t)((n + 3) & ~3) * 4u;
+        mbar_expect_tx(&sm.bias_bar, bytes);
+        dp_bulk_g2s(sm.act + DP_A_BIAS * 4, p.bias + (size_t)(n - 1) * p.bias_ld, bytes, &sm.bias_bar);
+      }
       mark(0, s, l, 1);
       grid_sync(sm, p.barrier, bar_target, G);
       mark(1, s, l, 2);
-      attention_phase(p, sm, seq, act_par, L, s);
+      attention_phase(p, sm, seq, bias_par, L, s);
       mark(2, s, l, 3);
       grid_sync(sm, p.barrier, bar_target, G);
       if (tid == 0) sm.att_epoch = (unsigned)(s - p.step_begin) * (unsigned)p.n_layers + (unsigned)l + 1u;      // every CTA's appends of (s, l) are visible
@@ -901,7 +989,7 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(const 
       mark(4, s, l, 5);
       grid_sync(sm, p.barrier, bar_target, G);
       mark(5, s, l, 6);
-      linear_phase(p, sm, seq, act_par, EPI_MLP2, p.HF, nullptr, 0, 0, 4 * (d / 8), L.s_2, nullptr, L.c2_2);
+      mlp2_phase(p, sm, seq, act_par, L);
       mark(6, s, l, 7);
       grid_sync(sm, p.barrier, bar_target, G);
       mark(7, s, l, 8);
@@ -925,8 +1013,8 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(const 
   }
   if (tid == 0 && p.profile != nullptr) {
 #pragma unroll
-    for (int i = 0; i < 12; ++i) p.profile[(size_t)blockIdx.x * 20 + i] = prof[i];
-    for (int i = 0; i < 8; ++i) p.profile[(size_t)blockIdx.x * 20 + 12 + i] = sm.fine[i];
+    for (int i = 0; i < 12; ++i) p.profile[(size_t)blockIdx.x * 32 + i] = sm.prof[i];
+    for (int i = 0; i < 10; ++i) p.profile[(size_t)blockIdx.x * 32 + 12 + i] = sm.fine[i];
   }
 }
 
@@ -994,9 +1082,10 @@ long long decode_packed_bytes(int n_rows, int d, int n_quarters) {
 
 void decode_workspace_sizes(int B, int d, int H, int vocab, long long* n_floats, long long* n_counters) {
   const long long vpad = (vocab + 7) / 8 * 8;
-  *n_floats = 16LL * d * 2 /*X, X1*/ + 16LL * 3 * d /*QKV*/ + 4LL * 16 * d /*P2*/ + 16LL * vpad /*LOGITS*/ + 16LL * (d / 8) * 2 + 16LL * H * 2 /*PSX, PSX1*/ +
-              16LL * d * 2 /*XF, X1F*/ + 4LL * 16 * d /*HF*/ + (long long)B * H * DP_MAXPARTS * DP_PART;
-  *n_counters = 64 + 2LL * B * H + d / 8;
+  *n_floats = 16LL * d * 2 /*X, X1*/ + 16LL * 3 * d /*QKV*/ + 16LL * vpad /*LOGITS*/ + 16LL * (d / 8) * 2 + 16LL * H * 2 /*PSX, PSX1*/ +
+              16LL * d * 2 /*XF, X1F*/ + 4LL * 16 * d /*HF*/;
+  *n_counters = 64;
+  (void)B;
 }
 
 int launch_decode_persistent(DecodeParams p, float* ws, unsigned int* counters, int sm_count, cudaStream_t st) {
@@ -1006,26 +1095,23 @@ int launch_decode_persistent(DecodeParams p, float* ws, unsigned int* counters, 
     return BEVGEN_ERR_ARG;
   if (p.step_begin == p.step_end) return BEVGEN_OK;
   const int G = sm_count;
-  const int nblk_max = p.Lmax >> 7;
-  if ((p.B * p.H * nblk_max + G - 1) / G + 1 > DP_MAXATT) return BEVGEN_ERR_ARG;
-  if ((p.B * p.H + G - 1) / G + 2 > DP_MAXBH) return BEVGEN_ERR_ARG;
+  if ((p.B * p.H + G - 1) / G > DP_MAXBH) return BEVGEN_ERR_ARG;
+  for (int l = 0; l < 1; ++l)
+    if (p.lay_ld > 0 && (p.lay_blk < 16 || (p.Lmax + p.lay_blk - 1) / p.lay_blk > DP_MAXLB)) return BEVGEN_ERR_ARG;
   p.vpad = (p.vocab + 7) / 8 * 8;
+  if (const char* e = getenv("BEVGEN_DP_DBG")) p.dbg = atoi(e);      // timing experiments only (results are garbage): see tools/decode_debug.py
   float* f = ws;
   p.X = f; f += 16 * d;
   p.X1 = f; f += 16 * d;
   p.QKV = f; f += 16 * 3 * d;
-  p.P2 = f; f += 4 * 16 * d;
   p.LOGITS = f; f += 16 * p.vpad;
   p.PSX = f; f += 16 * (d / 8) * 2;
   p.PSX1 = f; f += 16 * p.H * 2;
   p.XF = reinterpret_cast<uint8_t*>(f); f += 16 * d;          // 16 x d x (2 + 2) bytes
   p.X1F = reinterpret_cast<uint8_t*>(f); f += 16 * d;
   p.HF = reinterpret_cast<uint8_t*>(f); f += 4 * 16 * d;
-  p.ATTP = f;
   p.barrier = counters;
-  p.tick_att = reinterpret_cast<unsigned long long*>(counters + 64);          // 64-bit tickets (8-byte aligned: the buffer is 256-byte aligned)
-  p.tick_mlp2 = counters + 64 + 2 * p.B * p.H;
-  if (cudaMemsetAsync(counters, 0, sizeof(unsigned int) * (64 + 2 * (size_t)p.B * p.H + d / 8), st) != cudaSuccess) return BEVGEN_ERR_CUDA;
+  if (cudaMemsetAsync(counters, 0, sizeof(unsigned int) * 64, st) != cudaSuccess) return BEVGEN_ERR_CUDA;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(decode_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DpSmem)) != cudaSuccess) return BEVGEN_ERR_CUDA;

@@ -195,12 +195,12 @@ struct DecodeParams {
   float* trace;                    // [n_img][B][vocab] or NULL
   int lay_blk, lay_ld;
   // workspace (filled by the launcher)
-  float *X, *X1, *QKV, *P2, *LOGITS, *PSX, *PSX1, *ATTP;
+  float *X, *X1, *QKV, *LOGITS, *PSX, *PSX1;
   uint8_t *XF, *X1F, *HF;          // activation vectors in mma A-fragment order (fp16 hi + lo)
-  unsigned int *barrier, *tick_mlp2;
-  unsigned long long* tick_att;
+  unsigned int* barrier;
+  int dbg;                         // timing experiments (BEVGEN_DP_DBG): 1 skip attention math, 2 skip linear MMAs, 4 skip activation fetches, 8 producer copies nothing
   unsigned int* debug;             // optional pinned HOST buffer (8 uint32, zeroed): timeout diagnostics written before the trap
-  unsigned long long* profile;     // optional [grid][20] nanoseconds per phase (bodies and grid barriers), device memory
+  unsigned long long* profile;     // optional [grid][32] nanoseconds per phase (bodies and grid barriers), device memory
 };
 int launch_decode_persistent(DecodeParams p, float* ws, unsigned int* counters, int sm_count, cudaStream_t st);
 int launch_pack_decode_linear(const float* W, int n_rows, int ld, int d, int n_quarters, float lo_mul, void* out, cudaStream_t st);

@@ -92,8 +92,8 @@ class GPTSampler:
 
     PROFILE_SLOTS = ("qkv", "qkv_barrier", "attention", "attention_barrier", "mlp1", "mlp1_barrier", "mlp2", "mlp2_barrier", "head", "head_barrier",
                      "sample_embed", "sample_barrier",
-                     "fine_afrag", "fine_linear_ring_wait", "fine_linear_math", "fine_attn_prologue", "fine_attn_ring_wait", "fine_attn_unit_math", "fine_attn_merge",
-                     "fine_unused")
+                     "fine_afrag", "fine_linear_ring_wait", "fine_linear_math", "fine_attn_prologue", "fine_attn_wait_full_w0", "fine_attn_units_w0", "fine_attn_merge",
+                     "fine_mlp2", "fine_attn_wait_prev_w0", "fine_attn_end_barrier", "producer_ring_full_weights", "producer_ring_full_attn", "producer_epoch_gate")
 
     def last_profile(self):
         """Per-phase milliseconds of the last persistent launch (mean over CTAs; the kernel's own %globaltimer marks)."""
@@ -210,7 +210,7 @@ class GPTSampler:
         a.workspace, a.counters = pk["ws"].data_ptr(), pk["cnt"].data_ptr()
         if "dbg" not in pk:
             pk["dbg"] = torch.zeros(8, dtype=torch.int32).pin_memory()           # readable by the host after a time-out trap
-            pk["prof"] = torch.zeros((lib.bevgen_sm_count(), 20), dtype=torch.int64, device=e.dev)
+            pk["prof"] = torch.zeros((lib.bevgen_sm_count(), 32), dtype=torch.int64, device=e.dev)
         pk["dbg"].zero_()
         a.debug, a.profile = pk["dbg"].data_ptr(), pk["prof"].data_ptr()
         ops.Stats.launches += 1

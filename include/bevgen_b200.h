@@ -346,7 +346,7 @@ typedef struct bevgen_decode_args {
   float* workspace;                  /* bevgen_decode_workspace(...) floats */
   unsigned int* counters;            /* bevgen_decode_workspace(...) uint32 (zeroed by the call) */
   unsigned int* debug;               /* optional pinned HOST buffer of 8 zeroed uint32: a barrier / ring time-out (4 s) leaves (code, CTA, step, layer, phase, ...) here before trapping */
-  unsigned long long* profile;       /* optional device buffer [sm_count][20]: ns per phase body / grid barrier, summed over the launch */
+  unsigned long long* profile;       /* optional device buffer [sm_count][32]: ns per phase body / grid barrier, summed over the launch */
 } bevgen_decode_args;
 
 BEVGEN_API int bevgen_decode_persistent(const bevgen_decode_args* args, void* stream);

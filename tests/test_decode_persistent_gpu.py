@@ -43,15 +43,15 @@ def _one_layer_case(layers=1, B=3):
 
 
 def _ws_views(smp, cfg, B):
-    """The kernel's workspace layout (launch_decode_persistent): X, X1 [16][d], QKV [16][3d], P2 [4][16][d], LOGITS [16][vpad], ..."""
+    """The kernel's workspace layout (launch_decode_persistent): X, X1 [16][d], QKV [16][3d], LOGITS [16][vpad], ..."""
     d, ws = cfg.num_embed, smp._pk["ws"]
     o, out = 0, {}
-    for name, n in (("X", 16 * d), ("X1", 16 * d), ("QKV", 16 * 3 * d), ("P2", 4 * 16 * d)):
+    for name, n in (("X", 16 * d), ("X1", 16 * d), ("QKV", 16 * 3 * d)):
         out[name] = ws[o:o + n]
         o += n
     vpad = (cfg.vocab_size + 7) // 8 * 8
     out["LOGITS"] = ws[o:o + 16 * vpad]
-    return {k: (v.view(16, -1) if k != "P2" else v.view(4, 16, d)) for k, v in out.items()}
+    return {k: v.view(16, -1) for k, v in out.items()}
 
 
 @pytest.mark.parametrize("last_step", [1, 129, 257, 258, 260, 769])
