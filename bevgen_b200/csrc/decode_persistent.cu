@@ -238,12 +238,13 @@ __device__ __noinline__ void dp_producer(const DecodeParams& p, DpSmem& sm) {
   const int d = p.d, KG = d >> 6, upq = d >> 3;
   const uint32_t unit_bytes = (uint32_t)KG * DP_KG_BYTES;
   unsigned long long tw = 0ull, ta = 0ull, te = 0ull;
+  const bool prof = p.profile != nullptr;
   auto issue_unit = [&](const uint8_t* src) {
     const unsigned int slot = seq % DP_NSLOT;
     if (seq >= (unsigned)DP_NSLOT) {
-      const unsigned long long t0 = dp_globaltimer();
+      const unsigned long long t0 = prof ? dp_globaltimer() : 0ull;
       dp_mbar_wait(sm, &sm.empty[slot], ((seq / DP_NSLOT) - 1u) & 1u, 3u, seq);
-      tw += dp_globaltimer() - t0;
+      if (prof) tw += dp_globaltimer() - t0;
     }
     if (p.dbg & 8) mbar_arrive(&sm.full[slot]);
     else {
@@ -285,9 +286,9 @@ __device__ __noinline__ void dp_producer(const DecodeParams& p, DpSmem& sm) {
           for (int blk = 0; blk < nblk; ++blk, ++seq) {
             const unsigned int slot = seq % DP_NSLOT;
             if (seq >= (unsigned)DP_NSLOT) {
-              const unsigned long long t0 = dp_globaltimer();
+              const unsigned long long t0 = prof ? dp_globaltimer() : 0ull;
               dp_mbar_wait(sm, &sm.empty[slot], ((seq / DP_NSLOT) - 1u) & 1u, 3u, seq);
-              ta += dp_globaltimer() - t0;
+              if (prof) ta += dp_globaltimer() - t0;
             }
             const int cnt = min(128, n - blk * 128);
             const uint32_t kbytes = 64u * 128u * 2u, vbytes = (uint32_t)cnt * 128u;
@@ -387,8 +388,8 @@ __device__ __noinline__ void linear_phase(const DecodeParams& p, DpSmem& sm, uns
   float* red = reinterpret_cast<float*>(sm.act);
   int u0, u1;
   part_range(U, u0, u1);
-  unsigned long long tf = dp_globaltimer();
-  auto fine = [&](int k) { if (tid == 0) { const unsigned long long now = dp_globaltimer(); sm.fine[k] += now - tf; tf = now; } };
+  unsigned long long tf = p.profile != nullptr ? dp_globaltimer() : 0ull;
+  auto fine = [&](int k) { if (tid == 0 && p.profile != nullptr) { const unsigned long long now = dp_globaltimer(); sm.fine[k] += now - tf; tf = now; } };
   const bool fetch = !(p.dbg & 4);
   if (u1 > u0 && tid == 0 && fetch) {
     fence_proxy_async();
@@ -456,8 +457,8 @@ __device__ __noinline__ void mlp2_phase(const DecodeParams& p, DpSmem& sm, unsig
   int r0, r1;
   part_range(upq, r0, r1);
   if (r0 == r1) return;
-  unsigned long long tf = dp_globaltimer();
-  auto fine = [&](int k) { if (tid == 0) { const unsigned long long now = dp_globaltimer(); sm.fine[k] += now - tf; tf = now; } };
+  unsigned long long tf = p.profile != nullptr ? dp_globaltimer() : 0ull;
+  auto fine = [&](int k) { if (tid == 0 && p.profile != nullptr) { const unsigned long long now = dp_globaltimer(); sm.fine[k] += now - tf; tf = now; } };
   const int fb = tid >> 3, fn = tid & 7;                 // finalisation mapping (threads 0..127): 8 consecutive lanes = one batch row
   for (int ru = r0; ru < r1; ++ru) {
     const bool fetch = !(p.dbg & 4);
@@ -550,8 +551,8 @@ __device__ __noinline__ void attention_phase(const DecodeParams& p, DpSmem& sm, 
   const int npairs = bx < BH ? (BH - 1 - bx) / G + 1 : 0;
   if (npairs == 0) return;
   const int nun = npairs * nblk;
-  unsigned long long tf = dp_globaltimer();
-  auto fine = [&](int k) { if (tid == 0) { const unsigned long long now = dp_globaltimer(); sm.fine[k] += now - tf; tf = now; } };
+  unsigned long long tf = p.profile != nullptr ? dp_globaltimer() : 0ull;
+  auto fine = [&](int k) { if (tid == 0 && p.profile != nullptr) { const unsigned long long now = dp_globaltimer(); sm.fine[k] += now - tf; tf = now; } };
   float* fa = reinterpret_cast<float*>(sm.act);
   float* qs = fa + DP_A_QS;                            // [MAXBH][64]   q of every pair
   float* kn = fa + DP_A_KN;                            // [MAXBH][64]   newest key
@@ -959,9 +960,11 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(const 
   unsigned long long tmark = dp_globaltimer();
   auto mark = [&](int slot, unsigned int step, unsigned int layer, unsigned int phase) {
     if (tid == 0) {
-      const unsigned long long now = dp_globaltimer();
-      sm.prof[slot] += now - tmark;
-      tmark = now;
+      if (p.profile != nullptr) {
+        const unsigned long long now = dp_globaltimer();
+        sm.prof[slot] += now - tmark;
+        tmark = now;
+      }
       sm.where[0] = step; sm.where[1] = layer; sm.where[2] = phase;
     }
   };

@@ -80,6 +80,7 @@ class GPTSampler:
         self.fuse_ln2 = True             # ln2 applied by the last head CTA of the decode-attention kernel
         self.use_pdl = True              # programmatic dependent launch along the decode chain (bevgen_set_pdl)
         self.persistent = bool(B <= 16 and kvt == torch.float16)      # one persistent launch for all token steps
+        self.profile_phases = False      # per-phase %globaltimer marks inside the persistent kernel (each read costs ~0.3 us: off by default)
         self._pk = None
         self.graph = None
         self._graph_key = None
@@ -212,7 +213,7 @@ class GPTSampler:
             pk["dbg"] = torch.zeros(8, dtype=torch.int32).pin_memory()           # readable by the host after a time-out trap
             pk["prof"] = torch.zeros((lib.bevgen_sm_count(), 32), dtype=torch.int64, device=e.dev)
         pk["dbg"].zero_()
-        a.debug, a.profile = pk["dbg"].data_ptr(), pk["prof"].data_ptr()
+        a.debug, a.profile = pk["dbg"].data_ptr(), (pk["prof"].data_ptr() if self.profile_phases else None)
         ops.Stats.launches += 1
         _lib.check(lib.bevgen_decode_persistent(C.byref(a), _stream()), "decode_persistent")
 

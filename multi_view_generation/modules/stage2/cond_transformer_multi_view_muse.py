@@ -47,6 +47,7 @@ class Net2NetTransformer(_Base):
     decode_to_img = _ARNet2Net.decode_to_img
     get_input = _ARNet2Net.get_input
     get_xc = _ARNet2Net.get_xc
+    _memo_call = _ARNet2Net._memo_call
 
     def _dev(self):
         return self.maskgit.transformer.to_logits.weight.device

@@ -1,6 +1,6 @@
 """Persistent decode kernel on the full-size model: failure diagnostics + the kernel's own per-phase profile.
 python tools/decode_debug.py <case> [steps]   cases: plain | forced | trace | forced_trace | topk0"""
-import json, sys, time
+import json, os, sys, time
 from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
@@ -24,6 +24,7 @@ def main():
     bd = {k: v.cuda() for k, v in batch.items()}
     forced = cam.reshape(B, -1)[:, cfg.forward_shuffle_idx] if "forced" in case else None
     smp = GPTSampler(eng, B)
+    smp.profile_phases = os.environ.get("DP_PROFILE", "1") == "1"
     kw = dict(temperature=1.0, top_k=None if (case == "topk0" or "forced" in case) else 100, seed=3, forced_tokens=forced, steps=steps)
     res = {"case": case, "steps": steps, "layers": layers}
     try:
