@@ -332,15 +332,19 @@ __device__ __forceinline__ void store_frag(uint8_t* __restrict__ base, int b, in
 enum { EPI_QKV = 0, EPI_MLP1 = 1, EPI_MLP2 = 2, EPI_HEAD = 3 };
 
 // LayerNorm statistics of the 16 rows from the finalisers' partial sums ps[row][part][2] = (sum, sum of squares): warp w = row w.
-__device__ __forceinline__ void combine_row_stats(const DecodeParams& p, DpSmem& sm, const float* __restrict__ ps, int nparts, int which) {
+// Two halves so that the global loads (issued at the start of a phase) are in flight while the activation vector arrives and the MMAs run.
+__device__ __forceinline__ void row_stats_load(const DecodeParams& p, const float* __restrict__ ps, int nparts, float& S, float& Q) {
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float S = 0.f, Q = 0.f;
+  S = 0.f; Q = 0.f;
   if (w < p.B) {
     for (int i = lane; i < nparts; i += 32) {
       const float2 v = __ldcg(reinterpret_cast<const float2*>(ps) + (size_t)w * nparts + i);
       S += v.x; Q += v.y;
     }
   }
+}
+__device__ __forceinline__ void row_stats_finish(const DecodeParams& p, DpSmem& sm, int which, float S, float Q) {
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int o = 16; o; o >>= 1) { S += __shfl_xor_sync(0xffffffffu, S, o); Q += __shfl_xor_sync(0xffffffffu, Q, o); }
   if (lane == 0) {
     const float inv_d = 1.0f / (float)p.d, mean = S * inv_d;
@@ -396,8 +400,9 @@ __device__ __noinline__ void linear_phase(const DecodeParams& p, DpSmem& sm, uns
     mbar_expect_tx(&sm.act_bar, vec_bytes);
     dp_bulk_g2s(sm.act, frag_src, vec_bytes, &sm.act_bar);
   }
-  if (stats != nullptr) combine_row_stats(p, sm, stats, nparts, which);      // read by this phase's epilogue and (LN1) by the attention phase: both behind a barrier
-  if (u1 == u0) return;
+  float rsS, rsQ;
+  row_stats_load(p, stats, nparts, rsS, rsQ);          // consumed after the MMAs: the L2 round trip overlaps the activation fetch
+  if (u1 == u0) { row_stats_finish(p, sm, which, rsS, rsQ); return; }      // (LN1 statistics are also read by the attention phase)
   if (fetch) {
     dp_mbar_wait(sm, &sm.act_bar, act_par & 1u, 6u, (unsigned)u0);
     act_par ^= 1u;
@@ -405,7 +410,7 @@ __device__ __noinline__ void linear_phase(const DecodeParams& p, DpSmem& sm, uns
   uint32_t ahi[4][4], alo[4][4];
   if (w < KG) load_afrag(sm, w, lane, ahi, alo);
   fine(0);
-  bar_consumers();                          // fragments are in registers: act[] becomes the reduction scratch; row statistics are published
+  bar_consumers();                          // fragments are in registers: act[] becomes the reduction scratch
   // output element of a unit owned by this thread: element e -> lane e / 4, register e % 4 of the accumulator fragment -> (batch row, weight row)
   const int ui = tid >> 7, e = tid & 127;
   const int ln = e >> 2, j = e & 3;
@@ -431,10 +436,16 @@ __device__ __noinline__ void linear_phase(const DecodeParams& p, DpSmem& sm, uns
       }
     }
     seq += (unsigned)nb;
+    if (ub == u0) row_stats_finish(p, sm, which, rsS, rsQ);      // published by the barrier below
     bar_consumers();
     if (has) {
-      float v = 0.f;
-      for (int ww = 0; ww < KG; ++ww) v += red[(ui * 16 + ww) * 128 + e];
+      // (ii) four independent partial sums: the 16 shared-memory loads are in flight together
+      float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
+      const float* rp = red + (ui * 16) * 128 + e;
+      int ww = 0;
+      for (; ww + 4 <= KG; ww += 4) { v0 += rp[ww * 128]; v1 += rp[(ww + 1) * 128]; v2 += rp[(ww + 2) * 128]; v3 += rp[(ww + 3) * 128]; }
+      for (; ww < KG; ++ww) v0 += rp[ww * 128];
+      float v = (v0 + v1) + (v2 + v3);
       const float2 st = sm.rowstat[which][b];
       v = st.y * (v - st.x * c1v) + c2v;                                       // lazy LayerNorm + bias
       if (epi == EPI_QKV) p.QKV[(size_t)b * 3 * d + row] = v;
@@ -519,25 +530,8 @@ __device__ __noinline__ void mlp2_phase(const DecodeParams& p, DpSmem& sm, unsig
 }
 
 // ------------------------------------------------------------------------------------------------ attention phase (consumers)
-// The finished attention output of (scene b, head h), two channels per lane: x1 = LN1(x) + attention (Block.forward takes the residual from
-// the LayerNorm OUTPUT, mingpt_sparse.py:242-245) -> fp32 X1 (MLP2's residual), fragment-ordered X1F (MLP1's operand) and this head's
-// partial LayerNorm sums of the row.
-__device__ __forceinline__ void finish_head(const DecodeParams& p, const DpSmem& sm, const DecodeLayer& L, int b, int h, int lane, float o0, float o1) {
-  const int c0 = h * 64 + lane, c1 = c0 + 32;
-  const float2 st = sm.rowstat[0][b];
-  const size_t xi = (size_t)b * p.d;
-  const float y0 = (__ldcg(p.X + xi + c0) - st.x) * st.y * __ldg(L.ln1_g + c0) + __ldg(L.ln1_b + c0);
-  const float y1 = (__ldcg(p.X + xi + c1) - st.x) * st.y * __ldg(L.ln1_g + c1) + __ldg(L.ln1_b + c1);
-  const float x0 = y0 + o0, x1 = y1 + o1;
-  p.X1[xi + c0] = x0;
-  p.X1[xi + c1] = x1;
-  store_frag(p.X1F, b, c0, x0);
-  store_frag(p.X1F, b, c1, x1);
-  float sv = x0 + x1, qv = x0 * x0 + x1 * x1;
-  for (int o = 16; o; o >>= 1) { sv += __shfl_xor_sync(0xffffffffu, sv, o); qv += __shfl_xor_sync(0xffffffffu, qv, o); }
-  if (lane == 0) *reinterpret_cast<float2*>(p.PSX1 + ((size_t)b * p.H + h) * 2) = make_float2(sv, qv);
-}
-
+// The finished attention output of a pair gives x1 = LN1(x) + attention (Block.forward takes the residual from the LayerNorm OUTPUT,
+// mingpt_sparse.py:242-245) -> fp32 X1 (MLP2's residual), fragment-ordered X1F (MLP1's operand) and the head's partial LayerNorm sums of the row.
 // One CTA owns whole (scene, head) pairs (pairs blockIdx.x, blockIdx.x + grid, ...: no partial results cross CTAs).  A staged 128-key block
 // belongs to a group of four warps, each warp to 32 of its keys from the moment the block lands until the slot goes back - no barrier inside
 // a block: lane = (key pair, channel half) for q . K^T (4-byte loads of the transposed block against q broadcast from shared memory, one
@@ -586,7 +580,6 @@ __device__ __noinline__ void attention_phase(const DecodeParams& p, DpSmem& sm, 
       layrow[k * DP_MAXLB + jb] = L.layout[((size_t)h * p.lay_ld + r / p.lay_blk) * p.lay_ld + jb];
     }
   }
-  fence_proxy_async_all();               // the appended key / value will be read by cp.async.bulk (async proxy) in the next step
   if (tma_bias) { dp_mbar_wait(sm, &sm.bias_bar, bias_par & 1u, 7u, (unsigned)n); bias_par ^= 1u; }
   bar_consumers();
   fine(3);
@@ -714,25 +707,42 @@ __device__ __noinline__ void attention_phase(const DecodeParams& p, DpSmem& sm, 
   fine(5);
   bar_consumers();
   fine(9);
-  // ---- merge the 16 per-warp partials of each pair (fixed order), 2 channels per lane
+  // ---- merge the 16 per-warp partials of each pair (fixed order), 2 channels per lane; the residual operands are requested first
   if (w < npairs) {
     const int bh = bx + w * G, b = bh / H, h = bh - b * H;
+    const int c0 = h * 64 + lane, c1 = c0 + 32;
+    const size_t xi = (size_t)b * p.d;
+    const float xa = __ldcg(p.X + xi + c0), xb = __ldcg(p.X + xi + c1);
+    const float ga = __ldg(L.ln1_g + c0), gb = __ldg(L.ln1_g + c1), ba = __ldg(L.ln1_b + c0), bb = __ldg(L.ln1_b + c1);
     const float* t = tab + (w * 16) * DP_PART;
-    float M = -INFINITY;
-#pragma unroll
-    for (int ww = 0; ww < 16; ++ww) M = fmaxf(M, t[ww * DP_PART]);
+    // lane i < 16 owns partial i: its weight exp(m_i - M) is computed once and broadcast
+    const float mi = (lane < 16) ? t[lane * DP_PART] : -INFINITY;
+    float M = mi;
+    for (int of = 8; of; of >>= 1) M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, of));
+    M = __shfl_sync(0xffffffffu, M, 0);
+    const float wi = (mi == -INFINITY) ? 0.f : expf(mi - M);
+    const float li = (lane < 16) ? t[lane * DP_PART + 1] * wi : 0.f;
     float Ls = 0.f, o0 = 0.f, o1 = 0.f;
 #pragma unroll
     for (int ww = 0; ww < 16; ++ww) {
-      const float* tb = t + ww * DP_PART;
-      if (tb[0] == -INFINITY) continue;     // a warp without a block of this pair (its o[] is whatever the scratch held)
-      const float wgt = expf(tb[0] - M);
-      Ls += tb[1] * wgt;
-      o0 += tb[4 + lane] * wgt;
-      o1 += tb[4 + 32 + lane] * wgt;
+      const float wgt = __shfl_sync(0xffffffffu, wi, ww);
+      Ls += __shfl_sync(0xffffffffu, li, ww);
+      if (wgt != 0.f) {                   // a warp without a block of this pair left whatever the scratch held in o[]
+        o0 += t[ww * DP_PART + 4 + lane] * wgt;
+        o1 += t[ww * DP_PART + 4 + 32 + lane] * wgt;
+      }
     }
-    finish_head(p, sm, L, b, h, lane, o0 / Ls, o1 / Ls);
+    const float2 st = sm.rowstat[0][b];
+    const float x0 = ((xa - st.x) * st.y * ga + ba) + o0 / Ls, x1 = ((xb - st.x) * st.y * gb + bb) + o1 / Ls;
+    p.X1[xi + c0] = x0;
+    p.X1[xi + c1] = x1;
+    store_frag(p.X1F, b, c0, x0);
+    store_frag(p.X1F, b, c1, x1);
+    float sv = x0 + x1, qv = x0 * x0 + x1 * x1;
+    for (int of = 16; of; of >>= 1) { sv += __shfl_xor_sync(0xffffffffu, sv, of); qv += __shfl_xor_sync(0xffffffffu, qv, of); }
+    if (lane == 0) *reinterpret_cast<float2*>(p.PSX1 + ((size_t)b * p.H + h) * 2) = make_float2(sv, qv);
   }
+  fence_proxy_async_all();               // the appended key / value will be read by cp.async.bulk (async proxy) in the next step
   fine(6);
 }
 
