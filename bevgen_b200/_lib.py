@@ -4,10 +4,11 @@ There is deliberately no fallback: if the shared library is missing, or a call r
 RuntimeError is raised.  `load()` works without a GPU (symbol checks); the first compute call needs a B200.
 """
 import ctypes as C
+import os
 from pathlib import Path
 
 _HERE = Path(__file__).resolve().parent
-LIB_PATH = _HERE / "libbevgen_b200.so"
+LIB_PATH = Path(os.environ["BEVGEN_B200_LIB"]) if os.environ.get("BEVGEN_B200_LIB") else _HERE / "libbevgen_b200.so"      # override: A/B runs of two builds in one gpurun call
 MAX_TAPS = 9
 
 GF_GELU, GF_OUT_NCHW, GF_B_MN, GF_CAUSAL_SKIP, GF_CAUSAL_KLIMIT, GF_OUT_T, GF_OUT_F16F8 = 1, 2, 4, 8, 16, 32, 64

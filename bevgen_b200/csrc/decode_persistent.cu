@@ -65,17 +65,32 @@ struct DpSmem {
   unsigned int flags[48];
   unsigned int slotcnt[DP_NSLOT];                       // warps done with a slot shared by several consumer warps
   int found;
+  int rng[4][2];                                        // this CTA's unit range of the QKV / MLP1 / MLP2-row / head linears (part_range, computed once)
   volatile unsigned int rel[DP_NSLOT];                  // unit number last released from each slot (see ring_wait_prev_released)
   volatile unsigned int att_epoch;                      // attention phases whose closing grid barrier the consumers have passed (producer gate)
   unsigned int where[4];                                // step, layer, phase of the consumers (diagnostics)
   unsigned long long prof[12];                          // thread 0: ns per phase body / grid barrier (see GPTSampler.PROFILE_SLOTS)
   unsigned long long fine[20];                          // thread 0: ns in activation fetch | linear ring wait | linear mma + epilogue | attention prologue | attention ring wait (warp 0) | attention units | attention merge | MLP2
   unsigned int* debug;                                  // optional pinned host buffer: filled before a timeout trap
+  unsigned long long* trace;                            // optional event trace of thread 0 (one layer): (id << 48 | clock) entries
+  int trace_n, trace_on;
 };
 
 static_assert(sizeof(DpSmem) <= 232448, "DpSmem exceeds the 227 KB of shared memory a CTA can have on sm_100a");
 
 // ------------------------------------------------------------------------------------------------ small helpers
+// Event trace of thread 0: probe id + SM clock, recorded while trace_on (one layer of one CTA), read back by tools/decode_trace.py.
+// Compiled in only with -DBEVGEN_DP_TRACE (tools/build_variant.sh trace ...): every probe costs a shared-memory load on the critical path.
+#ifdef BEVGEN_DP_TRACE
+#define DP_TR(smref, id)                                                                                                   \
+  do {                                                                                                                     \
+    if (threadIdx.x == 0 && (smref).trace_on && (smref).trace_n < 1000) {                                                  \
+      (smref).trace[(smref).trace_n++] = ((unsigned long long)(id) << 48) | ((unsigned long long)clock64() & 0xffffffffffffull); \
+    }                                                                                                                      \
+  } while (0)
+#else
+#define DP_TR(smref, id) do { } while (0)
+#endif
 __device__ __forceinline__ void bar_consumers() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 __device__ __forceinline__ void bar_group(int g) { asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory"); }
 
@@ -108,6 +123,23 @@ __device__ __forceinline__ unsigned int atom_add_acq_rel_u32(unsigned int* p, un
   asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
   return old;
 }
+// Shared-memory loads the compiler may not sink to their first use: a batch of these is issued back to back, so one warp has several
+// loads in flight (ptxas otherwise places every LDS right before its consumer and relies on other warps to cover the 29 cycles).
+__device__ __forceinline__ uint32_t lds_u32(const void* p) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)));
+  return v;
+}
+__device__ __forceinline__ float lds_f32(const void* p) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(smem_u32(p)));
+  return v;
+}
+__device__ __forceinline__ uint4 lds_u128(const void* p) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(smem_u32(p)));
+  return v;
+}
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 // Before a timeout trap: leave (code, CTA, step, layer, phase, a, b) in the caller's pinned host buffer so the failure can be located
@@ -124,18 +156,23 @@ __device__ __noinline__ void dp_fail(const DpSmem& sm, unsigned int code, unsign
 // the running arrival count this CTA expects; the counter only grows (zeroed by the host before the launch).  A protocol bug or a
 // lost CTA becomes a trap after ~4 s instead of a hung GPU.
 __device__ __forceinline__ void grid_sync(DpSmem& sm, unsigned int* counter, unsigned int& target, unsigned int nctas) {
+  DP_TR(sm, 90);
   fence_proxy_async();                      // this thread's generic-proxy writes of act[] (scratch) before a later async-proxy refill
   bar_consumers();
+  DP_TR(sm, 91);
   target += nctas;
   if (threadIdx.x == 0) {
     red_release_gpu_add(counter, 1u);
+    DP_TR(sm, 92);
     const unsigned long long t0 = dp_globaltimer();
     unsigned int polls = 0, seen;
     while ((seen = ld_acquire_gpu(counter)) < target) {
       if ((++polls & 1023u) == 0 && dp_globaltimer() - t0 > 4000000000ull) dp_fail(sm, 1u, seen, target);
     }
+    DP_TR(sm, 93);
   }
   bar_consumers();
+  DP_TR(sm, 94);
 }
 
 __device__ __forceinline__ void mma_f16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
@@ -164,6 +201,8 @@ __device__ __forceinline__ void part_range(int U, int& u0, int& u1) {
   u0 = (int)(((long long)bx * U) / g);
   u1 = (int)(((long long)(bx + 1) * U) / g);
 }
+enum { RNG_QKV = 0, RNG_MLP1 = 1, RNG_MLP2 = 2, RNG_HEAD = 3 };
+__device__ __forceinline__ void cta_range(const DpSmem& sm, int which, int& u0, int& u1) { u0 = sm.rng[which][0]; u1 = sm.rng[which][1]; }
 __device__ __forceinline__ int cta_of_unit(int u, int U) { return (int)((((long long)(u + 1)) * gridDim.x - 1) / U); }
 
 __device__ __forceinline__ float consumers_sum(float v, float* red16) {
@@ -253,19 +292,19 @@ __device__ __noinline__ void dp_producer(const DecodeParams& p, DpSmem& sm) {
     }
     ++seq;
   };
-  auto stream_units = [&](const uint8_t* base, int U) {
+  auto stream_units = [&](const uint8_t* base, int which) {
     int u0, u1;
-    part_range(U, u0, u1);
+    cta_range(sm, which, u0, u1);
     for (int u = u0; u < u1; ++u) issue_unit(base + (size_t)u * unit_bytes);
   };
   const int BH = p.B * p.H;
   int r0, r1;
-  part_range(upq, r0, r1);
+  cta_range(sm, RNG_MLP2, r0, r1);
   for (int s = p.step_begin; s < p.step_end; ++s) {
     const int n = p.nc + s, nblk = (n + 127) >> 7;
     for (int l = 0; l < p.n_layers; ++l) {
       const DecodeLayer& L = p.layers[l];
-      stream_units(L.w_qkv, 3 * d / 8);
+      stream_units(L.w_qkv, RNG_QKV);
       if ((int)blockIdx.x < BH) {  // attention units: every 128-key block of this CTA's (scene, head) pairs
         if (s > p.step_begin) {
           // The blocks hold keys appended during step s - 1: do not run ahead of the grid barrier that closed attention phase (s - 1, l).
@@ -301,11 +340,11 @@ __device__ __noinline__ void dp_producer(const DecodeParams& p, DpSmem& sm) {
           }
         }
       }
-      stream_units(L.w_1, 4 * d / 8);
+      stream_units(L.w_1, RNG_MLP1);
       for (int ru = r0; ru < r1; ++ru)      // MLP2: the CTA's 8 output rows, the four K-quarters in turn
         for (int q = 0; q < 4; ++q) issue_unit(L.w_2 + ((size_t)q * upq + ru) * unit_bytes);
     }
-    stream_units(p.w_head, p.vpad / 8);
+    stream_units(p.w_head, RNG_HEAD);
   }
   if (p.profile != nullptr) {            // producer: ns blocked on a full ring (weight units | attention units), on the epoch gate
     p.profile[(size_t)blockIdx.x * 32 + 22] = tw; p.profile[(size_t)blockIdx.x * 32 + 23] = ta; p.profile[(size_t)blockIdx.x * 32 + 24] = te;
@@ -335,13 +374,14 @@ enum { EPI_QKV = 0, EPI_MLP1 = 1, EPI_MLP2 = 2, EPI_HEAD = 3 };
 // Two halves so that the global loads (issued at the start of a phase) are in flight while the activation vector arrives and the MMAs run.
 __device__ __forceinline__ void row_stats_load(const DecodeParams& p, const float* __restrict__ ps, int nparts, float& S, float& Q) {
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  S = 0.f; Q = 0.f;
-  if (w < p.B) {
-    for (int i = lane; i < nparts; i += 32) {
-      const float2 v = __ldcg(reinterpret_cast<const float2*>(ps) + (size_t)w * nparts + i);
-      S += v.x; Q += v.y;
-    }
+  float2 v[4];                              // nparts <= 128: four independent loads per lane, one L2 round trip
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int i = lane + 32 * j;
+    v[j] = (w < p.B && i < nparts) ? __ldcg(reinterpret_cast<const float2*>(ps) + (size_t)w * nparts + i) : make_float2(0.f, 0.f);
   }
+  S = (v[0].x + v[1].x) + (v[2].x + v[3].x);
+  Q = (v[0].y + v[1].y) + (v[2].y + v[3].y);
 }
 __device__ __forceinline__ void row_stats_finish(const DecodeParams& p, DpSmem& sm, int which, float S, float Q) {
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -384,16 +424,18 @@ __device__ __forceinline__ void unit_mma(const uint8_t* slot, int w, int lane, c
 // once, one output element per thread, whose epilogue constants were requested before the MMAs.
 //   frag_src: the activation vector in fragment order;  stats / nparts / which: partial sums of the lazy LayerNorm, see combine_row_stats
 __device__ __noinline__ void linear_phase(const DecodeParams& p, DpSmem& sm, unsigned int& seq, unsigned int& act_par, const int epi, const uint8_t* __restrict__ frag_src,
-                             const float* __restrict__ stats, int nparts, int which, int U, float inv_s, const float* __restrict__ c1,
+                             const float* __restrict__ stats, int nparts, int which, int rng, float inv_s, const float* __restrict__ c1,
                              const float* __restrict__ c2) {
   const int tid = opaque((int)threadIdx.x), w = tid >> 5, lane = tid & 31;
   const int d = opaque(p.d), KG = d >> 6;
   const uint32_t vec_bytes = (uint32_t)KG * 4096u;
   float* red = reinterpret_cast<float*>(sm.act);
+  DP_TR(sm, 10);
   int u0, u1;
-  part_range(U, u0, u1);
+  cta_range(sm, rng, u0, u1);
+  DP_TR(sm, 11);
   unsigned long long tf = p.profile != nullptr ? dp_globaltimer() : 0ull;
-  auto fine = [&](int k) { if (tid == 0 && p.profile != nullptr) { const unsigned long long now = dp_globaltimer(); sm.fine[k] += now - tf; tf = now; } };
+  auto fine = [&](int k) { if (tid == 0 && p.profile != nullptr && !sm.trace) { const unsigned long long now = dp_globaltimer(); sm.fine[k] += now - tf; tf = now; } };
   const bool fetch = !(p.dbg & 4);
   if (u1 > u0 && tid == 0 && fetch) {
     fence_proxy_async();
@@ -401,16 +443,27 @@ __device__ __noinline__ void linear_phase(const DecodeParams& p, DpSmem& sm, uns
     dp_bulk_g2s(sm.act, frag_src, vec_bytes, &sm.act_bar);
   }
   float rsS, rsQ;
+  DP_TR(sm, 12);
   row_stats_load(p, stats, nparts, rsS, rsQ);          // consumed after the MMAs: the L2 round trip overlaps the activation fetch
+  DP_TR(sm, 13);
   if (u1 == u0) { row_stats_finish(p, sm, which, rsS, rsQ); return; }      // (LN1 statistics are also read by the attention phase)
-  if (fetch) {
-    dp_mbar_wait(sm, &sm.act_bar, act_par & 1u, 6u, (unsigned)u0);
-    act_par ^= 1u;
+  // Only warp 0 touches the mbarriers (16 warps asking the same barrier serialise in the SM's sync unit: ~1500 cycles per wait in the
+  // trace of tools/decode_trace.py); the others learn through the CTA barrier.  The units were requested phases ago, so warp 0's
+  // waits for them normally return at once.
+  if (w == 0) {
+    if (fetch) dp_mbar_wait(sm, &sm.act_bar, act_par & 1u, 6u, (unsigned)u0);
+    const int nb0 = min(DP_MAXU, u1 - u0);
+    for (int k = 0; k < nb0; ++k) ring_wait_full(sm, seq + (unsigned)k);
   }
+  if (fetch) act_par ^= 1u;
+  bar_consumers();                          // the activation vector and the first batch of units have landed
+  DP_TR(sm, 14);
   uint32_t ahi[4][4], alo[4][4];
   if (w < KG) load_afrag(sm, w, lane, ahi, alo);
   fine(0);
+  DP_TR(sm, 15);
   bar_consumers();                          // fragments are in registers: act[] becomes the reduction scratch
+  DP_TR(sm, 16);
   // output element of a unit owned by this thread: element e -> lane e / 4, register e % 4 of the accumulator fragment -> (batch row, weight row)
   const int ui = tid >> 7, e = tid & 127;
   const int ln = e >> 2, j = e & 3;
@@ -421,23 +474,29 @@ __device__ __noinline__ void linear_phase(const DecodeParams& p, DpSmem& sm, uns
     const int row = (ub + ui) * 8 + nrow;
     float c1v = 0.f, c2v = 0.f;
     if (has) { c1v = __ldg(c1 + row); c2v = __ldg(c2 + row); }
+    if (ub != u0) {                          // a further batch (more than DP_MAXU units per CTA: small grids only)
+      if (w == 0) for (int k = 0; k < nb; ++k) ring_wait_full(sm, seq + (unsigned)k);
+      bar_consumers();
+    }
     if (w < KG) {
       for (int k = 0; k < nb; ++k) {
         const unsigned int sq = seq + (unsigned)k;
-        ring_wait_full(sm, sq);
-        fine(1);
+        DP_TR(sm, 17);
         float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f}, acc2[4] = {0.f, 0.f, 0.f, 0.f};
         if (!(p.dbg & 2)) unit_mma(sm.ring[sq % DP_NSLOT], w, lane, ahi, alo, acc0, acc1, acc2);
-        if (lane == 0) ring_release_shared(sm, sq, (unsigned)KG);      // issued after the MMAs, i.e. after every lane's loads have returned
         *reinterpret_cast<float4*>(&red[((k * 16 + w) * 32 + lane) * 4]) =
             make_float4((acc0[0] + acc2[0]) + acc1[0] * inv_s, (acc0[1] + acc2[1]) + acc1[1] * inv_s, (acc0[2] + acc2[2]) + acc1[2] * inv_s,
                         (acc0[3] + acc2[3]) + acc1[3] * inv_s);
         fine(2);
+        DP_TR(sm, 18);
       }
     }
-    seq += (unsigned)nb;
     if (ub == u0) row_stats_finish(p, sm, which, rsS, rsQ);      // published by the barrier below
-    bar_consumers();
+    DP_TR(sm, 19);
+    bar_consumers();                        // every warp's partial sums are written, i.e. its loads of the staged units have returned
+    if (tid == 0) for (int k = 0; k < nb; ++k) ring_release(sm, seq + (unsigned)k);      // one thread hands the batch's slots back
+    seq += (unsigned)nb;
+    DP_TR(sm, 20);
     if (has) {
       // (ii) four independent partial sums: the 16 shared-memory loads are in flight together
       float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
@@ -452,6 +511,7 @@ __device__ __noinline__ void linear_phase(const DecodeParams& p, DpSmem& sm, uns
       else if (epi == EPI_MLP1) { const int qq = row / d; store_frag(p.HF + (size_t)qq * vec_bytes, b, row - qq * d, gelu_erf(v)); }
       else if (row < p.vocab) p.LOGITS[(size_t)b * p.vocab + row] = v;
     }
+    DP_TR(sm, 21);
     if (ub + DP_MAXU < u1) bar_consumers();   // the reduction scratch is reused by the next batch
   }
   fine(2);
@@ -466,12 +526,13 @@ __device__ __noinline__ void mlp2_phase(const DecodeParams& p, DpSmem& sm, unsig
   const uint32_t vec_bytes = (uint32_t)KG * 4096u;
   float* red = reinterpret_cast<float*>(sm.act);
   int r0, r1;
-  part_range(upq, r0, r1);
+  cta_range(sm, RNG_MLP2, r0, r1);
   if (r0 == r1) return;
   unsigned long long tf = p.profile != nullptr ? dp_globaltimer() : 0ull;
-  auto fine = [&](int k) { if (tid == 0 && p.profile != nullptr) { const unsigned long long now = dp_globaltimer(); sm.fine[k] += now - tf; tf = now; } };
+  auto fine = [&](int k) { if (tid == 0 && p.profile != nullptr && !sm.trace) { const unsigned long long now = dp_globaltimer(); sm.fine[k] += now - tf; tf = now; } };
   const int fb = tid >> 3, fn = tid & 7;                 // finalisation mapping (threads 0..127): 8 consecutive lanes = one batch row
   for (int ru = r0; ru < r1; ++ru) {
+    DP_TR(sm, 30);
     const bool fetch = !(p.dbg & 4);
     if (tid == 0 && fetch) {
       fence_proxy_async();
@@ -484,22 +545,28 @@ __device__ __noinline__ void mlp2_phase(const DecodeParams& p, DpSmem& sm, unsig
     if (fin) base = __ldcg(p.X1 + (size_t)fb * d + row) + __ldg(L.c2_2 + row);
     float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f}, acc2[4] = {0.f, 0.f, 0.f, 0.f};
     for (int q = 0; q < 4; ++q) {
-      if (fetch) {
-        dp_mbar_wait(sm, &sm.act_bar, act_par & 1u, 6u, (unsigned)(ru * 4 + q));
-        act_par ^= 1u;
-      }
-      uint32_t ahi[4][4], alo[4][4];
-      if (w < KG) load_afrag(sm, w, lane, ahi, alo);
-      bar_consumers();                      // act[] is free again
-      if (q < 3 && tid == 0 && fetch) {
-        mbar_expect_tx(&sm.act_bar, vec_bytes);
-        dp_bulk_g2s(sm.act, p.HF + (size_t)(q + 1) * vec_bytes, vec_bytes, &sm.act_bar);
-      }
-      if (w < KG) {
+      if (w == 0) {                         // one warp waits on the mbarriers (see linear_phase), the barrier tells the others
+        if (fetch) dp_mbar_wait(sm, &sm.act_bar, act_par & 1u, 6u, (unsigned)(ru * 4 + q));
         ring_wait_full(sm, seq);
-        if (!(p.dbg & 2)) unit_mma(sm.ring[seq % DP_NSLOT], w, lane, ahi, alo, acc0, acc1, acc2);
-        if (lane == 0) ring_release_shared(sm, seq, (unsigned)KG);
       }
+      if (fetch) act_par ^= 1u;
+      bar_consumers();                      // activation quarter and weight unit have landed
+      DP_TR(sm, 31);
+      if (w < KG) {
+        uint32_t ahi[4][4], alo[4][4];
+        load_afrag(sm, w, lane, ahi, alo);
+        if (!(p.dbg & 2)) unit_mma(sm.ring[seq % DP_NSLOT], w, lane, ahi, alo, acc0, acc1, acc2);
+      }
+      DP_TR(sm, 32);
+      bar_consumers();                      // every warp's loads of act[] and of the slot have returned (the MMAs consumed them)
+      if (tid == 0) {
+        ring_release(sm, seq);
+        if (q < 3 && fetch) {
+          mbar_expect_tx(&sm.act_bar, vec_bytes);
+          dp_bulk_g2s(sm.act, p.HF + (size_t)(q + 1) * vec_bytes, vec_bytes, &sm.act_bar);
+        }
+      }
+      DP_TR(sm, 33);
       ++seq;
     }
     if (w < KG)
@@ -523,8 +590,10 @@ __device__ __noinline__ void mlp2_phase(const DecodeParams& p, DpSmem& sm, unsig
       sv += __shfl_xor_sync(0xffffffffu, sv, 4); qv += __shfl_xor_sync(0xffffffffu, qv, 4);
       if (fin && fn == 0) *reinterpret_cast<float2*>(p.PSX + ((size_t)fb * upq + ru) * 2) = make_float2(sv, qv);
     }
+    DP_TR(sm, 34);
     fence_proxy_async();
     bar_consumers();                        // the scratch is overwritten by the next vector
+    DP_TR(sm, 35);
   }
   fine(7);
 }
@@ -546,7 +615,7 @@ __device__ __noinline__ void attention_phase(const DecodeParams& p, DpSmem& sm, 
   if (npairs == 0) return;
   const int nun = npairs * nblk;
   unsigned long long tf = p.profile != nullptr ? dp_globaltimer() : 0ull;
-  auto fine = [&](int k) { if (tid == 0 && p.profile != nullptr) { const unsigned long long now = dp_globaltimer(); sm.fine[k] += now - tf; tf = now; } };
+  auto fine = [&](int k) { if (tid == 0 && p.profile != nullptr && !sm.trace) { const unsigned long long now = dp_globaltimer(); sm.fine[k] += now - tf; tf = now; } };
   float* fa = reinterpret_cast<float*>(sm.act);
   float* qs = fa + DP_A_QS;                            // [MAXBH][64]   q of every pair
   float* kn = fa + DP_A_KN;                            // [MAXBH][64]   newest key
@@ -555,6 +624,7 @@ __device__ __noinline__ void attention_phase(const DecodeParams& p, DpSmem& sm, 
   float* biasrow = fa + DP_A_BIAS;                     // camera-bias row r (requested after the QKV phase; zeros without a bias)
   uint8_t* layrow = reinterpret_cast<uint8_t*>(fa + DP_A_LAY);      // [MAXBH][DP_MAXLB] layout row of query block r / lay_blk per pair
   const bool tma_bias = p.bias != nullptr && (p.bias_ld & 3) == 0;
+  DP_TR(sm, 50);
   // ---- prologue: q / newest key / newest value of every pair (the latter two also appended to the cache), table reset, layout rows
   if (!tma_bias)
     for (int j = tid; j < n; j += DP_CONSUMERS) biasrow[j] = p.bias ? __ldg(p.bias + (size_t)r * p.bias_ld + j) : 0.f;
@@ -580,8 +650,11 @@ __device__ __noinline__ void attention_phase(const DecodeParams& p, DpSmem& sm, 
       layrow[k * DP_MAXLB + jb] = L.layout[((size_t)h * p.lay_ld + r / p.lay_blk) * p.lay_ld + jb];
     }
   }
+  DP_TR(sm, 51);
   if (tma_bias) { dp_mbar_wait(sm, &sm.bias_bar, bias_par & 1u, 7u, (unsigned)n); bias_par ^= 1u; }
+  DP_TR(sm, 52);
   bar_consumers();
+  DP_TR(sm, 53);
   fine(3);
   // ---- blocks: local unit i = pair k * nblk + block -> warp group i % 4; warp q4 of the group owns keys 32 q4 .. 32 q4 + 31 of the block
   // (all 16 warps busy on four blocks at a time: the shared-memory latency is hidden by the other warps of the scheduler)
@@ -606,8 +679,9 @@ __device__ __noinline__ void attention_phase(const DecodeParams& p, DpSmem& sm, 
     }
     if (lane == 0) { t[0] = m_run; t[1] = l_run; }
   };
+  int k = 0, blk = grp;                    // unit i = pair k * nblk + block blk, advanced without a division
+  while (blk >= nblk) { blk -= nblk; ++k; }
   for (int i = grp; i < nun; i += 4) {
-    const int k = i / nblk, blk = i - k * nblk;
     if (k != cur) {
       if (cur >= 0) flush(cur);
       cur = k; m_run = -INFINITY; l_run = 0.f;
@@ -616,11 +690,14 @@ __device__ __noinline__ void attention_phase(const DecodeParams& p, DpSmem& sm, 
     }
     const int j0 = blk << 7, cnt = min(128, n - j0);
     const unsigned int sq = seq + (unsigned)i;
-    if (w == 0) fine(5);
-    ring_wait_prev_released(sm, sq);
-    if (w == 0) fine(8);
-    ring_wait_full(sm, sq);
-    if (w == 0) fine(4);
+    DP_TR(sm, 54);
+    if (q4 == 0) {                         // one warp of the group waits (see linear_phase), the group barrier tells the other three
+      ring_wait_prev_released(sm, sq);
+      DP_TR(sm, 55);
+      ring_wait_full(sm, sq);
+    }
+    bar_group(grp);
+    DP_TR(sm, 56);
     if (kbase < cnt && !(p.dbg & 1)) {
       __half* Ks = reinterpret_cast<__half*>(sm.ring[sq % DP_NSLOT]);               // [64 channels][128 keys]
       __half* Vs = Ks + 64 * 128;                                                   // [cnt keys][64 channels]
@@ -699,13 +776,18 @@ __device__ __noinline__ void attention_phase(const DecodeParams& p, DpSmem& sm, 
       }
     }
     __syncwarp();                         // every lane is done with the slot and with pw[]
+    DP_TR(sm, 57);
     if (lane == 0) ring_release_shared(sm, sq, 4u);
-    if (w == 0) fine(5);
+    DP_TR(sm, 58);
+    blk += 4;
+    while (blk >= nblk) { blk -= nblk; ++k; }
   }
   if (cur >= 0) flush(cur);
   seq += (unsigned)nun;
   fine(5);
+  DP_TR(sm, 59);
   bar_consumers();
+  DP_TR(sm, 60);
   fine(9);
   // ---- merge the 16 per-warp partials of each pair (fixed order), 2 channels per lane; the residual operands are requested first
   if (w < npairs) {
@@ -742,7 +824,9 @@ __device__ __noinline__ void attention_phase(const DecodeParams& p, DpSmem& sm, 
     for (int of = 16; of; of >>= 1) { sv += __shfl_xor_sync(0xffffffffu, sv, of); qv += __shfl_xor_sync(0xffffffffu, qv, of); }
     if (lane == 0) *reinterpret_cast<float2*>(p.PSX1 + ((size_t)b * p.H + h) * 2) = make_float2(sv, qv);
   }
+  DP_TR(sm, 61);
   fence_proxy_async_all();               // the appended key / value will be read by cp.async.bulk (async proxy) in the next step
+  DP_TR(sm, 62);
   fine(6);
 }
 
@@ -943,6 +1027,12 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(const 
     mbar_init(&sm.bias_bar, 1);
     fence_barrier_init();
     sm.debug = p.debug;
+    part_range(3 * p.d / 8, sm.rng[RNG_QKV][0], sm.rng[RNG_QKV][1]);
+    part_range(4 * p.d / 8, sm.rng[RNG_MLP1][0], sm.rng[RNG_MLP1][1]);
+    part_range(p.d / 8, sm.rng[RNG_MLP2][0], sm.rng[RNG_MLP2][1]);
+    part_range(p.vpad / 8, sm.rng[RNG_HEAD][0], sm.rng[RNG_HEAD][1]);
+    sm.trace = (p.profile != nullptr && (p.dbg & 64) && blockIdx.x == (unsigned)p.trace_cta) ? p.profile + (size_t)gridDim.x * 32 : nullptr;
+    sm.trace_n = 0; sm.trace_on = 0;
     sm.where[0] = sm.where[1] = sm.where[2] = 0u;
     for (int i = 0; i < DP_NSLOT; ++i) { sm.rel[i] = 0xffffffffu; sm.slotcnt[i] = 0u; }
     for (int i = 0; i < 20; ++i) sm.fine[i] = 0ull;
@@ -981,8 +1071,10 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(const 
   for (int s = p.step_begin; s < p.step_end; ++s) {
     for (int l = 0; l < p.n_layers; ++l) {
       const DecodeLayer& L = p.layers[l];
+      if (tid == 0 && sm.trace != nullptr) sm.trace_on = (s == p.trace_step && l == p.n_layers / 4) ? 1 : 0;
+      DP_TR(sm, 1);
       mark(11, s, l, 0);
-      linear_phase(p, sm, seq, act_par, EPI_QKV, p.XF, p.PSX, d >> 3, 0, 3 * d / 8, L.s_qkv, L.c1_qkv, L.c2_qkv);
+      linear_phase(p, sm, seq, act_par, EPI_QKV, p.XF, p.PSX, d >> 3, 0, RNG_QKV, L.s_qkv, L.c1_qkv, L.c2_qkv);
       if (tid == 0 && has_pairs && tma_bias) {
         // camera-bias row of this step -> upper half of act[] (free since the fragments went to registers); waited for in the attention phase
         const int n = p.nc + s;
@@ -991,23 +1083,32 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(const 
         dp_bulk_g2s(sm.act + DP_A_BIAS * 4, p.bias + (size_t)(n - 1) * p.bias_ld, bytes, &sm.bias_bar);
       }
       mark(0, s, l, 1);
+      DP_TR(sm, 2);
       grid_sync(sm, p.barrier, bar_target, G);
       mark(1, s, l, 2);
+      DP_TR(sm, 3);
       attention_phase(p, sm, seq, bias_par, L, s);
       mark(2, s, l, 3);
+      DP_TR(sm, 4);
       grid_sync(sm, p.barrier, bar_target, G);
       if (tid == 0) sm.att_epoch = (unsigned)(s - p.step_begin) * (unsigned)p.n_layers + (unsigned)l + 1u;      // every CTA's appends of (s, l) are visible
       mark(3, s, l, 4);
-      linear_phase(p, sm, seq, act_par, EPI_MLP1, p.X1F, p.PSX1, H, 1, 4 * d / 8, L.s_1, L.c1_1, L.c2_1);
+      DP_TR(sm, 5);
+      linear_phase(p, sm, seq, act_par, EPI_MLP1, p.X1F, p.PSX1, H, 1, RNG_MLP1, L.s_1, L.c1_1, L.c2_1);
       mark(4, s, l, 5);
+      DP_TR(sm, 6);
       grid_sync(sm, p.barrier, bar_target, G);
       mark(5, s, l, 6);
+      DP_TR(sm, 7);
       mlp2_phase(p, sm, seq, act_par, L);
       mark(6, s, l, 7);
+      DP_TR(sm, 8);
       grid_sync(sm, p.barrier, bar_target, G);
       mark(7, s, l, 8);
+      DP_TR(sm, 9);
+      if (tid == 0 && sm.trace_on) { sm.trace_on = 0; sm.trace[1023] = (unsigned long long)sm.trace_n; }
     }
-    linear_phase(p, sm, seq, act_par, EPI_HEAD, p.XF, p.PSX, d >> 3, 0, p.vpad / 8, p.s_head, p.c1_head, p.c2_head);
+    linear_phase(p, sm, seq, act_par, EPI_HEAD, p.XF, p.PSX, d >> 3, 0, RNG_HEAD, p.s_head, p.c1_head, p.c2_head);
     mark(8, s, p.n_layers, 9);
     grid_sync(sm, p.barrier, bar_target, G);
     mark(9, s, p.n_layers, 10);
@@ -1112,7 +1213,10 @@ int launch_decode_persistent(DecodeParams p, float* ws, unsigned int* counters, 
   for (int l = 0; l < 1; ++l)
     if (p.lay_ld > 0 && (p.lay_blk < 16 || (p.Lmax + p.lay_blk - 1) / p.lay_blk > DP_MAXLB)) return BEVGEN_ERR_ARG;
   p.vpad = (p.vocab + 7) / 8 * 8;
-  if (const char* e = getenv("BEVGEN_DP_DBG")) p.dbg = atoi(e);      // timing experiments only (results are garbage): see tools/decode_debug.py
+  if (const char* e = getenv("BEVGEN_DP_DBG")) p.dbg = atoi(e);
+  p.trace_cta = 0; p.trace_step = p.step_begin + 300;
+  if (const char* e = getenv("BEVGEN_DP_TRACE_CTA")) p.trace_cta = atoi(e);
+  if (const char* e = getenv("BEVGEN_DP_TRACE_STEP")) p.trace_step = atoi(e);      // timing experiments only (results are garbage): see tools/decode_debug.py
   float* f = ws;
   p.X = f; f += 16 * d;
   p.X1 = f; f += 16 * d;

@@ -105,6 +105,7 @@ struct ConvFusedParams {
   const float* residual;   // [N][H][W][Cout] or null
   float* out;              // [N][H][W][Cout]
   double* gn_sums;         // [N][32][2] or null: GroupNorm statistics of `out`
+  int trace_cta, trace_step;       // BEVGEN_DP_DBG & 64: thread 0 of this CTA records a clock trace of one layer of this step behind the profile rows
   int dbg;                 // ablation switches (BEVGEN_CONV_DBG, tools/conv_ablation.py): 1 no global fetch, 2 no operand transform/stores,
                            // 4 epilogue drains TMEM only, 8 no MMA issue, 16 no weight traffic.  0 in production.
   float lo_scale;          // npass == 2 (fp16 + e4m3 corrections): 1 / (2^13 * weight scale), applied to the correction accumulator
@@ -198,6 +199,7 @@ struct DecodeParams {
   float *X, *X1, *QKV, *LOGITS, *PSX, *PSX1;
   uint8_t *XF, *X1F, *HF;          // activation vectors in mma A-fragment order (fp16 hi + lo)
   unsigned int* barrier;
+  int trace_cta, trace_step;       // BEVGEN_DP_DBG & 64: thread 0 of this CTA records a clock trace of one layer of this step behind the profile rows
   int dbg;                         // timing experiments (BEVGEN_DP_DBG): 1 skip attention math, 2 skip linear MMAs, 4 skip activation fetches, 8 producer copies nothing
   unsigned int* debug;             // optional pinned HOST buffer (8 uint32, zeroed): timeout diagnostics written before the trap
   unsigned long long* profile;     // optional [grid][32] nanoseconds per phase (bodies and grid barriers), device memory

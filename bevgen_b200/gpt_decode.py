@@ -100,7 +100,7 @@ class GPTSampler:
         """Per-phase milliseconds of the last persistent launch (mean over CTAs; the kernel's own %globaltimer marks)."""
         if not self._pk or "prof" not in self._pk:
             return None
-        t = self._pk["prof"].double().mean(0) / 1e6
+        t = self._pk["prof"][: -32].double().mean(0) / 1e6
         return {k: float(v) for k, v in zip(self.PROFILE_SLOTS, t.tolist())}
 
     def last_failure(self):
@@ -211,7 +211,7 @@ class GPTSampler:
         a.workspace, a.counters = pk["ws"].data_ptr(), pk["cnt"].data_ptr()
         if "dbg" not in pk:
             pk["dbg"] = torch.zeros(8, dtype=torch.int32).pin_memory()           # readable by the host after a time-out trap
-            pk["prof"] = torch.zeros((lib.bevgen_sm_count(), 32), dtype=torch.int64, device=e.dev)
+            pk["prof"] = torch.zeros((lib.bevgen_sm_count() + 32, 32), dtype=torch.int64, device=e.dev)      # + 1024 trace entries (BEVGEN_DP_DBG & 64)
         pk["dbg"].zero_()
         a.debug, a.profile = pk["dbg"].data_ptr(), (pk["prof"].data_ptr() if self.profile_phases else None)
         ops.Stats.launches += 1

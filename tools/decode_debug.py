@@ -35,6 +35,15 @@ def main():
             torch.cuda.synchronize()
             res[f"run{it}_s"] = time.time() - t0
         res["profile_ms"] = smp.last_profile()
+        if os.environ.get("DP_DUMP") == "1" and smp._pk and "prof" in smp._pk:
+            t = smp._pk["prof"][:-32].double().cpu() / 1e3 / ((steps - 1) * layers)       # us per layer-iteration, [cta][slot]
+            names = smp.PROFILE_SLOTS
+            q = torch.tensor([0.0, 0.1, 0.5, 0.9, 1.0], dtype=torch.double)
+            res["per_cta_us_per_layer(min,p10,p50,p90,max)"] = {names[i]: [round(float(v), 2) for v in torch.quantile(t[:, i], q)] for i in range(8)}
+            body = t[:, 0] + t[:, 2] + t[:, 4] + t[:, 6]
+            order = torch.argsort(body, descending=True)
+            res["slowest_ctas(body us/layer)"] = [(int(i), round(float(body[i]), 1)) for i in order[:10]]
+            res["fastest_ctas"] = [(int(i), round(float(body[i]), 1)) for i in order[-6:]]
         res["ms_per_token"] = res["run1_s"] * 1e3 / max(steps - 1, 1)
         res["ok"] = True
     except Exception as ex:
