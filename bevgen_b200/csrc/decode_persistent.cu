@@ -436,33 +436,32 @@ __device__ __noinline__ void linear_phase(const DecodeParams& p, DpSmem& sm, uns
   DP_TR(sm, 11);
   unsigned long long tf = p.profile != nullptr ? dp_globaltimer() : 0ull;
   auto fine = [&](int k) { if (tid == 0 && p.profile != nullptr && !sm.trace) { const unsigned long long now = dp_globaltimer(); sm.fine[k] += now - tf; tf = now; } };
-  const bool fetch = !(p.dbg & 4);
-  if (u1 > u0 && tid == 0 && fetch) {
-    fence_proxy_async();
-    mbar_expect_tx(&sm.act_bar, vec_bytes);
-    dp_bulk_g2s(sm.act, frag_src, vec_bytes, &sm.act_bar);
-  }
   float rsS, rsQ;
   DP_TR(sm, 12);
-  row_stats_load(p, stats, nparts, rsS, rsQ);          // consumed after the MMAs: the L2 round trip overlaps the activation fetch
+  row_stats_load(p, stats, nparts, rsS, rsQ);          // consumed after the MMAs
   DP_TR(sm, 13);
   if (u1 == u0) { row_stats_finish(p, sm, which, rsS, rsQ); return; }      // (LN1 statistics are also read by the attention phase)
+  // Every warp reads ITS k-group of the activation vector straight from L2 into the A registers (fragment order: 8 coalesced 16-byte
+  // loads per lane; .cg: the vector was written by other SMs in the previous phase) - no staging buffer, no barrier for it.
+  uint32_t ahi[4][4], alo[4][4];
+  if (w < KG) {
+    const uint4* src = reinterpret_cast<const uint4*>(frag_src + (size_t)w * 4096 + lane * 16);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint4 h4 = __ldcg(src + j * 32), l4 = __ldcg(src + 128 + j * 32);
+      ahi[j][0] = h4.x; ahi[j][1] = h4.y; ahi[j][2] = h4.z; ahi[j][3] = h4.w;
+      alo[j][0] = l4.x; alo[j][1] = l4.y; alo[j][2] = l4.z; alo[j][3] = l4.w;
+    }
+  }
   // Only warp 0 touches the mbarriers (16 warps asking the same barrier serialise in the SM's sync unit: ~1500 cycles per wait in the
   // trace of tools/decode_trace.py); the others learn through the CTA barrier.  The units were requested phases ago, so warp 0's
   // waits for them normally return at once.
   if (w == 0) {
-    if (fetch) dp_mbar_wait(sm, &sm.act_bar, act_par & 1u, 6u, (unsigned)u0);
     const int nb0 = min(DP_MAXU, u1 - u0);
     for (int k = 0; k < nb0; ++k) ring_wait_full(sm, seq + (unsigned)k);
   }
-  if (fetch) act_par ^= 1u;
-  bar_consumers();                          // the activation vector and the first batch of units have landed
-  DP_TR(sm, 14);
-  uint32_t ahi[4][4], alo[4][4];
-  if (w < KG) load_afrag(sm, w, lane, ahi, alo);
-  fine(0);
   DP_TR(sm, 15);
-  bar_consumers();                          // fragments are in registers: act[] becomes the reduction scratch
+  bar_consumers();                          // the first batch of units has landed; act[] (reduction scratch) is free: the previous phase is behind a grid barrier
   DP_TR(sm, 16);
   // output element of a unit owned by this thread: element e -> lane e / 4, register e % 4 of the accumulator fragment -> (batch row, weight row)
   const int ui = tid >> 7, e = tid & 127;
@@ -533,47 +532,37 @@ __device__ __noinline__ void mlp2_phase(const DecodeParams& p, DpSmem& sm, unsig
   const int fb = tid >> 3, fn = tid & 7;                 // finalisation mapping (threads 0..127): 8 consecutive lanes = one batch row
   for (int ru = r0; ru < r1; ++ru) {
     DP_TR(sm, 30);
-    const bool fetch = !(p.dbg & 4);
-    if (tid == 0 && fetch) {
-      fence_proxy_async();
-      mbar_expect_tx(&sm.act_bar, vec_bytes);
-      dp_bulk_g2s(sm.act, p.HF, vec_bytes, &sm.act_bar);
-    }
+    // The four weight units of this row unit were requested phases ago: warp 0 makes sure they have landed, then nothing inside the
+    // quarter loop synchronises - every warp reads ITS k-group of each activation quarter straight from L2 into the A registers
+    // (fragment order: 8 coalesced 16-byte loads per lane), so there is no staging buffer to wait for or to hand back.
+    if (w == 0) for (int q = 0; q < 4; ++q) ring_wait_full(sm, seq + (unsigned)q);
     const int row = ru * 8 + fn;
     const bool fin = tid < 128 && fb < p.B;
     float base = 0.f;
     if (fin) base = __ldcg(p.X1 + (size_t)fb * d + row) + __ldg(L.c2_2 + row);
+    bar_consumers();
+    DP_TR(sm, 31);
     float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f}, acc2[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int q = 0; q < 4; ++q) {
-      if (w == 0) {                         // one warp waits on the mbarriers (see linear_phase), the barrier tells the others
-        if (fetch) dp_mbar_wait(sm, &sm.act_bar, act_par & 1u, 6u, (unsigned)(ru * 4 + q));
-        ring_wait_full(sm, seq);
-      }
-      if (fetch) act_par ^= 1u;
-      bar_consumers();                      // activation quarter and weight unit have landed
-      DP_TR(sm, 31);
-      if (w < KG) {
+    if (w < KG) {
+      for (int q = 0; q < 4; ++q) {
+        const uint4* src = reinterpret_cast<const uint4*>(p.HF + (size_t)q * vec_bytes + (size_t)w * 4096 + lane * 16);
         uint32_t ahi[4][4], alo[4][4];
-        load_afrag(sm, w, lane, ahi, alo);
-        if (!(p.dbg & 2)) unit_mma(sm.ring[seq % DP_NSLOT], w, lane, ahi, alo, acc0, acc1, acc2);
-      }
-      DP_TR(sm, 32);
-      bar_consumers();                      // every warp's loads of act[] and of the slot have returned (the MMAs consumed them)
-      if (tid == 0) {
-        ring_release(sm, seq);
-        if (q < 3 && fetch) {
-          mbar_expect_tx(&sm.act_bar, vec_bytes);
-          dp_bulk_g2s(sm.act, p.HF + (size_t)(q + 1) * vec_bytes, vec_bytes, &sm.act_bar);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint4 h4 = __ldcg(src + j * 32), l4 = __ldcg(src + 128 + j * 32);
+          ahi[j][0] = h4.x; ahi[j][1] = h4.y; ahi[j][2] = h4.z; ahi[j][3] = h4.w;
+          alo[j][0] = l4.x; alo[j][1] = l4.y; alo[j][2] = l4.z; alo[j][3] = l4.w;
         }
+        if (!(p.dbg & 2)) unit_mma(sm.ring[(seq + (unsigned)q) % DP_NSLOT], w, lane, ahi, alo, acc0, acc1, acc2);
+        DP_TR(sm, 33);
       }
-      DP_TR(sm, 33);
-      ++seq;
-    }
-    if (w < KG)
       *reinterpret_cast<float4*>(&red[(w * 32 + lane) * 4]) =
           make_float4((acc0[0] + acc2[0]) + acc1[0] * L.s_2, (acc0[1] + acc2[1]) + acc1[1] * L.s_2, (acc0[2] + acc2[2]) + acc1[2] * L.s_2,
                       (acc0[3] + acc2[3]) + acc1[3] * L.s_2);
-    bar_consumers();
+    }
+    bar_consumers();                        // partial sums written; every warp's loads of the four slots have returned
+    if (tid == 0) for (int q = 0; q < 4; ++q) ring_release(sm, seq + (unsigned)q);
+    seq += 4u;
     if (tid < 128) {
       // (batch row fb, weight row fn) lives in lane 4 (fb % 8) + fn / 2, register 2 (fb / 8) + fn % 2 of the accumulator fragment
       const int ee = ((((fb & 7) << 2) | (fn >> 1)) << 2) | (((fb >> 3) << 1) | (fn & 1));
@@ -591,8 +580,7 @@ __device__ __noinline__ void mlp2_phase(const DecodeParams& p, DpSmem& sm, unsig
       if (fin && fn == 0) *reinterpret_cast<float2*>(p.PSX + ((size_t)fb * upq + ru) * 2) = make_float2(sv, qv);
     }
     DP_TR(sm, 34);
-    fence_proxy_async();
-    bar_consumers();                        // the scratch is overwritten by the next vector
+    if (ru + 1 < r1) bar_consumers();       // the scratch is reused by the next row unit
     DP_TR(sm, 35);
   }
   fine(7);
