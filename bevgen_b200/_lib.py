@@ -100,6 +100,9 @@ SIGNATURES = {
     "bevgen_conv_in3": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "bevgen_conv_out3": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp]),
     "bevgen_to_uint8_hwc": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "bevgen_absmax": (_i, [_vp, _ll, _vp, _vp]),
+    "bevgen_pack_split_bf16": (_i, [_vp, _ll, _vp, _vp, _vp]),
+    "bevgen_pack_f16f8": (_i, [_vp, _ll, _i, _i, _f, _f, _vp, _vp, _vp]),
     "bevgen_denormalize": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "bevgen_layernorm": (_i, [_vp, _ll, _i, _ll, _vp, _vp, _f, _vp, _vp, _vp, _vp]),
     "bevgen_layernorm_f16f8": (_i, [_vp, _ll, _i, _ll, _vp, _vp, _f, _vp, _vp, _vp, _i, _vp]),

@@ -335,6 +335,27 @@ BEVGEN_API int bevgen_conv_out3(const float* x_nhwc, int n, int h, int w, int c,
   CHECK_LAUNCH(launch_conv_out3(x_nhwc, affine, swish, weight_oihw, bias, out_nchw, n, h, w, c, g_sm_count, (cudaStream_t)stream), "conv_out3");
 }
 
+BEVGEN_API int bevgen_absmax(const float* x, long long n, float* out, void* stream) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  if (!x || !out || n < 1) return fail(BEVGEN_ERR_ARG, "absmax: bad args");
+  CHECK_LAUNCH(launch_absmax(x, n, out, g_sm_count, (cudaStream_t)stream), "absmax");
+}
+
+BEVGEN_API int bevgen_pack_split_bf16(const float* x, long long n, void* hi, void* lo, void* stream) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  if (!x || !hi || n < 1) return fail(BEVGEN_ERR_ARG, "pack_split_bf16: bad args");
+  CHECK_LAUNCH(launch_split_bf16(x, n, hi, lo, g_sm_count, (cudaStream_t)stream), "pack_split_bf16");
+}
+
+BEVGEN_API int bevgen_pack_f16f8(const float* w, long long rows, int cin, int chunk, float s, float w16_mul, void* w16, void* pair, void* stream) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  if (!w || !w16 || !pair) return fail(BEVGEN_ERR_ARG, "pack_f16f8: null pointer");
+  CHECK_LAUNCH(launch_pack_f16f8(w, rows, cin, chunk, s, w16_mul, w16, pair, g_sm_count, (cudaStream_t)stream), "pack_f16f8");
+}
+
 BEVGEN_API int bevgen_to_uint8_hwc(const float* x_nchw, void* out_nhwc_u8, int n, int c, int pixels, void* stream) {
   int rc = ensure_init();
   if (rc) return rc;

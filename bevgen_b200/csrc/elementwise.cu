@@ -2,6 +2,10 @@
 // fp32 NHWC activation into the bf16 (hi, lo) operand planes the GEMM consumes (fusing GroupNorm-apply, swish,
 // nearest 2x upsampling or the stride-2 space-to-depth split), conv_in im2col, LayerNorm, layout transposes,
 // row softmax and row gathers.  All are coalesced / 128-bit vectorised grid-stride kernels.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
+
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -344,6 +348,55 @@ int launch_denorm(const float* x, float* out, int N, int C, int P, const float* 
   if (C != 3) return BEVGEN_ERR_ARG;
   size_t total = (size_t)N * C * P;
   denorm_kernel<<<grid_for(total, 256, sm_count), 256, 0, st>>>(x, out, total, C, P, mean[0], mean[1], mean[2], std_[0], std_[1], std_[2]);
+  return cudaGetLastError() == cudaSuccess ? BEVGEN_OK : BEVGEN_ERR_CUDA;
+}
+
+// ------------------------------------------------------------------------------------------------ weight packing (load time)
+// max |x| over n floats -> *out (a float that must hold 0 before the launch; values are non-negative, so their bit patterns order like ints)
+__global__ void absmax_kernel(const float* __restrict__ x, long long n, float* __restrict__ out) {
+  float m = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) m = fmaxf(m, fabsf(x[i]));
+  for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(reinterpret_cast<int*>(out), __float_as_int(m));
+}
+int launch_absmax(const float* x, long long n, float* out, int sm_count, cudaStream_t st) {
+  absmax_kernel<<<sm_count * 4, 256, 0, st>>>(x, n, out);
+  return cudaGetLastError() == cudaSuccess ? BEVGEN_OK : BEVGEN_ERR_CUDA;
+}
+
+// fp32 -> bf16 hi (+ bf16 lo = bf16(x - hi)) planes (the operand format of the bf16x3 split product)
+__global__ void split_bf16_kernel(const float* __restrict__ x, long long n, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    hi[i] = h;
+    if (lo != nullptr) lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+}
+int launch_split_bf16(const float* x, long long n, void* hi, void* lo, int sm_count, cudaStream_t st) {
+  split_bf16_kernel<<<sm_count * 8, 256, 0, st>>>(x, n, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
+  return cudaGetLastError() == cudaSuccess ? BEVGEN_OK : BEVGEN_ERR_CUDA;
+}
+
+// fp32 weight rows [rows][cin] -> the f16f8 weight operand: w16 = fp16(w * w16_mul) and, per `chunk`-element piece of a row, `chunk` bytes
+// e4m3(w * s) followed by `chunk` bytes e4m3((w - w16 / w16_mul) * s * 2^13) (saturating, round to nearest even).  One thread per element.
+__global__ void pack_f16f8_kernel(const float* __restrict__ w, long long n, int cin, int chunk, float s, float w16_mul, __half* __restrict__ w16,
+                                  uint8_t* __restrict__ pair) {
+  const float lo_mul = s * 8192.0f, inv16 = 1.0f / w16_mul;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = w[i];
+    const __half h = __float2half_rn(v * w16_mul);
+    w16[i] = h;
+    const long long row = i / cin;
+    const int c = (int)(i - row * cin), piece = c / chunk, e = c - piece * chunk;
+    uint8_t* dst = pair + row * 2 * cin + (long long)piece * 2 * chunk + e;
+    dst[0] = (uint8_t)__nv_cvt_float_to_fp8(v * s, __NV_SATFINITE, __NV_E4M3);
+    dst[chunk] = (uint8_t)__nv_cvt_float_to_fp8((v - __half2float(h) * inv16) * lo_mul, __NV_SATFINITE, __NV_E4M3);
+  }
+}
+int launch_pack_f16f8(const float* w, long long rows, int cin, int chunk, float s, float w16_mul, void* w16, void* pair, int sm_count, cudaStream_t st) {
+  if (rows < 1 || cin < chunk || cin % chunk != 0 || !(chunk == 32 || chunk == 64) || !(s > 0.f) || !(w16_mul > 0.f)) return BEVGEN_ERR_ARG;
+  pack_f16f8_kernel<<<sm_count * 8, 256, 0, st>>>(w, rows * cin, cin, chunk, s, w16_mul, (__half*)w16, (uint8_t*)pair);
   return cudaGetLastError() == cudaSuccess ? BEVGEN_OK : BEVGEN_ERR_CUDA;
 }
 

@@ -71,6 +71,9 @@ int launch_conv_in3(const float* x, const float* w, const float* bias, float* ou
                     cudaStream_t st);
 int launch_conv_out3(const float* x, const float* affine, int swish, const float* w, const float* bias, float* out, int N, int H, int W, int C,
                      int sm_count, cudaStream_t st);
+int launch_absmax(const float* x, long long n, float* out, int sm_count, cudaStream_t st);
+int launch_split_bf16(const float* x, long long n, void* hi, void* lo, int sm_count, cudaStream_t st);
+int launch_pack_f16f8(const float* w, long long rows, int cin, int chunk, float s, float w16_mul, void* w16, void* pair, int sm_count, cudaStream_t st);
 int launch_to_uint8_hwc(const float* x, uint8_t* out, int N, int C, int P, int sm_count, cudaStream_t st);
 int launch_denorm(const float* x, float* out, int N, int C, int P, const float* mean, const float* std_, int sm_count, cudaStream_t st);
 int launch_row_sqnorm(const float* x, float* out, int rows, int D, cudaStream_t st);

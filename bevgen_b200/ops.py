@@ -41,10 +41,43 @@ def _chk_cuda(*ts):
 
 
 def split_planes(x: torch.Tensor, npass: int = 3):
-    """fp32 tensor -> (hi, lo) bf16 planes with x ~= hi + lo (packing-time helper for weights)."""
+    """fp32 tensor -> (hi, lo) bf16 planes with x ~= hi + lo (packing-time helper for weights): one bevgen_pack_split_bf16 launch."""
+    if not x.is_cuda:
+        return split_planes_torch(x, npass)
+    x = x.detach().float().contiguous()
+    hi = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    lo = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device) if npass == 3 else None
+    Stats.launches += 1
+    _lib.check(_lib.init().bevgen_pack_split_bf16(_ptr(x), x.numel(), _ptr(hi), _ptr(lo), _stream()), "pack_split_bf16")
+    return hi, lo
+
+
+def split_planes_torch(x: torch.Tensor, npass: int = 3):
+    """The same in torch ops (CPU tensors; the reference statement the pack kernels are tested against)."""
     hi = x.to(torch.bfloat16)
     lo = (x - hi.float()).to(torch.bfloat16) if npass == 3 else None
     return hi.contiguous(), (None if lo is None else lo.contiguous())
+
+
+def _weight_scale_exp(w: torch.Tensor) -> int:
+    """e with S = 2^e the largest power of two keeping max|w| * S <= 64 (bevgen_absmax: one launch + a 4-byte read-back at load time)."""
+    out = torch.zeros(1, dtype=torch.float32, device=w.device)
+    Stats.launches += 1
+    _lib.check(_lib.init().bevgen_absmax(_ptr(w), w.numel(), _ptr(out), _stream()), "absmax")
+    amax = float(out.item())
+    return 6 if amax == 0.0 else min(max(6 - math.ceil(math.log2(amax)), -16), 24)
+
+
+def _pack_f16f8_kernel(w2d: torch.Tensor, chunk: int, scaled16: bool):
+    rows, cin = w2d.shape
+    assert cin % chunk == 0
+    w = w2d.detach().float().contiguous()
+    s = 2.0 ** _weight_scale_exp(w)
+    w16 = torch.empty((rows, cin), dtype=torch.float16, device=w.device)
+    pair = torch.empty((rows, 2 * cin), dtype=torch.uint8, device=w.device)
+    Stats.launches += 1
+    _lib.check(_lib.init().bevgen_pack_f16f8(_ptr(w), rows, cin, chunk, s, s * 128.0 if scaled16 else 1.0, _ptr(w16), _ptr(pair), _stream()), "pack_f16f8")
+    return w16, pair, 1.0 / (2.0 ** F8_ACT_LO_SHIFT * s)
 
 
 F8_ACT_LO_SHIFT = 13        # conv_fused2.cu producer: lo8 = e4m3((x - fp16(x)) * 2^13), x8 = e4m3(x)
@@ -52,6 +85,11 @@ F8_ACT_SHIFT = 0
 
 
 def pack_f16f8(w2d: torch.Tensor):
+    """Kernel path (bevgen_pack_f16f8) of pack_f16f8_torch."""
+    return _pack_f16f8_kernel(w2d, 64, False) if w2d.is_cuda else pack_f16f8_torch(w2d)
+
+
+def pack_f16f8_torch(w2d: torch.Tensor):
     """fp32 weight rows [rows][cin] (cin % 64 == 0) -> (w16 [rows][cin] fp16, pair [rows][2*cin] uint8, lo_scale) for
     bevgen_conv3x3_fused_f16f8: per 64-channel chunk 64 bytes e4m3(w * S) then 64 bytes e4m3((w - fp16(w)) * S * 2^13), with
     S the largest power of two keeping max|w| * S <= 64 (so the residual plane stays <= 256; e4m3 saturates at 448)."""
@@ -83,6 +121,11 @@ def pack_act_f16f8(a: torch.Tensor):
 
 
 def pack_f16f8_block(w2d: torch.Tensor):
+    """Kernel path (bevgen_pack_f16f8, 32-element chunks, scaled fp16 plane) of pack_f16f8_block_torch."""
+    return _pack_f16f8_kernel(w2d, 32, True) if w2d.is_cuda else pack_f16f8_block_torch(w2d)
+
+
+def pack_f16f8_block_torch(w2d: torch.Tensor):
     """Weights for the 16x16-block f16f8 kernel (bevgen_conv3x3_fused_f16f8, block16=1): (w16s fp16(w * S * 2^7), pair [rows][2*cin] uint8 with,
     per 32-channel slice, 32 bytes e4m3(w * S) then 32 bytes e4m3((w - w16) * S * 2^13), lo_scale = 1 / (2^13 * S))."""
     rows, cin = w2d.shape
@@ -287,6 +330,11 @@ def layernorm(x, gamma, beta, y=None, out_hi=None, out_lo=None, eps=1e-5, rows=N
 
 
 def pack_linear_f16f8(w2d: torch.Tensor):
+    """Kernel path (bevgen_pack_f16f8, scaled fp16 plane) of pack_linear_f16f8_torch."""
+    return _pack_f16f8_kernel(w2d, 64, True) if w2d.is_cuda else pack_linear_f16f8_torch(w2d)
+
+
+def pack_linear_f16f8_torch(w2d: torch.Tensor):
     """nn.Linear weight [out][in] (in % 64 == 0) -> operands of linear_f16f8: (w16s = fp16(w * S * 2^7), pair [out][2*in] uint8 with, per
     64-element chunk, 64 bytes e4m3(w * S) then 64 bytes e4m3((w - w16) * S * 2^13), out_scale = 1 / (2^13 * S))."""
     rows, cin = w2d.shape

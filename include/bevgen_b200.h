@@ -169,6 +169,18 @@ BEVGEN_API int bevgen_conv_out3(const float* x_nhwc, int n, int h, int w, int c,
  * utils/callback.py:28-30,72-132: what leaves the GPU is a quarter of the fp32 bytes, already in the layout the JPEG encoder wants). */
 BEVGEN_API int bevgen_to_uint8_hwc(const float* x_nchw, void* out_nhwc_u8, int n, int c, int pixels, void* stream);
 
+/* ---------------------------------------------------------------- weight packing (model load; SURVEY 8b "bevgen_pack_*")
+ * The reference keeps nn.Parameter tensors as they are (stage1/model.py, transformer/mingpt_sparse.py); this library's kernels read
+ * pre-split operand planes, written once per weight version by these three entry points (bevgen_pack_decode_linear below packs the
+ * persistent decode kernel's slabs). */
+/* max |x| over n floats; *out must be 0.0f before the call */
+BEVGEN_API int bevgen_absmax(const float* x, long long n, float* out, void* stream);
+/* fp32 -> bf16 hi and (lo may be NULL) bf16(x - hi) planes: the bf16x3 split-product operand */
+BEVGEN_API int bevgen_pack_split_bf16(const float* x, long long n, void* hi_bf16, void* lo_bf16, void* stream);
+/* fp32 weight rows [rows][cin] -> f16f8 operand: w16 = fp16(w * w16_mul) [rows][cin]; pair [rows][2 * cin] bytes: per chunk (32 | 64)
+ * elements `chunk` bytes e4m3(w * s) then `chunk` bytes e4m3((w - w16 / w16_mul) * s * 2^13).  s = the power of two with max|w| * s <= 64. */
+BEVGEN_API int bevgen_pack_f16f8(const float* w, long long rows, int cin, int chunk, float s, float w16_mul, void* w16, void* pair_u8, void* stream);
+
 /* ---------------------------------------------------------------- stage-2 transformer */
 
 /* nn.LayerNorm(d) (mingpt_sparse.py:220-221,285): x fp32 rows (pitch x_row_stride elements) -> y fp32 [rows][d] (optional)

@@ -561,3 +561,24 @@ def test_conv_out3_direct(N_, H, W, C):
     ops.conv_out3(x_nhwc, w, b, out)
     torch.cuda.synchronize()
     assert (out.double() - F.conv2d(x.double(), w.double(), b.double(), padding=1)).abs().max().item() < 2e-5
+
+
+@pytest.mark.parametrize("rows,cin", [(24, 64), (130, 320), (384, 1024)])
+def test_pack_kernels_match_the_torch_statement(rows, cin):
+    """bevgen_pack_split_bf16 / bevgen_pack_f16f8 / bevgen_absmax (model-load packing) are bit-identical to the torch statements of the
+    formats (ops.*_torch), including saturation of the e4m3 residual plane and a zero matrix."""
+    g = torch.Generator().manual_seed(rows * 7 + cin)
+    for scale in (0.02, 3.0, 0.0):
+        w = (torch.randn(rows, cin, generator=g) * scale).cuda()
+        if scale == 3.0:
+            w[0, 0] = 37.5            # drives the power-of-two weight scale; residuals of small entries then saturate nowhere, large ones may
+        hi, lo = ops.split_planes(w)
+        hi_r, lo_r = ops.split_planes_torch(w)
+        assert torch.equal(hi.view(torch.int16), hi_r.view(torch.int16)) and torch.equal(lo.view(torch.int16), lo_r.view(torch.int16))
+        assert ops.split_planes(w, npass=1)[1] is None
+        for fn, ref in ((ops.pack_f16f8, ops.pack_f16f8_torch), (ops.pack_linear_f16f8, ops.pack_linear_f16f8_torch), (ops.pack_f16f8_block, ops.pack_f16f8_block_torch)):
+            a16, apair, asc = fn(w)
+            b16, bpair, bsc = ref(w)
+            assert asc == bsc, (fn.__name__, asc, bsc)
+            assert torch.equal(a16.view(torch.int16), b16.view(torch.int16)), fn.__name__
+            assert torch.equal(apair, bpair), fn.__name__
