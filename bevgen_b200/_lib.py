@@ -109,6 +109,8 @@ SIGNATURES = {
     "bevgen_linear_f16f8": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _i, _f, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "bevgen_ray_embed_add": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "bevgen_mg_head_planes": (_i, [_vp, _ll, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _ll, _i, _i, _i, _vp]),
+    "bevgen_mg_sample": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _i, _f, _ll, _vp]),
+    "bevgen_mg_remask": (_i, [_vp, _vp, _f, _vp, _vp, _ll, _i, _i, _ll, _vp]),
     "bevgen_mg_geglu_ln": (_i, [_vp, _ll, _vp, _vp, _vp, _ll, _i, _i, _f, _i, _vp]),
     "bevgen_embed_assemble": (_i, [C.POINTER(EmbedArgs), _vp]),
     "bevgen_attn_softmax": (_i, [_vp, _vp, _vp, _ll, _i, _i, _f, _vp, _vp, _vp, _i, _i, _i, _vp]),

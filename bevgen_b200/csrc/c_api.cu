@@ -459,6 +459,22 @@ BEVGEN_API int bevgen_mg_head_planes(const float* src, long long src_ld, int src
                                      dst_rows, dst_batch_rows, dst_ld, dst_col0, has_null, heads, (cudaStream_t)stream), "mg_head_planes");
 }
 
+BEVGEN_API int bevgen_mg_sample(const float* logits, const float* uniform, long long* ids, float* scores, long long rows, int vocab, int top_k,
+                                float inv_temperature, long long mask_id, void* stream) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  if (!logits || !uniform || !ids) return fail(BEVGEN_ERR_ARG, "mg_sample: null pointer");
+  CHECK_LAUNCH(launch_mg_sample(logits, uniform, ids, scores, rows, vocab, top_k, inv_temperature, mask_id, (cudaStream_t)stream), "mg_sample");
+}
+
+BEVGEN_API int bevgen_mg_remask(const float* scores, const float* uniform, float noise_scale, long long* ids, const long long* init_ids, long long rows,
+                                int hw, int n_mask, long long mask_id, void* stream) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  if (!scores || !ids) return fail(BEVGEN_ERR_ARG, "mg_remask: null pointer");
+  CHECK_LAUNCH(launch_mg_remask(scores, uniform, noise_scale, ids, init_ids, rows, hw, n_mask, mask_id, (cudaStream_t)stream), "mg_remask");
+}
+
 BEVGEN_API int bevgen_mg_geglu_ln(const float* h, long long h_ld, const float* gamma, void* out_hi, void* out_lo, long long rows, int f, int f_pad,
                                   float eps, int f16f8, void* stream) {
   if (!h || !gamma || !out_hi) return fail(BEVGEN_ERR_ARG, "mg_geglu_ln: bad args");

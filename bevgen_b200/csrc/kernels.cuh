@@ -139,6 +139,10 @@ int launch_ray_embed_add(float* h, const float* I_inv, const float* E_inv, const
 int launch_mg_head_planes(const float* src, long long src_ld, int src_col0, int n_src, int src_batch_rows, const float* null_vec, const float* scale,
                           uint16_t* hi, uint16_t* lo, int B, int dst_rows, int dst_batch_rows, long long dst_ld, int dst_col0, int has_null, int H,
                           cudaStream_t st);
+int launch_mg_sample(const float* logits, const float* u, long long* ids, float* scores, long long rows, int V, int k, float inv_temp, long long mask_id,
+                     cudaStream_t st);
+int launch_mg_remask(const float* scores, const float* u, float noise_scale, long long* ids, const long long* init_ids, long long rows, int hw, int n_mask,
+                     long long mask_id, cudaStream_t st);
 int launch_mg_geglu_ln(const float* hin, long long h_ld, const float* gamma, uint16_t* hi, uint16_t* lo, long long rows, int f, int f_pad, float eps,
                        int f16f8, cudaStream_t st);
 int launch_attn_fused(const CUtensorMap* tm_hi, const CUtensorMap* tm_lo, const void* bias_f16, const float* y, float* x1, int B, int H, int L,

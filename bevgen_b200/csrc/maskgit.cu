@@ -136,4 +136,162 @@ int launch_mg_geglu_ln(const float* hin, long long h_ld, const float* gamma, uin
   return cudaGetLastError() == cudaSuccess ? BEVGEN_OK : BEVGEN_ERR_CUDA;
 }
 
+// ------------------------------------------------------------------------------------------------
+// MaskGit.generate token bookkeeping between the forwards (muse_maskgit_pytorch.py:569-627), two launches per de-masking step.
+//
+// mg_sample: per token row, `filtered = top-k(logits)`, `pred = argmax(filtered / max(temp, 1e-10) + gumbel(u))` (:592-599, gumbel_sample /
+// top_k :41-60 with k = ceil((1 - thres) * vocab)), `ids = where(ids == mask_id, pred, ids)` (:601-603) and, without a token critic, the
+// next scores `1 - softmax(logits)[pred]`, -1e5 at positions that were not masked (:615-619).  u is the uniform noise tensor (torch.rand,
+// or the reference's own draws in the parity test).  Values tied with the k-th largest logit are all kept.  One CTA of 256 threads per row.
+// ------------------------------------------------------------------------------------------------
+constexpr int MG_MAXV = 4096;
+
+__global__ void __launch_bounds__(256) mg_sample_kernel(const float* __restrict__ logits, const float* __restrict__ u, long long* __restrict__ ids,
+                                                        float* __restrict__ scores, int V, int k, float inv_temp, long long mask_id) {
+  __shared__ float lg[MG_MAXV];
+  __shared__ int hist[256];
+  __shared__ unsigned int sel[2];
+  __shared__ float redv[8];
+  __shared__ int redi[8];
+  const long long row = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const float* lr = logits + row * V;
+  float mx = -INFINITY;
+  for (int i = tid; i < V; i += 256) { const float v = lr[i]; lg[i] = v; mx = fmaxf(mx, v); }
+  __syncthreads();
+  // k-th largest logit: 4-pass, 8-bit radix select on the order-preserving integer image of the floats
+  float thr = -INFINITY;
+  if (k > 0 && k < V) {
+    unsigned int prefix = 0u, known = 0u;
+    int krem = k;
+    for (int pass = 3; pass >= 0; --pass) {
+      hist[tid] = 0;
+      __syncthreads();
+      for (int i = tid; i < V; i += 256) {
+        const unsigned int b = __float_as_uint(lg[i]);
+        const unsigned int key = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+        if ((key & known) == prefix) atomicAdd(&hist[(key >> (8 * pass)) & 255u], 1);
+      }
+      __syncthreads();
+      if (tid < 32) {                      // lane owns bins 8 lane .. 8 lane + 7; suffix sums run from the top bin down
+        int c[8], local = 0;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { c[e] = hist[tid * 8 + e]; local += c[e]; }
+        int incl = local;
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_down_sync(0xffffffffu, incl, o);
+          if (tid + o < 32) incl += t;
+        }
+        const int above = incl - local;
+        if (above < krem && krem <= incl) {
+          int acc = above;
+#pragma unroll
+          for (int e = 7; e >= 0; --e) {
+            if (acc + c[e] >= krem) { sel[0] = (unsigned)(tid * 8 + e); sel[1] = (unsigned)(krem - acc); break; }
+            acc += c[e];
+          }
+        }
+      }
+      __syncthreads();
+      prefix |= sel[0] << (8 * pass);
+      known |= 255u << (8 * pass);
+      krem = (int)sel[1];
+      __syncthreads();
+    }
+    thr = __uint_as_float((prefix & 0x80000000u) ? (prefix & 0x7fffffffu) : ~prefix);
+  }
+  // arg-max of the kept logits / temp + gumbel noise (lowest index on ties), and the softmax denominator of the raw logits
+  const float* ur = u + row * V;
+  float best = -INFINITY, se = 0.f;
+  int bi = 0x7fffffff;
+  for (int i = tid; i < V; i += 256) {
+    const float v = lg[i];
+    if (v >= thr) {
+      const float g = -logf(fmaxf(-logf(fmaxf(ur[i], 1e-20f)), 1e-20f));
+      const float t = v * inv_temp + g;
+      if (t > best || (t == best && i < bi)) { best = t; bi = i; }
+    }
+  }
+  for (int o = 16; o; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  if (lane == 0) { redv[w] = best; redi[w] = bi; }
+  __syncthreads();
+  best = redv[0]; bi = redi[0];
+  for (int ww = 1; ww < 8; ++ww)
+    if (redv[ww] > best || (redv[ww] == best && redi[ww] < bi)) { best = redv[ww]; bi = redi[ww]; }
+  __syncthreads();
+  const long long old = ids[row];
+  const bool was_mask = old == mask_id;
+  if (scores != nullptr) {
+    if (lane == 0) redv[w] = mx;
+    __syncthreads();
+    mx = redv[0];
+    for (int ww = 1; ww < 8; ++ww) mx = fmaxf(mx, redv[ww]);
+    __syncthreads();
+    se = 0.f;
+    for (int i = tid; i < V; i += 256) se += expf(lg[i] - mx);
+    for (int o = 16; o; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
+    if (lane == 0) redv[w] = se;
+    __syncthreads();
+    if (tid == 0) {
+      float tot = 0.f;
+      for (int ww = 0; ww < 8; ++ww) tot += redv[ww];
+      scores[row] = was_mask ? 1.0f - expf(lg[bi] - mx) / tot : -1e5f;
+    }
+  }
+  if (tid == 0 && was_mask) ids[row] = bi;
+}
+
+int launch_mg_sample(const float* logits, const float* u, long long* ids, float* scores, long long rows, int V, int k, float inv_temp, long long mask_id,
+                     cudaStream_t st) {
+  if (rows < 1 || V < 1 || V > MG_MAXV || k < 0) return BEVGEN_ERR_ARG;
+  mg_sample_kernel<<<(unsigned)rows, 256, 0, st>>>(logits, u, ids, scores, V, k, inv_temp, mask_id);
+  return cudaGetLastError() == cudaSuccess ? BEVGEN_OK : BEVGEN_ERR_CUDA;
+}
+
+// mg_remask: per camera row of hw tokens, the n_mask positions with the largest scores (+ (u - 0.5) * noise_scale when u is given: the
+// critic-noise of :611-613) become mask_id again (:573-579: scores.topk(n_mask).indices scattered into ids), then positions given by
+// init_ids (partial decoding: init_ids != mask_id) are restored (:581-582).  Exact selection by rank (ties: lower index first).
+constexpr int MG_MAXHW = 2048;
+
+__global__ void __launch_bounds__(256) mg_remask_kernel(const float* __restrict__ scores, const float* __restrict__ u, float noise_scale,
+                                                        long long* __restrict__ ids, const long long* __restrict__ init_ids, int hw, int n_mask,
+                                                        long long mask_id) {
+  __shared__ float sc[MG_MAXHW];
+  const long long row = blockIdx.x;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < hw; i += 256) {
+    float v = scores[row * hw + i];
+    if (u != nullptr) v += (u[row * hw + i] - 0.5f) * noise_scale;
+    sc[i] = v;
+  }
+  __syncthreads();
+  for (int i = tid; i < hw; i += 256) {
+    const float v = sc[i];
+    int rank = 0;
+    for (int j = 0; j < hw; ++j) {
+      const float o = sc[j];
+      rank += (o > v || (o == v && j < i)) ? 1 : 0;
+    }
+    long long out = ids[row * hw + i];
+    if (rank < n_mask) out = mask_id;
+    if (init_ids != nullptr) {
+      const long long ini = init_ids[row * hw + i];
+      if (ini != mask_id) out = ini;
+    }
+    ids[row * hw + i] = out;
+  }
+}
+
+int launch_mg_remask(const float* scores, const float* u, float noise_scale, long long* ids, const long long* init_ids, long long rows, int hw, int n_mask,
+                     long long mask_id, cudaStream_t st) {
+  if (rows < 1 || hw < 1 || hw > MG_MAXHW || n_mask < 0) return BEVGEN_ERR_ARG;
+  mg_remask_kernel<<<(unsigned)rows, 256, 0, st>>>(scores, u, noise_scale, ids, init_ids, hw, n_mask, mask_id);
+  return cudaGetLastError() == cudaSuccess ? BEVGEN_OK : BEVGEN_ERR_CUDA;
+}
+
 }  // namespace bevgen

@@ -343,8 +343,7 @@ class MaskGitEngine:
     def generate(self, cond_ids, batch, timesteps=18, temperature=1.0, topk_filter_thres=0.9, critic_noise_scale=1.0, init_ids=None,
                  use_critic=None, noise=None, generator=None, trace=None, use_graph=True):
         """MaskGit.generate (:511-627).  noise(kind, step, shape) -> uniform(0, 1) tensor (tests replay the reference's draws); default:
-        torch.rand on the device.  The token bookkeeping between the forwards (top-k, scatter, gumbel arg-max) is a handful of torch
-        calls on [b*cam, hw(, vocab)] tensors."""
+        torch.rand on the device.  The token bookkeeping between the forwards runs in bevgen_mg_remask / bevgen_mg_sample."""
         dev = self.dev
         use_critic = (self.critic is not None) if use_critic is None else use_critic
         if noise is None:
@@ -360,11 +359,16 @@ class MaskGitEngine:
             init_mask = init_ids != self.mask_id
         k = math.ceil((1 - topk_filter_thres) * self.vocab)
         gr = self._graphs(cond_ids, batch, use_critic) if use_graph else None
+        # The cosine schedule is host (CPU tensor) arithmetic - no device read-back; the token bookkeeping between the forwards is two launches per
+        # step: mg_remask (top-n_mask of the scores + critic noise -> mask_id, init_ids restored) and mg_sample (top-k filter, gumbel
+        # arg-max, fill of the masked positions, and without a critic the next scores).
+        ids = ids.contiguous()
+        pending = None                                            # (uniform, scale) of the critic noise, folded into the next mg_remask
+        init_c = None if init_ids is None else init_ids.contiguous()
         for step, (t, until_x0) in enumerate(zip(torch.linspace(0, 1, timesteps), reversed(range(timesteps)))):
-            n_mask = max(int((torch.cos(t * math.pi * 0.5) * hw).item()), 1)
-            ids = ids.scatter(1, scores.topk(n_mask, dim=-1).indices, self.mask_id)
-            if init_ids is not None:
-                ids[init_mask] = init_ids[init_mask]
+            n_mask = max(int((torch.cos(t * math.pi * 0.5) * hw).item()), 1)      # CPU float32 arithmetic, exactly the reference's (:567); no device sync
+            ops.mg_remask(scores.contiguous(), ids, n_mask, self.mask_id, uniform=None if pending is None else pending[0],
+                          noise_scale=0.0 if pending is None else pending[1], init_ids=init_c)
             if gr is not None:
                 gr["ids"].copy_(ids)
                 gr["g_fwd"].replay()
@@ -374,13 +378,9 @@ class MaskGitEngine:
             if trace is not None:
                 trace.append((ids.clone(), logits.clone()))
             temp = temperature * (until_x0 / timesteps)
-            u = noise("gumbel", step, tuple(logits.shape)).to(dev)
-            g = -torch.log((-torch.log(u.clamp(min=1e-20))).clamp(min=1e-20))
-            val, ind = logits.topk(k, dim=-1)
-            filt = torch.full_like(logits, float("-inf")).scatter_(2, ind, val)
-            pred = (filt / max(temp, 1e-10) + g).argmax(-1)
-            is_mask = ids == self.mask_id
-            ids = torch.where(is_mask, pred, ids)
+            u = noise("gumbel", step, tuple(logits.shape)).to(dev, torch.float32).contiguous()
+            nxt = None if use_critic else torch.empty(shape, dtype=torch.float32, device=dev)
+            ops.mg_sample(logits.contiguous(), u, ids, k, 1.0 / max(temp, 1e-10), self.mask_id, scores=nxt)
             if use_critic:
                 if gr is not None:
                     gr["ids"].copy_(ids)
@@ -388,8 +388,7 @@ class MaskGitEngine:
                     scores = gr["scores"]
                 else:
                     scores = self.critic_scores(ids, cond_ids, batch)
-                scores = scores + (noise("critic", step, tuple(scores.shape)).to(dev) - 0.5) * critic_noise_scale * (until_x0 / timesteps)
+                pending = (noise("critic", step, tuple(scores.shape)).to(dev, torch.float32).contiguous(), critic_noise_scale * (until_x0 / timesteps))
             else:
-                scores = 1 - logits.softmax(-1).gather(2, pred[..., None])[..., 0]
-                scores = scores.masked_fill(~is_mask, -1e5)
+                scores, pending = nxt, None
         return ids.view(shape[0], self.cfg.cam_latent_h, self.cfg.cam_latent_w)

@@ -532,3 +532,27 @@ def ray_embed_add(h_nhwc, intrinsics_inv, extrinsics_inv, pixel, img_w, cam_w):
         raise ValueError("ray_embed_add: camera matrices / pixel plane do not match the latent shape")
     _lib.check(lib.bevgen_ray_embed_add(_ptr(h_nhwc), _ptr(intrinsics_inv), _ptr(extrinsics_inv), _ptr(pixel), _ptr(img_w), _ptr(cam_w), n, hh * ww, d,
                                         _stream()), "ray_embed_add")
+
+
+def mg_sample(logits, uniform, ids, top_k, inv_temperature, mask_id, scores=None):
+    """bevgen_mg_sample: ids[row] <- argmax(top-k(logits) * inv_temperature + gumbel(uniform)) where ids[row] == mask_id (in place);
+    scores (optional, fp32 [rows]) <- 1 - softmax(logits)[pred] at masked rows, -1e5 elsewhere."""
+    _chk_cuda(logits, uniform, ids)
+    rows, V = logits.numel() // logits.shape[-1], logits.shape[-1]
+    assert logits.dtype == torch.float32 and uniform.dtype == torch.float32 and ids.dtype == torch.int64 and ids.numel() == rows and uniform.numel() == rows * V
+    Stats.launches += 1
+    _lib.check(_lib.init().bevgen_mg_sample(_ptr(logits), _ptr(uniform), _ptr(ids), _ptr(scores), rows, V, int(top_k), float(inv_temperature), int(mask_id),
+                                           _stream()), "mg_sample")
+
+
+def mg_remask(scores, ids, n_mask, mask_id, uniform=None, noise_scale=0.0, init_ids=None):
+    """bevgen_mg_remask: per camera row [hw] of `ids` (in place), the n_mask largest scores (+ (uniform - 0.5) * noise_scale) -> mask_id, then
+    positions where init_ids != mask_id are restored."""
+    _chk_cuda(scores, ids)
+    hw = ids.shape[-1]
+    rows = ids.numel() // hw
+    assert scores.dtype == torch.float32 and scores.numel() == rows * hw and ids.dtype == torch.int64
+    Stats.launches += 1
+    _lib.check(_lib.init().bevgen_mg_remask(_ptr(scores), _ptr(uniform), float(noise_scale), _ptr(ids), _ptr(init_ids), rows, hw, int(n_mask), int(mask_id),
+                                           _stream()), "mg_remask")
+

@@ -275,6 +275,16 @@ BEVGEN_API int bevgen_mg_head_planes(const float* src, long long src_ld, int src
  * scaled fp16 plane and the e4m3 pair plane of a following bevgen_linear_f16f8 (f_pad % 64 == 0). */
 BEVGEN_API int bevgen_mg_geglu_ln(const float* h, long long h_ld, const float* gamma, void* out_hi, void* out_lo, long long rows, int f, int f_pad,
                                   float eps, int f16f8, void* stream);
+/* MaskGit.generate token bookkeeping between the forwards (muse_maskgit_pytorch.py:569-627).
+ * mg_sample (:592-603,615-619, top_k / gumbel_sample :41-60): per token row [vocab], keep the top_k logits (ties with the k-th kept),
+ * pred = argmax(kept * inv_temperature + gumbel(uniform)), ids[row] = pred where ids[row] == mask_id; scores (may be NULL) receives
+ * 1 - softmax(logits)[pred] at masked positions and -1e5 elsewhere.  uniform: [rows][vocab] in (0, 1). */
+BEVGEN_API int bevgen_mg_sample(const float* logits, const float* uniform, long long* ids, float* scores, long long rows, int vocab, int top_k,
+                                float inv_temperature, long long mask_id, void* stream);
+/* mg_remask (:573-582, critic noise :611-613): per camera row [hw], the n_mask largest of scores (+ (uniform - 0.5) * noise_scale when
+ * uniform != NULL) are set to mask_id in ids, then positions with init_ids != mask_id (init_ids may be NULL) are restored. */
+BEVGEN_API int bevgen_mg_remask(const float* scores, const float* uniform, float noise_scale, long long* ids, const long long* init_ids, long long rows,
+                                int hw, int n_mask, long long mask_id, void* stream);
 
 /* ---------------------------------------------------------------- KV-cache autoregressive decode
  * Replaces the per-token full forward of Net2NetTransformer.sample (modules/stage2/cond_transformer_multi_view.py:154-227)

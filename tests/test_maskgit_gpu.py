@@ -206,3 +206,41 @@ def test_reference_geometry_14x25_vs_oracle():
     assert torch.isfinite(logits).all()
     assert (logits.cpu() - want_l).abs().max().item() < LOGIT_TOL
     assert (emb.cpu() - want_e).abs().max().item() < LOGIT_TOL
+
+
+def test_token_bookkeeping_kernels_match_the_torch_statement():
+    """bevgen_mg_sample / bevgen_mg_remask against the torch lines of MaskGit.generate they replace (muse_maskgit_pytorch.py:569-619):
+    top-k filter + gumbel arg-max + fill of masked positions + `1 - softmax[pred]` scores; top-n re-masking with critic noise and init_ids."""
+    from bevgen_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(5)
+    R, hw, V, mask_id = 12, 350, 1025, 1024
+    logits = torch.randn(R * hw, V, device="cuda", generator=g) * 2.0
+    u = torch.rand(R * hw, V, device="cuda", generator=g)
+    ids = torch.randint(0, 1024, (R, hw), device="cuda", generator=g)
+    ids[torch.rand(R, hw, device="cuda", generator=g) < 0.6] = mask_id
+    for temp in (0.7, 0.0):
+        k = 103
+        gum = -torch.log((-torch.log(u.clamp(min=1e-20))).clamp(min=1e-20))
+        val, ind = logits.topk(k, dim=-1)
+        filt = torch.full_like(logits, float("-inf")).scatter_(1, ind, val)
+        pred = (filt / max(temp, 1e-10) + gum).argmax(-1).view(R, hw)
+        is_mask = ids == mask_id
+        want_ids = torch.where(is_mask, pred, ids)
+        want_sc = (1 - logits.softmax(-1).gather(1, pred.view(-1, 1))[:, 0]).view(R, hw).masked_fill(~is_mask, -1e5)
+        got_ids, got_sc = ids.clone(), torch.empty(R, hw, device="cuda")
+        ops.mg_sample(logits, u, got_ids, k, 1.0 / max(temp, 1e-10), mask_id, scores=got_sc)
+        assert (got_ids != want_ids).float().mean().item() < 2e-4            # a 1-ulp difference of logf may flip a near-tie
+        same = got_ids == want_ids
+        assert (got_sc - want_sc)[same].abs().max().item() < 1e-5
+    # re-masking: exact top-n by rank, critic noise folded in, init_ids restored
+    sc = torch.randn(R, hw, device="cuda", generator=g)
+    un = torch.rand(R, hw, device="cuda", generator=g)
+    init = torch.full((R, hw), mask_id, device="cuda")
+    init[:, :40] = 7
+    for n_mask in (1, 123, hw):
+        eff = sc + (un - 0.5) * 0.8
+        want = want_ids.scatter(1, eff.topk(n_mask, dim=-1).indices, mask_id)
+        want[init != mask_id] = init[init != mask_id]
+        got = want_ids.clone()
+        ops.mg_remask(sc, got, n_mask, mask_id, uniform=un, noise_scale=0.8, init_ids=init)
+        assert torch.equal(got, want), n_mask
