@@ -2,24 +2,29 @@
 // (reference modules/stage2/cond_transformer_multi_view.py:154-227; cached formulation of SURVEY.md §3.4) for up to 16 scenes:
 //   per step:  24 x { LN1 -> QKV linear -> single-row attention over the KV cache (+ append) -> LN2 -> MLP1 + GELU -> MLP2 + residual }
 //              -> LN_f -> head -> top-k / softmax / multinomial -> embedding of the drawn token -> next step.
-// One CTA per SM (148), 16 consumer warps + 1 producer warp.  The path is HBM-bound (per step: every weight once + the whole KV cache),
-// so the design is a BYTE STREAM per SM: every CTA owns a fixed, contiguous slab of each weight matrix (8-row units, packed CTA-major in
-// mma fragment order by bevgen_pack_decode_linear) and a contiguous range of (scene, head, 128-key block) attention units; the producer
-// warp walks that fixed sequence with cp.async.bulk into a 5 x 32 KB shared-memory ring and runs AHEAD of the grid barriers (the bytes
-// do not depend on the activations), so HBM keeps streaming while the consumers synchronise.  Phases are separated by a grid-wide
-// barrier (monotonic counter, release/acquire at gpu scope; 1.24 us measured floor, tools/micro).
+// One CTA per SM (148), 16 consumer warps + 1 producer thread.  Per step every weight and the whole KV cache cross HBM once, so the
+// data side is a BYTE STREAM per SM: every CTA owns a fixed, contiguous slab of each weight matrix (8-row units, packed CTA-major in mma
+// fragment order by bevgen_pack_decode_linear) and whole (scene, head) pairs of the KV cache; the producer walks that fixed sequence
+// with cp.async.bulk into a 5 x 32 KB shared-memory ring and runs AHEAD of the grid barriers (the bytes do not depend on the
+// activations).  Phases are separated by a grid-wide barrier (monotonic counter, release / acquire at gpu scope).  What the kernel's
+// time depends on is the LATENCY CHAIN of its 98 phases per token, not bandwidth (DESIGN.md "What bounds the decode kernel"); the
+// rules that came out of the clock traces (tools/decode_trace.py) and same-box A/B runs (tools/build_variant.sh):
+//   - ONE warp per CTA (per block group in attention) asks an mbarrier, a barrier tells the others (16 warps on one mbarrier serialise);
+//   - as few CTA-wide barriers inside a phase as possible (each one re-exposes the slowest warp's L2 latency): two in a linear phase,
+//     none between MLP2's K-quarters, one 128-thread barrier per attention block;
+//   - global loads that feed the epilogue are issued at the start of the phase, independent ones together; no gpu-scope atomics inside a phase.
 //   * activations (16 x d) travel through L2 ALREADY SPLIT into fp16 hi + lo planes in mma A-fragment order: whoever finalises an
-//     output element writes it there, and every CTA fetches the vector it needs with ONE cp.async.bulk (148 CTAs reading the same 64 KB
-//     cost 0.58 us through the TMA engine against 2.7 us with ld.global, tools/micro/decode_micro.cu) followed by 8 shared-memory loads
-//     per lane.  LayerNorm is applied LAZILY: gamma is folded into the packed weights, the linear runs on the raw vector, and the
-//     epilogue applies  rstd_b * (acc - mean_b * c1_n) + c2_n  with c1_n = sum_k gamma_k W_nk, c2_n = bias_n + sum_k beta_k W_nk; the row
-//     statistics come from per-unit partial sums the finalisers leave next to the vector (fixed order -> deterministic).
+//     output element writes it there, and every warp reads ITS k-group of the vector straight into its A registers (8 coalesced
+//     16-byte loads per lane).  LayerNorm is applied LAZILY: gamma is folded into the packed weights, the linear runs on the raw vector,
+//     and the epilogue applies  rstd_b * (acc - mean_b * c1_n) + c2_n  with c1_n = sum_k gamma_k W_nk, c2_n = bias_n + sum_k beta_k W_nk;
+//     the row statistics come from per-unit partial sums the finalisers leave next to the vector (fixed order -> deterministic).
 //   * linears: mma.sync m16n8k16, A = the 16 batch rows (fp16 hi + lo), B = 8 weight rows per unit as fp16 + an e4m3 residual plane
-//     -> 3 bytes / weight at fp32-equivalent accuracy: x_hi*w16 + x_lo*w16 + x_hi*w8/S, fp32 accumulate (2 cycles / MMA / SM measured).
-//   * attention: CUDA cores on the staged K^T (64 x 128) / V (128 x 64) fp16 blocks with conflict-free half2 loads, flash-decoding
-//     partials merged per (scene, head) by the last arriving CTA (one acq_rel ticket), camera-bias row added BEFORE the 1/sqrt(d_head)
-//     scale (sparse_self_attention.py:155-168).
-//   * split outputs (MLP2 K-quarters, attention key ranges) are finalised by the last arriver in a FIXED order -> bit-reproducible.
+//     -> 3 bytes / weight at fp32-equivalent accuracy: x_hi*w16 + x_lo*w16 + x_hi*w8/S, fp32 accumulate; warp w = k-group w of every unit,
+//     one cross-warp reduction per phase.  MLP2: the CTA owns 8 output rows over all four K-quarters (no cross-CTA partial sums).
+//   * attention: a CTA owns whole (scene, head) pairs; a staged K^T (64 x 128) / V (128 x 64) fp16 block belongs to a group of four warps
+//     (32 keys each, CUDA cores, online softmax per warp), the per-warp partials of a pair are merged once; camera-bias row added BEFORE
+//     the 1/sqrt(d_head) scale (sparse_self_attention.py:155-168); the newest key is patched into the staged block.
+//   * every reduction has a fixed order -> bit-reproducible.
 #include <cstdlib>
 
 #include <cuda_fp16.h>
