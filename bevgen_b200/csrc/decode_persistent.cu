@@ -114,6 +114,11 @@ __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ unsigned int ld_relaxed_gpu(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ void red_release_gpu_add(unsigned int* p, unsigned int v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -171,7 +176,7 @@ __device__ __forceinline__ void grid_sync(DpSmem& sm, unsigned int* counter, uns
     DP_TR(sm, 92);
     const unsigned long long t0 = dp_globaltimer();
     unsigned int polls = 0, seen;
-    while ((seen = ld_acquire_gpu(counter)) < target) {
+    while ((seen = ld_relaxed_gpu(counter)) < target) {      // no acquire fence (it would invalidate L1, i.e. every spilled register): all cross-CTA data is read with .cg / TMA
       if ((++polls & 1023u) == 0 && dp_globaltimer() - t0 > 4000000000ull) dp_fail(sm, 1u, seen, target);
     }
     DP_TR(sm, 93);
