@@ -185,6 +185,15 @@ __device__ __forceinline__ void grid_sync(DpSmem& sm, unsigned int* counter, uns
   DP_TR(sm, 94);
 }
 
+// Boundary between two layer phases of ONE CTA (no grid barrier: the data are self-validating, see "tag sync" below): the shared scratch
+// of the finished phase is free, and its generic-proxy writes of act[] are ordered before a later async-proxy refill.
+__device__ __forceinline__ void phase_sync(DpSmem& sm) {
+  DP_TR(sm, 90);
+  fence_proxy_async();
+  bar_consumers();
+  DP_TR(sm, 94);
+}
+
 __device__ __forceinline__ void mma_f16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
@@ -194,6 +203,54 @@ __device__ __forceinline__ uint32_t e4m3x2_to_f16x2(uint16_t v) {
   const __half2_raw h = __nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)v, __NV_E4M3);
   return (uint32_t)h.x | ((uint32_t)h.y << 16);
 }
+// ---- self-validating data ("tag sync") --------------------------------------------------------------------------------------------
+// Inside a token step the layer phases are NOT separated by grid barriers.  Every value that crosses CTAs carries a one-bit generation
+// tag in its least significant mantissa bit (fp32: 2^-23 relative, the fp16 hi / lo halves of an activation: lo absorbs the forced bit of
+// hi, 2^-20 relative), every buffer exists twice (instance = running layer number & 1) and the tag flips each time an instance is
+// rewritten.  A reader simply loads what it needs from L2 (ld.global.cg) and repeats the load while a tag is the old one: the poll IS the
+// data fetch, no release fence / atomic / second round trip per phase.  Buffer reuse is safe without a barrier because every phase reads
+// what the whole grid produced in the phase before: a CTA that writes generation c + 2 of an instance has (transitively) seen every CTA
+// finish its reads of generation c.  Real grid barriers remain around the head / sampling / embedding of a step (3 per token).
+__device__ __forceinline__ int dp_inst(int c) { return c & 1; }
+__device__ __forceinline__ unsigned int dp_tag(int c) { return (unsigned int)(((c >> 1) & 1) ^ 1); }
+__device__ __forceinline__ float tag_f32(float v, unsigned int tag) { return __uint_as_float((__float_as_uint(v) & ~1u) | tag); }
+__device__ __forceinline__ float ldcg_f32(const float* p) {
+  float v;
+  asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float2 ldcg_f32x2(const float2* p) {
+  float2 v;
+  asm volatile("ld.global.cg.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint4 ldcg_u128(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+// bounded polling: a protocol bug becomes a trap after ~4 s instead of a hung GPU
+struct DpPoll {
+  unsigned int spins = 0;
+  unsigned long long t0 = 0ull;
+};
+__device__ __forceinline__ void poll_tick(const DpSmem& sm, DpPoll& pg, unsigned int code, unsigned int a) {
+  if ((++pg.spins & 255u) == 0) {
+    const unsigned long long now = dp_globaltimer();
+    if (pg.t0 == 0ull) pg.t0 = now;
+    else if (now - pg.t0 > 4000000000ull) dp_fail(sm, code, a, pg.spins);
+  }
+}
+// one fp32 value of generation `tag`
+__device__ __forceinline__ float ld_tagged(const DpSmem& sm, const float* p, unsigned int tag, unsigned int code) {
+  float v = ldcg_f32(p);
+  if ((__float_as_uint(v) & 1u) != tag) {
+    DpPoll pg;
+    do { poll_tick(sm, pg, code, tag); v = ldcg_f32(p); } while ((__float_as_uint(v) & 1u) != tag);
+  }
+  return v;
+}
+
 // x -> fp16 hi, lo with x ~= hi + lo (22 significant bits)
 __device__ __forceinline__ void split_f16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
   const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
@@ -210,6 +267,13 @@ __device__ __forceinline__ void part_range(int U, int& u0, int& u1) {
   const int bx = opaque((int)blockIdx.x), g = opaque((int)gridDim.x);
   u0 = (int)(((long long)bx * U) / g);
   u1 = (int)(((long long)(bx + 1) * U) / g);
+}
+// MLP2: quarter q of the K = 4d hidden vector belongs to CTAs [q * (grid / 4), (q + 1) * (grid / 4)), which share its d / 8 row units
+__device__ __forceinline__ void quarter_range(int upq, int& u0, int& u1) {
+  const int cpq = (int)gridDim.x >> 2, q = (int)blockIdx.x / cpq, j = (int)blockIdx.x - q * cpq;
+  if (q >= 4) { u0 = u1 = 0; return; }
+  u0 = q * upq + (int)(((long long)j * upq) / cpq);
+  u1 = q * upq + (int)(((long long)(j + 1) * upq) / cpq);
 }
 enum { RNG_QKV = 0, RNG_MLP1 = 1, RNG_MLP2 = 2, RNG_HEAD = 3 };
 __device__ __forceinline__ void cta_range(const DpSmem& sm, int which, int& u0, int& u1) { u0 = sm.rng[which][0]; u1 = sm.rng[which][1]; }
@@ -281,10 +345,10 @@ __device__ __forceinline__ void ring_release_shared(DpSmem& sm, unsigned int seq
 // ------------------------------------------------------------------------------------------------ producer
 // The byte stream of this CTA, in exactly the order its consumers take it (both sides derive it from blockIdx alone):
 //   per layer: QKV units [part_range(3d/8)] | every 128-key block of the CTA's (scene, head) pairs | MLP1 units [part_range(4d/8)] |
-//              for every owned MLP2 row unit [part_range(d/8)]: its four K-quarters;   per step: head units [part_range(vpad/8)].
+//              MLP2 units of the CTA's K-quarter [quarter_range];   per step: head units [part_range(vpad/8)].
 __device__ __noinline__ void dp_producer(const DecodeParams& p, DpSmem& sm) {
   unsigned int seq = 0;
-  const int d = p.d, KG = d >> 6, upq = d >> 3;
+  const int d = p.d, KG = d >> 6;
   const uint32_t unit_bytes = (uint32_t)KG * DP_KG_BYTES;
   unsigned long long tw = 0ull, ta = 0ull, te = 0ull;
   const bool prof = p.profile != nullptr;
@@ -308,8 +372,6 @@ __device__ __noinline__ void dp_producer(const DecodeParams& p, DpSmem& sm) {
     for (int u = u0; u < u1; ++u) issue_unit(base + (size_t)u * unit_bytes);
   };
   const int BH = p.B * p.H;
-  int r0, r1;
-  cta_range(sm, RNG_MLP2, r0, r1);
   for (int s = p.step_begin; s < p.step_end; ++s) {
     const int n = p.nc + s, nblk = (n + 127) >> 7;
     for (int l = 0; l < p.n_layers; ++l) {
@@ -317,7 +379,7 @@ __device__ __noinline__ void dp_producer(const DecodeParams& p, DpSmem& sm) {
       stream_units(L.w_qkv, RNG_QKV);
       if ((int)blockIdx.x < BH) {  // attention units: every 128-key block of this CTA's (scene, head) pairs
         if (s > p.step_begin) {
-          // The blocks hold keys appended during step s - 1: do not run ahead of the grid barrier that closed attention phase (s - 1, l).
+          // The blocks hold keys this CTA's consumers appended during step s - 1: do not run ahead of their attention phase (s - 1, l).
           // With 24 layers the ring (5 units) never reaches that far back; tiny models (a few units per step) do.
           const unsigned int need = (unsigned)(s - 1 - p.step_begin) * (unsigned)p.n_layers + (unsigned)l + 1u;
           if (sm.att_epoch < need) {
@@ -329,7 +391,8 @@ __device__ __noinline__ void dp_producer(const DecodeParams& p, DpSmem& sm) {
             }
             te += dp_globaltimer() - te0;
           }
-          fence_proxy_async_all();          // generic-proxy stores (ordered by the grid barrier) -> this thread's async-proxy reads
+          __threadfence();                  // the consumers' appends (same CTA; observed through att_epoch) are performed at gpu scope ...
+          fence_proxy_async_all();          // ... and ordered before this thread's async-proxy reads
         }
         for (int bh = blockIdx.x; bh < BH; bh += gridDim.x) {
           for (int blk = 0; blk < nblk; ++blk, ++seq) {
@@ -351,8 +414,7 @@ __device__ __noinline__ void dp_producer(const DecodeParams& p, DpSmem& sm) {
         }
       }
       stream_units(L.w_1, RNG_MLP1);
-      for (int ru = r0; ru < r1; ++ru)      // MLP2: the CTA's 8 output rows, the four K-quarters in turn
-        for (int q = 0; q < 4; ++q) issue_unit(L.w_2 + ((size_t)q * upq + ru) * unit_bytes);
+      stream_units(L.w_2, RNG_MLP2);        // the CTA's row units of ITS K-quarter (unit number = quarter * d / 8 + row unit)
     }
     stream_units(p.w_head, RNG_HEAD);
   }
@@ -369,27 +431,64 @@ __device__ __forceinline__ int frag_off(int b, int c) {
   const int lane = ((b & 7) << 2) | ((cc & 7) >> 1), reg = (b >> 3) | ((cc >> 3) << 1);
   return kg * 4096 + ks * 512 + lane * 16 + reg * 4 + (cc & 1) * 2;
 }
-__device__ __forceinline__ void store_frag(uint8_t* __restrict__ base, int b, int c, float x) {
-  const __half hi = __float2half_rn(x);
-  const __half lo = __float2half_rn(x - __half2float(hi));
+// Both halves carry the generation tag in their last mantissa bit; lo is computed against the TAGGED hi, so hi + lo still has ~20 bits.
+__device__ __forceinline__ void store_frag(uint8_t* __restrict__ base, int b, int c, float x, unsigned int tag) {
+  const unsigned short hb = (unsigned short)((__half_as_ushort(__float2half_rn(x)) & 0xfffeu) | tag);
+  const unsigned short lb = (unsigned short)((__half_as_ushort(__float2half_rn(x - __half2float(__ushort_as_half(hb)))) & 0xfffeu) | tag);
   const int off = frag_off(b, c);
-  *reinterpret_cast<__half*>(base + off) = hi;
-  *reinterpret_cast<__half*>(base + off + 2048) = lo;
+  *reinterpret_cast<unsigned short*>(base + off) = hb;
+  *reinterpret_cast<unsigned short*>(base + off + 2048) = lb;
+}
+// Warp w's k-group of an activation vector (fragment order) straight from L2 into the A registers, repeated until every half of the rows
+// that exist (b < B) carries `tag`: 8 coalesced 16-byte loads per lane.
+__device__ __forceinline__ void load_afrag_tagged(const DpSmem& sm, const uint8_t* __restrict__ vec, int w, int lane, int B, unsigned int tag,
+                                                  uint32_t (&ahi)[4][4], uint32_t (&alo)[4][4]) {
+  const uint4* src = reinterpret_cast<const uint4*>(vec + (size_t)w * 4096 + lane * 16);
+  const uint32_t tm = tag ? 0x00010001u : 0u;
+  const int g = lane >> 2;
+  const uint32_t m0 = (g < B) ? 0x00010001u : 0u, m1 = (g + 8 < B) ? 0x00010001u : 0u;      // registers 0, 2: row g | 1, 3: row g + 8
+  DpPoll pg;
+  for (;;) {
+    uint32_t bad = 0u;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint4 h4 = ldcg_u128(src + j * 32), l4 = ldcg_u128(src + 128 + j * 32);
+      ahi[j][0] = h4.x; ahi[j][1] = h4.y; ahi[j][2] = h4.z; ahi[j][3] = h4.w;
+      alo[j][0] = l4.x; alo[j][1] = l4.y; alo[j][2] = l4.z; alo[j][3] = l4.w;
+      bad |= (((h4.x ^ tm) | (h4.z ^ tm) | (l4.x ^ tm) | (l4.z ^ tm)) & m0) | (((h4.y ^ tm) | (h4.w ^ tm) | (l4.y ^ tm) | (l4.w ^ tm)) & m1);
+    }
+    if (bad == 0u) break;
+    poll_tick(sm, pg, 8u, (unsigned)w);
+  }
+  __syncwarp();
 }
 
 // ------------------------------------------------------------------------------------------------ linear phase (consumers)
-enum { EPI_QKV = 0, EPI_MLP1 = 1, EPI_MLP2 = 2, EPI_HEAD = 3 };
+enum { EPI_QKV = 0, EPI_MLP1 = 1, EPI_M2P = 2, EPI_HEAD = 3 };      // EPI_M2P: a K-quarter of MLP2 -> raw partial sums (no LayerNorm, no bias)
 
 // LayerNorm statistics of the 16 rows from the finalisers' partial sums ps[row][part][2] = (sum, sum of squares): warp w = row w.
 // Two halves so that the global loads (issued at the start of a phase) are in flight while the activation vector arrives and the MMAs run.
-__device__ __forceinline__ void row_stats_load(const DecodeParams& p, const float* __restrict__ ps, int nparts, float& S, float& Q) {
+__device__ __forceinline__ void row_stats_load(const DecodeParams& p, const DpSmem& sm, const float* __restrict__ ps, int nparts, unsigned int tag, float& S,
+                                               float& Q) {
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float2 v[4];                              // nparts <= 128: four independent loads per lane, one L2 round trip
+  float2 v[4];                              // nparts <= 128: four independent loads per lane, one L2 round trip (repeated while a tag is old)
+  DpPoll pg;
+  for (;;) {
+    unsigned int bad = 0u;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int i = lane + 32 * j;
-    v[j] = (w < p.B && i < nparts) ? __ldcg(reinterpret_cast<const float2*>(ps) + (size_t)w * nparts + i) : make_float2(0.f, 0.f);
+    for (int j = 0; j < 4; ++j) {
+      const int i = lane + 32 * j;
+      if (w < p.B && i < nparts) {
+        v[j] = ldcg_f32x2(reinterpret_cast<const float2*>(ps) + (size_t)w * nparts + i);
+        bad |= ((__float_as_uint(v[j].x) ^ tag) | (__float_as_uint(v[j].y) ^ tag)) & 1u;
+      } else {
+        v[j] = make_float2(0.f, 0.f);
+      }
+    }
+    if (bad == 0u) break;
+    poll_tick(sm, pg, 9u, (unsigned)w);
   }
+  __syncwarp();
   S = (v[0].x + v[1].x) + (v[2].x + v[3].x);
   Q = (v[0].y + v[1].y) + (v[2].y + v[3].y);
 }
@@ -433,9 +532,11 @@ __device__ __forceinline__ void unit_mma(const uint8_t* slot, int w, int lane, c
 // and hands the slot back through a shared-memory counter (no CTA barrier per unit); the 16 partial sums of up to DP_MAXU units are added
 // once, one output element per thread, whose epilogue constants were requested before the MMAs.
 //   frag_src: the activation vector in fragment order;  stats / nparts / which: partial sums of the lazy LayerNorm, see combine_row_stats
+//   rtag: generation tag of the inputs (frag_src, stats);  out / wtag: where the results go (QKV: fp32 [16][3d], MLP1: the four fragment-
+//   order quarters, head: LOGITS - untagged, a real grid barrier follows) and the tag they carry
 __device__ __noinline__ void linear_phase(const DecodeParams& p, DpSmem& sm, unsigned int& seq, unsigned int& act_par, const int epi, const uint8_t* __restrict__ frag_src,
                              const float* __restrict__ stats, int nparts, int which, int rng, float inv_s, const float* __restrict__ c1,
-                             const float* __restrict__ c2) {
+                             const float* __restrict__ c2, unsigned int rtag, void* __restrict__ out, unsigned int wtag) {
   const int tid = opaque((int)threadIdx.x), w = tid >> 5, lane = tid & 31;
   const int d = opaque(p.d), KG = d >> 6;
   const uint32_t vec_bytes = (uint32_t)KG * 4096u;
@@ -446,23 +547,18 @@ __device__ __noinline__ void linear_phase(const DecodeParams& p, DpSmem& sm, uns
   DP_TR(sm, 11);
   unsigned long long tf = p.profile != nullptr ? dp_globaltimer() : 0ull;
   auto fine = [&](int k) { if (tid == 0 && p.profile != nullptr && !sm.trace) { const unsigned long long now = dp_globaltimer(); sm.fine[k] += now - tf; tf = now; } };
-  float rsS, rsQ;
+  float rsS = 0.f, rsQ = 0.f;
   DP_TR(sm, 12);
-  row_stats_load(p, stats, nparts, rsS, rsQ);          // consumed after the MMAs
+  const bool lnorm = epi != EPI_M2P;
+  // (a CTA without units only needs the statistics when its attention phase will: LN1 of the pairs it owns)
+  if (u1 == u0 && !(lnorm && which == 0 && (int)blockIdx.x < p.B * p.H)) return;
+  if (lnorm) row_stats_load(p, sm, stats, nparts, rtag, rsS, rsQ);          // consumed after the MMAs
   DP_TR(sm, 13);
-  if (u1 == u0) { row_stats_finish(p, sm, which, rsS, rsQ); return; }      // (LN1 statistics are also read by the attention phase)
+  if (u1 == u0) { row_stats_finish(p, sm, which, rsS, rsQ); return; }
   // Every warp reads ITS k-group of the activation vector straight from L2 into the A registers (fragment order: 8 coalesced 16-byte
   // loads per lane; .cg: the vector was written by other SMs in the previous phase) - no staging buffer, no barrier for it.
   uint32_t ahi[4][4], alo[4][4];
-  if (w < KG) {
-    const uint4* src = reinterpret_cast<const uint4*>(frag_src + (size_t)w * 4096 + lane * 16);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const uint4 h4 = __ldcg(src + j * 32), l4 = __ldcg(src + 128 + j * 32);
-      ahi[j][0] = h4.x; ahi[j][1] = h4.y; ahi[j][2] = h4.z; ahi[j][3] = h4.w;
-      alo[j][0] = l4.x; alo[j][1] = l4.y; alo[j][2] = l4.z; alo[j][3] = l4.w;
-    }
-  }
+  if (w < KG) load_afrag_tagged(sm, frag_src, w, lane, p.B, rtag, ahi, alo);
   // Only warp 0 touches the mbarriers (16 warps asking the same barrier serialise in the SM's sync unit: ~1500 cycles per wait in the
   // trace of tools/decode_trace.py); the others learn through the CTA barrier.  The units were requested phases ago, so warp 0's
   // waits for them normally return at once.
@@ -482,7 +578,7 @@ __device__ __noinline__ void linear_phase(const DecodeParams& p, DpSmem& sm, uns
     const bool has = ui < nb && b < p.B;
     const int row = (ub + ui) * 8 + nrow;
     float c1v = 0.f, c2v = 0.f;
-    if (has) { c1v = __ldg(c1 + row); c2v = __ldg(c2 + row); }
+    if (has && lnorm) { c1v = __ldg(c1 + row); c2v = __ldg(c2 + row); }
     if (ub != u0) {                          // a further batch (more than DP_MAXU units per CTA: small grids only)
       if (w == 0) for (int k = 0; k < nb; ++k) ring_wait_full(sm, seq + (unsigned)k);
       bar_consumers();
@@ -500,7 +596,7 @@ __device__ __noinline__ void linear_phase(const DecodeParams& p, DpSmem& sm, uns
         DP_TR(sm, 18);
       }
     }
-    if (ub == u0) row_stats_finish(p, sm, which, rsS, rsQ);      // published by the barrier below
+    if (ub == u0 && lnorm) row_stats_finish(p, sm, which, rsS, rsQ);      // published by the barrier below
     DP_TR(sm, 19);
     bar_consumers();                        // every warp's partial sums are written, i.e. its loads of the staged units have returned
     if (tid == 0) for (int k = 0; k < nb; ++k) ring_release(sm, seq + (unsigned)k);      // one thread hands the batch's slots back
@@ -514,10 +610,13 @@ __device__ __noinline__ void linear_phase(const DecodeParams& p, DpSmem& sm, uns
       for (; ww + 4 <= KG; ww += 4) { v0 += rp[ww * 128]; v1 += rp[(ww + 1) * 128]; v2 += rp[(ww + 2) * 128]; v3 += rp[(ww + 3) * 128]; }
       for (; ww < KG; ++ww) v0 += rp[ww * 128];
       float v = (v0 + v1) + (v2 + v3);
-      const float2 st = sm.rowstat[which][b];
-      v = st.y * (v - st.x * c1v) + c2v;                                       // lazy LayerNorm + bias
-      if (epi == EPI_QKV) p.QKV[(size_t)b * 3 * d + row] = v;
-      else if (epi == EPI_MLP1) { const int qq = row / d; store_frag(p.HF + (size_t)qq * vec_bytes, b, row - qq * d, gelu_erf(v)); }
+      if (lnorm) {
+        const float2 st = sm.rowstat[which][b];
+        v = st.y * (v - st.x * c1v) + c2v;                                     // lazy LayerNorm + bias
+      }
+      if (epi == EPI_QKV) reinterpret_cast<float*>(out)[(size_t)b * 3 * d + row] = tag_f32(v, wtag);
+      else if (epi == EPI_MLP1) { const int qq = row / d; store_frag(reinterpret_cast<uint8_t*>(out) + (size_t)qq * vec_bytes, b, row - qq * d, gelu_erf(v), wtag); }
+      else if (epi == EPI_M2P) { const int qq = row / d; reinterpret_cast<float*>(out)[((size_t)qq * 16 + b) * d + (row - qq * d)] = tag_f32(v, wtag); }
       else if (row < p.vocab) p.LOGITS[(size_t)b * p.vocab + row] = v;
     }
     DP_TR(sm, 21);
@@ -526,74 +625,49 @@ __device__ __noinline__ void linear_phase(const DecodeParams& p, DpSmem& sm, uns
   fine(2);
 }
 
-// MLP2 + residual: the CTA owns 8 output rows over the whole K = 4d (four K-quarters = four units and four activation vectors in turn; the
-// next quarter's vector is requested as soon as this one is in registers), so the new residual row segment, its fragment-order copy and the
-// unit's LayerNorm partial sums are finished here - no cross-CTA partials.
-__device__ __noinline__ void mlp2_phase(const DecodeParams& p, DpSmem& sm, unsigned int& seq, unsigned int& act_par, const DecodeLayer& L) {
-  const int tid = opaque((int)threadIdx.x), w = tid >> 5, lane = tid & 31;
-  const int d = opaque(p.d), KG = d >> 6, upq = d >> 3;
-  const uint32_t vec_bytes = (uint32_t)KG * 4096u;
-  float* red = reinterpret_cast<float*>(sm.act);
-  int r0, r1;
-  cta_range(sm, RNG_MLP2, r0, r1);
-  if (r0 == r1) return;
-  unsigned long long tf = p.profile != nullptr ? dp_globaltimer() : 0ull;
-  auto fine = [&](int k) { if (tid == 0 && p.profile != nullptr && !sm.trace) { const unsigned long long now = dp_globaltimer(); sm.fine[k] += now - tf; tf = now; } };
-  const int fb = tid >> 3, fn = tid & 7;                 // finalisation mapping (threads 0..127): 8 consecutive lanes = one batch row
-  for (int ru = r0; ru < r1; ++ru) {
-    DP_TR(sm, 30);
-    // The four weight units of this row unit were requested phases ago: warp 0 makes sure they have landed, then nothing inside the
-    // quarter loop synchronises - every warp reads ITS k-group of each activation quarter straight from L2 into the A registers
-    // (fragment order: 8 coalesced 16-byte loads per lane), so there is no staging buffer to wait for or to hand back.
-    if (w == 0) for (int q = 0; q < 4; ++q) ring_wait_full(sm, seq + (unsigned)q);
-    const int row = ru * 8 + fn;
-    const bool fin = tid < 128 && fb < p.B;
-    float base = 0.f;
-    if (fin) base = __ldcg(p.X1 + (size_t)fb * d + row) + __ldg(L.c2_2 + row);
-    bar_consumers();
-    DP_TR(sm, 31);
-    float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f}, acc2[4] = {0.f, 0.f, 0.f, 0.f};
-    if (w < KG) {
-      for (int q = 0; q < 4; ++q) {
-        const uint4* src = reinterpret_cast<const uint4*>(p.HF + (size_t)q * vec_bytes + (size_t)w * 4096 + lane * 16);
-        uint32_t ahi[4][4], alo[4][4];
+// MLP2 + residual, split over K: the four K-quarters of the hidden vector belong to four groups of gridDim / 4 CTAs; a CTA runs its row
+// units of ITS quarter as an ordinary linear phase (EPI_M2P: one 64 KB activation quarter per CTA instead of the whole 256 KB vector - the
+// 148-fold broadcast of the hidden vector was what the phase's time went into) and leaves tagged fp32 partial sums P2[quarter][16][d].
+// CTA ru < d / 8 then finishes row unit ru: residual + bias + the four partials in quarter order (polled like any other tagged value: no
+// atomic, no fence), the new residual rows, their fragment-order copy and the unit's LayerNorm partial sums.
+__device__ __noinline__ void mlp2_finalize(const DecodeParams& p, DpSmem& sm, const DecodeLayer& L, int c) {
+  const int tid = opaque((int)threadIdx.x);
+  const int d = opaque(p.d), upq = d >> 3, ru = opaque((int)blockIdx.x);
+  if (ru >= upq || tid >= 128) return;
+  const int inst = dp_inst(c);
+  const unsigned int tag = dp_tag(c);
+  const float* X1i = p.X1 + (size_t)inst * 16 * d;
+  const float* P2i = p.P2 + (size_t)inst * 4 * 16 * d;
+  float* Xo = p.X + (size_t)inst * 16 * d;
+  uint8_t* XFo = p.XF + (size_t)inst * (size_t)(d >> 6) * 4096;
+  float* PSXo = p.PSX + (size_t)inst * 16 * upq * 2;
+  const int fb = tid >> 3, fn = tid & 7;                 // 8 consecutive lanes = one batch row
+  const int row = ru * 8 + fn;
+  const bool fin = fb < p.B;
+  float v = 0.f;
+  if (fin) {
+    const float bias = __ldg(L.c2_2 + row);
+    float x1, pq[4];
+    DpPoll pg;
+    for (;;) {                              // five independent loads in flight; repeated while a tag is old
+      x1 = ldcg_f32(X1i + (size_t)fb * d + row);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint4 h4 = __ldcg(src + j * 32), l4 = __ldcg(src + 128 + j * 32);
-          ahi[j][0] = h4.x; ahi[j][1] = h4.y; ahi[j][2] = h4.z; ahi[j][3] = h4.w;
-          alo[j][0] = l4.x; alo[j][1] = l4.y; alo[j][2] = l4.z; alo[j][3] = l4.w;
-        }
-        if (!(p.dbg & 2)) unit_mma(sm.ring[(seq + (unsigned)q) % DP_NSLOT], w, lane, ahi, alo, acc0, acc1, acc2);
-        DP_TR(sm, 33);
-      }
-      *reinterpret_cast<float4*>(&red[(w * 32 + lane) * 4]) =
-          make_float4((acc0[0] + acc2[0]) + acc1[0] * L.s_2, (acc0[1] + acc2[1]) + acc1[1] * L.s_2, (acc0[2] + acc2[2]) + acc1[2] * L.s_2,
-                      (acc0[3] + acc2[3]) + acc1[3] * L.s_2);
+      for (int q = 0; q < 4; ++q) pq[q] = ldcg_f32(P2i + ((size_t)q * 16 + fb) * d + row);
+      const unsigned int bad = ((__float_as_uint(x1) ^ tag) | (__float_as_uint(pq[0]) ^ tag) | (__float_as_uint(pq[1]) ^ tag) | (__float_as_uint(pq[2]) ^ tag) |
+                                (__float_as_uint(pq[3]) ^ tag)) & 1u;
+      if (bad == 0u) break;
+      poll_tick(sm, pg, 13u, (unsigned)ru);
     }
-    bar_consumers();                        // partial sums written; every warp's loads of the four slots have returned
-    if (tid == 0) for (int q = 0; q < 4; ++q) ring_release(sm, seq + (unsigned)q);
-    seq += 4u;
-    if (tid < 128) {
-      // (batch row fb, weight row fn) lives in lane 4 (fb % 8) + fn / 2, register 2 (fb / 8) + fn % 2 of the accumulator fragment
-      const int ee = ((((fb & 7) << 2) | (fn >> 1)) << 2) | (((fb >> 3) << 1) | (fn & 1));
-      float v = 0.f;
-      for (int ww = 0; ww < KG; ++ww) v += red[ww * 128 + ee];
-      v = fin ? base + v : 0.f;
-      if (fin) {
-        p.X[(size_t)fb * d + row] = v;
-        store_frag(p.XF, fb, row, v);
-      }
-      float sv = v, qv = v * v;
-      sv += __shfl_xor_sync(0xffffffffu, sv, 1); qv += __shfl_xor_sync(0xffffffffu, qv, 1);
-      sv += __shfl_xor_sync(0xffffffffu, sv, 2); qv += __shfl_xor_sync(0xffffffffu, qv, 2);
-      sv += __shfl_xor_sync(0xffffffffu, sv, 4); qv += __shfl_xor_sync(0xffffffffu, qv, 4);
-      if (fin && fn == 0) *reinterpret_cast<float2*>(p.PSX + ((size_t)fb * upq + ru) * 2) = make_float2(sv, qv);
-    }
-    DP_TR(sm, 34);
-    if (ru + 1 < r1) bar_consumers();       // the scratch is reused by the next row unit
-    DP_TR(sm, 35);
+    v = (x1 + bias) + ((pq[0] + pq[1]) + (pq[2] + pq[3]));
+    Xo[(size_t)fb * d + row] = tag_f32(v, tag);
+    store_frag(XFo, fb, row, v, tag);
   }
-  fine(7);
+  __syncwarp();
+  float sv = v, qv = v * v;
+  sv += __shfl_xor_sync(0xffffffffu, sv, 1); qv += __shfl_xor_sync(0xffffffffu, qv, 1);
+  sv += __shfl_xor_sync(0xffffffffu, sv, 2); qv += __shfl_xor_sync(0xffffffffu, qv, 2);
+  sv += __shfl_xor_sync(0xffffffffu, sv, 4); qv += __shfl_xor_sync(0xffffffffu, qv, 4);
+  if (fin && fn == 0) *reinterpret_cast<float2*>(PSXo + ((size_t)fb * upq + ru) * 2) = make_float2(tag_f32(sv, tag), tag_f32(qv, tag));
 }
 
 // ------------------------------------------------------------------------------------------------ attention phase (consumers)
@@ -605,13 +679,20 @@ __device__ __noinline__ void mlp2_phase(const DecodeParams& p, DpSmem& sm, unsig
 // shuffle joins the halves), half-warp online softmax, lane = (key mod 4, 8 channels) for P . V (16-byte loads of the value rows,
 // probabilities through a 128-byte per-warp scratch).  Blocks go round-robin over the four groups, every warp keeps a running
 // (max, sum, o[64]) per pair and leaves it in a table that one warp per pair merges in warp order.
-__device__ __noinline__ void attention_phase(const DecodeParams& p, DpSmem& sm, unsigned int& seq, unsigned int& bias_par, const DecodeLayer& L, int s) {
+__device__ __noinline__ void attention_phase(const DecodeParams& p, DpSmem& sm, unsigned int& seq, unsigned int& bias_par, const DecodeLayer& L, int s, int c) {
   const int tid = opaque((int)threadIdx.x), w = tid >> 5, lane = tid & 31;
   const int d = opaque(p.d), H = opaque(p.H), BH = p.B * H, G = opaque((int)gridDim.x), bx = opaque((int)blockIdx.x);
   const int n = p.nc + s, r = n - 1, nblk = (n + 127) >> 7;
   const int npairs = bx < BH ? (BH - 1 - bx) / G + 1 : 0;
   if (npairs == 0) return;
   const int nun = npairs * nblk;
+  // inputs: QKV of this layer (generation c), the residual stream X of the layer before (generation c - 1: MLP2 or the embedding)
+  const unsigned int tag = dp_tag(c), ptag = dp_tag(c - 1);
+  const float* QKVi = p.QKV + (size_t)dp_inst(c) * 16 * 3 * d;
+  const float* Xi = p.X + (size_t)dp_inst(c - 1) * 16 * d;
+  float* X1o = p.X1 + (size_t)dp_inst(c) * 16 * d;
+  uint8_t* X1Fo = p.X1F + (size_t)dp_inst(c) * (size_t)(d >> 6) * 4096;
+  float* PSX1o = p.PSX1 + (size_t)dp_inst(c) * 16 * H * 2;
   unsigned long long tf = p.profile != nullptr ? dp_globaltimer() : 0ull;
   auto fine = [&](int k) { if (tid == 0 && p.profile != nullptr && !sm.trace) { const unsigned long long now = dp_globaltimer(); sm.fine[k] += now - tf; tf = now; } };
   float* fa = reinterpret_cast<float*>(sm.act);
@@ -629,7 +710,7 @@ __device__ __noinline__ void attention_phase(const DecodeParams& p, DpSmem& sm, 
   for (int i = tid; i < npairs * 192; i += DP_CONSUMERS) {
     const int k = i / 192, which = (i % 192) >> 6, c = i & 63;
     const int bh = bx + k * G, b = bh / H, h = bh - b * H;
-    const float v = __ldcg(p.QKV + (size_t)b * 3 * d + which * d + h * 64 + c);
+    const float v = ld_tagged(sm, QKVi + (size_t)b * 3 * d + which * d + h * 64 + c, tag, 11u);
     if (which == 0) qs[k * 64 + c] = v;
     else if (which == 1) {
       kn[k * 64 + c] = v;
@@ -792,7 +873,8 @@ __device__ __noinline__ void attention_phase(const DecodeParams& p, DpSmem& sm, 
     const int bh = bx + w * G, b = bh / H, h = bh - b * H;
     const int c0 = h * 64 + lane, c1 = c0 + 32;
     const size_t xi = (size_t)b * p.d;
-    const float xa = __ldcg(p.X + xi + c0), xb = __ldcg(p.X + xi + c1);
+    const float xa = ld_tagged(sm, Xi + xi + c0, ptag, 12u), xb = ld_tagged(sm, Xi + xi + c1, ptag, 12u);
+    __syncwarp();
     const float ga = __ldg(L.ln1_g + c0), gb = __ldg(L.ln1_g + c1), ba = __ldg(L.ln1_b + c0), bb = __ldg(L.ln1_b + c1);
     const float* t = tab + (w * 16) * DP_PART;
     // lane i < 16 owns partial i: its weight exp(m_i - M) is computed once and broadcast
@@ -814,13 +896,13 @@ __device__ __noinline__ void attention_phase(const DecodeParams& p, DpSmem& sm, 
     }
     const float2 st = sm.rowstat[0][b];
     const float x0 = ((xa - st.x) * st.y * ga + ba) + o0 / Ls, x1 = ((xb - st.x) * st.y * gb + bb) + o1 / Ls;
-    p.X1[xi + c0] = x0;
-    p.X1[xi + c1] = x1;
-    store_frag(p.X1F, b, c0, x0);
-    store_frag(p.X1F, b, c1, x1);
+    X1o[xi + c0] = tag_f32(x0, tag);
+    X1o[xi + c1] = tag_f32(x1, tag);
+    store_frag(X1Fo, b, c0, x0, tag);
+    store_frag(X1Fo, b, c1, x1, tag);
     float sv = x0 + x1, qv = x0 * x0 + x1 * x1;
     for (int of = 16; of; of >>= 1) { sv += __shfl_xor_sync(0xffffffffu, sv, of); qv += __shfl_xor_sync(0xffffffffu, qv, of); }
-    if (lane == 0) *reinterpret_cast<float2*>(p.PSX1 + ((size_t)b * p.H + h) * 2) = make_float2(sv, qv);
+    if (lane == 0) *reinterpret_cast<float2*>(PSX1o + ((size_t)b * p.H + h) * 2) = make_float2(tag_f32(sv, tag), tag_f32(qv, tag));
   }
   DP_TR(sm, 61);
   fence_proxy_async_all();               // the appended key / value will be read by cp.async.bulk (async proxy) in the next step
@@ -967,13 +1049,16 @@ __device__ __noinline__ int sample_row(const DecodeParams& p, DpSmem& sm, int b,
 
 // Embedding of decode-order image token `sdec` (value tok) of scene b (mingpt_sparse.py:332-350; same arithmetic as embed_kernel)
 // -> the residual-stream row in fp32 (X), in fragment order (XF) and its LayerNorm sums (PSX: the whole row in part 0, zeros elsewhere).
-__device__ __noinline__ void embed_row(const DecodeParams& p, DpSmem& sm, int b, int sdec, long long tok) {
+// Written as generation `c` (the layer before the first layer of the step that consumes it; real grid barriers surround this phase).
+__device__ __noinline__ void embed_row(const DecodeParams& p, DpSmem& sm, int b, int sdec, long long tok, int c) {
   const int tid = threadIdx.x, d = p.d;
+  const unsigned int tag = dp_tag(c);
+  uint8_t* XFo = p.XF + (size_t)dp_inst(c) * (size_t)(d >> 6) * 4096;
   const int j = p.fwd[sdec];
   const int cam = j / p.hw, px = j - cam * p.hw;
   const float* e = p.x_tok_emb + (size_t)tok * d;
   const float* pos = p.x_pos_emb + (size_t)j * d;
-  float* out = p.X + (size_t)b * d;
+  float* out = p.X + (size_t)dp_inst(c) * 16 * d + (size_t)b * d;
   float gv[2] = {0.f, 0.f};
   float inv = 0.f;
   if (p.img_embed_w != nullptr) {
@@ -988,9 +1073,9 @@ __device__ __noinline__ void embed_row(const DecodeParams& p, DpSmem& sm, int b,
     for (int rr = 0; rr < 4; ++rr) ray[rr] = E[rr * 4 + 0] * cv[0] + E[rr * 4 + 1] * cv[1] + E[rr * 4 + 2] * cv[2] + E[rr * 4 + 3] * cv[3];
     float ss = 0.f;
     int k = 0;
-    for (int c = tid; c < d; c += DP_CONSUMERS, ++k) {
-      const float4 wi = __ldg(reinterpret_cast<const float4*>(p.img_embed_w) + c);
-      const float4 wc = __ldg(reinterpret_cast<const float4*>(p.cam_embed_w) + c);
+    for (int ch = tid; ch < d; ch += DP_CONSUMERS, ++k) {
+      const float4 wi = __ldg(reinterpret_cast<const float4*>(p.img_embed_w) + ch);
+      const float4 wc = __ldg(reinterpret_cast<const float4*>(p.cam_embed_w) + ch);
       const float de = wi.x * ray[0] + wi.y * ray[1] + wi.z * ray[2] + wi.w * ray[3];
       const float ce = wc.x * E[3] + wc.y * E[7] + wc.z * E[11] + wc.w * E[15];
       gv[k] = de - ce;
@@ -1001,17 +1086,17 @@ __device__ __noinline__ void embed_row(const DecodeParams& p, DpSmem& sm, int b,
   }
   float sv = 0.f, qv = 0.f;
   int k = 0;
-  for (int c = tid; c < d; c += DP_CONSUMERS, ++k) {
-    const float x = (e[c] + gv[k] * inv) + pos[c];
-    out[c] = x;
-    store_frag(p.XF, b, c, x);
+  for (int ch = tid; ch < d; ch += DP_CONSUMERS, ++k) {
+    const float x = (e[ch] + gv[k] * inv) + pos[ch];
+    out[ch] = tag_f32(x, tag);
+    store_frag(XFo, b, ch, x, tag);
     sv += x; qv += x * x;
   }
   sv = consumers_sum(sv, sm.red16);
   qv = consumers_sum(qv, sm.red16);
   const int nparts = d >> 3;
-  float2* ps = reinterpret_cast<float2*>(p.PSX) + (size_t)b * nparts;
-  for (int i = tid; i < nparts; i += DP_CONSUMERS) ps[i] = (i == 0) ? make_float2(sv, qv) : make_float2(0.f, 0.f);
+  float2* ps = reinterpret_cast<float2*>(p.PSX + (size_t)dp_inst(c) * 16 * nparts * 2) + (size_t)b * nparts;
+  for (int i = tid; i < nparts; i += DP_CONSUMERS) ps[i] = (i == 0) ? make_float2(tag_f32(sv, tag), tag_f32(qv, tag)) : make_float2(tag_f32(0.f, tag), tag_f32(0.f, tag));
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
@@ -1027,7 +1112,7 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(const 
     sm.debug = p.debug;
     part_range(3 * p.d / 8, sm.rng[RNG_QKV][0], sm.rng[RNG_QKV][1]);
     part_range(4 * p.d / 8, sm.rng[RNG_MLP1][0], sm.rng[RNG_MLP1][1]);
-    part_range(p.d / 8, sm.rng[RNG_MLP2][0], sm.rng[RNG_MLP2][1]);
+    quarter_range(p.d / 8, sm.rng[RNG_MLP2][0], sm.rng[RNG_MLP2][1]);
     part_range(p.vpad / 8, sm.rng[RNG_HEAD][0], sm.rng[RNG_HEAD][1]);
     sm.trace = (p.profile != nullptr && (p.dbg & 64) && blockIdx.x == (unsigned)p.trace_cta) ? p.profile + (size_t)gridDim.x * 32 : nullptr;
     sm.trace_n = 0; sm.trace_on = 0;
@@ -1047,14 +1132,14 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(const 
   const int d = p.d, H = p.H;
   const bool has_pairs = (int)blockIdx.x < p.B * H;
   const bool tma_bias = p.bias != nullptr && (p.bias_ld & 3) == 0;
-  // X <- embedding of the token drawn at step step_begin - 1 (it is already in the token grid)
+  // X <- embedding of the token drawn at step step_begin - 1 (it is already in the token grid), as generation -1
   if ((int)blockIdx.x < p.B) {
     const int b = blockIdx.x, sdec = p.step_begin - 1;
     const int j = p.fwd[sdec];
-    embed_row(p, sm, b, sdec, p.cam_idx[((size_t)b * p.ncam + j / p.hw) * p.hw + (j % p.hw)]);
+    embed_row(p, sm, b, sdec, p.cam_idx[((size_t)b * p.ncam + j / p.hw) * p.hw + (j % p.hw)], -1);
   }
   grid_sync(sm, p.barrier, bar_target, G);
-  // optional per-CTA profile: nanoseconds spent in each phase body and in each phase's grid barrier, summed over the launch
+  // optional per-CTA profile: nanoseconds spent in each phase body and in each phase boundary, summed over the launch
   unsigned long long tmark = dp_globaltimer();
   auto mark = [&](int slot, unsigned int step, unsigned int layer, unsigned int phase) {
     if (tid == 0) {
@@ -1066,15 +1151,19 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(const 
       sm.where[0] = step; sm.where[1] = layer; sm.where[2] = phase;
     }
   };
+  const size_t vecb = (size_t)(d >> 6) * 4096;
+  int c = 0;                               // running layer number of this launch: instance c & 1, tag dp_tag(c) of everything layer c writes
   for (int s = p.step_begin; s < p.step_end; ++s) {
-    for (int l = 0; l < p.n_layers; ++l) {
+    for (int l = 0; l < p.n_layers; ++l, ++c) {
       const DecodeLayer& L = p.layers[l];
       if (tid == 0 && sm.trace != nullptr) sm.trace_on = (s == p.trace_step && l == p.n_layers / 4) ? 1 : 0;
       DP_TR(sm, 1);
       mark(11, s, l, 0);
-      linear_phase(p, sm, seq, act_par, EPI_QKV, p.XF, p.PSX, d >> 3, 0, RNG_QKV, L.s_qkv, L.c1_qkv, L.c2_qkv);
+      linear_phase(p, sm, seq, act_par, EPI_QKV, p.XF + (size_t)dp_inst(c - 1) * vecb, p.PSX + (size_t)dp_inst(c - 1) * 16 * (d >> 3) * 2, d >> 3, 0, RNG_QKV,
+                   L.s_qkv, L.c1_qkv, L.c2_qkv, dp_tag(c - 1), p.QKV + (size_t)dp_inst(c) * 16 * 3 * d, dp_tag(c));
       if (tid == 0 && has_pairs && tma_bias) {
-        // camera-bias row of this step -> upper half of act[] (free since the fragments went to registers); waited for in the attention phase
+        // camera-bias row of this step -> upper half of act[] (not part of the QKV reduction scratch, only ever written by these copies);
+        // waited for in the attention phase
         const int n = p.nc + s;
         const uint32_t bytes = (uint32_t)((n + 3) & ~3) * 4u;
         mbar_expect_tx(&sm.bias_bar, bytes);
@@ -1082,31 +1171,39 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(const 
       }
       mark(0, s, l, 1);
       DP_TR(sm, 2);
-      grid_sync(sm, p.barrier, bar_target, G);
+      phase_sync(sm);
       mark(1, s, l, 2);
       DP_TR(sm, 3);
-      attention_phase(p, sm, seq, bias_par, L, s);
+      attention_phase(p, sm, seq, bias_par, L, s, c);
       mark(2, s, l, 3);
       DP_TR(sm, 4);
-      grid_sync(sm, p.barrier, bar_target, G);
-      if (tid == 0) sm.att_epoch = (unsigned)(s - p.step_begin) * (unsigned)p.n_layers + (unsigned)l + 1u;      // every CTA's appends of (s, l) are visible
+      phase_sync(sm);
+      // this CTA's appends of (s, l) are done (it owns its pairs' cache rows): the producer may request the blocks of (s + 1, l)
+      if (tid == 0) { __threadfence_block(); sm.att_epoch = (unsigned)(s - p.step_begin) * (unsigned)p.n_layers + (unsigned)l + 1u; }
       mark(3, s, l, 4);
       DP_TR(sm, 5);
-      linear_phase(p, sm, seq, act_par, EPI_MLP1, p.X1F, p.PSX1, H, 1, RNG_MLP1, L.s_1, L.c1_1, L.c2_1);
+      linear_phase(p, sm, seq, act_par, EPI_MLP1, p.X1F + (size_t)dp_inst(c) * vecb, p.PSX1 + (size_t)dp_inst(c) * 16 * H * 2, H, 1, RNG_MLP1, L.s_1, L.c1_1,
+                   L.c2_1, dp_tag(c), p.HF + (size_t)dp_inst(c) * 4 * vecb, dp_tag(c));
       mark(4, s, l, 5);
       DP_TR(sm, 6);
-      grid_sync(sm, p.barrier, bar_target, G);
+      phase_sync(sm);
       mark(5, s, l, 6);
       DP_TR(sm, 7);
-      mlp2_phase(p, sm, seq, act_par, L);
+      {
+        const int cpq = (int)G >> 2, q2 = min((int)blockIdx.x / cpq, 3);
+        linear_phase(p, sm, seq, act_par, EPI_M2P, p.HF + ((size_t)dp_inst(c) * 4 + q2) * vecb, nullptr, 0, 0, RNG_MLP2, L.s_2, nullptr, nullptr, dp_tag(c),
+                     p.P2 + (size_t)dp_inst(c) * 4 * 16 * d, dp_tag(c));
+        mlp2_finalize(p, sm, L, c);
+      }
       mark(6, s, l, 7);
       DP_TR(sm, 8);
-      grid_sync(sm, p.barrier, bar_target, G);
+      phase_sync(sm);
       mark(7, s, l, 8);
       DP_TR(sm, 9);
       if (tid == 0 && sm.trace_on) { sm.trace_on = 0; sm.trace[1023] = (unsigned long long)sm.trace_n; }
     }
-    linear_phase(p, sm, seq, act_par, EPI_HEAD, p.XF, p.PSX, d >> 3, 0, RNG_HEAD, p.s_head, p.c1_head, p.c2_head);
+    linear_phase(p, sm, seq, act_par, EPI_HEAD, p.XF + (size_t)dp_inst(c - 1) * vecb, p.PSX + (size_t)dp_inst(c - 1) * 16 * (d >> 3) * 2, d >> 3, 0, RNG_HEAD,
+                 p.s_head, p.c1_head, p.c2_head, dp_tag(c - 1), nullptr, 0u);
     mark(8, s, p.n_layers, 9);
     grid_sync(sm, p.barrier, bar_target, G);
     mark(9, s, p.n_layers, 10);
@@ -1118,7 +1215,7 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(const 
         p.cam_idx[((size_t)b * p.ncam + j / p.hw) * p.hw + (j % p.hw)] = token;
         if (p.tokens_out != nullptr) p.tokens_out[(size_t)b * p.n_img + s] = token;
       }
-      if (s + 1 < p.step_end) embed_row(p, sm, b, s, token);
+      if (s + 1 < p.step_end) embed_row(p, sm, b, s, token, c - 1);
     }
     mark(10, s, p.n_layers, 11);
     grid_sync(sm, p.barrier, bar_target, G);
@@ -1194,8 +1291,9 @@ long long decode_packed_bytes(int n_rows, int d, int n_quarters) {
 
 void decode_workspace_sizes(int B, int d, int H, int vocab, long long* n_floats, long long* n_counters) {
   const long long vpad = (vocab + 7) / 8 * 8;
-  *n_floats = 16LL * d * 2 /*X, X1*/ + 16LL * 3 * d /*QKV*/ + 16LL * vpad /*LOGITS*/ + 16LL * (d / 8) * 2 + 16LL * H * 2 /*PSX, PSX1*/ +
-              16LL * d * 2 /*XF, X1F*/ + 4LL * 16 * d /*HF*/;
+  // every buffer that crosses CTAs inside a step exists twice (instance = running layer number & 1, see "tag sync")
+  *n_floats = 2 * (16LL * d * 2 /*X, X1*/ + 16LL * 3 * d /*QKV*/) + 16LL * vpad /*LOGITS*/ + 2 * (16LL * (d / 8) * 2 + 16LL * H * 2) /*PSX, PSX1*/ +
+              2 * (16LL * d * 2 /*XF, X1F*/ + 4LL * 16 * d /*HF*/) + 2 * 4LL * 16 * d /*P2*/;
   *n_counters = 64;
   (void)B;
 }
@@ -1216,16 +1314,19 @@ int launch_decode_persistent(DecodeParams p, float* ws, unsigned int* counters, 
   if (const char* e = getenv("BEVGEN_DP_TRACE_CTA")) p.trace_cta = atoi(e);
   if (const char* e = getenv("BEVGEN_DP_TRACE_STEP")) p.trace_step = atoi(e);      // timing experiments only (results are garbage): see tools/decode_debug.py
   float* f = ws;
-  p.X = f; f += 16 * d;
-  p.X1 = f; f += 16 * d;
-  p.QKV = f; f += 16 * 3 * d;
+  p.X = f; f += 2 * 16 * d;                                   // [2 instances][16][d]
+  p.X1 = f; f += 2 * 16 * d;
+  p.QKV = f; f += 2 * 16 * 3 * d;
   p.LOGITS = f; f += 16 * p.vpad;
-  p.PSX = f; f += 16 * (d / 8) * 2;
-  p.PSX1 = f; f += 16 * p.H * 2;
-  p.XF = reinterpret_cast<uint8_t*>(f); f += 16 * d;          // 16 x d x (2 + 2) bytes
-  p.X1F = reinterpret_cast<uint8_t*>(f); f += 16 * d;
-  p.HF = reinterpret_cast<uint8_t*>(f); f += 4 * 16 * d;
+  p.PSX = f; f += 2 * 16 * (d / 8) * 2;
+  p.PSX1 = f; f += 2 * 16 * p.H * 2;
+  p.XF = reinterpret_cast<uint8_t*>(f); f += 2 * 16 * d;      // [2] x 16 x d x (2 + 2) bytes
+  p.X1F = reinterpret_cast<uint8_t*>(f); f += 2 * 16 * d;
+  p.HF = reinterpret_cast<uint8_t*>(f); f += 2 * 4 * 16 * d;
+  p.P2 = f; f += 2 * 4 * 16 * d;                              // [2][4 K-quarters][16][d] partial sums of MLP2
   p.barrier = counters;
+  // all tags start at 0: the first generation written to every instance carries tag 1 (dp_tag), leftovers of an earlier launch must not pass
+  if (cudaMemsetAsync(ws, 0, sizeof(float) * (size_t)(f - ws), st) != cudaSuccess) return BEVGEN_ERR_CUDA;
   if (cudaMemsetAsync(counters, 0, sizeof(unsigned int) * 64, st) != cudaSuccess) return BEVGEN_ERR_CUDA;
   static bool configured = false;
   if (!configured) {

@@ -205,6 +205,7 @@ struct DecodeParams {
   // workspace (filled by the launcher)
   float *X, *X1, *QKV, *LOGITS, *PSX, *PSX1;
   uint8_t *XF, *X1F, *HF;          // activation vectors in mma A-fragment order (fp16 hi + lo)
+  float* P2;                       // MLP2 partial sums per K-quarter
   unsigned int* barrier;
   int trace_cta, trace_step;       // BEVGEN_DP_DBG & 64: thread 0 of this CTA records a clock trace of one layer of this step behind the profile rows
   int dbg;                         // timing experiments (BEVGEN_DP_DBG): 1 skip attention math, 2 skip linear MMAs, 4 skip activation fetches, 8 producer copies nothing

@@ -42,13 +42,14 @@ def _one_layer_case(layers=1, B=3):
     return cfg, sd, cam, bev, batch, eng, B
 
 
-def _ws_views(smp, cfg, B):
-    """The kernel's workspace layout (launch_decode_persistent): X, X1 [16][d], QKV [16][3d], LOGITS [16][vpad], ..."""
+def _ws_views(smp, cfg, B, c_last):
+    """The kernel's workspace layout (launch_decode_persistent): X, X1 [2][16][d], QKV [2][16][3d], LOGITS [16][vpad], ...  Everything that
+    crosses CTAs inside a step exists twice; layer number c of a launch (counted over its steps) writes instance c & 1."""
     d, ws = cfg.num_embed, smp._pk["ws"]
     o, out = 0, {}
     for name, n in (("X", 16 * d), ("X1", 16 * d), ("QKV", 16 * 3 * d)):
-        out[name] = ws[o:o + n]
-        o += n
+        out[name] = ws[o + (c_last & 1) * n:o + (c_last & 1) * n + n]
+        o += 2 * n
     vpad = (cfg.vocab_size + 7) // 8 * 8
     out["LOGITS"] = ws[o:o + 16 * vpad]
     return {k: v.view(16, -1) for k, v in out.items()}
@@ -66,7 +67,7 @@ def test_one_step_phase_by_phase(last_step):
     forced = cam.reshape(B, -1)[:, cfg.forward_shuffle_idx]
     toks, trace = smp.sample(bev, batch, forced_tokens=forced, trace_logits=True, steps=last_step + 1)
     torch.cuda.synchronize()
-    ws = _ws_views(smp, cfg, B)
+    ws = _ws_views(smp, cfg, B, c_last=last_step - 1)       # one layer per step, steps 1 .. last_step in the launch
     # the row the kernel processed last: sequence position nc + last_step - 1 (decode-order token last_step - 1, forced)
     nc = nc + last_step - 1
     x0 = eng.embed(smp.cam_idx, bev.cuda(), batch, sampling=True, row0=nc, nrows=1)[:, 0]
