@@ -730,7 +730,10 @@ __device__ __noinline__ void attention_phase(const DecodeParams& p, DpSmem& sm, 
     }
   }
   DP_TR(sm, 51);
-  if (tma_bias) { dp_mbar_wait(sm, &sm.bias_bar, bias_par & 1u, 7u, (unsigned)n); bias_par ^= 1u; }
+  if (tma_bias) {                        // one warp asks the mbarrier (see linear_phase), the barrier below tells the others
+    if (w == 0) dp_mbar_wait(sm, &sm.bias_bar, bias_par & 1u, 7u, (unsigned)n);
+    bias_par ^= 1u;
+  }
   DP_TR(sm, 52);
   bar_consumers();
   DP_TR(sm, 53);
@@ -867,6 +870,10 @@ __device__ __noinline__ void attention_phase(const DecodeParams& p, DpSmem& sm, 
   DP_TR(sm, 59);
   bar_consumers();
   DP_TR(sm, 60);
+  // The key / value appended in the prologue will be read by cp.async.bulk (async proxy) in the next step.  Here, not at the end of the
+  // phase: these stores completed long ago, the ones of the merge below would make the fence wait for their round trip.
+  fence_proxy_async_all();
+  DP_TR(sm, 62);
   fine(9);
   // ---- merge the 16 per-warp partials of each pair (fixed order), 2 channels per lane; the residual operands are requested first
   if (w < npairs) {
@@ -905,8 +912,6 @@ __device__ __noinline__ void attention_phase(const DecodeParams& p, DpSmem& sm, 
     if (lane == 0) *reinterpret_cast<float2*>(PSX1o + ((size_t)b * p.H + h) * 2) = make_float2(tag_f32(sv, tag), tag_f32(qv, tag));
   }
   DP_TR(sm, 61);
-  fence_proxy_async_all();               // the appended key / value will be read by cp.async.bulk (async proxy) in the next step
-  DP_TR(sm, 62);
   fine(6);
 }
 
