@@ -548,6 +548,13 @@ __device__ __noinline__ void linear_phase(const DecodeParams& p, DpSmem& sm, uns
   unsigned long long tf = p.profile != nullptr ? dp_globaltimer() : 0ull;
   auto fine = [&](int k) { if (tid == 0 && p.profile != nullptr && !sm.trace) { const unsigned long long now = dp_globaltimer(); sm.fine[k] += now - tf; tf = now; } };
   float rsS = 0.f, rsQ = 0.f;
+  // output element of a unit owned by this thread: element e -> lane e / 4, register e % 4 of the accumulator fragment -> (batch row, weight row);
+  // the epilogue constants of the first batch are requested before anything else (consumed after the MMAs)
+  const int ui = tid >> 7, e = tid & 127;
+  const int ln = e >> 2, j = e & 3;
+  const int b = (ln >> 2) + ((j & 2) ? 8 : 0), nrow = 2 * (ln & 3) + (j & 1);
+  float c1f = 0.f, c2f = 0.f;
+  if (epi != EPI_M2P && u0 + ui < u1 && b < p.B) { c1f = __ldg(c1 + (u0 + ui) * 8 + nrow); c2f = __ldg(c2 + (u0 + ui) * 8 + nrow); }
   DP_TR(sm, 12);
   const bool lnorm = epi != EPI_M2P;
   // (a CTA without units only needs the statistics when its attention phase will: LN1 of the pairs it owns)
@@ -569,16 +576,12 @@ __device__ __noinline__ void linear_phase(const DecodeParams& p, DpSmem& sm, uns
   DP_TR(sm, 15);
   bar_consumers();                          // the first batch of units has landed; act[] (reduction scratch) is free: the previous phase is behind a grid barrier
   DP_TR(sm, 16);
-  // output element of a unit owned by this thread: element e -> lane e / 4, register e % 4 of the accumulator fragment -> (batch row, weight row)
-  const int ui = tid >> 7, e = tid & 127;
-  const int ln = e >> 2, j = e & 3;
-  const int b = (ln >> 2) + ((j & 2) ? 8 : 0), nrow = 2 * (ln & 3) + (j & 1);
   for (int ub = u0; ub < u1; ub += DP_MAXU) {
     const int nb = min(DP_MAXU, u1 - ub);
     const bool has = ui < nb && b < p.B;
     const int row = (ub + ui) * 8 + nrow;
-    float c1v = 0.f, c2v = 0.f;
-    if (has && lnorm) { c1v = __ldg(c1 + row); c2v = __ldg(c2 + row); }
+    float c1v = c1f, c2v = c2f;
+    if (ub != u0 && has && lnorm) { c1v = __ldg(c1 + row); c2v = __ldg(c2 + row); }
     if (ub != u0) {                          // a further batch (more than DP_MAXU units per CTA: small grids only)
       if (w == 0) for (int k = 0; k < nb; ++k) ring_wait_full(sm, seq + (unsigned)k);
       bar_consumers();
@@ -880,8 +883,7 @@ __device__ __noinline__ void attention_phase(const DecodeParams& p, DpSmem& sm, 
     const int bh = bx + w * G, b = bh / H, h = bh - b * H;
     const int c0 = h * 64 + lane, c1 = c0 + 32;
     const size_t xi = (size_t)b * p.d;
-    const float xa = ld_tagged(sm, Xi + xi + c0, ptag, 12u), xb = ld_tagged(sm, Xi + xi + c1, ptag, 12u);
-    __syncwarp();
+    float xa = ldcg_f32(Xi + xi + c0), xb = ldcg_f32(Xi + xi + c1);      // both in flight; their tags are checked after the merge arithmetic
     const float ga = __ldg(L.ln1_g + c0), gb = __ldg(L.ln1_g + c1), ba = __ldg(L.ln1_b + c0), bb = __ldg(L.ln1_b + c1);
     const float* t = tab + (w * 16) * DP_PART;
     // lane i < 16 owns partial i: its weight exp(m_i - M) is computed once and broadcast
@@ -901,6 +903,11 @@ __device__ __noinline__ void attention_phase(const DecodeParams& p, DpSmem& sm, 
         o1 += t[ww * DP_PART + 4 + 32 + lane] * wgt;
       }
     }
+    if (((__float_as_uint(xa) ^ ptag) | (__float_as_uint(xb) ^ ptag)) & 1u) {
+      DpPoll pg;
+      do { poll_tick(sm, pg, 12u, (unsigned)bh); xa = ldcg_f32(Xi + xi + c0); xb = ldcg_f32(Xi + xi + c1); } while (((__float_as_uint(xa) ^ ptag) | (__float_as_uint(xb) ^ ptag)) & 1u);
+    }
+    __syncwarp();
     const float2 st = sm.rowstat[0][b];
     const float x0 = ((xa - st.x) * st.y * ga + ba) + o0 / Ls, x1 = ((xb - st.x) * st.y * gb + bb) + o1 / Ls;
     X1o[xi + c0] = tag_f32(x0, tag);
