@@ -51,7 +51,7 @@ constexpr int DP_MAXLB = DP_MAXL / 16;                  // layout blocks per row
 // upper part: the camera-bias row (requested right after the QKV phase, i.e. while the lower half is still the QKV reduction scratch)
 // and the layout row of every pair.
 constexpr int DP_A_QS = 0, DP_A_KN = DP_A_QS + DP_MAXBH * 64, DP_A_VN = DP_A_KN + DP_MAXBH * 64, DP_A_PW = DP_A_VN + DP_MAXBH * 64,
-              DP_A_TAB = DP_A_PW + 16 * 128, DP_A_LOW_END = DP_A_TAB + DP_MAXBH * 16 * DP_PART;
+              DP_A_TAB = DP_A_PW + 16 * 128, DP_A_MRG = DP_A_TAB + DP_MAXBH * 16 * DP_PART, DP_A_LOW_END = DP_A_MRG + DP_MAXBH * 3 * 64;
 constexpr int DP_A_BIAS = 8192, DP_A_LAY = DP_A_BIAS + DP_MAXL, DP_A_END = DP_A_LAY + DP_MAXBH * DP_MAXLB / 4;
 static_assert(DP_A_LOW_END <= DP_A_BIAS && DP_MAXU * 16 * 128 <= DP_A_BIAS, "scratch overlaps the prefetched camera-bias row");
 static_assert(DP_A_END * 4 <= DP_ACT_BYTES, "attention scratch does not fit the activation buffer");
@@ -151,6 +151,7 @@ __device__ __forceinline__ uint4 lds_u128(const void* p) {
   return v;
 }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 
 // Before a timeout trap: leave (code, CTA, step, layer, phase, a, b) in the caller's pinned host buffer so the failure can be located
 __device__ __noinline__ void dp_fail(const DpSmem& sm, unsigned int code, unsigned int a, unsigned int b) {
@@ -682,7 +683,8 @@ __device__ __noinline__ void mlp2_finalize(const DecodeParams& p, DpSmem& sm, co
 // shuffle joins the halves), half-warp online softmax, lane = (key mod 4, 8 channels) for P . V (16-byte loads of the value rows,
 // probabilities through a 128-byte per-warp scratch).  Blocks go round-robin over the four groups, every warp keeps a running
 // (max, sum, o[64]) per pair and leaves it in a table that one warp per pair merges in warp order.
-__device__ __noinline__ void attention_phase(const DecodeParams& p, DpSmem& sm, unsigned int& seq, unsigned int& bias_par, const DecodeLayer& L, int s, int c) {
+__device__ __noinline__ void attention_phase(const DecodeParams& p, DpSmem& sm, unsigned int& seq, unsigned int& bias_par, const DecodeLayer& L, int s, int c,
+                                            bool first_layer) {
   const int tid = opaque((int)threadIdx.x), w = tid >> 5, lane = tid & 31;
   const int d = opaque(p.d), H = opaque(p.H), BH = p.B * H, G = opaque((int)gridDim.x), bx = opaque((int)blockIdx.x);
   const int n = p.nc + s, r = n - 1, nblk = (n + 127) >> 7;
@@ -724,6 +726,14 @@ __device__ __noinline__ void attention_phase(const DecodeParams& p, DpSmem& sm, 
     }
   }
   for (int i = tid; i < npairs * 16; i += DP_CONSUMERS) { tab[i * DP_PART] = -INFINITY; tab[i * DP_PART + 1] = 0.f; }
+  // operands of the merge (previous residual row segment, ln1 gamma / beta of the head's channels): fetched now so that the merge does not
+  // wait for L2 / HBM; the residual keeps its tag bit and is checked there
+  float* mrg = fa + DP_A_MRG;                          // [MAXBH][3][64]
+  for (int i = DP_CONSUMERS - 1 - tid; i < npairs * 192; i += DP_CONSUMERS) {      // (from the last thread down: the first 384 threads fetch q / k / v)
+    const int k = i / 192, which = (i % 192) >> 6, c = i & 63;
+    const int bh = bx + k * G, b = bh / H, h = bh - b * H;
+    mrg[i] = which == 0 ? ldcg_f32(Xi + (size_t)b * d + h * 64 + c) : which == 1 ? __ldg(L.ln1_g + h * 64 + c) : __ldg(L.ln1_b + h * 64 + c);
+  }
   if (L.layout != nullptr) {
     const int nlb = (n + p.lay_blk - 1) / p.lay_blk;
     for (int i = tid; i < npairs * nlb; i += DP_CONSUMERS) {
@@ -733,8 +743,8 @@ __device__ __noinline__ void attention_phase(const DecodeParams& p, DpSmem& sm, 
     }
   }
   DP_TR(sm, 51);
-  if (tma_bias) {                        // one warp asks the mbarrier (see linear_phase), the barrier below tells the others
-    if (w == 0) dp_mbar_wait(sm, &sm.bias_bar, bias_par & 1u, 7u, (unsigned)n);
+  if (tma_bias && first_layer) {         // the row was requested at the start of the step and serves all its layers
+    if (w == 0) dp_mbar_wait(sm, &sm.bias_bar, bias_par & 1u, 7u, (unsigned)n);      // one warp asks the mbarrier (see linear_phase), the barrier below tells the others
     bias_par ^= 1u;
   }
   DP_TR(sm, 52);
@@ -875,7 +885,7 @@ __device__ __noinline__ void attention_phase(const DecodeParams& p, DpSmem& sm, 
   DP_TR(sm, 60);
   // The key / value appended in the prologue will be read by cp.async.bulk (async proxy) in the next step.  Here, not at the end of the
   // phase: these stores completed long ago, the ones of the merge below would make the fence wait for their round trip.
-  fence_proxy_async_all();
+  fence_proxy_async_global();
   DP_TR(sm, 62);
   fine(9);
   // ---- merge the 16 per-warp partials of each pair (fixed order), 2 channels per lane; the residual operands are requested first
@@ -883,8 +893,9 @@ __device__ __noinline__ void attention_phase(const DecodeParams& p, DpSmem& sm, 
     const int bh = bx + w * G, b = bh / H, h = bh - b * H;
     const int c0 = h * 64 + lane, c1 = c0 + 32;
     const size_t xi = (size_t)b * p.d;
-    float xa = ldcg_f32(Xi + xi + c0), xb = ldcg_f32(Xi + xi + c1);      // both in flight; their tags are checked after the merge arithmetic
-    const float ga = __ldg(L.ln1_g + c0), gb = __ldg(L.ln1_g + c1), ba = __ldg(L.ln1_b + c0), bb = __ldg(L.ln1_b + c1);
+    const float* mg = mrg + w * 192;
+    float xa = mg[lane], xb = mg[lane + 32];               // staged by the prologue; their tags are checked after the merge arithmetic
+    const float ga = mg[64 + lane], gb = mg[96 + lane], ba = mg[128 + lane], bb = mg[160 + lane];
     const float* t = tab + (w * 16) * DP_PART;
     // lane i < 16 owns partial i: its weight exp(m_i - M) is computed once and broadcast
     const float mi = (lane < 16) ? t[lane * DP_PART] : -INFINITY;
@@ -1166,32 +1177,40 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(const 
   const size_t vecb = (size_t)(d >> 6) * 4096;
   int c = 0;                               // running layer number of this launch: instance c & 1, tag dp_tag(c) of everything layer c writes
   for (int s = p.step_begin; s < p.step_end; ++s) {
+    if (tid == 0 && has_pairs && tma_bias) {
+      // camera-bias row of this step (the same for every layer) -> upper half of act[]: not part of any reduction / sampling scratch and only
+      // ever written by these copies; its readers of the previous step are behind the grid barriers.  Waited for in the first attention phase.
+      const int n = p.nc + s;
+      const uint32_t bytes = (uint32_t)((n + 3) & ~3) * 4u;
+      mbar_expect_tx(&sm.bias_bar, bytes);
+      dp_bulk_g2s(sm.act + DP_A_BIAS * 4, p.bias + (size_t)(n - 1) * p.bias_ld, bytes, &sm.bias_bar);
+    }
     for (int l = 0; l < p.n_layers; ++l, ++c) {
       const DecodeLayer& L = p.layers[l];
+      // (a copy of the layer block in shared memory measured 3 % slower; the global block only gets an L2 prefetch one layer ahead, it falls
+      // out of L2 between two token steps)
+      if (tid == DP_CONSUMERS - 32) {
+        const char* nl = reinterpret_cast<const char*>(p.layers + (l + 1 == p.n_layers ? 0 : l + 1));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(nl));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(nl + sizeof(DecodeLayer) - 4));
+      }
       if (tid == 0 && sm.trace != nullptr) sm.trace_on = (s == p.trace_step && l == p.n_layers / 4) ? 1 : 0;
       DP_TR(sm, 1);
       mark(11, s, l, 0);
       linear_phase(p, sm, seq, act_par, EPI_QKV, p.XF + (size_t)dp_inst(c - 1) * vecb, p.PSX + (size_t)dp_inst(c - 1) * 16 * (d >> 3) * 2, d >> 3, 0, RNG_QKV,
                    L.s_qkv, L.c1_qkv, L.c2_qkv, dp_tag(c - 1), p.QKV + (size_t)dp_inst(c) * 16 * 3 * d, dp_tag(c));
-      if (tid == 0 && has_pairs && tma_bias) {
-        // camera-bias row of this step -> upper half of act[] (not part of the QKV reduction scratch, only ever written by these copies);
-        // waited for in the attention phase
-        const int n = p.nc + s;
-        const uint32_t bytes = (uint32_t)((n + 3) & ~3) * 4u;
-        mbar_expect_tx(&sm.bias_bar, bytes);
-        dp_bulk_g2s(sm.act + DP_A_BIAS * 4, p.bias + (size_t)(n - 1) * p.bias_ld, bytes, &sm.bias_bar);
-      }
       mark(0, s, l, 1);
       DP_TR(sm, 2);
       phase_sync(sm);
       mark(1, s, l, 2);
       DP_TR(sm, 3);
-      attention_phase(p, sm, seq, bias_par, L, s, c);
+      attention_phase(p, sm, seq, bias_par, L, s, c, l == 0);
       mark(2, s, l, 3);
       DP_TR(sm, 4);
       phase_sync(sm);
       // this CTA's appends of (s, l) are done (it owns its pairs' cache rows): the producer may request the blocks of (s + 1, l)
-      if (tid == 0) { __threadfence_block(); sm.att_epoch = (unsigned)(s - p.step_begin) * (unsigned)p.n_layers + (unsigned)l + 1u; }
+      // (published by a thread that has no global stores of the merge in flight: the fence does not wait)
+      if (tid == DP_CONSUMERS - 1) { __threadfence_block(); sm.att_epoch = (unsigned)(s - p.step_begin) * (unsigned)p.n_layers + (unsigned)l + 1u; }
       mark(3, s, l, 4);
       DP_TR(sm, 5);
       linear_phase(p, sm, seq, act_par, EPI_MLP1, p.X1F + (size_t)dp_inst(c) * vecb, p.PSX1 + (size_t)dp_inst(c) * 16 * H * 2, H, 1, RNG_MLP1, L.s_1, L.c1_1,
