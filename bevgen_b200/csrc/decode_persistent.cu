@@ -6,9 +6,11 @@
 // data side is a BYTE STREAM per SM: every CTA owns a fixed, contiguous slab of each weight matrix (8-row units, packed CTA-major in mma
 // fragment order by bevgen_pack_decode_linear) and whole (scene, head) pairs of the KV cache; the producer walks that fixed sequence
 // with cp.async.bulk into a 5 x 32 KB shared-memory ring and runs AHEAD of the grid barriers (the bytes do not depend on the
-// activations).  Phases are separated by a grid-wide barrier (monotonic counter, release / acquire at gpu scope).  What the kernel's
-// time depends on is the LATENCY CHAIN of its 98 phases per token, not bandwidth (DESIGN.md "What bounds the decode kernel"); the
-// rules that came out of the clock traces (tools/decode_trace.py) and same-box A/B runs (tools/build_variant.sh):
+// activations).  The 96 layer phases of a step are NOT separated by grid barriers: everything that crosses CTAs is self-validating
+// ("tag sync", see the helpers below); grid-wide barriers (monotonic counter, release at gpu scope) only bracket the head / sampling /
+// embedding of a step.  What the kernel's time depends on is the LATENCY CHAIN of its 98 phases per token, not bandwidth (DESIGN.md
+// "What bounds the decode kernel"); the rules that came out of the clock traces (tools/decode_trace.py) and same-box A/B runs
+// (tools/build_variant.sh):
 //   - ONE warp per CTA (per block group in attention) asks an mbarrier, a barrier tells the others (16 warps on one mbarrier serialise);
 //   - as few CTA-wide barriers inside a phase as possible (each one re-exposes the slowest warp's L2 latency): two in a linear phase,
 //     none between MLP2's K-quarters, one 128-thread barrier per attention block;
@@ -20,7 +22,8 @@
 //     the row statistics come from per-unit partial sums the finalisers leave next to the vector (fixed order -> deterministic).
 //   * linears: mma.sync m16n8k16, A = the 16 batch rows (fp16 hi + lo), B = 8 weight rows per unit as fp16 + an e4m3 residual plane
 //     -> 3 bytes / weight at fp32-equivalent accuracy: x_hi*w16 + x_lo*w16 + x_hi*w8/S, fp32 accumulate; warp w = k-group w of every unit,
-//     one cross-warp reduction per phase.  MLP2: the CTA owns 8 output rows over all four K-quarters (no cross-CTA partial sums).
+//     one cross-warp reduction per phase.  MLP2 is split over K: a CTA works on one quarter of the hidden vector, the finaliser CTA of a
+//     row unit polls the four tagged partial sums (mlp2_finalize).
 //   * attention: a CTA owns whole (scene, head) pairs; a staged K^T (64 x 128) / V (128 x 64) fp16 block belongs to a group of four warps
 //     (32 keys each, CUDA cores, online softmax per warp), the per-warp partials of a pair are merged once; camera-bias row added BEFORE
 //     the 1/sqrt(d_head) scale (sparse_self_attention.py:155-168); the newest key is patched into the staged block.
@@ -212,6 +215,19 @@ __device__ __forceinline__ uint32_t e4m3x2_to_f16x2(uint16_t v) {
 // data fetch, no release fence / atomic / second round trip per phase.  Buffer reuse is safe without a barrier because every phase reads
 // what the whole grid produced in the phase before: a CTA that writes generation c + 2 of an instance has (transitively) seen every CTA
 // finish its reads of generation c.  Real grid barriers remain around the head / sampling / embedding of a step (3 per token).
+// Re-use, buffer by buffer (writer of generation c + 2 => every reader of generation c is done; "=>" follows what a CTA must have read):
+//   XF / X / PSX  (MLP2 finalisers -> QKV units, attention merge):  finaliser(c + 2) read P2(c + 2) => MLP2 units(c + 2) read HF(c + 2) =>
+//                 MLP1 units(c + 2) read all of X1F(c + 2) => every pair owner finished attention(c + 2), i.e. read its QKV(c + 2) => all QKV
+//                 units(c + 2) are written (every head has a pair) => their owners finished QKV(c + 1), the readers of XF(c);
+//   QKV           (QKV units -> pair owners):  QKV unit(c + 2) read all of XF(c + 1) => all finalisers(c + 1) done => ... all MLP1 units(c + 1)
+//                 read all of X1F(c + 1) => every pair owner finished attention(c + 1), hence attention(c);
+//   X1F / X1 / PSX1 (pair owners -> MLP1 units, finalisers):  pair owner at attention(c + 2) read QKV(c + 2) => (as above) all finalisers
+//                 (c + 1) and all MLP1 units(c + 1) are done, hence MLP1(c) and finalise(c);
+//   HF            (MLP1 units -> MLP2 units):  MLP1 unit(c + 2) read all of X1F(c + 2) => pair owners read QKV(c + 2) => QKV units read XF(c + 1)
+//                 => finalisers(c + 1) read P2(c + 1) => every MLP2 unit owner finished MLP2(c + 1), hence MLP2(c);
+//   P2            (MLP2 units -> finalisers):  MLP2 unit(c + 2) read HF(c + 2) => ... => QKV units read all of XF(c + 1) => all finalisers
+//                 (c + 1), hence finalise(c).
+// A CTA that owns nothing in a phase reads nothing in it (linear_phase returns before its loads), so it cannot lag behind as a reader.
 __device__ __forceinline__ int dp_inst(int c) { return c & 1; }
 __device__ __forceinline__ unsigned int dp_tag(int c) { return (unsigned int)(((c >> 1) & 1) ^ 1); }
 __device__ __forceinline__ float tag_f32(float v, unsigned int tag) { return __uint_as_float((__float_as_uint(v) & ~1u) | tag); }
