@@ -247,7 +247,7 @@ def self_check(model, batch_dev, out, rank):
 
 
 # ------------------------------------------------------------------------------------------------ main
-NCU_DECODE_TRAFFIC = 3845356438528 + 49531383040      # bytes per launch of the persistent decode kernel (ncu, see roofline.traffic_source)
+NCU_DECODE_TRAFFIC = 3842125670656 + 106683657984     # bytes per launch of the persistent decode kernel (ncu, see roofline.traffic_source)
 
 
 def main():
@@ -388,8 +388,8 @@ def main():
                      "bytes_in_the_shipped_format": packed, "achieved_in_shipped_format_GBps": packed / (dec_ms / 1e3) / 1e9,
                      "traffic": smp.ncu_traffic_bytes if smp.ncu_traffic_bytes is not None else (NCU_DECODE_TRAFFIC if smp.persistent else None),
                      "traffic_source": smp.ncu_traffic_source if smp.ncu_traffic_source is not None else
-                     ("profiles/r02_decode_full_launch_ncu.csv: dram__bytes_read.sum + dram__bytes_write.sum of ONE decode_persistent_kernel launch "
-                      "(1535 token steps, 16 scenes, 24 layers) = 3.845 TB + 0.050 TB, against 3.869 TB in the shipped format" if smp.persistent else None)},
+                     ("profiles/r03_decode_full_launch_ncu.csv: dram__bytes_read.sum + dram__bytes_write.sum of ONE decode_persistent_kernel launch "
+                      "(1535 token steps, 16 scenes, 24 layers) = 3.842 TB + 0.107 TB, against 3.869 TB in the shipped format" if smp.persistent else None)},
     }
     if not args.no_extras and world == 1:
         from tools import bench_extras
