@@ -196,14 +196,11 @@ def camera_bias_prior(num_cams, lat_h, lat_w, bev_h, bev_w, num_pad, window_len,
     return full
 
 
-def block_layouts(num_heads, block, density, num_img, num_cond, num_pad, window_len, fwd, causal_order, prob_img):
-    """Per-head block layout (heads, L/block, L/block) int64 (mask_generator.py:192-228).
-
-    static = maxpool_block(window ∪ cond columns); sampled = multinomial(avgpool_block(prob with 0.5 on
-    cond columns), n) without replacement, restricted to blocks with non-zero prior.  At density 1.0
-    every block with non-zero prior is drawn, so the result does not depend on the RNG.
-    `prob_img` is the (img,img) prior *before* cond padding (already permuted/masked/clamped).
-    """
+def layout_components(block, num_img, num_cond, num_pad, window_len, fwd, causal_order, prob_img):
+    """The intermediates of mask_generator.outward_pattern (:192-214) that the per-head layouts are drawn from:
+    (static block layout (nb, nb) bool = maxpool_block(window U cond columns), block prior (nb, nb) float32 =
+    avgpool_block(padded prior), padded prior (L, L) float64 with 0.5 on the cond columns).
+    `prob_img` is the (img,img) prior *before* cond padding (already permuted/masked/clamped)."""
     L = num_cond + num_img + num_pad
     nb = L // block
     _, window = image_masks(num_img, window_len, fwd, causal_order)
@@ -214,6 +211,18 @@ def block_layouts(num_heads, block, density, num_img, num_cond, num_pad, window_
     static_l = static.reshape(nb, block, nb, block).any(axis=(1, 3))
     pfull = with_cond(prob_img, num_cond, num_pad, 0.5, np.float64)
     prob_l = torch.nn.functional.avg_pool2d(torch.from_numpy(pfull)[None].to(torch.float), block, block)[0]
+    return static_l, prob_l, pfull
+
+
+def block_layouts(num_heads, block, density, num_img, num_cond, num_pad, window_len, fwd, causal_order, prob_img):
+    """Per-head block layout (heads, L/block, L/block) int64 (mask_generator.py:192-228).
+
+    static = maxpool_block(window ∪ cond columns); sampled = multinomial(avgpool_block(prob with 0.5 on
+    cond columns), n) without replacement, restricted to blocks with non-zero prior.  At density 1.0
+    every block with non-zero prior is drawn, so the result does not depend on the RNG.
+    """
+    static_l, prob_l, _ = layout_components(block, num_img, num_cond, num_pad, window_len, fwd, causal_order, prob_img)
+    nb = static_l.shape[0]
     n_draw = int((nb * nb) * density - int(static_l.sum()))
     nonzero = (prob_l > 0).numpy()
     heads = []

@@ -62,6 +62,29 @@ def golden_gptconfig():
         print("gptconfig", name, L)
 
 
+def golden_outward_pattern():
+    """mask_generator.outward_pattern (:131-214) itself: the intermediate tuple (allowed pattern, static block layout, block prior, padded
+    prior) that multi_outward_pattern draws the per-head layouts from."""
+    m = ref_import.stage2()
+    from multi_view_generation.modules.transformer import mask_generator as mg
+    for name in ("nusc6_16x16", "nusc6_16x16_noncausal", "nusc6_7x9"):
+        torch.manual_seed(0)
+        cfg = m.GPTConfig(**CONFIG_CASES[name])
+        allowed, static_layout, prob_layout, prob_matrix = mg.outward_pattern(cfg)
+        L = cfg.gpt_block_size
+        rows = np.unique(np.concatenate([np.arange(0, L, 97), [0, 255, 256, 257, L - 1]])).astype(np.int64)
+        rows = rows[rows < L]
+        np.savez_compressed(
+            OUT / f"outward_{name}.npz",
+            allowed_bits=np.packbits(allowed[0].numpy().astype(bool)), allowed_shape=np.array(allowed.shape),
+            allowed_dtype=str(allowed.dtype), static_bits=np.packbits(static_layout.numpy().astype(bool)),
+            static_shape=np.array(static_layout.shape), static_dtype=str(static_layout.dtype),
+            prob_layout=prob_layout.numpy(), prob_layout_dtype=str(prob_layout.dtype),
+            prob_rows=rows, prob_values=prob_matrix[rows].numpy(), prob_sum=np.float64(prob_matrix.double().sum().item()),
+            prob_dtype=str(prob_matrix.dtype), bias_sum=np.float64(mg.outward_pattern(cfg, return_camera_bias_matrix=True).double().sum().item()))
+        print("outward", name, tuple(static_layout.shape), static_layout.dtype, prob_layout.dtype, prob_matrix.dtype, allowed.dtype)
+
+
 def golden_vq():
     _, q = ref_import.stage1()
     for cb in ("normal", "default"):
@@ -356,5 +379,7 @@ if __name__ == "__main__":
         golden_vqgan_config2()
     if "gpt_full" in which:
         golden_gpt_full()
+    if "outward" in which:
+        golden_outward_pattern()
     if "gpt_variants" in which:
         golden_gpt_variants()

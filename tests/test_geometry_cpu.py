@@ -30,6 +30,32 @@ def test_gptconfig_matches_reference(name, golden_dir):
     assert cfg.layout_covers_mask(layouts)        # density=1.0: the block layout never removes an allowed position
 
 
+@pytest.mark.parametrize("name", ["nusc6_16x16", "nusc6_16x16_noncausal", "nusc6_7x9"])
+def test_outward_pattern_matches_reference(name, golden_dir):
+    """mask_generator.outward_pattern under the reference's import path: the intermediate tuple (allowed pattern, static block layout,
+    block prior, padded prior) against the reference's own function (goldens minted by oracle/make_golden.py outward), dtypes included."""
+    from multi_view_generation.modules.transformer import mask_generator as mg
+    g = np.load(golden_dir / f"outward_{name}.npz")
+    cfg = GPTConfig(**CONFIG_CASES[name])
+    allowed, static_layout, prob_layout, prob_matrix = mg.outward_pattern(cfg)
+    assert (str(allowed.dtype), str(static_layout.dtype), str(prob_layout.dtype), str(prob_matrix.dtype)) == (
+        str(g["allowed_dtype"]), str(g["static_dtype"]), str(g["prob_layout_dtype"]), str(g["prob_dtype"]))
+    assert tuple(allowed.shape) == tuple(g["allowed_shape"]) and tuple(static_layout.shape) == tuple(g["static_shape"])
+    L = cfg.gpt_block_size
+    ref_allowed = np.unpackbits(g["allowed_bits"])[: L * L].reshape(L, L).astype(bool)
+    for h in (0, cfg.num_heads - 1):
+        assert np.array_equal(allowed[h].numpy().astype(bool), ref_allowed)
+    nb = static_layout.shape[0]
+    assert np.array_equal(static_layout.numpy().astype(bool), np.unpackbits(g["static_bits"])[: nb * nb].reshape(nb, nb).astype(bool))
+    np.testing.assert_allclose(prob_layout.numpy(), g["prob_layout"], rtol=0, atol=1e-7)
+    np.testing.assert_allclose(prob_matrix[g["prob_rows"]].numpy(), g["prob_values"], rtol=0, atol=1e-12)
+    assert abs(prob_matrix.sum().item() - float(g["prob_sum"])) < 1e-6
+    bias = mg.outward_pattern(cfg, return_camera_bias_matrix=True)
+    assert bias.dtype == torch.float64 and abs(bias.sum().item() - float(g["bias_sum"])) < 1e-6
+    layouts, allowed2 = mg.multi_outward_pattern(cfg)
+    assert torch.equal(allowed2, allowed) and layouts.dtype == torch.int64
+
+
 def test_mask_closed_form():
     """allowed(i,j) = (j < n_cond) or (i >= n_cond and j <= i) — the property the KV cache rests on."""
     cfg = GPTConfig(**CONFIG_CASES["nusc6_16x16"])
