@@ -327,7 +327,9 @@ BEVGEN_API int bevgen_dec_advance(int* step_ptr, void* stream);
  * ONE launch runs decode steps [step_begin, step_end) of Net2NetTransformer.sample (cond_transformer_multi_view.py:154-227) for up to
  * 16 scenes: per step all transformer blocks (mingpt_sparse.py:240-253 with the single-row attention of sparse_self_attention.py:153-176
  * over the fp16 KV cache), ln_f + head (:385-391), the top-k / softmax / multinomial tail (:200-219) and the embedding of the drawn token
- * (:332-350).  One CTA per SM; weights stream once per step from the packed format below; phases are separated by grid barriers.  The
+ * (:332-350).  One CTA per SM; weights stream once per step from the packed format below; the layer phases of a step synchronise through
+ * generation tags in the data itself (every value that crosses CTAs carries one in its last mantissa bit, the workspace holds every such
+ * buffer twice), grid barriers only bracket the head / sampling / embedding of a step.  The
  * caches must have been prefilled (bevgen_kv_store) and token step_begin - 1 must be in cam_idx.  kv caches are fp16. */
 typedef struct bevgen_decode_layer {
   const void* w_qkv;                 /* bevgen_pack_decode_linear of [3d][d] (q | k | v rows), columns pre-multiplied by ln1.weight */
@@ -365,9 +367,9 @@ typedef struct bevgen_decode_args {
   long long* tokens_out;             /* [batch][n_img] or NULL */
   float* logits_trace;               /* [n_img][batch][vocab] or NULL */
   int layout_block, layout_ld;
-  float* workspace;                  /* bevgen_decode_workspace(...) floats */
+  float* workspace;                  /* bevgen_decode_workspace(...) floats (zeroed by the call: all generation tags start at 0) */
   unsigned int* counters;            /* bevgen_decode_workspace(...) uint32 (zeroed by the call) */
-  unsigned int* debug;               /* optional pinned HOST buffer of 8 zeroed uint32: a barrier / ring time-out (4 s) leaves (code, CTA, step, layer, phase, ...) here before trapping */
+  unsigned int* debug;               /* optional pinned HOST buffer of 8 zeroed uint32: a barrier / ring / tag-poll time-out (4 s) leaves (code, CTA, step, layer, phase, ...) here before trapping */
   unsigned long long* profile;       /* optional device buffer [sm_count][32]: ns per phase body / grid barrier, summed over the launch */
 } bevgen_decode_args;
 
