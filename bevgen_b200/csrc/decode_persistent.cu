@@ -483,6 +483,55 @@ __device__ __forceinline__ void load_afrag_tagged(const DpSmem& sm, const uint8_
 // ------------------------------------------------------------------------------------------------ linear phase (consumers)
 enum { EPI_QKV = 0, EPI_MLP1 = 1, EPI_M2P = 2, EPI_HEAD = 3 };      // EPI_M2P: a K-quarter of MLP2 -> raw partial sums (no LayerNorm, no bias)
 
+// Inputs of a linear phase in ONE round trip: the warp's k-group of the activation vector (-> A registers, see load_afrag_tagged) and the
+// LayerNorm partial sums of batch row w (warp w = row w, see row_stats_load); all twelve loads are issued before the first tag is
+// looked at, whatever is still of the old generation is asked for again.
+__device__ __forceinline__ void load_inputs_tagged(const DecodeParams& p, const DpSmem& sm, const float* __restrict__ ps, int nparts, bool do_stats,
+                                                   const uint8_t* __restrict__ vec, bool do_frag, int w, int lane, unsigned int tag, uint32_t (&ahi)[4][4],
+                                                   uint32_t (&alo)[4][4], float& S, float& Q) {
+  const uint4* src = reinterpret_cast<const uint4*>(vec + (size_t)w * 4096 + lane * 16);
+  const uint32_t tm = tag ? 0x00010001u : 0u;
+  const int g = lane >> 2;
+  const uint32_t m0 = (g < p.B) ? 0x00010001u : 0u, m1 = (g + 8 < p.B) ? 0x00010001u : 0u;      // registers 0, 2: row g | 1, 3: row g + 8
+  bool need_s = do_stats && w < p.B, need_f = do_frag;
+  float2 v[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) v[j] = make_float2(0.f, 0.f);
+  DpPoll pg;
+  for (;;) {
+    if (need_s) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int i = lane + 32 * j;
+        if (i < nparts) v[j] = ldcg_f32x2(reinterpret_cast<const float2*>(ps) + (size_t)w * nparts + i);
+      }
+    }
+    uint32_t bad_f = 0u;
+    if (need_f) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint4 h4 = ldcg_u128(src + j * 32), l4 = ldcg_u128(src + 128 + j * 32);
+        ahi[j][0] = h4.x; ahi[j][1] = h4.y; ahi[j][2] = h4.z; ahi[j][3] = h4.w;
+        alo[j][0] = l4.x; alo[j][1] = l4.y; alo[j][2] = l4.z; alo[j][3] = l4.w;
+        bad_f |= (((h4.x ^ tm) | (h4.z ^ tm) | (l4.x ^ tm) | (l4.z ^ tm)) & m0) | (((h4.y ^ tm) | (h4.w ^ tm) | (l4.y ^ tm) | (l4.w ^ tm)) & m1);
+      }
+    }
+    unsigned int bad_s = 0u;
+    if (need_s) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (lane + 32 * j < nparts) bad_s |= ((__float_as_uint(v[j].x) ^ tag) | (__float_as_uint(v[j].y) ^ tag)) & 1u;
+    }
+    need_s = need_s && bad_s != 0u;
+    need_f = need_f && bad_f != 0u;
+    if (!need_s && !need_f) break;
+    poll_tick(sm, pg, 8u, (unsigned)w);
+  }
+  __syncwarp();
+  S = (v[0].x + v[1].x) + (v[2].x + v[3].x);
+  Q = (v[0].y + v[1].y) + (v[2].y + v[3].y);
+}
+
 // LayerNorm statistics of the 16 rows from the finalisers' partial sums ps[row][part][2] = (sum, sum of squares): warp w = row w.
 // Two halves so that the global loads (issued at the start of a phase) are in flight while the activation vector arrives and the MMAs run.
 __device__ __forceinline__ void row_stats_load(const DecodeParams& p, const DpSmem& sm, const float* __restrict__ ps, int nparts, unsigned int tag, float& S,
@@ -576,13 +625,13 @@ __device__ __noinline__ void linear_phase(const DecodeParams& p, DpSmem& sm, uns
   const bool lnorm = epi != EPI_M2P;
   // (a CTA without units only needs the statistics when its attention phase will: LN1 of the pairs it owns)
   if (u1 == u0 && !(lnorm && which == 0 && (int)blockIdx.x < p.B * p.H)) return;
-  if (lnorm) row_stats_load(p, sm, stats, nparts, rtag, rsS, rsQ);          // consumed after the MMAs
+  // Every warp reads ITS k-group of the activation vector straight from L2 into the A registers (fragment order: 8 coalesced 16-byte
+  // loads per lane; .cg: the vector was written by other SMs in the previous phase) - no staging buffer, no barrier for it.  The
+  // statistics' partial sums (consumed after the MMAs) and the fragments are requested TOGETHER: one L2 round trip, not two.
+  uint32_t ahi[4][4], alo[4][4];
+  load_inputs_tagged(p, sm, stats, nparts, lnorm, frag_src, u1 > u0 && w < KG, w, lane, rtag, ahi, alo, rsS, rsQ);
   DP_TR(sm, 13);
   if (u1 == u0) { row_stats_finish(p, sm, which, rsS, rsQ); return; }
-  // Every warp reads ITS k-group of the activation vector straight from L2 into the A registers (fragment order: 8 coalesced 16-byte
-  // loads per lane; .cg: the vector was written by other SMs in the previous phase) - no staging buffer, no barrier for it.
-  uint32_t ahi[4][4], alo[4][4];
-  if (w < KG) load_afrag_tagged(sm, frag_src, w, lane, p.B, rtag, ahi, alo);
   // Only warp 0 touches the mbarriers (16 warps asking the same barrier serialise in the SM's sync unit: ~1500 cycles per wait in the
   // trace of tools/decode_trace.py); the others learn through the CTA barrier.  The units were requested phases ago, so warp 0's
   // waits for them normally return at once.
