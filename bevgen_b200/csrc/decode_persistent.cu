@@ -456,36 +456,13 @@ __device__ __forceinline__ void store_frag(uint8_t* __restrict__ base, int b, in
   *reinterpret_cast<unsigned short*>(base + off) = hb;
   *reinterpret_cast<unsigned short*>(base + off + 2048) = lb;
 }
-// Warp w's k-group of an activation vector (fragment order) straight from L2 into the A registers, repeated until every half of the rows
-// that exist (b < B) carries `tag`: 8 coalesced 16-byte loads per lane.
-__device__ __forceinline__ void load_afrag_tagged(const DpSmem& sm, const uint8_t* __restrict__ vec, int w, int lane, int B, unsigned int tag,
-                                                  uint32_t (&ahi)[4][4], uint32_t (&alo)[4][4]) {
-  const uint4* src = reinterpret_cast<const uint4*>(vec + (size_t)w * 4096 + lane * 16);
-  const uint32_t tm = tag ? 0x00010001u : 0u;
-  const int g = lane >> 2;
-  const uint32_t m0 = (g < B) ? 0x00010001u : 0u, m1 = (g + 8 < B) ? 0x00010001u : 0u;      // registers 0, 2: row g | 1, 3: row g + 8
-  DpPoll pg;
-  for (;;) {
-    uint32_t bad = 0u;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const uint4 h4 = ldcg_u128(src + j * 32), l4 = ldcg_u128(src + 128 + j * 32);
-      ahi[j][0] = h4.x; ahi[j][1] = h4.y; ahi[j][2] = h4.z; ahi[j][3] = h4.w;
-      alo[j][0] = l4.x; alo[j][1] = l4.y; alo[j][2] = l4.z; alo[j][3] = l4.w;
-      bad |= (((h4.x ^ tm) | (h4.z ^ tm) | (l4.x ^ tm) | (l4.z ^ tm)) & m0) | (((h4.y ^ tm) | (h4.w ^ tm) | (l4.y ^ tm) | (l4.w ^ tm)) & m1);
-    }
-    if (bad == 0u) break;
-    poll_tick(sm, pg, 8u, (unsigned)w);
-  }
-  __syncwarp();
-}
-
 // ------------------------------------------------------------------------------------------------ linear phase (consumers)
 enum { EPI_QKV = 0, EPI_MLP1 = 1, EPI_M2P = 2, EPI_HEAD = 3 };      // EPI_M2P: a K-quarter of MLP2 -> raw partial sums (no LayerNorm, no bias)
 
-// Inputs of a linear phase in ONE round trip: the warp's k-group of the activation vector (-> A registers, see load_afrag_tagged) and the
-// LayerNorm partial sums of batch row w (warp w = row w, see row_stats_load); all twelve loads are issued before the first tag is
-// looked at, whatever is still of the old generation is asked for again.
+// Inputs of a linear phase in ONE round trip: the warp's k-group of the activation vector (fragment order, 8 coalesced 16-byte loads per lane
+// straight into the A registers; every half of the rows that exist must carry `tag`) and the LayerNorm partial sums ps[row][part][2] of
+// batch row w (warp w = row w; nparts <= 128: four loads per lane).  All twelve loads are issued before the first tag is looked at,
+// whatever is still of the old generation is asked for again.
 __device__ __forceinline__ void load_inputs_tagged(const DecodeParams& p, const DpSmem& sm, const float* __restrict__ ps, int nparts, bool do_stats,
                                                    const uint8_t* __restrict__ vec, bool do_frag, int w, int lane, unsigned int tag, uint32_t (&ahi)[4][4],
                                                    uint32_t (&alo)[4][4], float& S, float& Q) {
@@ -534,30 +511,6 @@ __device__ __forceinline__ void load_inputs_tagged(const DecodeParams& p, const 
 
 // LayerNorm statistics of the 16 rows from the finalisers' partial sums ps[row][part][2] = (sum, sum of squares): warp w = row w.
 // Two halves so that the global loads (issued at the start of a phase) are in flight while the activation vector arrives and the MMAs run.
-__device__ __forceinline__ void row_stats_load(const DecodeParams& p, const DpSmem& sm, const float* __restrict__ ps, int nparts, unsigned int tag, float& S,
-                                               float& Q) {
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float2 v[4];                              // nparts <= 128: four independent loads per lane, one L2 round trip (repeated while a tag is old)
-  DpPoll pg;
-  for (;;) {
-    unsigned int bad = 0u;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int i = lane + 32 * j;
-      if (w < p.B && i < nparts) {
-        v[j] = ldcg_f32x2(reinterpret_cast<const float2*>(ps) + (size_t)w * nparts + i);
-        bad |= ((__float_as_uint(v[j].x) ^ tag) | (__float_as_uint(v[j].y) ^ tag)) & 1u;
-      } else {
-        v[j] = make_float2(0.f, 0.f);
-      }
-    }
-    if (bad == 0u) break;
-    poll_tick(sm, pg, 9u, (unsigned)w);
-  }
-  __syncwarp();
-  S = (v[0].x + v[1].x) + (v[2].x + v[3].x);
-  Q = (v[0].y + v[1].y) + (v[2].y + v[3].y);
-}
 __device__ __forceinline__ void row_stats_finish(const DecodeParams& p, DpSmem& sm, int which, float S, float Q) {
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int o = 16; o; o >>= 1) { S += __shfl_xor_sync(0xffffffffu, S, o); Q += __shfl_xor_sync(0xffffffffu, Q, o); }
@@ -777,6 +730,18 @@ __device__ __noinline__ void attention_phase(const DecodeParams& p, DpSmem& sm, 
   // ---- prologue: q / newest key / newest value of every pair (the latter two also appended to the cache), table reset, layout rows
   if (!tma_bias)
     for (int j = tid; j < n; j += DP_CONSUMERS) biasrow[j] = p.bias ? __ldg(p.bias + (size_t)r * p.bias_ld + j) : 0.f;
+  // operands of the merge (previous residual row segment, ln1 gamma / beta of the head's channels): fetched now so that the merge does not
+  // wait for L2 / HBM; the residual keeps its tag bit and is checked there.  Requested BEFORE the (polled) q / k / v loads so that both
+  // are in flight together; from the last thread down, the first 384 threads fetch q / k / v.
+  float* mrg = fa + DP_A_MRG;                          // [MAXBH][3][64]
+  auto merge_operand = [&](int i) {
+    const int k = i / 192, which = (i % 192) >> 6, c = i & 63;
+    const int bh = bx + k * G, b = bh / H, h = bh - b * H;
+    return which == 0 ? ldcg_f32(Xi + (size_t)b * d + h * 64 + c) : which == 1 ? __ldg(L.ln1_g + h * 64 + c) : __ldg(L.ln1_b + h * 64 + c);
+  };
+  const int mi0 = DP_CONSUMERS - 1 - tid;
+  float mv0 = 0.f;
+  if (mi0 < npairs * 192) mv0 = merge_operand(mi0);
   for (int i = tid; i < npairs * 192; i += DP_CONSUMERS) {
     const int k = i / 192, which = (i % 192) >> 6, c = i & 63;
     const int bh = bx + k * G, b = bh / H, h = bh - b * H;
@@ -791,14 +756,8 @@ __device__ __noinline__ void attention_phase(const DecodeParams& p, DpSmem& sm, 
     }
   }
   for (int i = tid; i < npairs * 16; i += DP_CONSUMERS) { tab[i * DP_PART] = -INFINITY; tab[i * DP_PART + 1] = 0.f; }
-  // operands of the merge (previous residual row segment, ln1 gamma / beta of the head's channels): fetched now so that the merge does not
-  // wait for L2 / HBM; the residual keeps its tag bit and is checked there
-  float* mrg = fa + DP_A_MRG;                          // [MAXBH][3][64]
-  for (int i = DP_CONSUMERS - 1 - tid; i < npairs * 192; i += DP_CONSUMERS) {      // (from the last thread down: the first 384 threads fetch q / k / v)
-    const int k = i / 192, which = (i % 192) >> 6, c = i & 63;
-    const int bh = bx + k * G, b = bh / H, h = bh - b * H;
-    mrg[i] = which == 0 ? ldcg_f32(Xi + (size_t)b * d + h * 64 + c) : which == 1 ? __ldg(L.ln1_g + h * 64 + c) : __ldg(L.ln1_b + h * 64 + c);
-  }
+  if (mi0 < npairs * 192) mrg[mi0] = mv0;
+  for (int i = mi0 + DP_CONSUMERS; i < npairs * 192; i += DP_CONSUMERS) mrg[i] = merge_operand(i);
   if (L.layout != nullptr) {
     const int nlb = (n + p.lay_blk - 1) / p.lay_blk;
     for (int i = tid; i < npairs * nlb; i += DP_CONSUMERS) {
