@@ -5,7 +5,7 @@
 // One CTA per SM (148), 16 consumer warps + 1 producer thread.  Per step every weight and the whole KV cache cross HBM once, so the
 // data side is a BYTE STREAM per SM: every CTA owns a fixed, contiguous slab of each weight matrix (8-row units, packed CTA-major in mma
 // fragment order by bevgen_pack_decode_linear) and whole (scene, head) pairs of the KV cache; the producer walks that fixed sequence
-// with cp.async.bulk into a 5 x 32 KB shared-memory ring and runs AHEAD of the grid barriers (the bytes do not depend on the
+// with cp.async.bulk into a 5 x 32 KB shared-memory ring and runs AHEAD of the phases (the bytes do not depend on the
 // activations).  The 96 layer phases of a step are NOT separated by grid barriers: everything that crosses CTAs is self-validating
 // ("tag sync", see the helpers below); grid-wide barriers (monotonic counter, release at gpu scope) only bracket the head / sampling /
 // embedding of a step.  What the kernel's time depends on is the LATENCY CHAIN of its 98 phases per token, not bandwidth (DESIGN.md
@@ -75,9 +75,9 @@ struct DpSmem {
   int found;
   int rng[4][2];                                        // this CTA's unit range of the QKV / MLP1 / MLP2-row / head linears (part_range, computed once)
   volatile unsigned int rel[DP_NSLOT];                  // unit number last released from each slot (see ring_wait_prev_released)
-  volatile unsigned int att_epoch;                      // attention phases whose closing grid barrier the consumers have passed (producer gate)
+  volatile unsigned int att_epoch;                      // attention phases (step-major count) whose appends this CTA's consumers have finished (producer gate)
   unsigned int where[4];                                // step, layer, phase of the consumers (diagnostics)
-  unsigned long long prof[12];                          // thread 0: ns per phase body / grid barrier (see GPTSampler.PROFILE_SLOTS)
+  unsigned long long prof[12];                          // thread 0: ns per phase body / phase boundary (see GPTSampler.PROFILE_SLOTS)
   unsigned long long fine[20];                          // thread 0: ns in activation fetch | linear ring wait | linear mma + epilogue | attention prologue | attention ring wait (warp 0) | attention units | attention merge | MLP2
   unsigned int* debug;                                  // optional pinned host buffer: filled before a timeout trap
   unsigned long long* trace;                            // optional event trace of thread 0 (one layer): (id << 48 | clock) entries
@@ -593,7 +593,7 @@ __device__ __noinline__ void linear_phase(const DecodeParams& p, DpSmem& sm, uns
     for (int k = 0; k < nb0; ++k) ring_wait_full(sm, seq + (unsigned)k);
   }
   DP_TR(sm, 15);
-  bar_consumers();                          // the first batch of units has landed; act[] (reduction scratch) is free: the previous phase is behind a grid barrier
+  bar_consumers();                          // the first batch of units has landed; act[] (reduction scratch) is free: the previous phase's readers are behind this or an earlier CTA barrier
   DP_TR(sm, 16);
   for (int ub = u0; ub < u1; ub += DP_MAXU) {
     const int nb = min(DP_MAXU, u1 - ub);

@@ -14,13 +14,13 @@ from bevgen_b200.gpt_engine import GPTEngine
 from oracle import synth
 from tests.cases import GPT_FULL, gpt_sizes
 
-NAMES = {1: "layer start", 2: "qkv done", 3: "grid barrier done", 4: "attention done", 5: "grid barrier done", 6: "mlp1 done", 7: "grid barrier done", 8: "mlp2 done", 9: "grid barrier done",
-         10: "lin: enter", 11: "lin: part_range", 12: "lin: act TMA issued", 13: "lin: stats loads issued", 14: "lin: act landed", 15: "lin: fragments loaded", 16: "lin: barrier A",
+NAMES = {1: "layer start", 2: "qkv done", 3: "phase boundary done", 4: "attention done", 5: "phase boundary done", 6: "mlp1 done", 7: "phase boundary done", 8: "mlp2 (partials + finalise) done", 9: "phase boundary done",
+         10: "lin: enter", 11: "lin: part_range", 12: "lin: act TMA issued", 13: "lin: stats + fragments loaded (tags valid)", 14: "lin: act landed", 15: "lin: fragments loaded", 16: "lin: barrier A",
          17: "lin: unit landed", 18: "lin: unit mma + sts", 19: "lin: stats finished", 20: "lin: barrier B", 21: "lin: epilogue",
          30: "mlp2: enter", 31: "mlp2: act quarter landed", 32: "mlp2: frags + barrier", 33: "mlp2: unit mma", 34: "mlp2: reduced + finalised", 35: "mlp2: barrier",
          50: "att: enter", 51: "att: prologue loads/stores", 52: "att: bias row landed", 53: "att: barrier", 54: "att: loop head", 55: "att: prev released", 56: "att: block landed",
          57: "att: block math", 58: "att: released", 59: "att: loop done", 60: "att: end barrier", 61: "att: merge + finish", 62: "att: proxy fence",
-         90: "gs: enter", 91: "gs: barrier 1", 92: "gs: red.release", 93: "gs: poll done", 94: "gs: barrier 2"}
+         90: "sync: enter", 91: "gs: barrier 1", 92: "gs: red.release", 93: "gs: poll done", 94: "sync: CTA barrier done"}
 
 
 def main():
