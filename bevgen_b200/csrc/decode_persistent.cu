@@ -585,13 +585,11 @@ __device__ __noinline__ void linear_phase(const DecodeParams& p, DpSmem& sm, uns
   load_inputs_tagged(p, sm, stats, nparts, lnorm, frag_src, u1 > u0 && w < KG, w, lane, rtag, ahi, alo, rsS, rsQ);
   DP_TR(sm, 13);
   if (u1 == u0) { row_stats_finish(p, sm, which, rsS, rsQ); return; }
-  // Only warp 0 touches the mbarriers (16 warps asking the same barrier serialise in the SM's sync unit: ~1500 cycles per wait in the
-  // trace of tools/decode_trace.py); the others learn through the CTA barrier.  The units were requested phases ago, so warp 0's
-  // waits for them normally return at once.
-  if (w == 0) {
-    const int nb0 = min(DP_MAXU, u1 - u0);
-    for (int k = 0; k < nb0; ++k) ring_wait_full(sm, seq + (unsigned)k);
-  }
+  // ONE warp asks each unit's mbarrier (16 warps asking the same barrier serialise in the SM's sync unit: ~1500 cycles per wait in the
+  // trace of tools/decode_trace.py), warp k the one of unit k of the batch; the others learn through the CTA barrier.  The units were
+  // requested phases ago, but even a wait that returns at once costs ~250 cycles: four in a row by warp 0 were ~1 K cycles in front of
+  // the first CTA barrier of every linear phase.
+  if (w < min(DP_MAXU, u1 - u0)) ring_wait_full(sm, seq + (unsigned)w);
   DP_TR(sm, 15);
   bar_consumers();                          // the first batch of units has landed; act[] (reduction scratch) is free: the previous phase's readers are behind this or an earlier CTA barrier
   DP_TR(sm, 16);
@@ -602,7 +600,7 @@ __device__ __noinline__ void linear_phase(const DecodeParams& p, DpSmem& sm, uns
     float c1v = c1f, c2v = c2f;
     if (ub != u0 && has && lnorm) { c1v = __ldg(c1 + row); c2v = __ldg(c2 + row); }
     if (ub != u0) {                          // a further batch (more than DP_MAXU units per CTA: small grids only)
-      if (w == 0) for (int k = 0; k < nb; ++k) ring_wait_full(sm, seq + (unsigned)k);
+      if (w < nb) ring_wait_full(sm, seq + (unsigned)w);
       bar_consumers();
     }
     if (w < KG) {
