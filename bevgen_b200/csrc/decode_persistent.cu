@@ -1359,6 +1359,7 @@ int launch_decode_persistent(DecodeParams p, float* ws, unsigned int* counters, 
   if (p.step_begin == p.step_end) return BEVGEN_OK;
   const int G = sm_count;
   if ((p.B * p.H + G - 1) / G > DP_MAXBH) return BEVGEN_ERR_ARG;
+  if (G < 4 || G < d / 8) return BEVGEN_ERR_ARG;      // MLP2: four K-quarter groups of CTAs, and CTA ru finishes row unit ru < d / 8
   for (int l = 0; l < 1; ++l)
     if (p.lay_ld > 0 && (p.lay_blk < 16 || (p.Lmax + p.lay_blk - 1) / p.lay_blk > DP_MAXLB)) return BEVGEN_ERR_ARG;
   p.vpad = (p.vocab + 7) / 8 * 8;
